@@ -1,0 +1,163 @@
+"""ctypes mirror of include/cair.h (struct layouts, status codes, weight packing).
+
+The structs are addressed by the reference's state_dict key names, so the
+same packing code serves device pointers (torch CUDA tensors -> libcair.so) and host pointers
+(numpy arrays -> the CPU oracle used by the tests).
+"""
+import ctypes as C
+
+CAIR_OK = 0
+ERR_NAMES = {-1: 'CAIR_ERR_BAD_ARG', -2: 'CAIR_ERR_BAD_SHAPE', -3: 'CAIR_ERR_UNSUPPORTED',
+             -4: 'CAIR_ERR_CUDA', -5: 'CAIR_ERR_WORKSPACE'}
+RNN_TYPES = {'LSTM': 0, 'GRU': 1}
+
+f32p = C.POINTER(C.c_float)
+i64p = C.POINTER(C.c_int64)
+i32p = C.POINTER(C.c_int32)
+
+
+class Linear(C.Structure):
+    _fields_ = [('w', f32p), ('b', f32p)]
+
+
+class LstmDir(C.Structure):
+    _fields_ = [('w_ih', f32p), ('w_hh', f32p), ('b_ih', f32p), ('b_hh', f32p)]
+
+
+class AttnMlp(C.Structure):
+    _fields_ = [('l0', Linear), ('l3', Linear)]
+
+
+class EsmWeights(C.Structure):
+    _fields_ = [('vocab', C.c_int32), ('emsize', C.c_int32), ('table', f32p)]
+
+
+class MtWeights(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in
+                ('vocab', 'emsize', 'featsize', 'nhid_query', 'nhid_doc', 'nchannels', 'nfilters',
+                 'match_filter_size', 'rnn_type', 'bidirectional')] + [
+        ('table', f32p), ('linear_projection', Linear),
+        ('query_fwd', LstmDir), ('query_rev', LstmDir), ('doc_fwd', LstmDir), ('doc_rev', LstmDir),
+        ('query_projection', Linear), ('document_projection', Linear), ('alpha', f32p),
+        ('conv1', Linear), ('conv2', Linear), ('conv3', Linear), ('conv', Linear), ('output', Linear)]
+
+
+class DrmmWeights(C.Structure):
+    _fields_ = [('vocab', C.c_int32), ('emsize', C.c_int32), ('nbins', C.c_int32), ('table', f32p),
+                ('gating', Linear), ('ffnn0', Linear), ('ffnn1', Linear), ('output', Linear)]
+
+
+class DuetWeights(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in
+                ('vocab', 'emsize', 'nfilters', 'local_filter_size', 'dist_filter_size', 'pool_size',
+                 'max_query_len', 'max_doc_len')] + [('table', f32p)] + [
+        (k, Linear) for k in ('local_conv1d', 'local_fc1', 'local_fc2', 'local_fc3', 'conv_q',
+                              'conv_d1', 'conv_d2', 'dist_fc1', 'dist_fc2', 'dist_fc3', 'dist_fc4')]
+
+
+class CarsWeights(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in
+                ('vocab', 'emsize', 'nhid_query', 'nhid_document', 'nhid_session_query',
+                 'nhid_session_document')] + [
+        ('rank_dims', C.c_int32 * 3), ('rank_pool', C.c_int32), ('table', f32p),
+        ('query_fwd', LstmDir), ('query_rev', LstmDir), ('doc_fwd', LstmDir), ('doc_rev', LstmDir),
+        ('q_attn', AttnMlp), ('d_attn', AttnMlp), ('click_attn', AttnMlp),
+        ('session_query_inner_attn', AttnMlp), ('session_doc_inner_attn', AttnMlp),
+        ('session_query', LstmDir), ('session_doc', LstmDir),
+        ('session_query_attn', Linear), ('session_doc_attn', Linear),
+        ('shared_session_projector', Linear), ('private_session_projector1', Linear),
+        ('q_projection', Linear), ('ranknet', Linear * 3)]
+
+
+TABLE_KEY = 'word_embeddings.make_embedding.emb_luts.0.weight'
+
+
+def _lin(get, name, bias=True):
+    return Linear(get(name + '.weight'), get(name + '.bias') if bias else None)
+
+
+def _lstm(get, prefix, suffix=''):
+    return LstmDir(get('%s.weight_ih_l0%s' % (prefix, suffix)), get('%s.weight_hh_l0%s' % (prefix, suffix)),
+                   get('%s.bias_ih_l0%s' % (prefix, suffix)), get('%s.bias_hh_l0%s' % (prefix, suffix)))
+
+
+def _attn(get, name):
+    return AttnMlp(_lin(get, name + '.0'), _lin(get, name + '.3'))
+
+
+def pack_esm(cfg, get):
+    return EsmWeights(cfg['src_vocab_size'], cfg['emsize'], get(TABLE_KEY))
+
+
+def pack_mt(cfg, get):
+    """cfg: the reference Namespace fields (rankers/mtensor.py:27-60); get(key) -> float*."""
+    bi = bool(cfg['bidirection'])
+    w = MtWeights(cfg['src_vocab_size'], cfg['emsize'], cfg['featsize'], cfg['nhid_query'],
+                  cfg['nhid_doc'], cfg['nchannels'], cfg['nfilters'], cfg['match_filter_size'],
+                  RNN_TYPES[cfg['rnn_type']], int(bi))
+    w.table = get(TABLE_KEY)
+    w.linear_projection = _lin(get, 'linear_projection')
+    w.query_fwd = _lstm(get, 'query_encoder.rnns.0')
+    w.doc_fwd = _lstm(get, 'document_encoder.rnns.0')
+    if bi:
+        w.query_rev = _lstm(get, 'query_encoder.rnns.0', '_reverse')
+        w.doc_rev = _lstm(get, 'document_encoder.rnns.0', '_reverse')
+    w.query_projection = _lin(get, 'query_projection')
+    w.document_projection = _lin(get, 'document_projection')
+    w.alpha = get('exact_match_channel.alpha')
+    for k in ('conv1', 'conv2', 'conv3', 'conv', 'output'):
+        setattr(w, k, _lin(get, k))
+    return w
+
+
+def pack_drmm(cfg, get):
+    w = DrmmWeights(cfg['src_vocab_size'], cfg['emsize'], cfg['nbins'], get(TABLE_KEY))
+    w.gating = _lin(get, 'gating_network.weight')
+    w.ffnn0 = _lin(get, 'ffnn.0')
+    w.ffnn1 = _lin(get, 'ffnn.1')
+    w.output = _lin(get, 'output')
+    return w
+
+
+def pack_duet(cfg, get):
+    w = DuetWeights(cfg['src_vocab_size'], cfg['emsize'], cfg['nfilters'], cfg['local_filter_size'],
+                    cfg['dist_filter_size'], cfg['pool_size'], cfg['max_query_len'], cfg['max_doc_len'],
+                    get(TABLE_KEY))
+    w.local_conv1d = _lin(get, 'local_model.conv1d')
+    w.local_fc1 = _lin(get, 'local_model.fc1')
+    w.local_fc2 = _lin(get, 'local_model.fc2')
+    w.local_fc3 = _lin(get, 'local_model.fc3')
+    for k in ('conv_q', 'conv_d1', 'conv_d2'):
+        setattr(w, k, _lin(get, 'distributed_model.' + k))
+    for i in (1, 2, 3, 4):
+        setattr(w, 'dist_fc%d' % i, _lin(get, 'distributed_model.fc%d' % i))
+    return w
+
+
+def pack_cars(cfg, get):
+    """Stock CARS ranking path (multitask/cars.py:28-131): LSTM, bidirectional, 1 layer, attn pooling."""
+    w = CarsWeights(cfg['src_vocab_size'], cfg['emsize'], cfg['nhid_query'], cfg['nhid_document'],
+                    cfg['nhid_session_query'], cfg['nhid_session_document'])
+    w.rank_dims = (C.c_int32 * 3)(256, 128, 1)
+    w.rank_pool = 2
+    w.table = get('embedder.' + TABLE_KEY)
+    w.query_fwd = _lstm(get, 'query_encoder.encoder.rnns.0')
+    w.query_rev = _lstm(get, 'query_encoder.encoder.rnns.0', '_reverse')
+    w.doc_fwd = _lstm(get, 'document_encoder.encoder.rnns.0')
+    w.doc_rev = _lstm(get, 'document_encoder.encoder.rnns.0', '_reverse')
+    for k in ('q_attn', 'd_attn', 'click_attn', 'session_query_inner_attn', 'session_doc_inner_attn'):
+        setattr(w, k, _attn(get, k))
+    w.session_query = _lstm(get, 'session_query_encoder.encoder.rnns.0')
+    w.session_doc = _lstm(get, 'session_doc_encoder.encoder.rnns.0')
+    w.session_query_attn = _lin(get, 'session_query_attn')
+    w.session_doc_attn = _lin(get, 'session_doc_attn')
+    w.shared_session_projector = _lin(get, 'shared_session_projector.linear', bias=False)
+    w.private_session_projector1 = _lin(get, 'private_session_projector1.linear', bias=False)
+    w.q_projection = _lin(get, 'q_projection.linear')
+    for i in range(3):
+        w.ranknet[i] = _lin(get, 'ranknet._linear_layers.%d' % i)
+    return w
+
+
+PACKERS = {'esm': pack_esm, 'match_tensor': pack_mt, 'drmm': pack_drmm, 'duet': pack_duet,
+           'cars': pack_cars}

@@ -1,0 +1,214 @@
+/*
+ * cair.h - C ABI of libcair.so: the B200-native (sm_100a) scoring hot path of
+ * wasiahmad/context_attentive_ir.
+ *
+ * The reference has no FFI boundary: its "plugin API" is the Python
+ * call  network(queries, que_len, documents, doc_len) -> FloatTensor[B,N]
+ * (neuroir/models/ranker.py:213,257; neuroir/models/multitask.py:264-269).  Every
+ * cair_<model>_forward below is what a binding for that call would bind; the reference
+ * forward it replaces is cited next to it.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no C++/torch types, no exceptions.
+ *  - every function returns an int32 status (CAIR_OK == 0, < 0 error class); the text of
+ *    the last error of the calling thread is cair_last_error().
+ *  - ids/lengths are int64, PAD=0 (neuroir/inputters/constants.py:1-4,
+ *    neuroir/inputters/ranker/vector.py:53-69); scores are fp32; row-major, contiguous.
+ *  - *_forward: all pointers are DEVICE pointers owned by the caller; the call enqueues
+ *    kernels on `stream` (a cudaStream_t passed as void*), never synchronises and never
+ *    allocates: scratch comes from the caller-provided workspace
+ *    (size from cair_<model>_workspace_bytes).
+ *  - *_forward_host: all pointers are HOST pointers (pinned memory recommended); the call
+ *    copies ids/lengths host->device, runs the same kernels, copies the scores back and
+ *    synchronises `stream` before returning.  Staging buffers live in the handle.
+ *  - weights structs hold DEVICE pointers in the torch state_dict layouts (SURVEY.md
+ *    App. D); cair_<model>_create repacks/converts them once into the handle; the caller
+ *    may free or modify its tensors afterwards (call create again to pick up new values).
+ *  - a handle is bound to one device; calls on one handle are serialised by the caller;
+ *    distinct handles may be used concurrently from different threads.
+ *
+ * The same weight structs (with HOST pointers) are consumed by the CPU oracle in
+ * oracle/cair_oracle.c, which is test infrastructure and not part of this library.
+ */
+#ifndef CAIR_H_
+#define CAIR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAIR_VERSION 100 /* 0.1.0 */
+
+enum {
+  CAIR_OK = 0,
+  CAIR_ERR_BAD_ARG = -1,     /* null pointer, negative size                              */
+  CAIR_ERR_BAD_SHAPE = -2,   /* shape the reference would assert on (e.g. mtensor.py:71) */
+  CAIR_ERR_UNSUPPORTED = -3, /* configuration outside what the kernels implement         */
+  CAIR_ERR_CUDA = -4,        /* CUDA runtime error, text in cair_last_error()            */
+  CAIR_ERR_WORKSPACE = -5    /* workspace too small / misaligned                         */
+};
+
+enum { CAIR_RNN_LSTM = 0, CAIR_RNN_GRU = 1 };
+
+typedef struct cair_handle cair_handle; /* opaque */
+
+int32_t cair_version(void);
+const char* cair_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+int64_t cair_launch_count(void);
+int32_t cair_destroy(cair_handle* h);
+
+/* ---- shared weight fragments ------------------------------------------------------------- */
+
+/* nn.Linear: w [out,in], b [out] or NULL (bias=False). */
+typedef struct {
+  const float* w;
+  const float* b;
+} cair_linear;
+
+/* One direction of one nn.LSTM layer, torch layout, gate row order i,f,g,o
+ * (neuroir/encoders/rnn_encoder.py:45-53 -> torch.nn.LSTM): w_ih [4h,in], w_hh [4h,h], b_* [4h]. */
+typedef struct {
+  const float* w_ih;
+  const float* w_hh;
+  const float* b_ih;
+  const float* b_hh;
+} cair_lstm_dir;
+
+/* nn.Sequential(Linear(H,H), Tanh, Dropout, Linear(H,1)) - state_dict keys "<name>.0.*", "<name>.3.*"
+ * (neuroir/multitask/cars.py:41-46). */
+typedef struct {
+  cair_linear l0;
+  cair_linear l3;
+} cair_attn_mlp;
+
+/* ---- kernel-level entry points (unit tests, reuse) --------------------------------------- */
+
+/* out[t,:] = table[ids[t],:]   (neuroir/modules/embeddings.py:243-252 + util_class.py:42-53).
+ * ids [T] int64, table [V,E] fp32, out [T,E] fp32. */
+int32_t cair_embed_gather(const float* table, int32_t V, int32_t E, const int64_t* ids, int64_t T,
+                          float* out, void* stream);
+
+/* RNNEncoder.forward with lengths (neuroir/encoders/rnn_encoder.py:62-141), one layer LSTM:
+ * x [n,L,in], len [n] int64 -> out [n,L,dirs*h], zeros at t >= len; reverse direction starts at
+ * each sequence's own last token.  rev may be NULL (unidirectional).
+ * h_n/c_n [dirs,n,h] optional (NULL to skip). */
+int32_t cair_lstm_forward(const float* x, const int64_t* len, int32_t n, int32_t L, int32_t in,
+                          int32_t h, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, float* out,
+                          float* h_n, float* c_n, void* stream);
+
+/* ---- ESM (neuroir/rankers/esm.py:19-45) --------------------------------------------------- */
+typedef struct {
+  int32_t vocab, emsize;
+  const float* table; /* word_embeddings.make_embedding.emb_luts.0.weight [V,E] */
+} cair_esm_weights;
+
+int32_t cair_esm_create(const cair_esm_weights* w, int32_t device, cair_handle** out);
+
+/* ---- Match-Tensor (neuroir/rankers/mtensor.py:27-60 ctor, :62-131 forward, :134-158 exact match) */
+typedef struct {
+  int32_t vocab, emsize, featsize, nhid_query, nhid_doc, nchannels, nfilters, match_filter_size;
+  int32_t rnn_type, bidirectional;
+  const float* table;              /* [V,E] */
+  cair_linear linear_projection;   /* [F,E] */
+  cair_lstm_dir query_fwd, query_rev, doc_fwd, doc_rev; /* {query,document}_encoder.rnns.0.* */
+  cair_linear query_projection;    /* [C,Hq] */
+  cair_linear document_projection; /* [C,Hd] */
+  const float* alpha;              /* exact_match_channel.alpha [1] */
+  cair_linear conv1, conv2, conv3; /* w [nf,C+1,3,{3,5,7}], b [nf] */
+  cair_linear conv;                /* w [mfs,3nf,1,1], b [mfs] */
+  cair_linear output;              /* w [1,mfs], b [1] */
+} cair_mt_weights;
+
+int32_t cair_mt_create(const cair_mt_weights* w, int32_t device, cair_handle** out);
+/* Stage outputs for parity tests (any may be NULL): encoder memory banks
+ * enc_q [B,Lq,Hq], enc_d [B*N,Ld,Hd] as RNNEncoder returns them (mtensor.py:93-94). */
+int32_t cair_mt_set_debug(cair_handle* h, float* enc_q, float* enc_d);
+
+/* ---- DRMM (neuroir/rankers/drmm.py:13-27 ctor, :29-84 forward, :87-98 gating) -------------- */
+typedef struct {
+  int32_t vocab, emsize, nbins; /* nbins must be 5 (neuroir/hyparam.py:78-81) */
+  const float* table;
+  cair_linear gating; /* gating_network.weight [1,E] */
+  cair_linear ffnn0;  /* ffnn.0 [1,5] */
+  cair_linear ffnn1;  /* ffnn.1 [1,1] */
+  cair_linear output; /* output [1,1] */
+} cair_drmm_weights;
+
+int32_t cair_drmm_create(const cair_drmm_weights* w, int32_t device, cair_handle** out);
+/* Optional parity output: hist [B*N,Lq,5] int32 (numpy.histogram counts, drmm.py:71-75). */
+int32_t cair_drmm_set_debug(cair_handle* h, int32_t* hist);
+
+/* ---- DUET (neuroir/rankers/duet.py:28-59, LocalModel :65-121, DistributedModel :127-208) --- */
+typedef struct {
+  int32_t vocab, emsize, nfilters, local_filter_size, dist_filter_size, pool_size;
+  int32_t max_query_len, max_doc_len;
+  const float* table;
+  cair_linear local_conv1d; /* [nf,Ld,1] */
+  cair_linear local_fc1;    /* [1,Lq]    */
+  cair_linear local_fc2;    /* [nf,nf]   */
+  cair_linear local_fc3;    /* [1,nf]    */
+  cair_linear conv_q;       /* [nf,E,3]  */
+  cair_linear conv_d1;      /* [nf,E,3]  */
+  cair_linear conv_d2;      /* [nf,nf,1] */
+  cair_linear dist_fc1;     /* [nf,nf]   */
+  cair_linear dist_fc2;     /* [1,Ld-pool-1] */
+  cair_linear dist_fc3;     /* [nf,nf]   */
+  cair_linear dist_fc4;     /* [1,nf]    */
+} cair_duet_weights;
+
+int32_t cair_duet_create(const cair_duet_weights* w, int32_t device, cair_handle** out);
+
+/* ---- forward for the four stand-alone rankers ---------------------------------------------
+ * network(queries, que_len, documents, doc_len) (neuroir/models/ranker.py:213,257):
+ * q [B,Lq], qlen [B], d [B,N,Ld], dlen [B,N] int64 -> scores [B,N] fp32 (no softmax).
+ * pair_begin/pair_count select the contiguous slice of the flattened pairs p=b*N+n this rank
+ * scores (doc-parallel sharding); scores is still indexed [B,N] and only
+ * the slice is written.  Use 0, B*N for everything. */
+int32_t cair_ranker_workspace_bytes(cair_handle* h, int32_t B, int32_t N, int32_t Lq, int32_t Ld,
+                                    size_t* bytes);
+int32_t cair_ranker_forward(cair_handle* h, const int64_t* q, const int64_t* qlen, const int64_t* d,
+                            const int64_t* dlen, int32_t B, int32_t N, int32_t Lq, int32_t Ld,
+                            int64_t pair_begin, int64_t pair_count, float* scores, void* workspace,
+                            size_t workspace_bytes, void* stream);
+int32_t cair_ranker_forward_host(cair_handle* h, const int64_t* q, const int64_t* qlen,
+                                 const int64_t* d, const int64_t* dlen, int32_t B, int32_t N,
+                                 int32_t Lq, int32_t Ld, float* scores, void* stream);
+
+/* ---- CARS ranking path (neuroir/multitask/cars.py:193-304 encode*, :306-458 encode_session,
+ *      :460-540 rank/rank_document, :671-691 apply_pooling; neuroir/modules/maxout.py:70-84) --- */
+typedef struct {
+  int32_t vocab, emsize, nhid_query, nhid_document, nhid_session_query, nhid_session_document;
+  int32_t rank_dims[3];  /* Maxout output_dims, reference fixes [256,128,1] (cars.py:128-131) */
+  int32_t rank_pool;     /* 2 */
+  const float* table;    /* embedder.word_embeddings.make_embedding.emb_luts.0.weight */
+  cair_lstm_dir query_fwd, query_rev, doc_fwd, doc_rev; /* {query,document}_encoder.encoder.rnns.0.* */
+  cair_attn_mlp q_attn, d_attn, click_attn;
+  cair_attn_mlp session_query_inner_attn, session_doc_inner_attn;
+  cair_lstm_dir session_query, session_doc; /* session_{query,doc}_encoder.encoder.rnns.0.* */
+  cair_linear session_query_attn, session_doc_attn;         /* [Hq,Hsq], [Hd,Hsd] */
+  cair_linear shared_session_projector, private_session_projector1; /* [Hd,Hsq+Hsd], no bias */
+  cair_linear q_projection;                                 /* [Hd,Hq] */
+  cair_linear ranknet[3];                                   /* ranknet._linear_layers.{0,1,2} */
+} cair_cars_weights;
+
+int32_t cair_cars_create(const cair_cars_weights* w, int32_t device, cair_handle** out);
+int32_t cair_cars_workspace_bytes(cair_handle* h, int32_t B, int32_t S, int32_t N, int32_t Lq,
+                                  int32_t Ld, size_t* bytes);
+/* encode + rank_document (multitask.py:264-269):
+ * q [B,S,Lq], qlen [B,S], d [B,S,N,Ld], dlen [B,S,N] int64, labels [B,S,N] fp32
+ * -> scores [B,S,N]; optional outputs (NULL to skip): pooled_q [B,S,Hq], pooled_d [B,S,N,Hd],
+ * clicks [B,S,Hd], sess_q_attn [B,S,Hsq], sess_d_attn [B,S,Hsd]. */
+int32_t cair_cars_forward(cair_handle* h, const int64_t* q, const int64_t* qlen, const int64_t* d,
+                          const int64_t* dlen, const float* labels, int32_t B, int32_t S, int32_t N,
+                          int32_t Lq, int32_t Ld, float* scores, float* pooled_q, float* pooled_d,
+                          float* clicks, float* sess_q_attn, float* sess_d_attn, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAIR_H_ */

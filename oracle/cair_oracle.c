@@ -1,0 +1,669 @@
+/*
+ * cair_oracle.c - TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain-C CPU restatement of the reference's scoring forward passes (eval mode), used only
+ * by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs as
+ * the checker for the CUDA library.  Nothing under context_attentive_ir_b200/ may link,
+ * import or call it.
+ *
+ * Pinned against the UNMODIFIED reference: the tests/golden npz files hold inputs, state_dicts and
+ * outputs produced by importing the reference's own modules from /root/reference
+ * (oracle/gen_golden.py); tests/test_oracle_golden.py checks every function below against
+ * them.  The reference itself ships no golden vectors or tests; the
+ * arithmetic lives in torch 2.11 (ATen CPU) and numpy 2.3 - not vendored, no lockfile - so
+ * operator semantics (nn.LSTM gate order, Conv2d cross-correlation, cosine_similarity
+ * eps clamp, numpy.histogram bin rule) are restated from their documentation and pinned
+ * operationally by those fixtures.
+ *
+ * Weight structs are the ones of include/cair.h but with HOST pointers.
+ * Dot products accumulate in double and round to float once; everything else is fp32.
+ * Pairs / sequences are processed in parallel with OpenMP when compiled with -fopenmp.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/cair.h"
+
+#define ORA_API __attribute__((visibility("default")))
+
+static float dotf(const float* a, const float* b, int n) {
+  double s = 0.0;
+  for (int k = 0; k < n; ++k) s += (double)a[k] * (double)b[k];
+  return (float)s;
+}
+
+static float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+/* modules/embeddings.py:243-252 + util_class.py:42-53: out[t,:] = table[ids[t],:] */
+ORA_API int cair_oracle_embed(const float* table, int V, int E, const int64_t* ids, int64_t T,
+                              float* out) {
+  for (int64_t t = 0; t < T; ++t) {
+    if (ids[t] < 0 || ids[t] >= V) return CAIR_ERR_BAD_ARG;
+    memcpy(out + t * E, table + ids[t] * (int64_t)E, sizeof(float) * E);
+  }
+  return CAIR_OK;
+}
+
+/* nn.Linear over rows: y[r,:] = x[r,:] W^T + b   (W [out,in]) */
+static void linear_rows(const float* x, int64_t rows, int in, const cair_linear* l, int out,
+                        float* y) {
+  for (int64_t r = 0; r < rows; ++r)
+    for (int o = 0; o < out; ++o)
+      y[r * out + o] = dotf(x + r * in, l->w + (int64_t)o * in, in) + (l->b ? l->b[o] : 0.0f);
+}
+
+/* One LSTM cell step, torch.nn.LSTM semantics (gate rows i,f,g,o; both biases added). */
+static void lstm_step(const float* x, int in, int h, const cair_lstm_dir* w, float* hs, float* cs,
+                      float* gates) {
+  for (int r = 0; r < 4 * h; ++r)
+    gates[r] = dotf(x, w->w_ih + (int64_t)r * in, in) + w->b_ih[r] +
+               dotf(hs, w->w_hh + (int64_t)r * h, h) + w->b_hh[r];
+  for (int u = 0; u < h; ++u) {
+    float ig = sigmoidf_(gates[u]), fg = sigmoidf_(gates[h + u]);
+    float gg = tanhf(gates[2 * h + u]);
+    cs[u] = fg * cs[u] + ig * gg;
+  }
+  for (int u = 0; u < h; ++u) hs[u] = sigmoidf_(gates[3 * h + u]) * tanhf(cs[u]);
+}
+
+/* RNNEncoder.forward with lengths (encoders/rnn_encoder.py:62-141), one LSTM layer.
+ * sort/pack/unpack/unsort is a per-sequence no-op: each sequence runs over its own
+ * len steps, the reverse direction starts at its own last token, outputs at t >= len are
+ * zero (the zero-pad of :135-139 and pad_packed_sequence). */
+ORA_API int cair_oracle_lstm(const float* x, const int64_t* len, int n, int L, int in, int h,
+                             const cair_lstm_dir* fwd, const cair_lstm_dir* rev, float* out,
+                             float* h_n, float* c_n) {
+  int dirs = rev ? 2 : 1;
+  for (int s = 0; s < n; ++s)
+    if (len[s] < 1 || len[s] > L) return CAIR_ERR_BAD_ARG;
+  memset(out, 0, sizeof(float) * (size_t)n * L * dirs * h);
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int s = 0; s < n; ++s) {
+    float* hs = (float*)malloc(sizeof(float) * h * 6);
+    float *cs = hs + h, *gates = hs + 2 * h;
+    int T = (int)len[s];
+    for (int dir = 0; dir < dirs; ++dir) {
+      const cair_lstm_dir* w = dir ? rev : fwd;
+      memset(hs, 0, sizeof(float) * 2 * h);
+      for (int k = 0; k < T; ++k) {
+        int t = dir ? T - 1 - k : k;
+        lstm_step(x + ((int64_t)s * L + t) * in, in, h, w, hs, cs, gates);
+        memcpy(out + ((int64_t)s * L + t) * dirs * h + dir * h, hs, sizeof(float) * h);
+      }
+      if (h_n) memcpy(h_n + ((int64_t)dir * n + s) * h, hs, sizeof(float) * h);
+      if (c_n) memcpy(c_n + ((int64_t)dir * n + s) * h, cs, sizeof(float) * h);
+    }
+    free(hs);
+  }
+  return CAIR_OK;
+}
+
+/* torch>=2 F.cosine_similarity: normalise each vector by max(||x||, eps) first, then dot. */
+static float cosine_norm_first(const float* a, const float* b, int n, float eps) {
+  float na = sqrtf(dotf(a, a, n)), nb = sqrtf(dotf(b, b, n));
+  if (na < eps) na = eps;
+  if (nb < eps) nb = eps;
+  double s = 0.0;
+  for (int k = 0; k < n; ++k) s += (double)(a[k] / na) * (double)(b[k] / nb);
+  return (float)s;
+}
+
+static int check_ids(const int64_t* ids, int64_t n, int V) {
+  for (int64_t i = 0; i < n; ++i)
+    if (ids[i] < 0 || ids[i] >= V) return 0;
+  return 1;
+}
+
+/* ---- ESM (rankers/esm.py:34-44): mean over the PADDED length, then cosine ---------------- */
+ORA_API int cair_oracle_esm(const cair_esm_weights* w, const int64_t* q, const int64_t* qlen,
+                            const int64_t* d, const int64_t* dlen, int B, int N, int Lq, int Ld,
+                            float* scores) {
+  (void)qlen;
+  (void)dlen;
+  int E = w->emsize;
+  if (!check_ids(q, (int64_t)B * Lq, w->vocab) || !check_ids(d, (int64_t)B * N * Ld, w->vocab))
+    return CAIR_ERR_BAD_ARG;
+#pragma omp parallel for
+  for (int b = 0; b < B; ++b) {
+    float* vq = (float*)calloc(2 * (size_t)E, sizeof(float));
+    float* vd = vq + E;
+    for (int t = 0; t < Lq; ++t)
+      for (int k = 0; k < E; ++k) vq[k] += w->table[q[b * Lq + t] * E + k];
+    for (int k = 0; k < E; ++k) vq[k] /= (float)Lq;
+    for (int n = 0; n < N; ++n) {
+      memset(vd, 0, sizeof(float) * E);
+      const int64_t* dd = d + ((int64_t)b * N + n) * Ld;
+      for (int t = 0; t < Ld; ++t)
+        for (int k = 0; k < E; ++k) vd[k] += w->table[dd[t] * E + k];
+      for (int k = 0; k < E; ++k) vd[k] /= (float)Ld;
+      scores[b * N + n] = cosine_norm_first(vq, vd, E, 1e-8f);
+    }
+    free(vq);
+  }
+  return CAIR_OK;
+}
+
+/* ---- Match-Tensor (rankers/mtensor.py:62-131; exact match :144-158) ----------------------- */
+ORA_API int cair_oracle_mt(const cair_mt_weights* w, const int64_t* q, const int64_t* qlen,
+                           const int64_t* d, const int64_t* dlen, int B, int N, int Lq, int Ld,
+                           float* scores, float* enc_q_out, float* enc_d_out) {
+  if (w->rnn_type != CAIR_RNN_LSTM) return CAIR_ERR_UNSUPPORTED;
+  int E = w->emsize, F = w->featsize, C = w->nchannels, nf = w->nfilters,
+      M = w->match_filter_size;
+  int dirs = w->bidirectional ? 2 : 1;
+  int Hq = w->nhid_query, Hd = w->nhid_doc, hq = Hq / dirs, hd = Hd / dirs;
+  int64_t BN = (int64_t)B * N;
+  if (!check_ids(q, (int64_t)B * Lq, w->vocab) || !check_ids(d, BN * Ld, w->vocab))
+    return CAIR_ERR_BAD_ARG;
+  /* :77-90 embedding + linear projection (pads project to the bias) */
+  float* eq = (float*)malloc(sizeof(float) * B * Lq * E);
+  float* ed = (float*)malloc(sizeof(float) * BN * Ld * E);
+  cair_oracle_embed(w->table, w->vocab, E, q, (int64_t)B * Lq, eq);
+  cair_oracle_embed(w->table, w->vocab, E, d, BN * Ld, ed);
+  float* pq = (float*)malloc(sizeof(float) * B * Lq * F);
+  float* pd = (float*)malloc(sizeof(float) * BN * Ld * F);
+  linear_rows(eq, (int64_t)B * Lq, E, &w->linear_projection, F, pq);
+  linear_rows(ed, BN * Ld, E, &w->linear_projection, F, pd);
+  free(eq);
+  free(ed);
+  /* :93-94 separate query / document encoders */
+  float* hq_ = (float*)malloc(sizeof(float) * B * Lq * Hq);
+  float* hd_ = (float*)malloc(sizeof(float) * BN * Ld * Hd);
+  int rc = cair_oracle_lstm(pq, qlen, B, Lq, F, hq, &w->query_fwd,
+                            dirs == 2 ? &w->query_rev : NULL, hq_, NULL, NULL);
+  if (rc == CAIR_OK)
+    rc = cair_oracle_lstm(pd, dlen, (int)BN, Ld, F, hd, &w->doc_fwd,
+                          dirs == 2 ? &w->doc_rev : NULL, hd_, NULL, NULL);
+  free(pq);
+  free(pd);
+  if (rc != CAIR_OK) {
+    free(hq_);
+    free(hd_);
+    return rc;
+  }
+  if (enc_q_out) memcpy(enc_q_out, hq_, sizeof(float) * B * Lq * Hq);
+  if (enc_d_out) memcpy(enc_d_out, hd_, sizeof(float) * BN * Ld * Hd);
+  /* :99,108 channel projections (bias also at pad positions) */
+  float* cq = (float*)malloc(sizeof(float) * B * Lq * C);
+  float* cd = (float*)malloc(sizeof(float) * BN * Ld * C);
+  linear_rows(hq_, (int64_t)B * Lq, Hq, &w->query_projection, C, cq);
+  linear_rows(hd_, BN * Ld, Hd, &w->document_projection, C, cd);
+  free(hq_);
+  free(hd_);
+  const float alpha = w->alpha[0];
+  const cair_linear* convs[3] = {&w->conv1, &w->conv2, &w->conv3};
+  const int C1 = C + 1;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t p = 0; p < BN; ++p) {
+    int b = (int)(p / N);
+    /* :100-119 match tensor [C+1, Lq, Ld] */
+    float* mt = (float*)malloc(sizeof(float) * (size_t)C1 * Lq * Ld);
+    float* y = (float*)malloc(sizeof(float) * (size_t)3 * nf * Lq * Ld);
+    for (int c = 0; c < C; ++c)
+      for (int i = 0; i < Lq; ++i)
+        for (int j = 0; j < Ld; ++j)
+          mt[((size_t)c * Lq + i) * Ld + j] = cq[((size_t)b * Lq + i) * C + c] * cd[(p * Ld + j) * C + c];
+    for (int i = 0; i < Lq; ++i)
+      for (int j = 0; j < Ld; ++j)
+        mt[((size_t)C * Lq + i) * Ld + j] = (q[b * Lq + i] == d[p * Ld + j]) ? alpha : 0.0f;
+    /* :122-125 three same-padded convs (cross-correlation) + ReLU */
+    for (int k = 0; k < 3; ++k) {
+      int kw = 3 + 2 * k, pw = 1 + k;
+      for (int f = 0; f < nf; ++f)
+        for (int i = 0; i < Lq; ++i)
+          for (int j = 0; j < Ld; ++j) {
+            double s = convs[k]->b[f];
+            for (int c = 0; c < C1; ++c)
+              for (int a = 0; a < 3; ++a) {
+                int ii = i + a - 1;
+                if (ii < 0 || ii >= Lq) continue;
+                for (int bb = 0; bb < kw; ++bb) {
+                  int jj = j + bb - pw;
+                  if (jj < 0 || jj >= Ld) continue;
+                  s += (double)convs[k]->w[(((size_t)f * C1 + c) * 3 + a) * kw + bb] *
+                       (double)mt[((size_t)c * Lq + i + a - 1) * Ld + jj];
+                }
+              }
+            float v = (float)s;
+            y[((size_t)(k * nf + f) * Lq + i) * Ld + j] = v > 0.0f ? v : 0.0f;
+          }
+    }
+    /* :126-130 1x1 conv (no activation), max over Ld then Lq (pads included), Linear(M,1) */
+    double sc = w->output.b[0];
+    for (int m = 0; m < M; ++m) {
+      float best = -INFINITY;
+      for (int i = 0; i < Lq; ++i)
+        for (int j = 0; j < Ld; ++j) {
+          double s = w->conv.b[m];
+          for (int f = 0; f < 3 * nf; ++f)
+            s += (double)w->conv.w[m * 3 * nf + f] * (double)y[((size_t)f * Lq + i) * Ld + j];
+          if ((float)s > best) best = (float)s;
+        }
+      sc += (double)w->output.w[m] * (double)best;
+    }
+    scores[p] = (float)sc;
+    free(mt);
+    free(y);
+  }
+  free(cq);
+  free(cd);
+  return CAIR_OK;
+}
+
+/* ---- DRMM (rankers/drmm.py:29-84, gating :87-98) ------------------------------------------
+ * numpy.histogram(x, bins=[-1,-.5,0,.5,1,1]): half-open bins [e_k, e_k+1), last bin closed,
+ * values outside [-1, 1] dropped.  With the duplicated last edge: bin 3 = [.5, 1), bin 4 = {1}. */
+static int drmm_bin(float c) {
+  if (!(c >= -1.0f) || c > 1.0f) return -1;
+  if (c == 1.0f) return 4;
+  if (c < -0.5f) return 0;
+  if (c < 0.0f) return 1;
+  if (c < 0.5f) return 2;
+  return 3;
+}
+
+ORA_API int cair_oracle_drmm(const cair_drmm_weights* w, const int64_t* q, const int64_t* qlen,
+                             const int64_t* d, const int64_t* dlen, int B, int N, int Lq, int Ld,
+                             float* scores, int32_t* hist_out, float* cos_out) {
+  (void)qlen;
+  (void)dlen;
+  if (w->nbins != 5) return CAIR_ERR_UNSUPPORTED;
+  int E = w->emsize;
+  int64_t BN = (int64_t)B * N;
+  if (!check_ids(q, (int64_t)B * Lq, w->vocab) || !check_ids(d, BN * Ld, w->vocab))
+    return CAIR_ERR_BAD_ARG;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t p = 0; p < BN; ++p) {
+    int b = (int)(p / N);
+    /* :45-51 gating softmax over ALL Lq positions (pads included) */
+    float* g = (float*)malloc(sizeof(float) * Lq);
+    float mx = -INFINITY, den = 0.0f;
+    for (int i = 0; i < Lq; ++i) {
+      g[i] = dotf(w->table + q[b * Lq + i] * E, w->gating.w, E) + w->gating.b[0];
+      if (g[i] > mx) mx = g[i];
+    }
+    for (int i = 0; i < Lq; ++i) {
+      g[i] = expf(g[i] - mx);
+      den += g[i];
+    }
+    double acc = 0.0;
+    for (int i = 0; i < Lq; ++i) {
+      int32_t h5[5] = {0, 0, 0, 0, 0};
+      const float* xq = w->table + q[b * Lq + i] * E;
+      for (int j = 0; j < Ld; ++j) {
+        float c = cosine_norm_first(xq, w->table + d[p * Ld + j] * E, E, 1e-8f);
+        if (cos_out) cos_out[(p * Lq + i) * Ld + j] = c;
+        int k = drmm_bin(c);
+        if (k >= 0) h5[k]++;
+      }
+      if (hist_out) memcpy(hist_out + (p * Lq + i) * 5, h5, sizeof(h5));
+      /* :26,80 ffnn = Linear(5,1) then Linear(1,1), no non-linearity */
+      float f0 = w->ffnn0.b[0];
+      for (int k = 0; k < 5; ++k) f0 += w->ffnn0.w[k] * (float)h5[k];
+      float f1 = w->ffnn1.w[0] * f0 + w->ffnn1.b[0];
+      acc += (double)f1 * (double)(g[i] / den);
+    }
+    scores[p] = w->output.w[0] * (float)acc + w->output.b[0];
+    free(g);
+  }
+  return CAIR_OK;
+}
+
+/* ---- DUET (rankers/duet.py:77-121 local, :148-208 distributed, :58 sum) -------------------- */
+ORA_API int cair_oracle_duet(const cair_duet_weights* w, const int64_t* q, const int64_t* qlen,
+                             const int64_t* d, const int64_t* dlen, int B, int N, int Lq, int Ld,
+                             float* scores, float* local_out) {
+  (void)qlen;
+  (void)dlen;
+  int E = w->emsize, nf = w->nfilters, ks = w->dist_filter_size, pool = w->pool_size;
+  /* shape algebra the reference asserts through its layer sizes (duet.py:69,73,144) */
+  if (Lq != w->max_query_len || Ld != w->max_doc_len || w->local_filter_size != 1 || ks != 3)
+    return CAIR_ERR_BAD_SHAPE;
+  int64_t BN = (int64_t)B * N;
+  if (!check_ids(q, (int64_t)B * Lq, w->vocab) || !check_ids(d, BN * Ld, w->vocab))
+    return CAIR_ERR_BAD_ARG;
+  int Tq = Lq - ks + 1, Td = Ld - ks + 1, Tp = Td - pool + 1; /* Tp == Ld - pool - 1 */
+  /* query side: conv_q -> tanh -> global max -> fc1 -> tanh */
+  float* rq = (float*)malloc(sizeof(float) * B * nf);
+  for (int b = 0; b < B; ++b) {
+    float* mq = (float*)malloc(sizeof(float) * nf);
+    for (int f = 0; f < nf; ++f) {
+      float best = -INFINITY;
+      for (int t = 0; t < Tq; ++t) {
+        double s = w->conv_q.b[f];
+        for (int k = 0; k < ks; ++k) {
+          const float* x = w->table + q[b * Lq + t + k] * E;
+          for (int e = 0; e < E; ++e) s += (double)w->conv_q.w[((size_t)f * E + e) * ks + k] * x[e];
+        }
+        float v = tanhf((float)s);
+        if (v > best) best = v;
+      }
+      mq[f] = best;
+    }
+    for (int f = 0; f < nf; ++f)
+      rq[b * nf + f] = tanhf(dotf(mq, w->dist_fc1.w + (size_t)f * nf, nf) + w->dist_fc1.b[f]);
+    free(mq);
+  }
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t p = 0; p < BN; ++p) {
+    int b = (int)(p / N);
+    const int64_t* dd = d + p * Ld;
+    /* local model: X[j,i] = (d_j == q_i); conv1d(Ld -> nf, k=1) over length Lq */
+    float* m1 = (float*)malloc(sizeof(float) * nf * 2);
+    float* m2 = m1 + nf;
+    for (int f = 0; f < nf; ++f) {
+      double s1 = w->local_fc1.b[0];
+      for (int i = 0; i < Lq; ++i) {
+        double s = w->local_conv1d.b[f];
+        for (int j = 0; j < Ld; ++j)
+          if (dd[j] == q[b * Lq + i]) s += w->local_conv1d.w[(size_t)f * Ld + j];
+        s1 += (double)w->local_fc1.w[i] * (double)tanhf((float)s);
+      }
+      m1[f] = tanhf((float)s1);
+    }
+    for (int f = 0; f < nf; ++f)
+      m2[f] = tanhf(dotf(m1, w->local_fc2.w + (size_t)f * nf, nf) + w->local_fc2.b[f]);
+    float local = tanhf(dotf(m2, w->local_fc3.w, nf) + w->local_fc3.b[0]);
+    if (local_out) local_out[p] = local;
+    /* distributed model */
+    float* cd = (float*)malloc(sizeof(float) * (size_t)nf * Td);
+    float* pl = (float*)malloc(sizeof(float) * (size_t)nf * Tp);
+    for (int f = 0; f < nf; ++f)
+      for (int t = 0; t < Td; ++t) {
+        double s = w->conv_d1.b[f];
+        for (int k = 0; k < ks; ++k) {
+          const float* x = w->table + dd[t + k] * E;
+          for (int e = 0; e < E; ++e) s += (double)w->conv_d1.w[((size_t)f * E + e) * ks + k] * x[e];
+        }
+        cd[(size_t)f * Td + t] = tanhf((float)s);
+      }
+    for (int f = 0; f < nf; ++f)
+      for (int t = 0; t < Tp; ++t) {
+        float best = cd[(size_t)f * Td + t];
+        for (int k = 1; k < pool; ++k)
+          if (cd[(size_t)f * Td + t + k] > best) best = cd[(size_t)f * Td + t + k];
+        pl[(size_t)f * Tp + t] = best;
+      }
+    for (int f = 0; f < nf; ++f) {
+      double s2 = w->dist_fc2.b[0];
+      for (int t = 0; t < Tp; ++t) {
+        double s = w->conv_d2.b[f];
+        for (int g = 0; g < nf; ++g) s += (double)w->conv_d2.w[(size_t)f * nf + g] * pl[(size_t)g * Tp + t];
+        float rd = tanhf((float)s);
+        s2 += (double)w->dist_fc2.w[t] * (double)(rq[b * nf + f] * rd);
+      }
+      m1[f] = tanhf((float)s2);
+    }
+    for (int f = 0; f < nf; ++f)
+      m2[f] = tanhf(dotf(m1, w->dist_fc3.w + (size_t)f * nf, nf) + w->dist_fc3.b[f]);
+    float dist = tanhf(dotf(m2, w->dist_fc4.w, nf) + w->dist_fc4.b[0]);
+    scores[p] = local + dist;
+    free(m1);
+    free(cd);
+    free(pl);
+  }
+  free(rq);
+  return CAIR_OK;
+}
+
+/* ---- CARS ranking path ------------------------------------------------------------------- */
+/* apply_pooling 'attn' (multitask/cars.py:671-691): score_t = l3(tanh(l0 x_t)), t >= len -> -inf
+ * (utils/misc.py:65-74), softmax over the padded length, weighted sum. */
+static void attn_pool(const float* enc, int L, int H, int len, const cair_attn_mlp* a, float* out) {
+  float* sc = (float*)malloc(sizeof(float) * (L + H));
+  float* hid = sc + L;
+  float mx = -INFINITY;
+  for (int t = 0; t < L; ++t) {
+    if (t >= len) {
+      sc[t] = -INFINITY;
+      continue;
+    }
+    for (int o = 0; o < H; ++o)
+      hid[o] = tanhf(dotf(enc + (size_t)t * H, a->l0.w + (size_t)o * H, H) + a->l0.b[o]);
+    sc[t] = dotf(hid, a->l3.w, H) + a->l3.b[0];
+    if (sc[t] > mx) mx = sc[t];
+  }
+  float den = 0.0f;
+  for (int t = 0; t < L; ++t) {
+    sc[t] = (t < len) ? expf(sc[t] - mx) : 0.0f;
+    den += sc[t];
+  }
+  for (int o = 0; o < H; ++o) {
+    double s = 0.0;
+    for (int t = 0; t < L; ++t) s += (double)enc[(size_t)t * H + o] * (double)(sc[t] / den);
+    out[o] = (float)s;
+  }
+  free(sc);
+}
+
+/* embed + BiLSTM + attention pooling over n sequences (cars.py:193-225 / :227-260) */
+static int cars_encode(const cair_cars_weights* w, const int64_t* ids, const int64_t* len, int n,
+                       int L, int H, const cair_lstm_dir* fwd, const cair_lstm_dir* rev,
+                       const cair_attn_mlp* attn, float* pooled) {
+  int E = w->emsize;
+  float* x = (float*)malloc(sizeof(float) * (size_t)n * L * E);
+  float* enc = (float*)malloc(sizeof(float) * (size_t)n * L * H);
+  int rc = cair_oracle_embed(w->table, w->vocab, E, ids, (int64_t)n * L, x);
+  if (rc == CAIR_OK) rc = cair_oracle_lstm(x, len, n, L, E, H / 2, fwd, rev, enc, NULL, NULL);
+  if (rc == CAIR_OK) {
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int s = 0; s < n; ++s)
+      attn_pool(enc + (size_t)s * L * H, L, H, (int)len[s], attn, pooled + (size_t)s * H);
+  }
+  free(x);
+  free(enc);
+  return rc;
+}
+
+/* softmax(scores[0..n)) then out = sum_k w_k * states[k] */
+static void softmax_mix(float* sc, int n, const float* states, int stride, int dim, float* out) {
+  float mx = -INFINITY, den = 0.0f;
+  for (int k = 0; k < n; ++k)
+    if (sc[k] > mx) mx = sc[k];
+  for (int k = 0; k < n; ++k) {
+    sc[k] = expf(sc[k] - mx);
+    den += sc[k];
+  }
+  for (int o = 0; o < dim; ++o) {
+    double s = 0.0;
+    for (int k = 0; k < n; ++k) s += (double)states[(size_t)k * stride + o] * (double)(sc[k] / den);
+    out[o] = (float)s;
+  }
+}
+
+/* Maxout (modules/maxout.py:70-84): affine to out*pool, view(out, pool), max over pool. */
+static void maxout_layer(const float* x, int in, const cair_linear* l, int out, int pool, float* y) {
+  for (int o = 0; o < out; ++o) {
+    float best = -INFINITY;
+    for (int p = 0; p < pool; ++p) {
+      int r = o * pool + p;
+      float v = dotf(x, l->w + (size_t)r * in, in) + l->b[r];
+      if (v > best) best = v;
+    }
+    y[o] = best;
+  }
+}
+
+ORA_API int cair_oracle_cars(const cair_cars_weights* w, const int64_t* q, const int64_t* qlen,
+                             const int64_t* d, const int64_t* dlen, const float* labels, int B,
+                             int S, int N, int Lq, int Ld, float* scores, float* pooled_q_out,
+                             float* pooled_d_out, float* clicks_out, float* sess_q_attn_out,
+                             float* sess_d_attn_out) {
+  int Hq = w->nhid_query, Hd = w->nhid_document, Hsq = w->nhid_session_query,
+      Hsd = w->nhid_session_document;
+  int BS = B * S;
+  if (!check_ids(q, (int64_t)BS * Lq, w->vocab) || !check_ids(d, (int64_t)BS * N * Ld, w->vocab))
+    return CAIR_ERR_BAD_ARG;
+  float* pq = (float*)malloc(sizeof(float) * (size_t)BS * Hq);
+  float* pd = (float*)malloc(sizeof(float) * (size_t)BS * N * Hd);
+  float* clk = (float*)malloc(sizeof(float) * (size_t)BS * Hd);
+  int rc = cars_encode(w, q, qlen, BS, Lq, Hq, &w->query_fwd, &w->query_rev, &w->q_attn, pq);
+  if (rc == CAIR_OK)
+    rc = cars_encode(w, d, dlen, BS * N, Ld, Hd, &w->doc_fwd, &w->doc_rev, &w->d_attn, pd);
+  if (rc != CAIR_OK) {
+    free(pq);
+    free(pd);
+    free(clk);
+    return rc;
+  }
+  /* encode_clicks (cars.py:262-304), including the batch-global mask width */
+  int m = 0;
+  for (int r = 0; r < BS; ++r) {
+    int k = 0;
+    for (int n = 0; n < N; ++n) k += labels[r * N + n] != 0.0f;
+    if (k > m) m = k;
+  }
+  for (int r = 0; r < BS; ++r) {
+    int* order = (int*)malloc(sizeof(int) * N);
+    float* sc = (float*)malloc(sizeof(float) * (N + Hd) + sizeof(float) * (size_t)N * Hd);
+    float* hid = sc + N;
+    float* sorted = hid + Hd;
+    int k = 0;
+    for (int n = 0; n < N; ++n) {
+      order[n] = n;
+      k += labels[r * N + n] != 0.0f;
+    }
+    /* stable descending sort by label (torch CPU sort keeps ties in index order) */
+    for (int a = 1; a < N; ++a) {
+      int v = order[a], c = a - 1;
+      while (c >= 0 && labels[r * N + order[c]] < labels[r * N + v]) {
+        order[c + 1] = order[c];
+        --c;
+      }
+      order[c + 1] = v;
+    }
+    for (int n = 0; n < N; ++n)
+      memcpy(sorted + (size_t)n * Hd, pd + ((size_t)r * N + order[n]) * Hd, sizeof(float) * Hd);
+    for (int n = 0; n < N; ++n) {
+      int keep = (n < m) ? (n < k) : 1;
+      if (!keep) {
+        sc[n] = -INFINITY;
+        continue;
+      }
+      for (int o = 0; o < Hd; ++o)
+        hid[o] = tanhf(dotf(sorted + (size_t)n * Hd, w->click_attn.l0.w + (size_t)o * Hd, Hd) +
+                       w->click_attn.l0.b[o]);
+      sc[n] = dotf(hid, w->click_attn.l3.w, Hd) + w->click_attn.l3.b[0];
+    }
+    softmax_mix(sc, N, sorted, Hd, Hd, clk + (size_t)r * Hd);
+    free(order);
+    free(sc);
+  }
+  if (pooled_q_out) memcpy(pooled_q_out, pq, sizeof(float) * (size_t)BS * Hq);
+  if (pooled_d_out) memcpy(pooled_d_out, pd, sizeof(float) * (size_t)BS * N * Hd);
+  if (clicks_out) memcpy(clicks_out, clk, sizeof(float) * (size_t)BS * Hd);
+  /* encode_session (cars.py:306-458) + rank (:460-520), per session b */
+  const int rd0 = w->rank_dims[0], rd1 = w->rank_dims[1], rd2 = w->rank_dims[2], pool = w->rank_pool;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int b = 0; b < B; ++b) {
+    int Hs = Hsq + Hsd;
+    float* Q = (float*)calloc((size_t)(S + 1) * Hsq, sizeof(float)); /* state 0 = zeros */
+    float* D = (float*)calloc((size_t)(S + 1) * Hsd, sizeof(float));
+    float* hq = (float*)calloc(2 * (size_t)Hsq + 4 * Hsq, sizeof(float));
+    float* cqs = hq + Hsq;
+    float* gq = cqs + Hsq;
+    float* hdn = (float*)calloc(2 * (size_t)Hsd + 4 * Hsd, sizeof(float));
+    float* cds = hdn + Hsd;
+    float* gd = cds + Hsd;
+    float* tmp = (float*)malloc(sizeof(float) * ((size_t)(S + 1) + Hq + Hd + Hs + Hd + 4 * Hd + rd0 + rd1 + rd2 + Hsq + Hsd));
+    float* att = tmp;
+    float* proj = att + (S + 1);
+    float* sess = proj + (Hq > Hd ? Hq : Hd);
+    float* qr = sess + Hs;
+    float* feat = qr + Hd;
+    float* y0 = feat + 4 * Hd;
+    float* y1 = y0 + rd0;
+    float* y2 = y1 + rd1;
+    float* hidb = y2 + rd2;
+    for (int s = 0; s < S; ++s) {
+      const float* cur = pq + ((size_t)b * S + s) * Hq;
+      int ns = s + 1;
+      /* attention over past query-session states with the current query (:349-354) */
+      for (int k = 0; k < ns; ++k) {
+        for (int o = 0; o < Hq; ++o)
+          proj[o] = dotf(Q + (size_t)k * Hsq, w->session_query_attn.w + (size_t)o * Hsq, Hsq) +
+                    w->session_query_attn.b[o];
+        att[k] = dotf(proj, cur, Hq);
+      }
+      softmax_mix(att, ns, Q, Hsq, Hsq, sess);
+      /* same for doc-session states, still keyed by the QUERY (:359-364) */
+      for (int k = 0; k < ns; ++k) {
+        for (int o = 0; o < Hd; ++o)
+          proj[o] = dotf(D + (size_t)k * Hsd, w->session_doc_attn.w + (size_t)o * Hsd, Hsd) +
+                    w->session_doc_attn.b[o];
+        att[k] = dotf(proj, cur, Hq);
+      }
+      softmax_mix(att, ns, D, Hsd, Hsd, sess + Hsq);
+      /* rank (:460-520) */
+      for (int o = 0; o < Hd; ++o)
+        qr[o] = dotf(cur, w->q_projection.w + (size_t)o * Hq, Hq) + w->q_projection.b[o] +
+                (dotf(sess, w->shared_session_projector.w + (size_t)o * Hs, Hs) +
+                 dotf(sess, w->private_session_projector1.w + (size_t)o * Hs, Hs));
+      for (int n = 0; n < N; ++n) {
+        const float* dv = pd + (((size_t)b * S + s) * N + n) * Hd;
+        for (int o = 0; o < Hd; ++o) {
+          feat[o] = qr[o];
+          feat[Hd + o] = dv[o];
+          feat[2 * Hd + o] = fabsf(qr[o] - dv[o]);
+          feat[3 * Hd + o] = qr[o] * dv[o];
+        }
+        maxout_layer(feat, 4 * Hd, &w->ranknet[0], rd0, pool, y0);
+        maxout_layer(y0, rd0, &w->ranknet[1], rd1, pool, y1);
+        maxout_layer(y1, rd1, &w->ranknet[2], rd2, pool, y2);
+        scores[((size_t)b * S + s) * N + n] = y2[0];
+      }
+      /* step both session LSTMs (:378-383, :400-405): single-step, carried (h, c) */
+      lstm_step(cur, Hq, Hsq, &w->session_query, hq, cqs, gq);
+      memcpy(Q + (size_t)(s + 1) * Hsq, hq, sizeof(float) * Hsq);
+      lstm_step(clk + ((size_t)b * S + s) * Hd, Hd, Hsd, &w->session_doc, hdn, cds, gd);
+      memcpy(D + (size_t)(s + 1) * Hsd, hdn, sizeof(float) * Hsd);
+      /* inner attention over states 1..s+1 (:385-389, :407-411) - decoder-side outputs */
+      if (sess_q_attn_out) {
+        for (int k = 0; k < ns; ++k) {
+          const float* st = Q + (size_t)(k + 1) * Hsq;
+          for (int o = 0; o < Hsq; ++o)
+            hidb[o] = tanhf(dotf(st, w->session_query_inner_attn.l0.w + (size_t)o * Hsq, Hsq) +
+                            w->session_query_inner_attn.l0.b[o]);
+          att[k] = dotf(hidb, w->session_query_inner_attn.l3.w, Hsq) + w->session_query_inner_attn.l3.b[0];
+        }
+        softmax_mix(att, ns, Q + Hsq, Hsq, Hsq, sess_q_attn_out + ((size_t)b * S + s) * Hsq);
+      }
+      if (sess_d_attn_out) {
+        for (int k = 0; k < ns; ++k) {
+          const float* st = D + (size_t)(k + 1) * Hsd;
+          for (int o = 0; o < Hsd; ++o)
+            hidb[o] = tanhf(dotf(st, w->session_doc_inner_attn.l0.w + (size_t)o * Hsd, Hsd) +
+                            w->session_doc_inner_attn.l0.b[o]);
+          att[k] = dotf(hidb, w->session_doc_inner_attn.l3.w, Hsd) + w->session_doc_inner_attn.l3.b[0];
+        }
+        softmax_mix(att, ns, D + Hsd, Hsd, Hsd, sess_d_attn_out + ((size_t)b * S + s) * Hsd);
+      }
+    }
+    free(Q);
+    free(D);
+    free(hq);
+    free(hdn);
+    free(tmp);
+  }
+  free(pq);
+  free(pd);
+  free(clk);
+  return CAIR_OK;
+}
+
+/* Ranker.predict post-op (models/ranker.py:257-258): softmax over the N candidates. */
+ORA_API int cair_oracle_softmax(const float* scores, int B, int N, float* out) {
+  for (int b = 0; b < B; ++b) {
+    float mx = -INFINITY, den = 0.0f;
+    for (int n = 0; n < N; ++n)
+      if (scores[b * N + n] > mx) mx = scores[b * N + n];
+    for (int n = 0; n < N; ++n) {
+      out[b * N + n] = expf(scores[b * N + n] - mx);
+      den += out[b * N + n];
+    }
+    for (int n = 0; n < N; ++n) out[b * N + n] /= den;
+  }
+  return CAIR_OK;
+}

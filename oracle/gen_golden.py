@@ -1,0 +1,233 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE - generates tests/golden/*.npz by running the UNMODIFIED reference.
+
+Imports the reference's own modules from /root/reference (read-only, never copied),
+builds each network on CPU with torch.manual_seed(1013) (the reference's default seed,
+main/ranker.py:49), feeds the seeded synthetic batches of
+context_attentive_ir_b200/synth.py and freezes inputs, state_dict and outputs.
+/root/reference does not exist on the GPU box, hence the frozen fixtures.
+
+Out-of-tree compat shims (library drift):
+  C1  rankers/drmm.py:71-75 - numpy.apply_along_axis over numpy.histogram returns a
+      ragged tuple and raises under numpy >= 1.24; the shim subclass restates forward
+      and replaces only those lines by a per-row numpy.histogram(...)[0].
+  C2  multitask/cars.py:298 - masked_fill_ with a uint8 mask raises under torch >= 2;
+      Tensor.masked_fill_ is wrapped to cast uint8 -> bool in this process only.
+
+Run:  python oracle/gen_golden.py            (writes tests/golden/)
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, '/root/reference')
+
+from context_attentive_ir_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+
+
+def _apply_shims():
+    orig = torch.Tensor.masked_fill_
+
+    def masked_fill_(self, mask, value):
+        if mask.dtype == torch.uint8:
+            mask = mask.bool()
+        return orig(self, mask, value)
+
+    torch.Tensor.masked_fill_ = masked_fill_
+
+
+def _drmm_shim_class():
+    import numpy
+    import torch.nn.functional as f
+    from neuroir.rankers.drmm import DRMM
+
+    class DRMMShim(DRMM):
+        def forward(self, batch_queries, query_len, batch_docs, doc_len):
+            batch_size = batch_queries.shape[0]
+            qlen = batch_queries.shape[1]
+            num_docs, dlen = batch_docs.shape[1], batch_docs.shape[2]
+            embedded_queries = self.word_embeddings(batch_queries.unsqueeze(2))
+            embedded_queries = self.emb_drop(embedded_queries)
+            term_weights = self.gating_network(embedded_queries).unsqueeze(1).expand(
+                batch_size, num_docs, qlen)
+            doc_rep = batch_docs.view(batch_size * num_docs, dlen)
+            embedded_docs = self.word_embeddings(doc_rep.unsqueeze(2))
+            embedded_docs = self.emb_drop(embedded_docs)
+            embedded_queries = torch.stack([embedded_queries] * num_docs, dim=1)
+            embedded_queries = embedded_queries.contiguous().view(batch_size * num_docs, qlen, -1)
+            embedded_queries = torch.stack([embedded_queries] * dlen, dim=2)
+            embedded_docs = torch.stack([embedded_docs] * qlen, dim=1)
+            cos_sim = f.cosine_similarity(embedded_queries, embedded_docs, 3)
+            cs = cos_sim.detach().cpu().numpy()
+            self._last_cos = cs
+            # --- the only replaced lines (drmm.py:71-75) ---
+            hist = numpy.stack([numpy.stack([numpy.histogram(cs[i, j], bins=self.bins)[0]
+                                             for j in range(cs.shape[1])])
+                                for i in range(cs.shape[0])])
+            self._last_hist = hist
+            histogram_feats = torch.from_numpy(hist).float()
+            # -----------------------------------------------
+            ffnn_out = self.ffnn(histogram_feats).squeeze(2)
+            ffnn_out = ffnn_out.view(batch_size, num_docs, -1).contiguous()
+            weighted_ffnn_out = ffnn_out * term_weights
+            score = self.output(torch.sum(weighted_ffnn_out, 2, keepdim=True)).squeeze(1)
+            return score.view(batch_size, num_docs)
+
+    return DRMMShim
+
+
+def _ns(**kw):
+    return argparse.Namespace(**kw)
+
+
+def _save(name, cfg, batch, net, outputs):
+    arrs = {}
+    for k, v in batch.items():
+        arrs['in/' + k] = v
+    for k, v in net.state_dict().items():
+        arrs['sd/' + k] = v.detach().cpu().numpy()
+    for k, v in outputs.items():
+        arrs['out/' + k] = v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)
+    meta = dict(cfg=cfg, torch=torch.__version__, numpy=np.__version__,
+                threads=torch.get_num_threads(), seed=1013)
+    arrs['meta'] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    path = os.path.join(OUT, name + '.npz')
+    np.savez_compressed(path, **arrs)
+    print('%-28s %8.1f KB  %s' % (name, os.path.getsize(path) / 1024,
+                                  {k: tuple(np.shape(v)) for k, v in outputs.items()}))
+
+
+def _t(batch):
+    return {k: torch.from_numpy(v) for k, v in batch.items()}
+
+
+# ------------------------------------------------------------------ ESM
+def gen_esm(name, seed, B, N, Lq, Ld, E, V, **kw):
+    from neuroir.rankers.esm import ESM
+    torch.manual_seed(1013)
+    net = ESM(_ns(emsize=E, src_vocab_size=V)).eval()
+    batch = synth.ranker_batch(seed, B, N, Lq, Ld, V, **kw)
+    t = _t(batch)
+    with torch.no_grad():
+        s = net(t['q'], t['qlen'], t['d'], t['dlen'])
+    _save(name, dict(model='esm', emsize=E, src_vocab_size=V), batch, net, dict(scores=s))
+
+
+# ------------------------------------------------------------------ Match-Tensor
+def gen_mt(name, seed, B, N, Lq, Ld, E, V, F, Hq, Hd, C, nf, mfs, **kw):
+    from neuroir.rankers.mtensor import MatchTensor
+    torch.manual_seed(1013)
+    cfg = dict(model='match_tensor', emsize=E, src_vocab_size=V, dropout_emb=0.2, rnn_type='LSTM',
+               bidirection=True, nlayers=1, dropout_rnn=0.2, featsize=F, nhid_query=Hq,
+               nhid_doc=Hd, nchannels=C, nfilters=nf, match_filter_size=mfs)
+    net = MatchTensor(_ns(**{k: v for k, v in cfg.items() if k != 'model'})).eval()
+    batch = synth.ranker_batch(seed, B, N, Lq, Ld, V, **kw)
+    t = _t(batch)
+    with torch.no_grad():
+        s = net(t['q'], t['qlen'], t['d'], t['dlen'])
+        # intermediates (mtensor.py:77-94), for stage-wise parity
+        xd = net.linear_projection(net.word_embeddings(t['d'].view(B * N, Ld).unsqueeze(2)))
+        xq = net.linear_projection(net.word_embeddings(t['q'].unsqueeze(2)))
+        _, hq = net.query_encoder(xq, t['qlen'])
+        _, hd = net.document_encoder(xd, t['dlen'].reshape(-1))
+    _save(name, cfg, batch, net, dict(scores=s, proj_docs=xd, enc_queries=hq, enc_docs=hd))
+
+
+# ------------------------------------------------------------------ DRMM
+def gen_drmm(name, seed, B, N, Lq, Ld, E, V, **kw):
+    DRMMShim = _drmm_shim_class()
+    torch.manual_seed(1013)
+    cfg = dict(model='drmm', emsize=E, src_vocab_size=V, dropout_emb=0.2, nbins=5)
+    net = DRMMShim(_ns(**{k: v for k, v in cfg.items() if k != 'model'})).eval()
+    batch = synth.ranker_batch(seed, B, N, Lq, Ld, V, **kw)
+    t = _t(batch)
+    with torch.no_grad():
+        s = net(t['q'], t['qlen'], t['d'], t['dlen'])
+    _save(name, cfg, batch, net, dict(scores=s, cos=net._last_cos, hist=net._last_hist))
+
+
+# ------------------------------------------------------------------ DUET
+def gen_duet(name, seed, B, N, Lq, Ld, E, V, nf, pool=5, **kw):
+    from neuroir.rankers.duet import DUET
+    torch.manual_seed(1013)
+    cfg = dict(model='duet', emsize=E, src_vocab_size=V, dropout_emb=0.2, dropout=0.2, use_word=True,
+               nfilters=nf, local_filter_size=1, dist_filter_size=3, pool_size=pool,
+               max_doc_len=Ld, max_query_len=Lq)
+    net = DUET(_ns(**{k: v for k, v in cfg.items() if k != 'model'})).eval()
+    batch = synth.ranker_batch(seed, B, N, Lq, Ld, V, **kw)
+    t = _t(batch)
+    with torch.no_grad():
+        s = net(t['q'], t['qlen'], t['d'], t['dlen'])
+        loc = net.local_model(t['q'], t['d'])
+    _save(name, cfg, batch, net, dict(scores=s, local=loc))
+
+
+# ------------------------------------------------------------------ CARS (ranking path)
+def gen_cars(name, seed, B, S, N, Lq, Ld, E, V, Hq, Hd, Hs, max_clicks=1, **kw):
+    from neuroir.multitask.cars import CARS
+    torch.manual_seed(1013)
+    cfg = dict(model='cars', emsize=E, src_vocab_size=V, tgt_vocab_size=50, dropout_emb=0.2, dropout=0.2,
+               rnn_type='LSTM', bidirection=True, nlayers=1, nhid_query=Hq, nhid_document=Hd,
+               nhid_click=Hs, nhid_session_query=Hs, nhid_session_document=Hs, nhid_decoder=Hs,
+               query_session_off=False, doc_session_off=False, dropout_rnn=0.2,
+               attn_type='general', mlp_nhid=150, pool_type='attn', regularize_coeff=0.1,
+               alpha=0.1, lambda1=0.01, lambda2=0.0001, turn_ranker_off=False,
+               turn_recommender_off=False)
+    net = CARS(_ns(**{k: v for k, v in cfg.items() if k != 'model'})).eval()
+    batch = synth.session_batch(seed, B, S, N, Lq, Ld, V, max_clicks=max_clicks, **kw)
+    t = _t(batch)
+    with torch.no_grad():
+        pooled, enc_src, _ = net.encode(t['q'], t['qlen'])
+        pooled_docs = net.encode_document(t['d'], t['dlen'])
+        clicks = net.encode_clicks(pooled_docs, t['label'])
+        scores, states, sess_attn = net.rank_document(pooled, t['d'], t['dlen'], t['label'])
+    # decoder-side weights are not on the scoring path: drop them to keep fixtures small
+    sd = {k: v for k, v in net.state_dict().items()
+          if not k.startswith(('decoder.', 'token_prob_predictor', 'dec_attn', 'transform_'))}
+
+    class _SD:
+        def state_dict(self):
+            return sd
+    _save(name, cfg, batch, _SD(), dict(scores=scores, pooled_queries=pooled, pooled_docs=pooled_docs,
+                                        clicks=clicks, sess_q_attn=sess_attn[0], sess_d_attn=sess_attn[1]))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    _apply_shims()
+    torch.set_num_threads(1)  # deterministic MKLDNN summation order
+    # BASELINE configs[0]: the reference's own CPU-runnable case (vocab cut 10k -> 1k to keep the file small)
+    gen_esm('esm_cfg1', 1235, B=8, N=5, Lq=10, Ld=50, E=64, V=1000)
+    gen_esm('esm_e300', 11, B=3, N=4, Lq=20, Ld=200, E=300, V=300, bos_eos=True)
+    # Match-Tensor: tiny, cfg2 architecture (H=128) at reduced batch/vocab, stock 30/140 sizes
+    gen_mt('mt_tiny', 21, B=3, N=4, Lq=7, Ld=23, E=32, V=100, F=8, Hq=12, Hd=20, C=10, nf=4, mfs=6,
+           overlap=0.2)
+    gen_mt('mt_cfg2arch', 1236, B=2, N=3, Lq=20, Ld=200, E=300, V=400, F=40, Hq=128, Hd=128, C=50, nf=6,
+           mfs=20, bos_eos=True, overlap=0.1)
+    gen_mt('mt_stock', 23, B=2, N=2, Lq=20, Ld=200, E=300, V=400, F=40, Hq=30, Hd=140, C=50, nf=6,
+           mfs=20, bos_eos=True)
+    gen_mt('mt_fullpad', 24, B=2, N=2, Lq=12, Ld=40, E=48, V=200, F=16, Hq=32, Hd=32, C=18, nf=6,
+           mfs=20, variable=False)
+    # DRMM: strict (disjoint ids) and overlapping (bin-edge cells excluded by the test using out/cos)
+    gen_drmm('drmm_strict', 1237, B=3, N=4, Lq=20, Ld=200, E=300, V=400, disjoint=True)
+    gen_drmm('drmm_overlap', 32, B=2, N=3, Lq=12, Ld=60, E=64, V=300, bos_eos=True, overlap=0.1)
+    # DUET (force_pad shapes: every batch padded to max lens, lengths still variable)
+    gen_duet('duet_tiny', 41, B=2, N=3, Lq=8, Ld=30, E=24, V=120, nf=16, overlap=0.2)
+    gen_duet('duet_e300', 1239, B=2, N=3, Lq=20, Ld=200, E=300, V=400, nf=64, bos_eos=True, overlap=0.1)
+    # CARS ranking path
+    gen_cars('cars_tiny', 51, B=2, S=3, N=4, Lq=6, Ld=17, E=24, V=150, Hq=16, Hd=16, Hs=24, max_clicks=1)
+    gen_cars('cars_clicks', 52, B=3, S=4, N=5, Lq=8, Ld=30, E=32, V=200, Hq=32, Hd=32, Hs=48, max_clicks=3)
+    gen_cars('cars_mid', 1238, B=2, S=7, N=10, Lq=20, Ld=200, E=300, V=400, Hq=64, Hd=64, Hs=96,
+             max_clicks=2)
+
+
+if __name__ == '__main__':
+    main()
