@@ -1,0 +1,418 @@
+// C ABI of libcair.so (include/cair.h): handles, weight repacking, forward orchestration.
+#include <cstdarg>
+#include <cstring>
+
+#include "models.cuh"
+
+namespace cair {
+
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launches{0};
+thread_local Profiler* g_prof = nullptr;
+
+int32_t fail(int32_t code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+}  // namespace cair
+
+using namespace cair;
+
+struct cair_handle {
+  int model = 0;
+  int device = 0;
+  Owned own;
+  int* d_err = nullptr;  // device error flags (ERRF_*)
+  Profiler prof;
+  // weights: struct copies hold the caller's device pointers only where create() documents a copy
+  EsmState esm;
+  MtState mt;
+  DrmmState drmm;
+  DuetState duet;
+  CarsState cars;
+  // host-path staging (cair_ranker_forward_host)
+  void* stage_dev = nullptr;
+  size_t stage_dev_bytes = 0;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int32_t new_handle(int model, int device, cair_handle** out) {
+  if (!out) return fail(CAIR_ERR_BAD_ARG, "null handle out-pointer");
+  int ndev = 0;
+  CAIR_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(CAIR_ERR_BAD_ARG, "device %d out of range (%d visible)", device, ndev);
+  cair_handle* h = new cair_handle();
+  h->model = model, h->device = device;
+  *out = h;
+  return CAIR_OK;
+}
+
+template <typename T>
+int32_t copy_weights(Owned& own, const T* src, size_t n, T** dst, cudaStream_t s) {
+  if (!src) return fail(CAIR_ERR_BAD_ARG, "null weight pointer");
+  CAIR_CUDA(own.alloc(dst, n));
+  CAIR_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+  return CAIR_OK;
+}
+
+int32_t finish_create(cair_handle* h, int32_t rc, cair_handle** out) {
+  if (rc == CAIR_OK) {
+    cudaError_t e = cudaStreamSynchronize(0);
+    if (e != cudaSuccess) rc = fail(CAIR_ERR_CUDA, "create: %s", cudaGetErrorString(e));
+  }
+  if (rc != CAIR_OK) {
+    h->own.release();
+    delete h;
+    *out = nullptr;
+  }
+  return rc;
+}
+
+int32_t init_err_flag(cair_handle* h) {
+  CAIR_CUDA(h->own.alloc(&h->d_err, 1));
+  CAIR_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int), 0));
+  return CAIR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t cair_version(void) { return CAIR_VERSION; }
+const char* cair_last_error(void) { return g_last_error.c_str(); }
+int64_t cair_launch_count(void) { return g_launches.load(); }
+
+int32_t cair_destroy(cair_handle* h) {
+  if (!h) return CAIR_OK;
+  DeviceGuard g(h->device);
+  h->own.release();
+  h->prof.release();
+  if (h->stage_dev) cudaFree(h->stage_dev);
+  if (h->ws) cudaFree(h->ws);
+  delete h;
+  return CAIR_OK;
+}
+
+int32_t cair_poll_error(cair_handle* h, void* stream) {
+  if (!h) return fail(CAIR_ERR_BAD_ARG, "null handle");
+  DeviceGuard g(h->device);
+  int flags = 0;
+  CAIR_CUDA(cudaMemcpyAsync(&flags, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CAIR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (flags) {
+    CAIR_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int), (cudaStream_t)stream));
+    if (flags & ERRF_BAD_TOKEN) return fail(CAIR_ERR_BAD_ARG, "token id outside [0, vocab)");
+    return fail(CAIR_ERR_BAD_ARG, "sequence length outside [1, padded length]");
+  }
+  return CAIR_OK;
+}
+
+// ---- kernel-level entry points -----------------------------------------------------------------
+int32_t cair_embed_gather(const float* table, int32_t V, int32_t E, const int64_t* ids, int64_t T, float* out,
+                          void* stream) {
+  if (!table || !ids || !out || V <= 0 || E <= 0 || T < 0) return fail(CAIR_ERR_BAD_ARG, "embed_gather: bad argument");
+  return embed_gather(table, V, E, ids, T, out, nullptr, (cudaStream_t)stream);
+}
+
+int32_t cair_lstm_forward(const float* x, const int64_t* len, int32_t n, int32_t L, int32_t in, int32_t h,
+                          const cair_lstm_dir* fwd, const cair_lstm_dir* rev, float* out, float* h_n, float* c_n,
+                          void* stream) {
+  if (!x || !len || !out || !fwd || n < 0 || L <= 0) return fail(CAIR_ERR_BAD_ARG, "lstm_forward: bad argument");
+  // unit-test entry point: packs the weights and allocates its scratch on every call
+  cudaStream_t s = (cudaStream_t)stream;
+  Owned own;
+  LstmPack p;
+  int32_t rc = lstm_pack(own, fwd, rev, in, h, &p, s);
+  float* pre = nullptr;
+  int* err = nullptr;
+  if (rc == CAIR_OK && own.alloc(&pre, lstm_workspace_floats(p, n, L)) != cudaSuccess) rc = fail(CAIR_ERR_CUDA, "lstm_forward: out of memory");
+  if (rc == CAIR_OK && own.alloc(&err, 1) != cudaSuccess) rc = fail(CAIR_ERR_CUDA, "lstm_forward: out of memory");
+  if (rc == CAIR_OK) {
+    cudaMemsetAsync(err, 0, sizeof(int), s);
+    rc = lstm_run(p, gemm_dense(x, in), len, n, L, out, h_n, c_n, pre, err, s);
+  }
+  int flags = 0;
+  if (rc == CAIR_OK) cudaMemcpyAsync(&flags, err, sizeof(int), cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  own.release();
+  if (rc == CAIR_OK && e != cudaSuccess) rc = fail(CAIR_ERR_CUDA, "lstm_forward: %s", cudaGetErrorString(e));
+  if (rc == CAIR_OK && flags) rc = fail(CAIR_ERR_BAD_ARG, "lstm_forward: length outside [1, L]");
+  return rc;
+}
+
+// ---- create ------------------------------------------------------------------------------------
+int32_t cair_esm_create(const cair_esm_weights* w, int32_t device, cair_handle** out) {
+  if (!w || !w->table || w->vocab <= 0 || w->emsize <= 0) return fail(CAIR_ERR_BAD_ARG, "esm_create: bad weights");
+  cair_handle* h = nullptr;
+  CAIR_TRY(new_handle(CAIR_MODEL_ESM, device, &h));
+  DeviceGuard g(device);
+  int32_t rc = init_err_flag(h);
+  h->esm.V = w->vocab, h->esm.E = w->emsize;
+  if (rc == CAIR_OK) rc = copy_weights(h->own, w->table, (size_t)w->vocab * w->emsize, &h->esm.table, 0);
+  rc = finish_create(h, rc, out);
+  if (rc == CAIR_OK) *out = h;
+  return rc;
+}
+
+int32_t cair_mt_create(const cair_mt_weights* w, int32_t device, cair_handle** out) {
+  if (!w || !w->table) return fail(CAIR_ERR_BAD_ARG, "mt_create: bad weights");
+  if (w->rnn_type != CAIR_RNN_LSTM) return fail(CAIR_ERR_UNSUPPORTED, "mt_create: only rnn_type LSTM is implemented");
+  int dirs = w->bidirectional ? 2 : 1;
+  if (w->nhid_query % dirs || w->nhid_doc % dirs) return fail(CAIR_ERR_BAD_SHAPE, "mt_create: hidden size not divisible by directions");
+  cair_handle* h = nullptr;
+  CAIR_TRY(new_handle(CAIR_MODEL_MT, device, &h));
+  DeviceGuard g(device);
+  int32_t rc = init_err_flag(h);
+  if (rc == CAIR_OK) rc = mt_create_state(h->own, *w, &h->mt, 0);
+  rc = finish_create(h, rc, out);
+  if (rc == CAIR_OK) *out = h;
+  return rc;
+}
+
+int32_t cair_mt_set_debug(cair_handle* h, float* enc_q, float* enc_d) {
+  if (!h || h->model != CAIR_MODEL_MT) return fail(CAIR_ERR_BAD_ARG, "mt_set_debug: not a match-tensor handle");
+  h->mt.dbg_enc_q = enc_q, h->mt.dbg_enc_d = enc_d;
+  return CAIR_OK;
+}
+
+int32_t cair_drmm_create(const cair_drmm_weights* w, int32_t device, cair_handle** out) {
+  if (!w || !w->table) return fail(CAIR_ERR_BAD_ARG, "drmm_create: bad weights");
+  if (w->nbins != 5) return fail(CAIR_ERR_UNSUPPORTED, "drmm_create: nbins must be 5 (neuroir/hyparam.py:78-81)");
+  cair_handle* h = nullptr;
+  CAIR_TRY(new_handle(CAIR_MODEL_DRMM, device, &h));
+  DeviceGuard g(device);
+  int32_t rc = init_err_flag(h);
+  DrmmState& st = h->drmm;
+  st.w = *w;
+  float* t = nullptr;
+  if (rc == CAIR_OK) rc = copy_weights(h->own, w->table, (size_t)w->vocab * w->emsize, &t, 0);
+  st.w.table = t;
+  auto cp = [&](const float* src, size_t n, const float** dst) {
+    float* p = nullptr;
+    if (rc == CAIR_OK) rc = copy_weights(h->own, src, n, &p, 0);
+    *dst = p;
+  };
+  cp(w->gating.w, w->emsize, &st.w.gating.w);
+  cp(w->gating.b, 1, &st.w.gating.b);
+  cp(w->ffnn0.w, 5, &st.w.ffnn0.w);
+  cp(w->ffnn0.b, 1, &st.w.ffnn0.b);
+  cp(w->ffnn1.w, 1, &st.w.ffnn1.w);
+  cp(w->ffnn1.b, 1, &st.w.ffnn1.b);
+  cp(w->output.w, 1, &st.w.output.w);
+  cp(w->output.b, 1, &st.w.output.b);
+  rc = finish_create(h, rc, out);
+  if (rc == CAIR_OK) *out = h;
+  return rc;
+}
+
+int32_t cair_drmm_set_debug(cair_handle* h, int32_t* hist) {
+  if (!h || h->model != CAIR_MODEL_DRMM) return fail(CAIR_ERR_BAD_ARG, "drmm_set_debug: not a DRMM handle");
+  h->drmm.dbg_hist = hist;
+  return CAIR_OK;
+}
+
+int32_t cair_duet_create(const cair_duet_weights* w, int32_t device, cair_handle** out) {
+  if (!w || !w->table) return fail(CAIR_ERR_BAD_ARG, "duet_create: bad weights");
+  if (w->local_filter_size != 1 || w->dist_filter_size != 3)
+    return fail(CAIR_ERR_UNSUPPORTED, "duet_create: only local_filter_size=1, dist_filter_size=3 (the shapes duet.py:144 admits)");
+  cair_handle* h = nullptr;
+  CAIR_TRY(new_handle(CAIR_MODEL_DUET, device, &h));
+  DeviceGuard g(device);
+  int32_t rc = init_err_flag(h);
+  if (rc == CAIR_OK) rc = duet_create_state(h->own, *w, &h->duet, 0);
+  rc = finish_create(h, rc, out);
+  if (rc == CAIR_OK) *out = h;
+  return rc;
+}
+
+int32_t cair_cars_create(const cair_cars_weights* w, int32_t device, cair_handle** out) {
+  if (!w || !w->table) return fail(CAIR_ERR_BAD_ARG, "cars_create: bad weights");
+  cair_handle* h = nullptr;
+  CAIR_TRY(new_handle(CAIR_MODEL_CARS, device, &h));
+  DeviceGuard g(device);
+  int32_t rc = init_err_flag(h);
+  if (rc == CAIR_OK) rc = cars_create_state(h->own, *w, &h->cars, 0);
+  rc = finish_create(h, rc, out);
+  if (rc == CAIR_OK) *out = h;
+  return rc;
+}
+
+// ---- stand-alone rankers: workspace + forward ---------------------------------------------------
+static int32_t check_ranker_args(cair_handle* h, int32_t B, int32_t N, int32_t Lq, int32_t Ld) {
+  if (!h) return fail(CAIR_ERR_BAD_ARG, "null handle");
+  if (h->model == CAIR_MODEL_CARS) return fail(CAIR_ERR_BAD_ARG, "CARS handles use cair_cars_forward");
+  if (B <= 0 || N <= 0 || Lq <= 0 || Ld <= 0) return fail(CAIR_ERR_BAD_SHAPE, "B, N, Lq, Ld must be positive");
+  return CAIR_OK;
+}
+
+static int32_t ranker_run(cair_handle* h, const int64_t* q, const int64_t* qlen, const int64_t* d,
+                          const int64_t* dlen, int B, int N, int Lq, int Ld, int64_t pb, int64_t pc, float* scores,
+                          Arena& ws, cudaStream_t s, bool dry) {
+  switch (h->model) {
+    case CAIR_MODEL_ESM:
+      if (dry) return CAIR_OK;
+      return esm_forward(h->esm.table, h->esm.V, h->esm.E, q, d, N, Lq, Ld, pb, pc, scores, h->d_err, s);
+    case CAIR_MODEL_DRMM:
+      if (dry) return CAIR_OK;
+      return drmm_forward(h->drmm.w, q, d, N, Lq, Ld, pb, pc, scores, h->drmm.dbg_hist, h->d_err, s);
+    case CAIR_MODEL_MT:
+      return mt_forward(h->mt, q, qlen, d, dlen, B, N, Lq, Ld, pb, pc, scores, ws, h->d_err, s, dry);
+    case CAIR_MODEL_DUET:
+      return duet_forward(h->duet, q, d, B, N, Lq, Ld, pb, pc, scores, ws, h->d_err, s, dry);
+  }
+  return fail(CAIR_ERR_BAD_ARG, "unknown model");
+}
+
+int32_t cair_ranker_workspace_bytes(cair_handle* h, int32_t B, int32_t N, int32_t Lq, int32_t Ld, size_t* bytes) {
+  CAIR_TRY(check_ranker_args(h, B, N, Lq, Ld));
+  if (!bytes) return fail(CAIR_ERR_BAD_ARG, "null bytes");
+  Arena a(nullptr, 0);
+  CAIR_TRY(ranker_run(h, nullptr, nullptr, nullptr, nullptr, B, N, Lq, Ld, 0, (int64_t)B * N, nullptr, a, 0, true));
+  *bytes = align_up(a.off) + 256;
+  return CAIR_OK;
+}
+
+int32_t cair_ranker_forward(cair_handle* h, const int64_t* q, const int64_t* qlen, const int64_t* d,
+                            const int64_t* dlen, int32_t B, int32_t N, int32_t Lq, int32_t Ld, int64_t pair_begin,
+                            int64_t pair_count, float* scores, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  CAIR_TRY(check_ranker_args(h, B, N, Lq, Ld));
+  if (!q || !qlen || !d || !dlen || !scores) return fail(CAIR_ERR_BAD_ARG, "ranker_forward: null tensor");
+  if (pair_begin < 0 || pair_count < 0 || pair_begin + pair_count > (int64_t)B * N)
+    return fail(CAIR_ERR_BAD_ARG, "ranker_forward: pair slice [%lld, +%lld) outside B*N", (long long)pair_begin, (long long)pair_count);
+  if (((uintptr_t)workspace & 255) != 0) return fail(CAIR_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  DeviceGuard g(h->device);
+  Arena probe(nullptr, 0);
+  CAIR_TRY(ranker_run(h, nullptr, nullptr, nullptr, nullptr, B, N, Lq, Ld, pair_begin, pair_count, nullptr, probe, 0, true));
+  if (probe.off > workspace_bytes || (probe.off > 0 && !workspace))
+    return fail(CAIR_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", probe.off, workspace_bytes);
+  Arena ws(workspace, workspace_bytes);
+  h->prof.reset();
+  g_prof = &h->prof;
+  prof_mark("begin", (cudaStream_t)stream);
+  int32_t rc = ranker_run(h, q, qlen, d, dlen, B, N, Lq, Ld, pair_begin, pair_count, scores, ws, (cudaStream_t)stream, false);
+  prof_mark("end", (cudaStream_t)stream);
+  g_prof = nullptr;
+  return rc;
+}
+
+int32_t cair_profile_enable(cair_handle* h, int32_t on) {
+  if (!h) return fail(CAIR_ERR_BAD_ARG, "null handle");
+  h->prof.on = on != 0;
+  h->prof.reset();
+  return CAIR_OK;
+}
+
+int32_t cair_profile_read(cair_handle* h, char* names, size_t names_bytes, float* ms, int32_t capacity, int32_t* count) {
+  if (!h || !ms || !count) return fail(CAIR_ERR_BAD_ARG, "profile_read: bad argument");
+  DeviceGuard g(h->device);
+  Profiler& p = h->prof;
+  int n = p.cursor > 0 ? p.cursor - 1 : 0;
+  if (n > capacity) n = capacity;
+  std::string joined;
+  for (int i = 0; i < n; ++i) {
+    CAIR_CUDA(cudaEventSynchronize(p.ev[i + 1]));
+    CAIR_CUDA(cudaEventElapsedTime(&ms[i], p.ev[i], p.ev[i + 1]));
+    joined += p.names[i];
+    joined += (i + 1 < n) ? "," : "";
+  }
+  if (names && names_bytes > 0) {
+    strncpy(names, joined.c_str(), names_bytes - 1);
+    names[names_bytes - 1] = 0;
+  }
+  *count = n;
+  return CAIR_OK;
+}
+
+int32_t cair_ranker_forward_host(cair_handle* h, const int64_t* q, const int64_t* qlen, const int64_t* d,
+                                 const int64_t* dlen, int32_t B, int32_t N, int32_t Lq, int32_t Ld, float* scores,
+                                 void* stream) {
+  CAIR_TRY(check_ranker_args(h, B, N, Lq, Ld));
+  if (!q || !qlen || !d || !dlen || !scores) return fail(CAIR_ERR_BAD_ARG, "ranker_forward_host: null tensor");
+  DeviceGuard g(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t nq = (size_t)B * Lq, nd = (size_t)B * N * Ld, nb = (size_t)B, nbn = (size_t)B * N;
+  const size_t in_bytes = (nq + nb + nd + nbn) * sizeof(int64_t);
+  const size_t need = align_up(in_bytes) + align_up(nbn * sizeof(float));
+  if (need > h->stage_dev_bytes) {
+    if (h->stage_dev) CAIR_CUDA(cudaFree(h->stage_dev));
+    h->stage_dev = nullptr, h->stage_dev_bytes = 0;
+    CAIR_CUDA(cudaMalloc(&h->stage_dev, need));
+    h->stage_dev_bytes = need;
+  }
+  size_t wsb = 0;
+  CAIR_TRY(cair_ranker_workspace_bytes(h, B, N, Lq, Ld, &wsb));
+  if (wsb > h->ws_bytes) {
+    if (h->ws) CAIR_CUDA(cudaFree(h->ws));
+    h->ws = nullptr, h->ws_bytes = 0;
+    CAIR_CUDA(cudaMalloc(&h->ws, wsb));
+    h->ws_bytes = wsb;
+  }
+  int64_t* dq = (int64_t*)h->stage_dev;
+  int64_t* dql = dq + nq;
+  int64_t* dd = dql + nb;
+  int64_t* ddl = dd + nd;
+  float* ds = (float*)((char*)h->stage_dev + align_up(in_bytes));
+  CAIR_CUDA(cudaMemcpyAsync(dq, q, nq * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  CAIR_CUDA(cudaMemcpyAsync(dql, qlen, nb * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  CAIR_CUDA(cudaMemcpyAsync(dd, d, nd * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  CAIR_CUDA(cudaMemcpyAsync(ddl, dlen, nbn * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  CAIR_TRY(cair_ranker_forward(h, dq, dql, dd, ddl, B, N, Lq, Ld, 0, (int64_t)nbn, ds, h->ws, h->ws_bytes, stream));
+  CAIR_CUDA(cudaMemcpyAsync(scores, ds, nbn * sizeof(float), cudaMemcpyDeviceToHost, s));
+  return cair_poll_error(h, stream);  // synchronises the stream
+}
+
+// ---- CARS ----------------------------------------------------------------------------------------
+int32_t cair_cars_workspace_bytes(cair_handle* h, int32_t B, int32_t S, int32_t N, int32_t Lq, int32_t Ld,
+                                  size_t* bytes) {
+  if (!h || h->model != CAIR_MODEL_CARS || !bytes) return fail(CAIR_ERR_BAD_ARG, "cars_workspace_bytes: bad argument");
+  if (B <= 0 || S <= 0 || N <= 0 || Lq <= 0 || Ld <= 0) return fail(CAIR_ERR_BAD_SHAPE, "B, S, N, Lq, Ld must be positive");
+  Arena a(nullptr, 0);
+  CarsIO io{};
+  CAIR_TRY(cars_forward(h->cars, io, B, S, N, Lq, Ld, 0, B, a, h->d_err, 0, true));
+  *bytes = align_up(a.off) + 256;
+  return CAIR_OK;
+}
+
+int32_t cair_cars_forward(cair_handle* h, const int64_t* q, const int64_t* qlen, const int64_t* d,
+                          const int64_t* dlen, const float* labels, int32_t B, int32_t S, int32_t N, int32_t Lq,
+                          int32_t Ld, int32_t session_begin, int32_t session_count, float* scores, float* pooled_q,
+                          float* pooled_d, float* clicks, float* sess_q_attn, float* sess_d_attn, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  if (!h || h->model != CAIR_MODEL_CARS) return fail(CAIR_ERR_BAD_ARG, "cars_forward: not a CARS handle");
+  if (B <= 0 || S <= 0 || N <= 0 || Lq <= 0 || Ld <= 0) return fail(CAIR_ERR_BAD_SHAPE, "B, S, N, Lq, Ld must be positive");
+  if (!q || !qlen || !d || !dlen || !labels || !scores) return fail(CAIR_ERR_BAD_ARG, "cars_forward: null tensor");
+  if (session_begin < 0 || session_count < 0 || session_begin + session_count > B)
+    return fail(CAIR_ERR_BAD_ARG, "cars_forward: session slice outside B");
+  if (((uintptr_t)workspace & 255) != 0) return fail(CAIR_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  DeviceGuard g(h->device);
+  CarsIO io{q, qlen, d, dlen, labels, scores, pooled_q, pooled_d, clicks, sess_q_attn, sess_d_attn};
+  Arena probe(nullptr, 0);
+  CAIR_TRY(cars_forward(h->cars, io, B, S, N, Lq, Ld, session_begin, session_count, probe, h->d_err, 0, true));
+  if (probe.off > workspace_bytes || (probe.off > 0 && !workspace))
+    return fail(CAIR_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", probe.off, workspace_bytes);
+  Arena ws(workspace, workspace_bytes);
+  return cars_forward(h->cars, io, B, S, N, Lq, Ld, session_begin, session_count, ws, h->d_err, (cudaStream_t)stream, false);
+}
+
+}  // extern "C"

@@ -1,0 +1,186 @@
+// Shared helpers of libcair.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/cair.h"
+
+namespace cair {
+
+extern thread_local std::string g_last_error;
+extern std::atomic<int64_t> g_launches;
+
+int32_t fail(int32_t code, const char* fmt, ...);
+
+#define CAIR_CUDA(expr)                                                                    \
+  do {                                                                                     \
+    cudaError_t e_ = (expr);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return ::cair::fail(CAIR_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #expr,       \
+                          cudaGetErrorString(e_));                                         \
+  } while (0)
+
+#define CAIR_TRY(expr)                 \
+  do {                                 \
+    int32_t rc_ = (expr);              \
+    if (rc_ != CAIR_OK) return rc_;    \
+  } while (0)
+
+// Every kernel launch of the library goes through this: counts it (cair_launch_count) and
+// surfaces launch-configuration errors immediately.
+#define CAIR_LAUNCH(kernel, grid, block, smem, stream, ...)                                \
+  do {                                                                                     \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                            \
+    ::cair::g_launches.fetch_add(1, std::memory_order_relaxed);                            \
+    cudaError_t e_ = cudaGetLastError();                                                   \
+    if (e_ != cudaSuccess)                                                                 \
+      return ::cair::fail(CAIR_ERR_CUDA, "%s:%d launch %s: %s", __FILE__, __LINE__,        \
+                          #kernel, cudaGetErrorString(e_));                                \
+  } while (0)
+
+constexpr int kSMs = 148;  // B200
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Bump allocator over the caller-provided workspace (forward never allocates).
+struct Arena {
+  char* base;
+  size_t cap, off;
+  Arena(void* p, size_t bytes) : base((char*)p), cap(bytes), off(0) {}
+  template <typename T>
+  T* take(size_t n) {
+    size_t o = align_up(off);
+    off = o + n * sizeof(T);
+    return (T*)(base ? base + o : nullptr);
+  }
+  bool ok() const { return off <= cap; }
+};
+
+// Device buffers owned by a handle.
+struct Owned {
+  std::vector<void*> ptrs;
+  template <typename T>
+  cudaError_t alloc(T** out, size_t n) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T) > 0 ? n * sizeof(T) : 16);
+    if (e == cudaSuccess) ptrs.push_back(p);
+    *out = (T*)p;
+    return e;
+  }
+  void release() {
+    for (void* p : ptrs) cudaFree(p);
+    ptrs.clear();
+  }
+};
+
+enum { ERRF_BAD_TOKEN = 1, ERRF_BAD_LENGTH = 2 };
+
+// Optional stage timing (cair_profile_*): CUDA events recorded on the launching stream between the
+// stages of a forward; interval i runs from mark i to mark i+1.  Off by default (no events recorded).
+struct Profiler {
+  bool on = false;
+  int cursor = 0;
+  std::vector<std::string> names;
+  std::vector<cudaEvent_t> ev;
+  void reset() { cursor = 0; }
+  void mark(const char* name, cudaStream_t s) {
+    if (!on) return;
+    if (cursor == (int)ev.size()) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return;
+      ev.push_back(e);
+      names.push_back(name);
+    }
+    names[cursor] = name;
+    cudaEventRecord(ev[cursor++], s);
+  }
+  void release() {
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    ev.clear();
+    names.clear();
+  }
+};
+extern thread_local Profiler* g_prof;
+inline void prof_mark(const char* name, cudaStream_t s) {
+  if (g_prof) g_prof->mark(name, s);
+}
+
+// ---- device helpers ------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// Token id -> table row, flagging ids outside [0, V) (the reference raises IndexError there,
+// modules/embeddings.py:165 nn.Embedding) and substituting the PAD row.
+__device__ __forceinline__ int64_t checked_id(int64_t id, int V, int* err) {
+  if (id < 0 || id >= V) {
+    if (err) atomicOr(err, ERRF_BAD_TOKEN);
+    return 0;
+  }
+  return id;
+}
+
+// 128-bit streaming load that does not allocate in L1 (gathered rows are touched once).
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+}  // namespace cair
+
+// ---- internal cross-file API -----------------------------------------------------------------
+namespace cair {
+
+enum Act { ACT_NONE = 0, ACT_TANH = 1 };
+
+// A-row providers of the generic GEMM  C[M,N] = act(A[M,K] W[N,K]^T + bias).
+struct GemmA {
+  const float* dense;   // row r at dense + r*lda (when table == nullptr)
+  int64_t lda;
+  const float* table;   // gathered: row r = concat_{k<win} table[ids[seq*L + t + k]], r = seq*T + t
+  const int64_t* ids;
+  int V, E, win, L, T;  // K must equal win*E
+  int* err;
+  int pool;             // dense only: row r = seq*T + t holds max_{k<win} dense[(seq*L + t + k)*lda + :]
+};                      // (max_pool1d(win, stride 1) over the time axis fused into the A load)
+inline GemmA gemm_dense(const float* a, int64_t lda) { return GemmA{a, lda, nullptr, nullptr, 0, 0, 0, 0, 0, nullptr, 0}; }
+inline GemmA gemm_gather(const float* table, int V, int E, const int64_t* ids, int win, int L, int T, int* err) {
+  return GemmA{nullptr, 0, table, ids, V, E, win, L, T, err, 0};
+}
+inline GemmA gemm_pooled(const float* a, int64_t lda, int win, int L, int T) {
+  return GemmA{a, lda, nullptr, nullptr, 0, 0, win, L, T, nullptr, 1};
+}
+int32_t gemm_f32(const GemmA& a, const float* w, const float* bias, float* c, int64_t ldc, int64_t M,
+                 int N, int K, Act act, cudaStream_t s);
+
+// LSTM weights repacked for the recurrent kernel.
+struct LstmPack {
+  int in, h, dirs;
+  float* w_ih;    // [dirs*4h, in]  (fwd rows then rev rows): the pre-gate GEMM's W
+  float* bias;    // [dirs*4h]      b_ih + b_hh
+  float* w_hh_t;  // [dirs][h][4h]  k-major recurrent weights
+};
+int32_t lstm_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, int in, int h, LstmPack* out,
+                  cudaStream_t s);
+size_t lstm_workspace_floats(const LstmPack& p, int64_t n, int L);
+// pre-gates GEMM (optionally gathering rows from `table`) + recurrence; out [n,L,dirs*h], zeros at t>=len.
+int32_t lstm_run(const LstmPack& p, const GemmA& x, const int64_t* len, int n, int L, float* out, float* h_n,
+                 float* c_n, float* ws_pre, int* err, cudaStream_t s);
+
+}  // namespace cair

@@ -1,0 +1,199 @@
+// RNNEncoder.forward for one (bi)LSTM layer (neuroir/encoders/rnn_encoder.py:62-141).
+//
+// Two phases:
+//   1. pre-gates  P[n*L, dirs*4h] = X W_ih^T + (b_ih + b_hh)  - one GEMM over all time steps
+//      (X optionally gathered from an embedding table inside the GEMM);
+//   2. a persistent recurrence kernel: one CTA owns a tile of TS sequences of one direction
+//      for all of their steps; W_hh^T lives in shared memory (or is streamed from L2 when it
+//      does not fit), h/c state never leaves the SM, only h_t is stored to the memory bank.
+// Packed-sequence semantics without sorting: sequence s runs exactly len[s] steps, the
+// reverse direction starts at its own last token, bank rows t >= len[s] are written as zeros
+// (pad_packed_sequence + the zero pad of rnn_encoder.py:135-139).
+#include "common.cuh"
+
+namespace cair {
+
+constexpr int TS = 8;            // sequences per CTA
+constexpr int REC_THREADS = 256;
+
+__global__ void lstm_pack_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                                 const float* __restrict__ b_ih, const float* __restrict__ b_hh, int in, int h,
+                                 float* __restrict__ o_ih, float* __restrict__ o_bias,
+                                 float* __restrict__ o_hh_t) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int G = 4 * h;
+  if (i < (int64_t)G * in) o_ih[i] = w_ih[i];
+  if (i < G) o_bias[i] = b_ih[i] + b_hh[i];
+  if (i < (int64_t)G * h) {
+    int r = (int)(i / h), k = (int)(i % h);
+    o_hh_t[(int64_t)k * G + r] = w_hh[i];
+  }
+}
+
+int32_t lstm_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, int in, int h, LstmPack* out,
+                  cudaStream_t s) {
+  if (!fwd || !fwd->w_ih || !fwd->w_hh || !fwd->b_ih || !fwd->b_hh) return fail(CAIR_ERR_BAD_ARG, "lstm: null weights");
+  if (in <= 0 || h <= 0) return fail(CAIR_ERR_BAD_ARG, "lstm: bad sizes");
+  int dirs = rev ? 2 : 1, G = 4 * h;
+  out->in = in, out->h = h, out->dirs = dirs;
+  CAIR_CUDA(own.alloc(&out->w_ih, (size_t)dirs * G * in));
+  CAIR_CUDA(own.alloc(&out->bias, (size_t)dirs * G));
+  CAIR_CUDA(own.alloc(&out->w_hh_t, (size_t)dirs * G * h));
+  for (int d = 0; d < dirs; ++d) {
+    const cair_lstm_dir* w = d ? rev : fwd;
+    if (!w->w_ih || !w->w_hh || !w->b_ih || !w->b_hh) return fail(CAIR_ERR_BAD_ARG, "lstm: null weights");
+    int64_t n = (int64_t)G * (in > h ? in : h);
+    CAIR_LAUNCH(lstm_pack_kernel, (unsigned)((n + 255) / 256), 256, 0, s, w->w_ih, w->w_hh, w->b_ih, w->b_hh, in,
+                h, out->w_ih + (size_t)d * G * in, out->bias + (size_t)d * G, out->w_hh_t + (size_t)d * G * h);
+  }
+  return CAIR_OK;
+}
+
+size_t lstm_workspace_floats(const LstmPack& p, int64_t n, int L) { return (size_t)n * L * p.dirs * 4 * p.h; }
+
+// smem: [W_hh^T: h*G floats if WSMEM] [hprev: TS*hp] [c: TS*h] [gates: TS*G] ; hp = h rounded up to 4
+template <bool WSMEM>
+__global__ void __launch_bounds__(REC_THREADS) lstm_rec_kernel(const float* __restrict__ pre,
+                                                               const float* __restrict__ w_hh_t,
+                                                               const int64_t* __restrict__ len, int n, int L, int h,
+                                                               int dirs, float* __restrict__ out,
+                                                               float* __restrict__ h_n, float* __restrict__ c_n,
+                                                               int* err) {
+  extern __shared__ __align__(16) float smem[];
+  const int G = 4 * h, hp = (h + 3) & ~3;
+  const int dir = blockIdx.y;
+  const int s0 = blockIdx.x * TS;
+  const int tid = threadIdx.x;
+  float* wsm = smem;
+  float* hprev = smem + (WSMEM ? (size_t)h * G : 0);
+  float* cst = hprev + TS * hp;
+  float* gates = cst + TS * h;
+  __shared__ int slen[TS];
+  __shared__ int smaxlen;
+
+  const float* wt = w_hh_t + (size_t)dir * h * G;
+  if (WSMEM)
+    for (int i = tid; i < h * G; i += REC_THREADS) wsm[i] = wt[i];
+  const float* W = WSMEM ? wsm : wt;
+  for (int i = tid; i < TS * hp; i += REC_THREADS) hprev[i] = 0.f;
+  for (int i = tid; i < TS * h; i += REC_THREADS) cst[i] = 0.f;
+  if (tid < TS) {
+    int s = s0 + tid, l = 0;
+    if (s < n) {
+      int64_t ll = len[s];
+      if (ll < 1 || ll > L) {
+        atomicOr(err, ERRF_BAD_LENGTH);
+        ll = ll < 1 ? 1 : L;
+      }
+      l = (int)ll;
+    }
+    slen[tid] = l;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int m = 0;
+    for (int s = 0; s < TS; ++s) m = max(m, slen[s]);
+    smaxlen = m;
+  }
+  // zero the pad rows of the memory bank (this direction's half)
+  const int Hout = dirs * h;
+  for (int s = 0; s < TS; ++s) {
+    if (s0 + s >= n) break;
+    int npad = (L - slen[s]) * h;
+    float* o = out + ((size_t)(s0 + s) * L + slen[s]) * Hout + dir * h;
+    for (int i = tid; i < npad; i += REC_THREADS) o[(size_t)(i / h) * Hout + (i % h)] = 0.f;
+  }
+  __syncthreads();
+  const int maxlen = smaxlen;
+  const int PG = dirs * G;  // pre-gate row width
+
+  for (int step = 0; step < maxlen; ++step) {
+    // gate rows: r = tid, tid+256, ...
+    for (int r = tid; r < G; r += REC_THREADS) {
+      float acc[TS];
+#pragma unroll
+      for (int s = 0; s < TS; ++s) {
+        int l = slen[s];
+        float v = 0.f;
+        if (step < l) {
+          int t = dir ? l - 1 - step : step;
+          v = pre[((size_t)(s0 + s) * L + t) * PG + dir * G + r];
+        }
+        acc[s] = v;
+      }
+      int k = 0;
+      for (; k + 4 <= h; k += 4) {
+        float w0 = W[(size_t)(k + 0) * G + r], w1 = W[(size_t)(k + 1) * G + r];
+        float w2 = W[(size_t)(k + 2) * G + r], w3 = W[(size_t)(k + 3) * G + r];
+#pragma unroll
+        for (int s = 0; s < TS; ++s) {
+          float4 hv = *reinterpret_cast<const float4*>(&hprev[s * hp + k]);
+          acc[s] = fmaf(w0, hv.x, acc[s]);
+          acc[s] = fmaf(w1, hv.y, acc[s]);
+          acc[s] = fmaf(w2, hv.z, acc[s]);
+          acc[s] = fmaf(w3, hv.w, acc[s]);
+        }
+      }
+      for (; k < h; ++k) {
+        float w0 = W[(size_t)k * G + r];
+#pragma unroll
+        for (int s = 0; s < TS; ++s) acc[s] = fmaf(w0, hprev[s * hp + k], acc[s]);
+      }
+#pragma unroll
+      for (int s = 0; s < TS; ++s) gates[s * G + r] = acc[s];
+    }
+    __syncthreads();
+    for (int i = tid; i < TS * h; i += REC_THREADS) {
+      int s = i / h, u = i - s * h;
+      int l = slen[s];
+      if (step < l) {
+        const float* g = gates + s * G;
+        float ig = sigmoid_f(g[u]), fg = sigmoid_f(g[h + u]);
+        float gg = tanhf(g[2 * h + u]), og = sigmoid_f(g[3 * h + u]);
+        float c = fg * cst[i] + ig * gg;
+        float hv = og * tanhf(c);
+        cst[i] = c;
+        hprev[s * hp + u] = hv;
+        int t = dir ? l - 1 - step : step;
+        out[((size_t)(s0 + s) * L + t) * Hout + dir * h + u] = hv;
+      }
+    }
+    __syncthreads();
+  }
+  if (h_n || c_n)
+    for (int i = tid; i < TS * h; i += REC_THREADS) {
+      int s = i / h, u = i - s * h;
+      if (s0 + s >= n) continue;
+      if (h_n) h_n[((size_t)dir * n + s0 + s) * h + u] = hprev[s * hp + u];
+      if (c_n) c_n[((size_t)dir * n + s0 + s) * h + u] = cst[i];
+    }
+}
+
+int32_t lstm_run(const LstmPack& p, const GemmA& x, const int64_t* len, int n, int L, float* out, float* h_n,
+                 float* c_n, float* ws_pre, int* err, cudaStream_t s) {
+  if (n <= 0) return CAIR_OK;
+  const int G = 4 * p.h, PG = p.dirs * G;
+  CAIR_TRY(gemm_f32(x, p.w_ih, p.bias, ws_pre, PG, (int64_t)n * L, PG, p.in, ACT_NONE, s));
+  prof_mark("lstm_recurrence", s);
+  const int hp = (p.h + 3) & ~3;
+  size_t state = (size_t)(TS * hp + TS * p.h + TS * G) * sizeof(float);
+  size_t wbytes = (size_t)p.h * G * sizeof(float);
+  dim3 grid((n + TS - 1) / TS, p.dirs);
+  if (wbytes + state <= 200 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CAIR_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    CAIR_LAUNCH(lstm_rec_kernel<true>, grid, REC_THREADS, wbytes + state, s, ws_pre, p.w_hh_t, len, n, L, p.h,
+                p.dirs, out, h_n, c_n, err);
+  } else {
+    if (state > 48 * 1024)
+      CAIR_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)state));
+    CAIR_LAUNCH(lstm_rec_kernel<false>, grid, REC_THREADS, state, s, ws_pre, p.w_hh_t, len, n, L, p.h, p.dirs, out,
+                h_n, c_n, err);
+  }
+  return CAIR_OK;
+}
+
+}  // namespace cair

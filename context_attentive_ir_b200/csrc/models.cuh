@@ -1,0 +1,101 @@
+// Per-model state held by a cair_handle and the internal forward entry points.
+#pragma once
+#include "common.cuh"
+
+namespace cair {
+
+enum { CAIR_MODEL_ESM = 1, CAIR_MODEL_MT = 2, CAIR_MODEL_DRMM = 3, CAIR_MODEL_DUET = 4, CAIR_MODEL_CARS = 5 };
+
+int32_t embed_gather(const float* table, int V, int E, const int64_t* ids, int64_t T, float* out, int* err,
+                     cudaStream_t s);
+
+// ---- ESM ----
+struct EsmState {
+  int V = 0, E = 0;
+  float* table = nullptr;
+};
+int32_t esm_forward(const float* table, int V, int E, const int64_t* q, const int64_t* d, int N, int Lq, int Ld,
+                    int64_t pair_begin, int64_t pair_count, float* scores, int* err, cudaStream_t s);
+
+// ---- DRMM ----
+struct DrmmState {
+  cair_drmm_weights w{};  // pointers into handle-owned copies
+  int32_t* dbg_hist = nullptr;
+};
+int32_t drmm_forward(const cair_drmm_weights& w, const int64_t* q, const int64_t* d, int N, int Lq, int Ld,
+                     int64_t pair_begin, int64_t pair_count, float* scores, int32_t* hist_out, int* err,
+                     cudaStream_t s);
+
+// ---- Match-Tensor ----
+struct MtPack {
+  int C, nf, FP, FPP, M;
+  float* w7;    // [3][7][C][FPP]   merged conv weights of the C product channels, f fastest
+  float* wem;   // [3][7][FPP]      alpha * merged weights of the exact-match channel
+  float* bias;  // [FPP]
+  float* w1;    // [M][FPP]         1x1 conv
+  float* b1;    // [M]
+  float* wo;    // [M] + bo at [M]
+};
+struct MtState {
+  int V = 0, E = 0, F = 0, Hq = 0, Hd = 0, C = 0;
+  float* folded = nullptr;  // [V, F] = table W_p^T + b_p  (eval-mode fold of mtensor.py:77-90)
+  LstmPack enc_q{}, enc_d{};
+  float *wq = nullptr, *bq = nullptr, *wd = nullptr, *bd = nullptr;  // channel projections
+  MtPack pack{};
+  float *dbg_enc_q = nullptr, *dbg_enc_d = nullptr;
+};
+int32_t mt_create_state(Owned& own, const cair_mt_weights& w, MtState* st, cudaStream_t s);
+int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, const int64_t* d, const int64_t* dlen,
+                   int B, int N, int Lq, int Ld, int64_t pb, int64_t pc, float* scores, Arena& ws, int* err,
+                   cudaStream_t s, bool dry);
+
+// ---- DUET ----
+struct DuetState {
+  int V = 0, E = 0, nf = 0, pool = 0, Lq = 0, Ld = 0;
+  float* table = nullptr;
+  float *lconv_t = nullptr, *lconv_b = nullptr;  // [Ld][nf] transposed local conv1d weight, [nf]
+  float *lfc1_w = nullptr, *lfc1_b = nullptr, *lfc2_w = nullptr, *lfc2_b = nullptr, *lfc3_w = nullptr, *lfc3_b = nullptr;
+  float *cq_w = nullptr, *cq_b = nullptr, *cd1_w = nullptr, *cd1_b = nullptr;  // [nf][3*E] (tap-major K)
+  float *cd2_w = nullptr, *cd2_b = nullptr;
+  float *fc1_w = nullptr, *fc1_b = nullptr, *fc2_w = nullptr, *fc2_b = nullptr, *fc3_w = nullptr, *fc3_b = nullptr,
+        *fc4_w = nullptr, *fc4_b = nullptr;
+};
+int32_t duet_create_state(Owned& own, const cair_duet_weights& w, DuetState* st, cudaStream_t s);
+int32_t duet_forward(const DuetState& st, const int64_t* q, const int64_t* d, int B, int N, int Lq, int Ld,
+                     int64_t pb, int64_t pc, float* scores, Arena& ws, int* err, cudaStream_t s, bool dry);
+
+// ---- CARS ----
+struct AttnPack {
+  int H = 0;
+  float *w0 = nullptr, *b0 = nullptr, *w3 = nullptr, *b3 = nullptr;
+};
+struct CarsState {
+  int V = 0, E = 0, Hq = 0, Hd = 0, Hsq = 0, Hsd = 0;
+  int rd[3] = {0, 0, 0}, pool = 2;
+  float* table = nullptr;
+  LstmPack enc_q{}, enc_d{}, sess_q{}, sess_d{};
+  AttnPack q_attn, d_attn, click_attn, sq_inner, sd_inner;
+  float *sqa_w = nullptr, *sqa_b = nullptr, *sda_w = nullptr, *sda_b = nullptr;  // session_{query,doc}_attn
+  float *qp_w = nullptr, *qp_b = nullptr;  // q_projection
+  float* sess_proj = nullptr;              // shared_session_projector + private_session_projector1 [Hd, Hsq+Hsd]
+  float *rk_w[3] = {nullptr, nullptr, nullptr}, *rk_b[3] = {nullptr, nullptr, nullptr};
+};
+struct CarsIO {
+  const int64_t *q, *qlen, *d, *dlen;
+  const float* labels;
+  float *scores, *pooled_q, *pooled_d, *clicks, *sess_q_attn, *sess_d_attn;
+};
+int32_t cars_create_state(Owned& own, const cair_cars_weights& w, CarsState* st, cudaStream_t s);
+int32_t cars_forward(const CarsState& st, const CarsIO& io, int B, int S, int N, int Lq, int Ld, int sb, int sc,
+                     Arena& ws, int* err, cudaStream_t s, bool dry);
+
+// helper shared by the model files
+template <typename T>
+inline int32_t dev_copy(Owned& own, const T* src, size_t n, T** dst, cudaStream_t s) {
+  if (!src) return fail(CAIR_ERR_BAD_ARG, "null weight pointer");
+  CAIR_CUDA(own.alloc(dst, n));
+  CAIR_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+  return CAIR_OK;
+}
+
+}  // namespace cair

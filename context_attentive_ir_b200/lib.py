@@ -1,0 +1,74 @@
+"""Loader and ctypes prototypes of libcair.so (the C ABI declared in include/cair.h).
+
+There is no CPU or PyTorch fallback: if the CUDA library is missing or a call fails, this
+module raises."""
+import ctypes as C
+import os
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libcair.so')
+_lib = None
+
+vp = C.c_void_p
+i32 = C.c_int32
+i64 = C.c_int64
+
+# name -> (restype, argtypes); every symbol include/cair.h declares
+PROTOTYPES = {
+    'cair_version': (i32, []),
+    'cair_last_error': (C.c_char_p, []),
+    'cair_launch_count': (i64, []),
+    'cair_destroy': (i32, [vp]),
+    'cair_poll_error': (i32, [vp, vp]),
+    'cair_profile_enable': (i32, [vp, i32]),
+    'cair_profile_read': (i32, [vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_float), i32, C.POINTER(i32)]),
+    'cair_embed_gather': (i32, [vp, i32, i32, vp, i64, vp, vp]),
+    'cair_lstm_forward': (i32, [vp, vp, i32, i32, i32, i32, C.POINTER(_abi.LstmDir), C.POINTER(_abi.LstmDir),
+                                vp, vp, vp, vp]),
+    'cair_esm_create': (i32, [C.POINTER(_abi.EsmWeights), i32, C.POINTER(vp)]),
+    'cair_mt_create': (i32, [C.POINTER(_abi.MtWeights), i32, C.POINTER(vp)]),
+    'cair_mt_set_debug': (i32, [vp, vp, vp]),
+    'cair_drmm_create': (i32, [C.POINTER(_abi.DrmmWeights), i32, C.POINTER(vp)]),
+    'cair_drmm_set_debug': (i32, [vp, vp]),
+    'cair_duet_create': (i32, [C.POINTER(_abi.DuetWeights), i32, C.POINTER(vp)]),
+    'cair_ranker_workspace_bytes': (i32, [vp, i32, i32, i32, i32, C.POINTER(C.c_size_t)]),
+    'cair_ranker_forward': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, vp, vp, C.c_size_t, vp]),
+    'cair_ranker_forward_host': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]),
+    'cair_cars_create': (i32, [C.POINTER(_abi.CarsWeights), i32, C.POINTER(vp)]),
+    'cair_cars_workspace_bytes': (i32, [vp, i32, i32, i32, i32, i32, C.POINTER(C.c_size_t)]),
+    'cair_cars_forward': (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32,
+                                vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]),
+}
+
+
+class CairError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__('%s: %s' % (_abi.ERR_NAMES.get(code, code), text))
+        self.code = code
+
+
+def load():
+    """dlopen libcair.so (built in-tree by __graft_entry__.build()); raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError('%s not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                               '(or `make -C context_attentive_ir_b200/csrc`); there is no fallback path' % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise CairError(rc, (load().cair_last_error() or b'').decode())
+
+
+def launch_count():
+    return int(load().cair_launch_count())

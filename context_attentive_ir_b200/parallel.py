@@ -1,0 +1,81 @@
+"""Doc-parallel sharding of the scoring path across the GPUs of one box.
+
+One process per GPU (torchrun); weights replicated; the flattened (query, doc) pairs p = b*N + n
+are cut into contiguous, equal slices; every rank scores its slice with no data-path collective;
+ONE all-gather of the per-pair fp32 scores (NCCL over NVLink on GPUs, gloo in the CPU tests)
+gives every rank the full [B, N] matrix for the softmax / pairwise loss / MAP that need all N
+candidates of a query (neuroir/models/ranker.py:87,258).  CARS shards by session instead
+(sessions are independent; multitask/cars.py has no cross-session op except the click-mask width,
+which libcair always computes over the replicated labels).
+"""
+import torch
+import torch.distributed as dist
+
+
+def pair_slice(rank, world, total):
+    """Contiguous slice [begin, begin+count) of `total` units for `rank`; slices are ceil(total/world)
+    long (balanced even when N=10, world=8); trailing ranks may get a short or empty slice."""
+    per = (total + world - 1) // world
+    begin = min(rank * per, total)
+    return begin, min(per, total - begin)
+
+
+def gather_scores(local, total, group=None):
+    """local: 1-D tensor with this rank's slice (count may differ on the last ranks).
+    Returns the 1-D tensor of all `total` scores on every rank (one all_gather)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local[:total]
+    per = (total + world - 1) // world
+    send = local.new_zeros(per)
+    send[:local.numel()] = local
+    recv = local.new_empty(per * world)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return recv[:total]
+
+
+class ShardedRanker:
+    """Wraps a ranker network: each rank scores its pair slice, one all-gather assembles [B, N].
+    `score_slice(q, qlen, d, dlen, begin, count) -> [B, N] tensor with the slice filled` defaults to the
+    network's own pair_slice forward; tests inject a CPU scorer to exercise the plumbing under gloo."""
+
+    def __init__(self, network, score_slice=None, group=None):
+        self.network = network
+        self.group = group
+        self.score_slice = score_slice or (lambda q, ql, d, dl, b, c: network(q, ql, d, dl, pair_slice=(b, c)))
+
+    def __call__(self, q, qlen, d, dlen):
+        B, N = d.shape[0], d.shape[1]
+        total = B * N
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        begin, count = pair_slice(rank, world, total)
+        full = self.score_slice(q, qlen, d, dlen, begin, count)
+        local = full.reshape(-1)[begin:begin + count].contiguous()
+        return gather_scores(local, total, self.group).reshape(B, N)
+
+
+class ShardedCars:
+    """Session-sharded CARS scoring: rank r scores sessions [begin, begin+count), one all-gather of scores."""
+
+    def __init__(self, network, score_slice=None, group=None):
+        self.network = network
+        self.group = group
+        self.score_slice = score_slice or (
+            lambda q, ql, d, dl, lab, b, c: network.score(q, ql, d, dl, lab, session_slice=(b, c))['scores'])
+
+    def __call__(self, q, qlen, d, dlen, labels):
+        B, S, N = d.shape[0], d.shape[1], d.shape[2]
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        begin, count = pair_slice(rank, world, B)
+        full = self.score_slice(q, qlen, d, dlen, labels, begin, count)
+        local = full.reshape(B, -1)[begin:begin + count].reshape(-1).contiguous()
+        per = (B + world - 1) // world
+        if world == 1:
+            return full
+        send = local.new_zeros(per * S * N)
+        send[:local.numel()] = local
+        recv = local.new_empty(per * S * N * world)
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        return recv[:B * S * N].reshape(B, S, N)

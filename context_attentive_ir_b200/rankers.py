@@ -1,0 +1,345 @@
+"""Host-side mirror of the reference's ranker networks (neuroir/rankers/*.py).
+
+Same constructor contract (an argparse.Namespace from neuroir.config.get_model_args plus
+src_vocab_size), same call contract `network(queries, que_len, documents, doc_len) ->
+FloatTensor[B, N]` (neuroir/models/ranker.py:213,257), same parameter names / shapes /
+initialisers as the reference modules, so reference state_dicts load by key.
+The arithmetic is not here: forward() hands device pointers to libcair.so.  Inputs must be CUDA
+tensors; there is no CPU or eager-PyTorch fallback.  Scoring only (eval / no_grad): the backward
+pass is the first "next" row of the scope table.
+"""
+import ctypes as C
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import _abi, lib
+
+PAD = 0
+
+
+class Embeddings(nn.Module):
+    """Parameter container mirroring neuroir/modules/embeddings.py:124-196 (word LUT only):
+    key `make_embedding.emb_luts.0.weight`, PAD row zero."""
+
+    def __init__(self, word_vec_size, word_vocab_size, word_padding_idx=PAD, fix_word_vecs=False):
+        super().__init__()
+        self.word_vec_size = word_vec_size
+        self.embedding_size = word_vec_size
+        luts = nn.ModuleList([nn.Embedding(word_vocab_size, word_vec_size, padding_idx=word_padding_idx)])
+        self.make_embedding = nn.Sequential(OrderedDict([('emb_luts', luts)]))
+        if fix_word_vecs:
+            self.word_lut.weight.requires_grad = False
+
+    @property
+    def word_lut(self):
+        return self.make_embedding[0][0]
+
+    @property
+    def emb_luts(self):
+        return self.make_embedding[0]
+
+    def init_word_vectors(self, vocabulary, embeddings_index, fixed):
+        """Same contract as embeddings.py:216-229: rows of words absent from the index become zero."""
+        pretrained = torch.zeros(len(vocabulary), self.word_vec_size)
+        for i in range(len(vocabulary)):
+            tok = vocabulary.ind2tok[i]
+            if tok in embeddings_index:
+                pretrained[i] = embeddings_index[tok]
+        self.word_lut.weight.data.copy_(pretrained)
+        if fixed:
+            self.word_lut.weight.requires_grad = False
+
+    def forward(self, source):  # [B, L, 1] ids -> [B, L, E]; only used by callers outside the fused path
+        ids = source.squeeze(-1).contiguous()
+        w = self.word_lut.weight
+        if not ids.is_cuda:
+            raise RuntimeError('context_attentive_ir_b200 runs on CUDA tensors only')
+        out = torch.empty(ids.shape + (w.shape[1],), device=ids.device, dtype=torch.float32)
+        lib.check(lib.load().cair_embed_gather(w.data_ptr(), w.shape[0], w.shape[1], ids.data_ptr(), ids.numel(),
+                                               out.data_ptr(), torch.cuda.current_stream(ids.device).cuda_stream))
+        return out
+
+
+class RNNEncoder(nn.Module):
+    """Parameter container mirroring neuroir/encoders/rnn_encoder.py:25-60 (keys `rnns.<i>.*`)."""
+
+    def __init__(self, rnn_type, input_size, bidirectional, num_layers, hidden_size, dropout=0.0):
+        super().__init__()
+        dirs = 2 if bidirectional else 1
+        assert hidden_size % dirs == 0
+        self.rnn_type, self.bidirectional, self.nlayers = rnn_type, bidirectional, num_layers
+        self.hidden_size = hidden_size // dirs
+        self.rnns = nn.ModuleList()
+        for i in range(num_layers):
+            in_sz = input_size if i == 0 else self.hidden_size * dirs
+            self.rnns.append(getattr(nn, rnn_type)(input_size=in_sz, hidden_size=self.hidden_size, num_layers=1,
+                                                    bidirectional=bidirectional, batch_first=True))
+        self.dropout = nn.Dropout(dropout)
+
+
+def _ptr_getter(module, keep):
+    sd = dict(module.named_parameters())
+    sd.update(dict(module.named_buffers()))
+
+    def get(key):
+        t = sd[key]
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.detach().float().contiguous()
+            keep.append(t)
+        return C.cast(t.data_ptr(), _abi.f32p)
+    return get
+
+
+class _CairModule(nn.Module):
+    """Owns the libcair handle; rebuilds it when a parameter changed (version / storage / device)."""
+    MODEL = None
+
+    def _cfg(self):
+        raise NotImplementedError
+
+    def _create(self, weights, device, out):
+        raise NotImplementedError
+
+    def _state_key(self):
+        return tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters())
+
+    def _handle_for(self, device):
+        key = (self._state_key(), device.index)
+        h = self.__dict__.get('_cair_handle')
+        if h is not None and self.__dict__.get('_cair_key') == key:
+            return h
+        self._release()
+        if any(not p.is_cuda for p in self.parameters()):
+            raise RuntimeError('%s parameters must be on a CUDA device (call .cuda()); no CPU path exists'
+                               % type(self).__name__)
+        keep = []
+        w = _abi.PACKERS[self.MODEL](self._cfg(), _ptr_getter(self, keep))
+        out = C.c_void_p()
+        torch.cuda.synchronize(device)  # weights may still be in flight on another stream
+        lib.check(self._create(C.byref(w), device.index, C.byref(out)))
+        self.__dict__['_cair_handle'] = out
+        self.__dict__['_cair_key'] = key
+        self.__dict__['_cair_ws'] = None
+        return out
+
+    def _release(self):
+        h = self.__dict__.get('_cair_handle')
+        if h is not None:
+            lib.load().cair_destroy(h)
+            self.__dict__['_cair_handle'] = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _workspace(self, nbytes, device):
+        ws = self.__dict__.get('_cair_ws')
+        if ws is None or ws.numel() < nbytes or ws.device != device:
+            ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+            self.__dict__['_cair_ws'] = ws
+        return ws
+
+    @staticmethod
+    def _ids(t, name):
+        if not torch.is_tensor(t):
+            t = torch.as_tensor(t)
+        if not t.is_cuda:
+            raise RuntimeError('%s must be a CUDA tensor (context_attentive_ir_b200 has no CPU path)' % name)
+        return t.to(torch.int64).contiguous()
+
+
+class _Ranker(_CairModule):
+    def forward(self, batch_queries, query_len, batch_docs, doc_len, pair_slice=None):
+        """scores[B, N] (fp32, no softmax).  pair_slice=(begin, count) scores only that contiguous
+        slice of the flattened pairs (doc-parallel sharding); the rest of the output is left zero."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError('training through libcair is not implemented yet (scoring path only); '
+                                      'call under torch.no_grad() / .eval()')
+        assert batch_queries.shape[0] == batch_docs.shape[0]  # rankers/*.py, e.g. mtensor.py:71
+        q = self._ids(batch_queries, 'batch_queries')
+        d = self._ids(batch_docs, 'batch_docs')
+        ql = self._ids(query_len, 'query_len').to(q.device)
+        dl = self._ids(doc_len, 'doc_len').to(q.device).reshape(d.shape[0], d.shape[1])
+        B, Lq = q.shape
+        _, N, Ld = d.shape
+        dev = q.device
+        L = lib.load()
+        h = self._handle_for(dev)
+        nbytes = C.c_size_t()
+        lib.check(L.cair_ranker_workspace_bytes(h, B, N, Lq, Ld, C.byref(nbytes)))
+        ws = self._workspace(nbytes.value, dev)
+        begin, count = (0, B * N) if pair_slice is None else pair_slice
+        scores = torch.zeros(B, N, dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        lib.check(L.cair_ranker_forward(h, q.data_ptr(), ql.data_ptr(), d.data_ptr(), dl.data_ptr(), B, N, Lq, Ld,
+                                        begin, count, scores.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        return scores
+
+    def forward_host(self, q, qlen, d, dlen, out=None, device=None):
+        """End-to-end entry point on HOST tensors (pinned recommended): ids are copied host->device,
+        scored, and the scores copied back; returns a CPU tensor.  Raises on bad token ids / lengths."""
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        B, Lq = q.shape
+        _, N, Ld = d.shape
+        if out is None:
+            out = torch.empty(B, N, dtype=torch.float32).pin_memory()
+        L = lib.load()
+        h = self._handle_for(dev)
+        lib.check(L.cair_ranker_forward_host(h, q.data_ptr(), qlen.data_ptr(), d.data_ptr(), dlen.data_ptr(),
+                                             B, N, Lq, Ld, out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+        return out
+
+    def poll_error(self):
+        h = self.__dict__.get('_cair_handle')
+        if h is not None:
+            lib.check(lib.load().cair_poll_error(h, torch.cuda.current_stream().cuda_stream))
+
+
+class ESM(_Ranker):
+    """neuroir/rankers/esm.py:11-45."""
+    MODEL = 'esm'
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.word_embeddings = Embeddings(args.emsize, args.src_vocab_size, PAD)
+
+    def _cfg(self):
+        return dict(src_vocab_size=self.args.src_vocab_size, emsize=self.args.emsize)
+
+    def _create(self, w, device, out):
+        return lib.load().cair_esm_create(w, device, out)
+
+
+class ExactMatchChannel(nn.Module):
+    """neuroir/rankers/mtensor.py:134-142: one learnable scalar, U(0,1) init."""
+
+    def __init__(self):
+        super().__init__()
+        self.alpha = nn.Parameter(torch.empty(1))
+        nn.init.uniform_(self.alpha)
+
+
+class MatchTensor(_Ranker):
+    """neuroir/rankers/mtensor.py:24-131."""
+    MODEL = 'match_tensor'
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.word_embeddings = Embeddings(args.emsize, args.src_vocab_size, PAD)
+        self.emb_drop = nn.Dropout(p=args.dropout_emb)
+        self.linear_projection = nn.Linear(args.emsize, args.featsize)
+        self.query_encoder = RNNEncoder(args.rnn_type, args.featsize, args.bidirection, args.nlayers,
+                                        args.nhid_query, args.dropout_rnn)
+        self.document_encoder = RNNEncoder(args.rnn_type, args.featsize, args.bidirection, args.nlayers,
+                                           args.nhid_doc, args.dropout_rnn)
+        self.query_projection = nn.Linear(args.nhid_query, args.nchannels)
+        self.document_projection = nn.Linear(args.nhid_doc, args.nchannels)
+        self.exact_match_channel = ExactMatchChannel()
+        self.conv1 = nn.Conv2d(args.nchannels + 1, args.nfilters, (3, 3), padding=1)
+        self.conv2 = nn.Conv2d(args.nchannels + 1, args.nfilters, (3, 5), padding=(1, 2))
+        self.conv3 = nn.Conv2d(args.nchannels + 1, args.nfilters, (3, 7), padding=(1, 3))
+        self.conv = nn.Conv2d(args.nfilters * 3, args.match_filter_size, (1, 1))
+        self.output = nn.Linear(args.match_filter_size, 1)
+        if args.nlayers != 1:
+            raise NotImplementedError('libcair implements single-layer encoders (neuroir/hyparam.py:88-100 uses 1)')
+
+    def _cfg(self):
+        a = self.args
+        return dict(src_vocab_size=a.src_vocab_size, emsize=a.emsize, featsize=a.featsize, nhid_query=a.nhid_query,
+                    nhid_doc=a.nhid_doc, nchannels=a.nchannels, nfilters=a.nfilters,
+                    match_filter_size=a.match_filter_size, rnn_type=a.rnn_type, bidirection=a.bidirection)
+
+    def _create(self, w, device, out):
+        return lib.load().cair_mt_create(w, device, out)
+
+
+class GatingNetwork(nn.Module):
+    """neuroir/rankers/drmm.py:87-93."""
+
+    def __init__(self, emsize):
+        super().__init__()
+        self.weight = nn.Linear(emsize, 1)
+
+
+class DRMM(_Ranker):
+    """neuroir/rankers/drmm.py:10-84."""
+    MODEL = 'drmm'
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.word_embeddings = Embeddings(args.emsize, args.src_vocab_size, PAD)
+        self.emb_drop = nn.Dropout(p=args.dropout_emb)
+        self.nbins = args.nbins
+        self.bins = [-1.0, -0.5, 0, 0.5, 1.0, 1.0]
+        self.gating_network = GatingNetwork(args.emsize)
+        self.ffnn = nn.Sequential(nn.Linear(self.nbins, 1), nn.Linear(1, 1))
+        self.output = nn.Linear(1, 1)
+
+    def _cfg(self):
+        return dict(src_vocab_size=self.args.src_vocab_size, emsize=self.args.emsize, nbins=self.nbins)
+
+    def _create(self, w, device, out):
+        return lib.load().cair_drmm_create(w, device, out)
+
+
+class LocalModel(nn.Module):
+    """neuroir/rankers/duet.py:62-75."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.conv1d = nn.Conv1d(args.max_doc_len, args.nfilters, args.local_filter_size)
+        self.drop = nn.Dropout(args.dropout)
+        self.fc1 = nn.Linear(args.max_query_len, 1)
+        self.fc2 = nn.Linear(args.nfilters, args.nfilters)
+        self.fc3 = nn.Linear(args.nfilters, 1)
+
+
+class DistributedModel(nn.Module):
+    """neuroir/rankers/duet.py:124-146."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.conv_q = nn.Conv1d(args.emsize, args.nfilters, args.dist_filter_size)
+        self.conv_d1 = nn.Conv1d(args.emsize, args.nfilters, args.dist_filter_size)
+        self.conv_d2 = nn.Conv1d(args.nfilters, args.nfilters, 1)
+        self.pool_size = args.pool_size
+        self.dropout = nn.Dropout(args.dropout)
+        self.fc1 = nn.Linear(args.nfilters, args.nfilters)
+        self.fc2 = nn.Linear(args.max_doc_len - args.pool_size - 1, 1)
+        self.fc3 = nn.Linear(args.nfilters, args.nfilters)
+        self.fc4 = nn.Linear(args.nfilters, 1)
+
+
+class DUET(_Ranker):
+    """neuroir/rankers/duet.py:9-59."""
+    MODEL = 'duet'
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.use_word = args.use_word
+        if not self.use_word:
+            raise TypeError('Non-word inputs are not supported!')  # duet.py:23
+        self.word_embeddings = Embeddings(args.emsize, args.src_vocab_size, PAD)
+        self.emb_drop = nn.Dropout(p=args.dropout_emb)
+        self.local_model = LocalModel(args)
+        self.distributed_model = DistributedModel(args)
+
+    def _cfg(self):
+        a = self.args
+        return dict(src_vocab_size=a.src_vocab_size, emsize=a.emsize, nfilters=a.nfilters,
+                    local_filter_size=a.local_filter_size, dist_filter_size=a.dist_filter_size,
+                    pool_size=a.pool_size, max_query_len=a.max_query_len, max_doc_len=a.max_doc_len)
+
+    def _create(self, w, device, out):
+        return lib.load().cair_duet_create(w, device, out)
+
+
+RANKERS = {'ESM': ESM, 'MATCH_TENSOR': MatchTensor, 'DRMM': DRMM, 'DUET': DUET}

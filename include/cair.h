@@ -42,6 +42,12 @@ extern "C" {
 
 #define CAIR_VERSION 100 /* 0.1.0 */
 
+#if defined(__GNUC__)
+#define CAIR_API __attribute__((visibility("default")))
+#else
+#define CAIR_API
+#endif
+
 enum {
   CAIR_OK = 0,
   CAIR_ERR_BAD_ARG = -1,     /* null pointer, negative size                              */
@@ -55,11 +61,24 @@ enum { CAIR_RNN_LSTM = 0, CAIR_RNN_GRU = 1 };
 
 typedef struct cair_handle cair_handle; /* opaque */
 
-int32_t cair_version(void);
-const char* cair_last_error(void);
+CAIR_API int32_t cair_version(void);
+CAIR_API const char* cair_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
-int64_t cair_launch_count(void);
-int32_t cair_destroy(cair_handle* h);
+CAIR_API int64_t cair_launch_count(void);
+CAIR_API int32_t cair_destroy(cair_handle* h);
+/* Kernels never trap on bad input: token ids outside [0, vocab) (nn.Embedding raises IndexError,
+ * neuroir/modules/embeddings.py:165) and lengths outside [1, L] (pack_padded_sequence raises,
+ * neuroir/encoders/rnn_encoder.py:73) set a device flag instead.  This call synchronises `stream`,
+ * returns CAIR_ERR_BAD_ARG if the flag was set since the last poll, and clears it.
+ * The *_forward_host entry points poll before returning. */
+CAIR_API int32_t cair_poll_error(cair_handle* h, void* stream);
+
+/* Stage timing for bench.py's roofline: when enabled, *_forward records CUDA events on the launching
+ * stream between its stages (a few events per call, no synchronisation).  cair_profile_read waits
+ * for the last recorded call and returns the stage durations in ms and their comma-joined names. */
+CAIR_API int32_t cair_profile_enable(cair_handle* h, int32_t on);
+CAIR_API int32_t cair_profile_read(cair_handle* h, char* names, size_t names_bytes, float* ms,
+                                   int32_t capacity, int32_t* count);
 
 /* ---- shared weight fragments ------------------------------------------------------------- */
 
@@ -89,14 +108,14 @@ typedef struct {
 
 /* out[t,:] = table[ids[t],:]   (neuroir/modules/embeddings.py:243-252 + util_class.py:42-53).
  * ids [T] int64, table [V,E] fp32, out [T,E] fp32. */
-int32_t cair_embed_gather(const float* table, int32_t V, int32_t E, const int64_t* ids, int64_t T,
+CAIR_API int32_t cair_embed_gather(const float* table, int32_t V, int32_t E, const int64_t* ids, int64_t T,
                           float* out, void* stream);
 
 /* RNNEncoder.forward with lengths (neuroir/encoders/rnn_encoder.py:62-141), one layer LSTM:
  * x [n,L,in], len [n] int64 -> out [n,L,dirs*h], zeros at t >= len; reverse direction starts at
  * each sequence's own last token.  rev may be NULL (unidirectional).
  * h_n/c_n [dirs,n,h] optional (NULL to skip). */
-int32_t cair_lstm_forward(const float* x, const int64_t* len, int32_t n, int32_t L, int32_t in,
+CAIR_API int32_t cair_lstm_forward(const float* x, const int64_t* len, int32_t n, int32_t L, int32_t in,
                           int32_t h, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, float* out,
                           float* h_n, float* c_n, void* stream);
 
@@ -106,7 +125,7 @@ typedef struct {
   const float* table; /* word_embeddings.make_embedding.emb_luts.0.weight [V,E] */
 } cair_esm_weights;
 
-int32_t cair_esm_create(const cair_esm_weights* w, int32_t device, cair_handle** out);
+CAIR_API int32_t cair_esm_create(const cair_esm_weights* w, int32_t device, cair_handle** out);
 
 /* ---- Match-Tensor (neuroir/rankers/mtensor.py:27-60 ctor, :62-131 forward, :134-158 exact match) */
 typedef struct {
@@ -123,10 +142,10 @@ typedef struct {
   cair_linear output;              /* w [1,mfs], b [1] */
 } cair_mt_weights;
 
-int32_t cair_mt_create(const cair_mt_weights* w, int32_t device, cair_handle** out);
+CAIR_API int32_t cair_mt_create(const cair_mt_weights* w, int32_t device, cair_handle** out);
 /* Stage outputs for parity tests (any may be NULL): encoder memory banks
  * enc_q [B,Lq,Hq], enc_d [B*N,Ld,Hd] as RNNEncoder returns them (mtensor.py:93-94). */
-int32_t cair_mt_set_debug(cair_handle* h, float* enc_q, float* enc_d);
+CAIR_API int32_t cair_mt_set_debug(cair_handle* h, float* enc_q, float* enc_d);
 
 /* ---- DRMM (neuroir/rankers/drmm.py:13-27 ctor, :29-84 forward, :87-98 gating) -------------- */
 typedef struct {
@@ -138,9 +157,9 @@ typedef struct {
   cair_linear output; /* output [1,1] */
 } cair_drmm_weights;
 
-int32_t cair_drmm_create(const cair_drmm_weights* w, int32_t device, cair_handle** out);
+CAIR_API int32_t cair_drmm_create(const cair_drmm_weights* w, int32_t device, cair_handle** out);
 /* Optional parity output: hist [B*N,Lq,5] int32 (numpy.histogram counts, drmm.py:71-75). */
-int32_t cair_drmm_set_debug(cair_handle* h, int32_t* hist);
+CAIR_API int32_t cair_drmm_set_debug(cair_handle* h, int32_t* hist);
 
 /* ---- DUET (neuroir/rankers/duet.py:28-59, LocalModel :65-121, DistributedModel :127-208) --- */
 typedef struct {
@@ -160,7 +179,7 @@ typedef struct {
   cair_linear dist_fc4;     /* [1,nf]    */
 } cair_duet_weights;
 
-int32_t cair_duet_create(const cair_duet_weights* w, int32_t device, cair_handle** out);
+CAIR_API int32_t cair_duet_create(const cair_duet_weights* w, int32_t device, cair_handle** out);
 
 /* ---- forward for the four stand-alone rankers ---------------------------------------------
  * network(queries, que_len, documents, doc_len) (neuroir/models/ranker.py:213,257):
@@ -168,13 +187,13 @@ int32_t cair_duet_create(const cair_duet_weights* w, int32_t device, cair_handle
  * pair_begin/pair_count select the contiguous slice of the flattened pairs p=b*N+n this rank
  * scores (doc-parallel sharding); scores is still indexed [B,N] and only
  * the slice is written.  Use 0, B*N for everything. */
-int32_t cair_ranker_workspace_bytes(cair_handle* h, int32_t B, int32_t N, int32_t Lq, int32_t Ld,
+CAIR_API int32_t cair_ranker_workspace_bytes(cair_handle* h, int32_t B, int32_t N, int32_t Lq, int32_t Ld,
                                     size_t* bytes);
-int32_t cair_ranker_forward(cair_handle* h, const int64_t* q, const int64_t* qlen, const int64_t* d,
+CAIR_API int32_t cair_ranker_forward(cair_handle* h, const int64_t* q, const int64_t* qlen, const int64_t* d,
                             const int64_t* dlen, int32_t B, int32_t N, int32_t Lq, int32_t Ld,
                             int64_t pair_begin, int64_t pair_count, float* scores, void* workspace,
                             size_t workspace_bytes, void* stream);
-int32_t cair_ranker_forward_host(cair_handle* h, const int64_t* q, const int64_t* qlen,
+CAIR_API int32_t cair_ranker_forward_host(cair_handle* h, const int64_t* q, const int64_t* qlen,
                                  const int64_t* d, const int64_t* dlen, int32_t B, int32_t N,
                                  int32_t Lq, int32_t Ld, float* scores, void* stream);
 
@@ -195,17 +214,22 @@ typedef struct {
   cair_linear ranknet[3];                                   /* ranknet._linear_layers.{0,1,2} */
 } cair_cars_weights;
 
-int32_t cair_cars_create(const cair_cars_weights* w, int32_t device, cair_handle** out);
-int32_t cair_cars_workspace_bytes(cair_handle* h, int32_t B, int32_t S, int32_t N, int32_t Lq,
+CAIR_API int32_t cair_cars_create(const cair_cars_weights* w, int32_t device, cair_handle** out);
+CAIR_API int32_t cair_cars_workspace_bytes(cair_handle* h, int32_t B, int32_t S, int32_t N, int32_t Lq,
                                   int32_t Ld, size_t* bytes);
 /* encode + rank_document (multitask.py:264-269):
  * q [B,S,Lq], qlen [B,S], d [B,S,N,Ld], dlen [B,S,N] int64, labels [B,S,N] fp32
  * -> scores [B,S,N]; optional outputs (NULL to skip): pooled_q [B,S,Hq], pooled_d [B,S,N,Hd],
- * clicks [B,S,Hd], sess_q_attn [B,S,Hsq], sess_d_attn [B,S,Hsd]. */
-int32_t cair_cars_forward(cair_handle* h, const int64_t* q, const int64_t* qlen, const int64_t* d,
+ * clicks [B,S,Hd], sess_q_attn [B,S,Hsq], sess_d_attn [B,S,Hsd].
+ * session_begin/session_count select the sessions this rank computes (sessions are independent
+ * except for the batch-global click-mask width, which is always taken over ALL B*S label rows -
+ * SURVEY.md section 8e / App. B4); all tensors are indexed [B,...] and only the slice is written.
+ * workspace_bytes is sized for all B sessions by cair_cars_workspace_bytes. */
+CAIR_API int32_t cair_cars_forward(cair_handle* h, const int64_t* q, const int64_t* qlen, const int64_t* d,
                           const int64_t* dlen, const float* labels, int32_t B, int32_t S, int32_t N,
-                          int32_t Lq, int32_t Ld, float* scores, float* pooled_q, float* pooled_d,
-                          float* clicks, float* sess_q_attn, float* sess_d_attn, void* workspace,
+                          int32_t Lq, int32_t Ld, int32_t session_begin, int32_t session_count,
+                          float* scores, float* pooled_q, float* pooled_d, float* clicks,
+                          float* sess_q_attn, float* sess_d_attn, void* workspace,
                           size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

@@ -208,28 +208,35 @@ ORA_API int cair_oracle_mt(const cair_mt_weights* w, const int64_t* q, const int
     for (int i = 0; i < Lq; ++i)
       for (int j = 0; j < Ld; ++j)
         mt[((size_t)C * Lq + i) * Ld + j] = (q[b * Lq + i] == d[p * Ld + j]) ? alpha : 0.0f;
-    /* :122-125 three same-padded convs (cross-correlation) + ReLU */
+    /* :122-125 three same-padded convs (cross-correlation) + ReLU.  Same (c, a, bb) summation order
+     * per output cell as a naive per-cell loop, arranged with j innermost so the compiler vectorises. */
+    double* accb = (double*)malloc(sizeof(double) * (size_t)Lq * Ld);
     for (int k = 0; k < 3; ++k) {
       int kw = 3 + 2 * k, pw = 1 + k;
-      for (int f = 0; f < nf; ++f)
-        for (int i = 0; i < Lq; ++i)
-          for (int j = 0; j < Ld; ++j) {
-            double s = convs[k]->b[f];
-            for (int c = 0; c < C1; ++c)
-              for (int a = 0; a < 3; ++a) {
+      for (int f = 0; f < nf; ++f) {
+        for (int x = 0; x < Lq * Ld; ++x) accb[x] = convs[k]->b[f];
+        for (int c = 0; c < C1; ++c)
+          for (int a = 0; a < 3; ++a)
+            for (int bb = 0; bb < kw; ++bb) {
+              const double wv = convs[k]->w[(((size_t)f * C1 + c) * 3 + a) * kw + bb];
+              int jlo = pw - bb > 0 ? pw - bb : 0;
+              int jhi = Ld + pw - bb < Ld ? Ld + pw - bb : Ld;
+              for (int i = 0; i < Lq; ++i) {
                 int ii = i + a - 1;
                 if (ii < 0 || ii >= Lq) continue;
-                for (int bb = 0; bb < kw; ++bb) {
-                  int jj = j + bb - pw;
-                  if (jj < 0 || jj >= Ld) continue;
-                  s += (double)convs[k]->w[(((size_t)f * C1 + c) * 3 + a) * kw + bb] *
-                       (double)mt[((size_t)c * Lq + i + a - 1) * Ld + jj];
-                }
+                const float* src = mt + ((size_t)c * Lq + ii) * Ld + (bb - pw);
+                double* dst = accb + (size_t)i * Ld;
+                for (int j = jlo; j < jhi; ++j) dst[j] += wv * (double)src[j];
               }
-            float v = (float)s;
-            y[((size_t)(k * nf + f) * Lq + i) * Ld + j] = v > 0.0f ? v : 0.0f;
-          }
+            }
+        float* yo = y + (size_t)(k * nf + f) * Lq * Ld;
+        for (int x = 0; x < Lq * Ld; ++x) {
+          float v = (float)accb[x];
+          yo[x] = v > 0.0f ? v : 0.0f;
+        }
+      }
     }
+    free(accb);
     /* :126-130 1x1 conv (no activation), max over Ld then Lq (pads included), Linear(M,1) */
     double sc = w->output.b[0];
     for (int m = 0; m < M; ++m) {

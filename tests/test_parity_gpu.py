@@ -1,0 +1,274 @@
+"""Parity tests proper: the CUDA path (through the nn.Module mirrors -> C ABI of libcair.so)
+against (a) the frozen outputs of the unmodified reference (tests/golden) and (b) the CPU oracle
+on fresh seeded inputs, plus size-independent properties at BASELINE.json's full shapes.
+Tolerance: 1e-3 relative fp32 (BASELINE.json north_star), relative error floored at 1 % of the
+batch score scale (oracle_lib.rel_err)."""
+import numpy as np
+import pytest
+import torch
+
+from context_attentive_ir_b200 import lib, synth
+
+import helpers
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+DEV = 'cuda:0'
+
+
+def _max_rel(a, ref):
+    return float(ol.rel_err(a, ref).max())
+
+
+def _run(name, **kw):
+    cfg, ins, sd, outs = ol.load_golden(name)
+    net = helpers.build_module(cfg, sd, DEV)
+    with torch.no_grad():
+        s = net(*helpers.to_dev(ins, DEV), **kw)
+    torch.cuda.synchronize()
+    net.poll_error()
+    return cfg, ins, sd, outs, net, s.cpu().numpy()
+
+
+def test_native_library_is_the_one_running():
+    n0 = lib.launch_count()
+    _run('esm_cfg1')
+    assert lib.launch_count() > n0
+
+
+@pytest.mark.parametrize('name', ['esm_cfg1', 'esm_e300'])
+def test_esm_golden(name):
+    *_, outs, net, s = _run(name)
+    assert _max_rel(s, outs['scores']) < 1e-4
+
+
+@pytest.mark.parametrize('name', ['mt_tiny', 'mt_fullpad', 'mt_stock', 'mt_cfg2arch'])
+def test_match_tensor_golden(name):
+    cfg, ins, sd, outs = ol.load_golden(name)
+    net = helpers.build_module(cfg, sd, DEV)
+    B, Lq = ins['q'].shape
+    _, N, Ld = ins['d'].shape
+    enc_q = torch.full((B, Lq, cfg['nhid_query']), float('nan'), device=DEV)
+    enc_d = torch.full((B * N, Ld, cfg['nhid_doc']), float('nan'), device=DEV)
+    with torch.no_grad():
+        net(*helpers.to_dev(ins, DEV))  # creates the handle
+        lib.check(lib.load().cair_mt_set_debug(net._cair_handle, enc_q.data_ptr(), enc_d.data_ptr()))
+        s = net(*helpers.to_dev(ins, DEV))
+        lib.check(lib.load().cair_mt_set_debug(net._cair_handle, None, None))
+    torch.cuda.synchronize()
+    # stage-wise: encoder memory banks (zeros at pads) then scores
+    assert np.abs(enc_q.cpu().numpy() - outs['enc_queries']).max() < 2e-4
+    ed = enc_d.cpu().numpy()
+    assert np.abs(ed - outs['enc_docs']).max() < 2e-4
+    dl = ins['dlen'].reshape(-1)
+    for i in range(len(dl)):
+        assert not ed[i, dl[i]:].any()
+    assert _max_rel(s.cpu().numpy(), outs['scores']) < TOL
+
+
+def test_drmm_golden_strict():
+    cfg, ins, sd, outs = ol.load_golden('drmm_strict')
+    net = helpers.build_module(cfg, sd, DEV)
+    B, Lq = ins['q'].shape
+    _, N, Ld = ins['d'].shape
+    hist = torch.full((B * N, Lq, 5), -1, dtype=torch.int32, device=DEV)
+    with torch.no_grad():
+        net(*helpers.to_dev(ins, DEV))
+        lib.check(lib.load().cair_drmm_set_debug(net._cair_handle, hist.data_ptr()))
+        s = net(*helpers.to_dev(ins, DEV))
+        lib.check(lib.load().cair_drmm_set_debug(net._cair_handle, None))
+    torch.cuda.synchronize()
+    assert (hist.cpu().numpy() == outs['hist']).all()   # integer work: bit-exact
+    assert _max_rel(s.cpu().numpy(), outs['scores']) < 1e-4
+
+
+def test_drmm_golden_overlap_rows_away_from_bin_edges():
+    cfg, ins, sd, outs = ol.load_golden('drmm_overlap')
+    net = helpers.build_module(cfg, sd, DEV)
+    B, Lq = ins['q'].shape
+    _, N, Ld = ins['d'].shape
+    hist = torch.zeros((B * N, Lq, 5), dtype=torch.int32, device=DEV)
+    with torch.no_grad():
+        net(*helpers.to_dev(ins, DEV))
+        lib.check(lib.load().cair_drmm_set_debug(net._cair_handle, hist.data_ptr()))
+        net(*helpers.to_dev(ins, DEV))
+        lib.check(lib.load().cair_drmm_set_debug(net._cair_handle, None))
+    torch.cuda.synchronize()
+    ref_cos = outs['cos']
+    edges = np.array([-1.0, -0.5, 0.0, 0.5, 1.0], np.float32)
+    near = (np.abs(ref_cos[..., None] - edges) < 4e-7).any(-1) & (ref_cos != 0.0)
+    clean = ~near.any(-1)
+    assert clean.sum() > 0
+    h = hist.cpu().numpy()
+    assert (h[clean] == outs['hist'][clean]).all()
+    # every row still accounts for all Ld cells except the (few) dropped > 1.0 ones
+    assert (h.sum(-1) <= Ld).all() and (h.sum(-1) >= Ld - near.sum(-1)).all()
+
+
+@pytest.mark.parametrize('name', ['duet_tiny', 'duet_e300'])
+def test_duet_golden(name):
+    *_, outs, net, s = _run(name)
+    assert _max_rel(s, outs['scores']) < TOL
+
+
+def test_duet_rejects_unpadded_batches():
+    cfg, ins, sd, outs = ol.load_golden('duet_tiny')
+    net = helpers.build_module(cfg, sd, DEV)
+    q, ql, d, dl = helpers.to_dev(ins, DEV)
+    with pytest.raises(lib.CairError, match='BAD_SHAPE'):
+        net(q[:, :-1], ql, d, dl)
+
+
+@pytest.mark.parametrize('name', ['cars_tiny', 'cars_clicks', 'cars_mid'])
+def test_cars_golden(name):
+    cfg, ins, sd, outs = ol.load_golden(name)
+    net = helpers.build_module(cfg, sd, DEV)
+    args = helpers.to_dev(ins, DEV, ('q', 'qlen', 'd', 'dlen', 'label'))
+    with torch.no_grad():
+        out = net.score(*args, want_stages=True)
+        # the reference's two-call predict sequence gives the same scores
+        pooled, _, _ = net.encode(args[0], args[1])
+        s2, _, attns = net.rank_document(pooled, args[2], args[3], args[4])
+    torch.cuda.synchronize()
+    for k in ('pooled_queries', 'pooled_docs', 'clicks', 'sess_q_attn', 'sess_d_attn'):
+        assert np.abs(out[k].cpu().numpy() - outs[k]).max() < 5e-4, k
+    assert _max_rel(out['scores'].cpu().numpy(), outs['scores']) < TOL
+    assert torch.equal(s2, out['scores'])
+
+
+# ---- fresh seeded inputs against the oracle, sizes the oracle finishes in seconds ---------------
+def _fresh(cfg, seed, B, N, Lq, Ld, **kw):
+    torch.manual_seed(seed)
+    net = helpers.build_module(cfg).to(DEV)
+    batch = synth.ranker_batch(seed, B, N, Lq, Ld, cfg['src_vocab_size'], **kw)
+    with torch.no_grad():
+        s = net(*helpers.to_dev(batch, DEV)).cpu().numpy()
+    o = ol.run_ranker(cfg, helpers.state_dict_numpy(net), batch['q'], batch['qlen'], batch['d'], batch['dlen'])
+    return net, batch, s, o['scores']
+
+
+MT_CFG2 = dict(model='match_tensor', emsize=300, src_vocab_size=5000, dropout_emb=0.2, rnn_type='LSTM',
+               bidirection=True, nlayers=1, dropout_rnn=0.2, featsize=40, nhid_query=128, nhid_doc=128,
+               nchannels=50, nfilters=6, match_filter_size=20)
+
+
+def test_match_tensor_cfg2_shapes_vs_oracle():
+    net, batch, s, ref = _fresh(MT_CFG2, 101, B=4, N=10, Lq=20, Ld=200, bos_eos=True, overlap=0.05)
+    assert _max_rel(s, ref) < TOL
+
+
+def test_match_tensor_ragged_and_minimal_lengths():
+    cfg = dict(MT_CFG2, src_vocab_size=500)
+    torch.manual_seed(3)
+    net = helpers.build_module(cfg).to(DEV)
+    batch = synth.ranker_batch(7, 3, 5, 20, 200, 500)
+    batch['qlen'][1] = 1          # shortest legal query
+    batch['q'][1, 1:] = 0
+    batch['dlen'][2, :] = 1       # one-token documents
+    batch['d'][2, :, 1:] = 0
+    with torch.no_grad():
+        s = net(*helpers.to_dev(batch, DEV)).cpu().numpy()
+    ref = ol.run_ranker(cfg, helpers.state_dict_numpy(net), batch['q'], batch['qlen'], batch['d'], batch['dlen'])['scores']
+    assert _max_rel(s, ref) < TOL
+
+
+def test_drmm_cfg3_shapes_vs_oracle():
+    cfg = dict(model='drmm', emsize=300, src_vocab_size=5000, dropout_emb=0.2, nbins=5)
+    net, batch, s, ref = _fresh(cfg, 102, B=6, N=10, Lq=20, Ld=200, disjoint=True)
+    assert _max_rel(s, ref) < TOL
+
+
+def test_esm_cfg1_vs_oracle():
+    cfg = dict(model='esm', emsize=64, src_vocab_size=10000)
+    net, batch, s, ref = _fresh(cfg, 103, B=8, N=5, Lq=10, Ld=50)
+    assert _max_rel(s, ref) < 1e-4
+
+
+def test_duet_cfg5_shapes_vs_oracle():
+    cfg = dict(model='duet', emsize=300, src_vocab_size=3000, dropout_emb=0.2, dropout=0.2, use_word=True,
+               nfilters=300, local_filter_size=1, dist_filter_size=3, pool_size=5, max_doc_len=200, max_query_len=20)
+    net, batch, s, ref = _fresh(cfg, 104, B=2, N=10, Lq=20, Ld=200, overlap=0.1)
+    assert _max_rel(s, ref) < TOL
+
+
+# ---- properties at full BASELINE shapes (no oracle needed) ------------------------------------------
+def test_match_tensor_full_cfg2_properties():
+    cfg = dict(MT_CFG2, src_vocab_size=131072)
+    torch.manual_seed(5)
+    net = helpers.build_module(cfg).to(DEV)
+    B, N, Lq, Ld = 128, 10, 20, 200
+    batch = synth.ranker_batch(1236, B, N, Lq, Ld, cfg['src_vocab_size'], bos_eos=True)
+    q, ql, d, dl = helpers.to_dev(batch, DEV)
+    with torch.no_grad():
+        s = net(q, ql, d, dl)
+        # (1) permutation equivariance over the candidate docs of each query
+        perm = torch.randperm(N, device=DEV)
+        sp = net(q, ql, d[:, perm].contiguous(), dl[:, perm].contiguous())
+        # (2) batch-composition independence: a sub-batch scores the same
+        sub = net(q[:5], ql[:5], d[:5], dl[:5])
+        # (3) doc-parallel slices assemble to the full result
+        half = B * N // 2 + 3
+        a = net(q, ql, d, dl, pair_slice=(0, half))
+        b = net(q, ql, d, dl, pair_slice=(half, B * N - half))
+    torch.cuda.synchronize()
+    net.poll_error()
+    assert torch.isfinite(s).all()
+    scale = s.abs().max().item()
+    assert (sp - s[:, perm]).abs().max().item() <= 1e-5 * scale
+    assert (sub - s[:5]).abs().max().item() <= 1e-5 * scale
+    assert torch.equal((a + b), s)
+    # (4) end-to-end host entry point returns the same scores
+    hs = net.forward_host(*[torch.from_numpy(batch[k]).pin_memory() for k in ('q', 'qlen', 'd', 'dlen')])
+    assert torch.equal(hs, s.cpu())
+    # (5) the spot-checked oracle agrees on a few pairs of the big batch
+    idx = [0, 57, 127]
+    ref = ol.run_ranker(cfg, helpers.state_dict_numpy(net), batch['q'][idx], batch['qlen'][idx], batch['d'][idx],
+                        batch['dlen'][idx])['scores']
+    assert _max_rel(s[idx].cpu().numpy(), ref) < TOL
+
+
+def test_bad_token_id_is_reported():
+    cfg, ins, sd, outs = ol.load_golden('esm_cfg1')
+    net = helpers.build_module(cfg, sd, DEV)
+    q, ql, d, dl = helpers.to_dev(ins, DEV)
+    q = q.clone()
+    q[0, 0] = cfg['src_vocab_size'] + 5
+    with torch.no_grad():
+        net(q, ql, d, dl)
+    with pytest.raises(lib.CairError, match='BAD_ARG'):
+        net.poll_error()
+
+
+def test_lstm_entry_point_vs_oracle():
+    rng = np.random.default_rng(9)
+    n, L, inp, h = 37, 23, 40, 64
+    x = rng.standard_normal((n, L, inp)).astype(np.float32)
+    lens = rng.integers(1, L + 1, n).astype(np.int64)
+    lens[0] = L
+
+    def mk():
+        k = 1.0 / np.sqrt(h)
+        return dict(w_ih=rng.uniform(-k, k, (4 * h, inp)).astype(np.float32),
+                    w_hh=rng.uniform(-k, k, (4 * h, h)).astype(np.float32),
+                    b_ih=rng.uniform(-k, k, 4 * h).astype(np.float32), b_hh=rng.uniform(-k, k, 4 * h).astype(np.float32))
+    fwd, rev = mk(), mk()
+    ref, hn, cn = ol.run_lstm(x, lens, fwd, rev, h)
+    import ctypes as C
+    from context_attentive_ir_b200 import _abi
+    t = {k: torch.from_numpy(v).to(DEV) for k, v in dict(x=x, lens=lens).items()}
+    wf = {k: torch.from_numpy(v).to(DEV) for k, v in fwd.items()}
+    wr = {k: torch.from_numpy(v).to(DEV) for k, v in rev.items()}
+
+    def sd(w):
+        return _abi.LstmDir(*[C.cast(w[k].data_ptr(), _abi.f32p) for k in ('w_ih', 'w_hh', 'b_ih', 'b_hh')])
+    out = torch.full((n, L, 2 * h), float('nan'), device=DEV)
+    hn_d = torch.zeros(2, n, h, device=DEV)
+    cn_d = torch.zeros(2, n, h, device=DEV)
+    f, r = sd(wf), sd(wr)
+    lib.check(lib.load().cair_lstm_forward(t['x'].data_ptr(), t['lens'].data_ptr(), n, L, inp, h, C.byref(f), C.byref(r),
+                                           out.data_ptr(), hn_d.data_ptr(), cn_d.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream))
+    assert np.abs(out.cpu().numpy() - ref).max() < 1e-4
+    assert np.abs(hn_d.cpu().numpy() - hn).max() < 1e-4
+    assert np.abs(cn_d.cpu().numpy() - cn).max() < 1e-4
