@@ -246,7 +246,7 @@ def run_product(args):
             roof = dict(kernel='mt_interact_kernel', bound='tensor', achieved=ach, peak=tf_peak, unit='TFLOP/s',
                         frac=ach / tf_peak, traffic=None, achieved_ref_equiv=fl['interact_ref'] / fl['interact_exec'] * ach,
                         ms_per_launch=stages[top], peak_source=peak_src)
-        elif top == 'lstm_recurrence':
+        elif top in ('doc_recurrence', 'lstm_recurrence'):
             ach = 2 * LD * 2 * 4 * 64 * 64 * pairs_local / (stages[top] / 1e3) / 1e12
             roof = dict(kernel='lstm_rec_kernel', bound='tensor', achieved=ach, peak=tf_peak, unit='TFLOP/s',
                         frac=ach / tf_peak, traffic=None, ms_per_launch=stages[top], peak_source=peak_src)

@@ -181,6 +181,6 @@ int32_t lstm_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* rev
 size_t lstm_workspace_floats(const LstmPack& p, int64_t n, int L);
 // pre-gates GEMM (optionally gathering rows from `table`) + recurrence; out [n,L,dirs*h], zeros at t>=len.
 int32_t lstm_run(const LstmPack& p, const GemmA& x, const int64_t* len, int n, int L, float* out, float* h_n,
-                 float* c_n, float* ws_pre, int* err, cudaStream_t s);
+                 float* c_n, float* ws_pre, int* err, cudaStream_t s, const char* rec_name = "lstm_recurrence");
 
 }  // namespace cair

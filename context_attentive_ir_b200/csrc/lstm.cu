@@ -170,11 +170,11 @@ __global__ void __launch_bounds__(REC_THREADS) lstm_rec_kernel(const float* __re
 }
 
 int32_t lstm_run(const LstmPack& p, const GemmA& x, const int64_t* len, int n, int L, float* out, float* h_n,
-                 float* c_n, float* ws_pre, int* err, cudaStream_t s) {
+                 float* c_n, float* ws_pre, int* err, cudaStream_t s, const char* rec_name) {
   if (n <= 0) return CAIR_OK;
   const int G = 4 * p.h, PG = p.dirs * G;
   CAIR_TRY(gemm_f32(x, p.w_ih, p.bias, ws_pre, PG, (int64_t)n * L, PG, p.in, ACT_NONE, s));
-  prof_mark("lstm_recurrence", s);
+  prof_mark(rec_name, s);
   const int hp = (p.h + 3) & ~3;
   size_t state = (size_t)(TS * hp + TS * p.h + TS * G) * sizeof(float);
   size_t wbytes = (size_t)p.h * G * sizeof(float);

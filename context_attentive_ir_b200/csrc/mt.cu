@@ -297,10 +297,10 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
   // embedding + projection (folded table) -> BiLSTM encoders (:77-94)
   prof_mark("encode_queries", s);
   CAIR_TRY(lstm_run(st.enc_q, gemm_gather(st.folded, st.V, st.F, qs, 1, 1, 1, err), qlen + qb, (int)nq, Lq, enc_q,
-                    nullptr, nullptr, pre_q, err, s));
+                    nullptr, nullptr, pre_q, err, s, "query_recurrence"));
   prof_mark("doc_pregates", s);
   CAIR_TRY(lstm_run(st.enc_d, gemm_gather(st.folded, st.V, st.F, ds, 1, 1, 1, err), dlen + pb, (int)pc, Ld, enc_d,
-                    nullptr, nullptr, pre_d, err, s));
+                    nullptr, nullptr, pre_d, err, s, "doc_recurrence"));
   if (st.dbg_enc_q)
     CAIR_CUDA(cudaMemcpyAsync(st.dbg_enc_q + (size_t)qb * Lq * st.Hq, enc_q, (size_t)nq * Lq * st.Hq * sizeof(float),
                               cudaMemcpyDeviceToDevice, s));
