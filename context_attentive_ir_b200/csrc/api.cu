@@ -195,6 +195,13 @@ int32_t cair_mt_set_debug(cair_handle* h, float* enc_q, float* enc_d) {
   return CAIR_OK;
 }
 
+int32_t cair_mt_set_impl(cair_handle* h, int32_t impl) {
+  if (!h || h->model != CAIR_MODEL_MT) return fail(CAIR_ERR_BAD_ARG, "mt_set_impl: not a match-tensor handle");
+  if (impl != MT_IMPL_FP32 && impl != MT_IMPL_TC) return fail(CAIR_ERR_BAD_ARG, "mt_set_impl: impl must be 0 (fp32) or 1 (tcgen05)");
+  h->mt.impl = impl;
+  return CAIR_OK;
+}
+
 int32_t cair_drmm_create(const cair_drmm_weights* w, int32_t device, cair_handle** out) {
   if (!w || !w->table) return fail(CAIR_ERR_BAD_ARG, "drmm_create: bad weights");
   if (w->nbins != 5) return fail(CAIR_ERR_UNSUPPORTED, "drmm_create: nbins must be 5 (neuroir/hyparam.py:78-81)");

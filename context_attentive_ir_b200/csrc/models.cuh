@@ -36,8 +36,17 @@ struct MtPack {
   float* b1;    // [M]
   float* wo;    // [M] + bo at [M]
 };
+constexpr int MT_TC_MAXM = 32;  // match_filter_size bound of the tcgen05 interaction kernel
+bool mt_tc_supported(const MtPack& p, int Lq, int Ld);
+void mt_tc_workspace(const MtPack& p, int64_t nq, int64_t pc, int Lq, size_t* img_bytes, size_t* max_floats);
+int32_t mt_tc_interact(const MtPack& p, const float* cq, const float* cd, uint8_t* timg, float* maxbuf,
+                       const int64_t* q, const int64_t* d, int N, int Lq, int Ld, int64_t pair_begin,
+                       int64_t pair_count, int64_t q_begin, int64_t nq, float* scores, cudaStream_t s);
+
+enum { MT_IMPL_FP32 = 0, MT_IMPL_TC = 1 };
 struct MtState {
   int V = 0, E = 0, F = 0, Hq = 0, Hd = 0, C = 0;
+  int impl = MT_IMPL_TC;  // interaction kernel: tcgen05 bf16x3 (default) or the fp32 CUDA-core kernel
   float* folded = nullptr;  // [V, F] = table W_p^T + b_p  (eval-mode fold of mtensor.py:77-90)
   LstmPack enc_q{}, enc_d{};
   float *wq = nullptr, *bq = nullptr, *wd = nullptr, *bd = nullptr;  // channel projections

@@ -1,0 +1,101 @@
+// On-device self test of the tcgen05 conventions in umma.cuh (descriptor fields, canonical no-swizzle
+// K-major layout, row-shifted start addresses, TMEM lane/column mapping, split-bf16 accumulation):
+//   D[m][n] = sum_k A[m + shift][k] * B[n][k],   m < 128, n < N, one CTA, one accumulator tile.
+// Driven by tests/test_parity_gpu.py against a float64 product.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace cair {
+
+using namespace umma;
+
+__global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                            float* __restrict__ D, int N, int K, int shift, int RA,
+                                                            int split, uint32_t tcols) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KC = K / 8;
+  const uint32_t a_plane = RA * 16, b_plane = N * 16;
+  uint8_t* a_hi = sm;
+  uint8_t* a_lo = a_hi + (size_t)KC * a_plane;
+  uint8_t* b_hi = a_lo + (size_t)KC * a_plane;
+  uint8_t* b_lo = b_hi + (size_t)KC * b_plane;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, tcols);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  for (int idx = tid; idx < RA * K; idx += 128) {
+    int r = idx / K, k = idx - r * K;
+    float v = (r < 128 + shift) ? A[(size_t)r * K + k] : 0.f;
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    size_t off = (size_t)(k >> 3) * a_plane + (size_t)r * 16 + (k & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(a_hi + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(a_lo + off) = lo;
+  }
+  for (int idx = tid; idx < N * K; idx += 128) {
+    int r = idx / K, k = idx - r * K;
+    __nv_bfloat16 hi, lo;
+    split_bf16(B[(size_t)r * K + k], hi, lo);
+    size_t off = (size_t)(k >> 3) * b_plane + (size_t)r * 16 + (k & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(b_hi + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(b_lo + off) = lo;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = idesc_bf16_f32(128, N);
+    bool acc = false;
+    for (int pass = 0; pass < (split ? 3 : 1); ++pass) {
+      const uint8_t* ap = (pass == 1) ? a_lo : a_hi;
+      const uint8_t* bp = (pass == 2) ? b_lo : b_hi;
+      for (int ks = 0; ks < K / 16; ++ks) {
+        uint64_t ad = smem_desc(smem_u32(ap) + (2 * ks) * a_plane + shift * 16, a_plane, 128);
+        uint64_t bd = smem_desc(smem_u32(bp) + (2 * ks) * b_plane, b_plane, 128);
+        mma_bf16_ss(tbase, ad, bd, idesc, acc);
+        acc = true;
+      }
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    float v[32];
+    tmem_ld32(tbase + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+    const int m = warp * 32 + lane;
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (c0 + c < N) D[(size_t)m * N + c0 + c] = v[c];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, tcols);
+}
+
+}  // namespace cair
+
+extern "C" int32_t cair_umma_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t shift,
+                                      int32_t split, void* stream) {
+  using namespace cair;
+  if (!A || !B || !D || N < 16 || N > 256 || N % 16 || K < 16 || K % 16 || shift < 0 || shift > 64)
+    return fail(CAIR_ERR_BAD_ARG, "umma_selftest: need 16<=N<=256, N%%16==0, K%%16==0, 0<=shift<=64");
+  int RA = (128 + shift + 7) & ~7;
+  size_t smem = (size_t)(K / 8) * 16 * (RA + N) * 2;
+  if (smem > 220 * 1024) return fail(CAIR_ERR_BAD_ARG, "umma_selftest: operands do not fit in shared memory");
+  uint32_t tcols = 32;
+  while ((int)tcols < N) tcols <<= 1;
+  // tmem_ld32 reads 32-column groups: keep the whole last group inside the allocation
+  while ((int)tcols < ((N + 31) & ~31)) tcols <<= 1;
+  CAIR_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CAIR_LAUNCH(umma_selftest_kernel, 1, 128, smem, (cudaStream_t)stream, A, B, D, N, K, shift, RA, split, tcols);
+  return CAIR_OK;
+}

@@ -27,9 +27,11 @@ PROTOTYPES = {
     'cair_embed_gather': (i32, [vp, i32, i32, vp, i64, vp, vp]),
     'cair_lstm_forward': (i32, [vp, vp, i32, i32, i32, i32, C.POINTER(_abi.LstmDir), C.POINTER(_abi.LstmDir),
                                 vp, vp, vp, vp]),
+    'cair_umma_selftest': (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
     'cair_esm_create': (i32, [C.POINTER(_abi.EsmWeights), i32, C.POINTER(vp)]),
     'cair_mt_create': (i32, [C.POINTER(_abi.MtWeights), i32, C.POINTER(vp)]),
     'cair_mt_set_debug': (i32, [vp, vp, vp]),
+    'cair_mt_set_impl': (i32, [vp, i32]),
     'cair_drmm_create': (i32, [C.POINTER(_abi.DrmmWeights), i32, C.POINTER(vp)]),
     'cair_drmm_set_debug': (i32, [vp, vp]),
     'cair_duet_create': (i32, [C.POINTER(_abi.DuetWeights), i32, C.POINTER(vp)]),

@@ -122,7 +122,11 @@ class _CairModule(nn.Module):
         self.__dict__['_cair_handle'] = out
         self.__dict__['_cair_key'] = key
         self.__dict__['_cair_ws'] = None
+        self._on_handle_created(out)
         return out
+
+    def _on_handle_created(self, handle):
+        pass
 
     def _release(self):
         h = self.__dict__.get('_cair_handle')
@@ -257,6 +261,19 @@ class MatchTensor(_Ranker):
 
     def _create(self, w, device, out):
         return lib.load().cair_mt_create(w, device, out)
+
+    def set_interaction_impl(self, impl):
+        """'tc' (default): tcgen05 bf16x3 tensor-core interaction kernel; 'fp32': CUDA-core fp32 kernel."""
+        self.__dict__['_cair_impl'] = {'fp32': 0, 'tc': 1}[impl]
+        h = self.__dict__.get('_cair_handle')
+        if h is not None:
+            lib.check(lib.load().cair_mt_set_impl(h, self.__dict__['_cair_impl']))
+        return self
+
+    def _on_handle_created(self, handle):
+        impl = self.__dict__.get('_cair_impl')
+        if impl is not None:
+            lib.check(lib.load().cair_mt_set_impl(handle, impl))
 
 
 class GatingNetwork(nn.Module):

@@ -119,6 +119,12 @@ CAIR_API int32_t cair_lstm_forward(const float* x, const int64_t* len, int32_t n
                           int32_t h, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, float* out,
                           float* h_n, float* c_n, void* stream);
 
+/* On-device self test of the tcgen05 operand/descriptor conventions (csrc/umma.cuh):
+ * D[m][n] = sum_k A[m+shift][k] * B[n][k] for m < 128; A [(128+shift),K], B [N,K], D [128,N] fp32 device
+ * pointers; split=0: plain bf16 operands, split=1: bf16x3 split precision (~fp32 accuracy). */
+CAIR_API int32_t cair_umma_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K,
+                                    int32_t shift, int32_t split, void* stream);
+
 /* ---- ESM (neuroir/rankers/esm.py:19-45) --------------------------------------------------- */
 typedef struct {
   int32_t vocab, emsize;
@@ -146,6 +152,11 @@ CAIR_API int32_t cair_mt_create(const cair_mt_weights* w, int32_t device, cair_h
 /* Stage outputs for parity tests (any may be NULL): encoder memory banks
  * enc_q [B,Lq,Hq], enc_d [B*N,Ld,Hd] as RNNEncoder returns them (mtensor.py:93-94). */
 CAIR_API int32_t cair_mt_set_debug(cair_handle* h, float* enc_q, float* enc_d);
+
+/* Interaction kernel selection: 1 = tcgen05 bf16x3 split-precision tensor-core kernel (default when the
+ * configuration fits: nfilters in {4,6}, nchannels <= 64, match_filter_size <= 32), 0 = fp32 CUDA-core
+ * kernel (always available; the on-device cross-check of the tensor-core path). */
+CAIR_API int32_t cair_mt_set_impl(cair_handle* h, int32_t impl);
 
 /* ---- DRMM (neuroir/rankers/drmm.py:13-27 ctor, :29-84 forward, :87-98 gating) -------------- */
 typedef struct {

@@ -43,10 +43,34 @@ def test_esm_golden(name):
     assert _max_rel(s, outs['scores']) < 1e-4
 
 
+def test_tcgen05_conventions_selftest():
+    """D = A[shift:shift+128] @ B^T through tcgen05.mma with the library's operand layout / descriptors."""
+    rng = np.random.default_rng(0)
+    L = lib.load()
+    for (N, K, shift, split) in [(64, 64, 0, 0), (96, 64, 3, 1), (96, 64, 6, 1), (256, 112, 0, 1), (16, 16, 1, 0)]:
+        A = rng.standard_normal((128 + shift, K)).astype(np.float32)
+        B = rng.standard_normal((N, K)).astype(np.float32)
+        a, b = torch.from_numpy(A).to(DEV), torch.from_numpy(B).to(DEV)
+        d = torch.full((128, N), float('nan'), device=DEV)
+        lib.check(L.cair_umma_selftest(a.data_ptr(), b.data_ptr(), d.data_ptr(), N, K, shift, split,
+                                       torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        if split:
+            ref = A[shift:shift + 128].astype(np.float64) @ B.astype(np.float64).T
+            tol = 2e-4
+        else:
+            bf = lambda x: torch.from_numpy(x).to(torch.bfloat16).to(torch.float64).numpy()
+            ref = bf(A[shift:shift + 128]) @ bf(B).T
+            tol = 1e-4
+        err = np.abs(d.cpu().numpy() - ref).max()
+        assert err < tol, (N, K, shift, split, err)
+
+
+@pytest.mark.parametrize('impl', ['tc', 'fp32'])
 @pytest.mark.parametrize('name', ['mt_tiny', 'mt_fullpad', 'mt_stock', 'mt_cfg2arch'])
-def test_match_tensor_golden(name):
+def test_match_tensor_golden(name, impl):
     cfg, ins, sd, outs = ol.load_golden(name)
-    net = helpers.build_module(cfg, sd, DEV)
+    net = helpers.build_module(cfg, sd, DEV).set_interaction_impl(impl)
     B, Lq = ins['q'].shape
     _, N, Ld = ins['d'].shape
     enc_q = torch.full((B, Lq, cfg['nhid_query']), float('nan'), device=DEV)
@@ -65,6 +89,19 @@ def test_match_tensor_golden(name):
     for i in range(len(dl)):
         assert not ed[i, dl[i]:].any()
     assert _max_rel(s.cpu().numpy(), outs['scores']) < TOL
+    net.poll_error()
+
+
+def test_match_tensor_tc_vs_fp32_kernels_cfg2():
+    """The tensor-core interaction kernel against the fp32 CUDA-core kernel on the same device inputs."""
+    torch.manual_seed(11)
+    net = helpers.build_module(MT_CFG2).to(DEV)
+    batch = synth.ranker_batch(77, 16, 10, 20, 200, MT_CFG2['src_vocab_size'], bos_eos=True, overlap=0.05)
+    args = helpers.to_dev(batch, DEV)
+    with torch.no_grad():
+        a = net.set_interaction_impl('tc')(*args).cpu().numpy()
+        b = net.set_interaction_impl('fp32')(*args).cpu().numpy()
+    assert _max_rel(a, b) < 2e-4
 
 
 def test_drmm_golden_strict():
