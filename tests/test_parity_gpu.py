@@ -57,7 +57,7 @@ def test_tcgen05_conventions_selftest():
         torch.cuda.synchronize()
         if split:
             ref = A[shift:shift + 128].astype(np.float64) @ B.astype(np.float64).T
-            tol = 2e-4
+            tol = 1e-3  # ~2^-16 relative per product, |sum| ~ sqrt(K)
         else:
             bf = lambda x: torch.from_numpy(x).to(torch.bfloat16).to(torch.float64).numpy()
             ref = bf(A[shift:shift + 128]) @ bf(B).T
