@@ -145,11 +145,17 @@ int32_t cair_lstm_forward(const float* x, const int64_t* len, int32_t n, int32_t
   int32_t rc = lstm_pack(own, fwd, rev, in, h, &p, s);
   float* pre = nullptr;
   int* err = nullptr;
-  if (rc == CAIR_OK && own.alloc(&pre, lstm_workspace_floats(p, n, L)) != cudaSuccess) rc = fail(CAIR_ERR_CUDA, "lstm_forward: out of memory");
+  const bool tc = lstm_tc_supported(in, h);  // tensor-core kernel when the shape fits, fp32 kernel otherwise
+  LstmTcPack tp;
+  if (rc == CAIR_OK && tc) rc = lstm_tc_pack(own, fwd, rev, in, h, &tp, s);
+  if (rc == CAIR_OK && !tc && own.alloc(&pre, lstm_workspace_floats(p, n, L)) != cudaSuccess) rc = fail(CAIR_ERR_CUDA, "lstm_forward: out of memory");
   if (rc == CAIR_OK && own.alloc(&err, 1) != cudaSuccess) rc = fail(CAIR_ERR_CUDA, "lstm_forward: out of memory");
   if (rc == CAIR_OK) {
     cudaMemsetAsync(err, 0, sizeof(int), s);
-    rc = lstm_run(p, gemm_dense(x, in), len, n, L, out, h_n, c_n, pre, err, s);
+    if (tc)
+      rc = lstm_tc_run(tp, p.bias, gemm_dense(x, in), len, n, L, out, h_n, c_n, err, s, "lstm_recurrence");
+    else
+      rc = lstm_run(p, gemm_dense(x, in), len, n, L, out, h_n, c_n, pre, err, s);
   }
   int flags = 0;
   if (rc == CAIR_OK) cudaMemcpyAsync(&flags, err, sizeof(int), cudaMemcpyDeviceToHost, s);

@@ -183,4 +183,16 @@ size_t lstm_workspace_floats(const LstmPack& p, int64_t n, int L);
 int32_t lstm_run(const LstmPack& p, const GemmA& x, const int64_t* len, int n, int L, float* out, float* h_n,
                  float* c_n, float* ws_pre, int* err, cudaStream_t s, const char* rec_name = "lstm_recurrence");
 
+// tcgen05 LSTM (lstm_tc.cu): fused input + recurrent projection per step, weights resident in smem.
+struct LstmTcPack {
+  int in = 0, h = 0, dirs = 0;
+  uint8_t* wimg = nullptr;  // [dirs][2 row tiles][hi|lo] bf16 operand images
+};
+bool lstm_tc_supported(int in, int h);
+int32_t lstm_tc_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, int in, int h, LstmTcPack* out,
+                     cudaStream_t s);
+// bias: [dirs][4h] = b_ih + b_hh (LstmPack::bias)
+int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, const int64_t* len, int n, int L,
+                    float* out, float* h_n, float* c_n, int* err, cudaStream_t s, const char* rec_name);
+
 }  // namespace cair

@@ -1,0 +1,314 @@
+// (Bi)LSTM recurrence on the 5th-gen tensor cores: one fused tcgen05 tile per time step.
+// RNNEncoder.forward semantics (neuroir/encoders/rnn_encoder.py:62-141), same contract as lstm.cu.
+//
+// Per step the gate pre-activations of NSEQ=32 sequences are ONE GEMM  G^T[4h x 32] = W[4h x K] . Z^T,
+// Z = [x_t | h_{t-1}] (K = 48 + 64), i.e. the input projection and the recurrent projection are fused:
+// no pre-gate tensor is ever written to HBM.  The big, constant operand (the weights, up to 2 x 128 gate
+// rows) is the MMA's M side and stays resident in shared memory for all steps (bulk-copied once); the
+// small per-step operand (32 sequences) is the N side, so a step costs 2 x 7 x 3 MMAs of 16 cycles
+// instead of 128-cycle ones.  bf16x3 split precision (hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM)
+// keeps ~fp32 accuracy through the 200-step recurrence (plain bf16/tf32 does not hold the 1e-3 bar).
+// Gate rows are permuted so that TMEM lane quarter q of row tile m holds gate type q (i,f,g,o) of units
+// 32m..32m+31: the activation is warp-uniform and bias is a per-thread scalar.
+// Warp roles (288 threads): warps 0-7 epilogue (phase 1: tcgen05.ld + sigmoid/tanh -> smem; phase 2: c/h
+// update in registers, h written as next step's bf16 hi/lo operand + fp32 memory bank), warp 8: MMA issuer
+// and gather of x_{t+1} (embedding rows by token id, or dense rows) into the other operand buffer.
+#include "models.cuh"
+#include "umma.cuh"
+
+namespace cair {
+
+using namespace umma;
+
+constexpr int LT_XP = 48;                 // K slots of the x part (in <= 48)
+constexpr int LT_HP = 64;                 // K slots of the h part (h <= 64)
+constexpr int LT_K = LT_XP + LT_HP;       // 112
+constexpr int LT_PLANES = LT_K / 8;       // 14
+constexpr int LT_NSEQ = 32;               // sequences per CTA = N of the MMA
+constexpr int LT_THREADS = 288;
+constexpr uint32_t LT_APLANE = 128 * 16;  // weight image: 128 rows per plane
+constexpr uint32_t LT_BPLANE = LT_NSEQ * 16;
+constexpr uint32_t LT_AIMG = LT_PLANES * LT_APLANE;  // one (row tile, hi|lo) image: 28672 B
+constexpr uint32_t LT_BIMG = LT_PLANES * LT_BPLANE;  // one (hi|lo) image: 7168 B
+
+bool lstm_tc_supported(int in, int h) { return in >= 1 && in <= LT_XP && h >= 1 && h <= LT_HP; }
+
+// weight image [dir][row tile][hi|lo][plane][row][8 x bf16]; row = type*32 + l  <->  gate row type*h + (32*tile + l)
+__global__ void lstm_tc_pack_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, int in, int h,
+                                    uint8_t* __restrict__ img) {
+  const int total = 2 * LT_PLANES * 128 * 8;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int e = idx & 7, row = (idx >> 3) & 127, pl = (idx >> 10) % LT_PLANES, mt = idx / (LT_PLANES * 1024);
+    const int k = pl * 8 + e, type = row >> 5, u = mt * 32 + (row & 31);
+    float v = 0.f;
+    if (u < h) {
+      const int grow = type * h + u;
+      if (k < LT_XP) {
+        if (k < in) v = w_ih[(size_t)grow * in + k];
+      } else if (k - LT_XP < h) {
+        v = w_hh[(size_t)grow * h + (k - LT_XP)];
+      }
+    }
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    const size_t off = (size_t)pl * LT_APLANE + (size_t)row * 16 + e * 2;
+    uint8_t* base = img + (size_t)mt * 2 * LT_AIMG;
+    *reinterpret_cast<__nv_bfloat16*>(base + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(base + LT_AIMG + off) = lo;
+  }
+}
+
+int32_t lstm_tc_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, int in, int h, LstmTcPack* out,
+                     cudaStream_t s) {
+  const int dirs = rev ? 2 : 1;
+  out->in = in, out->h = h, out->dirs = dirs;
+  CAIR_CUDA(own.alloc(&out->wimg, (size_t)dirs * 4 * LT_AIMG));
+  for (int d = 0; d < dirs; ++d) {
+    const cair_lstm_dir* w = d ? rev : fwd;
+    CAIR_LAUNCH(lstm_tc_pack_kernel, 64, 256, 0, s, w->w_ih, w->w_hh, in, h, out->wimg + (size_t)d * 4 * LT_AIMG);
+  }
+  return CAIR_OK;
+}
+
+__device__ __forceinline__ void lt_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void lt_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// accurate-enough fast activations: ex2.approx (2^-22 rel) + rcp.approx (1 ulp); inputs clamped so nothing overflows
+__device__ __forceinline__ float lt_sigmoid(float x) {
+  x = fminf(fmaxf(x, -30.f), 30.f);
+  return __fdividef(1.0f, 1.0f + exp2f(-1.4426950408889634f * x));
+}
+__device__ __forceinline__ float lt_tanh(float x) {
+  x = fminf(fmaxf(x, -15.f), 15.f);
+  const float e = exp2f(-2.8853900817779268f * x);  // exp(-2x)
+  return __fdividef(1.0f - e, 1.0f + e);
+}
+
+// smem: W image (4 x LT_AIMG) | B images [2 parities][hi|lo] (4 x LT_BIMG) | gsm [4][32][64] f32 | slen[32]
+__global__ void __launch_bounds__(LT_THREADS, 1)
+    lstm_tc_kernel(GemmA x, const uint8_t* __restrict__ wimg_all, const float* __restrict__ bias_all,
+                   const int64_t* __restrict__ len, int n, int L, int in, int h, int dirs, uint32_t ks_mask,
+                   float* __restrict__ out, float* __restrict__ h_n, float* __restrict__ c_n, int* err) {
+  extern __shared__ __align__(128) uint8_t smraw[];
+  __shared__ uint64_t bar_w, bar_b, bar_acc;
+  __shared__ uint32_t tmem_slot;
+  __shared__ int slen[LT_NSEQ];
+  __shared__ int smaxlen;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dir = blockIdx.y, s0 = blockIdx.x * LT_NSEQ;
+  const int nmt = (h + 31) / 32;  // row tiles in use (1 or 2)
+  uint8_t* w_img = smraw;
+  uint8_t* b_img = w_img + 4 * LT_AIMG;
+  float* gsm = reinterpret_cast<float*>(b_img + 4 * LT_BIMG);
+  const float* bias = bias_all + (size_t)dir * 4 * h;
+  const int Hout = dirs * h;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, 64);
+  if (tid == 32) {
+    mbar_init(&bar_w, 1);
+    mbar_init(&bar_b, 9);    // 8 epilogue warps (h written) + the MMA warp (x written)
+    mbar_init(&bar_acc, 1);
+    fence_mbar_init();
+  }
+  if (tid < LT_NSEQ) {
+    int s = s0 + tid, l = 0;
+    if (s < n) {
+      int64_t ll = len[s];
+      if (ll < 1 || ll > L) {
+        atomicOr(err, ERRF_BAD_LENGTH);
+        ll = ll < 1 ? 1 : L;
+      }
+      l = (int)ll;
+    }
+    slen[tid] = l;
+  }
+  // zero both operand buffers (h_0 = 0, K padding stays zero for ever)
+  for (int i = tid; i < (int)(4 * LT_BIMG / 16); i += LT_THREADS) reinterpret_cast<uint4*>(b_img)[i] = make_uint4(0, 0, 0, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    int m = 0;
+    for (int s = 0; s < LT_NSEQ; ++s) m = max(m, slen[s]);
+    smaxlen = m;
+    // weights of this direction: one bulk copy, resident for all steps
+    const uint32_t bytes = (uint32_t)(nmt * 2) * LT_AIMG;
+    mbar_arrive_expect_tx(&bar_w, bytes);
+    const uint8_t* src = wimg_all + (size_t)dir * 4 * LT_AIMG;
+    for (uint32_t o = 0; o < bytes; o += LT_AIMG) bulk_g2s(w_img + o, src + o, LT_AIMG, &bar_w);
+  }
+  // zero the pad rows of the memory bank (this direction's half)
+  for (int s = 0; s < LT_NSEQ; ++s) {
+    if (s0 + s >= n) break;
+    const int npad = (L - slen[s]) * h;
+    float* o = out + ((size_t)(s0 + s) * L + slen[s]) * Hout + dir * h;
+    for (int i = tid; i < npad; i += LT_THREADS) o[(size_t)(i / h) * Hout + (i % h)] = 0.f;
+  }
+  __syncthreads();
+  const int maxlen = smaxlen;
+  const uint32_t tbase = tmem_slot;
+
+  if (warp == 8) {
+    // ===================== MMA issuer + x gather =====================
+    const int myl = slen[lane];
+    auto gather_x = [&](int step, int parity) {
+      // lane <-> sequence row; x row -> hi/lo bf16 -> x planes of operand buffer `parity`
+      uint8_t* bh = b_img + (size_t)parity * 2 * LT_BIMG;
+      const bool active = step < myl;
+      const int t = dir ? myl - 1 - step : step;
+      const int64_t r = (int64_t)(s0 + lane) * L + (active ? t : 0);
+      const float* src = nullptr;
+      if (active) {
+        if (x.table) {
+          int64_t id = checked_id(x.ids[r], x.V, x.err);
+          src = x.table + id * x.E;
+        } else {
+          src = x.dense + r * x.lda;
+        }
+      }
+      for (int pl = 0; pl * 8 < in; ++pl) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (active && pl * 8 + e < in) ? src[pl * 8 + e] : 0.f;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(v[2 * e], h0, l0);
+          split_bf16(v[2 * e + 1], h1, l1);
+          hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          lo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        const size_t off = (size_t)pl * LT_BPLANE + (size_t)lane * 16;
+        *reinterpret_cast<uint4*>(bh + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(bh + LT_BIMG + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) lt_arrive(&bar_b);
+    };
+    gather_x(0, 0);
+    if (lane == 0) mbar_wait(&bar_w, 0);
+    __syncwarp();
+    const uint32_t idesc = idesc_bf16_f32(128, LT_NSEQ);
+    const uint32_t w0 = smem_u32(w_img), b0 = smem_u32(b_img);
+    for (int step = 0; step < maxlen; ++step) {
+      const int par = step & 1;
+      if (lane == 0) {
+        mbar_wait(&bar_b, par);
+        tc_fence_after();
+        const uint32_t bb = b0 + (uint32_t)par * 2 * LT_BIMG;
+        for (int mt = 0; mt < nmt; ++mt) {
+          const uint32_t wa = w0 + (uint32_t)mt * 2 * LT_AIMG;
+          const uint32_t tacc = tbase + (uint32_t)mt * LT_NSEQ;
+          bool acc = false;
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t wp = wa + (pass == 1 ? LT_AIMG : 0);   // weights: hi, lo, hi
+            const uint32_t bp = bb + (pass == 2 ? LT_BIMG : 0);   // activations: hi, hi, lo
+#pragma unroll
+            for (int ks = 0; ks < LT_K / 16; ++ks) {
+              if (!((ks_mask >> ks) & 1)) continue;
+              mma_bf16_ss(tacc, smem_desc(wp + (uint32_t)(2 * ks) * LT_APLANE, LT_APLANE, 128),
+                          smem_desc(bp + (uint32_t)(2 * ks) * LT_BPLANE, LT_BPLANE, 128), idesc, acc);
+              acc = true;
+            }
+          }
+        }
+        mma_commit(&bar_acc);
+      }
+      __syncwarp();
+      if (step + 1 < maxlen) gather_x(step + 1, par ^ 1);
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int mt = warp >> 2, type = warp & 3;       // phase 1: row tile, gate type (= TMEM lane quarter)
+    const int u1 = mt * 32 + lane;                    // phase 1 unit
+    const float bias1 = (u1 < h) ? bias[type * h + u1] : 0.f;
+    const int u2 = tid & 63, sg = tid >> 6;           // phase 2: unit, sequence group (s = sg + 4k)
+    float cst[8], hst[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cst[k] = 0.f, hst[k] = 0.f;
+    if (lane == 0 && maxlen > 0) lt_arrive(&bar_b);   // h_0 = 0 is already in operand buffer 0
+    for (int step = 0; step < maxlen; ++step) {
+      const int par = step & 1;
+      mbar_wait(&bar_acc, par);
+      tc_fence_after();
+      // ---- phase 1: activation of one gate row for 32 sequences ----
+      if (mt < nmt) {
+        float v[32];
+        tmem_ld32(tbase + ((uint32_t)(type * 32) << 16) + (uint32_t)mt * LT_NSEQ, v);
+        tmem_ld_wait();
+        if (u1 < h) {
+#pragma unroll
+          for (int s = 0; s < 32; ++s) {
+            const float a = v[s] + bias1;
+            gsm[(type * 32 + s) * 64 + u1] = (type == 2) ? lt_tanh(a) : lt_sigmoid(a);
+          }
+        }
+      }
+      tc_fence_before();
+      lt_named_bar(1, 256);
+      // ---- phase 2: state update for (unit u2, sequences sg + 4k) ----
+      uint8_t* bn = b_img + (size_t)(par ^ 1) * 2 * LT_BIMG;  // next step's operand buffer
+      if (u2 < h) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int s = sg + 4 * k;
+          const int l = slen[s];
+          if (step < l) {
+            const float ig = gsm[(0 * 32 + s) * 64 + u2], fg = gsm[(1 * 32 + s) * 64 + u2];
+            const float gg = gsm[(2 * 32 + s) * 64 + u2], og = gsm[(3 * 32 + s) * 64 + u2];
+            const float c = fg * cst[k] + ig * gg;
+            const float hv = og * lt_tanh(c);
+            cst[k] = c, hst[k] = hv;
+            const int t = dir ? l - 1 - step : step;
+            out[((size_t)(s0 + s) * L + t) * Hout + dir * h + u2] = hv;
+          }
+          __nv_bfloat16 hi, lo;
+          split_bf16(hst[k], hi, lo);
+          const size_t off = (size_t)((LT_XP + u2) >> 3) * LT_BPLANE + (size_t)s * 16 + (u2 & 7) * 2;
+          *reinterpret_cast<__nv_bfloat16*>(bn + off) = hi;
+          *reinterpret_cast<__nv_bfloat16*>(bn + LT_BIMG + off) = lo;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && step + 1 < maxlen) lt_arrive(&bar_b);
+    }
+    if (u2 < h && (h_n || c_n)) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int s = sg + 4 * k;
+        if (s0 + s >= n) continue;
+        if (h_n) h_n[((size_t)dir * n + s0 + s) * h + u2] = hst[k];
+        if (c_n) c_n[((size_t)dir * n + s0 + s) * h + u2] = cst[k];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 64);
+}
+
+int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, const int64_t* len, int n, int L,
+                    float* out, float* h_n, float* c_n, int* err, cudaStream_t s, const char* rec_name) {
+  if (n <= 0) return CAIR_OK;
+  prof_mark(rec_name, s);
+  uint32_t ks_mask = 0;
+  for (int ks = 0; ks < LT_K / 16; ++ks) {
+    const int k0 = 16 * ks, k1 = k0 + 16;
+    const bool x_part = k0 < p.in;
+    const bool h_part = k1 > LT_XP && k0 < LT_XP + p.h;
+    if (x_part || h_part) ks_mask |= 1u << ks;
+  }
+  const size_t smem = (size_t)4 * LT_AIMG + 4 * LT_BIMG + (size_t)4 * 32 * 64 * sizeof(float);
+  CAIR_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((n + LT_NSEQ - 1) / LT_NSEQ, p.dirs);
+  CAIR_LAUNCH(lstm_tc_kernel, grid, LT_THREADS, smem, s, x, p.wimg, bias, len, n, L, p.in, p.h, p.dirs, ks_mask, out,
+              h_n, c_n, err);
+  return CAIR_OK;
+}
+
+}  // namespace cair

@@ -49,6 +49,7 @@ struct MtState {
   int impl = MT_IMPL_TC;  // interaction kernel: tcgen05 bf16x3 (default) or the fp32 CUDA-core kernel
   float* folded = nullptr;  // [V, F] = table W_p^T + b_p  (eval-mode fold of mtensor.py:77-90)
   LstmPack enc_q{}, enc_d{};
+  LstmTcPack tc_q{}, tc_d{};  // tensor-core encoders (valid when lstm_tc_supported)
   float *wq = nullptr, *bq = nullptr, *wd = nullptr, *bd = nullptr;  // channel projections
   MtPack pack{};
   float *dbg_enc_q = nullptr, *dbg_enc_d = nullptr;

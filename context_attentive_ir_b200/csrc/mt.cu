@@ -268,6 +268,10 @@ int32_t mt_create_state(Owned& own, const cair_mt_weights& w, MtState* st, cudaS
                     w.featsize, w.vocab, w.featsize, w.emsize, ACT_NONE, s));
   CAIR_TRY(lstm_pack(own, &w.query_fwd, dirs == 2 ? &w.query_rev : nullptr, w.featsize, w.nhid_query / dirs, &st->enc_q, s));
   CAIR_TRY(lstm_pack(own, &w.doc_fwd, dirs == 2 ? &w.doc_rev : nullptr, w.featsize, w.nhid_doc / dirs, &st->enc_d, s));
+  if (lstm_tc_supported(w.featsize, w.nhid_query / dirs))
+    CAIR_TRY(lstm_tc_pack(own, &w.query_fwd, dirs == 2 ? &w.query_rev : nullptr, w.featsize, w.nhid_query / dirs, &st->tc_q, s));
+  if (lstm_tc_supported(w.featsize, w.nhid_doc / dirs))
+    CAIR_TRY(lstm_tc_pack(own, &w.doc_fwd, dirs == 2 ? &w.doc_rev : nullptr, w.featsize, w.nhid_doc / dirs, &st->tc_d, s));
   CAIR_TRY(dev_copy(own, w.query_projection.w, (size_t)w.nchannels * w.nhid_query, &st->wq, s));
   CAIR_TRY(dev_copy(own, w.query_projection.b, (size_t)w.nchannels, &st->bq, s));
   CAIR_TRY(dev_copy(own, w.document_projection.w, (size_t)w.nchannels * w.nhid_doc, &st->wd, s));
@@ -283,9 +287,11 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
   // queries touched by the pair slice [pb, pb+pc)
   const int64_t qb = pc > 0 ? pb / N : 0;
   const int64_t nq = pc > 0 ? (pb + pc - 1) / N - qb + 1 : 0;
-  float* pre_q = ws.take<float>(lstm_workspace_floats(st.enc_q, nq, Lq));
+  const bool tc_q = st.impl == MT_IMPL_TC && st.tc_q.wimg != nullptr;
+  const bool tc_d = st.impl == MT_IMPL_TC && st.tc_d.wimg != nullptr;
+  float* pre_q = ws.take<float>(tc_q ? 0 : lstm_workspace_floats(st.enc_q, nq, Lq));
   float* enc_q = ws.take<float>((size_t)nq * Lq * st.Hq);
-  float* pre_d = ws.take<float>(lstm_workspace_floats(st.enc_d, pc, Ld));
+  float* pre_d = ws.take<float>(tc_d ? 0 : lstm_workspace_floats(st.enc_d, pc, Ld));
   float* enc_d = ws.take<float>((size_t)pc * Ld * st.Hd);
   float* cq = ws.take<float>((size_t)nq * Lq * st.C);
   float* cd = ws.take<float>((size_t)pc * Ld * st.C);
@@ -307,11 +313,19 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
   const int64_t* ds = d + pb * Ld;
   // embedding + projection (folded table) -> BiLSTM encoders (:77-94)
   prof_mark("encode_queries", s);
-  CAIR_TRY(lstm_run(st.enc_q, gemm_gather(st.folded, st.V, st.F, qs, 1, 1, 1, err), qlen + qb, (int)nq, Lq, enc_q,
-                    nullptr, nullptr, pre_q, err, s, "query_recurrence"));
+  if (tc_q)
+    CAIR_TRY(lstm_tc_run(st.tc_q, st.enc_q.bias, gemm_gather(st.folded, st.V, st.F, qs, 1, 1, 1, err), qlen + qb, (int)nq,
+                         Lq, enc_q, nullptr, nullptr, err, s, "query_recurrence"));
+  else
+    CAIR_TRY(lstm_run(st.enc_q, gemm_gather(st.folded, st.V, st.F, qs, 1, 1, 1, err), qlen + qb, (int)nq, Lq, enc_q,
+                      nullptr, nullptr, pre_q, err, s, "query_recurrence"));
   prof_mark("doc_pregates", s);
-  CAIR_TRY(lstm_run(st.enc_d, gemm_gather(st.folded, st.V, st.F, ds, 1, 1, 1, err), dlen + pb, (int)pc, Ld, enc_d,
-                    nullptr, nullptr, pre_d, err, s, "doc_recurrence"));
+  if (tc_d)
+    CAIR_TRY(lstm_tc_run(st.tc_d, st.enc_d.bias, gemm_gather(st.folded, st.V, st.F, ds, 1, 1, 1, err), dlen + pb, (int)pc,
+                         Ld, enc_d, nullptr, nullptr, err, s, "doc_recurrence"));
+  else
+    CAIR_TRY(lstm_run(st.enc_d, gemm_gather(st.folded, st.V, st.F, ds, 1, 1, 1, err), dlen + pb, (int)pc, Ld, enc_d,
+                      nullptr, nullptr, pre_d, err, s, "doc_recurrence"));
   if (st.dbg_enc_q)
     CAIR_CUDA(cudaMemcpyAsync(st.dbg_enc_q + (size_t)qb * Lq * st.Hq, enc_q, (size_t)nq * Lq * st.Hq * sizeof(float),
                               cudaMemcpyDeviceToDevice, s));
