@@ -189,35 +189,40 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
       if (lane == 0) lt_arrive(&bar_b);
     };
     gather_x(0, 0);
-    if (lane == 0) mbar_wait(&bar_w, 0);
-    __syncwarp();
+    mbar_wait(&bar_w, 0);
+    const uint32_t issue = elect_one();
     const uint32_t idesc = idesc_bf16_f32(128, LT_NSEQ);
     const uint32_t w0 = smem_u32(w_img), b0 = smem_u32(b_img);
+    // descriptor bases (16-byte units are added to the low word; the address field never carries)
+    const uint64_t wd0 = smem_desc(w0, LT_APLANE, 128);
+    const uint64_t bd0 = smem_desc(b0, LT_BPLANE, 128);
     for (int step = 0; step < maxlen; ++step) {
       const int par = step & 1;
-      if (lane == 0) {
-        mbar_wait(&bar_b, par);
-        tc_fence_after();
-        const uint32_t bb = b0 + (uint32_t)par * 2 * LT_BIMG;
-        for (int mt = 0; mt < nmt; ++mt) {
-          const uint32_t wa = w0 + (uint32_t)mt * 2 * LT_AIMG;
+      mbar_wait(&bar_b, par);
+      tc_fence_after();
+      const uint64_t bdp = bd0 + (uint64_t)((uint32_t)par * 2 * LT_BIMG >> 4);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        if (mt < nmt) {
+          const uint64_t wdm = wd0 + (uint64_t)((uint32_t)mt * 2 * LT_AIMG >> 4);
           const uint32_t tacc = tbase + (uint32_t)mt * LT_NSEQ;
-          bool acc = false;
+          uint32_t acc = 0;
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t wp = wa + (pass == 1 ? LT_AIMG : 0);   // weights: hi, lo, hi
-            const uint32_t bp = bb + (pass == 2 ? LT_BIMG : 0);   // activations: hi, hi, lo
+            const uint64_t wp = wdm + (pass == 1 ? (LT_AIMG >> 4) : 0);   // weights: hi, lo, hi
+            const uint64_t bp = bdp + (pass == 2 ? (LT_BIMG >> 4) : 0);   // activations: hi, hi, lo
 #pragma unroll
             for (int ks = 0; ks < LT_K / 16; ++ks) {
-              if (!((ks_mask >> ks) & 1)) continue;
-              mma_bf16_ss(tacc, smem_desc(wp + (uint32_t)(2 * ks) * LT_APLANE, LT_APLANE, 128),
-                          smem_desc(bp + (uint32_t)(2 * ks) * LT_BPLANE, LT_BPLANE, 128), idesc, acc);
-              acc = true;
+              if ((ks_mask >> ks) & 1) {
+                mma_bf16_ss_w(tacc, wp + (uint64_t)((2 * ks) * (LT_APLANE >> 4)), bp + (uint64_t)((2 * ks) * (LT_BPLANE >> 4)),
+                              idesc, acc, issue);
+                acc = 1;
+              }
             }
           }
         }
-        mma_commit(&bar_acc);
       }
+      mma_commit_w(&bar_acc, issue);
       __syncwarp();
       if (step + 1 < maxlen) gather_x(step + 1, par ^ 1);
     }

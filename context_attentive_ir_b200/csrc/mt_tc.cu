@@ -151,10 +151,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (whole warp runs the uniform control flow, one elected lane issues) =========
+    {
+      const uint32_t issue = elect_one();
       const uint32_t idesc = idesc_bf16_f32(128, TC_NROWS);
       const uint32_t a0 = smem_u32(a_img), b0 = smem_u32(b_ring);
+      const uint64_t ad_hi = smem_desc(a0, a_plane, 128), ad_lo = smem_desc(a0 + a_half, a_plane, 128);
+      const uint32_t a_ks = (2 * a_plane) >> 4, b_ks = (2 * b_plane) >> 4, b_lo_off = b_half >> 4;
+      const int nks = CP / 16;
       uint32_t it = 0, tile = 0, pair_it = 0;
       for (int64_t pl = blockIdx.x; pl < pair_count; pl += gridDim.x, ++pair_it) {
         mbar_wait(&a_full, pair_it & 1);
@@ -167,22 +171,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const int s = it % nstages;
             mbar_wait(&full_b[s], (it / nstages) & 1);
             tc_fence_after();
-            const uint32_t bs = b0 + (uint32_t)s * slab;
-            for (int mt = 0; mt < nmt; ++mt) {
-              const uint32_t tacc = tbase + (uint32_t)(as * 2 + mt) * TC_NROWS;
-              for (int ks = 0; ks < CP / 16; ++ks) {
-                const uint32_t ao = (uint32_t)(2 * ks) * a_plane + (uint32_t)(mt * 128 + bt) * 16;
-                const uint32_t bo = (uint32_t)(2 * ks) * b_plane;
-                const uint64_t a_hi = smem_desc(a0 + ao, a_plane, 128), a_lo = smem_desc(a0 + a_half + ao, a_plane, 128);
-                const uint64_t b_hi = smem_desc(bs + bo, b_plane, 128), b_lo = smem_desc(bs + b_half + bo, b_plane, 128);
-                mma_bf16_ss(tacc, a_hi, b_hi, idesc, (bt | ks) != 0);
-                mma_bf16_ss(tacc, a_lo, b_hi, idesc, true);
-                mma_bf16_ss(tacc, a_hi, b_lo, idesc, true);
+            const uint64_t bd_hi = smem_desc(b0 + (uint32_t)s * slab, b_plane, 128);
+            const uint32_t accf = bt != 0;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              if (mt < nmt) {
+                const uint32_t tacc = tbase + (uint32_t)(as * 2 + mt) * TC_NROWS;
+                const uint64_t ah = ad_hi + (uint64_t)(mt * 128 + bt), al = ad_lo + (uint64_t)(mt * 128 + bt);
+                for (int ks = 0; ks < nks; ++ks) {
+                  const uint64_t ahk = ah + (uint64_t)(ks * a_ks), alk = al + (uint64_t)(ks * a_ks);
+                  const uint64_t bhk = bd_hi + (uint64_t)(ks * b_ks), blk = bhk + (uint64_t)b_lo_off;
+                  mma_bf16_ss_w(tacc, ahk, bhk, idesc, accf | (uint32_t)(ks != 0), issue);
+                  mma_bf16_ss_w(tacc, alk, bhk, idesc, 1, issue);
+                  mma_bf16_ss_w(tacc, ahk, blk, idesc, 1, issue);
+                }
               }
             }
-            mma_commit(&empty_b[s]);        // slab free once these MMAs retire
+            mma_commit_w(&empty_b[s], issue);        // slab free once these MMAs retire
           }
-          mma_commit(&acc_full[as]);        // accumulator stage complete
+          mma_commit_w(&acc_full[as], issue);        // accumulator stage complete
         }
       }
     }
