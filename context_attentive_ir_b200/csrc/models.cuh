@@ -37,9 +37,18 @@ struct MtPack {
   float* wo;    // [M] + bo at [M]
 };
 constexpr int MT_TC_MAXM = 32;  // match_filter_size bound of the tcgen05 interaction kernel
+// Epilogue weights of the tcgen05 interaction kernel, passed BY VALUE as a __grid_constant__ kernel
+// parameter so the hot loop reads them as constant-bank operands (host copy made once at create).
+struct MtEpiConst {
+  float wem[21][24];        // alpha * W7[f, C, a, bt], index a*7+bt
+  float bias[24];           // merged conv bias
+  float w1[MT_TC_MAXM][24]; // 1x1 conv
+  float b1[MT_TC_MAXM];
+};
 bool mt_tc_supported(const MtPack& p, int Lq, int Ld);
 void mt_tc_workspace(const MtPack& p, int64_t nq, int64_t pc, int Lq, size_t* img_bytes, size_t* max_floats);
-int32_t mt_tc_interact(const MtPack& p, const float* cq, const float* cd, uint8_t* timg, float* maxbuf,
+int32_t mt_epi_const(const MtPack& p, MtEpiConst* out, cudaStream_t s);  // synchronises s
+int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const float* cq, const float* cd, uint8_t* timg, float* maxbuf,
                        const int64_t* q, const int64_t* d, int N, int Lq, int Ld, int64_t pair_begin,
                        int64_t pair_count, int64_t q_begin, int64_t nq, float* scores, cudaStream_t s);
 
@@ -52,6 +61,7 @@ struct MtState {
   LstmTcPack tc_q{}, tc_d{};  // tensor-core encoders (valid when lstm_tc_supported)
   float *wq = nullptr, *bq = nullptr, *wd = nullptr, *bd = nullptr;  // channel projections
   MtPack pack{};
+  MtEpiConst epi{};
   float *dbg_enc_q = nullptr, *dbg_enc_d = nullptr;
 };
 int32_t mt_create_state(Owned& own, const cair_mt_weights& w, MtState* st, cudaStream_t s);

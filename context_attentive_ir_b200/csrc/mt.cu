@@ -277,6 +277,7 @@ int32_t mt_create_state(Owned& own, const cair_mt_weights& w, MtState* st, cudaS
   CAIR_TRY(dev_copy(own, w.document_projection.w, (size_t)w.nchannels * w.nhid_doc, &st->wd, s));
   CAIR_TRY(dev_copy(own, w.document_projection.b, (size_t)w.nchannels, &st->bd, s));
   CAIR_TRY(mt_pack(own, w, &st->pack, s));
+  CAIR_TRY(mt_epi_const(st->pack, &st->epi, s));
   return CAIR_OK;
 }
 
@@ -336,7 +337,7 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
   prof_mark("projections", s);
   CAIR_TRY(gemm_f32(gemm_dense(enc_q, st.Hq), st.wq, st.bq, cq, st.C, nq * Lq, st.C, st.Hq, ACT_NONE, s));
   CAIR_TRY(gemm_f32(gemm_dense(enc_d, st.Hd), st.wd, st.bd, cd, st.C, pc * Ld, st.C, st.Hd, ACT_NONE, s));
-  if (use_tc) return mt_tc_interact(st.pack, cq, cd, timg, maxbuf, q, d, N, Lq, Ld, pb, pc, qb, nq, scores, s);
+  if (use_tc) return mt_tc_interact(st.pack, st.epi, cq, cd, timg, maxbuf, q, d, N, Lq, Ld, pb, pc, qb, nq, scores, s);
   return mt_interact(st.pack, cq, cd, T, q, d, N, Lq, Ld, pb, pc, qb, nq, scores, s);
 }
 

@@ -21,6 +21,9 @@
 //               running max in registers; accumulators are double-buffered in TMEM (4 x 96 columns) so
 //               the epilogue of tile t overlaps the MMAs of tile t+1.  Last: max over rows, Linear, ONE
 //               4-byte score store per pair.
+#include <cstring>
+#include <vector>
+
 #include "models.cuh"
 #include "umma.cuh"
 
@@ -38,8 +41,8 @@ static inline int tc_cp(int C) { return (C + 15) & ~15; }
 static inline size_t tc_slab_bytes(int CP) { return (size_t)2 * (CP / 8) * TC_NROWS * 16; }  // hi + lo, one tap
 static inline size_t tc_a_bytes(int CP) { return (size_t)2 * (CP / 8) * TC_MAXRA * 16; }
 static inline size_t tc_misc_bytes(const MtPack& p, int Lq) {
-  return (size_t)(21 * p.FPP + p.FPP + MT_TC_MAXM * p.FPP + MT_TC_MAXM + MT_TC_MAXM * 8) * sizeof(float) +
-         (size_t)(TC_MAXRA + 8 + Lq) * sizeof(int);
+  (void)p;
+  return (size_t)(MT_TC_MAXM * 8) * sizeof(float) + (size_t)(TC_MAXRA + 8 + Lq) * sizeof(int);
 }
 static inline int tc_stages(const MtPack& p, int Lq) {
   const int CP = tc_cp(p.C);
@@ -88,9 +91,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <int NF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     mt_tc_interact_kernel(const float* __restrict__ cd, const uint8_t* __restrict__ timg, MtPack p,
-                          const int64_t* __restrict__ q, const int64_t* __restrict__ d, int N, int Lq, int Ld, int CP,
-                          int ntiles, int nstages, int64_t pair_begin, int64_t pair_count, int64_t q_begin,
-                          float* __restrict__ scores) {
+                          const __grid_constant__ MtEpiConst ec, const int64_t* __restrict__ q,
+                          const int64_t* __restrict__ d, int N, int Lq, int Ld, int CP, int ntiles, int nstages,
+                          int64_t pair_begin, int64_t pair_count, int64_t q_begin, float* __restrict__ scores) {
   constexpr int FP = 3 * NF, FPP = (FP + 3) & ~3, IPT = TC_NROWS / FP;
   extern __shared__ __align__(128) uint8_t smraw[];
   __shared__ uint64_t full_b[8], empty_b[8], acc_full[2], acc_empty[2], a_full;
@@ -104,11 +107,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t slab = 2 * b_half;
   uint8_t* a_img = smraw;
   uint8_t* b_ring = a_img + (size_t)2 * KC * TC_MAXRA * 16;  // host side: tc_a_bytes()
-  float* wem = reinterpret_cast<float*>(b_ring + (size_t)nstages * slab);
-  float* bias = wem + 21 * FPP;
-  float* w1 = bias + FPP;
-  float* b1 = w1 + MT_TC_MAXM * FPP;
-  float* red = b1 + MT_TC_MAXM;                     // [8 warps][32]
+  // epilogue weights (exact-match taps, bias, 1x1 conv) come from the constant bank (kernel parameter `ec`):
+  // FFMA takes them as immediate c[][] operands, no shared-memory loads in the hot loop
+  float* red = reinterpret_cast<float*>(b_ring + (size_t)nstages * slab);  // [8 warps][32]
   int* dids = reinterpret_cast<int*>(red + MT_TC_MAXM * 8);
   int* qids = dids + TC_MAXRA + 8;
 
@@ -125,10 +126,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     mbar_init(&a_full, 8);
     fence_mbar_init();
   }
-  for (int i = tid; i < 21 * FPP; i += TC_THREADS) wem[i] = p.wem[i];
-  for (int i = tid; i < FPP; i += TC_THREADS) bias[i] = p.bias[i];
-  for (int i = tid; i < M * FPP; i += TC_THREADS) w1[i] = p.w1[i];
-  for (int i = tid; i < M; i += TC_THREADS) b1[i] = p.b1[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -257,7 +254,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             tmem_ld_wait();
             if (i < Lq && jrow < Ld) {
 #pragma unroll
-              for (int f = 0; f < FPP; ++f) y[f] = (f < FP) ? y[f] + bias[f] : 0.f;
+              for (int f = 0; f < FPP; ++f) y[f] = (f < FP) ? y[f] + ec.bias[f] : 0.f;
               // exact-match channel: alpha * W7[f, C, a, bt] wherever q[i+a-1] == d[j+bt-3] (PAD==PAD counts)
 #pragma unroll
               for (int a = 0; a < 3; ++a) {
@@ -267,9 +264,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
                 for (int bt = 0; bt < 7; ++bt) {
                   if (dj[bt] == qi) {
-                    const float* we = wem + (a * 7 + bt) * FPP;
 #pragma unroll
-                    for (int f = 0; f < FP; ++f) y[f] += we[f];
+                    for (int f = 0; f < FP; ++f) y[f] += ec.wem[a * 7 + bt][f];
                   }
                 }
               }
@@ -278,17 +274,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
               for (int m = 0; m < MT_TC_MAXM; ++m) {
                 if (m < M) {
-                  float z = b1[m];
-                  const float4* wr = reinterpret_cast<const float4*>(w1 + m * FPP);
+                  // two independent FMA chains per output (ILP), weights as constant-bank operands
+                  float z0 = ec.b1[m], z1 = 0.f;
 #pragma unroll
-                  for (int f4 = 0; f4 < FPP / 4; ++f4) {
-                    float4 w4 = wr[f4];
-                    z = fmaf(w4.x, y[4 * f4 + 0], z);
-                    z = fmaf(w4.y, y[4 * f4 + 1], z);
-                    z = fmaf(w4.z, y[4 * f4 + 2], z);
-                    z = fmaf(w4.w, y[4 * f4 + 3], z);
+                  for (int f = 0; f < FP; f += 2) {
+                    z0 = fmaf(ec.w1[m][f], y[f], z0);
+                    if (f + 1 < FP) z1 = fmaf(ec.w1[m][f + 1], y[f + 1], z1);
                   }
-                  mx[m] = fmaxf(mx[m], z);
+                  mx[m] = fmaxf(mx[m], z0 + z1);
                 }
               }
             }
@@ -338,8 +331,28 @@ void mt_tc_workspace(const MtPack& p, int64_t nq, int64_t pc, int Lq, size_t* im
   *max_floats = 0;
 }
 
-int32_t mt_tc_interact(const MtPack& p, const float* cq, const float* cd, uint8_t* timg, float* maxbuf,
-                       const int64_t* q, const int64_t* d, int N, int Lq, int Ld, int64_t pair_begin,
+// Host copy of the epilogue weights (exact-match taps, bias, 1x1 conv) for the constant-bank kernel parameter.
+int32_t mt_epi_const(const MtPack& p, MtEpiConst* out, cudaStream_t s) {
+  memset(out, 0, sizeof(*out));
+  if (p.FPP > 24 || p.M > MT_TC_MAXM) return CAIR_OK;  // tensor-core path unsupported anyway
+  std::vector<float> wem((size_t)21 * p.FPP), bias(p.FPP), w1((size_t)p.M * p.FPP), b1(p.M);
+  CAIR_CUDA(cudaMemcpyAsync(wem.data(), p.wem, wem.size() * 4, cudaMemcpyDeviceToHost, s));
+  CAIR_CUDA(cudaMemcpyAsync(bias.data(), p.bias, bias.size() * 4, cudaMemcpyDeviceToHost, s));
+  CAIR_CUDA(cudaMemcpyAsync(w1.data(), p.w1, w1.size() * 4, cudaMemcpyDeviceToHost, s));
+  CAIR_CUDA(cudaMemcpyAsync(b1.data(), p.b1, b1.size() * 4, cudaMemcpyDeviceToHost, s));
+  CAIR_CUDA(cudaStreamSynchronize(s));
+  for (int t = 0; t < 21; ++t)
+    for (int f = 0; f < p.FPP; ++f) out->wem[t][f] = wem[(size_t)t * p.FPP + f];
+  for (int f = 0; f < p.FPP; ++f) out->bias[f] = bias[f];
+  for (int m = 0; m < p.M; ++m) {
+    out->b1[m] = b1[m];
+    for (int f = 0; f < p.FPP; ++f) out->w1[m][f] = w1[(size_t)m * p.FPP + f];
+  }
+  return CAIR_OK;
+}
+
+int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const float* cq, const float* cd, uint8_t* timg,
+                       float* maxbuf, const int64_t* q, const int64_t* d, int N, int Lq, int Ld, int64_t pair_begin,
                        int64_t pair_count, int64_t q_begin, int64_t nq, float* scores, cudaStream_t s) {
   (void)maxbuf;
   if (pair_count <= 0) return CAIR_OK;
@@ -353,12 +366,12 @@ int32_t mt_tc_interact(const MtPack& p, const float* cq, const float* cd, uint8_
   const unsigned grid = (unsigned)(pair_count < kSMs ? pair_count : kSMs);
   if (p.nf == 6) {
     CAIR_CUDA(cudaFuncSetAttribute(mt_tc_interact_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CAIR_LAUNCH(mt_tc_interact_kernel<6>, grid, TC_THREADS, smem, s, cd, timg, p, q, d, N, Lq, Ld, CP, ntiles, nstages,
-                pair_begin, pair_count, q_begin, scores);
+    CAIR_LAUNCH(mt_tc_interact_kernel<6>, grid, TC_THREADS, smem, s, cd, timg, p, ec, q, d, N, Lq, Ld, CP, ntiles,
+                nstages, pair_begin, pair_count, q_begin, scores);
   } else {
     CAIR_CUDA(cudaFuncSetAttribute(mt_tc_interact_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CAIR_LAUNCH(mt_tc_interact_kernel<4>, grid, TC_THREADS, smem, s, cd, timg, p, q, d, N, Lq, Ld, CP, ntiles, nstages,
-                pair_begin, pair_count, q_begin, scores);
+    CAIR_LAUNCH(mt_tc_interact_kernel<4>, grid, TC_THREADS, smem, s, cd, timg, p, ec, q, d, N, Lq, Ld, CP, ntiles,
+                nstages, pair_begin, pair_count, q_begin, scores);
   }
   return CAIR_OK;
 }
