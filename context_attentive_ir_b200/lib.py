@@ -28,6 +28,7 @@ PROTOTYPES = {
     'cair_lstm_forward': (i32, [vp, vp, i32, i32, i32, i32, C.POINTER(_abi.LstmDir), C.POINTER(_abi.LstmDir),
                                 vp, vp, vp, vp]),
     'cair_umma_selftest': (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
+    'cair_umma_bench': (i32, [i32, i32, i32, i32, vp, vp]),
     'cair_esm_create': (i32, [C.POINTER(_abi.EsmWeights), i32, C.POINTER(vp)]),
     'cair_mt_create': (i32, [C.POINTER(_abi.MtWeights), i32, C.POINTER(vp)]),
     'cair_mt_set_debug': (i32, [vp, vp, vp]),

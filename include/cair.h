@@ -125,6 +125,12 @@ CAIR_API int32_t cair_lstm_forward(const float* x, const int64_t* len, int32_t n
 CAIR_API int32_t cair_umma_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K,
                                     int32_t shift, int32_t split, void* stream);
 
+/* Microbenchmark of the tcgen05 issue path: `reps` x K/16 back-to-back MMAs (M=128, N, bf16) by one CTA;
+ * cycles[0] = SM cycles to issue them, cycles[1] = cycles until they have all retired (device int64[2]).
+ * uniform=1: whole-warp uniform issue loop (as the product kernels), 0: single-thread issue. */
+CAIR_API int32_t cair_umma_bench(int32_t N, int32_t K, int32_t reps, int32_t uniform, long long* cycles,
+                                 void* stream);
+
 /* ---- ESM (neuroir/rankers/esm.py:19-45) --------------------------------------------------- */
 typedef struct {
   int32_t vocab, emsize;
