@@ -100,31 +100,32 @@ extern "C" int32_t cair_umma_selftest(const float* A, const float* B, float* D, 
   return CAIR_OK;
 }
 
-// ---- issue/throughput microbenchmark: `reps` back-to-back passes of K/16 MMAs (M=128, N) on zeroed operands ----
+// ---- issue/throughput microbenchmark: `reps` back-to-back passes of K/16 MMAs (M=128, N) on zeroed operands,
+// issued concurrently by `nwarps` warps (each into its own TMEM columns) ----
 namespace cair {
 using namespace umma;
-__global__ void __launch_bounds__(128) umma_bench_kernel(int N, int K, int reps, int uniform, uint32_t tcols,
+__global__ void __launch_bounds__(160) umma_bench_kernel(int N, int K, int reps, int uniform, int nwarps, uint32_t tcols,
                                                          long long* __restrict__ cycles) {
   extern __shared__ __align__(128) uint8_t sm[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar[4];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int KC = K / 8;
   const uint32_t a_plane = 128 * 16, b_plane = N * 16;
-  for (int i = tid; i < (int)((size_t)KC * (a_plane + b_plane) / 16); i += 128) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (int)((size_t)KC * (a_plane + b_plane) / 16); i += 160) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 0) tmem_alloc(&tmem_slot, tcols);
   if (tid == 0) {
-    mbar_init(&bar, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
     fence_mbar_init();
   }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tbase = tmem_slot;
   const uint32_t idesc = idesc_bf16_f32(128, N);
   const uint32_t a0 = smem_u32(sm), b0 = a0 + KC * a_plane;
-  if (warp == 1) {
+  if (warp >= 1 && warp <= nwarps) {
+    const uint32_t tbase = tmem_slot + (uint32_t)(warp - 1) * N;
     long long t0 = clock64();
     if (uniform) {
       const uint32_t issue = elect_one();
@@ -133,33 +134,38 @@ __global__ void __launch_bounds__(128) umma_bench_kernel(int N, int K, int reps,
         for (int ks = 0; ks < K / 16; ++ks)
           mma_bf16_ss_w(tbase, ad + (uint64_t)(ks * ((2 * a_plane) >> 4)), bd + (uint64_t)(ks * ((2 * b_plane) >> 4)), idesc, 1, issue);
       long long t1 = clock64();
-      mma_commit_w(&bar, issue);
-      mbar_wait(&bar, 0);
+      mma_commit_w(&bar[warp - 1], issue);
+      mbar_wait(&bar[warp - 1], 0);
       long long t2 = clock64();
-      if (issue) cycles[0] = t1 - t0, cycles[1] = t2 - t0;
+      if (issue) cycles[2 * (warp - 1)] = t1 - t0, cycles[2 * (warp - 1) + 1] = t2 - t0;
     } else if ((tid & 31) == 0) {
       for (int r = 0; r < reps; ++r)
         for (int ks = 0; ks < K / 16; ++ks)
           mma_bf16_ss(tbase, smem_desc(a0 + (2 * ks) * a_plane, a_plane, 128), smem_desc(b0 + (2 * ks) * b_plane, b_plane, 128), idesc, true);
       long long t1 = clock64();
-      mma_commit(&bar);
-      mbar_wait(&bar, 0);
+      mma_commit(&bar[warp - 1]);
+      mbar_wait(&bar[warp - 1], 0);
       long long t2 = clock64();
-      cycles[0] = t1 - t0, cycles[1] = t2 - t0;
+      cycles[2 * (warp - 1)] = t1 - t0, cycles[2 * (warp - 1) + 1] = t2 - t0;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tbase, tcols);
+  if (warp == 0) tmem_dealloc(tmem_slot, tcols);
 }
 }  // namespace cair
 
-extern "C" int32_t cair_umma_bench(int32_t N, int32_t K, int32_t reps, int32_t uniform, long long* cycles, void* stream) {
+extern "C" CAIR_API int32_t cair_umma_bench(int32_t N, int32_t K, int32_t reps, int32_t uniform, long long* cycles,
+                                            void* stream) {
   using namespace cair;
+  // uniform: bit 0 = warp-uniform issue loop, bits 4.. = number of concurrently issuing warps (default 1)
+  int nwarps = uniform >> 4;
+  if (nwarps < 1) nwarps = 1;
+  if (nwarps > 4 || nwarps * N > 512) return fail(CAIR_ERR_BAD_ARG, "umma_bench: too many warps / columns");
   size_t smem = (size_t)(K / 8) * 16 * (128 + N);
   uint32_t tcols = 32;
-  while ((int)tcols < N) tcols <<= 1;
+  while ((int)tcols < nwarps * N) tcols <<= 1;
   CAIR_CUDA(cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CAIR_LAUNCH(umma_bench_kernel, 1, 128, smem, (cudaStream_t)stream, N, K, reps, uniform, tcols, cycles);
+  CAIR_LAUNCH(umma_bench_kernel, 1, 160, smem, (cudaStream_t)stream, N, K, reps, uniform & 1, nwarps, tcols, cycles);
   return CAIR_OK;
 }

@@ -4,13 +4,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from context_attentive_ir_b200 import lib
 L = C.CDLL(lib.LIB_PATH)
-out = torch.zeros(2, dtype=torch.int64, device='cuda')
-for uniform in (0, 1):
-    for N in (16, 32, 64, 96, 128, 256):
-        for K in (64,):
-            reps = 200
-            L.cair_umma_bench(N, K, reps, uniform, C.c_void_p(out.data_ptr()), None)
-            torch.cuda.synchronize()
-            n = reps * K // 16
-            print('uniform=%d N=%3d: issue %.1f cyc/MMA, issue+drain %.1f cyc/MMA (floor %.0f)' % (
-                uniform, N, out[0].item() / n, out[1].item() / n, 128 * N / 256))
+out = torch.zeros(8, dtype=torch.int64, device='cuda')
+for nw in (1, 2, 4):
+    for N in (16, 32, 64, 96, 128):
+        if nw * N > 512:
+            continue
+        reps, K = 200, 64
+        L.cair_umma_bench(N, K, reps, 1 | (nw << 4), C.c_void_p(out.data_ptr()), None)
+        torch.cuda.synchronize()
+        n = reps * K // 16
+        o = out.cpu().tolist()
+        print('warps=%d N=%3d: per-warp issue %.1f cyc/MMA, all retired after %.1f cyc per (MMA of one warp) => %.1f cyc/MMA aggregate (floor %.0f)' % (
+            nw, N, o[0] / n, max(o[1:2 * nw:2]) / n, max(o[1:2 * nw:2]) / n / nw, 128 * N / 256))
