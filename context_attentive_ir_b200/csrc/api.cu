@@ -208,6 +208,13 @@ int32_t cair_mt_set_impl(cair_handle* h, int32_t impl) {
   return CAIR_OK;
 }
 
+namespace cair { extern long long* g_mt_dbg; }
+// debugging aid (not in the public header): role-timing counters of the tcgen05 interaction kernel
+extern "C" __attribute__((visibility("default"))) int32_t cair_mt_debug_timing(long long* dev_counters) {
+  cair::g_mt_dbg = dev_counters;
+  return CAIR_OK;
+}
+
 int32_t cair_drmm_create(const cair_drmm_weights* w, int32_t device, cair_handle** out) {
   if (!w || !w->table) return fail(CAIR_ERR_BAD_ARG, "drmm_create: bad weights");
   if (w->nbins != 5) return fail(CAIR_ERR_UNSUPPORTED, "drmm_create: nbins must be 5 (neuroir/hyparam.py:78-81)");

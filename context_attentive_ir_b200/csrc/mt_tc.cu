@@ -88,12 +88,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Optional role timing (dbg != nullptr, CTA 0 only): cycles spent in each wait / phase, see cair_mt_debug_timing.
+#define TC_T0() long long t0_ = dbg ? clock64() : 0
+#define TC_ACC(slot) do { if (dbg && blockIdx.x == 0 && lane == 0) dbg[slot] += clock64() - t0_; } while (0)
+
 template <int NF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     mt_tc_interact_kernel(const float* __restrict__ cd, const uint8_t* __restrict__ timg, MtPack p,
                           const __grid_constant__ MtEpiConst ec, const int64_t* __restrict__ q,
                           const int64_t* __restrict__ d, int N, int Lq, int Ld, int CP, int ntiles, int nstages,
-                          int64_t pair_begin, int64_t pair_count, int64_t q_begin, float* __restrict__ scores) {
+                          int64_t pair_begin, int64_t pair_count, int64_t q_begin, float* __restrict__ scores,
+                          long long* __restrict__ dbg) {
   constexpr int FP = 3 * NF, FPP = (FP + 3) & ~3, IPT = TC_NROWS / FP;
   extern __shared__ __align__(128) uint8_t smraw[];
   __shared__ uint64_t full_b[8], empty_b[8], acc_full[2], acc_empty[2], a_full;
@@ -143,7 +148,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int t = 0; t < ntiles * 7; ++t, ++it) {
           const int s = it % nstages;
           const uint32_t ph = (it / nstages) & 1;
-          mbar_wait_relaxed(&empty_b[s], ph ^ 1);
+          { TC_T0(); mbar_wait_relaxed(&empty_b[s], ph ^ 1); TC_ACC(0); }
           mbar_arrive_expect_tx(&full_b[s], slab);
           bulk_g2s(b_ring + (size_t)s * slab, src + (size_t)t * slab, slab, &full_b[s]);
         }
@@ -159,16 +164,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const uint32_t a_ks = (2 * a_plane) >> 4, b_ks = (2 * b_plane) >> 4, b_lo_off = b_half >> 4;
       const int nks = CP / 16;
       uint32_t it = 0, tile = 0, pair_it = 0;
+      const long long tk0 = dbg ? clock64() : 0;
       for (int64_t pl = blockIdx.x; pl < pair_count; pl += gridDim.x, ++pair_it) {
-        mbar_wait(&a_full, pair_it & 1);
+        if (dbg && blockIdx.x == 0 && lane == 0) dbg[7] = clock64() - tk0, dbg[8] = pair_it;
+        { TC_T0(); mbar_wait(&a_full, pair_it & 1); TC_ACC(1); }
         tc_fence_after();
         for (int nt = 0; nt < ntiles; ++nt, ++tile) {
           const int as = tile & 1;
-          mbar_wait(&acc_empty[as], ((tile >> 1) & 1) ^ 1);
+          { TC_T0(); mbar_wait(&acc_empty[as], ((tile >> 1) & 1) ^ 1); TC_ACC(2); }
           tc_fence_after();
           for (int bt = 0; bt < 7; ++bt, ++it) {
             const int s = it % nstages;
-            mbar_wait(&full_b[s], (it / nstages) & 1);
+            { TC_T0(); mbar_wait(&full_b[s], (it / nstages) & 1); TC_ACC(3); }
             tc_fence_after();
             const uint64_t bd_hi = smem_desc(b0 + (uint32_t)s * slab, b_plane, 128);
             const uint32_t accf = bt != 0;
@@ -202,6 +209,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (int64_t pl = blockIdx.x; pl < pair_count; pl += gridDim.x) {
       const int64_t pg = pair_begin + pl;
       const int64_t b = pg / N;
+      TC_T0();
       // ---- stage A (previous pair's MMAs have retired: its last acc_full was observed) ----
       const float* cdp = cd + (size_t)pl * Ld * C;
       for (int u = et; u < RA * KC; u += TC_EPI_THREADS) {
@@ -233,6 +241,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       for (int i = et; i < Lq; i += TC_EPI_THREADS) qids[i] = (int)q[b * Lq + i];
       fence_proxy_async();
       named_bar_sync(1, TC_EPI_THREADS);          // dids/qids visible to all epilogue threads
+      if (warp == 0) TC_ACC(5);
       if (lane == 0) mbar_arrive(&a_full);
 
       float mx[MT_TC_MAXM];
@@ -244,8 +253,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
       for (int nt = 0; nt < ntiles; ++nt, ++tile) {
         const int as = tile & 1;
-        mbar_wait_relaxed(&acc_full[as], (tile >> 1) & 1);
+        { TC_T0(); mbar_wait_relaxed(&acc_full[as], (tile >> 1) & 1); if (warp == 0) TC_ACC(4); }
         tc_fence_after();
+        const long long te0_ = dbg ? clock64() : 0;
         if (mt < nmt) {
           const uint32_t tacc = tbase + ((uint32_t)lane_base << 16) + (uint32_t)(as * 2 + mt) * TC_NROWS;
 #pragma unroll 1
@@ -291,6 +301,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         tc_fence_before();
         __syncwarp();
+        if (dbg && blockIdx.x == 0 && warp == 0 && lane == 0) dbg[6] += clock64() - te0_;
         if (lane == 0) mbar_arrive(&acc_empty[as]);
       }
       // ---- max over all rows of the pair, Linear(M -> 1), one store ----
@@ -318,6 +329,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   __syncthreads();
   if (warp == 0) tmem_dealloc(tbase, TC_TCOLS);
 }
+
+long long* g_mt_dbg = nullptr;  // device buffer of 16 counters when role timing is on (tools/mt_timing.py)
 
 bool mt_tc_supported(const MtPack& p, int Lq, int Ld) {
   if (p.nf != 4 && p.nf != 6) return false;
@@ -369,11 +382,11 @@ int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const float* cq, c
   if (p.nf == 6) {
     CAIR_CUDA(cudaFuncSetAttribute(mt_tc_interact_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CAIR_LAUNCH(mt_tc_interact_kernel<6>, grid, TC_THREADS, smem, s, cd, timg, p, ec, q, d, N, Lq, Ld, CP, ntiles,
-                nstages, pair_begin, pair_count, q_begin, scores);
+                nstages, pair_begin, pair_count, q_begin, scores, g_mt_dbg);
   } else {
     CAIR_CUDA(cudaFuncSetAttribute(mt_tc_interact_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CAIR_LAUNCH(mt_tc_interact_kernel<4>, grid, TC_THREADS, smem, s, cd, timg, p, ec, q, d, N, Lq, Ld, CP, ntiles,
-                nstages, pair_begin, pair_count, q_begin, scores);
+                nstages, pair_begin, pair_count, q_begin, scores, g_mt_dbg);
   }
   return CAIR_OK;
 }
