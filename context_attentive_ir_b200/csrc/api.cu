@@ -208,7 +208,6 @@ int32_t cair_mt_set_impl(cair_handle* h, int32_t impl) {
   return CAIR_OK;
 }
 
-namespace cair { extern long long* g_mt_dbg; }
 // debugging aid (not in the public header): role-timing counters of the tcgen05 interaction kernel
 extern "C" __attribute__((visibility("default"))) int32_t cair_mt_debug_timing(long long* dev_counters) {
   cair::g_mt_dbg = dev_counters;

@@ -52,6 +52,7 @@ int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const float* cq, c
                        const int64_t* q, const int64_t* d, int N, int Lq, int Ld, int64_t pair_begin,
                        int64_t pair_count, int64_t q_begin, int64_t nq, float* scores, cudaStream_t s);
 
+extern long long* g_mt_dbg;  // optional role-timing counters of the tcgen05 interaction kernel (debug)
 enum { MT_IMPL_FP32 = 0, MT_IMPL_TC = 1 };
 struct MtState {
   int V = 0, E = 0, F = 0, Hq = 0, Hd = 0, C = 0;
