@@ -283,18 +283,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               }
 #pragma unroll
               for (int f = 0; f < FPP; ++f) y[f] = fmaxf(y[f], 0.f);
+              // 1x1 conv: f outer, m inner -> MT_TC_MAXM independent accumulators, no dependent-FMA stalls;
+              // weights are constant-bank operands.  Outputs m >= M compute on zero weights and are ignored.
+              float z[MT_TC_MAXM];
 #pragma unroll
-              for (int m = 0; m < MT_TC_MAXM; ++m) {
-                if (m < M) {
-                  // two independent FMA chains per output (ILP), weights as constant-bank operands
-                  float z0 = ec.b1[m], z1 = 0.f;
+              for (int m = 0; m < MT_TC_MAXM; ++m) z[m] = ec.b1[m];
+              if (M <= 20) {
 #pragma unroll
-                  for (int f = 0; f < FP; f += 2) {
-                    z0 = fmaf(ec.w1[m][f], y[f], z0);
-                    if (f + 1 < FP) z1 = fmaf(ec.w1[m][f + 1], y[f + 1], z1);
-                  }
-                  mx[m] = fmaxf(mx[m], z0 + z1);
-                }
+                for (int f = 0; f < FP; ++f)
+#pragma unroll
+                  for (int m = 0; m < 20; ++m) z[m] = fmaf(ec.w1[m][f], y[f], z[m]);
+#pragma unroll
+                for (int m = 0; m < 20; ++m) mx[m] = fmaxf(mx[m], z[m]);
+              } else {
+#pragma unroll
+                for (int f = 0; f < FP; ++f)
+#pragma unroll
+                  for (int m = 0; m < MT_TC_MAXM; ++m) z[m] = fmaf(ec.w1[m][f], y[f], z[m]);
+#pragma unroll
+                for (int m = 0; m < MT_TC_MAXM; ++m) mx[m] = fmaxf(mx[m], z[m]);
               }
             }
           }
