@@ -42,7 +42,7 @@ static inline size_t tc_slab_bytes(int CP) { return (size_t)2 * (CP / 8) * TC_NR
 static inline size_t tc_a_bytes(int CP) { return (size_t)2 * (CP / 8) * TC_MAXRA * 16; }
 static inline size_t tc_misc_bytes(const MtPack& p, int Lq) {
   (void)p;
-  return (size_t)(MT_TC_MAXM * 8) * sizeof(float) + (size_t)(TC_MAXRA + 8 + Lq) * sizeof(int);
+  return (size_t)(MT_TC_MAXM * 8 + 24 * MT_TC_MAXM) * sizeof(float) + (size_t)(TC_MAXRA + 8 + Lq) * sizeof(int);
 }
 static inline int tc_stages(const MtPack& p, int Lq) {
   const int CP = tc_cp(p.C);
@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   // epilogue weights (exact-match taps, bias, 1x1 conv) come from the constant bank (kernel parameter `ec`):
   // FFMA takes them as immediate c[][] operands, no shared-memory loads in the hot loop
   float* red = reinterpret_cast<float*>(b_ring + (size_t)nstages * slab);  // [8 warps][32]
-  int* dids = reinterpret_cast<int*>(red + MT_TC_MAXM * 8);
+  float* w1t = red + MT_TC_MAXM * 8;               // [24][32] 1x1 conv weights, transposed (m contiguous)
+  int* dids = reinterpret_cast<int*>(w1t + 24 * MT_TC_MAXM);
   int* qids = dids + TC_MAXRA + 8;
 
   if (warp == 0) tmem_alloc(&tmem_slot, TC_TCOLS);
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     mbar_init(&a_full, 8);
     fence_mbar_init();
   }
+  for (int i = tid; i < 24 * MT_TC_MAXM; i += TC_THREADS) w1t[i] = ec.w1[i % MT_TC_MAXM][i / MT_TC_MAXM];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -283,23 +285,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               }
 #pragma unroll
               for (int f = 0; f < FPP; ++f) y[f] = fmaxf(y[f], 0.f);
-              // 1x1 conv: f outer, m inner -> MT_TC_MAXM independent accumulators, no dependent-FMA stalls;
-              // weights are constant-bank operands.  Outputs m >= M compute on zero weights and are ignored.
+              // 1x1 conv: f outer, m inner -> independent accumulators (no dependent-FMA stalls); the weights
+              // come from shared memory as broadcast LDS.128 (w1t[f][m], m contiguous).  Outputs m >= M see zero
+              // weights and are ignored at the end.
               float z[MT_TC_MAXM];
 #pragma unroll
               for (int m = 0; m < MT_TC_MAXM; ++m) z[m] = ec.b1[m];
               if (M <= 20) {
 #pragma unroll
-                for (int f = 0; f < FP; ++f)
+                for (int f = 0; f < FP; ++f) {
+                  const float4* wr = reinterpret_cast<const float4*>(w1t + f * MT_TC_MAXM);
 #pragma unroll
-                  for (int m = 0; m < 20; ++m) z[m] = fmaf(ec.w1[m][f], y[f], z[m]);
+                  for (int m4 = 0; m4 < 5; ++m4) {
+                    const float4 w4 = wr[m4];
+                    z[4 * m4 + 0] = fmaf(w4.x, y[f], z[4 * m4 + 0]);
+                    z[4 * m4 + 1] = fmaf(w4.y, y[f], z[4 * m4 + 1]);
+                    z[4 * m4 + 2] = fmaf(w4.z, y[f], z[4 * m4 + 2]);
+                    z[4 * m4 + 3] = fmaf(w4.w, y[f], z[4 * m4 + 3]);
+                  }
+                }
 #pragma unroll
                 for (int m = 0; m < 20; ++m) mx[m] = fmaxf(mx[m], z[m]);
               } else {
 #pragma unroll
-                for (int f = 0; f < FP; ++f)
+                for (int f = 0; f < FP; ++f) {
+                  const float4* wr = reinterpret_cast<const float4*>(w1t + f * MT_TC_MAXM);
 #pragma unroll
-                  for (int m = 0; m < MT_TC_MAXM; ++m) z[m] = fmaf(ec.w1[m][f], y[f], z[m]);
+                  for (int m4 = 0; m4 < MT_TC_MAXM / 4; ++m4) {
+                    const float4 w4 = wr[m4];
+                    z[4 * m4 + 0] = fmaf(w4.x, y[f], z[4 * m4 + 0]);
+                    z[4 * m4 + 1] = fmaf(w4.y, y[f], z[4 * m4 + 1]);
+                    z[4 * m4 + 2] = fmaf(w4.z, y[f], z[4 * m4 + 2]);
+                    z[4 * m4 + 3] = fmaf(w4.w, y[f], z[4 * m4 + 3]);
+                  }
+                }
 #pragma unroll
                 for (int m = 0; m < MT_TC_MAXM; ++m) mx[m] = fmaxf(mx[m], z[m]);
               }
