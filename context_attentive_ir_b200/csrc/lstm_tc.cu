@@ -10,9 +10,10 @@
 // keeps ~fp32 accuracy through the 200-step recurrence (plain bf16/tf32 does not hold the 1e-3 bar).
 // Gate rows are permuted so that TMEM lane quarter q of row tile m holds gate type q (i,f,g,o) of units
 // 32m..32m+31: the activation is warp-uniform and bias is a per-thread scalar.
-// Warp roles (288 threads): warps 0-7 epilogue (phase 1: tcgen05.ld + sigmoid/tanh -> smem; phase 2: c/h
-// update in registers, h written as next step's bf16 hi/lo operand + fp32 memory bank), warp 8: MMA issuer
-// and gather of x_{t+1} (embedding rows by token id, or dense rows) into the other operand buffer.
+// Warp roles (320 threads): warps 0-7 epilogue (phase 1: tcgen05.ld + sigmoid/tanh -> smem; phase 2: c/h
+// update in registers, h written as next step's bf16 hi/lo operand + fp32 memory bank), warp 8: MMA issuer,
+// warp 9: gather of x (embedding rows by token id, or dense rows) into a 4-slot operand ring, running up
+// to 3 steps ahead so the global-load latency never sits on the recurrence's critical path.
 #include "models.cuh"
 #include "umma.cuh"
 
@@ -25,7 +26,7 @@ constexpr int LT_HP = 64;                 // K slots of the h part (h <= 64)
 constexpr int LT_K = LT_XP + LT_HP;       // 112
 constexpr int LT_PLANES = LT_K / 8;       // 14
 constexpr int LT_NSEQ = 32;               // sequences per CTA = N of the MMA
-constexpr int LT_THREADS = 288;
+constexpr int LT_THREADS = 320;
 constexpr uint32_t LT_APLANE = 128 * 16;  // weight image: 128 rows per plane
 constexpr uint32_t LT_BPLANE = LT_NSEQ * 16;
 constexpr uint32_t LT_AIMG = LT_PLANES * LT_APLANE;  // one (row tile, hi|lo) image: 28672 B
@@ -85,13 +86,17 @@ __device__ __forceinline__ float lt_tanh(float x) {
   return __fdividef(1.0f - e, 1.0f + e);
 }
 
-// smem: W image (4 x LT_AIMG) | B images [2 parities][hi|lo] (4 x LT_BIMG) | gsm [4][32][64] f32 | slen[32]
+constexpr int LT_XS = 4;                                   // x-operand ring slots (gather runs up to 3 steps ahead)
+constexpr uint32_t LT_XIMG = (LT_XP / 8) * LT_BPLANE;     // one (hi|lo) x image: 6 planes, 3072 B
+constexpr uint32_t LT_HIMG = (LT_HP / 8) * LT_BPLANE;     // one (hi|lo) h image: 8 planes, 4096 B
+
+// smem: W image (4 x LT_AIMG) | h operand [2 parities][hi|lo] | x operand ring [LT_XS][hi|lo] | gsm [4][32][64] f32
 __global__ void __launch_bounds__(LT_THREADS, 1)
     lstm_tc_kernel(GemmA x, const uint8_t* __restrict__ wimg_all, const float* __restrict__ bias_all,
                    const int64_t* __restrict__ len, int n, int L, int in, int h, int dirs, uint32_t ks_mask,
                    float* __restrict__ out, float* __restrict__ h_n, float* __restrict__ c_n, int* err) {
   extern __shared__ __align__(128) uint8_t smraw[];
-  __shared__ uint64_t bar_w, bar_b, bar_acc;
+  __shared__ uint64_t bar_w, bar_h, bar_acc, x_full[LT_XS], x_empty[LT_XS];
   __shared__ uint32_t tmem_slot;
   __shared__ int slen[LT_NSEQ];
   __shared__ int smaxlen;
@@ -99,16 +104,21 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
   const int dir = blockIdx.y, s0 = blockIdx.x * LT_NSEQ;
   const int nmt = (h + 31) / 32;  // row tiles in use (1 or 2)
   uint8_t* w_img = smraw;
-  uint8_t* b_img = w_img + 4 * LT_AIMG;
-  float* gsm = reinterpret_cast<float*>(b_img + 4 * LT_BIMG);
+  uint8_t* h_img = w_img + 4 * LT_AIMG;
+  uint8_t* x_img = h_img + 4 * LT_HIMG;
+  float* gsm = reinterpret_cast<float*>(x_img + 2 * LT_XS * LT_XIMG);
   const float* bias = bias_all + (size_t)dir * 4 * h;
   const int Hout = dirs * h;
 
   if (warp == 0) tmem_alloc(&tmem_slot, 64);
   if (tid == 32) {
     mbar_init(&bar_w, 1);
-    mbar_init(&bar_b, 9);    // 8 epilogue warps (h written) + the MMA warp (x written)
+    mbar_init(&bar_h, 8);     // 8 epilogue warps: h_t written as next step's operand
     mbar_init(&bar_acc, 1);
+    for (int i = 0; i < LT_XS; ++i) {
+      mbar_init(&x_full[i], 1);
+      mbar_init(&x_empty[i], 1);
+    }
     fence_mbar_init();
   }
   if (tid < LT_NSEQ) {
@@ -123,8 +133,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     }
     slen[tid] = l;
   }
-  // zero both operand buffers (h_0 = 0, K padding stays zero for ever)
-  for (int i = tid; i < (int)(4 * LT_BIMG / 16); i += LT_THREADS) reinterpret_cast<uint4*>(b_img)[i] = make_uint4(0, 0, 0, 0);
+  // zero the operand buffers (h_0 = 0, K padding stays zero for ever)
+  for (int i = tid; i < (int)((4 * LT_HIMG + 2 * LT_XS * LT_XIMG) / 16); i += LT_THREADS)
+    reinterpret_cast<uint4*>(h_img)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -149,58 +161,71 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
   const int maxlen = smaxlen;
   const uint32_t tbase = tmem_slot;
 
-  if (warp == 8) {
-    // ===================== MMA issuer + x gather =====================
-    const int myl = slen[lane];
-    auto gather_x = [&](int step, int parity) {
-      // lane <-> sequence row; x row -> hi/lo bf16 -> x planes of operand buffer `parity`
-      uint8_t* bh = b_img + (size_t)parity * 2 * LT_BIMG;
+  if (warp == 9) {
+    // ===================== x gather: embedding rows (or dense rows) -> hi/lo bf16 ring, runs ahead =====================
+    const int myl = slen[lane];   // lane <-> sequence row
+    const bool vec = (in & 3) == 0 && (x.table ? ((x.E & 3) == 0) : ((x.lda & 3) == 0));
+    for (int step = 0; step < maxlen; ++step) {
+      const int slot = step % LT_XS;
+      mbar_wait_relaxed(&x_empty[slot], ((step / LT_XS) & 1) ^ 1);
       const bool active = step < myl;
       const int t = dir ? myl - 1 - step : step;
       const int64_t r = (int64_t)(s0 + lane) * L + (active ? t : 0);
       const float* src = nullptr;
-      if (active) {
-        if (x.table) {
-          int64_t id = checked_id(x.ids[r], x.V, x.err);
-          src = x.table + id * x.E;
-        } else {
-          src = x.dense + r * x.lda;
+      if (active) src = x.table ? x.table + checked_id(x.ids[r], x.V, x.err) * x.E : x.dense + r * x.lda;
+      float v[LT_XP];
+#pragma unroll
+      for (int k4 = 0; k4 < LT_XP / 4; ++k4) {
+        float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active && k4 * 4 < in) {
+          if (vec) {
+            f4 = *reinterpret_cast<const float4*>(src + k4 * 4);
+          } else {
+            f4.x = src[k4 * 4];
+            if (k4 * 4 + 1 < in) f4.y = src[k4 * 4 + 1];
+            if (k4 * 4 + 2 < in) f4.z = src[k4 * 4 + 2];
+            if (k4 * 4 + 3 < in) f4.w = src[k4 * 4 + 3];
+          }
         }
+        v[4 * k4] = f4.x, v[4 * k4 + 1] = f4.y, v[4 * k4 + 2] = f4.z, v[4 * k4 + 3] = f4.w;
       }
-      for (int pl = 0; pl * 8 < in; ++pl) {
-        float v[8];
+      uint8_t* xh = x_img + (size_t)slot * 2 * LT_XIMG;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = (active && pl * 8 + e < in) ? src[pl * 8 + e] : 0.f;
-        uint32_t hi[4], lo[4];
+      for (int pl = 0; pl < LT_XP / 8; ++pl) {
+        if (pl * 8 < in) {
+          uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(v[2 * e], h0, l0);
-          split_bf16(v[2 * e + 1], h1, l1);
-          hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-          lo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(v[pl * 8 + 2 * e], h0, l0);
+            split_bf16(v[pl * 8 + 2 * e + 1], h1, l1);
+            hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          }
+          const size_t off = (size_t)pl * LT_BPLANE + (size_t)lane * 16;
+          *reinterpret_cast<uint4*>(xh + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(xh + LT_XIMG + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-        const size_t off = (size_t)pl * LT_BPLANE + (size_t)lane * 16;
-        *reinterpret_cast<uint4*>(bh + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(bh + LT_BIMG + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) lt_arrive(&bar_b);
-    };
-    gather_x(0, 0);
+      if (lane == 0) lt_arrive(&x_full[slot]);
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer (uniform control flow, one elected lane issues) =====================
     mbar_wait(&bar_w, 0);
     const uint32_t issue = elect_one();
     const uint32_t idesc = idesc_bf16_f32(128, LT_NSEQ);
-    const uint32_t w0 = smem_u32(w_img), b0 = smem_u32(b_img);
-    // descriptor bases (16-byte units are added to the low word; the address field never carries)
-    const uint64_t wd0 = smem_desc(w0, LT_APLANE, 128);
-    const uint64_t bd0 = smem_desc(b0, LT_BPLANE, 128);
+    const uint64_t wd0 = smem_desc(smem_u32(w_img), LT_APLANE, 128);
+    const uint64_t hd0 = smem_desc(smem_u32(h_img), LT_BPLANE, 128);
+    const uint64_t xd0 = smem_desc(smem_u32(x_img), LT_BPLANE, 128);
     for (int step = 0; step < maxlen; ++step) {
-      const int par = step & 1;
-      mbar_wait(&bar_b, par);
+      const int par = step & 1, slot = step % LT_XS;
+      mbar_wait(&x_full[slot], (step / LT_XS) & 1);
+      mbar_wait(&bar_h, par);
       tc_fence_after();
-      const uint64_t bdp = bd0 + (uint64_t)((uint32_t)par * 2 * LT_BIMG >> 4);
+      const uint64_t hdp = hd0 + (uint64_t)((uint32_t)par * 2 * LT_HIMG >> 4);
+      const uint64_t xdp = xd0 + (uint64_t)((uint32_t)slot * 2 * LT_XIMG >> 4);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         if (mt < nmt) {
@@ -210,12 +235,14 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
             const uint64_t wp = wdm + (pass == 1 ? (LT_AIMG >> 4) : 0);   // weights: hi, lo, hi
-            const uint64_t bp = bdp + (pass == 2 ? (LT_BIMG >> 4) : 0);   // activations: hi, hi, lo
+            const uint64_t xp = xdp + (pass == 2 ? (LT_XIMG >> 4) : 0);   // activations: hi, hi, lo
+            const uint64_t hp = hdp + (pass == 2 ? (LT_HIMG >> 4) : 0);
 #pragma unroll
             for (int ks = 0; ks < LT_K / 16; ++ks) {
               if ((ks_mask >> ks) & 1) {
-                mma_bf16_ss_w(tacc, wp + (uint64_t)((2 * ks) * (LT_APLANE >> 4)), bp + (uint64_t)((2 * ks) * (LT_BPLANE >> 4)),
-                              idesc, acc, issue);
+                const uint64_t bd = (ks < LT_XP / 16) ? xp + (uint64_t)((2 * ks) * (LT_BPLANE >> 4))
+                                                      : hp + (uint64_t)((2 * (ks - LT_XP / 16)) * (LT_BPLANE >> 4));
+                mma_bf16_ss_w(tacc, wp + (uint64_t)((2 * ks) * (LT_APLANE >> 4)), bd, idesc, acc, issue);
                 acc = 1;
               }
             }
@@ -223,8 +250,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
         }
       }
       mma_commit_w(&bar_acc, issue);
-      __syncwarp();
-      if (step + 1 < maxlen) gather_x(step + 1, par ^ 1);
+      mma_commit_w(&x_empty[slot], issue);
     }
   } else {
     // ===================== epilogue warps =====================
@@ -235,7 +261,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     float cst[8], hst[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) cst[k] = 0.f, hst[k] = 0.f;
-    if (lane == 0 && maxlen > 0) lt_arrive(&bar_b);   // h_0 = 0 is already in operand buffer 0
+    if (lane == 0 && maxlen > 0) lt_arrive(&bar_h);   // h_0 = 0 is already in operand buffer 0
     for (int step = 0; step < maxlen; ++step) {
       const int par = step & 1;
       mbar_wait(&bar_acc, par);
@@ -256,7 +282,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
       tc_fence_before();
       lt_named_bar(1, 256);
       // ---- phase 2: state update for (unit u2, sequences sg + 4k) ----
-      uint8_t* bn = b_img + (size_t)(par ^ 1) * 2 * LT_BIMG;  // next step's operand buffer
+      uint8_t* hn = h_img + (size_t)(par ^ 1) * 2 * LT_HIMG;  // next step's h operand
       if (u2 < h) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -273,14 +299,14 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
           }
           __nv_bfloat16 hi, lo;
           split_bf16(hst[k], hi, lo);
-          const size_t off = (size_t)((LT_XP + u2) >> 3) * LT_BPLANE + (size_t)s * 16 + (u2 & 7) * 2;
-          *reinterpret_cast<__nv_bfloat16*>(bn + off) = hi;
-          *reinterpret_cast<__nv_bfloat16*>(bn + LT_BIMG + off) = lo;
+          const size_t off = (size_t)(u2 >> 3) * LT_BPLANE + (size_t)s * 16 + (u2 & 7) * 2;
+          *reinterpret_cast<__nv_bfloat16*>(hn + off) = hi;
+          *reinterpret_cast<__nv_bfloat16*>(hn + LT_HIMG + off) = lo;
         }
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0 && step + 1 < maxlen) lt_arrive(&bar_b);
+      if (lane == 0 && step + 1 < maxlen) lt_arrive(&bar_h);
     }
     if (u2 < h && (h_n || c_n)) {
 #pragma unroll
@@ -308,7 +334,7 @@ int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, cons
     const bool h_part = k1 > LT_XP && k0 < LT_XP + p.h;
     if (x_part || h_part) ks_mask |= 1u << ks;
   }
-  const size_t smem = (size_t)4 * LT_AIMG + 4 * LT_BIMG + (size_t)4 * 32 * 64 * sizeof(float);
+  const size_t smem = (size_t)4 * LT_AIMG + 4 * LT_HIMG + 2 * LT_XS * LT_XIMG + (size_t)4 * 32 * 64 * sizeof(float);
   CAIR_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((n + LT_NSEQ - 1) / LT_NSEQ, p.dirs);
   CAIR_LAUNCH(lstm_tc_kernel, grid, LT_THREADS, smem, s, x, p.wimg, bias, len, n, L, p.in, p.h, p.dirs, ks_mask, out,
