@@ -214,6 +214,11 @@ extern "C" __attribute__((visibility("default"))) int32_t cair_mt_debug_timing(l
   return CAIR_OK;
 }
 
+extern "C" __attribute__((visibility("default"))) int32_t cair_lstm_debug_timing(long long* dev_counters) {
+  cair::g_lstm_dbg = dev_counters;
+  return CAIR_OK;
+}
+
 int32_t cair_drmm_create(const cair_drmm_weights* w, int32_t device, cair_handle** out) {
   if (!w || !w->table) return fail(CAIR_ERR_BAD_ARG, "drmm_create: bad weights");
   if (w->nbins != 5) return fail(CAIR_ERR_UNSUPPORTED, "drmm_create: nbins must be 5 (neuroir/hyparam.py:78-81)");

@@ -188,6 +188,7 @@ struct LstmTcPack {
   int in = 0, h = 0, dirs = 0;
   uint8_t* wimg = nullptr;  // [dirs][2 row tiles][hi|lo] bf16 operand images
 };
+extern long long* g_lstm_dbg;  // optional role-timing counters (debug)
 bool lstm_tc_supported(int in, int h);
 int32_t lstm_tc_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, int in, int h, LstmTcPack* out,
                      cudaStream_t s);

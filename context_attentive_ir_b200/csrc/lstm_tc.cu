@@ -86,6 +86,11 @@ __device__ __forceinline__ float lt_tanh(float x) {
   return __fdividef(1.0f - e, 1.0f + e);
 }
 
+// Optional role timing (dbg != nullptr; CTA (0,0), lane 0 of the role's first warp), see tools/lstm_timing.py
+#define LT_T0() long long t0_ = dbg ? clock64() : 0
+#define LT_ACC(slot) do { if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) dbg[slot] += clock64() - t0_; } while (0)
+long long* g_lstm_dbg = nullptr;
+
 constexpr int LT_XS = 4;                                   // x-operand ring slots (gather runs up to 3 steps ahead)
 constexpr uint32_t LT_XIMG = (LT_XP / 8) * LT_BPLANE;     // one (hi|lo) x image: 6 planes, 3072 B
 constexpr uint32_t LT_HIMG = (LT_HP / 8) * LT_BPLANE;     // one (hi|lo) h image: 8 planes, 4096 B
@@ -94,7 +99,8 @@ constexpr uint32_t LT_HIMG = (LT_HP / 8) * LT_BPLANE;     // one (hi|lo) h image
 __global__ void __launch_bounds__(LT_THREADS, 1)
     lstm_tc_kernel(GemmA x, const uint8_t* __restrict__ wimg_all, const float* __restrict__ bias_all,
                    const int64_t* __restrict__ len, int n, int L, int in, int h, int dirs, uint32_t ks_mask,
-                   float* __restrict__ out, float* __restrict__ h_n, float* __restrict__ c_n, int* err) {
+                   float* __restrict__ out, float* __restrict__ h_n, float* __restrict__ c_n, int* err,
+                   long long* __restrict__ dbg) {
   extern __shared__ __align__(128) uint8_t smraw[];
   __shared__ uint64_t bar_w, bar_h, bar_acc, x_full[LT_XS], x_empty[LT_XS];
   __shared__ uint32_t tmem_slot;
@@ -167,7 +173,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     const bool vec = (in & 3) == 0 && (x.table ? ((x.E & 3) == 0) : ((x.lda & 3) == 0));
     for (int step = 0; step < maxlen; ++step) {
       const int slot = step % LT_XS;
-      mbar_wait_relaxed(&x_empty[slot], ((step / LT_XS) & 1) ^ 1);
+      { LT_T0(); mbar_wait_relaxed(&x_empty[slot], ((step / LT_XS) & 1) ^ 1); LT_ACC(7); }
       const bool active = step < myl;
       const int t = dir ? myl - 1 - step : step;
       const int64_t r = (int64_t)(s0 + lane) * L + (active ? t : 0);
@@ -221,9 +227,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     const uint64_t xd0 = smem_desc(smem_u32(x_img), LT_BPLANE, 128);
     for (int step = 0; step < maxlen; ++step) {
       const int par = step & 1, slot = step % LT_XS;
-      mbar_wait(&x_full[slot], (step / LT_XS) & 1);
-      mbar_wait(&bar_h, par);
+      { LT_T0(); mbar_wait(&x_full[slot], (step / LT_XS) & 1); LT_ACC(0); }
+      { LT_T0(); mbar_wait(&bar_h, par); LT_ACC(1); }
       tc_fence_after();
+      LT_T0();
       const uint64_t hdp = hd0 + (uint64_t)((uint32_t)par * 2 * LT_HIMG >> 4);
       const uint64_t xdp = xd0 + (uint64_t)((uint32_t)slot * 2 * LT_XIMG >> 4);
 #pragma unroll
@@ -251,6 +258,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
       }
       mma_commit_w(&bar_acc, issue);
       mma_commit_w(&x_empty[slot], issue);
+      LT_ACC(2);
     }
   } else {
     // ===================== epilogue warps =====================
@@ -264,8 +272,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     if (lane == 0 && maxlen > 0) lt_arrive(&bar_h);   // h_0 = 0 is already in operand buffer 0
     for (int step = 0; step < maxlen; ++step) {
       const int par = step & 1;
-      mbar_wait(&bar_acc, par);
+      { LT_T0(); mbar_wait(&bar_acc, par); if (warp == 0) LT_ACC(3); }
       tc_fence_after();
+      LT_T0();
       // ---- phase 1: activation of one gate row for 32 sequences ----
       if (mt < nmt) {
         float v[32];
@@ -280,7 +289,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
         }
       }
       tc_fence_before();
+      if (warp == 0) LT_ACC(4);
       lt_named_bar(1, 256);
+      if (warp == 0) LT_ACC(5);
       // ---- phase 2: state update for (unit u2, sequences sg + 4k) ----
       uint8_t* hn = h_img + (size_t)(par ^ 1) * 2 * LT_HIMG;  // next step's h operand
       if (u2 < h) {
@@ -306,6 +317,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
       }
       fence_proxy_async();
       __syncwarp();
+      if (warp == 0) LT_ACC(6);
       if (lane == 0 && step + 1 < maxlen) lt_arrive(&bar_h);
     }
     if (u2 < h && (h_n || c_n)) {
@@ -338,7 +350,7 @@ int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, cons
   CAIR_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((n + LT_NSEQ - 1) / LT_NSEQ, p.dirs);
   CAIR_LAUNCH(lstm_tc_kernel, grid, LT_THREADS, smem, s, x, p.wimg, bias, len, n, L, p.in, p.h, p.dirs, ks_mask, out,
-              h_n, c_n, err);
+              h_n, c_n, err, g_lstm_dbg);
   return CAIR_OK;
 }
 
