@@ -10,9 +10,9 @@
 // keeps ~fp32 accuracy through the 200-step recurrence (plain bf16/tf32 does not hold the 1e-3 bar).
 // Gate rows are permuted so that TMEM lane quarter q of row tile m holds gate type q (i,f,g,o) of units
 // 32m..32m+31: the activation is warp-uniform and bias is a per-thread scalar.
-// Warp roles (320 threads): warps 0-7 epilogue (phase 1: tcgen05.ld + sigmoid/tanh -> smem; phase 2: c/h
-// update in registers, h written as next step's bf16 hi/lo operand + fp32 memory bank), warp 8: MMA issuer,
-// warp 9: gather of x (embedding rows by token id, or dense rows) into a 4-slot operand ring, running up
+// Warp roles (576 threads): warps 0-15 epilogue (phase 1: tcgen05.ld + sigmoid/tanh -> smem; phase 2: c/h
+// update in registers, h written as next step's bf16 hi/lo operand + fp32 memory bank), warp 16: MMA issuer,
+// warp 17: gather of x (embedding rows by token id, or dense rows) into a 4-slot operand ring, running up
 // to 3 steps ahead so the global-load latency never sits on the recurrence's critical path.
 #include "models.cuh"
 #include "umma.cuh"
@@ -26,7 +26,8 @@ constexpr int LT_HP = 64;                 // K slots of the h part (h <= 64)
 constexpr int LT_K = LT_XP + LT_HP;       // 112
 constexpr int LT_PLANES = LT_K / 8;       // 14
 constexpr int LT_NSEQ = 32;               // sequences per CTA = N of the MMA
-constexpr int LT_THREADS = 320;
+constexpr int LT_EPI_WARPS = 16;          // epilogue warps (4 per SM sub-partition)
+constexpr int LT_THREADS = (LT_EPI_WARPS + 2) * 32;
 constexpr uint32_t LT_APLANE = 128 * 16;  // weight image: 128 rows per plane
 constexpr uint32_t LT_BPLANE = LT_NSEQ * 16;
 constexpr uint32_t LT_AIMG = LT_PLANES * LT_APLANE;  // one (row tile, hi|lo) image: 28672 B
@@ -75,16 +76,10 @@ __device__ __forceinline__ void lt_named_bar(int id, int n) { asm volatile("bar.
 __device__ __forceinline__ void lt_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// accurate-enough fast activations: ex2.approx (2^-22 rel) + rcp.approx (1 ulp); inputs clamped so nothing overflows
-__device__ __forceinline__ float lt_sigmoid(float x) {
-  x = fminf(fmaxf(x, -30.f), 30.f);
-  return __fdividef(1.0f, 1.0f + exp2f(-1.4426950408889634f * x));
-}
-__device__ __forceinline__ float lt_tanh(float x) {
-  x = fminf(fmaxf(x, -15.f), 15.f);
-  const float e = exp2f(-2.8853900817779268f * x);  // exp(-2x)
-  return __fdividef(1.0f - e, 1.0f + e);
-}
+// fast, accurate-enough activations: ex2.approx (2^-22 rel) + rcp.approx (1 ulp).  No clamping needed:
+// exp2 saturates to inf/0 and 1/(1+inf) = 0.  tanh(x) = 2*sigmoid(2x) - 1 shares the same two MUFU ops.
+__device__ __forceinline__ float lt_sigmoid(float x) { return __fdividef(1.0f, 1.0f + exp2f(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float lt_tanh(float x) { return fmaf(2.0f, lt_sigmoid(2.0f * x), -1.0f); }
 
 // Optional role timing (dbg != nullptr; CTA (0,0), lane 0 of the role's first warp), see tools/lstm_timing.py
 #define LT_T0() long long t0_ = dbg ? clock64() : 0
@@ -119,7 +114,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
   if (warp == 0) tmem_alloc(&tmem_slot, 64);
   if (tid == 32) {
     mbar_init(&bar_w, 1);
-    mbar_init(&bar_h, 8);     // 8 epilogue warps: h_t written as next step's operand
+    mbar_init(&bar_h, LT_EPI_WARPS);  // epilogue warps: h_t written as next step's operand
     mbar_init(&bar_acc, 1);
     for (int i = 0; i < LT_XS; ++i) {
       mbar_init(&x_full[i], 1);
@@ -167,7 +162,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
   const int maxlen = smaxlen;
   const uint32_t tbase = tmem_slot;
 
-  if (warp == 9) {
+  if (warp == LT_EPI_WARPS + 1) {
     // ===================== x gather: embedding rows (or dense rows) -> hi/lo bf16 ring, runs ahead =====================
     const int myl = slen[lane];   // lane <-> sequence row
     const bool vec = (in & 3) == 0 && (x.table ? ((x.E & 3) == 0) : ((x.lda & 3) == 0));
@@ -217,7 +212,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
       __syncwarp();
       if (lane == 0) lt_arrive(&x_full[slot]);
     }
-  } else if (warp == 8) {
+  } else if (warp == LT_EPI_WARPS) {
     // ===================== MMA issuer (uniform control flow, one elected lane issues) =====================
     mbar_wait(&bar_w, 0);
     const uint32_t issue = elect_one();
@@ -262,50 +257,56 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     }
   } else {
     // ===================== epilogue warps =====================
-    const int mt = warp >> 2, type = warp & 3;       // phase 1: row tile, gate type (= TMEM lane quarter)
-    const int u1 = mt * 32 + lane;                    // phase 1 unit
+    // phase 1: warp -> (row tile mt, gate type = TMEM lane quarter, half of the 32 sequences); lane -> unit
+    const int type = warp & 3, mt = (warp >> 2) & 1, shalf = warp >> 3;
+    const int u1 = mt * 32 + lane;
     const float bias1 = (u1 < h) ? bias[type * h + u1] : 0.f;
-    const int u2 = tid & 63, sg = tid >> 6;           // phase 2: unit, sequence group (s = sg + 4k)
-    float cst[8], hst[8];
+    const float pre = (type == 2) ? 2.0f : 1.0f;     // tanh(x) = 2*sigmoid(2x) - 1 for the cell gate
+    const float post_a = (type == 2) ? 2.0f : 1.0f, post_b = (type == 2) ? -1.0f : 0.0f;
+    // phase 2: thread -> unit u2, sequences s = sg + 8k (k < 4)
+    const int u2 = tid & 63, sg = tid >> 6;
+    float cst[4], hst[4];
+    int lk[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) cst[k] = 0.f, hst[k] = 0.f;
+    for (int k = 0; k < 4; ++k) cst[k] = 0.f, hst[k] = 0.f, lk[k] = slen[sg + 8 * k];
     if (lane == 0 && maxlen > 0) lt_arrive(&bar_h);   // h_0 = 0 is already in operand buffer 0
     for (int step = 0; step < maxlen; ++step) {
       const int par = step & 1;
       { LT_T0(); mbar_wait(&bar_acc, par); if (warp == 0) LT_ACC(3); }
       tc_fence_after();
       LT_T0();
-      // ---- phase 1: activation of one gate row for 32 sequences ----
+      // ---- phase 1: activation of one gate row for 16 sequences ----
       if (mt < nmt) {
-        float v[32];
-        tmem_ld32(tbase + ((uint32_t)(type * 32) << 16) + (uint32_t)mt * LT_NSEQ, v);
+        float v[16];
+        tmem_ld16(tbase + ((uint32_t)(type * 32) << 16) + (uint32_t)(mt * LT_NSEQ + shalf * 16), v);
         tmem_ld_wait();
         if (u1 < h) {
 #pragma unroll
-          for (int s = 0; s < 32; ++s) {
-            const float a = v[s] + bias1;
-            gsm[(type * 32 + s) * 64 + u1] = (type == 2) ? lt_tanh(a) : lt_sigmoid(a);
+          for (int s = 0; s < 16; ++s) {
+            const float sgm = lt_sigmoid(pre * (v[s] + bias1));
+            gsm[(type * 32 + shalf * 16 + s) * 64 + u1] = fmaf(post_a, sgm, post_b);
           }
         }
       }
       tc_fence_before();
       if (warp == 0) LT_ACC(4);
-      lt_named_bar(1, 256);
+      lt_named_bar(1, LT_EPI_WARPS * 32);
       if (warp == 0) LT_ACC(5);
-      // ---- phase 2: state update for (unit u2, sequences sg + 4k) ----
+      // ---- phase 2: state update, branch-free so the 4 items interleave ----
       uint8_t* hn = h_img + (size_t)(par ^ 1) * 2 * LT_HIMG;  // next step's h operand
       if (u2 < h) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int s = sg + 4 * k;
-          const int l = slen[s];
-          if (step < l) {
-            const float ig = gsm[(0 * 32 + s) * 64 + u2], fg = gsm[(1 * 32 + s) * 64 + u2];
-            const float gg = gsm[(2 * 32 + s) * 64 + u2], og = gsm[(3 * 32 + s) * 64 + u2];
-            const float c = fg * cst[k] + ig * gg;
-            const float hv = og * lt_tanh(c);
-            cst[k] = c, hst[k] = hv;
-            const int t = dir ? l - 1 - step : step;
+        for (int k = 0; k < 4; ++k) {
+          const int s = sg + 8 * k;
+          const bool act = step < lk[k];
+          const float ig = gsm[(0 * 32 + s) * 64 + u2], fg = gsm[(1 * 32 + s) * 64 + u2];
+          const float gg = gsm[(2 * 32 + s) * 64 + u2], og = gsm[(3 * 32 + s) * 64 + u2];
+          const float c = fmaf(fg, cst[k], ig * gg);
+          const float hv = og * lt_tanh(c);
+          cst[k] = act ? c : cst[k];
+          hst[k] = act ? hv : hst[k];
+          if (act) {
+            const int t = dir ? lk[k] - 1 - step : step;
             out[((size_t)(s0 + s) * L + t) * Hout + dir * h + u2] = hv;
           }
           __nv_bfloat16 hi, lo;
@@ -322,8 +323,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     }
     if (u2 < h && (h_n || c_n)) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int s = sg + 4 * k;
+      for (int k = 0; k < 4; ++k) {
+        const int s = sg + 8 * k;
         if (s0 + s >= n) continue;
         if (h_n) h_n[((size_t)dir * n + s0 + s) * h + u2] = hst[k];
         if (c_n) c_n[((size_t)dir * n + s0 + s) * h + u2] = cst[k];
