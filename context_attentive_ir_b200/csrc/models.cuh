@@ -46,9 +46,9 @@ struct MtEpiConst {
   float b1[MT_TC_MAXM];
 };
 bool mt_tc_supported(const MtPack& p, int Lq, int Ld);
-void mt_tc_workspace(const MtPack& p, int64_t nq, int64_t pc, int Lq, size_t* img_bytes, size_t* max_floats);
+void mt_tc_workspace(const MtPack& p, int64_t nq, int64_t pc, int Lq, int Ld, size_t* timg_bytes, size_t* aimg_bytes);
 int32_t mt_epi_const(const MtPack& p, MtEpiConst* out, cudaStream_t s);  // synchronises s
-int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const float* cq, const float* cd, uint8_t* timg, float* maxbuf,
+int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const float* cq, const float* cd, uint8_t* timg, uint8_t* aimg,
                        const int64_t* q, const int64_t* d, int N, int Lq, int Ld, int64_t pair_begin,
                        int64_t pair_count, int64_t q_begin, int64_t nq, float* scores, cudaStream_t s);
 

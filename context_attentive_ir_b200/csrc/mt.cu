@@ -299,12 +299,12 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
   const bool use_tc = st.impl == MT_IMPL_TC && mt_tc_supported(st.pack, Lq, Ld);
   float* T = nullptr;
   uint8_t* timg = nullptr;
-  float* maxbuf = nullptr;
+  uint8_t* aimg = nullptr;
   if (use_tc) {
-    size_t img_bytes, max_floats;
-    mt_tc_workspace(st.pack, nq, pc, Lq, &img_bytes, &max_floats);
-    timg = ws.take<uint8_t>(img_bytes);
-    maxbuf = ws.take<float>(max_floats);
+    size_t timg_bytes, aimg_bytes;
+    mt_tc_workspace(st.pack, nq, pc, Lq, Ld, &timg_bytes, &aimg_bytes);
+    timg = ws.take<uint8_t>(timg_bytes);
+    aimg = ws.take<uint8_t>(aimg_bytes);
   } else {
     T = ws.take<float>(mt_t_floats(st.pack, nq, Lq));
   }
@@ -337,7 +337,7 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
   prof_mark("projections", s);
   CAIR_TRY(gemm_f32(gemm_dense(enc_q, st.Hq), st.wq, st.bq, cq, st.C, nq * Lq, st.C, st.Hq, ACT_NONE, s));
   CAIR_TRY(gemm_f32(gemm_dense(enc_d, st.Hd), st.wd, st.bd, cd, st.C, pc * Ld, st.C, st.Hd, ACT_NONE, s));
-  if (use_tc) return mt_tc_interact(st.pack, st.epi, cq, cd, timg, maxbuf, q, d, N, Lq, Ld, pb, pc, qb, nq, scores, s);
+  if (use_tc) return mt_tc_interact(st.pack, st.epi, cq, cd, timg, aimg, q, d, N, Lq, Ld, pb, pc, qb, nq, scores, s);
   return mt_interact(st.pack, cq, cd, T, q, d, N, Lq, Ld, pb, pc, qb, nq, scores, s);
 }
 

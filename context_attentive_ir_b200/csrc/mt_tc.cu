@@ -34,7 +34,7 @@ using namespace umma;
 constexpr int TC_NROWS = 96;      // N of the MMA (columns of one accumulator tile)
 constexpr int TC_TCOLS = 512;     // TMEM columns allocated: 2 stages x 2 row tiles x 96 (384) -> next power of two
 constexpr int TC_MAXRA = 264;     // staged A rows: 2*128 + 6 halo rows, rounded up to 8
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 352;   // 8 epilogue warps + B producer + MMA issuer + A producer
 constexpr int TC_EPI_THREADS = 256;
 
 static inline int tc_cp(int C) { return (C + 15) & ~15; }
@@ -81,6 +81,38 @@ __global__ void __launch_bounds__(256) mt_tc_build_t_kernel(const float* __restr
   }
 }
 
+// A images: per pair [hi|lo][plane c/8][row r <-> doc position r-3][8 x bf16]; halo / pad rows and pad channels are 0.
+// One thread per 16-byte unit; the interaction kernel then loads a whole image with one bulk copy.
+__global__ void __launch_bounds__(256) mt_tc_image_kernel(const float* __restrict__ cd, int C, int Ld, int KC, int RA,
+                                                           int64_t pair_count, uint8_t* __restrict__ aimg) {
+  const int64_t pl = blockIdx.x;
+  const float* cdp = cd + (size_t)pl * Ld * C;
+  const size_t half = (size_t)KC * RA * 16;
+  uint8_t* out = aimg + (size_t)pl * 2 * half;
+  for (int u = threadIdx.x; u < RA * KC; u += blockDim.x) {
+    const int kc = u / RA, r = u - kc * RA;
+    const int j = r - 3;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = kc * 8 + e;
+      v[e] = (j >= 0 && j < Ld && c < C) ? cdp[(size_t)j * C + c] : 0.f;
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v[2 * e], h0, l0);
+      split_bf16(v[2 * e + 1], h1, l1);
+      hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      lo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    const size_t off = ((size_t)kc * RA + r) * 16;
+    *reinterpret_cast<uint4*>(out + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(out + half + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -94,14 +126,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 template <int NF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-    mt_tc_interact_kernel(const float* __restrict__ cd, const uint8_t* __restrict__ timg, MtPack p,
+    mt_tc_interact_kernel(const uint8_t* __restrict__ aimg, const uint8_t* __restrict__ timg, MtPack p,
                           const __grid_constant__ MtEpiConst ec, const int64_t* __restrict__ q,
                           const int64_t* __restrict__ d, int N, int Lq, int Ld, int CP, int ntiles, int nstages,
                           int64_t pair_begin, int64_t pair_count, int64_t q_begin, float* __restrict__ scores,
                           long long* __restrict__ dbg) {
   constexpr int FP = 3 * NF, FPP = (FP + 3) & ~3, IPT = TC_NROWS / FP;
   extern __shared__ __align__(128) uint8_t smraw[];
-  __shared__ uint64_t full_b[8], empty_b[8], acc_full[2], acc_empty[2], a_full;
+  __shared__ uint64_t full_b[8], empty_b[8], acc_full[2], acc_empty[2], a_full, a_empty;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int C = p.C, M = p.M, KC = CP / 8;
@@ -129,7 +161,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 8);   // one arrive per epilogue warp
     }
-    mbar_init(&a_full, 8);
+    mbar_init(&a_full, 1);
+    mbar_init(&a_empty, 1);
     fence_mbar_init();
   }
   for (int i = tid; i < 24 * MT_TC_MAXM; i += TC_THREADS) w1t[i] = ec.w1[i % MT_TC_MAXM][i / MT_TC_MAXM];
@@ -154,6 +187,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           mbar_arrive_expect_tx(&full_b[s], slab);
           bulk_g2s(b_ring + (size_t)s * slab, src + (size_t)t * slab, slab, &full_b[s]);
         }
+      }
+    }
+  } else if (warp == 10) {
+    // ================= A producer: one bulk copy of the pair's document image, as soon as the previous pair's MMAs retired ======
+    if (lane == 0) {
+      uint32_t pair_it = 0;
+      for (int64_t pl = blockIdx.x; pl < pair_count; pl += gridDim.x, ++pair_it) {
+        mbar_wait_relaxed(&a_empty, (pair_it & 1) ^ 1);
+        const uint32_t bytes = 2 * a_half;
+        const uint8_t* src = aimg + (size_t)pl * bytes;
+        mbar_arrive_expect_tx(&a_full, bytes);
+        for (uint32_t o = 0; o < bytes; o += 16896) bulk_g2s(a_img + o, src + o, min(16896u, bytes - o), &a_full);
       }
     }
   } else if (warp == 9) {
@@ -199,6 +244,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
           mma_commit_w(&acc_full[as], issue);        // accumulator stage complete
         }
+        mma_commit_w(&a_empty, issue);               // document image free once this pair's MMAs retire
       }
     }
   } else {
@@ -212,39 +258,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int64_t pg = pair_begin + pl;
       const int64_t b = pg / N;
       TC_T0();
-      // ---- stage A (previous pair's MMAs have retired: its last acc_full was observed) ----
-      const float* cdp = cd + (size_t)pl * Ld * C;
-      for (int u = et; u < RA * KC; u += TC_EPI_THREADS) {
-        const int kc = u / RA, r = u - kc * RA;
-        const int j = r - 3;
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          int c = kc * 8 + e;
-          v[e] = (j >= 0 && j < Ld && c < C) ? cdp[(size_t)j * C + c] : 0.f;
-        }
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(v[2 * e], h0, l0);
-          split_bf16(v[2 * e + 1], h1, l1);
-          hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-          lo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-        }
-        const size_t off = (size_t)kc * a_plane + (size_t)r * 16;
-        *reinterpret_cast<uint4*>(a_img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(a_img + a_half + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      }
+      // ---- token ids of the pair for the exact-match channel ----
       for (int i = et; i < TC_MAXRA + 8; i += TC_EPI_THREADS) {
         int j = i - 3;
         dids[i] = (j >= 0 && j < Ld) ? (int)d[pg * Ld + j] : -1;
       }
       for (int i = et; i < Lq; i += TC_EPI_THREADS) qids[i] = (int)q[b * Lq + i];
-      fence_proxy_async();
       named_bar_sync(1, TC_EPI_THREADS);          // dids/qids visible to all epilogue threads
       if (warp == 0) TC_ACC(5);
-      if (lane == 0) mbar_arrive(&a_full);
 
       float mx[MT_TC_MAXM];
 #pragma unroll
@@ -364,12 +385,13 @@ bool mt_tc_supported(const MtPack& p, int Lq, int Ld) {
   return tc_stages(p, Lq) >= 2;
 }
 
-void mt_tc_workspace(const MtPack& p, int64_t nq, int64_t pc, int Lq, size_t* img_bytes, size_t* max_floats) {
-  (void)pc;
+static inline int tc_ra(int Ld) { return (((Ld + 127) / 128) * 128 + 6 + 7) & ~7; }
+
+void mt_tc_workspace(const MtPack& p, int64_t nq, int64_t pc, int Lq, int Ld, size_t* timg_bytes, size_t* aimg_bytes) {
   const int CP = tc_cp(p.C);
   const int IPT = TC_NROWS / p.FP, ntiles = (Lq + IPT - 1) / IPT;
-  *img_bytes = (size_t)nq * ntiles * 7 * tc_slab_bytes(CP);
-  *max_floats = 0;
+  *timg_bytes = (size_t)nq * ntiles * 7 * tc_slab_bytes(CP);
+  *aimg_bytes = (size_t)pc * 2 * (CP / 8) * tc_ra(Ld) * 16;
 }
 
 // Host copy of the epilogue weights (exact-match taps, bias, 1x1 conv) for the constant-bank kernel parameter.
@@ -393,9 +415,8 @@ int32_t mt_epi_const(const MtPack& p, MtEpiConst* out, cudaStream_t s) {
 }
 
 int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const float* cq, const float* cd, uint8_t* timg,
-                       float* maxbuf, const int64_t* q, const int64_t* d, int N, int Lq, int Ld, int64_t pair_begin,
+                       uint8_t* aimg, const int64_t* q, const int64_t* d, int N, int Lq, int Ld, int64_t pair_begin,
                        int64_t pair_count, int64_t q_begin, int64_t nq, float* scores, cudaStream_t s) {
-  (void)maxbuf;
   if (pair_count <= 0) return CAIR_OK;
   const int CP = tc_cp(p.C);
   const int IPT = TC_NROWS / p.FP, ntiles = (Lq + IPT - 1) / IPT;
@@ -403,15 +424,17 @@ int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const float* cq, c
   prof_mark("build_T", s);
   CAIR_LAUNCH(mt_tc_build_t_kernel, dim3(ntiles, (unsigned)nq), 256, 0, s, cq, p, Lq, CP, IPT, ntiles, timg);
   const size_t smem = tc_a_bytes(CP) + (size_t)nstages * tc_slab_bytes(CP) + tc_misc_bytes(p, Lq);
+  prof_mark("doc_image", s);
+  CAIR_LAUNCH(mt_tc_image_kernel, (unsigned)pair_count, 256, 0, s, cd, p.C, Ld, CP / 8, tc_ra(Ld), pair_count, aimg);
   prof_mark("interact", s);
   const unsigned grid = (unsigned)(pair_count < kSMs ? pair_count : kSMs);
   if (p.nf == 6) {
     CAIR_CUDA(cudaFuncSetAttribute(mt_tc_interact_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CAIR_LAUNCH(mt_tc_interact_kernel<6>, grid, TC_THREADS, smem, s, cd, timg, p, ec, q, d, N, Lq, Ld, CP, ntiles,
+    CAIR_LAUNCH(mt_tc_interact_kernel<6>, grid, TC_THREADS, smem, s, aimg, timg, p, ec, q, d, N, Lq, Ld, CP, ntiles,
                 nstages, pair_begin, pair_count, q_begin, scores, g_mt_dbg);
   } else {
     CAIR_CUDA(cudaFuncSetAttribute(mt_tc_interact_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CAIR_LAUNCH(mt_tc_interact_kernel<4>, grid, TC_THREADS, smem, s, cd, timg, p, ec, q, d, N, Lq, Ld, CP, ntiles,
+    CAIR_LAUNCH(mt_tc_interact_kernel<4>, grid, TC_THREADS, smem, s, aimg, timg, p, ec, q, d, N, Lq, Ld, CP, ntiles,
                 nstages, pair_begin, pair_count, q_begin, scores, g_mt_dbg);
   }
   return CAIR_OK;
