@@ -107,6 +107,9 @@ int32_t cair_destroy(cair_handle* h) {
   DeviceGuard g(h->device);
   h->own.release();
   h->prof.release();
+  if (h->mt.side) cudaStreamDestroy(h->mt.side);
+  if (h->mt.ev_fork) cudaEventDestroy(h->mt.ev_fork);
+  if (h->mt.ev_join) cudaEventDestroy(h->mt.ev_join);
   if (h->stage_dev) cudaFree(h->stage_dev);
   if (h->ws) cudaFree(h->ws);
   delete h;

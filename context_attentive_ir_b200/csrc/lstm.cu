@@ -174,7 +174,7 @@ int32_t lstm_run(const LstmPack& p, const GemmA& x, const int64_t* len, int n, i
   if (n <= 0) return CAIR_OK;
   const int G = 4 * p.h, PG = p.dirs * G;
   CAIR_TRY(gemm_f32(x, p.w_ih, p.bias, ws_pre, PG, (int64_t)n * L, PG, p.in, ACT_NONE, s));
-  prof_mark(rec_name, s);
+  if (rec_name) prof_mark(rec_name, s);
   const int hp = (p.h + 3) & ~3;
   size_t state = (size_t)(TS * hp + TS * p.h + TS * G) * sizeof(float);
   size_t wbytes = (size_t)p.h * G * sizeof(float);

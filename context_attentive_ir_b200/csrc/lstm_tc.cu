@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
 int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, const int64_t* len, int n, int L,
                     float* out, float* h_n, float* c_n, int* err, cudaStream_t s, const char* rec_name) {
   if (n <= 0) return CAIR_OK;
-  prof_mark(rec_name, s);
+  if (rec_name) prof_mark(rec_name, s);
   uint32_t ks_mask = 0;
   for (int ks = 0; ks < LT_K / 16; ++ks) {
     const int k0 = 16 * ks, k1 = k0 + 16;

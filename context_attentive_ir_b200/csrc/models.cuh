@@ -30,6 +30,7 @@ int32_t drmm_forward(const cair_drmm_weights& w, const int64_t* q, const int64_t
 struct MtPack {
   int C, nf, FP, FPP, M;
   float* w7;    // [3][7][C][FPP]   merged conv weights of the C product channels, f fastest
+  float* w7t;   // [3][7][FP][CP]   same, channel fastest and zero-padded to CP = ceil16(C) (tensor-core T builder)
   float* wem;   // [3][7][FPP]      alpha * merged weights of the exact-match channel
   float* bias;  // [FPP]
   float* w1;    // [M][FPP]         1x1 conv
@@ -48,7 +49,9 @@ struct MtEpiConst {
 bool mt_tc_supported(const MtPack& p, int Lq, int Ld);
 void mt_tc_workspace(const MtPack& p, int64_t nq, int64_t pc, int Lq, int Ld, size_t* timg_bytes, size_t* aimg_bytes);
 int32_t mt_epi_const(const MtPack& p, MtEpiConst* out, cudaStream_t s);  // synchronises s
-int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const float* cq, const float* cd, uint8_t* timg, uint8_t* aimg,
+int32_t mt_tc_build_t(const MtPack& p, const float* cq, uint8_t* timg, int Lq, int64_t nq, cudaStream_t s);
+int32_t mt_tc_doc_image(const MtPack& p, const float* cd, uint8_t* aimg, int Ld, int64_t pair_count, cudaStream_t s);
+int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const uint8_t* timg, const uint8_t* aimg,
                        const int64_t* q, const int64_t* d, int N, int Lq, int Ld, int64_t pair_begin,
                        int64_t pair_count, int64_t q_begin, int64_t nq, float* scores, cudaStream_t s);
 
@@ -63,6 +66,8 @@ struct MtState {
   float *wq = nullptr, *bq = nullptr, *wd = nullptr, *bd = nullptr;  // channel projections
   MtPack pack{};
   MtEpiConst epi{};
+  cudaStream_t side = nullptr;            // query-side work runs here, forked/joined with events
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   float *dbg_enc_q = nullptr, *dbg_enc_d = nullptr;
 };
 int32_t mt_create_state(Owned& own, const cair_mt_weights& w, MtState* st, cudaStream_t s);

@@ -41,8 +41,10 @@ __global__ void mt_pack_kernel(const float* __restrict__ c1, const float* __rest
       const float* w = k == 0 ? c1 : (k == 1 ? c2 : c3);
       if (bb >= 0 && bb < kw) v = w[(((size_t)ff * C1 + c) * 3 + a) * kw + bb];
     }
-    if (c < C)
+    if (c < C) {
       p.w7[(((size_t)a * 7 + bt) * C + c) * FPP + f] = v;
+      if (f < p.FP) p.w7t[(((size_t)a * 7 + bt) * p.FP + f) * ((C + 15) & ~15) + c] = v;
+    }
     else
       p.wem[((size_t)a * 7 + bt) * FPP + f] = v * alpha[0];
   }
@@ -71,6 +73,11 @@ int32_t mt_pack(Owned& own, const cair_mt_weights& w, MtPack* p, cudaStream_t s)
   if (p->FP > MT_MAXF) return fail(CAIR_ERR_UNSUPPORTED, "match_tensor: nfilters %d > %d", w.nfilters, MT_MAXF / 3);
   if (p->M > MT_MAXM) return fail(CAIR_ERR_UNSUPPORTED, "match_tensor: match_filter_size %d > %d", p->M, MT_MAXM);
   CAIR_CUDA(own.alloc(&p->w7, (size_t)21 * p->C * p->FPP));
+  {
+    const size_t n7t = (size_t)21 * p->FP * ((p->C + 15) & ~15);
+    CAIR_CUDA(own.alloc(&p->w7t, n7t));
+    CAIR_CUDA(cudaMemsetAsync(p->w7t, 0, n7t * sizeof(float), s));
+  }
   CAIR_CUDA(own.alloc(&p->wem, (size_t)21 * p->FPP));
   CAIR_CUDA(own.alloc(&p->bias, (size_t)p->FPP));
   CAIR_CUDA(own.alloc(&p->w1, (size_t)p->M * p->FPP));
@@ -278,6 +285,9 @@ int32_t mt_create_state(Owned& own, const cair_mt_weights& w, MtState* st, cudaS
   CAIR_TRY(dev_copy(own, w.document_projection.b, (size_t)w.nchannels, &st->bd, s));
   CAIR_TRY(mt_pack(own, w, &st->pack, s));
   CAIR_TRY(mt_epi_const(st->pack, &st->epi, s));
+  CAIR_CUDA(cudaStreamCreateWithFlags(&st->side, cudaStreamNonBlocking));
+  CAIR_CUDA(cudaEventCreateWithFlags(&st->ev_fork, cudaEventDisableTiming));
+  CAIR_CUDA(cudaEventCreateWithFlags(&st->ev_join, cudaEventDisableTiming));
   return CAIR_OK;
 }
 
@@ -312,32 +322,47 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
   if (!ws.ok()) return fail(CAIR_ERR_WORKSPACE, "match_tensor: workspace too small");
   const int64_t* qs = q + qb * Lq;
   const int64_t* ds = d + pb * Ld;
-  // embedding + projection (folded table) -> BiLSTM encoders (:77-94)
-  prof_mark("encode_queries", s);
+  // The query side (encoder, channel projection, T operand) depends only on the queries: it runs on the handle's
+  // side stream, concurrently with the document encoder (which occupies ~80 of the 148 SMs), and joins before
+  // the interaction kernel.  Fork/join with events keeps the caller's stream semantics (and is graph-capturable).
+  cudaStream_t sq = st.side ? st.side : s;
+  if (st.side) {
+    CAIR_CUDA(cudaEventRecord(st.ev_fork, s));
+    CAIR_CUDA(cudaStreamWaitEvent(st.side, st.ev_fork, 0));
+  }
+  // ---- query side: embedding + projection (folded table) -> BiLSTM (:77-94) -> channel projection (:99) ----
   if (tc_q)
     CAIR_TRY(lstm_tc_run(st.tc_q, st.enc_q.bias, gemm_gather(st.folded, st.V, st.F, qs, 1, 1, 1, err), qlen + qb, (int)nq,
-                         Lq, enc_q, nullptr, nullptr, err, s, "query_recurrence"));
+                         Lq, enc_q, nullptr, nullptr, err, sq, st.side ? nullptr : "query_recurrence"));
   else
     CAIR_TRY(lstm_run(st.enc_q, gemm_gather(st.folded, st.V, st.F, qs, 1, 1, 1, err), qlen + qb, (int)nq, Lq, enc_q,
-                      nullptr, nullptr, pre_q, err, s, "query_recurrence"));
-  prof_mark("doc_pregates", s);
+                      nullptr, nullptr, pre_q, err, sq, st.side ? nullptr : "query_recurrence"));
+  if (st.dbg_enc_q)
+    CAIR_CUDA(cudaMemcpyAsync(st.dbg_enc_q + (size_t)qb * Lq * st.Hq, enc_q, (size_t)nq * Lq * st.Hq * sizeof(float),
+                              cudaMemcpyDeviceToDevice, sq));
+  CAIR_TRY(gemm_f32(gemm_dense(enc_q, st.Hq), st.wq, st.bq, cq, st.C, nq * Lq, st.C, st.Hq, ACT_NONE, sq));
+  if (use_tc) CAIR_TRY(mt_tc_build_t(st.pack, cq, timg, Lq, nq, sq));
+  if (st.side) CAIR_CUDA(cudaEventRecord(st.ev_join, st.side));
+  // ---- document side ----
   if (tc_d)
     CAIR_TRY(lstm_tc_run(st.tc_d, st.enc_d.bias, gemm_gather(st.folded, st.V, st.F, ds, 1, 1, 1, err), dlen + pb, (int)pc,
                          Ld, enc_d, nullptr, nullptr, err, s, "doc_recurrence"));
   else
     CAIR_TRY(lstm_run(st.enc_d, gemm_gather(st.folded, st.V, st.F, ds, 1, 1, 1, err), dlen + pb, (int)pc, Ld, enc_d,
                       nullptr, nullptr, pre_d, err, s, "doc_recurrence"));
-  if (st.dbg_enc_q)
-    CAIR_CUDA(cudaMemcpyAsync(st.dbg_enc_q + (size_t)qb * Lq * st.Hq, enc_q, (size_t)nq * Lq * st.Hq * sizeof(float),
-                              cudaMemcpyDeviceToDevice, s));
   if (st.dbg_enc_d)
     CAIR_CUDA(cudaMemcpyAsync(st.dbg_enc_d + (size_t)pb * Ld * st.Hd, enc_d, (size_t)pc * Ld * st.Hd * sizeof(float),
                               cudaMemcpyDeviceToDevice, s));
-  // channel projections (:99,108): the bias also lands on pad positions (zero memory-bank rows)
-  prof_mark("projections", s);
-  CAIR_TRY(gemm_f32(gemm_dense(enc_q, st.Hq), st.wq, st.bq, cq, st.C, nq * Lq, st.C, st.Hq, ACT_NONE, s));
+  // channel projection (:108): the bias also lands on pad positions (zero memory-bank rows)
+  prof_mark("doc_projection", s);
   CAIR_TRY(gemm_f32(gemm_dense(enc_d, st.Hd), st.wd, st.bd, cd, st.C, pc * Ld, st.C, st.Hd, ACT_NONE, s));
-  if (use_tc) return mt_tc_interact(st.pack, st.epi, cq, cd, timg, aimg, q, d, N, Lq, Ld, pb, pc, qb, nq, scores, s);
+  if (use_tc) {
+    CAIR_TRY(mt_tc_doc_image(st.pack, cd, aimg, Ld, pc, s));
+    prof_mark("join_query_side", s);
+    if (st.side) CAIR_CUDA(cudaStreamWaitEvent(s, st.ev_join, 0));
+    return mt_tc_interact(st.pack, st.epi, timg, aimg, q, d, N, Lq, Ld, pb, pc, qb, nq, scores, s);
+  }
+  if (st.side) CAIR_CUDA(cudaStreamWaitEvent(s, st.ev_join, 0));
   return mt_interact(st.pack, cq, cd, T, q, d, N, Lq, Ld, pb, pc, qb, nq, scores, s);
 }
 

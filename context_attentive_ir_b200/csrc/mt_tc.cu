@@ -51,33 +51,46 @@ static inline int tc_stages(const MtPack& p, int Lq) {
   return s > 8 ? 8 : s;
 }
 
-// B slabs for (query qi, column tile nt, tap bt): [hi|lo][plane c/8][row n = il*FP + f][8 x bf16]
+// B slabs for (query qi, column tile nt, tap bt): [hi|lo][plane c/8][row n = il*FP + f][8 x bf16].
+// One thread per 16-byte unit (8 channels of one (i, f, tap)): T = sum_a W7[f,c,a,bt] * cq[i+a-1,c], split to hi/lo.
 __global__ void __launch_bounds__(256) mt_tc_build_t_kernel(const float* __restrict__ cq, MtPack p, int Lq, int CP,
                                                             int IPT, int ntiles, uint8_t* __restrict__ img) {
-  const int nt = blockIdx.x, qi = blockIdx.y;
-  const int C = p.C, FP = p.FP, FPP = p.FPP, KC = CP / 8;
+  const int nt = blockIdx.x / 7, bt = blockIdx.x - nt * 7, qi = blockIdx.y;
+  const int C = p.C, FP = p.FP, KC = CP / 8;
   const size_t half = (size_t)KC * TC_NROWS * 16;
-  const int per_tap = KC * TC_NROWS * 8;
-  for (int idx = threadIdx.x; idx < 7 * per_tap; idx += blockDim.x) {
-    const int bt = idx / per_tap, rem = idx - bt * per_tap;
-    const int e = rem & 7, n = (rem >> 3) % TC_NROWS, kc = rem / (8 * TC_NROWS);
-    const int c = kc * 8 + e;
+  uint8_t* out = img + (((size_t)qi * ntiles + nt) * 7 + bt) * 2 * half;
+  for (int u = threadIdx.x; u < KC * TC_NROWS; u += blockDim.x) {
+    const int kc = u / TC_NROWS, n = u - kc * TC_NROWS;
     const int il = n / FP, f = n - il * FP, i = nt * IPT + il;
-    float v = 0.f;
-    if (il < IPT && i < Lq && c < C) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (il < IPT && i < Lq) {
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        int ii = i + a - 1;
-        if (ii >= 0 && ii < Lq)
-          v = fmaf(p.w7[(((size_t)a * 7 + bt) * C + c) * FPP + f], cq[((size_t)qi * Lq + ii) * C + c], v);
+        const int ii = i + a - 1;
+        if (ii < 0 || ii >= Lq) continue;
+        const float4* w4 = reinterpret_cast<const float4*>(p.w7t + (((size_t)a * 7 + bt) * FP + f) * CP + kc * 8);
+        const float4 wa = w4[0], wb = w4[1];
+        const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        const float* cr = cq + ((size_t)qi * Lq + ii) * C + kc * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (kc * 8 + e < C) v[e] = fmaf(w[e], cr[e], v[e]);
       }
     }
-    __nv_bfloat16 hi, lo;
-    split_bf16(v, hi, lo);
-    uint8_t* out = img + (((size_t)qi * ntiles + nt) * 7 + bt) * 2 * half;
-    const size_t off = ((size_t)kc * TC_NROWS + n) * 16 + e * 2;
-    *reinterpret_cast<__nv_bfloat16*>(out + off) = hi;
-    *reinterpret_cast<__nv_bfloat16*>(out + half + off) = lo;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v[2 * e], h0, l0);
+      split_bf16(v[2 * e + 1], h1, l1);
+      hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      lo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    const size_t off = ((size_t)kc * TC_NROWS + n) * 16;
+    *reinterpret_cast<uint4*>(out + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(out + half + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -414,18 +427,30 @@ int32_t mt_epi_const(const MtPack& p, MtEpiConst* out, cudaStream_t s) {
   return CAIR_OK;
 }
 
-int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const float* cq, const float* cd, uint8_t* timg,
-                       uint8_t* aimg, const int64_t* q, const int64_t* d, int N, int Lq, int Ld, int64_t pair_begin,
-                       int64_t pair_count, int64_t q_begin, int64_t nq, float* scores, cudaStream_t s) {
+int32_t mt_tc_build_t(const MtPack& p, const float* cq, uint8_t* timg, int Lq, int64_t nq, cudaStream_t s) {
+  if (nq <= 0) return CAIR_OK;
+  const int CP = tc_cp(p.C);
+  const int IPT = TC_NROWS / p.FP, ntiles = (Lq + IPT - 1) / IPT;
+  CAIR_LAUNCH(mt_tc_build_t_kernel, dim3(ntiles * 7, (unsigned)nq), 256, 0, s, cq, p, Lq, CP, IPT, ntiles, timg);
+  return CAIR_OK;
+}
+
+int32_t mt_tc_doc_image(const MtPack& p, const float* cd, uint8_t* aimg, int Ld, int64_t pair_count, cudaStream_t s) {
+  if (pair_count <= 0) return CAIR_OK;
+  prof_mark("doc_image", s);
+  CAIR_LAUNCH(mt_tc_image_kernel, (unsigned)pair_count, 256, 0, s, cd, p.C, Ld, tc_cp(p.C) / 8, tc_ra(Ld), pair_count, aimg);
+  return CAIR_OK;
+}
+
+int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const uint8_t* timg, const uint8_t* aimg, const int64_t* q,
+                       const int64_t* d, int N, int Lq, int Ld, int64_t pair_begin, int64_t pair_count, int64_t q_begin,
+                       int64_t nq, float* scores, cudaStream_t s) {
+  (void)nq;
   if (pair_count <= 0) return CAIR_OK;
   const int CP = tc_cp(p.C);
   const int IPT = TC_NROWS / p.FP, ntiles = (Lq + IPT - 1) / IPT;
   const int nstages = tc_stages(p, Lq);
-  prof_mark("build_T", s);
-  CAIR_LAUNCH(mt_tc_build_t_kernel, dim3(ntiles, (unsigned)nq), 256, 0, s, cq, p, Lq, CP, IPT, ntiles, timg);
   const size_t smem = tc_a_bytes(CP) + (size_t)nstages * tc_slab_bytes(CP) + tc_misc_bytes(p, Lq);
-  prof_mark("doc_image", s);
-  CAIR_LAUNCH(mt_tc_image_kernel, (unsigned)pair_count, 256, 0, s, cd, p.C, Ld, CP / 8, tc_ra(Ld), pair_count, aimg);
   prof_mark("interact", s);
   const unsigned grid = (unsigned)(pair_count < kSMs ? pair_count : kSMs);
   if (p.nf == 6) {
