@@ -259,6 +259,13 @@ def run_product(args):
             ach = bytes_per_pair_folded() * pairs_local / (stages[top] / 1e3) / 1e9
             roof = dict(kernel=top, bound='hbm', achieved=ach, peak=hbm_peak, unit='GB/s', frac=ach / hbm_peak,
                         traffic=None, ms_per_launch=stages[top], peak_source=peak_src)
+        try:
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+            if roof and roof['kernel'] in tr:
+                roof['traffic'] = tr[roof['kernel']]['bytes']
+                roof['traffic_source'] = tr[roof['kernel']]['capture']
+        except Exception:
+            pass
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             rate, dt, cores = cpu_oracle_rate(args.cpu_sample_queries)
