@@ -55,6 +55,16 @@ class DuetWeights(C.Structure):
                               'conv_d1', 'conv_d2', 'dist_fc1', 'dist_fc2', 'dist_fc3', 'dist_fc4')]
 
 
+class DssmWeights(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ('vocab', 'emsize', 'nhid', 'nout')] + [('table', f32p)] + [
+        (k, Linear) for k in ('query_mlp0', 'query_mlp2', 'doc_mlp0', 'doc_mlp2')]
+
+
+class CdssmWeights(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ('vocab', 'emsize', 'nhid', 'nout')] + [('table', f32p)] + [
+        (k, Linear) for k in ('query_conv', 'query_sem', 'doc_conv', 'doc_sem')]
+
+
 class CarsWeights(C.Structure):
     _fields_ = [(k, C.c_int32) for k in
                 ('vocab', 'emsize', 'nhid_query', 'nhid_document', 'nhid_session_query',
@@ -134,6 +144,20 @@ def pack_duet(cfg, get):
     return w
 
 
+def pack_dssm(cfg, get):
+    w = DssmWeights(cfg['src_vocab_size'], cfg['emsize'], cfg['nhid'], cfg['nout'], get(TABLE_KEY))
+    w.query_mlp0, w.query_mlp2 = _lin(get, 'query_mlp.0'), _lin(get, 'query_mlp.2')
+    w.doc_mlp0, w.doc_mlp2 = _lin(get, 'doc_mlp.0'), _lin(get, 'doc_mlp.2')
+    return w
+
+
+def pack_cdssm(cfg, get):
+    w = CdssmWeights(cfg['src_vocab_size'], cfg['emsize'], cfg['nhid'], cfg['nout'], get(TABLE_KEY))
+    w.query_conv, w.query_sem = _lin(get, 'query_conv'), _lin(get, 'query_sem')
+    w.doc_conv, w.doc_sem = _lin(get, 'doc_conv'), _lin(get, 'doc_sem')
+    return w
+
+
 def pack_cars(cfg, get):
     """Stock CARS ranking path (multitask/cars.py:28-131): LSTM, bidirectional, 1 layer, attn pooling."""
     w = CarsWeights(cfg['src_vocab_size'], cfg['emsize'], cfg['nhid_query'], cfg['nhid_document'],
@@ -159,5 +183,5 @@ def pack_cars(cfg, get):
     return w
 
 
-PACKERS = {'esm': pack_esm, 'match_tensor': pack_mt, 'drmm': pack_drmm, 'duet': pack_duet,
+PACKERS = {'dssm': pack_dssm, 'cdssm': pack_cdssm, 'esm': pack_esm, 'match_tensor': pack_mt, 'drmm': pack_drmm, 'duet': pack_duet,
            'cars': pack_cars}

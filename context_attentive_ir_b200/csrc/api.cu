@@ -35,6 +35,8 @@ struct cair_handle {
   MtState mt;
   DrmmState drmm;
   DuetState duet;
+  DssmState dssm;
+  CdssmState cdssm;
   CarsState cars;
   // host-path staging (cair_ranker_forward_host)
   void* stage_dev = nullptr;
@@ -272,6 +274,30 @@ int32_t cair_duet_create(const cair_duet_weights* w, int32_t device, cair_handle
   return rc;
 }
 
+int32_t cair_dssm_create(const cair_dssm_weights* w, int32_t device, cair_handle** out) {
+  if (!w || !w->table || w->nhid <= 0 || w->nout <= 0) return fail(CAIR_ERR_BAD_ARG, "dssm_create: bad weights");
+  cair_handle* h = nullptr;
+  CAIR_TRY(new_handle(CAIR_MODEL_DSSM, device, &h));
+  DeviceGuard g(device);
+  int32_t rc = init_err_flag(h);
+  if (rc == CAIR_OK) rc = dssm_create_state(h->own, *w, &h->dssm, 0);
+  rc = finish_create(h, rc, out);
+  if (rc == CAIR_OK) *out = h;
+  return rc;
+}
+
+int32_t cair_cdssm_create(const cair_cdssm_weights* w, int32_t device, cair_handle** out) {
+  if (!w || !w->table || w->nhid <= 0 || w->nout <= 0) return fail(CAIR_ERR_BAD_ARG, "cdssm_create: bad weights");
+  cair_handle* h = nullptr;
+  CAIR_TRY(new_handle(CAIR_MODEL_CDSSM, device, &h));
+  DeviceGuard g(device);
+  int32_t rc = init_err_flag(h);
+  if (rc == CAIR_OK) rc = cdssm_create_state(h->own, *w, &h->cdssm, 0);
+  rc = finish_create(h, rc, out);
+  if (rc == CAIR_OK) *out = h;
+  return rc;
+}
+
 int32_t cair_cars_create(const cair_cars_weights* w, int32_t device, cair_handle** out) {
   if (!w || !w->table) return fail(CAIR_ERR_BAD_ARG, "cars_create: bad weights");
   cair_handle* h = nullptr;
@@ -304,6 +330,10 @@ static int32_t ranker_run(cair_handle* h, const int64_t* q, const int64_t* qlen,
       return drmm_forward(h->drmm.w, q, d, N, Lq, Ld, pb, pc, scores, h->drmm.dbg_hist, h->d_err, s);
     case CAIR_MODEL_MT:
       return mt_forward(h->mt, q, qlen, d, dlen, B, N, Lq, Ld, pb, pc, scores, ws, h->d_err, s, dry);
+    case CAIR_MODEL_DSSM:
+      return dssm_forward(h->dssm, q, d, N, Lq, Ld, pb, pc, scores, ws, h->d_err, s, dry);
+    case CAIR_MODEL_CDSSM:
+      return cdssm_forward(h->cdssm, q, d, N, Lq, Ld, pb, pc, scores, ws, h->d_err, s, dry);
     case CAIR_MODEL_DUET:
       return duet_forward(h->duet, q, d, B, N, Lq, Ld, pb, pc, scores, ws, h->d_err, s, dry);
   }

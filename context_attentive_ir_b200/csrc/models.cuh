@@ -4,7 +4,8 @@
 
 namespace cair {
 
-enum { CAIR_MODEL_ESM = 1, CAIR_MODEL_MT = 2, CAIR_MODEL_DRMM = 3, CAIR_MODEL_DUET = 4, CAIR_MODEL_CARS = 5 };
+enum { CAIR_MODEL_ESM = 1, CAIR_MODEL_MT = 2, CAIR_MODEL_DRMM = 3, CAIR_MODEL_DUET = 4, CAIR_MODEL_CARS = 5,
+       CAIR_MODEL_DSSM = 6, CAIR_MODEL_CDSSM = 7 };
 
 int32_t embed_gather(const float* table, int V, int E, const int64_t* ids, int64_t T, float* out, int* err,
                      cudaStream_t s);
@@ -74,6 +75,25 @@ int32_t mt_create_state(Owned& own, const cair_mt_weights& w, MtState* st, cudaS
 int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, const int64_t* d, const int64_t* dlen,
                    int B, int N, int Lq, int Ld, int64_t pb, int64_t pc, float* scores, Arena& ws, int* err,
                    cudaStream_t s, bool dry);
+
+// ---- DSSM / CDSSM ----
+struct DssmState {
+  int V = 0, E = 0, H = 0, O = 0;
+  float* table = nullptr;
+  float *w[4] = {nullptr, nullptr, nullptr, nullptr}, *b[4] = {nullptr, nullptr, nullptr, nullptr};  // q0, q2, d0, d2
+};
+int32_t dssm_create_state(Owned& own, const cair_dssm_weights& w, DssmState* st, cudaStream_t s);
+int32_t dssm_forward(const DssmState& st, const int64_t* q, const int64_t* d, int N, int Lq, int Ld, int64_t pb,
+                     int64_t pc, float* scores, Arena& ws, int* err, cudaStream_t s, bool dry);
+struct CdssmState {
+  int V = 0, E = 0, H = 0, O = 0;
+  float* table = nullptr;
+  float *w5[2] = {nullptr, nullptr}, *b5[2] = {nullptr, nullptr};  // merged 5-token conv weights [H, 5E] (query, doc)
+  float *ws[2] = {nullptr, nullptr}, *bs[2] = {nullptr, nullptr};  // sem Linear [O, H]
+};
+int32_t cdssm_create_state(Owned& own, const cair_cdssm_weights& w, CdssmState* st, cudaStream_t s);
+int32_t cdssm_forward(const CdssmState& st, const int64_t* q, const int64_t* d, int N, int Lq, int Ld, int64_t pb,
+                      int64_t pc, float* scores, Arena& ws, int* err, cudaStream_t s, bool dry);
 
 // ---- DUET ----
 struct DuetState {

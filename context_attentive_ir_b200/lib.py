@@ -35,6 +35,8 @@ PROTOTYPES = {
     'cair_mt_set_impl': (i32, [vp, i32]),
     'cair_drmm_create': (i32, [C.POINTER(_abi.DrmmWeights), i32, C.POINTER(vp)]),
     'cair_drmm_set_debug': (i32, [vp, vp]),
+    'cair_dssm_create': (i32, [C.POINTER(_abi.DssmWeights), i32, C.POINTER(vp)]),
+    'cair_cdssm_create': (i32, [C.POINTER(_abi.CdssmWeights), i32, C.POINTER(vp)]),
     'cair_duet_create': (i32, [C.POINTER(_abi.DuetWeights), i32, C.POINTER(vp)]),
     'cair_ranker_workspace_bytes': (i32, [vp, i32, i32, i32, i32, C.POINTER(C.c_size_t)]),
     'cair_ranker_forward': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, vp, vp, C.c_size_t, vp]),

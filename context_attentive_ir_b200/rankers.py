@@ -219,6 +219,49 @@ class ESM(_Ranker):
         return lib.load().cair_esm_create(w, device, out)
 
 
+class DSSM(_Ranker):
+    """neuroir/rankers/dssm.py:7-63."""
+    MODEL = 'dssm'
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.word_embeddings = Embeddings(args.emsize, args.src_vocab_size, PAD)
+        self.emb_drop = nn.Dropout(p=args.dropout_emb)
+        self.query_mlp = nn.Sequential(nn.Linear(args.emsize, args.nhid), nn.Tanh(), nn.Linear(args.nhid, args.nout), nn.Tanh())
+        self.doc_mlp = nn.Sequential(nn.Linear(args.emsize, args.nhid), nn.Tanh(), nn.Linear(args.nhid, args.nout), nn.Tanh())
+
+    def _cfg(self):
+        a = self.args
+        return dict(src_vocab_size=a.src_vocab_size, emsize=a.emsize, nhid=a.nhid, nout=a.nout)
+
+    def _create(self, w, device, out):
+        return lib.load().cair_dssm_create(w, device, out)
+
+
+class CDSSM(_Ranker):
+    """neuroir/rankers/cdssm.py:7-77."""
+    MODEL = 'cdssm'
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.window = 3
+        self.word_embeddings = Embeddings(args.emsize, args.src_vocab_size, PAD)
+        self.emb_drop = nn.Dropout(p=args.dropout_emb)
+        self.query_conv = nn.Conv1d(self.window * args.emsize, args.nhid, 3)
+        self.query_sem = nn.Linear(args.nhid, args.nout)
+        self.doc_conv = nn.Conv1d(self.window * args.emsize, args.nhid, 3)
+        self.doc_sem = nn.Linear(args.nhid, args.nout)
+
+    def _cfg(self):
+        a = self.args
+        return dict(src_vocab_size=a.src_vocab_size, emsize=a.emsize, nhid=a.nhid, nout=a.nout)
+
+    def _create(self, w, device, out):
+        return lib.load().cair_cdssm_create(w, device, out)
+
+
 class ExactMatchChannel(nn.Module):
     """neuroir/rankers/mtensor.py:134-142: one learnable scalar, U(0,1) init."""
 
@@ -359,4 +402,4 @@ class DUET(_Ranker):
         return lib.load().cair_duet_create(w, device, out)
 
 
-RANKERS = {'ESM': ESM, 'MATCH_TENSOR': MatchTensor, 'DRMM': DRMM, 'DUET': DUET}
+RANKERS = {'DSSM': DSSM, 'CDSSM': CDSSM, 'ESM': ESM, 'MATCH_TENSOR': MatchTensor, 'DRMM': DRMM, 'DUET': DUET}

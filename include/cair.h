@@ -198,7 +198,25 @@ typedef struct {
 
 CAIR_API int32_t cair_duet_create(const cair_duet_weights* w, int32_t device, cair_handle** out);
 
-/* ---- forward for the four stand-alone rankers ---------------------------------------------
+/* ---- DSSM (neuroir/rankers/dssm.py:10-31 ctor, :33-63 forward) ------------------------------------------- */
+typedef struct {
+  int32_t vocab, emsize, nhid, nout;
+  const float* table;
+  cair_linear query_mlp0, query_mlp2; /* query_mlp.0 [nhid,E], query_mlp.2 [nout,nhid] */
+  cair_linear doc_mlp0, doc_mlp2;     /* doc_mlp.0, doc_mlp.2 */
+} cair_dssm_weights;
+CAIR_API int32_t cair_dssm_create(const cair_dssm_weights* w, int32_t device, cair_handle** out);
+
+/* ---- CDSSM (neuroir/rankers/cdssm.py:10-30 ctor, :42-77 forward) ------------------------------------------ */
+typedef struct {
+  int32_t vocab, emsize, nhid, nout;
+  const float* table;
+  cair_linear query_conv, query_sem; /* Conv1d [nhid, 3E, 3], Linear [nout, nhid] */
+  cair_linear doc_conv, doc_sem;
+} cair_cdssm_weights;
+CAIR_API int32_t cair_cdssm_create(const cair_cdssm_weights* w, int32_t device, cair_handle** out);
+
+/* ---- forward for the stand-alone rankers ---------------------------------------------
  * network(queries, que_len, documents, doc_len) (neuroir/models/ranker.py:213,257):
  * q [B,Lq], qlen [B], d [B,N,Ld], dlen [B,N] int64 -> scores [B,N] fp32 (no softmax).
  * pair_begin/pair_count select the contiguous slice of the flattened pairs p=b*N+n this rank

@@ -674,3 +674,90 @@ ORA_API int cair_oracle_softmax(const float* scores, int B, int N, float* out) {
   }
   return CAIR_OK;
 }
+
+/* ---- DSSM (rankers/dssm.py:33-63): max-pool over ALL positions (zero PAD rows take part), two-layer tanh MLP per
+ * side, cosine ---------------------------------------------------------------------------------------------- */
+static void mlp2_tanh(const float* x, int in, const cair_linear* l0, int hid, const cair_linear* l1, int out, float* y) {
+  float* h = (float*)malloc(sizeof(float) * hid);
+  for (int o = 0; o < hid; ++o) h[o] = tanhf(dotf(x, l0->w + (size_t)o * in, in) + l0->b[o]);
+  for (int o = 0; o < out; ++o) y[o] = tanhf(dotf(h, l1->w + (size_t)o * hid, hid) + l1->b[o]);
+  free(h);
+}
+
+ORA_API int cair_oracle_dssm(const cair_dssm_weights* w, const int64_t* q, const int64_t* qlen, const int64_t* d,
+                             const int64_t* dlen, int B, int N, int Lq, int Ld, float* scores) {
+  (void)qlen;
+  (void)dlen;
+  int E = w->emsize, H = w->nhid, O = w->nout;
+  if (!check_ids(q, (int64_t)B * Lq, w->vocab) || !check_ids(d, (int64_t)B * N * Ld, w->vocab)) return CAIR_ERR_BAD_ARG;
+#pragma omp parallel for
+  for (int b = 0; b < B; ++b) {
+    float* buf = (float*)malloc(sizeof(float) * (2 * (size_t)E + 2 * O));
+    float *pq = buf, *pd = buf + E, *rq = pd + E, *rd = rq + O;
+    for (int k = 0; k < E; ++k) {
+      float m = -INFINITY;
+      for (int t = 0; t < Lq; ++t) m = fmaxf(m, w->table[q[b * Lq + t] * E + k]);
+      pq[k] = m;
+    }
+    mlp2_tanh(pq, E, &w->query_mlp0, H, &w->query_mlp2, O, rq);
+    for (int n = 0; n < N; ++n) {
+      const int64_t* dd = d + ((int64_t)b * N + n) * Ld;
+      for (int k = 0; k < E; ++k) {
+        float m = -INFINITY;
+        for (int t = 0; t < Ld; ++t) m = fmaxf(m, w->table[dd[t] * E + k]);
+        pd[k] = m;
+      }
+      mlp2_tanh(pd, E, &w->doc_mlp0, H, &w->doc_mlp2, O, rd);
+      scores[b * N + n] = cosine_norm_first(rq, rd, O, 1e-8f);
+    }
+    free(buf);
+  }
+  return CAIR_OK;
+}
+
+/* ---- CDSSM (rankers/cdssm.py:32-77): window-3 interleave, Conv1d(3E -> L, k=3) (valid), tanh, Linear(L,O), tanh,
+ * max over positions, cosine ----------------------------------------------------------------------------------- */
+static void cdssm_side(const float* table, int E, const int64_t* ids, int L, const cair_linear* conv, int Lh,
+                       const cair_linear* sem, int O, float* rep) {
+  int T1 = L - 2, T2 = T1 - 2;  /* interleaved length, conv output length */
+  float* hid = (float*)malloc(sizeof(float) * Lh);
+  for (int o = 0; o < O; ++o) rep[o] = -INFINITY;
+  for (int t = 0; t < T2; ++t) {
+    for (int f = 0; f < Lh; ++f) {
+      double s = conv->b[f];
+      for (int k = 0; k < 3; ++k)       /* conv tap over the interleaved sequence */
+        for (int wi = 0; wi < 3; ++wi) { /* position inside the window-3 interleave */
+          const float* x = table + ids[t + k + wi] * E;
+          const float* wr = conv->w + ((size_t)f * 3 * E + (size_t)wi * E) * 3 + k;
+          for (int e = 0; e < E; ++e) s += (double)wr[(size_t)e * 3] * (double)x[e];
+        }
+      hid[f] = tanhf((float)s);
+    }
+    for (int o = 0; o < O; ++o) {
+      float v = tanhf(dotf(hid, sem->w + (size_t)o * Lh, Lh) + sem->b[o]);
+      if (v > rep[o]) rep[o] = v;
+    }
+  }
+  free(hid);
+}
+
+ORA_API int cair_oracle_cdssm(const cair_cdssm_weights* w, const int64_t* q, const int64_t* qlen, const int64_t* d,
+                              const int64_t* dlen, int B, int N, int Lq, int Ld, float* scores) {
+  (void)qlen;
+  (void)dlen;
+  int E = w->emsize, H = w->nhid, O = w->nout;
+  if (Lq < 5 || Ld < 5) return CAIR_ERR_BAD_SHAPE;  /* interleave needs >= 3 tokens, the k=3 conv 2 more */
+  if (!check_ids(q, (int64_t)B * Lq, w->vocab) || !check_ids(d, (int64_t)B * N * Ld, w->vocab)) return CAIR_ERR_BAD_ARG;
+#pragma omp parallel for
+  for (int b = 0; b < B; ++b) {
+    float* rq = (float*)malloc(sizeof(float) * 2 * O);
+    float* rd = rq + O;
+    cdssm_side(w->table, E, q + (size_t)b * Lq, Lq, &w->query_conv, H, &w->query_sem, O, rq);
+    for (int n = 0; n < N; ++n) {
+      cdssm_side(w->table, E, d + ((size_t)b * N + n) * Ld, Ld, &w->doc_conv, H, &w->doc_sem, O, rd);
+      scores[b * N + n] = cosine_norm_first(rq, rd, O, 1e-8f);
+    }
+    free(rq);
+  }
+  return CAIR_OK;
+}

@@ -121,6 +121,22 @@ def gen_esm(name, seed, B, N, Lq, Ld, E, V, **kw):
     _save(name, dict(model='esm', emsize=E, src_vocab_size=V), batch, net, dict(scores=s))
 
 
+# ------------------------------------------------------------------ DSSM / CDSSM
+def gen_dssm(name, seed, B, N, Lq, Ld, E, V, nhid, nout, conv=False, **kw):
+    if conv:
+        from neuroir.rankers.cdssm import CDSSM as Net
+    else:
+        from neuroir.rankers.dssm import DSSM as Net
+    torch.manual_seed(1013)
+    cfg = dict(model='cdssm' if conv else 'dssm', emsize=E, src_vocab_size=V, dropout_emb=0.2, nhid=nhid, nout=nout)
+    net = Net(_ns(**{k: v for k, v in cfg.items() if k != 'model'})).eval()
+    batch = synth.ranker_batch(seed, B, N, Lq, Ld, V, **kw)
+    t = _t(batch)
+    with torch.no_grad():
+        s = net(t['q'], t['qlen'], t['d'], t['dlen'])
+    _save(name, cfg, batch, net, dict(scores=s))
+
+
 # ------------------------------------------------------------------ Match-Tensor
 def gen_mt(name, seed, B, N, Lq, Ld, E, V, F, Hq, Hd, C, nf, mfs, **kw):
     from neuroir.rankers.mtensor import MatchTensor
@@ -204,6 +220,11 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     _apply_shims()
     torch.set_num_threads(1)  # deterministic MKLDNN summation order
+    only = sys.argv[1:]  # optional: fixture-name prefixes to (re)generate
+    if only:
+        g = globals()
+        for fn in ('gen_esm', 'gen_mt', 'gen_drmm', 'gen_duet', 'gen_cars', 'gen_dssm'):
+            g[fn] = (lambda f: (lambda name, *a, **k: f(name, *a, **k) if any(name.startswith(o) for o in only) else None))(g[fn])
     # BASELINE configs[0]: the reference's own CPU-runnable case (vocab cut 10k -> 1k to keep the file small)
     gen_esm('esm_cfg1', 1235, B=8, N=5, Lq=10, Ld=50, E=64, V=1000)
     gen_esm('esm_e300', 11, B=3, N=4, Lq=20, Ld=200, E=300, V=300, bos_eos=True)
@@ -219,6 +240,11 @@ def main():
     # DRMM: strict (disjoint ids) and overlapping (bin-edge cells excluded by the test using out/cos)
     gen_drmm('drmm_strict', 1237, B=3, N=4, Lq=20, Ld=200, E=300, V=400, disjoint=True)
     gen_drmm('drmm_overlap', 32, B=2, N=3, Lq=12, Ld=60, E=64, V=300, bos_eos=True, overlap=0.1)
+    # DSSM / CDSSM (stock sizes nhid=300, nout=128 at E=300; tiny variants)
+    gen_dssm('dssm_tiny', 61, B=2, N=3, Lq=6, Ld=19, E=24, V=120, nhid=16, nout=8)
+    gen_dssm('dssm_e300', 1240, B=3, N=4, Lq=20, Ld=200, E=300, V=400, nhid=300, nout=128, bos_eos=True)
+    gen_dssm('cdssm_tiny', 62, B=2, N=3, Lq=7, Ld=21, E=24, V=120, nhid=16, nout=8, conv=True)
+    gen_dssm('cdssm_e300', 1241, B=2, N=3, Lq=20, Ld=200, E=300, V=400, nhid=96, nout=64, conv=True, bos_eos=True)
     # DUET (force_pad shapes: every batch padded to max lens, lengths still variable)
     gen_duet('duet_tiny', 41, B=2, N=3, Lq=8, Ld=30, E=24, V=120, nf=16, overlap=0.2)
     gen_duet('duet_e300', 1239, B=2, N=3, Lq=20, Ld=200, E=300, V=400, nf=64, bos_eos=True, overlap=0.1)

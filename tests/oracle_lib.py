@@ -85,6 +85,9 @@ def run_ranker(cfg, sd, q, qlen, d, dlen, want=()):
         _check(L.cair_oracle_drmm(C.byref(w), qp, qlp, dp, dlp, B, N, Lq, Ld, _f32(scores),
                                   hist.ctypes.data_as(_abi.i32p) if hist is not None else None, _f32(cos)), 'drmm')
         out.update(hist=hist, cos=cos)
+    elif model in ('dssm', 'cdssm'):
+        fn = getattr(L, 'cair_oracle_' + model)
+        _check(fn(C.byref(w), qp, qlp, dp, dlp, B, N, Lq, Ld, _f32(scores)), model)
     elif model == 'duet':
         loc = np.zeros((B, N), np.float32) if 'local' in want else None
         _check(L.cair_oracle_duet(C.byref(w), qp, qlp, dp, dlp, B, N, Lq, Ld, _f32(scores), _f32(loc)), 'duet')

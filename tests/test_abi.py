@@ -24,7 +24,7 @@ def header_symbols():
 
 def test_library_exports_every_declared_symbol():
     syms = header_symbols()
-    assert len(syms) >= 19
+    assert len(syms) >= 25
     L = lib.load()
     for s in syms:
         assert hasattr(L, s), s
@@ -40,7 +40,8 @@ def test_no_compute_without_gpu_fails_loudly():
         net(q, ql, d, dl)
 
 
-@pytest.mark.parametrize('name', ['esm_cfg1', 'mt_cfg2arch', 'mt_stock', 'drmm_strict', 'duet_e300', 'cars_mid'])
+@pytest.mark.parametrize('name', ['esm_cfg1', 'mt_cfg2arch', 'mt_stock', 'drmm_strict', 'duet_e300', 'cars_mid', 'dssm_e300',
+                                  'cdssm_tiny'])
 def test_state_dict_keys_and_shapes_match_reference(name):
     cfg, _, sd, _ = ol.load_golden(name)
     net = helpers.build_module(cfg)

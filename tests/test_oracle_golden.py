@@ -93,3 +93,16 @@ def test_bad_token_id_is_an_error():
     q[0, 0] = cfg['src_vocab_size']
     with pytest.raises(RuntimeError, match='BAD_ARG'):
         ol.run_ranker(cfg, sd, q, ins['qlen'], ins['d'], ins['dlen'])
+
+
+@pytest.mark.parametrize('name', ['dssm_tiny', 'dssm_e300', 'cdssm_tiny', 'cdssm_e300'])
+def test_dssm_cdssm(name):
+    cfg, ins, sd, outs = ol.load_golden(name)
+    o = ol.run_ranker(cfg, sd, ins['q'], ins['qlen'], ins['d'], ins['dlen'])
+    assert _max_rel(o['scores'], outs['scores']) < 1e-4
+
+
+def test_cdssm_rejects_too_short_sequences():
+    cfg, ins, sd, outs = ol.load_golden('cdssm_tiny')
+    with pytest.raises(RuntimeError, match='BAD_SHAPE'):
+        ol.run_ranker(cfg, sd, ins['q'][:, :4], ins['qlen'], ins['d'], ins['dlen'])

@@ -149,6 +149,12 @@ def test_duet_golden(name):
     assert _max_rel(s, outs['scores']) < TOL
 
 
+@pytest.mark.parametrize('name', ['dssm_tiny', 'dssm_e300', 'cdssm_tiny', 'cdssm_e300'])
+def test_dssm_cdssm_golden(name):
+    *_, outs, net, s = _run(name)
+    assert _max_rel(s, outs['scores']) < TOL
+
+
 def test_duet_rejects_unpadded_batches():
     cfg, ins, sd, outs = ol.load_golden('duet_tiny')
     net = helpers.build_module(cfg, sd, DEV)
