@@ -206,6 +206,12 @@ int32_t cair_mt_set_debug(cair_handle* h, float* enc_q, float* enc_d) {
   return CAIR_OK;
 }
 
+int32_t cair_set_gemm_impl(int32_t impl) {
+  if (impl != 0 && impl != 1) return fail(CAIR_ERR_BAD_ARG, "set_gemm_impl: 0 (fp32 CUDA cores) or 1 (tcgen05)");
+  g_gemm_impl = impl;
+  return CAIR_OK;
+}
+
 int32_t cair_mt_set_impl(cair_handle* h, int32_t impl) {
   if (!h || h->model != CAIR_MODEL_MT) return fail(CAIR_ERR_BAD_ARG, "mt_set_impl: not a match-tensor handle");
   if (impl != MT_IMPL_FP32 && impl != MT_IMPL_TC) return fail(CAIR_ERR_BAD_ARG, "mt_set_impl: impl must be 0 (fp32) or 1 (tcgen05)");

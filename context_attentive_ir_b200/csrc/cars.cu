@@ -20,6 +20,7 @@ static int32_t attn_copy(Owned& own, const cair_attn_mlp& a, int H, AttnPack* p,
   CAIR_TRY(dev_copy(own, a.l0.b, (size_t)H, &p->b0, s));
   CAIR_TRY(dev_copy(own, a.l3.w, (size_t)H, &p->w3, s));
   CAIR_TRY(dev_copy(own, a.l3.b, 1, &p->b3, s));
+  CAIR_TRY(gemm_tc_pack(own, p->w0, H, H, &p->w0_tc, s));
   return CAIR_OK;
 }
 
@@ -366,7 +367,7 @@ static int32_t encode_pool(const CarsState& st, const LstmPack& lp, const AttnPa
   const int H = ap.H;
   CAIR_TRY(lstm_run(lp, gemm_gather(st.table, st.V, st.E, ids, 1, 1, 1, err), len, (int)n, L, enc, nullptr, nullptr,
                     pre, err, s));
-  CAIR_TRY(gemm_f32(gemm_dense(enc, H), ap.w0, ap.b0, hid, H, n * L, H, H, ACT_TANH, s));
+  CAIR_TRY(gemm_auto(gemm_dense(enc, H), ap.w0, ap.w0_tc, ap.b0, hid, H, n * L, H, H, ACT_TANH, s));
   CAIR_LAUNCH(attn_pool_kernel, (unsigned)n, 256, (size_t)L * sizeof(float), s, enc, hid, len, L, H, ap.w3, ap.b3,
               pooled);
   return CAIR_OK;
@@ -408,7 +409,8 @@ int32_t cars_forward(const CarsState& st, const CarsIO& io, int B, int S, int N,
   // 2. click vectors
   CAIR_CUDA(cudaMemsetAsync(mwidth, 0, sizeof(int), s));
   CAIR_LAUNCH(click_width_kernel, (B * S + 255) / 256, 256, 0, s, io.labels, B * S, N, mwidth);
-  CAIR_TRY(gemm_f32(gemm_dense(pd, Hd), st.click_attn.w0, st.click_attn.b0, hid_c, Hd, ndocs, Hd, Hd, ACT_TANH, s));
+  CAIR_TRY(gemm_auto(gemm_dense(pd, Hd), st.click_attn.w0, st.click_attn.w0_tc, st.click_attn.b0, hid_c, Hd, ndocs, Hd, Hd,
+                     ACT_TANH, s));
   CAIR_LAUNCH(rowdot_kernel, (unsigned)((ndocs + 7) / 8), 256, 0, s, hid_c, ndocs, Hd, st.click_attn.w3, st.click_attn.b3, att_c);
   CAIR_LAUNCH(clicks_kernel, (unsigned)nrows, 128, (size_t)N * 8, s, pd, att_c, io.labels, N, Hd, mwidth, r0, clk);
   // 3. session LSTMs over the pooled queries / click vectors (zero initial state, S steps each)

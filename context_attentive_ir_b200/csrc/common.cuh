@@ -169,12 +169,30 @@ inline GemmA gemm_pooled(const float* a, int64_t lda, int win, int L, int T) {
 int32_t gemm_f32(const GemmA& a, const float* w, const float* bias, float* c, int64_t ldc, int64_t M,
                  int N, int K, Act act, cudaStream_t s);
 
+// tcgen05 GEMM (gemm_tc.cu): weights pre-packed as bf16 hi/lo operand images per (column tile, K chunk).
+struct GemmTcW {
+  int N = 0, K = 0, NT = 0, nct = 0, nkc = 0;
+  uint8_t* img = nullptr;
+};
+extern int g_gemm_impl;  // 1 (default): tcgen05 GEMM where usable, 0: fp32 CUDA-core GEMM everywhere
+int32_t gemm_tc_pack(Owned& own, const float* w, int N, int K, GemmTcW* out, cudaStream_t s);
+bool gemm_tc_usable(const GemmA& a, int K);
+int32_t gemm_tc(const GemmA& a, const GemmTcW& w, const float* bias, float* c, int64_t ldc, int64_t M, Act act,
+                cudaStream_t s);
+// tensor-core GEMM when a packed image exists and the A provider is 128-bit loadable, else the fp32 kernel
+inline int32_t gemm_auto(const GemmA& a, const float* w, const GemmTcW& tw, const float* bias, float* c, int64_t ldc,
+                         int64_t M, int N, int K, Act act, cudaStream_t s) {
+  if (tw.img && M >= 128 && gemm_tc_usable(a, K)) return gemm_tc(a, tw, bias, c, ldc, M, act, s);
+  return gemm_f32(a, w, bias, c, ldc, M, N, K, act, s);
+}
+
 // LSTM weights repacked for the recurrent kernel.
 struct LstmPack {
   int in, h, dirs;
   float* w_ih;    // [dirs*4h, in]  (fwd rows then rev rows): the pre-gate GEMM's W
   float* bias;    // [dirs*4h]      b_ih + b_hh
   float* w_hh_t;  // [dirs][h][4h]  k-major recurrent weights
+  GemmTcW w_ih_tc;  // tensor-core image of w_ih (pre-gate GEMM)
 };
 int32_t lstm_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, int in, int h, LstmPack* out,
                   cudaStream_t s);

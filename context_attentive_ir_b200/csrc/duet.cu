@@ -42,6 +42,8 @@ int32_t duet_create_state(Owned& own, const cair_duet_weights& w, DuetState* st,
   int64_t total = (int64_t)nf * (3 * E > Ld ? 3 * E : Ld);
   CAIR_LAUNCH(duet_pack_kernel, (unsigned)((total + 255) / 256), 256, 0, s, w.local_conv1d.w, nf, Ld, st->lconv_t,
               w.conv_q.w, w.conv_d1.w, E, st->cq_w, st->cd1_w);
+  CAIR_TRY(gemm_tc_pack(own, st->cq_w, nf, 3 * E, &st->cq_tc, s));
+  CAIR_TRY(gemm_tc_pack(own, st->cd1_w, nf, 3 * E, &st->cd1_tc, s));
   CAIR_TRY(dev_copy(own, w.local_conv1d.b, (size_t)nf, &st->lconv_b, s));
   CAIR_TRY(dev_copy(own, w.local_fc1.w, (size_t)Lq, &st->lfc1_w, s));
   CAIR_TRY(dev_copy(own, w.local_fc1.b, 1, &st->lfc1_b, s));
@@ -53,6 +55,7 @@ int32_t duet_create_state(Owned& own, const cair_duet_weights& w, DuetState* st,
   CAIR_TRY(dev_copy(own, w.conv_d1.b, (size_t)nf, &st->cd1_b, s));
   CAIR_TRY(dev_copy(own, w.conv_d2.w, (size_t)nf * nf, &st->cd2_w, s));
   CAIR_TRY(dev_copy(own, w.conv_d2.b, (size_t)nf, &st->cd2_b, s));
+  CAIR_TRY(gemm_tc_pack(own, st->cd2_w, nf, nf, &st->cd2_tc, s));
   CAIR_TRY(dev_copy(own, w.dist_fc1.w, (size_t)nf * nf, &st->fc1_w, s));
   CAIR_TRY(dev_copy(own, w.dist_fc1.b, (size_t)nf, &st->fc1_b, s));
   CAIR_TRY(dev_copy(own, w.dist_fc2.w, (size_t)(Ld - w.pool_size - 1), &st->fc2_w, s));
@@ -179,14 +182,15 @@ int32_t duet_forward(const DuetState& st, const int64_t* q, const int64_t* d, in
               st.lfc1_w, st.lfc1_b, m1l);
   CAIR_TRY(gemm_f32(gemm_dense(m1l, nf), st.lfc2_w, st.lfc2_b, m2l, nf, pc, nf, nf, ACT_TANH, s));
   // distributed model, query side
-  CAIR_TRY(gemm_f32(gemm_gather(st.table, st.V, E, q + qb * Lq, 3, Lq, Tq, err), st.cq_w, st.cq_b, cqv, nf, nq * Tq,
-                    nf, 3 * E, ACT_TANH, s));
+  CAIR_TRY(gemm_auto(gemm_gather(st.table, st.V, E, q + qb * Lq, 3, Lq, Tq, err), st.cq_w, st.cq_tc, st.cq_b, cqv, nf,
+                     nq * Tq, nf, 3 * E, ACT_TANH, s));
   CAIR_LAUNCH(colmax_kernel, (unsigned)nq, 256, 0, s, cqv, Tq, nf, mq);
   CAIR_TRY(gemm_f32(gemm_dense(mq, nf), st.fc1_w, st.fc1_b, rq, nf, nq, nf, nf, ACT_TANH, s));
   // distributed model, document side
-  CAIR_TRY(gemm_f32(gemm_gather(st.table, st.V, E, d + pb * Ld, 3, Ld, Td, err), st.cd1_w, st.cd1_b, cdv, nf, pc * Td,
-                    nf, 3 * E, ACT_TANH, s));
-  CAIR_TRY(gemm_f32(gemm_pooled(cdv, nf, st.pool, Td, Tp), st.cd2_w, st.cd2_b, rd, nf, pc * Tp, nf, nf, ACT_TANH, s));
+  CAIR_TRY(gemm_auto(gemm_gather(st.table, st.V, E, d + pb * Ld, 3, Ld, Td, err), st.cd1_w, st.cd1_tc, st.cd1_b, cdv, nf,
+                     pc * Td, nf, 3 * E, ACT_TANH, s));
+  CAIR_TRY(gemm_auto(gemm_pooled(cdv, nf, st.pool, Td, Tp), st.cd2_w, st.cd2_tc, st.cd2_b, rd, nf, pc * Tp, nf, nf,
+                     ACT_TANH, s));
   CAIR_LAUNCH(duet_hadamard_kernel, dim3((unsigned)pc, (nf + 127) / 128), 128, 0, s, rd, rq, st.fc2_w, st.fc2_b, N, Tp,
               nf, pb, qb, m1d);
   CAIR_TRY(gemm_f32(gemm_dense(m1d, nf), st.fc3_w, st.fc3_b, m2d, nf, pc, nf, nf, ACT_TANH, s));

@@ -46,6 +46,8 @@ int32_t lstm_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* rev
     CAIR_LAUNCH(lstm_pack_kernel, (unsigned)((n + 255) / 256), 256, 0, s, w->w_ih, w->w_hh, w->b_ih, w->b_hh, in,
                 h, out->w_ih + (size_t)d * G * in, out->bias + (size_t)d * G, out->w_hh_t + (size_t)d * G * h);
   }
+  if ((size_t)dirs * G * in >= 64 * 1024)  // big input projections (CARS: 1024 x 300) go to the tensor cores
+    CAIR_TRY(gemm_tc_pack(own, out->w_ih, dirs * G, in, &out->w_ih_tc, s));
   return CAIR_OK;
 }
 
@@ -173,7 +175,7 @@ int32_t lstm_run(const LstmPack& p, const GemmA& x, const int64_t* len, int n, i
                  float* c_n, float* ws_pre, int* err, cudaStream_t s, const char* rec_name) {
   if (n <= 0) return CAIR_OK;
   const int G = 4 * p.h, PG = p.dirs * G;
-  CAIR_TRY(gemm_f32(x, p.w_ih, p.bias, ws_pre, PG, (int64_t)n * L, PG, p.in, ACT_NONE, s));
+  CAIR_TRY(gemm_auto(x, p.w_ih, p.w_ih_tc, p.bias, ws_pre, PG, (int64_t)n * L, PG, p.in, ACT_NONE, s));
   if (rec_name) prof_mark(rec_name, s);
   const int hp = (p.h + 3) & ~3;
   size_t state = (size_t)(TS * hp + TS * p.h + TS * G) * sizeof(float);

@@ -65,6 +65,7 @@ struct MtState {
   LstmPack enc_q{}, enc_d{};
   LstmTcPack tc_q{}, tc_d{};  // tensor-core encoders (valid when lstm_tc_supported)
   float *wq = nullptr, *bq = nullptr, *wd = nullptr, *bd = nullptr;  // channel projections
+  GemmTcW wd_tc;                                                      // tensor-core image of the doc projection
   MtPack pack{};
   MtEpiConst epi{};
   cudaStream_t side = nullptr;            // query-side work runs here, forked/joined with events
@@ -103,6 +104,7 @@ struct DuetState {
   float *lfc1_w = nullptr, *lfc1_b = nullptr, *lfc2_w = nullptr, *lfc2_b = nullptr, *lfc3_w = nullptr, *lfc3_b = nullptr;
   float *cq_w = nullptr, *cq_b = nullptr, *cd1_w = nullptr, *cd1_b = nullptr;  // [nf][3*E] (tap-major K)
   float *cd2_w = nullptr, *cd2_b = nullptr;
+  GemmTcW cq_tc, cd1_tc, cd2_tc;  // tensor-core images of the three convolutions
   float *fc1_w = nullptr, *fc1_b = nullptr, *fc2_w = nullptr, *fc2_b = nullptr, *fc3_w = nullptr, *fc3_b = nullptr,
         *fc4_w = nullptr, *fc4_b = nullptr;
 };
@@ -114,6 +116,7 @@ int32_t duet_forward(const DuetState& st, const int64_t* q, const int64_t* d, in
 struct AttnPack {
   int H = 0;
   float *w0 = nullptr, *b0 = nullptr, *w3 = nullptr, *b3 = nullptr;
+  GemmTcW w0_tc;
 };
 struct CarsState {
   int V = 0, E = 0, Hq = 0, Hd = 0, Hsq = 0, Hsd = 0;

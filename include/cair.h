@@ -159,6 +159,10 @@ CAIR_API int32_t cair_mt_create(const cair_mt_weights* w, int32_t device, cair_h
  * enc_q [B,Lq,Hq], enc_d [B*N,Ld,Hd] as RNNEncoder returns them (mtensor.py:93-94). */
 CAIR_API int32_t cair_mt_set_debug(cair_handle* h, float* enc_q, float* enc_d);
 
+/* Process-wide GEMM engine for the generic projections / convolutions (DUET, CARS, DSSM, channel projections):
+ * 1 = tcgen05 bf16x3 tensor-core GEMM where the operand layout allows (default), 0 = fp32 CUDA-core GEMM. */
+CAIR_API int32_t cair_set_gemm_impl(int32_t impl);
+
 /* Interaction kernel selection: 1 = tcgen05 bf16x3 split-precision tensor-core kernel (default when the
  * configuration fits: nfilters in {4,6}, nchannels <= 64, match_filter_size <= 32), 0 = fp32 CUDA-core
  * kernel (always available; the on-device cross-check of the tensor-core path). */

@@ -143,8 +143,16 @@ def test_drmm_golden_overlap_rows_away_from_bin_edges():
     assert (h.sum(-1) <= Ld).all() and (h.sum(-1) >= Ld - near.sum(-1)).all()
 
 
+@pytest.fixture(params=['tcgen05-gemm', 'fp32-gemm'])
+def gemm_engine(request):
+    """Runs a test with both engines of the generic GEMM (tcgen05 bf16x3 / fp32 CUDA cores)."""
+    lib.check(lib.load().cair_set_gemm_impl(1 if request.param == 'tcgen05-gemm' else 0))
+    yield request.param
+    lib.check(lib.load().cair_set_gemm_impl(1))
+
+
 @pytest.mark.parametrize('name', ['duet_tiny', 'duet_e300'])
-def test_duet_golden(name):
+def test_duet_golden(name, gemm_engine):
     *_, outs, net, s = _run(name)
     assert _max_rel(s, outs['scores']) < TOL
 
@@ -164,7 +172,7 @@ def test_duet_rejects_unpadded_batches():
 
 
 @pytest.mark.parametrize('name', ['cars_tiny', 'cars_clicks', 'cars_mid'])
-def test_cars_golden(name):
+def test_cars_golden(name, gemm_engine):
     cfg, ins, sd, outs = ol.load_golden(name)
     net = helpers.build_module(cfg, sd, DEV)
     args = helpers.to_dev(ins, DEV, ('q', 'qlen', 'd', 'dlen', 'label'))
@@ -228,7 +236,7 @@ def test_esm_cfg1_vs_oracle():
     assert _max_rel(s, ref) < 1e-4
 
 
-def test_duet_cfg5_shapes_vs_oracle():
+def test_duet_cfg5_shapes_vs_oracle(gemm_engine):
     cfg = dict(model='duet', emsize=300, src_vocab_size=3000, dropout_emb=0.2, dropout=0.2, use_word=True,
                nfilters=300, local_filter_size=1, dist_filter_size=3, pool_size=5, max_doc_len=200, max_query_len=20)
     net, batch, s, ref = _fresh(cfg, 104, B=2, N=10, Lq=20, Ld=200, overlap=0.1)
@@ -281,6 +289,23 @@ def test_bad_token_id_is_reported():
         net(q, ql, d, dl)
     with pytest.raises(lib.CairError, match='BAD_ARG'):
         net.poll_error()
+
+
+def test_cars_cfg4_architecture_vs_oracle(gemm_engine):
+    """Stock CARS sizes (E=300, H=256, session 512) at a reduced batch: exercises the tensor-core pre-gate GEMM."""
+    cfg = dict(model='cars', emsize=300, src_vocab_size=2000, tgt_vocab_size=50, dropout_emb=0.2, dropout=0.2, rnn_type='LSTM',
+               bidirection=True, nlayers=1, nhid_query=256, nhid_document=256, nhid_click=512, nhid_session_query=512,
+               nhid_session_document=512, nhid_decoder=512, query_session_off=False, doc_session_off=False, dropout_rnn=0.2,
+               attn_type='general', mlp_nhid=150, pool_type='attn', regularize_coeff=0.1, alpha=0.1, lambda1=0.01,
+               lambda2=0.0001, turn_ranker_off=False, turn_recommender_off=False)
+    torch.manual_seed(7)
+    net = helpers.build_module(cfg).to(DEV)
+    batch = synth.session_batch(1238, 2, 3, 10, 20, 60, cfg['src_vocab_size'], max_clicks=2)
+    args = helpers.to_dev(batch, DEV, ('q', 'qlen', 'd', 'dlen', 'label'))
+    with torch.no_grad():
+        s = net.score(*args)['scores'].cpu().numpy()
+    ref = ol.run_cars(cfg, helpers.state_dict_numpy(net), batch['q'], batch['qlen'], batch['d'], batch['dlen'], batch['label'])
+    assert _max_rel(s, ref['scores']) < TOL
 
 
 def test_lstm_entry_point_vs_oracle():
