@@ -283,7 +283,6 @@ int32_t mt_create_state(Owned& own, const cair_mt_weights& w, MtState* st, cudaS
   CAIR_TRY(dev_copy(own, w.query_projection.b, (size_t)w.nchannels, &st->bq, s));
   CAIR_TRY(dev_copy(own, w.document_projection.w, (size_t)w.nchannels * w.nhid_doc, &st->wd, s));
   CAIR_TRY(dev_copy(own, w.document_projection.b, (size_t)w.nchannels, &st->bd, s));
-  CAIR_TRY(gemm_tc_pack(own, st->wd, w.nchannels, w.nhid_doc, &st->wd_tc, s));
   CAIR_TRY(mt_pack(own, w, &st->pack, s));
   CAIR_TRY(mt_epi_const(st->pack, &st->epi, s));
   CAIR_CUDA(cudaStreamCreateWithFlags(&st->side, cudaStreamNonBlocking));
@@ -356,10 +355,8 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
                               cudaMemcpyDeviceToDevice, s));
   // channel projection (:108): the bias also lands on pad positions (zero memory-bank rows)
   prof_mark("doc_projection", s);
-  if (st.impl == MT_IMPL_TC)
-    CAIR_TRY(gemm_auto(gemm_dense(enc_d, st.Hd), st.wd, st.wd_tc, st.bd, cd, st.C, pc * Ld, st.C, st.Hd, ACT_NONE, s));
-  else
-    CAIR_TRY(gemm_f32(gemm_dense(enc_d, st.Hd), st.wd, st.bd, cd, st.C, pc * Ld, st.C, st.Hd, ACT_NONE, s));
+  // (K = 128, N = 50 is too small a tile for the tcgen05 GEMM's per-CTA setup: the fp32 kernel is faster here)
+  CAIR_TRY(gemm_f32(gemm_dense(enc_d, st.Hd), st.wd, st.bd, cd, st.C, pc * Ld, st.C, st.Hd, ACT_NONE, s));
   if (use_tc) {
     CAIR_TRY(mt_tc_doc_image(st.pack, cd, aimg, Ld, pc, s));
     prof_mark("join_query_side", s);

@@ -139,6 +139,26 @@ __device__ __forceinline__ void mma_commit_w(uint64_t* bar, uint32_t issue) {
       ::"r"(smem_u32(bar)), "r"(issue)
       : "memory");
 }
+// A operand from TENSOR MEMORY (".ts" form): A[128 x 16] bf16 lives in 8 TMEM columns (lane = row, each 32-bit column
+// holds two consecutive K elements, even k in the low half); B still comes from shared memory.
+__device__ __forceinline__ void mma_bf16_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+// registers -> TMEM: thread i of warp w writes lane 32*(w%4)+i, 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // All previously issued MMAs of this thread arrive on the mbarrier when they complete
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {

@@ -50,7 +50,33 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restr
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_slot;
-  if (tid == 0) {
+  if (split == 2) {
+    // A operand from tensor memory: thread <-> row; columns [acol, acol + K/2) hold bf16 pairs (k, k+1)
+    const uint32_t acol = (uint32_t)((N + 31) & ~31);
+    const int m = warp * 32 + lane;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const __nv_bfloat16 lo = __float2bfloat16_rn(A[(size_t)(m + shift) * K + k0 + 2 * e]);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(A[(size_t)(m + shift) * K + k0 + 2 * e + 1]);
+        pk[e] = (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+      }
+      tmem_st8(tbase + ((uint32_t)(warp * 32) << 16) + acol + (uint32_t)(k0 / 2), pk);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) {
+      const uint32_t issue = elect_one();
+      const uint32_t idesc = idesc_bf16_f32(128, N);
+      for (int ks = 0; ks < K / 16; ++ks)
+        mma_bf16_ts_w(tbase, tbase + acol + (uint32_t)(ks * 8), smem_desc(smem_u32(b_hi) + (2 * ks) * b_plane, b_plane, 128),
+                      idesc, (uint32_t)(ks != 0), issue);
+      mma_commit_w(&bar, issue);
+    }
+  } else if (tid == 0) {
     const uint32_t idesc = idesc_bf16_f32(128, N);
     bool acc = false;
     for (int pass = 0; pass < (split ? 3 : 1); ++pass) {
@@ -95,6 +121,8 @@ extern "C" int32_t cair_umma_selftest(const float* A, const float* B, float* D, 
   while ((int)tcols < N) tcols <<= 1;
   // tmem_ld32 reads 32-column groups: keep the whole last group inside the allocation
   while ((int)tcols < ((N + 31) & ~31)) tcols <<= 1;
+  if (split == 2)  // room for the A operand columns (K/2) behind the accumulator
+    while ((int)tcols < ((N + 31) & ~31) + K / 2) tcols <<= 1;
   CAIR_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CAIR_LAUNCH(umma_selftest_kernel, 1, 128, smem, (cudaStream_t)stream, A, B, D, N, K, shift, RA, split, tcols);
   return CAIR_OK;
@@ -130,9 +158,16 @@ __global__ void __launch_bounds__(160) umma_bench_kernel(int N, int K, int reps,
     if (uniform) {
       const uint32_t issue = elect_one();
       const uint64_t ad = smem_desc(a0, a_plane, 128), bd = smem_desc(b0, b_plane, 128);
-      for (int r = 0; r < reps; ++r)
-        for (int ks = 0; ks < K / 16; ++ks)
-          mma_bf16_ss_w(tbase, ad + (uint64_t)(ks * ((2 * a_plane) >> 4)), bd + (uint64_t)(ks * ((2 * b_plane) >> 4)), idesc, 1, issue);
+      if (uniform & 2) {
+        const uint32_t acol = tmem_slot + 256;  // operand columns (contents irrelevant for timing)
+        for (int r = 0; r < reps; ++r)
+          for (int ks = 0; ks < K / 16; ++ks)
+            mma_bf16_ts_w(tbase, acol + (uint32_t)(ks * 8), bd + (uint64_t)(ks * ((2 * b_plane) >> 4)), idesc, 1, issue);
+      } else {
+        for (int r = 0; r < reps; ++r)
+          for (int ks = 0; ks < K / 16; ++ks)
+            mma_bf16_ss_w(tbase, ad + (uint64_t)(ks * ((2 * a_plane) >> 4)), bd + (uint64_t)(ks * ((2 * b_plane) >> 4)), idesc, 1, issue);
+      }
       long long t1 = clock64();
       mma_commit_w(&bar[warp - 1], issue);
       mbar_wait(&bar[warp - 1], 0);
@@ -159,13 +194,14 @@ extern "C" CAIR_API int32_t cair_umma_bench(int32_t N, int32_t K, int32_t reps, 
                                             void* stream) {
   using namespace cair;
   // uniform: bit 0 = warp-uniform issue loop, bits 4.. = number of concurrently issuing warps (default 1)
-  int nwarps = uniform >> 4;
+  int nwarps = (uniform >> 4) & 15;
   if (nwarps < 1) nwarps = 1;
   if (nwarps > 4 || nwarps * N > 512) return fail(CAIR_ERR_BAD_ARG, "umma_bench: too many warps / columns");
   size_t smem = (size_t)(K / 8) * 16 * (128 + N);
   uint32_t tcols = 32;
   while ((int)tcols < nwarps * N) tcols <<= 1;
+  if (uniform & 2) tcols = 512;
   CAIR_CUDA(cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CAIR_LAUNCH(umma_bench_kernel, 1, 160, smem, (cudaStream_t)stream, N, K, reps, uniform & 1, nwarps, tcols, cycles);
+  CAIR_LAUNCH(umma_bench_kernel, 1, 160, smem, (cudaStream_t)stream, N, K, reps, uniform & 3, nwarps, tcols, cycles);
   return CAIR_OK;
 }

@@ -47,7 +47,8 @@ def test_tcgen05_conventions_selftest():
     """D = A[shift:shift+128] @ B^T through tcgen05.mma with the library's operand layout / descriptors."""
     rng = np.random.default_rng(0)
     L = lib.load()
-    for (N, K, shift, split) in [(64, 64, 0, 0), (96, 64, 3, 1), (96, 64, 6, 1), (256, 112, 0, 1), (16, 16, 1, 0)]:
+    for (N, K, shift, split) in [(64, 64, 0, 0), (96, 64, 3, 1), (96, 64, 6, 1), (256, 112, 0, 1), (16, 16, 1, 0),
+                                 (32, 112, 0, 2), (64, 32, 2, 2)]:  # split=2: A operand from tensor memory
         A = rng.standard_normal((128 + shift, K)).astype(np.float32)
         B = rng.standard_normal((N, K)).astype(np.float32)
         a, b = torch.from_numpy(A).to(DEV), torch.from_numpy(B).to(DEV)
@@ -55,7 +56,7 @@ def test_tcgen05_conventions_selftest():
         lib.check(L.cair_umma_selftest(a.data_ptr(), b.data_ptr(), d.data_ptr(), N, K, shift, split,
                                        torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
-        if split:
+        if split == 1:
             ref = A[shift:shift + 128].astype(np.float64) @ B.astype(np.float64).T
             tol = 1e-3  # ~2^-16 relative per product, |sum| ~ sqrt(K)
         else:
