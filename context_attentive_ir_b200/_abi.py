@@ -65,6 +65,24 @@ class CdssmWeights(C.Structure):
         (k, Linear) for k in ('query_conv', 'query_sem', 'doc_conv', 'doc_sem')]
 
 
+ARC_MAX_LAYERS = 4
+
+
+class ArciWeights(C.Structure):
+    _fields_ = [('vocab', C.c_int32), ('emsize', C.c_int32), ('nlayers', C.c_int32),
+                ('filters', C.c_int32 * ARC_MAX_LAYERS), ('kernel', C.c_int32 * ARC_MAX_LAYERS),
+                ('pool', C.c_int32 * ARC_MAX_LAYERS), ('max_query_len', C.c_int32), ('max_doc_len', C.c_int32),
+                ('table', f32p), ('qconv', Linear * ARC_MAX_LAYERS), ('dconv', Linear * ARC_MAX_LAYERS),
+                ('mlp0', Linear), ('mlp1', Linear)]
+
+
+class ArciiWeights(C.Structure):
+    _fields_ = [('vocab', C.c_int32), ('emsize', C.c_int32), ('filters_1d', C.c_int32), ('kernel_1d', C.c_int32),
+                ('nlayers2d', C.c_int32), ('filters_2d', C.c_int32 * ARC_MAX_LAYERS), ('max_query_len', C.c_int32),
+                ('max_doc_len', C.c_int32), ('table', f32p), ('conv_query', Linear), ('conv_doc', Linear),
+                ('conv2d', Linear * ARC_MAX_LAYERS), ('mlp0', Linear), ('mlp1', Linear)]
+
+
 class CarsWeights(C.Structure):
     _fields_ = [(k, C.c_int32) for k in
                 ('vocab', 'emsize', 'nhid_query', 'nhid_document', 'nhid_session_query',
@@ -158,6 +176,36 @@ def pack_cdssm(cfg, get):
     return w
 
 
+def pack_arci(cfg, get):
+    nl = len(cfg['filters_1d'])
+    if nl > ARC_MAX_LAYERS:
+        raise NotImplementedError('ARC-I with more than %d conv layers' % ARC_MAX_LAYERS)
+    w = ArciWeights(cfg['src_vocab_size'], cfg['emsize'], nl)
+    for i in range(nl):
+        w.filters[i], w.kernel[i], w.pool[i] = cfg['filters_1d'][i], cfg['kernel_size_1d'][i], cfg['maxpool_size_1d'][i]
+        w.qconv[i] = _lin(get, 'query_conv1d_layers.%d.0' % i)
+        w.dconv[i] = _lin(get, 'doc_conv1d_layers.%d.0' % i)
+    w.max_query_len, w.max_doc_len, w.table = cfg['max_query_len'], cfg['max_doc_len'], get(TABLE_KEY)
+    w.mlp0, w.mlp1 = _lin(get, 'mlp.0'), _lin(get, 'mlp.1')
+    return w
+
+
+def pack_arcii(cfg, get):
+    nl = len(cfg['filters_2d'])
+    if nl > ARC_MAX_LAYERS:
+        raise NotImplementedError('ARC-II with more than %d conv2d layers' % ARC_MAX_LAYERS)
+    if any(list(k) != [3, 3] for k in cfg['kernel_size_2d']) or any(list(k) != [2, 2] for k in cfg['maxpool_size_2d']):
+        raise NotImplementedError('libcair implements the stock 3x3 kernels / 2x2 max-pools (neuroir/hyparam.py:61-76)')
+    w = ArciiWeights(cfg['src_vocab_size'], cfg['emsize'], cfg['filters_1d'], cfg['kernel_size_1d'], nl)
+    for i in range(nl):
+        w.filters_2d[i] = cfg['filters_2d'][i]
+        w.conv2d[i] = _lin(get, 'conv2d_layers.%d.0' % i)
+    w.max_query_len, w.max_doc_len, w.table = cfg['max_query_len'], cfg['max_doc_len'], get(TABLE_KEY)
+    w.conv_query, w.conv_doc = _lin(get, 'conv_query'), _lin(get, 'conv_doc')
+    w.mlp0, w.mlp1 = _lin(get, 'mlp.0'), _lin(get, 'mlp.1')
+    return w
+
+
 def pack_cars(cfg, get):
     """Stock CARS ranking path (multitask/cars.py:28-131): LSTM, bidirectional, 1 layer, attn pooling."""
     w = CarsWeights(cfg['src_vocab_size'], cfg['emsize'], cfg['nhid_query'], cfg['nhid_document'],
@@ -183,5 +231,5 @@ def pack_cars(cfg, get):
     return w
 
 
-PACKERS = {'dssm': pack_dssm, 'cdssm': pack_cdssm, 'esm': pack_esm, 'match_tensor': pack_mt, 'drmm': pack_drmm, 'duet': pack_duet,
+PACKERS = {'arci': pack_arci, 'arcii': pack_arcii, 'dssm': pack_dssm, 'cdssm': pack_cdssm, 'esm': pack_esm, 'match_tensor': pack_mt, 'drmm': pack_drmm, 'duet': pack_duet,
            'cars': pack_cars}

@@ -36,6 +36,8 @@ struct cair_handle {
   DrmmState drmm;
   DuetState duet;
   DssmState dssm;
+  ArciState arci;
+  ArciiState arcii;
   CdssmState cdssm;
   CarsState cars;
   // host-path staging (cair_ranker_forward_host)
@@ -304,6 +306,30 @@ int32_t cair_cdssm_create(const cair_cdssm_weights* w, int32_t device, cair_hand
   return rc;
 }
 
+int32_t cair_arci_create(const cair_arci_weights* w, int32_t device, cair_handle** out) {
+  if (!w || !w->table) return fail(CAIR_ERR_BAD_ARG, "arci_create: bad weights");
+  cair_handle* h = nullptr;
+  CAIR_TRY(new_handle(CAIR_MODEL_ARCI, device, &h));
+  DeviceGuard g(device);
+  int32_t rc = init_err_flag(h);
+  if (rc == CAIR_OK) rc = arci_create_state(h->own, *w, &h->arci, 0);
+  rc = finish_create(h, rc, out);
+  if (rc == CAIR_OK) *out = h;
+  return rc;
+}
+
+int32_t cair_arcii_create(const cair_arcii_weights* w, int32_t device, cair_handle** out) {
+  if (!w || !w->table) return fail(CAIR_ERR_BAD_ARG, "arcii_create: bad weights");
+  cair_handle* h = nullptr;
+  CAIR_TRY(new_handle(CAIR_MODEL_ARCII, device, &h));
+  DeviceGuard g(device);
+  int32_t rc = init_err_flag(h);
+  if (rc == CAIR_OK) rc = arcii_create_state(h->own, *w, &h->arcii, 0);
+  rc = finish_create(h, rc, out);
+  if (rc == CAIR_OK) *out = h;
+  return rc;
+}
+
 int32_t cair_cars_create(const cair_cars_weights* w, int32_t device, cair_handle** out) {
   if (!w || !w->table) return fail(CAIR_ERR_BAD_ARG, "cars_create: bad weights");
   cair_handle* h = nullptr;
@@ -340,6 +366,10 @@ static int32_t ranker_run(cair_handle* h, const int64_t* q, const int64_t* qlen,
       return dssm_forward(h->dssm, q, d, N, Lq, Ld, pb, pc, scores, ws, h->d_err, s, dry);
     case CAIR_MODEL_CDSSM:
       return cdssm_forward(h->cdssm, q, d, N, Lq, Ld, pb, pc, scores, ws, h->d_err, s, dry);
+    case CAIR_MODEL_ARCI:
+      return arci_forward(h->arci, q, d, N, Lq, Ld, pb, pc, scores, ws, h->d_err, s, dry);
+    case CAIR_MODEL_ARCII:
+      return arcii_forward(h->arcii, q, d, N, Lq, Ld, pb, pc, scores, ws, h->d_err, s, dry);
     case CAIR_MODEL_DUET:
       return duet_forward(h->duet, q, d, B, N, Lq, Ld, pb, pc, scores, ws, h->d_err, s, dry);
   }

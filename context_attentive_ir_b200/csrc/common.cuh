@@ -147,24 +147,77 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
 // ---- internal cross-file API -----------------------------------------------------------------
 namespace cair {
 
-enum Act { ACT_NONE = 0, ACT_TANH = 1 };
+enum Act { ACT_NONE = 0, ACT_TANH = 1, ACT_RELU = 2 };
 
 // A-row providers of the generic GEMM  C[M,N] = act(A[M,K] W[N,K]^T + bias).
 struct GemmA {
   const float* dense;   // row r at dense + r*lda (when table == nullptr)
   int64_t lda;
-  const float* table;   // gathered: row r = concat_{k<win} table[ids[seq*L + t + k]], r = seq*T + t
+  const float* table;   // gathered: row r = concat_{k<win} table[ids[seq*L + t + k - pad]], r = seq*T + t
   const int64_t* ids;
   int V, E, win, L, T;  // K must equal win*E
   int* err;
   int pool;             // dense only: row r = seq*T + t holds max_{k<win} dense[(seq*L + t + k)*lda + :]
-};                      // (max_pool1d(win, stride 1) over the time axis fused into the A load)
-inline GemmA gemm_dense(const float* a, int64_t lda) { return GemmA{a, lda, nullptr, nullptr, 0, 0, 0, 0, 0, nullptr, 0}; }
-inline GemmA gemm_gather(const float* table, int V, int E, const int64_t* ids, int win, int L, int T, int* err) {
-  return GemmA{nullptr, 0, table, ids, V, E, win, L, T, err, 0};
+                        // (max_pool1d(win, stride 1) over the time axis fused into the A load)
+  int pad;              // gathered / windowed: left zero padding in positions ("same" convolutions)
+  int dwin;             // dense windows (E = channels): 1 = 1-D window of `win` positions (im2col of a Conv1d over
+                        // [seq, L, E]), 2 = 3x3 window over a [seq, L/Wm, Wm, E] map (im2col of a Conv2d, pad 1)
+  int Wm;               // map width for dwin == 2
+};
+inline GemmA gemm_dense(const float* a, int64_t lda) { return GemmA{a, lda, nullptr, nullptr, 0, 0, 0, 0, 0, nullptr, 0, 0, 0, 0}; }
+inline GemmA gemm_gather(const float* table, int V, int E, const int64_t* ids, int win, int L, int T, int* err,
+                         int pad = 0) {
+  return GemmA{nullptr, 0, table, ids, V, E, win, L, T, err, 0, pad, 0, 0};
 }
 inline GemmA gemm_pooled(const float* a, int64_t lda, int win, int L, int T) {
-  return GemmA{a, lda, nullptr, nullptr, 0, 0, win, L, T, nullptr, 1};
+  return GemmA{a, lda, nullptr, nullptr, 0, 0, win, L, T, nullptr, 1, 0, 0, 0};
+}
+// same-padded Conv1d over a dense [seq, L, C] tensor: row (seq, t) = concat_{k<win} x[seq, t + k - win/2, :]
+inline GemmA gemm_window1d(const float* a, int C, int win, int L) {
+  return GemmA{a, C, nullptr, nullptr, 0, C, win, L, L, nullptr, 0, win / 2, 1, 0};
+}
+// 3x3 same-padded Conv2d over a dense NHWC map [seq, H, W, C]: row (seq, y, x) = concat_{ky,kx} x[seq, y+ky-1, x+kx-1, :]
+inline GemmA gemm_window2d(const float* a, int C, int H, int W) {
+  return GemmA{a, C, nullptr, nullptr, 0, C, 9, H * W, H * W, nullptr, 0, 1, 2, W};
+}
+
+// One 4-float slice A[r][kk..kk+3] (kk % 4 == 0, E % 4 == 0) for every provider; zeros outside the padding.
+__device__ __forceinline__ float4 gemm_a_load4(const GemmA& a, int64_t r, int kk) {
+  if (a.table) {
+    const int64_t seq = r / a.T;
+    const int t = (int)(r - seq * a.T);
+    const int seg = kk / a.E;
+    const int pos = t + seg - a.pad;
+    if (pos < 0 || pos >= a.L) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t id = checked_id(a.ids[seq * a.L + pos], a.V, a.err);
+    return *reinterpret_cast<const float4*>(a.table + id * a.E + (kk - seg * a.E));
+  }
+  if (a.dwin == 1) {
+    const int64_t seq = r / a.L;
+    const int t = (int)(r - seq * a.L);
+    const int seg = kk / a.E;
+    const int pos = t + seg - a.pad;
+    if (pos < 0 || pos >= a.L) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return *reinterpret_cast<const float4*>(a.dense + (seq * a.L + pos) * a.lda + (kk - seg * a.E));
+  }
+  if (a.dwin == 2) {
+    const int64_t seq = r / a.L;
+    const int p = (int)(r - seq * a.L);
+    const int y = p / a.Wm, x = p - y * a.Wm;
+    const int seg = kk / a.E;
+    const int yy = y + seg / 3 - 1, xx = x + seg % 3 - 1;
+    if (yy < 0 || yy >= a.L / a.Wm || xx < 0 || xx >= a.Wm) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return *reinterpret_cast<const float4*>(a.dense + (seq * a.L + yy * a.Wm + xx) * a.lda + (kk - seg * a.E));
+  }
+  if (!a.pool) return *reinterpret_cast<const float4*>(a.dense + r * a.lda + kk);
+  const int64_t seq = r / a.T;
+  const float* base = a.dense + (seq * a.L + (r - seq * a.T)) * a.lda + kk;
+  float4 m = *reinterpret_cast<const float4*>(base);
+  for (int k = 1; k < a.win; ++k) {
+    const float4 v = *reinterpret_cast<const float4*>(base + k * a.lda);
+    m.x = fmaxf(m.x, v.x), m.y = fmaxf(m.y, v.y), m.z = fmaxf(m.z, v.z), m.w = fmaxf(m.w, v.w);
+  }
+  return m;
 }
 int32_t gemm_f32(const GemmA& a, const float* w, const float* bias, float* c, int64_t ldc, int64_t M,
                  int N, int K, Act act, cudaStream_t s);

@@ -11,28 +11,34 @@ namespace cair {
 
 constexpr int BM = 64, BN = 64, BK = 16, PADT = 4;
 
-__device__ __forceinline__ const float* a_ptr(const GemmA& a, int64_t r, int kk) {
-  if (a.table == nullptr) return a.dense + r * a.lda + kk;
-  int64_t seq = r / a.T;
-  int t = (int)(r - seq * a.T);
-  int seg = kk / a.E;
-  int64_t id = checked_id(a.ids[seq * a.L + t + seg], a.V, a.err);
-  return a.table + id * a.E + (kk - seg * a.E);
-}
-__device__ __forceinline__ float4 a_load4(const GemmA& a, int64_t r, int kk) {
-  if (!a.pool) return *reinterpret_cast<const float4*>(a_ptr(a, r, kk));
-  int64_t seq = r / a.T;
-  const float* base = a.dense + (seq * a.L + (r - seq * a.T)) * a.lda + kk;
-  float4 m = *reinterpret_cast<const float4*>(base);
-  for (int k = 1; k < a.win; ++k) {
-    float4 v = *reinterpret_cast<const float4*>(base + k * a.lda);
-    m.x = fmaxf(m.x, v.x), m.y = fmaxf(m.y, v.y), m.z = fmaxf(m.z, v.z), m.w = fmaxf(m.w, v.w);
-  }
-  return m;
-}
+// scalar element for the non-vectorisable case (K or E not a multiple of 4): plain / gathered / pooled providers
 __device__ __forceinline__ float a_load1(const GemmA& a, int64_t r, int kk) {
-  if (!a.pool) return *a_ptr(a, r, kk);
-  int64_t seq = r / a.T;
+  if (a.table) {
+    const int64_t seq = r / a.T;
+    const int t = (int)(r - seq * a.T);
+    const int seg = kk / a.E;
+    const int pos = t + seg - a.pad;
+    if (pos < 0 || pos >= a.L) return 0.f;
+    return a.table[checked_id(a.ids[seq * a.L + pos], a.V, a.err) * a.E + (kk - seg * a.E)];
+  }
+  if (a.dwin == 1) {
+    const int64_t seq = r / a.L;
+    const int seg = kk / a.E;
+    const int pos = (int)(r - seq * a.L) + seg - a.pad;
+    if (pos < 0 || pos >= a.L) return 0.f;
+    return a.dense[(seq * a.L + pos) * a.lda + (kk - seg * a.E)];
+  }
+  if (a.dwin == 2) {
+    const int64_t seq = r / a.L;
+    const int p = (int)(r - seq * a.L);
+    const int y = p / a.Wm, x = p - y * a.Wm;
+    const int seg = kk / a.E;
+    const int yy = y + seg / 3 - 1, xx = x + seg % 3 - 1;
+    if (yy < 0 || yy >= a.L / a.Wm || xx < 0 || xx >= a.Wm) return 0.f;
+    return a.dense[(seq * a.L + yy * a.Wm + xx) * a.lda + (kk - seg * a.E)];
+  }
+  if (!a.pool) return a.dense[r * a.lda + kk];
+  const int64_t seq = r / a.T;
   const float* base = a.dense + (seq * a.L + (r - seq * a.T)) * a.lda + kk;
   float m = base[0];
   for (int k = 1; k < a.win; ++k) m = fmaxf(m, base[k * a.lda]);
@@ -64,7 +70,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmA a, const float* __r
     if (arow < M) {
       if (VEC) {
         if (kk < K) {
-          float4 v = a_load4(a, arow, kk);
+          float4 v = gemm_a_load4(a, arow, kk);
           av[0] = v.x, av[1] = v.y, av[2] = v.z, av[3] = v.w;
         }
       } else {
@@ -113,6 +119,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmA a, const float* __r
       if (col >= N) continue;
       float v = acc[i][j] + (bias ? bias[col] : 0.f);
       if (act == ACT_TANH) v = tanhf(v);
+      if (act == ACT_RELU) v = fmaxf(v, 0.f);
       c[r * ldc + col] = v;
     }
   }
@@ -121,10 +128,12 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmA a, const float* __r
 int32_t gemm_f32(const GemmA& a, const float* w, const float* bias, float* c, int64_t ldc, int64_t M, int N,
                  int K, Act act, cudaStream_t s) {
   if (M <= 0 || N <= 0 || K <= 0) return CAIR_OK;
-  if (a.table && K != a.win * a.E) return fail(CAIR_ERR_BAD_ARG, "gemm_f32: K != win*E");
+  if ((a.table || a.dwin) && K != a.win * a.E) return fail(CAIR_ERR_BAD_ARG, "gemm_f32: K != win*E");
   bool vec = (K % 4 == 0) && ((uintptr_t)w % 16 == 0);
   if (a.table)
     vec = vec && (a.E % 4 == 0) && ((uintptr_t)a.table % 16 == 0);
+  else if (a.dwin)
+    vec = vec && (a.E % 4 == 0) && (a.lda % 4 == 0) && ((uintptr_t)a.dense % 16 == 0);
   else
     vec = vec && (a.lda % 4 == 0) && ((uintptr_t)a.dense % 16 == 0);
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));

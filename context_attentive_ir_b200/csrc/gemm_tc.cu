@@ -69,26 +69,6 @@ __device__ __forceinline__ void gt_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// fp32 source pointer of A[r][kk..kk+3] (kk % 4 == 0), or nullptr when the provider needs the pooled path
-__device__ __forceinline__ float4 gt_load4(const GemmA& a, int64_t r, int kk) {
-  if (a.table) {
-    const int64_t seq = r / a.T;
-    const int t = (int)(r - seq * a.T);
-    const int seg = kk / a.E;
-    const int64_t id = checked_id(a.ids[seq * a.L + t + seg], a.V, a.err);
-    return *reinterpret_cast<const float4*>(a.table + id * a.E + (kk - seg * a.E));
-  }
-  if (!a.pool) return *reinterpret_cast<const float4*>(a.dense + r * a.lda + kk);
-  const int64_t seq = r / a.T;
-  const float* base = a.dense + (seq * a.L + (r - seq * a.T)) * a.lda + kk;
-  float4 m = *reinterpret_cast<const float4*>(base);
-  for (int k = 1; k < a.win; ++k) {
-    const float4 v = *reinterpret_cast<const float4*>(base + k * a.lda);
-    m.x = fmaxf(m.x, v.x), m.y = fmaxf(m.y, v.y), m.z = fmaxf(m.z, v.z), m.w = fmaxf(m.w, v.w);
-  }
-  return m;
-}
-
 // smem: A ring [stages][hi|lo] | W ring [stages][hi|lo]
 __global__ void __launch_bounds__(GT_THREADS, 1)
     gemm_tc_kernel(GemmA a, const uint8_t* __restrict__ wimg, const float* __restrict__ bias, float* __restrict__ c,
@@ -166,7 +146,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1)
 #pragma unroll
       for (int i = 0; i < GT_BK / 4; ++i) {
         const int kk = kc * GT_BK + i * 4;
-        v[i] = (rvalid && kk < K) ? gt_load4(a, r, kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = (rvalid && kk < K) ? gemm_a_load4(a, r, kk) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       uint8_t* ah = a_ring + (size_t)s * 2 * GT_AIMG;
 #pragma unroll
@@ -206,6 +186,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1)
           if (c0 + j < NT && col < N) {
             float x = v[j] + (bias ? bias[col] : 0.f);
             if (act == ACT_TANH) x = tanhf(x);
+            if (act == ACT_RELU) x = fmaxf(x, 0.f);
             crow[j] = x;
           }
         }
@@ -221,13 +202,14 @@ bool gemm_tc_usable(const GemmA& a, int K) {
   if (!g_gemm_impl) return false;
   if (K % 4) return false;
   if (a.table) return (a.E % 4 == 0) && ((uintptr_t)a.table % 16 == 0);
+  if (a.dwin) return (a.E % 4 == 0) && (a.lda % 4 == 0) && ((uintptr_t)a.dense % 16 == 0);
   return (a.lda % 4 == 0) && ((uintptr_t)a.dense % 16 == 0);
 }
 
 int32_t gemm_tc(const GemmA& a, const GemmTcW& w, const float* bias, float* c, int64_t ldc, int64_t M, Act act,
                 cudaStream_t s) {
   if (M <= 0) return CAIR_OK;
-  if (a.table && w.K != a.win * a.E) return fail(CAIR_ERR_BAD_ARG, "gemm_tc: K != win*E");
+  if ((a.table || a.dwin) && w.K != a.win * a.E) return fail(CAIR_ERR_BAD_ARG, "gemm_tc: K != win*E");
   const size_t smem = (size_t)GT_STAGES * 2 * GT_AIMG + (size_t)GT_STAGES * 2 * (GT_BK / 8) * w.NT * 16;
   uint32_t tcols = 32;
   while ((int)tcols < ((w.NT + 31) & ~31)) tcols <<= 1;

@@ -5,7 +5,7 @@
 namespace cair {
 
 enum { CAIR_MODEL_ESM = 1, CAIR_MODEL_MT = 2, CAIR_MODEL_DRMM = 3, CAIR_MODEL_DUET = 4, CAIR_MODEL_CARS = 5,
-       CAIR_MODEL_DSSM = 6, CAIR_MODEL_CDSSM = 7 };
+       CAIR_MODEL_DSSM = 6, CAIR_MODEL_CDSSM = 7, CAIR_MODEL_ARCI = 8, CAIR_MODEL_ARCII = 9 };
 
 int32_t embed_gather(const float* table, int V, int E, const int64_t* ids, int64_t T, float* out, int* err,
                      cudaStream_t s);
@@ -95,6 +95,32 @@ struct CdssmState {
 int32_t cdssm_create_state(Owned& own, const cair_cdssm_weights& w, CdssmState* st, cudaStream_t s);
 int32_t cdssm_forward(const CdssmState& st, const int64_t* q, const int64_t* d, int N, int Lq, int Ld, int64_t pb,
                       int64_t pc, float* scores, Arena& ws, int* err, cudaStream_t s, bool dry);
+
+// ---- ARC-I / ARC-II ----
+struct ArciState {
+  int V = 0, E = 0, nl = 0, Lq = 0, Ld = 0, Lqo = 0, Ldo = 0, hid = 0;
+  int F[CAIR_ARC_MAX_LAYERS] = {0}, k[CAIR_ARC_MAX_LAYERS] = {0}, P[CAIR_ARC_MAX_LAYERS] = {0};
+  float* table = nullptr;
+  float *qw[CAIR_ARC_MAX_LAYERS] = {nullptr}, *qb[CAIR_ARC_MAX_LAYERS] = {nullptr};  // [F][k*C] tap-major
+  float *dw[CAIR_ARC_MAX_LAYERS] = {nullptr}, *db[CAIR_ARC_MAX_LAYERS] = {nullptr};
+  GemmTcW qtc[CAIR_ARC_MAX_LAYERS], dtc[CAIR_ARC_MAX_LAYERS], mdtc;
+  float *mq = nullptr, *md = nullptr, *b0 = nullptr, *w1 = nullptr, *b1 = nullptr;  // mlp.0 split (query | doc), columns permuted
+};
+int32_t arci_create_state(Owned& own, const cair_arci_weights& w, ArciState* st, cudaStream_t s);
+int32_t arci_forward(const ArciState& st, const int64_t* q, const int64_t* d, int N, int Lq, int Ld, int64_t pb, int64_t pc,
+                     float* scores, Arena& ws, int* err, cudaStream_t s, bool dry);
+struct ArciiState {
+  int V = 0, E = 0, F1 = 0, k1 = 0, nl = 0, Lq = 0, Ld = 0, Hf = 0, Wf = 0, Cf = 0, hid = 0;
+  int F2[CAIR_ARC_MAX_LAYERS] = {0};
+  float* table = nullptr;
+  float *cqw = nullptr, *cqb = nullptr, *cdw = nullptr, *cdb = nullptr;
+  float *w2[CAIR_ARC_MAX_LAYERS] = {nullptr}, *b2[CAIR_ARC_MAX_LAYERS] = {nullptr};  // [F][(ky*3+kx)*C + c]
+  GemmTcW cqtc, cdtc, tc2[CAIR_ARC_MAX_LAYERS], m0tc;
+  float *m0 = nullptr, *b0 = nullptr, *w1 = nullptr, *b1 = nullptr;
+};
+int32_t arcii_create_state(Owned& own, const cair_arcii_weights& w, ArciiState* st, cudaStream_t s);
+int32_t arcii_forward(const ArciiState& st, const int64_t* q, const int64_t* d, int N, int Lq, int Ld, int64_t pb, int64_t pc,
+                      float* scores, Arena& ws, int* err, cudaStream_t s, bool dry);
 
 // ---- DUET ----
 struct DuetState {

@@ -8,7 +8,7 @@ def install():
     """Call once before neuroir.models.Ranker / Multitask are instantiated.  Returns the list of rebound names."""
     done = []
     import neuroir.models.ranker as ref_ranker
-    for name, cls in (('DSSM', rankers.DSSM), ('CDSSM', rankers.CDSSM), ('ESM', rankers.ESM), ('MatchTensor', rankers.MatchTensor), ('DRMM', rankers.DRMM),
+    for name, cls in (('ARCI', rankers.ARCI), ('ARCII', rankers.ARCII), ('DSSM', rankers.DSSM), ('CDSSM', rankers.CDSSM), ('ESM', rankers.ESM), ('MatchTensor', rankers.MatchTensor), ('DRMM', rankers.DRMM),
                       ('DUET', rankers.DUET)):
         setattr(ref_ranker, name, cls)
         done.append('neuroir.models.ranker.' + name)

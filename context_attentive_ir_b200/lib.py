@@ -38,6 +38,8 @@ PROTOTYPES = {
     'cair_drmm_set_debug': (i32, [vp, vp]),
     'cair_dssm_create': (i32, [C.POINTER(_abi.DssmWeights), i32, C.POINTER(vp)]),
     'cair_cdssm_create': (i32, [C.POINTER(_abi.CdssmWeights), i32, C.POINTER(vp)]),
+    'cair_arci_create': (i32, [C.POINTER(_abi.ArciWeights), i32, C.POINTER(vp)]),
+    'cair_arcii_create': (i32, [C.POINTER(_abi.ArciiWeights), i32, C.POINTER(vp)]),
     'cair_duet_create': (i32, [C.POINTER(_abi.DuetWeights), i32, C.POINTER(vp)]),
     'cair_ranker_workspace_bytes': (i32, [vp, i32, i32, i32, i32, C.POINTER(C.c_size_t)]),
     'cair_ranker_forward': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, vp, vp, C.c_size_t, vp]),

@@ -262,6 +262,79 @@ class CDSSM(_Ranker):
         return lib.load().cair_cdssm_create(w, device, out)
 
 
+class ARCI(_Ranker):
+    """neuroir/rankers/arci.py:7-105."""
+    MODEL = 'arci'
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.word_embeddings = Embeddings(args.emsize, args.src_vocab_size, PAD)
+        self.emb_drop = nn.Dropout(p=args.dropout_emb)
+        nl = len(args.filters_1d)
+        assert nl == len(args.kernel_size_1d) == len(args.maxpool_size_1d)
+        qf, df = args.max_query_len, args.max_doc_len
+        ql, dl = [], []
+        for i in range(nl):
+            inp = args.emsize if i == 0 else args.filters_1d[i - 1]
+            for lst in (ql, dl):
+                lst.append(nn.Sequential(nn.Conv1d(inp, args.filters_1d[i], args.kernel_size_1d[i],
+                                                   padding=args.kernel_size_1d[i] // 2),
+                                         nn.ReLU(inplace=True), nn.MaxPool1d(args.maxpool_size_1d[i])))
+            df, qf = df // args.maxpool_size_1d[i], qf // args.maxpool_size_1d[i]
+            assert qf != 0 and df != 0
+        self.query_conv1d_layers, self.doc_conv1d_layers = nn.ModuleList(ql), nn.ModuleList(dl)
+        inp = args.filters_1d[-1] * (qf + df)
+        self.mlp = nn.Sequential(nn.Linear(inp, inp // 2), nn.Linear(inp // 2, 1))
+
+    def _cfg(self):
+        a = self.args
+        return dict(src_vocab_size=a.src_vocab_size, emsize=a.emsize, filters_1d=list(a.filters_1d),
+                    kernel_size_1d=list(a.kernel_size_1d), maxpool_size_1d=list(a.maxpool_size_1d),
+                    max_query_len=a.max_query_len, max_doc_len=a.max_doc_len)
+
+    def _create(self, w, device, out):
+        return lib.load().cair_arci_create(w, device, out)
+
+
+class ARCII(_Ranker):
+    """neuroir/rankers/arcii.py:7-111."""
+    MODEL = 'arcii'
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.word_embeddings = Embeddings(args.emsize, args.src_vocab_size, PAD)
+        self.emb_drop = nn.Dropout(p=args.dropout_emb)
+        self.conv_query = nn.Conv1d(args.emsize, args.filters_1d, args.kernel_size_1d, padding=args.kernel_size_1d // 2)
+        self.conv_doc = nn.Conv1d(args.emsize, args.filters_1d, args.kernel_size_1d, padding=args.kernel_size_1d // 2)
+        self.maxpool1 = nn.MaxPool2d((2, 2))
+        nl = len(args.kernel_size_2d)
+        assert nl == len(args.maxpool_size_2d)
+        df, qf = args.max_doc_len // 2, args.max_query_len // 2
+        layers = []
+        for i in range(nl):
+            inp = args.filters_1d if i == 0 else args.filters_2d[i - 1]
+            ks, mp = args.kernel_size_2d[i], args.maxpool_size_2d[i]
+            layers.append(nn.Sequential(nn.Conv2d(inp, args.filters_2d[i], tuple(ks), padding=(ks[0] // 2, ks[1] // 2)),
+                                        nn.ReLU(inplace=True), nn.MaxPool2d((mp[0], mp[1]))))
+            df, qf = df // mp[0], qf // mp[1]
+            assert qf != 0 and df != 0
+        self.conv2d_layers = nn.ModuleList(layers)
+        inp = args.filters_2d[-1] * qf * df
+        self.mlp = nn.Sequential(nn.Linear(inp, inp // 2), nn.Linear(inp // 2, 1))
+
+    def _cfg(self):
+        a = self.args
+        return dict(src_vocab_size=a.src_vocab_size, emsize=a.emsize, filters_1d=a.filters_1d, kernel_size_1d=a.kernel_size_1d,
+                    filters_2d=list(a.filters_2d), kernel_size_2d=[list(k) for k in a.kernel_size_2d],
+                    maxpool_size_2d=[list(k) for k in a.maxpool_size_2d], max_query_len=a.max_query_len,
+                    max_doc_len=a.max_doc_len)
+
+    def _create(self, w, device, out):
+        return lib.load().cair_arcii_create(w, device, out)
+
+
 class ExactMatchChannel(nn.Module):
     """neuroir/rankers/mtensor.py:134-142: one learnable scalar, U(0,1) init."""
 
@@ -402,4 +475,4 @@ class DUET(_Ranker):
         return lib.load().cair_duet_create(w, device, out)
 
 
-RANKERS = {'DSSM': DSSM, 'CDSSM': CDSSM, 'ESM': ESM, 'MATCH_TENSOR': MatchTensor, 'DRMM': DRMM, 'DUET': DUET}
+RANKERS = {'ARCI': ARCI, 'ARCII': ARCII, 'DSSM': DSSM, 'CDSSM': CDSSM, 'ESM': ESM, 'MATCH_TENSOR': MatchTensor, 'DRMM': DRMM, 'DUET': DUET}

@@ -220,6 +220,31 @@ typedef struct {
 } cair_cdssm_weights;
 CAIR_API int32_t cair_cdssm_create(const cair_cdssm_weights* w, int32_t device, cair_handle** out);
 
+/* ---- ARC-I (neuroir/rankers/arci.py:10-58 ctor, :60-105 forward) ------------------------------------------- */
+#define CAIR_ARC_MAX_LAYERS 4
+typedef struct {
+  int32_t vocab, emsize, nlayers;                 /* nlayers = len(filters_1d) <= CAIR_ARC_MAX_LAYERS */
+  int32_t filters[CAIR_ARC_MAX_LAYERS], kernel[CAIR_ARC_MAX_LAYERS], pool[CAIR_ARC_MAX_LAYERS];
+  int32_t max_query_len, max_doc_len;
+  const float* table;
+  cair_linear qconv[CAIR_ARC_MAX_LAYERS];         /* query_conv1d_layers.<i>.0 : [F_i, C_i, k_i] */
+  cair_linear dconv[CAIR_ARC_MAX_LAYERS];         /* doc_conv1d_layers.<i>.0 */
+  cair_linear mlp0, mlp1;                         /* mlp.0 [inp/2, inp], mlp.1 [1, inp/2] */
+} cair_arci_weights;
+CAIR_API int32_t cair_arci_create(const cair_arci_weights* w, int32_t device, cair_handle** out);
+
+/* ---- ARC-II (neuroir/rankers/arcii.py:10-56 ctor, :58-111 forward); 2-D kernels 3x3, max-pools 2x2 ---------- */
+typedef struct {
+  int32_t vocab, emsize, filters_1d, kernel_1d, nlayers2d;
+  int32_t filters_2d[CAIR_ARC_MAX_LAYERS];
+  int32_t max_query_len, max_doc_len;
+  const float* table;
+  cair_linear conv_query, conv_doc;               /* [F1, E, k1] */
+  cair_linear conv2d[CAIR_ARC_MAX_LAYERS];        /* conv2d_layers.<i>.0 : [F2_i, C_i, 3, 3] */
+  cair_linear mlp0, mlp1;
+} cair_arcii_weights;
+CAIR_API int32_t cair_arcii_create(const cair_arcii_weights* w, int32_t device, cair_handle** out);
+
 /* ---- forward for the stand-alone rankers ---------------------------------------------
  * network(queries, que_len, documents, doc_len) (neuroir/models/ranker.py:213,257):
  * q [B,Lq], qlen [B], d [B,N,Ld], dlen [B,N] int64 -> scores [B,N] fp32 (no softmax).

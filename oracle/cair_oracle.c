@@ -761,3 +761,197 @@ ORA_API int cair_oracle_cdssm(const cair_cdssm_weights* w, const int64_t* q, con
   }
   return CAIR_OK;
 }
+
+/* ---- ARC-I (rankers/arci.py:60-105) -----------------------------------------------------------------------
+ * per side: [Conv1d(same padding k/2) -> ReLU -> MaxPool1d(pool)] x nlayers over the embedded tokens, flatten(1) of the
+ * [C, L'] maps, concat(query, doc), Linear(inp, inp/2) -> Linear(inp/2, 1) (no non-linearity between them). */
+static int arc_conv_stack(const float* x0, int L, int Cin, int nl, const int32_t* filters, const int32_t* kernel,
+                          const int32_t* pool, const cair_linear* convs, float** out, int* Lout) {
+  float* cur = (float*)malloc(sizeof(float) * (size_t)L * Cin);  /* [L][C] */
+  memcpy(cur, x0, sizeof(float) * (size_t)L * Cin);
+  for (int l = 0; l < nl; ++l) {
+    int F = filters[l], k = kernel[l], pad = k / 2, P = pool[l], Lp = L / P;
+    float* y = (float*)malloc(sizeof(float) * (size_t)L * F);
+    for (int t = 0; t < L; ++t)
+      for (int f = 0; f < F; ++f) {
+        double s = convs[l].b[f];
+        for (int kk = 0; kk < k; ++kk) {
+          int tt = t + kk - pad;
+          if (tt < 0 || tt >= L) continue;
+          for (int c = 0; c < Cin; ++c) s += (double)convs[l].w[((size_t)f * Cin + c) * k + kk] * (double)cur[(size_t)tt * Cin + c];
+        }
+        y[(size_t)t * F + f] = (float)s > 0.f ? (float)s : 0.f;
+      }
+    float* z = (float*)malloc(sizeof(float) * (size_t)(Lp > 0 ? Lp : 1) * F);
+    for (int t = 0; t < Lp; ++t)
+      for (int f = 0; f < F; ++f) {
+        float m = -INFINITY;
+        for (int u = 0; u < P; ++u) m = fmaxf(m, y[(size_t)(t * P + u) * F + f]);
+        z[(size_t)t * F + f] = m;
+      }
+    free(cur);
+    free(y);
+    cur = z, L = Lp, Cin = F;
+    if (L <= 0) {
+      free(cur);
+      return CAIR_ERR_BAD_SHAPE;
+    }
+  }
+  *out = cur, *Lout = L;
+  return CAIR_OK;
+}
+
+ORA_API int cair_oracle_arci(const cair_arci_weights* w, const int64_t* q, const int64_t* qlen, const int64_t* d,
+                             const int64_t* dlen, int B, int N, int Lq, int Ld, float* scores) {
+  (void)qlen;
+  (void)dlen;
+  if (Lq != w->max_query_len || Ld != w->max_doc_len) return CAIR_ERR_BAD_SHAPE; /* mlp in-features are baked in (:46-57) */
+  int E = w->emsize, nl = w->nlayers, Fl = w->filters[nl - 1];
+  if (!check_ids(q, (int64_t)B * Lq, w->vocab) || !check_ids(d, (int64_t)B * N * Ld, w->vocab)) return CAIR_ERR_BAD_ARG;
+  int rc_all = CAIR_OK;
+#pragma omp parallel for
+  for (int b = 0; b < B; ++b) {
+    float* xq = (float*)malloc(sizeof(float) * (size_t)Lq * E);
+    cair_oracle_embed(w->table, w->vocab, E, q + (size_t)b * Lq, Lq, xq);
+    float* fq = NULL;
+    int Lqo = 0;
+    int rc = arc_conv_stack(xq, Lq, E, nl, w->filters, w->kernel, w->pool, w->qconv, &fq, &Lqo);
+    free(xq);
+    if (rc != CAIR_OK) {
+      rc_all = rc;
+      continue;
+    }
+    for (int n = 0; n < N; ++n) {
+      float* xd = (float*)malloc(sizeof(float) * (size_t)Ld * E);
+      cair_oracle_embed(w->table, w->vocab, E, d + ((size_t)b * N + n) * Ld, Ld, xd);
+      float* fd = NULL;
+      int Ldo = 0;
+      rc = arc_conv_stack(xd, Ld, E, nl, w->filters, w->kernel, w->pool, w->dconv, &fd, &Ldo);
+      free(xd);
+      if (rc != CAIR_OK) {
+        rc_all = rc;
+        continue;
+      }
+      int inp = Fl * (Lqo + Ldo), hid = inp / 2;
+      /* flatten(1) of [C, L'] maps: index c*L' + l; query block first */
+      float* com = (float*)malloc(sizeof(float) * (size_t)inp);
+      for (int c = 0; c < Fl; ++c) {
+        for (int l = 0; l < Lqo; ++l) com[c * Lqo + l] = fq[(size_t)l * Fl + c];
+        for (int l = 0; l < Ldo; ++l) com[Fl * Lqo + c * Ldo + l] = fd[(size_t)l * Fl + c];
+      }
+      double sc = w->mlp1.b[0];
+      for (int o = 0; o < hid; ++o)
+        sc += (double)w->mlp1.w[o] * (double)(dotf(com, w->mlp0.w + (size_t)o * inp, inp) + w->mlp0.b[o]);
+      scores[b * N + n] = (float)sc;
+      free(com);
+      free(fd);
+    }
+    free(fq);
+  }
+  return rc_all;
+}
+
+/* ---- ARC-II (rankers/arcii.py:58-111) --------------------------------------------------------------------
+ * Conv1d(same) on both sides (no activation), comb[f,j,i] = cd[f,j] + cq[f,i] (a SUM, :99), MaxPool2d(2,2), then
+ * [Conv2d(3x3, same) -> ReLU -> MaxPool2d(2,2)] x nlayers over the (doc, query) map, flatten(1), two Linear layers. */
+ORA_API int cair_oracle_arcii(const cair_arcii_weights* w, const int64_t* q, const int64_t* qlen, const int64_t* d,
+                              const int64_t* dlen, int B, int N, int Lq, int Ld, float* scores) {
+  (void)qlen;
+  (void)dlen;
+  if (Lq != w->max_query_len || Ld != w->max_doc_len) return CAIR_ERR_BAD_SHAPE;
+  int E = w->emsize, F1 = w->filters_1d, k1 = w->kernel_1d, pad1 = k1 / 2, nl = w->nlayers2d;
+  if (!check_ids(q, (int64_t)B * Lq, w->vocab) || !check_ids(d, (int64_t)B * N * Ld, w->vocab)) return CAIR_ERR_BAD_ARG;
+  int64_t BN = (int64_t)B * N;
+  int rc_all = CAIR_OK;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t p = 0; p < BN; ++p) {
+    int b = (int)(p / N);
+    /* 1-D convs: cq [Lq][F1], cd [Ld][F1] */
+    float* cq = (float*)malloc(sizeof(float) * (size_t)(Lq + Ld) * F1);
+    float* cd = cq + (size_t)Lq * F1;
+    for (int side = 0; side < 2; ++side) {
+      const int64_t* ids = side ? d + p * Ld : q + (size_t)b * Lq;
+      int L = side ? Ld : Lq;
+      const cair_linear* cv = side ? &w->conv_doc : &w->conv_query;
+      float* o = side ? cd : cq;
+      for (int t = 0; t < L; ++t)
+        for (int f = 0; f < F1; ++f) {
+          double s = cv->b[f];
+          for (int kk = 0; kk < k1; ++kk) {
+            int tt = t + kk - pad1;
+            if (tt < 0 || tt >= L) continue;
+            const float* x = w->table + ids[tt] * E;
+            for (int e = 0; e < E; ++e) s += (double)cv->w[((size_t)f * E + e) * k1 + kk] * (double)x[e];
+          }
+          o[(size_t)t * F1 + f] = (float)s;
+        }
+    }
+    /* sum + first 2x2 max-pool: map [H][W][C], H = Ld/2 (docs), W = Lq/2 (query) */
+    int H = Ld / 2, W = Lq / 2, C = F1;
+    float* cur = (float*)malloc(sizeof(float) * (size_t)H * W * C);
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x)
+        for (int c = 0; c < C; ++c) {
+          float m = -INFINITY;
+          for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx)
+              m = fmaxf(m, cd[(size_t)(2 * y + dy) * F1 + c] + cq[(size_t)(2 * x + dx) * F1 + c]);
+          cur[((size_t)y * W + x) * C + c] = m;
+        }
+    free(cq);
+    int bad = 0;
+    for (int l = 0; l < nl && !bad; ++l) {
+      int F = w->filters_2d[l];
+      float* yv = (float*)malloc(sizeof(float) * (size_t)H * W * F);
+      for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x)
+          for (int f = 0; f < F; ++f) {
+            double s = w->conv2d[l].b[f];
+            for (int ky = 0; ky < 3; ++ky)
+              for (int kx = 0; kx < 3; ++kx) {
+                int yy = y + ky - 1, xx = x + kx - 1;
+                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                const float* src = cur + ((size_t)yy * W + xx) * C;
+                const float* wr = w->conv2d[l].w + (size_t)f * C * 9 + ky * 3 + kx;
+                for (int c = 0; c < C; ++c) s += (double)wr[(size_t)c * 9] * (double)src[c];
+              }
+            yv[((size_t)y * W + x) * F + f] = (float)s > 0.f ? (float)s : 0.f;
+          }
+      int H2 = H / 2, W2 = W / 2;
+      if (H2 <= 0 || W2 <= 0) {
+        bad = 1;
+        free(yv);
+        break;
+      }
+      float* z = (float*)malloc(sizeof(float) * (size_t)H2 * W2 * F);
+      for (int y = 0; y < H2; ++y)
+        for (int x = 0; x < W2; ++x)
+          for (int f = 0; f < F; ++f) {
+            float m = -INFINITY;
+            for (int dy = 0; dy < 2; ++dy)
+              for (int dx = 0; dx < 2; ++dx) m = fmaxf(m, yv[((size_t)(2 * y + dy) * W + 2 * x + dx) * F + f]);
+            z[((size_t)y * W2 + x) * F + f] = m;
+          }
+      free(yv);
+      free(cur);
+      cur = z, H = H2, W = W2, C = F;
+    }
+    if (bad) {
+      rc_all = CAIR_ERR_BAD_SHAPE;
+      free(cur);
+      continue;
+    }
+    int inp = C * H * W, hid = inp / 2;
+    float* com = (float*)malloc(sizeof(float) * (size_t)inp); /* flatten(1) of [C, H, W] */
+    for (int c = 0; c < C; ++c)
+      for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) com[((size_t)c * H + y) * W + x] = cur[((size_t)y * W + x) * C + c];
+    double sc = w->mlp1.b[0];
+    for (int o = 0; o < hid; ++o)
+      sc += (double)w->mlp1.w[o] * (double)(dotf(com, w->mlp0.w + (size_t)o * inp, inp) + w->mlp0.b[o]);
+    scores[p] = (float)sc;
+    free(com);
+    free(cur);
+  }
+  return rc_all;
+}

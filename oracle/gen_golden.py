@@ -137,6 +137,23 @@ def gen_dssm(name, seed, B, N, Lq, Ld, E, V, nhid, nout, conv=False, **kw):
     _save(name, cfg, batch, net, dict(scores=s))
 
 
+# ------------------------------------------------------------------ ARC-I / ARC-II
+def gen_arc(name, seed, B, N, Lq, Ld, E, V, two, **arch):
+    if two:
+        from neuroir.rankers.arcii import ARCII as Net
+    else:
+        from neuroir.rankers.arci import ARCI as Net
+    torch.manual_seed(1013)
+    cfg = dict(model='arcii' if two else 'arci', emsize=E, src_vocab_size=V, dropout_emb=0.2, max_query_len=Lq,
+               max_doc_len=Ld, **arch)
+    net = Net(_ns(**{k: v for k, v in cfg.items() if k != 'model'})).eval()
+    batch = synth.ranker_batch(seed, B, N, Lq, Ld, V, bos_eos=True)
+    t = _t(batch)
+    with torch.no_grad():
+        s = net(t['q'], t['qlen'], t['d'], t['dlen'])
+    _save(name, cfg, batch, net, dict(scores=s))
+
+
 # ------------------------------------------------------------------ Match-Tensor
 def gen_mt(name, seed, B, N, Lq, Ld, E, V, F, Hq, Hd, C, nf, mfs, **kw):
     from neuroir.rankers.mtensor import MatchTensor
@@ -223,7 +240,7 @@ def main():
     only = sys.argv[1:]  # optional: fixture-name prefixes to (re)generate
     if only:
         g = globals()
-        for fn in ('gen_esm', 'gen_mt', 'gen_drmm', 'gen_duet', 'gen_cars', 'gen_dssm'):
+        for fn in ('gen_esm', 'gen_mt', 'gen_drmm', 'gen_duet', 'gen_cars', 'gen_dssm', 'gen_arc'):
             g[fn] = (lambda f: (lambda name, *a, **k: f(name, *a, **k) if any(name.startswith(o) for o in only) else None))(g[fn])
     # BASELINE configs[0]: the reference's own CPU-runnable case (vocab cut 10k -> 1k to keep the file small)
     gen_esm('esm_cfg1', 1235, B=8, N=5, Lq=10, Ld=50, E=64, V=1000)
@@ -245,6 +262,15 @@ def main():
     gen_dssm('dssm_e300', 1240, B=3, N=4, Lq=20, Ld=200, E=300, V=400, nhid=300, nout=128, bos_eos=True)
     gen_dssm('cdssm_tiny', 62, B=2, N=3, Lq=7, Ld=21, E=24, V=120, nhid=16, nout=8, conv=True)
     gen_dssm('cdssm_e300', 1241, B=2, N=3, Lq=20, Ld=200, E=300, V=400, nhid=96, nout=64, conv=True, bos_eos=True)
+    # ARC-I / ARC-II (force_pad shapes; stock layer structure at reduced widths to keep the fixtures small)
+    gen_arc('arci_tiny', 71, B=2, N=3, Lq=8, Ld=30, E=16, V=100, two=False, filters_1d=[12, 8], kernel_size_1d=[3, 3],
+            maxpool_size_1d=[2, 2])
+    gen_arc('arci_mid', 1242, B=2, N=3, Lq=20, Ld=200, E=300, V=300, two=False, filters_1d=[32, 16], kernel_size_1d=[3, 3],
+            maxpool_size_1d=[2, 2])
+    gen_arc('arcii_tiny', 72, B=2, N=3, Lq=8, Ld=24, E=16, V=100, two=True, filters_1d=8, kernel_size_1d=3,
+            filters_2d=[12, 8], kernel_size_2d=[[3, 3], [3, 3]], maxpool_size_2d=[[2, 2], [2, 2]])
+    gen_arc('arcii_mid', 1243, B=2, N=3, Lq=10, Ld=100, E=300, V=300, two=True, filters_1d=32, kernel_size_1d=3,
+            filters_2d=[48, 32], kernel_size_2d=[[3, 3], [3, 3]], maxpool_size_2d=[[2, 2], [2, 2]])
     # DUET (force_pad shapes: every batch padded to max lens, lengths still variable)
     gen_duet('duet_tiny', 41, B=2, N=3, Lq=8, Ld=30, E=24, V=120, nf=16, overlap=0.2)
     gen_duet('duet_e300', 1239, B=2, N=3, Lq=20, Ld=200, E=300, V=400, nf=64, bos_eos=True, overlap=0.1)

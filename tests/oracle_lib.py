@@ -85,7 +85,7 @@ def run_ranker(cfg, sd, q, qlen, d, dlen, want=()):
         _check(L.cair_oracle_drmm(C.byref(w), qp, qlp, dp, dlp, B, N, Lq, Ld, _f32(scores),
                                   hist.ctypes.data_as(_abi.i32p) if hist is not None else None, _f32(cos)), 'drmm')
         out.update(hist=hist, cos=cos)
-    elif model in ('dssm', 'cdssm'):
+    elif model in ('dssm', 'cdssm', 'arci', 'arcii'):
         fn = getattr(L, 'cair_oracle_' + model)
         _check(fn(C.byref(w), qp, qlp, dp, dlp, B, N, Lq, Ld, _f32(scores)), model)
     elif model == 'duet':

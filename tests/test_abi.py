@@ -41,7 +41,7 @@ def test_no_compute_without_gpu_fails_loudly():
 
 
 @pytest.mark.parametrize('name', ['esm_cfg1', 'mt_cfg2arch', 'mt_stock', 'drmm_strict', 'duet_e300', 'cars_mid', 'dssm_e300',
-                                  'cdssm_tiny'])
+                                  'cdssm_tiny', 'arci_mid', 'arcii_mid'])
 def test_state_dict_keys_and_shapes_match_reference(name):
     cfg, _, sd, _ = ol.load_golden(name)
     net = helpers.build_module(cfg)

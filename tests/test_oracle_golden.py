@@ -106,3 +106,10 @@ def test_cdssm_rejects_too_short_sequences():
     cfg, ins, sd, outs = ol.load_golden('cdssm_tiny')
     with pytest.raises(RuntimeError, match='BAD_SHAPE'):
         ol.run_ranker(cfg, sd, ins['q'][:, :4], ins['qlen'], ins['d'], ins['dlen'])
+
+
+@pytest.mark.parametrize('name', ['arci_tiny', 'arci_mid', 'arcii_tiny', 'arcii_mid'])
+def test_arc(name):
+    cfg, ins, sd, outs = ol.load_golden(name)
+    o = ol.run_ranker(cfg, sd, ins['q'], ins['qlen'], ins['d'], ins['dlen'])
+    assert _max_rel(o['scores'], outs['scores']) < 1e-4

@@ -164,6 +164,12 @@ def test_dssm_cdssm_golden(name):
     assert _max_rel(s, outs['scores']) < TOL
 
 
+@pytest.mark.parametrize('name', ['arci_tiny', 'arci_mid', 'arcii_tiny', 'arcii_mid'])
+def test_arc_golden(name, gemm_engine):
+    *_, outs, net, s = _run(name)
+    assert _max_rel(s, outs['scores']) < TOL
+
+
 def test_duet_rejects_unpadded_batches():
     cfg, ins, sd, outs = ol.load_golden('duet_tiny')
     net = helpers.build_module(cfg, sd, DEV)
