@@ -189,7 +189,7 @@ int32_t cair_esm_create(const cair_esm_weights* w, int32_t device, cair_handle**
 
 int32_t cair_mt_create(const cair_mt_weights* w, int32_t device, cair_handle** out) {
   if (!w || !w->table) return fail(CAIR_ERR_BAD_ARG, "mt_create: bad weights");
-  if (w->rnn_type != CAIR_RNN_LSTM) return fail(CAIR_ERR_UNSUPPORTED, "mt_create: only rnn_type LSTM is implemented");
+  if (w->rnn_type != CAIR_RNN_LSTM && w->rnn_type != CAIR_RNN_GRU) return fail(CAIR_ERR_UNSUPPORTED, "mt_create: rnn_type must be LSTM or GRU");
   int dirs = w->bidirectional ? 2 : 1;
   if (w->nhid_query % dirs || w->nhid_doc % dirs) return fail(CAIR_ERR_BAD_SHAPE, "mt_create: hidden size not divisible by directions");
   cair_handle* h = nullptr;

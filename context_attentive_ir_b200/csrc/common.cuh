@@ -242,13 +242,15 @@ inline int32_t gemm_auto(const GemmA& a, const float* w, const GemmTcW& tw, cons
 // LSTM weights repacked for the recurrent kernel.
 struct LstmPack {
   int in, h, dirs;
+  int gates = 4;    // 4: LSTM (i,f,g,o), 3: GRU (r,z,n)
+  float* b_hn = nullptr;  // [dirs][h] GRU only: hidden bias of the candidate gate (stays inside r * (...))
   float* w_ih;    // [dirs*4h, in]  (fwd rows then rev rows): the pre-gate GEMM's W
   float* bias;    // [dirs*4h]      b_ih + b_hh
   float* w_hh_t;  // [dirs][h][4h]  k-major recurrent weights
   GemmTcW w_ih_tc;  // tensor-core image of w_ih (pre-gate GEMM)
 };
 int32_t lstm_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, int in, int h, LstmPack* out,
-                  cudaStream_t s);
+                  cudaStream_t s, int rnn_type = CAIR_RNN_LSTM);
 size_t lstm_workspace_floats(const LstmPack& p, int64_t n, int L);
 // pre-gates GEMM (optionally gathering rows from `table`) + recurrence; out [n,L,dirs*h], zeros at t>=len.
 int32_t lstm_run(const LstmPack& p, const GemmA& x, const int64_t* len, int n, int L, float* out, float* h_n,

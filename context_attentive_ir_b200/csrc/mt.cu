@@ -273,11 +273,12 @@ int32_t mt_create_state(Owned& own, const cair_mt_weights& w, MtState* st, cudaS
   CAIR_CUDA(own.alloc(&st->folded, (size_t)w.vocab * w.featsize));
   CAIR_TRY(gemm_f32(gemm_dense(w.table, w.emsize), w.linear_projection.w, w.linear_projection.b, st->folded,
                     w.featsize, w.vocab, w.featsize, w.emsize, ACT_NONE, s));
-  CAIR_TRY(lstm_pack(own, &w.query_fwd, dirs == 2 ? &w.query_rev : nullptr, w.featsize, w.nhid_query / dirs, &st->enc_q, s));
-  CAIR_TRY(lstm_pack(own, &w.doc_fwd, dirs == 2 ? &w.doc_rev : nullptr, w.featsize, w.nhid_doc / dirs, &st->enc_d, s));
-  if (lstm_tc_supported(w.featsize, w.nhid_query / dirs))
+  CAIR_TRY(lstm_pack(own, &w.query_fwd, dirs == 2 ? &w.query_rev : nullptr, w.featsize, w.nhid_query / dirs, &st->enc_q, s, w.rnn_type));
+  CAIR_TRY(lstm_pack(own, &w.doc_fwd, dirs == 2 ? &w.doc_rev : nullptr, w.featsize, w.nhid_doc / dirs, &st->enc_d, s, w.rnn_type));
+  const bool lstm = w.rnn_type == CAIR_RNN_LSTM;  // the tensor-core recurrence implements the LSTM cell; GRU runs on the fp32 kernel
+  if (lstm && lstm_tc_supported(w.featsize, w.nhid_query / dirs))
     CAIR_TRY(lstm_tc_pack(own, &w.query_fwd, dirs == 2 ? &w.query_rev : nullptr, w.featsize, w.nhid_query / dirs, &st->tc_q, s));
-  if (lstm_tc_supported(w.featsize, w.nhid_doc / dirs))
+  if (lstm && lstm_tc_supported(w.featsize, w.nhid_doc / dirs))
     CAIR_TRY(lstm_tc_pack(own, &w.doc_fwd, dirs == 2 ? &w.doc_rev : nullptr, w.featsize, w.nhid_doc / dirs, &st->tc_d, s));
   CAIR_TRY(dev_copy(own, w.query_projection.w, (size_t)w.nchannels * w.nhid_query, &st->wq, s));
   CAIR_TRY(dev_copy(own, w.query_projection.b, (size_t)w.nchannels, &st->bq, s));

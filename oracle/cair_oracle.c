@@ -68,13 +68,35 @@ static void lstm_step(const float* x, int in, int h, const cair_lstm_dir* w, flo
   for (int u = 0; u < h; ++u) hs[u] = sigmoidf_(gates[3 * h + u]) * tanhf(cs[u]);
 }
 
+/* One GRU cell step, torch.nn.GRU semantics (gate rows r,z,n; n = tanh(W_in x + b_in + r * (W_hn h + b_hn))). */
+static void gru_step(const float* x, int in, int h, const cair_lstm_dir* w, float* hs, float* gates) {
+  for (int u = 0; u < h; ++u) {
+    float ar = dotf(x, w->w_ih + (int64_t)u * in, in) + w->b_ih[u] + dotf(hs, w->w_hh + (int64_t)u * h, h) + w->b_hh[u];
+    float az = dotf(x, w->w_ih + (int64_t)(h + u) * in, in) + w->b_ih[h + u] + dotf(hs, w->w_hh + (int64_t)(h + u) * h, h) + w->b_hh[h + u];
+    float xn = dotf(x, w->w_ih + (int64_t)(2 * h + u) * in, in) + w->b_ih[2 * h + u];
+    float hn = dotf(hs, w->w_hh + (int64_t)(2 * h + u) * h, h) + w->b_hh[2 * h + u];
+    float r = sigmoidf_(ar), z = sigmoidf_(az);
+    float nn = tanhf(xn + r * hn);
+    gates[u] = (1.0f - z) * nn + z * hs[u];
+  }
+  memcpy(hs, gates, sizeof(float) * h);
+}
+
 /* RNNEncoder.forward with lengths (encoders/rnn_encoder.py:62-141), one LSTM layer.
  * sort/pack/unpack/unsort is a per-sequence no-op: each sequence runs over its own
  * len steps, the reverse direction starts at its own last token, outputs at t >= len are
  * zero (the zero-pad of :135-139 and pad_packed_sequence). */
+static int oracle_rnn(int rnn_type, const float* x, const int64_t* len, int n, int L, int in, int h,
+                      const cair_lstm_dir* fwd, const cair_lstm_dir* rev, float* out, float* h_n, float* c_n);
+
 ORA_API int cair_oracle_lstm(const float* x, const int64_t* len, int n, int L, int in, int h,
                              const cair_lstm_dir* fwd, const cair_lstm_dir* rev, float* out,
                              float* h_n, float* c_n) {
+  return oracle_rnn(CAIR_RNN_LSTM, x, len, n, L, in, h, fwd, rev, out, h_n, c_n);
+}
+
+static int oracle_rnn(int rnn_type, const float* x, const int64_t* len, int n, int L, int in, int h,
+                      const cair_lstm_dir* fwd, const cair_lstm_dir* rev, float* out, float* h_n, float* c_n) {
   int dirs = rev ? 2 : 1;
   for (int s = 0; s < n; ++s)
     if (len[s] < 1 || len[s] > L) return CAIR_ERR_BAD_ARG;
@@ -89,7 +111,10 @@ ORA_API int cair_oracle_lstm(const float* x, const int64_t* len, int n, int L, i
       memset(hs, 0, sizeof(float) * 2 * h);
       for (int k = 0; k < T; ++k) {
         int t = dir ? T - 1 - k : k;
-        lstm_step(x + ((int64_t)s * L + t) * in, in, h, w, hs, cs, gates);
+        if (rnn_type == CAIR_RNN_GRU)
+          gru_step(x + ((int64_t)s * L + t) * in, in, h, w, hs, gates);
+        else
+          lstm_step(x + ((int64_t)s * L + t) * in, in, h, w, hs, cs, gates);
         memcpy(out + ((int64_t)s * L + t) * dirs * h + dir * h, hs, sizeof(float) * h);
       }
       if (h_n) memcpy(h_n + ((int64_t)dir * n + s) * h, hs, sizeof(float) * h);
@@ -149,7 +174,7 @@ ORA_API int cair_oracle_esm(const cair_esm_weights* w, const int64_t* q, const i
 ORA_API int cair_oracle_mt(const cair_mt_weights* w, const int64_t* q, const int64_t* qlen,
                            const int64_t* d, const int64_t* dlen, int B, int N, int Lq, int Ld,
                            float* scores, float* enc_q_out, float* enc_d_out) {
-  if (w->rnn_type != CAIR_RNN_LSTM) return CAIR_ERR_UNSUPPORTED;
+  if (w->rnn_type != CAIR_RNN_LSTM && w->rnn_type != CAIR_RNN_GRU) return CAIR_ERR_UNSUPPORTED;
   int E = w->emsize, F = w->featsize, C = w->nchannels, nf = w->nfilters,
       M = w->match_filter_size;
   int dirs = w->bidirectional ? 2 : 1;
@@ -171,11 +196,11 @@ ORA_API int cair_oracle_mt(const cair_mt_weights* w, const int64_t* q, const int
   /* :93-94 separate query / document encoders */
   float* hq_ = (float*)malloc(sizeof(float) * B * Lq * Hq);
   float* hd_ = (float*)malloc(sizeof(float) * BN * Ld * Hd);
-  int rc = cair_oracle_lstm(pq, qlen, B, Lq, F, hq, &w->query_fwd,
-                            dirs == 2 ? &w->query_rev : NULL, hq_, NULL, NULL);
+  int rc = oracle_rnn(w->rnn_type, pq, qlen, B, Lq, F, hq, &w->query_fwd,
+                      dirs == 2 ? &w->query_rev : NULL, hq_, NULL, NULL);
   if (rc == CAIR_OK)
-    rc = cair_oracle_lstm(pd, dlen, (int)BN, Ld, F, hd, &w->doc_fwd,
-                          dirs == 2 ? &w->doc_rev : NULL, hd_, NULL, NULL);
+    rc = oracle_rnn(w->rnn_type, pd, dlen, (int)BN, Ld, F, hd, &w->doc_fwd,
+                    dirs == 2 ? &w->doc_rev : NULL, hd_, NULL, NULL);
   free(pq);
   free(pd);
   if (rc != CAIR_OK) {

@@ -155,10 +155,10 @@ def gen_arc(name, seed, B, N, Lq, Ld, E, V, two, **arch):
 
 
 # ------------------------------------------------------------------ Match-Tensor
-def gen_mt(name, seed, B, N, Lq, Ld, E, V, F, Hq, Hd, C, nf, mfs, **kw):
+def gen_mt(name, seed, B, N, Lq, Ld, E, V, F, Hq, Hd, C, nf, mfs, rnn_type='LSTM', **kw):
     from neuroir.rankers.mtensor import MatchTensor
     torch.manual_seed(1013)
-    cfg = dict(model='match_tensor', emsize=E, src_vocab_size=V, dropout_emb=0.2, rnn_type='LSTM',
+    cfg = dict(model='match_tensor', emsize=E, src_vocab_size=V, dropout_emb=0.2, rnn_type=rnn_type,
                bidirection=True, nlayers=1, dropout_rnn=0.2, featsize=F, nhid_query=Hq,
                nhid_doc=Hd, nchannels=C, nfilters=nf, match_filter_size=mfs)
     net = MatchTensor(_ns(**{k: v for k, v in cfg.items() if k != 'model'})).eval()
@@ -254,6 +254,8 @@ def main():
            mfs=20, bos_eos=True)
     gen_mt('mt_fullpad', 24, B=2, N=2, Lq=12, Ld=40, E=48, V=200, F=16, Hq=32, Hd=32, C=18, nf=6,
            mfs=20, variable=False)
+    gen_mt('mt_gru', 25, B=2, N=3, Lq=9, Ld=31, E=32, V=150, F=12, Hq=20, Hd=28, C=10, nf=6, mfs=8, rnn_type='GRU',
+           bos_eos=True, overlap=0.15)
     # DRMM: strict (disjoint ids) and overlapping (bin-edge cells excluded by the test using out/cos)
     gen_drmm('drmm_strict', 1237, B=3, N=4, Lq=20, Ld=200, E=300, V=400, disjoint=True)
     gen_drmm('drmm_overlap', 32, B=2, N=3, Lq=12, Ld=60, E=64, V=300, bos_eos=True, overlap=0.1)
