@@ -163,7 +163,8 @@ constexpr int DQ_NV = 3;    // float4 column groups per lane (E/4 <= 96)
 constexpr int DQ_PF = 2;    // prefetch depth (tokens)
 
 __device__ __forceinline__ float4 dq_ld(const float* row, int c4, int E4) {
-  return c4 < E4 ? ldg_stream(reinterpret_cast<const float4*>(row) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  // cached read-only path: the 4 query-group warps of a stream read the same row, 3 of them hit L1
+  return c4 < E4 ? __ldg(reinterpret_cast<const float4*>(row) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 __device__ __forceinline__ float dq_dot(const float4& a, const float4& b, float acc) {
   acc = fmaf(a.x, b.x, acc);
