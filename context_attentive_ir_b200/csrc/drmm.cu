@@ -149,181 +149,12 @@ __global__ void __launch_bounds__(DR_THREADS) drmm_kernel(const float* __restric
     for (int i = tid; i < Lq * 5; i += DR_THREADS) hist_out[p * Lq * 5 + i] = hist[i];
 }
 
-// ---- register-resident variant (E % 4 == 0, E <= 384, Lq <= 20): the fast path for the stock shapes ----
-// Each warp keeps its slice of 5 normalised query rows in REGISTERS (lane <-> three 128-bit column groups), so the
-// hot loop touches no shared memory: per document token the warp streams the embedding row straight from global
-// memory (3 x LDG.128 per lane, two tokens prefetched), computes its norm and 5 dot products, reduces the partial
-// sums with a butterfly transpose (each value lands on a fixed lane, which keeps that row's five bin counters in
-// registers), and bins.  8 warps = 4 query groups x 2 token streams; <= 128 registers so two CTAs share an SM and
-// 32 rows are in flight per SM to cover the HBM latency.
-constexpr int DQ_RH = 5;    // query rows per warp
-constexpr int DQ_QG = 4;    // query groups (DQ_RH * DQ_QG >= Lq)
-constexpr int DQ_NS = 2;    // token streams per CTA
-constexpr int DQ_NV = 3;    // float4 column groups per lane (E/4 <= 96)
-constexpr int DQ_PF = 2;    // prefetch depth (tokens)
-
-__device__ __forceinline__ float4 dq_ld(const float* row, int c4, int E4) {
-  // cached read-only path: the 4 query-group warps of a stream read the same row, 3 of them hit L1
-  return c4 < E4 ? __ldg(reinterpret_cast<const float4*>(row) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-}
-__device__ __forceinline__ float dq_dot(const float4& a, const float4& b, float acc) {
-  acc = fmaf(a.x, b.x, acc);
-  acc = fmaf(a.y, b.y, acc);
-  acc = fmaf(a.z, b.z, acc);
-  return fmaf(a.w, b.w, acc);
-}
-
-__global__ void __launch_bounds__(DR_THREADS, 2) drmm_reg_kernel(const float* __restrict__ table, int V, int E,
-                                                                 const int64_t* __restrict__ q, const int64_t* __restrict__ d,
-                                                                 int N, int Lq, int Ld, int64_t pair_begin,
-                                                                 const float* __restrict__ wg, const float* __restrict__ bg,
-                                                                 const float* __restrict__ w0, const float* __restrict__ b0,
-                                                                 const float* __restrict__ w1, const float* __restrict__ b1,
-                                                                 const float* __restrict__ wo, const float* __restrict__ bo,
-                                                                 float* __restrict__ scores, int32_t* __restrict__ hist_out,
-                                                                 int* err) {
-  __shared__ float gate[DR_MAXLQ];
-  __shared__ int hist[DR_MAXLQ * 5];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int grp = warp % DQ_QG, stream = warp / DQ_QG;   // query rows [5*grp, 5*grp+5); tokens stream, stream+2, ...
-  const int64_t p = pair_begin + blockIdx.x;
-  const int64_t b = p / N;
-  const int E4 = E >> 2;
-  for (int i = tid; i < DR_MAXLQ * 5; i += DR_THREADS) hist[i] = 0;
-  // ---- this warp's query rows: gather, (gate logit on the raw row), normalise by max(||x||, eps), keep in registers ----
-  float4 qr[DQ_RH][DQ_NV];
-#pragma unroll
-  for (int r = 0; r < DQ_RH; ++r) {
-    const int i = grp * DQ_RH + r;
-    float ss = 0.f, gl = 0.f;
-    if (i < Lq) {
-      const float* src = table + checked_id(q[b * Lq + i], V, err) * E;
-#pragma unroll
-      for (int v = 0; v < DQ_NV; ++v) {
-        const int c4 = lane + 32 * v;
-        qr[r][v] = dq_ld(src, c4, E4);
-        ss = dq_dot(qr[r][v], qr[r][v], ss);
-        if (c4 < E4) gl = dq_dot(qr[r][v], *reinterpret_cast<const float4*>(wg + 4 * c4), gl);
-      }
-    } else {
-#pragma unroll
-      for (int v = 0; v < DQ_NV; ++v) qr[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    ss = warp_sum(ss);
-    gl = warp_sum(gl);
-    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-8f);
-#pragma unroll
-    for (int v = 0; v < DQ_NV; ++v) qr[r][v].x *= inv, qr[r][v].y *= inv, qr[r][v].z *= inv, qr[r][v].w *= inv;
-    if (stream == 0 && lane == 0 && i < Lq) gate[i] = gl + bg[0];
-  }
-  __syncthreads();
-  // After the butterfly, lane L holds the 32-lane total of value index (L >> 2) & 7 -> a fixed query row per lane.
-  const int myv = (lane >> 2) & 7;
-  const bool owner = (lane & 3) == 0 && myv < DQ_RH && grp * DQ_RH + myv < Lq;
-  int cnt[5] = {0, 0, 0, 0, 0};
-  // ---- stream the document tokens, DQ_PF rows in flight ----
-  float4 nx[DQ_PF][DQ_NV];
-#pragma unroll
-  for (int f = 0; f < DQ_PF; ++f) {
-    const int j = stream + DQ_NS * f;
-    const float* src = j < Ld ? table + checked_id(d[p * Ld + j], V, err) * E : table;
-#pragma unroll
-    for (int v = 0; v < DQ_NV; ++v) nx[f][v] = dq_ld(src, lane + 32 * v, j < Ld ? E4 : 0);
-  }
-  for (int j = stream; j < Ld; j += DQ_NS) {
-    float4 dv[DQ_NV];
-#pragma unroll
-    for (int v = 0; v < DQ_NV; ++v) dv[v] = nx[0][v];
-#pragma unroll
-    for (int f = 0; f + 1 < DQ_PF; ++f)
-#pragma unroll
-      for (int v = 0; v < DQ_NV; ++v) nx[f][v] = nx[f + 1][v];
-    {  // refill the prefetch queue
-      const int jn = j + DQ_NS * DQ_PF;
-      const float* src = jn < Ld ? table + checked_id(d[p * Ld + jn], V, err) * E : table;
-#pragma unroll
-      for (int v = 0; v < DQ_NV; ++v) nx[DQ_PF - 1][v] = dq_ld(src, lane + 32 * v, jn < Ld ? E4 : 0);
-    }
-    float ss = 0.f;
-#pragma unroll
-    for (int v = 0; v < DQ_NV; ++v) ss = dq_dot(dv[v], dv[v], ss);
-    float val[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      float a = 0.f;
-      if (r < DQ_RH) {
-#pragma unroll
-        for (int v = 0; v < DQ_NV; ++v) a = dq_dot(qr[r][v], dv[v], a);
-      }
-      val[r] = a;
-    }
-    ss = warp_sum(ss);
-    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-8f);
-    // butterfly transpose-reduce: 8 values over 32 lanes in 4+2+1 exchange shuffles + 2 plain ones
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool up = lane & 16;
-      const float send = up ? val[k] : val[k + 4], keep = up ? val[k + 4] : val[k];
-      val[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const bool up = lane & 8;
-      const float send = up ? val[k] : val[k + 2], keep = up ? val[k + 2] : val[k];
-      val[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    {
-      const bool up = lane & 4;
-      const float send = up ? val[0] : val[1], keep = up ? val[1] : val[0];
-      val[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    val[0] += __shfl_xor_sync(0xffffffffu, val[0], 2);
-    val[0] += __shfl_xor_sync(0xffffffffu, val[0], 1);
-    if (owner) {
-      const int bin = drmm_bin(val[0] * inv);   // the query rows are already normalised
-#pragma unroll
-      for (int k = 0; k < 5; ++k) cnt[k] += (bin == k);
-    }
-  }
-  if (owner) {
-    const int i = grp * DQ_RH + myv;
-#pragma unroll
-    for (int k = 0; k < 5; ++k)
-      if (cnt[k]) atomicAdd(&hist[i * 5 + k], cnt[k]);
-  }
-  __syncthreads();
-  // ---- epilogue: softmax gate over ALL Lq positions, ffnn(5->1->1), weighted sum, output ----
-  if (warp == 0) {
-    float g = (lane < Lq) ? gate[lane] : -INFINITY;
-    float mx = warp_max(g);
-    float ex = (lane < Lq) ? __expf(g - mx) : 0.f;
-    float den = warp_sum(ex);
-    float f = 0.f;
-    if (lane < Lq) {
-      float f0 = b0[0];
-#pragma unroll
-      for (int k = 0; k < 5; ++k) f0 = fmaf(w0[k], (float)hist[lane * 5 + k], f0);
-      f = (w1[0] * f0 + b1[0]) * (ex / den);
-    }
-    f = warp_sum(f);
-    if (lane == 0) scores[p] = wo[0] * f + bo[0];
-  }
-  if (hist_out)
-    for (int i = tid; i < Lq * 5; i += DR_THREADS) hist_out[p * Lq * 5 + i] = hist[i];
-}
-
 int32_t drmm_forward(const cair_drmm_weights& w, const int64_t* q, const int64_t* d, int N, int Lq, int Ld,
                      int64_t pair_begin, int64_t pair_count, float* scores, int32_t* hist_out, int* err,
                      cudaStream_t s) {
   if (pair_count <= 0) return CAIR_OK;
   if (Lq > DR_MAXLQ) return fail(CAIR_ERR_UNSUPPORTED, "drmm: max_query_len %d > %d", Lq, DR_MAXLQ);
   const int E = w.emsize;
-  if ((E & 3) == 0 && E / 4 <= 32 * DQ_NV && Lq <= DQ_QG * DQ_RH && ((uintptr_t)w.table & 15) == 0 && ((uintptr_t)w.gating.w & 15) == 0) {
-    CAIR_LAUNCH(drmm_reg_kernel, (unsigned)pair_count, DR_THREADS, 0, s, w.table, w.vocab, E, q, d, N, Lq, Ld, pair_begin,
-                w.gating.w, w.gating.b, w.ffnn0.w, w.ffnn0.b, w.ffnn1.w, w.ffnn1.b, w.output.w, w.output.b, scores,
-                hist_out, err);
-    return CAIR_OK;
-  }
   int ES = (E + 3) & ~3;
   if (((ES / 4) & 1) == 0) ES += 4;  // odd number of 16-byte groups per row: conflict-free LDS.128
   size_t smem = ((size_t)(Lq + DR_CHUNK) * ES + DR_MAXLQ) * sizeof(float) + (size_t)Lq * 5 * sizeof(int);
