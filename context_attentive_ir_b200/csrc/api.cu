@@ -45,6 +45,20 @@ struct cair_handle {
   size_t stage_dev_bytes = 0;
   void* ws = nullptr;
   size_t ws_bytes = 0;
+  // host path as one CUDA graph (H2D + kernels + D2H), re-captured when the call signature changes
+  struct HostKey {
+    const void *q = nullptr, *ql = nullptr, *d = nullptr, *dl = nullptr, *scores = nullptr, *stage = nullptr, *ws = nullptr;
+    int B = 0, N = 0, Lq = 0, Ld = 0, impl = -1;
+    bool operator==(const HostKey& o) const {
+      return q == o.q && ql == o.ql && d == o.d && dl == o.dl && scores == o.scores && stage == o.stage && ws == o.ws &&
+             B == o.B && N == o.N && Lq == o.Lq && Ld == o.Ld && impl == o.impl;
+    }
+  } host_key;
+  int host_key_hits = 0;
+  cudaGraphExec_t host_graph = nullptr;
+  cudaStream_t host_stream = nullptr;
+  cudaEvent_t host_ev = nullptr;
+  int* host_err = nullptr;  // pinned
 };
 
 namespace {
@@ -116,6 +130,10 @@ int32_t cair_destroy(cair_handle* h) {
   if (h->mt.ev_join) cudaEventDestroy(h->mt.ev_join);
   if (h->stage_dev) cudaFree(h->stage_dev);
   if (h->ws) cudaFree(h->ws);
+  if (h->host_graph) cudaGraphExecDestroy(h->host_graph);
+  if (h->host_stream) cudaStreamDestroy(h->host_stream);
+  if (h->host_ev) cudaEventDestroy(h->host_ev);
+  if (h->host_err) cudaFreeHost(h->host_err);
   delete h;
   return CAIR_OK;
 }
@@ -466,13 +484,68 @@ int32_t cair_ranker_forward_host(cair_handle* h, const int64_t* q, const int64_t
   int64_t* dd = dql + nb;
   int64_t* ddl = dd + nd;
   float* ds = (float*)((char*)h->stage_dev + align_up(in_bytes));
-  CAIR_CUDA(cudaMemcpyAsync(dq, q, nq * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-  CAIR_CUDA(cudaMemcpyAsync(dql, qlen, nb * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-  CAIR_CUDA(cudaMemcpyAsync(dd, d, nd * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-  CAIR_CUDA(cudaMemcpyAsync(ddl, dlen, nbn * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-  CAIR_TRY(cair_ranker_forward(h, dq, dql, dd, ddl, B, N, Lq, Ld, 0, (int64_t)nbn, ds, h->ws, h->ws_bytes, stream));
-  CAIR_CUDA(cudaMemcpyAsync(scores, ds, nbn * sizeof(float), cudaMemcpyDeviceToHost, s));
-  return cair_poll_error(h, stream);  // synchronises the stream
+  if (!h->host_stream) {
+    CAIR_CUDA(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+    CAIR_CUDA(cudaEventCreateWithFlags(&h->host_ev, cudaEventDisableTiming));
+    CAIR_CUDA(cudaHostAlloc((void**)&h->host_err, sizeof(int), cudaHostAllocDefault));
+  }
+  // The whole call runs on the handle's own stream, ordered after the work already queued on `stream`
+  // (the legacy default stream cannot be captured); the call returns after a host synchronisation.
+  cudaStream_t hs = h->host_stream;
+  CAIR_CUDA(cudaEventRecord(h->host_ev, s));
+  CAIR_CUDA(cudaStreamWaitEvent(hs, h->host_ev, 0));
+  auto enqueue = [&]() -> int32_t {
+    CAIR_CUDA(cudaMemcpyAsync(dq, q, nq * sizeof(int64_t), cudaMemcpyHostToDevice, hs));
+    CAIR_CUDA(cudaMemcpyAsync(dql, qlen, nb * sizeof(int64_t), cudaMemcpyHostToDevice, hs));
+    CAIR_CUDA(cudaMemcpyAsync(dd, d, nd * sizeof(int64_t), cudaMemcpyHostToDevice, hs));
+    CAIR_CUDA(cudaMemcpyAsync(ddl, dlen, nbn * sizeof(int64_t), cudaMemcpyHostToDevice, hs));
+    CAIR_TRY(cair_ranker_forward(h, dq, dql, dd, ddl, B, N, Lq, Ld, 0, (int64_t)nbn, ds, h->ws, h->ws_bytes, hs));
+    CAIR_CUDA(cudaMemcpyAsync(scores, ds, nbn * sizeof(float), cudaMemcpyDeviceToHost, hs));
+    CAIR_CUDA(cudaMemcpyAsync(h->host_err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, hs));
+    return CAIR_OK;
+  };
+  cair_handle::HostKey key;
+  key.q = q, key.ql = qlen, key.d = d, key.dl = dlen, key.scores = scores, key.stage = h->stage_dev, key.ws = h->ws;
+  key.B = B, key.N = N, key.Lq = Lq, key.Ld = Ld, key.impl = h->mt.impl * 2 + g_gemm_impl;
+  const bool same = key == h->host_key;
+  if (same && h->host_graph && !h->prof.on) {
+    CAIR_CUDA(cudaGraphLaunch(h->host_graph, hs));
+  } else if (same && !h->prof.on && h->host_key_hits >= 1) {
+    // second call with this signature: capture H2D + kernels + D2H once, replay from now on
+    if (h->host_graph) cudaGraphExecDestroy(h->host_graph);
+    h->host_graph = nullptr;
+    cudaGraph_t graph = nullptr;
+    CAIR_CUDA(cudaStreamBeginCapture(hs, cudaStreamCaptureModeThreadLocal));
+    int32_t rc = enqueue();
+    cudaError_t ce = cudaStreamEndCapture(hs, &graph);
+    if (rc != CAIR_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (ce != cudaSuccess) return fail(CAIR_ERR_CUDA, "forward_host: graph capture failed: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&h->host_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return fail(CAIR_ERR_CUDA, "forward_host: graph instantiate failed: %s", cudaGetErrorString(ce));
+    CAIR_CUDA(cudaGraphLaunch(h->host_graph, hs));
+  } else {
+    if (!same) {
+      if (h->host_graph) cudaGraphExecDestroy(h->host_graph);
+      h->host_graph = nullptr;
+      h->host_key = key;
+      h->host_key_hits = 0;
+    }
+    h->host_key_hits++;
+    CAIR_TRY(enqueue());
+  }
+  CAIR_CUDA(cudaStreamSynchronize(hs));
+  if (*h->host_err) {
+    const int flags = *h->host_err;
+    CAIR_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int), hs));
+    CAIR_CUDA(cudaStreamSynchronize(hs));
+    if (flags & ERRF_BAD_TOKEN) return fail(CAIR_ERR_BAD_ARG, "token id outside [0, vocab)");
+    return fail(CAIR_ERR_BAD_ARG, "sequence length outside [1, padded length]");
+  }
+  return CAIR_OK;
 }
 
 // ---- CARS ----------------------------------------------------------------------------------------

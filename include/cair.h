@@ -20,7 +20,10 @@
  *    (size from cair_<model>_workspace_bytes).
  *  - *_forward_host: all pointers are HOST pointers (pinned memory recommended); the call
  *    copies ids/lengths host->device, runs the same kernels, copies the scores back and
- *    synchronises `stream` before returning.  Staging buffers live in the handle.
+ *    returns after a host synchronisation.  The work runs on a stream owned by the handle,
+ *    ordered after everything already queued on `stream`; from the second call with the same
+ *    buffers and shapes on, the whole sequence is replayed as ONE captured CUDA graph.
+ *    Staging buffers live in the handle.
  *  - weights structs hold DEVICE pointers in the torch state_dict layouts (SURVEY.md
  *    App. D); cair_<model>_create repacks/converts them once into the handle; the caller
  *    may free or modify its tensors afterwards (call create again to pick up new values).

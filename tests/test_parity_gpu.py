@@ -277,8 +277,12 @@ def test_match_tensor_full_cfg2_properties():
     assert (sub - s[:5]).abs().max().item() <= 1e-5 * scale
     assert torch.equal((a + b), s)
     # (4) end-to-end host entry point returns the same scores
-    hs = net.forward_host(*[torch.from_numpy(batch[k]).pin_memory() for k in ('q', 'qlen', 'd', 'dlen')])
-    assert torch.equal(hs, s.cpu())
+    host = [torch.from_numpy(batch[k]).pin_memory() for k in ('q', 'qlen', 'd', 'dlen')]
+    out = torch.empty(B, N, dtype=torch.float32).pin_memory()
+    for _ in range(4):  # 1st call eager, 2nd captures the CUDA graph, later calls replay it
+        out.zero_()
+        hs = net.forward_host(*host, out=out)
+        assert torch.equal(hs, s.cpu())
     # (5) the spot-checked oracle agrees on a few pairs of the big batch
     idx = [0, 57, 127]
     ref = ol.run_ranker(cfg, helpers.state_dict_numpy(net), batch['q'][idx], batch['qlen'][idx], batch['d'][idx],
