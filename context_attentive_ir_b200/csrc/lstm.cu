@@ -14,7 +14,6 @@
 
 namespace cair {
 
-constexpr int TS = 8;            // sequences per CTA
 constexpr int REC_THREADS = 256;
 
 __global__ void lstm_pack_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
@@ -63,7 +62,9 @@ int32_t lstm_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* rev
 size_t lstm_workspace_floats(const LstmPack& p, int64_t n, int L) { return (size_t)n * L * p.dirs * p.gates * p.h; }
 
 // smem: [W_hh^T: h*G floats if WSMEM] [hprev: TS*hp] [c (LSTM) | pre_n (GRU): TS*h] [gates: TS*G] ; hp = h rounded up to 4
-template <bool WSMEM, bool GRU>
+// TS = sequences per CTA: 8 when W_hh^T is resident in shared memory, 16 when it is streamed from L2 every step
+// (halves the L2 traffic of the big hidden sizes, e.g. CARS h = 128 per direction).
+template <bool WSMEM, bool GRU, int TS>
 __global__ void __launch_bounds__(REC_THREADS) rnn_rec_kernel(const float* __restrict__ pre, const float* __restrict__ w_hh_t,
                                                               const float* __restrict__ b_hn_all,
                                                               const int64_t* __restrict__ len, int n, int L, int h, int dirs,
@@ -193,13 +194,13 @@ __global__ void __launch_bounds__(REC_THREADS) rnn_rec_kernel(const float* __res
     }
 }
 
-template <bool WSMEM, bool GRU>
+template <bool WSMEM, bool GRU, int TS>
 static int32_t launch_rec(const LstmPack& p, const float* pre, const int64_t* len, int n, int L, float* out, float* h_n,
                           float* c_n, int* err, size_t smem, cudaStream_t s) {
   if (smem > 48 * 1024)
-    CAIR_CUDA(cudaFuncSetAttribute(rnn_rec_kernel<WSMEM, GRU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CAIR_CUDA(cudaFuncSetAttribute(rnn_rec_kernel<WSMEM, GRU, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((n + TS - 1) / TS, p.dirs);
-  CAIR_LAUNCH((rnn_rec_kernel<WSMEM, GRU>), grid, REC_THREADS, smem, s, pre, p.w_hh_t, p.b_hn, len, n, L, p.h, p.dirs, out,
+  CAIR_LAUNCH((rnn_rec_kernel<WSMEM, GRU, TS>), grid, REC_THREADS, smem, s, pre, p.w_hh_t, p.b_hn, len, n, L, p.h, p.dirs, out,
               h_n, c_n, err);
   return CAIR_OK;
 }
@@ -211,15 +212,16 @@ int32_t lstm_run(const LstmPack& p, const GemmA& x, const int64_t* len, int n, i
   CAIR_TRY(gemm_auto(x, p.w_ih, p.w_ih_tc, p.bias, ws_pre, PG, (int64_t)n * L, PG, p.in, ACT_NONE, s));
   if (rec_name) prof_mark(rec_name, s);
   const int hp = (p.h + 3) & ~3;
-  const size_t state = (size_t)(TS * hp + TS * p.h + TS * G) * sizeof(float);
   const size_t wbytes = (size_t)p.h * G * sizeof(float);
-  const bool wsmem = wbytes + state <= 200 * 1024;
-  const size_t smem = state + (wsmem ? wbytes : 0);
+  const size_t state8 = (size_t)(8 * hp + 8 * p.h + 8 * G) * sizeof(float);
+  const size_t state16 = 2 * state8;
+  const bool wsmem = wbytes + state8 <= 200 * 1024;
   const bool gru = p.gates == 3;
-  if (wsmem) return gru ? launch_rec<true, true>(p, ws_pre, len, n, L, out, h_n, c_n, err, smem, s)
-                        : launch_rec<true, false>(p, ws_pre, len, n, L, out, h_n, c_n, err, smem, s);
-  return gru ? launch_rec<false, true>(p, ws_pre, len, n, L, out, h_n, c_n, err, smem, s)
-             : launch_rec<false, false>(p, ws_pre, len, n, L, out, h_n, c_n, err, smem, s);
+  if (wsmem)
+    return gru ? launch_rec<true, true, 8>(p, ws_pre, len, n, L, out, h_n, c_n, err, state8 + wbytes, s)
+               : launch_rec<true, false, 8>(p, ws_pre, len, n, L, out, h_n, c_n, err, state8 + wbytes, s);
+  return gru ? launch_rec<false, true, 16>(p, ws_pre, len, n, L, out, h_n, c_n, err, state16, s)
+             : launch_rec<false, false, 16>(p, ws_pre, len, n, L, out, h_n, c_n, err, state16, s);
 }
 
 }  // namespace cair
