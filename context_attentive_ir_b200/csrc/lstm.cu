@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(REC_THREADS) rnn_rec_kernel(const float* __res
 template <bool WSMEM, bool GRU, int TS>
 static int32_t launch_rec(const LstmPack& p, const float* pre, const int64_t* len, int n, int L, float* out, float* h_n,
                           float* c_n, int* err, size_t smem, cudaStream_t s) {
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)  // static smem counts against the 48 KB default limit too
     CAIR_CUDA(cudaFuncSetAttribute(rnn_rec_kernel<WSMEM, GRU, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((n + TS - 1) / TS, p.dirs);
   CAIR_LAUNCH((rnn_rec_kernel<WSMEM, GRU, TS>), grid, REC_THREADS, smem, s, pre, p.w_hh_t, p.b_hn, len, n, L, p.h, p.dirs, out,
