@@ -62,8 +62,7 @@ int32_t lstm_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* rev
 size_t lstm_workspace_floats(const LstmPack& p, int64_t n, int L) { return (size_t)n * L * p.dirs * p.gates * p.h; }
 
 // smem: [W_hh^T: h*G floats if WSMEM] [hprev: TS*hp] [c (LSTM) | pre_n (GRU): TS*h] [gates: TS*G] ; hp = h rounded up to 4
-// TS = sequences per CTA: 8 when W_hh^T is resident in shared memory, 16 when it is streamed from L2 every step
-// (halves the L2 traffic of the big hidden sizes, e.g. CARS h = 128 per direction).
+// TS = sequences per CTA.
 template <bool WSMEM, bool GRU, int TS>
 __global__ void __launch_bounds__(REC_THREADS) rnn_rec_kernel(const float* __restrict__ pre, const float* __restrict__ w_hh_t,
                                                               const float* __restrict__ b_hn_all,
@@ -140,7 +139,8 @@ __global__ void __launch_bounds__(REC_THREADS) rnn_rec_kernel(const float* __res
         acc[s] = v;
       }
       int k = 0;
-      for (; k + 4 <= h; k += 4) {
+#pragma unroll 4
+      for (; k + 4 <= h; k += 4) {  // partially unrolled: 16 independent weight loads in flight when W is streamed from L2
         float w0 = W[(size_t)(k + 0) * G + r], w1 = W[(size_t)(k + 1) * G + r];
         float w2 = W[(size_t)(k + 2) * G + r], w3 = W[(size_t)(k + 3) * G + r];
 #pragma unroll
@@ -220,8 +220,9 @@ int32_t lstm_run(const LstmPack& p, const GemmA& x, const int64_t* len, int n, i
   if (wsmem)
     return gru ? launch_rec<true, true, 8>(p, ws_pre, len, n, L, out, h_n, c_n, err, state8 + wbytes, s)
                : launch_rec<true, false, 8>(p, ws_pre, len, n, L, out, h_n, c_n, err, state8 + wbytes, s);
-  return gru ? launch_rec<false, true, 16>(p, ws_pre, len, n, L, out, h_n, c_n, err, state16, s)
-             : launch_rec<false, false, 16>(p, ws_pre, len, n, L, out, h_n, c_n, err, state16, s);
+  (void)state16;  // TS = 16 measured slower (fewer CTAs in flight); the streamed path keeps 8 sequences per CTA
+  return gru ? launch_rec<false, true, 8>(p, ws_pre, len, n, L, out, h_n, c_n, err, state8, s)
+             : launch_rec<false, false, 8>(p, ws_pre, len, n, L, out, h_n, c_n, err, state8, s);
 }
 
 }  // namespace cair
