@@ -234,7 +234,7 @@ int32_t cair_set_gemm_impl(int32_t impl) {
 
 int32_t cair_mt_set_impl(cair_handle* h, int32_t impl) {
   if (!h || h->model != CAIR_MODEL_MT) return fail(CAIR_ERR_BAD_ARG, "mt_set_impl: not a match-tensor handle");
-  if (impl != MT_IMPL_FP32 && impl != MT_IMPL_TC) return fail(CAIR_ERR_BAD_ARG, "mt_set_impl: impl must be 0 (fp32) or 1 (tcgen05)");
+  if (impl < MT_IMPL_FP32 || impl > MT_IMPL_TC_SPLIT) return fail(CAIR_ERR_BAD_ARG, "mt_set_impl: impl must be 0 (fp32), 1 (tcgen05) or 2 (tcgen05, unfused projection)");
   h->mt.impl = impl;
   return CAIR_OK;
 }

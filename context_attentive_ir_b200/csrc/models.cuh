@@ -52,12 +52,16 @@ void mt_tc_workspace(const MtPack& p, int64_t nq, int64_t pc, int Lq, int Ld, si
 int32_t mt_epi_const(const MtPack& p, MtEpiConst* out, cudaStream_t s);  // synchronises s
 int32_t mt_tc_build_t(const MtPack& p, const float* cq, uint8_t* timg, int Lq, int64_t nq, cudaStream_t s);
 int32_t mt_tc_doc_image(const MtPack& p, const float* cd, uint8_t* aimg, int Ld, int64_t pair_count, cudaStream_t s);
+bool mt_tc_proj_supported(int C, int Hd);
+int32_t mt_tc_pack_wd(Owned& own, const float* wd, int C, int Hd, uint8_t** img, cudaStream_t s);
+int32_t mt_tc_proj_image(const MtPack& p, const float* enc_d, int Hd, const uint8_t* wd_img, const float* bd,
+                         uint8_t* aimg, int Ld, int64_t pair_count, cudaStream_t s);
 int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const uint8_t* timg, const uint8_t* aimg,
                        const int64_t* q, const int64_t* d, int N, int Lq, int Ld, int64_t pair_begin,
                        int64_t pair_count, int64_t q_begin, int64_t nq, float* scores, cudaStream_t s);
 
 extern long long* g_mt_dbg;  // optional role-timing counters of the tcgen05 interaction kernel (debug)
-enum { MT_IMPL_FP32 = 0, MT_IMPL_TC = 1 };
+enum { MT_IMPL_FP32 = 0, MT_IMPL_TC = 1, MT_IMPL_TC_SPLIT = 2 };  // 2: tcgen05 interaction, fp32 doc projection + image kernel
 struct MtState {
   int V = 0, E = 0, F = 0, Hq = 0, Hd = 0, C = 0;
   int impl = MT_IMPL_TC;  // interaction kernel: tcgen05 bf16x3 (default) or the fp32 CUDA-core kernel
@@ -65,7 +69,7 @@ struct MtState {
   LstmPack enc_q{}, enc_d{};
   LstmTcPack tc_q{}, tc_d{};  // tensor-core encoders (valid when lstm_tc_supported)
   float *wq = nullptr, *bq = nullptr, *wd = nullptr, *bd = nullptr;  // channel projections
-  GemmTcW wd_tc;                                                      // tensor-core image of the doc projection
+  uint8_t* wd_img = nullptr;  // hi/lo operand image of the doc projection (fused projection + A image kernel)
   MtPack pack{};
   MtEpiConst epi{};
   cudaStream_t side = nullptr;            // query-side work runs here, forked/joined with events

@@ -285,6 +285,7 @@ int32_t mt_create_state(Owned& own, const cair_mt_weights& w, MtState* st, cudaS
   CAIR_TRY(dev_copy(own, w.document_projection.w, (size_t)w.nchannels * w.nhid_doc, &st->wd, s));
   CAIR_TRY(dev_copy(own, w.document_projection.b, (size_t)w.nchannels, &st->bd, s));
   CAIR_TRY(mt_pack(own, w, &st->pack, s));
+  if (mt_tc_proj_supported(w.nchannels, w.nhid_doc)) CAIR_TRY(mt_tc_pack_wd(own, st->wd, w.nchannels, w.nhid_doc, &st->wd_img, s));
   CAIR_TRY(mt_epi_const(st->pack, &st->epi, s));
   CAIR_CUDA(cudaStreamCreateWithFlags(&st->side, cudaStreamNonBlocking));
   CAIR_CUDA(cudaEventCreateWithFlags(&st->ev_fork, cudaEventDisableTiming));
@@ -299,15 +300,15 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
   // queries touched by the pair slice [pb, pb+pc)
   const int64_t qb = pc > 0 ? pb / N : 0;
   const int64_t nq = pc > 0 ? (pb + pc - 1) / N - qb + 1 : 0;
-  const bool tc_q = st.impl == MT_IMPL_TC && st.tc_q.wimg != nullptr;
-  const bool tc_d = st.impl == MT_IMPL_TC && st.tc_d.wimg != nullptr;
+  const bool tc_q = st.impl != MT_IMPL_FP32 && st.tc_q.wimg != nullptr;
+  const bool tc_d = st.impl != MT_IMPL_FP32 && st.tc_d.wimg != nullptr;
   float* pre_q = ws.take<float>(tc_q ? 0 : lstm_workspace_floats(st.enc_q, nq, Lq));
   float* enc_q = ws.take<float>((size_t)nq * Lq * st.Hq);
   float* pre_d = ws.take<float>(tc_d ? 0 : lstm_workspace_floats(st.enc_d, pc, Ld));
   float* enc_d = ws.take<float>((size_t)pc * Ld * st.Hd);
   float* cq = ws.take<float>((size_t)nq * Lq * st.C);
   float* cd = ws.take<float>((size_t)pc * Ld * st.C);
-  const bool use_tc = st.impl == MT_IMPL_TC && mt_tc_supported(st.pack, Lq, Ld);
+  const bool use_tc = st.impl != MT_IMPL_FP32 && mt_tc_supported(st.pack, Lq, Ld);
   float* T = nullptr;
   uint8_t* timg = nullptr;
   uint8_t* aimg = nullptr;
@@ -356,14 +357,19 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
                               cudaMemcpyDeviceToDevice, s));
   // channel projection (:108): the bias also lands on pad positions (zero memory-bank rows)
   prof_mark("doc_projection", s);
-  // (K = 128, N = 50 is too small a tile for the tcgen05 GEMM's per-CTA setup: the fp32 kernel is faster here)
-  CAIR_TRY(gemm_f32(gemm_dense(enc_d, st.Hd), st.wd, st.bd, cd, st.C, pc * Ld, st.C, st.Hd, ACT_NONE, s));
   if (use_tc) {
-    CAIR_TRY(mt_tc_doc_image(st.pack, cd, aimg, Ld, pc, s));
+    if (st.wd_img && st.impl == MT_IMPL_TC) {
+      // tcgen05 projection written straight into the interaction kernel's operand image
+      CAIR_TRY(mt_tc_proj_image(st.pack, enc_d, st.Hd, st.wd_img, st.bd, aimg, Ld, pc, s));
+    } else {
+      CAIR_TRY(gemm_f32(gemm_dense(enc_d, st.Hd), st.wd, st.bd, cd, st.C, pc * Ld, st.C, st.Hd, ACT_NONE, s));
+      CAIR_TRY(mt_tc_doc_image(st.pack, cd, aimg, Ld, pc, s));
+    }
     prof_mark("join_query_side", s);
     if (st.side) CAIR_CUDA(cudaStreamWaitEvent(s, st.ev_join, 0));
     return mt_tc_interact(st.pack, st.epi, timg, aimg, q, d, N, Lq, Ld, pb, pc, qb, nq, scores, s);
   }
+  CAIR_TRY(gemm_f32(gemm_dense(enc_d, st.Hd), st.wd, st.bd, cd, st.C, pc * Ld, st.C, st.Hd, ACT_NONE, s));
   if (st.side) CAIR_CUDA(cudaStreamWaitEvent(s, st.ev_join, 0));
   return mt_interact(st.pack, cq, cd, T, q, d, N, Lq, Ld, pb, pc, qb, nq, scores, s);
 }

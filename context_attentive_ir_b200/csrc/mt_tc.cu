@@ -126,6 +126,171 @@ __global__ void __launch_bounds__(256) mt_tc_image_kernel(const float* __restric
   }
 }
 
+// ---- fused document channel projection + A image (mtensor.py:108 feeding the interaction GEMM) ----
+// cd = enc_d Wd^T + bd is itself a GEMM (M = document positions, K = Hd, N = C): persistent CTAs walk the
+// (pair, 128-row tile) items, keep the hi/lo image of Wd resident in shared memory, stage each tile of encoder
+// rows as a hi/lo bf16 operand image, run KP/16 x 3 tcgen05.mma and write the result straight from TMEM into the
+// interaction kernel's A image (bias added, split to hi/lo) - the fp32 [pairs, Ld, C] tensor never exists.
+constexpr int PJ_THREADS = 256;
+// Plane stride 128 rows + one 16-byte pad and a 64-byte skew of the lo half: the 8 lanes of one 128-bit store phase
+// (4 planes x hi/lo of one row) then hit 8 distinct 16-byte bank groups.
+constexpr uint32_t PJ_APLANE = 128 * 16 + 16;
+constexpr uint32_t PJ_LOSKEW = 64;
+
+// Wd image: [hi|lo][plane k/8][row n < CP][8 x bf16], zero beyond (C, Hd)
+__global__ void mt_tc_pack_wd_kernel(const float* __restrict__ w, int C, int Hd, int CP, int KP, uint8_t* __restrict__ img) {
+  const size_t half = (size_t)(KP / 8) * CP * 16;
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < (KP / 8) * CP; u += gridDim.x * blockDim.x) {
+    const int kc = u / CP, n = u - kc * CP;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v[2];
+#pragma unroll
+      for (int z = 0; z < 2; ++z) {
+        const int k = kc * 8 + 2 * e + z;
+        v[z] = (n < C && k < Hd) ? w[(size_t)n * Hd + k] : 0.f;
+      }
+      split_bf16x2(v[0], v[1], hi[e], lo[e]);
+    }
+    const size_t off = ((size_t)kc * CP + n) * 16;
+    *reinterpret_cast<uint4*>(img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(img + half + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// smem: A image [hi|lo][KP/8][128 rows (+pad)][16 B] | W image [hi|lo][KP/8][CP rows][16 B] | bias[CP]
+__global__ void __launch_bounds__(PJ_THREADS, 2)
+    mt_tc_proj_image_kernel(const float* __restrict__ enc, int Hd, int KP, const uint8_t* __restrict__ wimg,
+                            const float* __restrict__ bd, int C, int CP, int Ld, int RA, int ntile, int64_t nitems,
+                            uint32_t tcols, uint8_t* __restrict__ aimg) {
+  extern __shared__ __align__(128) uint8_t smraw[];
+  __shared__ uint64_t w_full, acc_full;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t a_half = (uint32_t)(KP / 8) * PJ_APLANE + PJ_LOSKEW;
+  const uint32_t w_plane = (uint32_t)CP * 16, w_half = (uint32_t)(KP / 8) * w_plane;
+  uint8_t* a_img = smraw;
+  uint8_t* w_img = smraw + 2 * a_half;
+  float* bias_s = reinterpret_cast<float*>(w_img + 2 * w_half);
+  const int KC = CP / 8;
+  const size_t o_half = (size_t)KC * RA * 16;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, tcols);
+  if (tid == 32) {
+    mbar_init(&w_full, 1);
+    mbar_init(&acc_full, 1);
+    fence_mbar_init();
+  }
+  for (int c = tid; c < CP; c += PJ_THREADS) bias_s[c] = c < C ? bd[c] : 0.f;  // pad channels: W rows 0, bias 0
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  if (tid == 0) {
+    const uint32_t bytes = 2 * w_half;
+    mbar_arrive_expect_tx(&w_full, bytes);
+    for (uint32_t o = 0; o < bytes; o += 32768) bulk_g2s(w_img + o, wimg + o, min(32768u, bytes - o), &w_full);
+  }
+  const uint32_t issue = elect_one();
+  const uint32_t idesc = idesc_bf16_f32(128, CP);
+  const uint64_t ah = smem_desc(smem_u32(a_img), PJ_APLANE, 128), al = ah + (uint64_t)(a_half >> 4);
+  const uint64_t wh = smem_desc(smem_u32(w_img), w_plane, 128), wl = wh + (uint64_t)(w_half >> 4);
+  const int half = lane & 1;
+  const int ncb = (KP + 127) / 128;  // 128-channel column blocks: one warp load = one 512-byte row segment
+  const int row0 = warp * 16;        // warp <-> 16 rows of the tile
+  uint32_t phase = 0;
+  bool w_ready = false;
+
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int64_t pl = item / ntile;
+    const int mt = (int)(item - pl * ntile);
+    const float* src = enc + ((size_t)pl * Ld + (size_t)mt * 128) * Hd;
+    const int nrow = min(128, Ld - mt * 128);
+    // ---- stage the encoder rows: a lane pair owns one 8-channel unit of the row.  Rows >= nrow only feed accumulator
+    //      rows the epilogue never reads, so they are loaded from a clamped (valid) address and left as they are. ----
+    for (int cb = 0; cb < ncb; ++cb) {
+      const int k = cb * 128 + lane * 4, kc = k >> 3;
+      const float* colp = src + min(k, Hd - 4);
+      float4 v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        v[i] = ldg_stream(reinterpret_cast<const float4*>(colp + (size_t)min(row0 + i, nrow - 1) * Hd));
+      uint8_t* dst = a_img + (half ? a_half : 0u) + (uint32_t)kc * PJ_APLANE + (uint32_t)row0 * 16;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        uint32_t hw0, lw0, hw1, lw1;
+        split_bf16x2(v[i].x, v[i].y, hw0, lw0);
+        split_bf16x2(v[i].z, v[i].w, hw1, lw1);
+        // even lane keeps the hi unit, odd lane the lo unit: swap the two words the partner needs
+        const uint32_t r0 = __shfl_xor_sync(0xffffffffu, half ? hw0 : lw0, 1);
+        const uint32_t r1 = __shfl_xor_sync(0xffffffffu, half ? hw1 : lw1, 1);
+        uint4 unit = half ? make_uint4(r0, r1, lw0, lw1) : make_uint4(hw0, hw1, r0, r1);
+        if (k >= Hd) unit = make_uint4(0u, 0u, 0u, 0u);  // K padding (Hd < KP)
+        if (k < KP) *reinterpret_cast<uint4*>(dst + i * 16) = unit;
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (warp == 0) {
+      if (!w_ready) mbar_wait(&w_full, 0), w_ready = true;
+      tc_fence_after();
+      for (int ks = 0; ks < KP / 16; ++ks) {
+        const uint64_t ao = (uint64_t)(ks * ((2 * PJ_APLANE) >> 4)), wo = (uint64_t)(ks * ((2 * w_plane) >> 4));
+        mma_bf16_ss_w(tbase, ah + ao, wh + wo, idesc, (uint32_t)(ks != 0), issue);
+        mma_bf16_ss_w(tbase, al + ao, wh + wo, idesc, 1, issue);
+        mma_bf16_ss_w(tbase, ah + ao, wl + wo, idesc, 1, issue);
+      }
+      mma_commit_w(&acc_full, issue);
+    }
+    // ---- halo / tail rows of the image are zero ----
+    uint8_t* out = aimg + (size_t)pl * 2 * o_half;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    if (mt == 0 && tid < 3)
+      for (int kc = 0; kc < KC; ++kc) {
+        *reinterpret_cast<uint4*>(out + ((size_t)kc * RA + tid) * 16) = zero;
+        *reinterpret_cast<uint4*>(out + o_half + ((size_t)kc * RA + tid) * 16) = zero;
+      }
+    if (mt == ntile - 1)
+      for (int r = Ld + 3 + tid; r < RA; r += PJ_THREADS)
+        for (int kc = 0; kc < KC; ++kc) {
+          *reinterpret_cast<uint4*>(out + ((size_t)kc * RA + r) * 16) = zero;
+          *reinterpret_cast<uint4*>(out + o_half + ((size_t)kc * RA + r) * 16) = zero;
+        }
+    mbar_wait_relaxed(&acc_full, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue: lane <-> row (TMEM lane quarter warp % 4), warps 0-3 / 4-7 take alternate 16-column chunks;
+    //      + bias, split, 16-byte units of the A image ----
+    const int rl = (warp & 3) * 32 + lane, j = mt * 128 + rl;
+    for (int c0 = (warp >> 2) * 16; c0 < CP; c0 += 32) {
+      float v[16];
+      tmem_ld16(tbase + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      if (j < Ld) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint32_t hi[4], lo[4];
+          const float4 ba = *reinterpret_cast<const float4*>(bias_s + c0 + g * 8);
+          const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + g * 8 + 4);
+          split_bf16x2(v[g * 8 + 0] + ba.x, v[g * 8 + 1] + ba.y, hi[0], lo[0]);
+          split_bf16x2(v[g * 8 + 2] + ba.z, v[g * 8 + 3] + ba.w, hi[1], lo[1]);
+          split_bf16x2(v[g * 8 + 4] + bb.x, v[g * 8 + 5] + bb.y, hi[2], lo[2]);
+          split_bf16x2(v[g * 8 + 6] + bb.z, v[g * 8 + 7] + bb.w, hi[3], lo[3]);
+          const size_t off = ((size_t)(c0 / 8 + g) * RA + j + 3) * 16;
+          *reinterpret_cast<uint4*>(out + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(out + o_half + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // TMEM accumulator and the A image are reusable
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, tcols);
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -439,6 +604,36 @@ int32_t mt_tc_doc_image(const MtPack& p, const float* cd, uint8_t* aimg, int Ld,
   if (pair_count <= 0) return CAIR_OK;
   prof_mark("doc_image", s);
   CAIR_LAUNCH(mt_tc_image_kernel, (unsigned)pair_count, 256, 0, s, cd, p.C, Ld, tc_cp(p.C) / 8, tc_ra(Ld), pair_count, aimg);
+  return CAIR_OK;
+}
+
+// Fused projection + image (see mt_tc_proj_image_kernel).  wd_img from mt_tc_pack_wd.
+static inline int pj_kp(int Hd) { return (Hd + 15) & ~15; }
+static inline size_t pj_smem(int C, int Hd) {
+  return (size_t)2 * ((pj_kp(Hd) / 8) * PJ_APLANE + PJ_LOSKEW) + (size_t)pj_kp(Hd) * 4 * tc_cp(C) + (size_t)tc_cp(C) * 4;
+}
+bool mt_tc_proj_supported(int C, int Hd) {
+  return Hd % 4 == 0 && tc_cp(C) <= 256 && pj_smem(C, Hd) <= 110 * 1024;  // two CTAs per SM
+}
+int32_t mt_tc_pack_wd(Owned& own, const float* wd, int C, int Hd, uint8_t** img, cudaStream_t s) {
+  const int CP = tc_cp(C), KP = pj_kp(Hd);
+  CAIR_CUDA(own.alloc(img, (size_t)2 * (KP / 8) * CP * 16));
+  CAIR_LAUNCH(mt_tc_pack_wd_kernel, 8, 256, 0, s, wd, C, Hd, CP, KP, *img);
+  return CAIR_OK;
+}
+int32_t mt_tc_proj_image(const MtPack& p, const float* enc_d, int Hd, const uint8_t* wd_img, const float* bd,
+                         uint8_t* aimg, int Ld, int64_t pair_count, cudaStream_t s) {
+  if (pair_count <= 0) return CAIR_OK;
+  if ((uintptr_t)enc_d % 16) return fail(CAIR_ERR_BAD_ARG, "match_tensor: encoder output not 16-byte aligned");
+  const int CP = tc_cp(p.C), KP = pj_kp(Hd), ntile = (Ld + 127) / 128;
+  const int64_t nitems = pair_count * ntile;
+  const size_t smem = pj_smem(p.C, Hd);
+  uint32_t tcols = 32;
+  while ((int)tcols < CP) tcols <<= 1;
+  CAIR_CUDA(cudaFuncSetAttribute(mt_tc_proj_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)(nitems < 2 * kSMs ? nitems : 2 * kSMs);
+  CAIR_LAUNCH(mt_tc_proj_image_kernel, grid, PJ_THREADS, smem, s, enc_d, Hd, KP, wd_img, bd, p.C, CP, Ld, tc_ra(Ld), ntile,
+              nitems, tcols, aimg);
   return CAIR_OK;
 }
 

@@ -379,8 +379,9 @@ class MatchTensor(_Ranker):
         return lib.load().cair_mt_create(w, device, out)
 
     def set_interaction_impl(self, impl):
-        """'tc' (default): tcgen05 bf16x3 tensor-core interaction kernel; 'fp32': CUDA-core fp32 kernel."""
-        self.__dict__['_cair_impl'] = {'fp32': 0, 'tc': 1}[impl]
+        """'tc' (default): tcgen05 bf16x3 tensor-core kernels; 'fp32': CUDA-core fp32 kernels;
+        'tc_split': tensor-core interaction with the unfused fp32 document projection."""
+        self.__dict__['_cair_impl'] = {'fp32': 0, 'tc': 1, 'tc_split': 2}[impl]
         h = self.__dict__.get('_cair_handle')
         if h is not None:
             lib.check(lib.load().cair_mt_set_impl(h, self.__dict__['_cair_impl']))

@@ -168,7 +168,9 @@ CAIR_API int32_t cair_set_gemm_impl(int32_t impl);
 
 /* Interaction kernel selection: 1 = tcgen05 bf16x3 split-precision tensor-core kernel (default when the
  * configuration fits: nfilters in {4,6}, nchannels <= 64, match_filter_size <= 32), 0 = fp32 CUDA-core
- * kernel (always available; the on-device cross-check of the tensor-core path). */
+ * kernel (always available; the on-device cross-check of the tensor-core path), 2 = as 1 but with the
+ * document channel projection on the fp32 GEMM followed by a separate image kernel (A/B check of the fused
+ * tcgen05 projection that impl 1 uses). */
 CAIR_API int32_t cair_mt_set_impl(cair_handle* h, int32_t impl);
 
 /* ---- DRMM (neuroir/rankers/drmm.py:13-27 ctor, :29-84 forward, :87-98 gating) -------------- */

@@ -67,7 +67,7 @@ def test_tcgen05_conventions_selftest():
         assert err < tol, (N, K, shift, split, err)
 
 
-@pytest.mark.parametrize('impl', ['tc', 'fp32'])
+@pytest.mark.parametrize('impl', ['tc', 'tc_split', 'fp32'])
 @pytest.mark.parametrize('name', ['mt_tiny', 'mt_fullpad', 'mt_stock', 'mt_cfg2arch', 'mt_gru'])
 def test_match_tensor_golden(name, impl):
     cfg, ins, sd, outs = ol.load_golden(name)
