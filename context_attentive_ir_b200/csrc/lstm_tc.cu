@@ -8,12 +8,15 @@
 // small per-step operand (32 sequences) is the N side, so a step costs 2 x 7 x 3 MMAs of 16 cycles
 // instead of 128-cycle ones.  bf16x3 split precision (hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM)
 // keeps ~fp32 accuracy through the 200-step recurrence (plain bf16/tf32 does not hold the 1e-3 bar).
-// Gate rows are permuted so that TMEM lane quarter q of row tile m holds gate type q (i,f,g,o) of units
-// 32m..32m+31: the activation is warp-uniform and bias is a per-thread scalar.
-// Warp roles (576 threads): warps 0-15 epilogue (phase 1: tcgen05.ld + sigmoid/tanh -> smem; phase 2: c/h
-// update in registers, h written as next step's bf16 hi/lo operand + fp32 memory bank), warp 16: MMA issuer,
-// warp 17: gather of x (embedding rows by token id, or dense rows) into a 4-slot operand ring, running up
-// to 3 steps ahead so the global-load latency never sits on the recurrence's critical path.
+// Gate rows are permuted so that, inside every 32-lane TMEM quarter, rows 8*type + j hold gate `type` (i,f,g,o) of
+// unit j: a pair of tcgen05.ld.16x256b then hands each thread ALL FOUR gates of one unit for 4 sequences, so the
+// whole cell update (5 exponentials + 2 reciprocals per element, c/h state in registers) runs without any
+// inter-thread exchange.
+// Warp roles (672 threads): warps 0-15 epilogue (TMEM -> gates -> c/h update; h written as next step's bf16 hi/lo
+// operand, then the fp32 memory bank), warp 16: MMA issuer - the x part of step t+1 is issued right behind the h
+// part of step t into the other TMEM accumulator, so only the recurrent half of the GEMM sits on the critical path,
+// warps 17-20: gather of x (embedding rows by token id, or dense rows) into a 4-slot operand ring, one warp per
+// slot, so the id -> row -> convert latency chain of a step has four step times to complete.
 #include "models.cuh"
 #include "umma.cuh"
 
@@ -27,7 +30,8 @@ constexpr int LT_K = LT_XP + LT_HP;       // 112
 constexpr int LT_PLANES = LT_K / 8;       // 14
 constexpr int LT_NSEQ = 32;               // sequences per CTA = N of the MMA
 constexpr int LT_EPI_WARPS = 16;          // epilogue warps (4 per SM sub-partition)
-constexpr int LT_THREADS = (LT_EPI_WARPS + 2) * 32;
+constexpr int LT_XS = 4;                   // x-operand ring slots = gather warps (warp g fills slot g for steps = g mod 4)
+constexpr int LT_THREADS = (LT_EPI_WARPS + 1 + LT_XS) * 32;
 constexpr uint32_t LT_APLANE = 128 * 16;  // weight image: 128 rows per plane
 constexpr uint32_t LT_BPLANE = LT_NSEQ * 16;
 constexpr uint32_t LT_AIMG = LT_PLANES * LT_APLANE;  // one (row tile, hi|lo) image: 28672 B
@@ -35,13 +39,13 @@ constexpr uint32_t LT_BIMG = LT_PLANES * LT_BPLANE;  // one (hi|lo) image: 7168 
 
 bool lstm_tc_supported(int in, int h) { return in >= 1 && in <= LT_XP && h >= 1 && h <= LT_HP; }
 
-// weight image [dir][row tile][hi|lo][plane][row][8 x bf16]; row = type*32 + l  <->  gate row type*h + (32*tile + l)
+// weight image [dir][row tile][hi|lo][plane][row][8 x bf16]; row = 32*q + 8*type + j  <->  gate row type*h + (32*tile + 8*q + j)
 __global__ void lstm_tc_pack_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, int in, int h,
                                     uint8_t* __restrict__ img) {
   const int total = 2 * LT_PLANES * 128 * 8;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int e = idx & 7, row = (idx >> 3) & 127, pl = (idx >> 10) % LT_PLANES, mt = idx / (LT_PLANES * 1024);
-    const int k = pl * 8 + e, type = row >> 5, u = mt * 32 + (row & 31);
+    const int k = pl * 8 + e, type = (row >> 3) & 3, u = mt * 32 + (row >> 5) * 8 + (row & 7);
     float v = 0.f;
     if (u < h) {
       const int grow = type * h + u;
@@ -76,21 +80,45 @@ __device__ __forceinline__ void lt_named_bar(int id, int n) { asm volatile("bar.
 __device__ __forceinline__ void lt_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// fast, accurate-enough activations: ex2.approx (2^-22 rel) + rcp.approx (1 ulp).  No clamping needed:
-// exp2 saturates to inf/0 and 1/(1+inf) = 0.  tanh(x) = 2*sigmoid(2x) - 1 shares the same two MUFU ops.
-__device__ __forceinline__ float lt_sigmoid(float x) { return __fdividef(1.0f, 1.0f + exp2f(-1.4426950408889634f * x)); }
-__device__ __forceinline__ float lt_tanh(float x) { return fmaf(2.0f, lt_sigmoid(2.0f * x), -1.0f); }
+// tcgen05.ld.16x256b.x2: 16 TMEM lanes x 16 columns per warp; thread (t0 = lane % 4, t1 = lane / 4) receives
+// r0,r1 = (lane t1, cols 2t0, 2t0+1), r2,r3 = (lane t1+8, same cols), r4..r7 = the same for cols + 8.
+__device__ __forceinline__ void lt_tmem_ld_16x256b_x2(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+// e^{-x} with the argument clamped to +-25 (sigmoid / tanh are saturated to fp32 rounding well before that; the clamp
+// keeps products of three (1 + e) terms finite).  ex2.approx: 2^-22 relative error.
+__device__ __forceinline__ float lt_expneg(float x) {
+  return exp2f(-1.4426950408889634f * fminf(fmaxf(x, -25.0f), 25.0f));
+}
+// One LSTM cell update with 5 exponentials and 2 reciprocals (instead of 5 + 5):
+//   sigmoid(a) = 1/(1+ea),  tanh(b) = (1-eb)/(1+eb)  with  ea = e^-a, eb = e^-2b
+//   c' = sigmoid(f) c + sigmoid(i) tanh(g) = [c (1+ei)(1+eg) + (1-eg)(1+ef)] / [(1+ef)(1+ei)(1+eg)]
+//   h' = sigmoid(o) tanh(c')              = (1-ec) / [(1+eo)(1+ec)]
+__device__ __forceinline__ void lt_cell(float gi, float gf, float gg, float go, float c, float& c_new, float& h_new) {
+  const float ei = lt_expneg(gi), ef = lt_expneg(gf), eg = lt_expneg(2.0f * gg), eo = lt_expneg(go);
+  const float pi = 1.0f + ei, pf = 1.0f + ef, pg = 1.0f + eg;
+  const float pig = pi * pg;
+  const float num = fmaf(c, pig, (1.0f - eg) * pf);
+  c_new = __fdividef(num, pig * pf);
+  const float ec = lt_expneg(2.0f * c_new);
+  h_new = __fdividef(1.0f - ec, (1.0f + eo) * (1.0f + ec));
+}
 
 // Optional role timing (dbg != nullptr; CTA (0,0), lane 0 of the role's first warp), see tools/lstm_timing.py
 #define LT_T0() long long t0_ = dbg ? clock64() : 0
 #define LT_ACC(slot) do { if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) dbg[slot] += clock64() - t0_; } while (0)
 long long* g_lstm_dbg = nullptr;
 
-constexpr int LT_XS = 4;                                   // x-operand ring slots (gather runs up to 3 steps ahead)
 constexpr uint32_t LT_XIMG = (LT_XP / 8) * LT_BPLANE;     // one (hi|lo) x image: 6 planes, 3072 B
 constexpr uint32_t LT_HIMG = (LT_HP / 8) * LT_BPLANE;     // one (hi|lo) h image: 8 planes, 4096 B
+constexpr uint32_t LT_TCOLS = 4 * LT_NSEQ;                 // TMEM columns: 2 parities x 2 row tiles x 32
 
-// smem: W image (4 x LT_AIMG) | h operand [2 parities][hi|lo] | x operand ring [LT_XS][hi|lo] | gsm [4][32][64] f32
+// smem: W image (4 x LT_AIMG) | h operand [2 parities][hi|lo] | x operand ring [LT_XS][hi|lo]
+// TMEM: [2 step parities][2 row tiles][32 sequences] fp32 columns
 __global__ void __launch_bounds__(LT_THREADS, 1)
     lstm_tc_kernel(GemmA x, const uint8_t* __restrict__ wimg_all, const float* __restrict__ bias_all,
                    const int64_t* __restrict__ len, int n, int L, int in, int h, int dirs, uint32_t ks_mask,
@@ -107,11 +135,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
   uint8_t* w_img = smraw;
   uint8_t* h_img = w_img + 4 * LT_AIMG;
   uint8_t* x_img = h_img + 4 * LT_HIMG;
-  float* gsm = reinterpret_cast<float*>(x_img + 2 * LT_XS * LT_XIMG);
   const float* bias = bias_all + (size_t)dir * 4 * h;
   const int Hout = dirs * h;
 
-  if (warp == 0) tmem_alloc(&tmem_slot, 64);
+  if (warp == 0) tmem_alloc(&tmem_slot, LT_TCOLS);
   if (tid == 32) {
     mbar_init(&bar_w, 1);
     mbar_init(&bar_h, LT_EPI_WARPS);  // epilogue warps: h_t written as next step's operand
@@ -162,12 +189,13 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
   const int maxlen = smaxlen;
   const uint32_t tbase = tmem_slot;
 
-  if (warp == LT_EPI_WARPS + 1) {
-    // ===================== x gather: embedding rows (or dense rows) -> hi/lo bf16 ring, runs ahead =====================
+  if (warp > LT_EPI_WARPS) {
+    // ===================== x gather: embedding rows (or dense rows) -> hi/lo bf16 ring =====================
+    // One warp per ring slot: each has LT_XS step times to cover its id -> row -> convert latency chain.
     const int myl = slen[lane];   // lane <-> sequence row
     const bool vec = (in & 3) == 0 && (x.table ? ((x.E & 3) == 0) : ((x.lda & 3) == 0));
-    for (int step = 0; step < maxlen; ++step) {
-      const int slot = step % LT_XS;
+    const int slot = warp - LT_EPI_WARPS - 1;
+    for (int step = slot; step < maxlen; step += LT_XS) {
       { LT_T0(); mbar_wait_relaxed(&x_empty[slot], ((step / LT_XS) & 1) ^ 1); LT_ACC(7); }
       const bool active = step < myl;
       const int t = dir ? myl - 1 - step : step;
@@ -220,120 +248,132 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     const uint64_t wd0 = smem_desc(smem_u32(w_img), LT_APLANE, 128);
     const uint64_t hd0 = smem_desc(smem_u32(h_img), LT_BPLANE, 128);
     const uint64_t xd0 = smem_desc(smem_u32(x_img), LT_BPLANE, 128);
-    for (int step = 0; step < maxlen; ++step) {
-      const int par = step & 1, slot = step % LT_XS;
-      { LT_T0(); mbar_wait(&x_full[slot], (step / LT_XS) & 1); LT_ACC(0); }
-      { LT_T0(); mbar_wait(&bar_h, par); LT_ACC(1); }
-      tc_fence_after();
-      LT_T0();
-      const uint64_t hdp = hd0 + (uint64_t)((uint32_t)par * 2 * LT_HIMG >> 4);
-      const uint64_t xdp = xd0 + (uint64_t)((uint32_t)slot * 2 * LT_XIMG >> 4);
+    // k-steps [ks_lo, ks_hi) of one step's GEMM into the accumulators of parity `par`; `fresh`: first MMA overwrites
+    auto issue_part = [&](int par, uint64_t bdesc0, uint32_t bimg, int ks_lo, int ks_hi, int ks_sub, bool fresh) {
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         if (mt < nmt) {
           const uint64_t wdm = wd0 + (uint64_t)((uint32_t)mt * 2 * LT_AIMG >> 4);
-          const uint32_t tacc = tbase + (uint32_t)mt * LT_NSEQ;
-          uint32_t acc = 0;
+          const uint32_t tacc = tbase + (uint32_t)(par * 2 + mt) * LT_NSEQ;
+          uint32_t acc = fresh ? 0u : 1u;
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
             const uint64_t wp = wdm + (pass == 1 ? (LT_AIMG >> 4) : 0);   // weights: hi, lo, hi
-            const uint64_t xp = xdp + (pass == 2 ? (LT_XIMG >> 4) : 0);   // activations: hi, hi, lo
-            const uint64_t hp = hdp + (pass == 2 ? (LT_HIMG >> 4) : 0);
+            const uint64_t bp = bdesc0 + (pass == 2 ? (bimg >> 4) : 0);   // activations: hi, hi, lo
 #pragma unroll
             for (int ks = 0; ks < LT_K / 16; ++ks) {
-              if ((ks_mask >> ks) & 1) {
-                const uint64_t bd = (ks < LT_XP / 16) ? xp + (uint64_t)((2 * ks) * (LT_BPLANE >> 4))
-                                                      : hp + (uint64_t)((2 * (ks - LT_XP / 16)) * (LT_BPLANE >> 4));
-                mma_bf16_ss_w(tacc, wp + (uint64_t)((2 * ks) * (LT_APLANE >> 4)), bd, idesc, acc, issue);
+              if (ks >= ks_lo && ks < ks_hi && ((ks_mask >> ks) & 1)) {
+                mma_bf16_ss_w(tacc, wp + (uint64_t)((2 * ks) * (LT_APLANE >> 4)),
+                              bp + (uint64_t)((2 * (ks - ks_sub)) * (LT_BPLANE >> 4)), idesc, acc, issue);
                 acc = 1;
               }
             }
           }
         }
       }
+    };
+    if (maxlen > 0) {
+      { LT_T0(); mbar_wait(&x_full[0], 0); LT_ACC(0); }
+      tc_fence_after();
+      issue_part(0, xd0, LT_XIMG, 0, LT_XP / 16, 0, true);
+    }
+    for (int step = 0; step < maxlen; ++step) {
+      const int par = step & 1, slot = step % LT_XS;
+      // h_{step-1} is in operand buffer `par`; the epilogue of step-1 has also finished reading accumulator par^1
+      { LT_T0(); mbar_wait(&bar_h, par); LT_ACC(1); }
+      tc_fence_after();
+      LT_T0();
+      issue_part(par, hd0 + (uint64_t)((uint32_t)par * 2 * LT_HIMG >> 4), LT_HIMG, LT_XP / 16, LT_K / 16, LT_XP / 16, false);
       mma_commit_w(&bar_acc, issue);
       mma_commit_w(&x_empty[slot], issue);
       LT_ACC(2);
+      if (step + 1 < maxlen) {
+        // x part of the next step, behind the h part in the tensor pipe: runs while the epilogue works
+        const int nslot = (step + 1) % LT_XS;
+        { LT_T0(); mbar_wait(&x_full[nslot], ((step + 1) / LT_XS) & 1); LT_ACC(0); }
+        tc_fence_after();
+        issue_part(par ^ 1, xd0 + (uint64_t)((uint32_t)nslot * 2 * LT_XIMG >> 4), LT_XIMG, 0, LT_XP / 16, 0, true);
+      }
     }
   } else {
     // ===================== epilogue warps =====================
-    // phase 1: warp -> (row tile mt, gate type = TMEM lane quarter, half of the 32 sequences); lane -> unit
-    const int type = warp & 3, mt = (warp >> 2) & 1, shalf = warp >> 3;
-    const int u1 = mt * 32 + lane;
-    const float bias1 = (u1 < h) ? bias[type * h + u1] : 0.f;
-    const float pre = (type == 2) ? 2.0f : 1.0f;     // tanh(x) = 2*sigmoid(2x) - 1 for the cell gate
-    const float post_a = (type == 2) ? 2.0f : 1.0f, post_b = (type == 2) ? -1.0f : 0.0f;
-    // phase 2: thread -> unit u2, sequences s = sg + 8k (k < 4)
-    const int u2 = tid & 63, sg = tid >> 6;
+    // warp -> (TMEM lane quarter q, row tile mt, half of the 32 sequences); lane -> (t0 = lane % 4, j = lane / 4):
+    // unit u = 32 mt + 8 q + j, sequences sl[c] = 16 shalf + {2 t0, 2 t0 + 1, 8 + 2 t0, 9 + 2 t0}
+    const int q = warp & 3, mt = (warp >> 2) & 1, shalf = warp >> 3;
+    const int t0i = lane & 3, j = lane >> 2;
+    const int u = mt * 32 + q * 8 + j;
+    const bool uvalid = u < h && mt < nmt;
+    float bi = 0.f, bf = 0.f, bg = 0.f, bo = 0.f;
+    if (uvalid) bi = bias[u], bf = bias[h + u], bg = bias[2 * h + u], bo = bias[3 * h + u];
+    int sl[4], lk[4];
     float cst[4], hst[4];
-    int lk[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) cst[k] = 0.f, hst[k] = 0.f, lk[k] = slen[sg + 8 * k];
+    for (int c = 0; c < 4; ++c) {
+      sl[c] = shalf * 16 + (c >> 1) * 8 + 2 * t0i + (c & 1);
+      lk[c] = slen[sl[c]];
+      cst[c] = 0.f, hst[c] = 0.f;
+    }
+    const uint32_t tq = tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * LT_NSEQ + shalf * 16);
+    const uint32_t hoff = (uint32_t)(u >> 3) * LT_BPLANE + (uint32_t)(u & 7) * 2;
     if (lane == 0 && maxlen > 0) lt_arrive(&bar_h);   // h_0 = 0 is already in operand buffer 0
     for (int step = 0; step < maxlen; ++step) {
       const int par = step & 1;
       { LT_T0(); mbar_wait(&bar_acc, par); if (warp == 0) LT_ACC(3); }
       tc_fence_after();
       LT_T0();
-      // ---- phase 1: activation of one gate row for 16 sequences ----
+      float hv[4];
       if (mt < nmt) {
-        float v[16];
-        tmem_ld16(tbase + ((uint32_t)(type * 32) << 16) + (uint32_t)(mt * LT_NSEQ + shalf * 16), v);
+        float ga[8], gb[8];  // ga: gates i (0,1,4,5) and f (2,3,6,7); gb: g and o
+        const uint32_t ta = tq + (uint32_t)(par * 2 * LT_NSEQ);
+        lt_tmem_ld_16x256b_x2(ta, ga);
+        lt_tmem_ld_16x256b_x2(ta + (16u << 16), gb);
         tmem_ld_wait();
-        if (u1 < h) {
+        tc_fence_before();
+        uint8_t* hn = h_img + (size_t)(par ^ 1) * 2 * LT_HIMG + hoff;  // next step's h operand
 #pragma unroll
-          for (int s = 0; s < 16; ++s) {
-            const float sgm = lt_sigmoid(pre * (v[s] + bias1));
-            gsm[(type * 32 + shalf * 16 + s) * 64 + u1] = fmaf(post_a, sgm, post_b);
-          }
-        }
-      }
-      tc_fence_before();
-      if (warp == 0) LT_ACC(4);
-      lt_named_bar(1, LT_EPI_WARPS * 32);
-      if (warp == 0) LT_ACC(5);
-      // ---- phase 2: state update, branch-free so the 4 items interleave ----
-      uint8_t* hn = h_img + (size_t)(par ^ 1) * 2 * LT_HIMG;  // next step's h operand
-      if (u2 < h) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int s = sg + 8 * k;
-          const bool act = step < lk[k];
-          const float ig = gsm[(0 * 32 + s) * 64 + u2], fg = gsm[(1 * 32 + s) * 64 + u2];
-          const float gg = gsm[(2 * 32 + s) * 64 + u2], og = gsm[(3 * 32 + s) * 64 + u2];
-          const float c = fmaf(fg, cst[k], ig * gg);
-          const float hv = og * lt_tanh(c);
-          cst[k] = act ? c : cst[k];
-          hst[k] = act ? hv : hst[k];
-          if (act) {
-            const int t = dir ? lk[k] - 1 - step : step;
-            out[((size_t)(s0 + s) * L + t) * Hout + dir * h + u2] = hv;
-          }
+        for (int c = 0; c < 4; ++c) {
+          const int r = (c >> 1) * 4 + (c & 1);
+          float cn, hn_v;
+          lt_cell(ga[r] + bi, ga[r + 2] + bf, gb[r] + bg, gb[r + 2] + bo, cst[c], cn, hn_v);
+          const bool act = step < lk[c];
+          cst[c] = act ? cn : cst[c];
+          hst[c] = act ? hn_v : hst[c];
+          hv[c] = hn_v;
           __nv_bfloat16 hi, lo;
-          split_bf16(hst[k], hi, lo);
-          const size_t off = (size_t)(u2 >> 3) * LT_BPLANE + (size_t)s * 16 + (u2 & 7) * 2;
-          *reinterpret_cast<__nv_bfloat16*>(hn + off) = hi;
-          *reinterpret_cast<__nv_bfloat16*>(hn + LT_HIMG + off) = lo;
+          split_bf16(hst[c], hi, lo);
+          *reinterpret_cast<__nv_bfloat16*>(hn + sl[c] * 16) = hi;
+          *reinterpret_cast<__nv_bfloat16*>(hn + LT_HIMG + sl[c] * 16) = lo;
         }
       }
       fence_proxy_async();
       __syncwarp();
-      if (warp == 0) LT_ACC(6);
       if (lane == 0 && step + 1 < maxlen) lt_arrive(&bar_h);
-    }
-    if (u2 < h && (h_n || c_n)) {
+      if (warp == 0) LT_ACC(4);
+      // memory bank (fp32), off the critical path: 8 consecutive units x 4 sequences per warp store
+      if (uvalid) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int s = sg + 8 * k;
+        for (int c = 0; c < 4; ++c) {
+          if (step < lk[c]) {
+            const int t = dir ? lk[c] - 1 - step : step;
+            out[((size_t)(s0 + sl[c]) * L + t) * Hout + dir * h + u] = hv[c];
+          }
+        }
+      }
+      if (warp == 0) LT_ACC(5);
+    }
+    if (uvalid && (h_n || c_n)) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int s = sl[c];
         if (s0 + s >= n) continue;
-        if (h_n) h_n[((size_t)dir * n + s0 + s) * h + u2] = hst[k];
-        if (c_n) c_n[((size_t)dir * n + s0 + s) * h + u2] = cst[k];
+        if (h_n) h_n[((size_t)dir * n + s0 + s) * h + u] = hst[c];
+        if (c_n) c_n[((size_t)dir * n + s0 + s) * h + u] = cst[c];
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tbase, 64);
+  if (warp == 0) tmem_dealloc(tbase, LT_TCOLS);
 }
 
 int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, const int64_t* len, int n, int L,
@@ -347,7 +387,7 @@ int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, cons
     const bool h_part = k1 > LT_XP && k0 < LT_XP + p.h;
     if (x_part || h_part) ks_mask |= 1u << ks;
   }
-  const size_t smem = (size_t)4 * LT_AIMG + 4 * LT_HIMG + 2 * LT_XS * LT_XIMG + (size_t)4 * 32 * 64 * sizeof(float);
+  const size_t smem = (size_t)4 * LT_AIMG + 4 * LT_HIMG + 2 * LT_XS * LT_XIMG;
   CAIR_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((n + LT_NSEQ - 1) / LT_NSEQ, p.dirs);
   CAIR_LAUNCH(lstm_tc_kernel, grid, LT_THREADS, smem, s, x, p.wimg, bias, len, n, L, p.in, p.h, p.dirs, ks_mask, out,

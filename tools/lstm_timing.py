@@ -18,8 +18,8 @@ with torch.no_grad():
     net(q, ql, d, dl)
     torch.cuda.synchronize()
     L.cair_lstm_debug_timing(None)
-names = ['mma wait x_full', 'mma wait bar_h', 'mma issue+commit', 'epi(w0) wait bar_acc', 'epi(w0) phase 1',
-         'epi(w0) phase1 + named barrier', 'epi(w0) phase1+bar+phase 2', 'gather wait x_empty']
+names = ['mma wait x_full', 'mma wait bar_h', 'mma issue h part + commit', 'epi(w0) wait bar_acc',
+         'epi(w0) tmem ld + cell + h operand + arrive', 'epi(w0) same + memory-bank stores', '-', 'gather wait x_empty']
 print('(query encoder 20 steps + doc encoder 200 steps of CTA (0,0), cycles)')
 for n, v in zip(names, cnt.cpu().tolist()):
     print('%-40s %12d   per step %8.0f' % (n, v, v / 220))
