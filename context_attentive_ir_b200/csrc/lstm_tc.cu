@@ -37,10 +37,14 @@ constexpr uint32_t LT_BPLANE = LT_NSEQ * 16;
 constexpr uint32_t LT_AIMG = LT_PLANES * LT_APLANE;  // one (row tile, hi|lo) image: 28672 B
 constexpr uint32_t LT_BIMG = LT_PLANES * LT_BPLANE;  // one (hi|lo) image: 7168 B
 
-bool lstm_tc_supported(int in, int h) { return in >= 1 && in <= LT_XP && h >= 1 && h <= LT_HP; }
+// in < LT_XP: K slot `in` of the x part carries a constant 1 whose weight column is the bias (folded into the GEMM)
+bool lstm_tc_supported(int in, int h) { return in >= 1 && in < LT_XP && h >= 1 && h <= LT_HP; }
 
-// weight image [dir][row tile][hi|lo][plane][row][8 x bf16]; row = 32*q + 8*type + j  <->  gate row type*h + (32*tile + 8*q + j)
-__global__ void lstm_tc_pack_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, int in, int h,
+// weight image [dir][row tile][hi|lo][plane][row][8 x bf16]; row = 32*q + 8*type + j  <->  gate row type*h + (32*tile + 8*q + j).
+// Column `in` holds b_ih + b_hh (the x operand carries a constant 1 there), and every row is pre-scaled by -log2(e)
+// (-2 log2(e) for the cell gate g): the accumulator is directly the exp2 argument of e^-a / e^-2g in lt_cell.
+__global__ void lstm_tc_pack_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                                    const float* __restrict__ b_ih, const float* __restrict__ b_hh, int in, int h,
                                     uint8_t* __restrict__ img) {
   const int total = 2 * LT_PLANES * 128 * 8;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -51,10 +55,12 @@ __global__ void lstm_tc_pack_kernel(const float* __restrict__ w_ih, const float*
       const int grow = type * h + u;
       if (k < LT_XP) {
         if (k < in) v = w_ih[(size_t)grow * in + k];
+        else if (k == in) v = (b_ih ? b_ih[grow] : 0.f) + (b_hh ? b_hh[grow] : 0.f);
       } else if (k - LT_XP < h) {
         v = w_hh[(size_t)grow * h + (k - LT_XP)];
       }
     }
+    v *= (type == 2) ? -2.0f * 1.4426950408889634f : -1.4426950408889634f;
     __nv_bfloat16 hi, lo;
     split_bf16(v, hi, lo);
     const size_t off = (size_t)pl * LT_APLANE + (size_t)row * 16 + e * 2;
@@ -71,7 +77,7 @@ int32_t lstm_tc_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* 
   CAIR_CUDA(own.alloc(&out->wimg, (size_t)dirs * 4 * LT_AIMG));
   for (int d = 0; d < dirs; ++d) {
     const cair_lstm_dir* w = d ? rev : fwd;
-    CAIR_LAUNCH(lstm_tc_pack_kernel, 64, 256, 0, s, w->w_ih, w->w_hh, in, h, out->wimg + (size_t)d * 4 * LT_AIMG);
+    CAIR_LAUNCH(lstm_tc_pack_kernel, 64, 256, 0, s, w->w_ih, w->w_hh, w->b_ih, w->b_hh, in, h, out->wimg + (size_t)d * 4 * LT_AIMG);
   }
   return CAIR_OK;
 }
@@ -89,23 +95,31 @@ __device__ __forceinline__ void lt_tmem_ld_16x256b_x2(uint32_t taddr, float* v) 
                : "r"(taddr)
                : "memory");
 }
-// e^{-x} with the argument clamped to +-25 (sigmoid / tanh are saturated to fp32 rounding well before that; the clamp
-// keeps products of three (1 + e) terms finite).  ex2.approx: 2^-22 relative error.
-__device__ __forceinline__ float lt_expneg(float x) {
-  return exp2f(-1.4426950408889634f * fminf(fmaxf(x, -25.0f), 25.0f));
+// 2^t with t clamped from above at 42: products of three (1 + e) terms stay below 2^126, and sigmoid / tanh are
+// saturated to fp32 rounding long before.  ex2.approx: 2^-22 relative error; large negative t flushes to 0.
+__device__ __forceinline__ float lt_ex2(float t) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fminf(t, 42.0f)));
+  return r;
 }
-// One LSTM cell update with 5 exponentials and 2 reciprocals (instead of 5 + 5):
+__device__ __forceinline__ float lt_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// One LSTM cell update with 5 exponentials and 2 reciprocals (instead of 5 + 5).  Inputs are the exp2 arguments the
+// pre-scaled weights produce: ti = -log2e a_i, tf = -log2e a_f, tg = -2 log2e a_g, to = -log2e a_o.
 //   sigmoid(a) = 1/(1+ea),  tanh(b) = (1-eb)/(1+eb)  with  ea = e^-a, eb = e^-2b
 //   c' = sigmoid(f) c + sigmoid(i) tanh(g) = [c (1+ei)(1+eg) + (1-eg)(1+ef)] / [(1+ef)(1+ei)(1+eg)]
 //   h' = sigmoid(o) tanh(c')              = (1-ec) / [(1+eo)(1+ec)]
-__device__ __forceinline__ void lt_cell(float gi, float gf, float gg, float go, float c, float& c_new, float& h_new) {
-  const float ei = lt_expneg(gi), ef = lt_expneg(gf), eg = lt_expneg(2.0f * gg), eo = lt_expneg(go);
+__device__ __forceinline__ void lt_cell(float ti, float tf, float tg, float to, float c, float& c_new, float& h_new) {
+  const float ei = lt_ex2(ti), ef = lt_ex2(tf), eg = lt_ex2(tg), eo = lt_ex2(to);
   const float pi = 1.0f + ei, pf = 1.0f + ef, pg = 1.0f + eg;
   const float pig = pi * pg;
   const float num = fmaf(c, pig, (1.0f - eg) * pf);
-  c_new = __fdividef(num, pig * pf);
-  const float ec = lt_expneg(2.0f * c_new);
-  h_new = __fdividef(1.0f - ec, (1.0f + eo) * (1.0f + ec));
+  c_new = num * lt_rcp(pig * pf);
+  const float ec = lt_ex2(-2.0f * 1.4426950408889634f * c_new);
+  h_new = (1.0f - ec) * lt_rcp((1.0f + eo) * (1.0f + ec));
 }
 
 // Optional role timing (dbg != nullptr; CTA (0,0), lane 0 of the role's first warp), see tools/lstm_timing.py
@@ -132,10 +146,15 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int dir = blockIdx.y, s0 = blockIdx.x * LT_NSEQ;
   const int nmt = (h + 31) / 32;  // row tiles in use (1 or 2)
+  if (dbg && tid == 0 && blockIdx.x == 1 && blockIdx.y == 0) {  // whole-kernel cycles / ns of the un-instrumented CTA (1,0)
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    dbg[8] -= clock64(), dbg[9] -= (long long)ns;
+  }
   uint8_t* w_img = smraw;
   uint8_t* h_img = w_img + 4 * LT_AIMG;
   uint8_t* x_img = h_img + 4 * LT_HIMG;
-  const float* bias = bias_all + (size_t)dir * 4 * h;
+  (void)bias_all;  // folded into the weight image
   const int Hout = dirs * h;
 
   if (warp == 0) tmem_alloc(&tmem_slot, LT_TCOLS);
@@ -216,12 +235,17 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
             if (k4 * 4 + 3 < in) f4.w = src[k4 * 4 + 3];
           }
         }
+        if (k4 == (in >> 2)) {  // bias column: constant 1 at K slot `in`
+          const int e = in & 3;
+          f4.x = e == 0 ? 1.0f : f4.x, f4.y = e == 1 ? 1.0f : f4.y, f4.z = e == 2 ? 1.0f : f4.z, f4.w = e == 3 ? 1.0f : f4.w;
+        }
         v[4 * k4] = f4.x, v[4 * k4 + 1] = f4.y, v[4 * k4 + 2] = f4.z, v[4 * k4 + 3] = f4.w;
       }
+
       uint8_t* xh = x_img + (size_t)slot * 2 * LT_XIMG;
 #pragma unroll
       for (int pl = 0; pl < LT_XP / 8; ++pl) {
-        if (pl * 8 < in) {
+        if (pl * 8 <= in) {
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -250,6 +274,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     const uint64_t xd0 = smem_desc(smem_u32(x_img), LT_BPLANE, 128);
     // k-steps [ks_lo, ks_hi) of one step's GEMM into the accumulators of parity `par`; `fresh`: first MMA overwrites
     auto issue_part = [&](int par, uint64_t bdesc0, uint32_t bimg, int ks_lo, int ks_hi, int ks_sub, bool fresh) {
+      // (row tile outermost: interleaving the two accumulators between consecutive MMAs measured slower)
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         if (mt < nmt) {
@@ -272,6 +297,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
         }
       }
     };
+    long long ts_m[4] = {0, 0, 0, 0};
     if (maxlen > 0) {
       { LT_T0(); mbar_wait(&x_full[0], 0); LT_ACC(0); }
       tc_fence_after();
@@ -281,11 +307,13 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
       const int par = step & 1, slot = step % LT_XS;
       // h_{step-1} is in operand buffer `par`; the epilogue of step-1 has also finished reading accumulator par^1
       { LT_T0(); mbar_wait(&bar_h, par); LT_ACC(1); }
+      if (step == 100 || step == 101) ts_m[(step - 100) * 2] = clock64();
       tc_fence_after();
       LT_T0();
       issue_part(par, hd0 + (uint64_t)((uint32_t)par * 2 * LT_HIMG >> 4), LT_HIMG, LT_XP / 16, LT_K / 16, LT_XP / 16, false);
       mma_commit_w(&bar_acc, issue);
       mma_commit_w(&x_empty[slot], issue);
+      if (step == 100 || step == 101) ts_m[(step - 100) * 2 + 1] = clock64();
       LT_ACC(2);
       if (step + 1 < maxlen) {
         // x part of the next step, behind the h part in the tensor pipe: runs while the epilogue works
@@ -295,6 +323,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
         issue_part(par ^ 1, xd0 + (uint64_t)((uint32_t)nslot * 2 * LT_XIMG >> 4), LT_XIMG, 0, LT_XP / 16, 0, true);
       }
     }
+    if (dbg && lane == 0 && blockIdx.x == 1 && blockIdx.y == 0 && maxlen > 101)
+      for (int i = 0; i < 4; ++i) dbg[16 + i] = ts_m[i];
   } else {
     // ===================== epilogue warps =====================
     // warp -> (TMEM lane quarter q, row tile mt, half of the 32 sequences); lane -> (t0 = lane % 4, j = lane / 4):
@@ -303,8 +333,6 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     const int t0i = lane & 3, j = lane >> 2;
     const int u = mt * 32 + q * 8 + j;
     const bool uvalid = u < h && mt < nmt;
-    float bi = 0.f, bf = 0.f, bg = 0.f, bo = 0.f;
-    if (uvalid) bi = bias[u], bf = bias[h + u], bg = bias[2 * h + u], bo = bias[3 * h + u];
     int sl[4], lk[4];
     float cst[4], hst[4];
 #pragma unroll
@@ -315,10 +343,12 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     }
     const uint32_t tq = tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * LT_NSEQ + shalf * 16);
     const uint32_t hoff = (uint32_t)(u >> 3) * LT_BPLANE + (uint32_t)(u & 7) * 2;
+    long long ts_e[4] = {0, 0, 0, 0};
     if (lane == 0 && maxlen > 0) lt_arrive(&bar_h);   // h_0 = 0 is already in operand buffer 0
     for (int step = 0; step < maxlen; ++step) {
       const int par = step & 1;
       { LT_T0(); mbar_wait(&bar_acc, par); if (warp == 0) LT_ACC(3); }
+      if (step == 100) ts_e[0] = clock64();
       tc_fence_after();
       LT_T0();
       float hv[4];
@@ -328,13 +358,14 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
         lt_tmem_ld_16x256b_x2(ta, ga);
         lt_tmem_ld_16x256b_x2(ta + (16u << 16), gb);
         tmem_ld_wait();
+        if (step == 100) ts_e[1] = clock64();
         tc_fence_before();
         uint8_t* hn = h_img + (size_t)(par ^ 1) * 2 * LT_HIMG + hoff;  // next step's h operand
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int r = (c >> 1) * 4 + (c & 1);
           float cn, hn_v;
-          lt_cell(ga[r] + bi, ga[r + 2] + bf, gb[r] + bg, gb[r + 2] + bo, cst[c], cn, hn_v);
+          lt_cell(ga[r], ga[r + 2], gb[r], gb[r + 2], cst[c], cn, hn_v);
           const bool act = step < lk[c];
           cst[c] = act ? cn : cst[c];
           hst[c] = act ? hn_v : hst[c];
@@ -345,9 +376,11 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
           *reinterpret_cast<__nv_bfloat16*>(hn + LT_HIMG + sl[c] * 16) = lo;
         }
       }
+      if (step == 100) ts_e[2] = clock64();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0 && step + 1 < maxlen) lt_arrive(&bar_h);
+      if (step == 100) ts_e[3] = clock64();
       if (warp == 0) LT_ACC(4);
       // memory bank (fp32), off the critical path: 8 consecutive units x 4 sequences per warp store
       if (uvalid) {
@@ -361,6 +394,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
       }
       if (warp == 0) LT_ACC(5);
     }
+    if (dbg && lane == 0 && blockIdx.x == 1 && blockIdx.y == 0 && maxlen > 101)
+      for (int i = 0; i < 4; ++i) dbg[24 + warp * 4 + i] = ts_e[i];
     if (uvalid && (h_n || c_n)) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -373,6 +408,11 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
+  if (dbg && tid == 0 && blockIdx.x == 1 && blockIdx.y == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    dbg[8] += clock64(), dbg[9] += (long long)ns;
+  }
   if (warp == 0) tmem_dealloc(tbase, LT_TCOLS);
 }
 
@@ -383,7 +423,7 @@ int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, cons
   uint32_t ks_mask = 0;
   for (int ks = 0; ks < LT_K / 16; ++ks) {
     const int k0 = 16 * ks, k1 = k0 + 16;
-    const bool x_part = k0 < p.in;
+    const bool x_part = k0 < p.in + 1;  // + the bias column
     const bool h_part = k1 > LT_XP && k0 < LT_XP + p.h;
     if (x_part || h_part) ks_mask |= 1u << ks;
   }
