@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
                    float* __restrict__ out, float* __restrict__ h_n, float* __restrict__ c_n, int* err,
                    long long* __restrict__ dbg) {
   extern __shared__ __align__(128) uint8_t smraw[];
-  __shared__ uint64_t bar_w, bar_h, bar_acc, x_full[LT_XS], x_empty[LT_XS];
+  __shared__ uint64_t bar_w, bar_h[2], bar_acc[2], x_full[LT_XS], x_empty[LT_XS];
   __shared__ uint32_t tmem_slot;
   __shared__ int slen[LT_NSEQ];
   __shared__ int smaxlen;
@@ -160,8 +160,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
   if (warp == 0) tmem_alloc(&tmem_slot, LT_TCOLS);
   if (tid == 32) {
     mbar_init(&bar_w, 1);
-    mbar_init(&bar_h, LT_EPI_WARPS);  // epilogue warps: h_t written as next step's operand
-    mbar_init(&bar_acc, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_h[i], LT_EPI_WARPS / 2);  // epilogue warps of row tile i: their 32 units of h_t are in place
+      mbar_init(&bar_acc[i], 1);               // accumulator of row tile i is complete
+    }
     for (int i = 0; i < LT_XS; ++i) {
       mbar_init(&x_full[i], 1);
       mbar_init(&x_empty[i], 1);
@@ -273,11 +275,12 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     const uint64_t hd0 = smem_desc(smem_u32(h_img), LT_BPLANE, 128);
     const uint64_t xd0 = smem_desc(smem_u32(x_img), LT_BPLANE, 128);
     // k-steps [ks_lo, ks_hi) of one step's GEMM into the accumulators of parity `par`; `fresh`: first MMA overwrites
-    auto issue_part = [&](int par, uint64_t bdesc0, uint32_t bimg, int ks_lo, int ks_hi, int ks_sub, bool fresh) {
+    auto issue_part = [&](int par, uint64_t bdesc0, uint32_t bimg, int ks_lo, int ks_hi, int ks_sub, bool fresh,
+                          int mt_lo, int mt_hi) {
       // (row tile outermost: interleaving the two accumulators between consecutive MMAs measured slower)
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        if (mt < nmt) {
+        if (mt < nmt && mt >= mt_lo && mt < mt_hi) {
           const uint64_t wdm = wd0 + (uint64_t)((uint32_t)mt * 2 * LT_AIMG >> 4);
           const uint32_t tacc = tbase + (uint32_t)(par * 2 + mt) * LT_NSEQ;
           uint32_t acc = fresh ? 0u : 1u;
@@ -301,17 +304,29 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     if (maxlen > 0) {
       { LT_T0(); mbar_wait(&x_full[0], 0); LT_ACC(0); }
       tc_fence_after();
-      issue_part(0, xd0, LT_XIMG, 0, LT_XP / 16, 0, true);
+      issue_part(0, xd0, LT_XIMG, 0, LT_XP / 16, 0, true, 0, 2);
     }
     for (int step = 0; step < maxlen; ++step) {
       const int par = step & 1, slot = step % LT_XS;
-      // h_{step-1} is in operand buffer `par`; the epilogue of step-1 has also finished reading accumulator par^1
-      { LT_T0(); mbar_wait(&bar_h, par); LT_ACC(1); }
+      // The h part is software-pipelined against the previous step's epilogue.  K half kh of h_{step-1} (units
+      // 32 kh .. 32 kh + 31) is produced by the epilogue warps of row tile kh, which signal bar_h[kh]: the K-half-0
+      // MMAs of BOTH row tiles go out as soon as the tile-0 warps are done (the tile-1 warps are still in their cell
+      // update); after bar_h[1] only the K-half-1 MMAs remain, tile 0 first with its own commit, so the tile-0 warps
+      // start this step's epilogue while the tile-1 MMAs still run.  Both waits together also guarantee that the
+      // epilogue of step-1 has finished reading accumulator par^1 (re-used by the x part below).
+      const uint64_t hdp = hd0 + (uint64_t)((uint32_t)par * 2 * LT_HIMG >> 4);
+      constexpr int KH0 = LT_XP / 16, KH1 = LT_XP / 16 + LT_HP / 32, KH2 = LT_K / 16;
+      { LT_T0(); mbar_wait(&bar_h[0], par); LT_ACC(1); }
       if (step == 100 || step == 101) ts_m[(step - 100) * 2] = clock64();
       tc_fence_after();
       LT_T0();
-      issue_part(par, hd0 + (uint64_t)((uint32_t)par * 2 * LT_HIMG >> 4), LT_HIMG, LT_XP / 16, LT_K / 16, LT_XP / 16, false);
-      mma_commit_w(&bar_acc, issue);
+      issue_part(par, hdp, LT_HIMG, KH0, KH1, KH0, false, 0, 2);
+      mbar_wait(&bar_h[1], par);
+      tc_fence_after();
+      issue_part(par, hdp, LT_HIMG, KH1, KH2, KH0, false, 0, 1);
+      mma_commit_w(&bar_acc[0], issue);
+      issue_part(par, hdp, LT_HIMG, KH1, KH2, KH0, false, 1, 2);
+      mma_commit_w(&bar_acc[1], issue);
       mma_commit_w(&x_empty[slot], issue);
       if (step == 100 || step == 101) ts_m[(step - 100) * 2 + 1] = clock64();
       LT_ACC(2);
@@ -320,7 +335,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
         const int nslot = (step + 1) % LT_XS;
         { LT_T0(); mbar_wait(&x_full[nslot], ((step + 1) / LT_XS) & 1); LT_ACC(0); }
         tc_fence_after();
-        issue_part(par ^ 1, xd0 + (uint64_t)((uint32_t)nslot * 2 * LT_XIMG >> 4), LT_XIMG, 0, LT_XP / 16, 0, true);
+        issue_part(par ^ 1, xd0 + (uint64_t)((uint32_t)nslot * 2 * LT_XIMG >> 4), LT_XIMG, 0, LT_XP / 16, 0, true, 0, 2);
       }
     }
     if (dbg && lane == 0 && blockIdx.x == 1 && blockIdx.y == 0 && maxlen > 101)
@@ -344,10 +359,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     const uint32_t tq = tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * LT_NSEQ + shalf * 16);
     const uint32_t hoff = (uint32_t)(u >> 3) * LT_BPLANE + (uint32_t)(u & 7) * 2;
     long long ts_e[4] = {0, 0, 0, 0};
-    if (lane == 0 && maxlen > 0) lt_arrive(&bar_h);   // h_0 = 0 is already in operand buffer 0
+    if (lane == 0 && maxlen > 0) lt_arrive(&bar_h[mt]);   // h_0 = 0 is already in operand buffer 0
     for (int step = 0; step < maxlen; ++step) {
       const int par = step & 1;
-      { LT_T0(); mbar_wait(&bar_acc, par); if (warp == 0) LT_ACC(3); }
+      { LT_T0(); mbar_wait(&bar_acc[mt], par); if (warp == 0) LT_ACC(3); }
       if (step == 100) ts_e[0] = clock64();
       tc_fence_after();
       LT_T0();
@@ -379,7 +394,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
       if (step == 100) ts_e[2] = clock64();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0 && step + 1 < maxlen) lt_arrive(&bar_h);
+      if (lane == 0 && step + 1 < maxlen) lt_arrive(&bar_h[mt]);
       if (step == 100) ts_e[3] = clock64();
       if (warp == 0) LT_ACC(4);
       // memory bank (fp32), off the critical path: 8 consecutive units x 4 sequences per warp store
