@@ -135,7 +135,7 @@ constexpr uint32_t LT_TCOLS = 4 * LT_NSEQ;                 // TMEM columns: 2 pa
 // TMEM: [2 step parities][2 row tiles][32 sequences] fp32 columns
 __global__ void __launch_bounds__(LT_THREADS, 1)
     lstm_tc_kernel(GemmA x, const uint8_t* __restrict__ wimg_all, const float* __restrict__ bias_all,
-                   const int64_t* __restrict__ len, int n, int L, int in, int h, int dirs, uint32_t ks_mask,
+                   const int64_t* __restrict__ len, int n, int L, int in, int h, int dirs, uint32_t ks_mask, int spc,
                    float* __restrict__ out, float* __restrict__ h_n, float* __restrict__ c_n, int* err,
                    long long* __restrict__ dbg) {
   extern __shared__ __align__(128) uint8_t smraw[];
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
   __shared__ int slen[LT_NSEQ];
   __shared__ int smaxlen;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int dir = blockIdx.y, s0 = blockIdx.x * LT_NSEQ;
+  const int dir = blockIdx.y, s0 = blockIdx.x * spc;  // spc <= LT_NSEQ sequences per CTA; MMA columns beyond stay empty
   const int nmt = (h + 31) / 32;  // row tiles in use (1 or 2)
   if (dbg && tid == 0 && blockIdx.x == 1 && blockIdx.y == 0) {  // whole-kernel cycles / ns of the un-instrumented CTA (1,0)
     unsigned long long ns;
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
   }
   if (tid < LT_NSEQ) {
     int s = s0 + tid, l = 0;
-    if (s < n) {
+    if (s < n && tid < spc) {
       int64_t ll = len[s];
       if (ll < 1 || ll > L) {
         atomicOr(err, ERRF_BAD_LENGTH);
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     for (uint32_t o = 0; o < bytes; o += LT_AIMG) bulk_g2s(w_img + o, src + o, LT_AIMG, &bar_w);
   }
   // zero the pad rows of the memory bank (this direction's half)
-  for (int s = 0; s < LT_NSEQ; ++s) {
+  for (int s = 0; s < spc; ++s) {
     if (s0 + s >= n) break;
     const int npad = (L - slen[s]) * h;
     float* o = out + ((size_t)(s0 + s) * L + slen[s]) * Hout + dir * h;
@@ -348,6 +348,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     const int t0i = lane & 3, j = lane >> 2;
     const int u = mt * 32 + q * 8 + j;
     const bool uvalid = u < h && mt < nmt;
+    // column groups of 8 sequences beyond spc are empty: skip their cells (warp-uniform)
+    const bool do01 = shalf * 16 < spc, do23 = shalf * 16 + 8 < spc;
     int sl[4], lk[4];
     float cst[4], hst[4];
 #pragma unroll
@@ -366,8 +368,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
       if (step == 100) ts_e[0] = clock64();
       tc_fence_after();
       LT_T0();
-      float hv[4];
-      if (mt < nmt) {
+      float hv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (mt < nmt && do01) {
         float ga[8], gb[8];  // ga: gates i (0,1,4,5) and f (2,3,6,7); gb: g and o
         const uint32_t ta = tq + (uint32_t)(par * 2 * LT_NSEQ);
         lt_tmem_ld_16x256b_x2(ta, ga);
@@ -378,6 +380,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
         uint8_t* hn = h_img + (size_t)(par ^ 1) * 2 * LT_HIMG + hoff;  // next step's h operand
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+          if (c >= 2 && !do23) continue;
           const int r = (c >> 1) * 4 + (c & 1);
           float cn, hn_v;
           lt_cell(ga[r], ga[r + 2], gb[r], gb[r + 2], cst[c], cn, hn_v);
@@ -415,7 +418,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int s = sl[c];
-        if (s0 + s >= n) continue;
+        if (s0 + s >= n || s >= spc) continue;
         if (h_n) h_n[((size_t)dir * n + s0 + s) * h + u] = hst[c];
         if (c_n) c_n[((size_t)dir * n + s0 + s) * h + u] = cst[c];
       }
@@ -444,8 +447,16 @@ int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, cons
   }
   const size_t smem = (size_t)4 * LT_AIMG + 4 * LT_HIMG + 2 * LT_XS * LT_XIMG;
   CAIR_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((n + LT_NSEQ - 1) / LT_NSEQ, p.dirs);
-  CAIR_LAUNCH(lstm_tc_kernel, grid, LT_THREADS, smem, s, x, p.wimg, bias, len, n, L, p.in, p.h, p.dirs, ks_mask, out,
+  // Sequences per CTA: the per-step cost is latency + the cell updates of one SM (MUFU / issue bound), not the MMAs
+  // (an N = 32 MMA costs the same as a narrower one), so use the fewest sequences per CTA that still fit one wave.
+  int spc = LT_NSEQ;
+  for (int c = 8; c < LT_NSEQ; c += 8)
+    if ((int64_t)((n + c - 1) / c) * p.dirs <= kSMs) {
+      spc = c;
+      break;
+    }
+  dim3 grid((n + spc - 1) / spc, p.dirs);
+  CAIR_LAUNCH(lstm_tc_kernel, grid, LT_THREADS, smem, s, x, p.wimg, bias, len, n, L, p.in, p.h, p.dirs, ks_mask, spc, out,
               h_n, c_n, err, g_lstm_dbg);
   return CAIR_OK;
 }
