@@ -266,7 +266,12 @@ bool lstm_tc_supported(int in, int h);
 int32_t lstm_tc_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, int in, int h, LstmTcPack* out,
                      cudaStream_t s);
 // bias: [dirs][4h] = b_ih + b_hh (LstmPack::bias)
+// ximg (optional, gathered x only): the table pre-split into x-operand rows by lstm_tc_pack_table - the gather warps
+// then copy 16-byte units instead of converting fp32 rows on every step.
 int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, const int64_t* len, int n, int L,
-                    float* out, float* h_n, float* c_n, int* err, cudaStream_t s, const char* rec_name);
+                    float* out, float* h_n, float* c_n, int* err, cudaStream_t s, const char* rec_name,
+                    const uint8_t* ximg = nullptr);
+// table [V, in] fp32 -> image [V][hi|lo][48 x bf16] (constant 1 in K slot `in` = the bias column, zero padding)
+int32_t lstm_tc_pack_table(Owned& own, const float* table, int V, int in, uint8_t** img, cudaStream_t s);
 
 }  // namespace cair

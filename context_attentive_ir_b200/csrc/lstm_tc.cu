@@ -31,7 +31,14 @@ constexpr int LT_PLANES = LT_K / 8;       // 14
 constexpr int LT_NSEQ = 32;               // sequences per CTA = N of the MMA
 constexpr int LT_EPI_WARPS = 16;          // epilogue warps (4 per SM sub-partition)
 constexpr int LT_XS = 4;                   // x-operand ring slots = gather warps (warp g fills slot g for steps = g mod 4)
-constexpr int LT_THREADS = (LT_EPI_WARPS + 1 + LT_XS) * 32;
+// Auxiliary warps are placed so that no SM sub-partition (warp % 4) carries both the MMA issuer and a gather warp on
+// top of its four epilogue warps: warp 17 = issuer, warps 18, 19, 22, 23 = gather slots 0..3; warps 16, 20, 21 idle.
+constexpr int LT_WARPS = 24;
+constexpr int LT_MMA_WARP = 17;
+constexpr int LT_THREADS = LT_WARPS * 32;
+__device__ __forceinline__ int lt_gather_slot(int warp) {
+  return warp == 18 ? 0 : warp == 19 ? 1 : warp == 22 ? 2 : warp == 23 ? 3 : -1;
+}
 constexpr uint32_t LT_APLANE = 128 * 16;  // weight image: 128 rows per plane
 constexpr uint32_t LT_BPLANE = LT_NSEQ * 16;
 constexpr uint32_t LT_AIMG = LT_PLANES * LT_APLANE;  // one (row tile, hi|lo) image: 28672 B
@@ -79,6 +86,27 @@ int32_t lstm_tc_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* 
     const cair_lstm_dir* w = d ? rev : fwd;
     CAIR_LAUNCH(lstm_tc_pack_kernel, 64, 256, 0, s, w->w_ih, w->w_hh, w->b_ih, w->b_hh, in, h, out->wimg + (size_t)d * 4 * LT_AIMG);
   }
+  return CAIR_OK;
+}
+
+// x-operand rows of a gathered table: row v = [hi: LT_XP bf16][lo: LT_XP bf16] (192 B), K slot `in` = 1 (bias column).
+__global__ void lstm_tc_pack_table_kernel(const float* __restrict__ table, int V, int in, uint8_t* __restrict__ img) {
+  const int64_t total = (int64_t)V * LT_XP;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = idx / LT_XP;
+    const int k = (int)(idx - v * LT_XP);
+    const float x = k < in ? table[v * in + k] : (k == in ? 1.0f : 0.f);
+    __nv_bfloat16 hi, lo;
+    split_bf16(x, hi, lo);
+    __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(img + v * (2 * LT_XP * 2));
+    row[k] = hi;
+    row[LT_XP + k] = lo;
+  }
+}
+
+int32_t lstm_tc_pack_table(Owned& own, const float* table, int V, int in, uint8_t** img, cudaStream_t s) {
+  CAIR_CUDA(own.alloc(img, (size_t)V * 2 * LT_XP * 2));
+  CAIR_LAUNCH(lstm_tc_pack_table_kernel, 1184, 256, 0, s, table, V, in, *img);
   return CAIR_OK;
 }
 
@@ -137,7 +165,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     lstm_tc_kernel(GemmA x, const uint8_t* __restrict__ wimg_all, const float* __restrict__ bias_all,
                    const int64_t* __restrict__ len, int n, int L, int in, int h, int dirs, uint32_t ks_mask, int spc,
                    float* __restrict__ out, float* __restrict__ h_n, float* __restrict__ c_n, int* err,
-                   long long* __restrict__ dbg) {
+                   long long* __restrict__ dbg, const uint8_t* __restrict__ ximg) {
   extern __shared__ __align__(128) uint8_t smraw[];
   __shared__ uint64_t bar_w, bar_h[2], bar_acc[2], x_full[LT_XS], x_empty[LT_XS];
   __shared__ uint32_t tmem_slot;
@@ -210,17 +238,42 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
   const int maxlen = smaxlen;
   const uint32_t tbase = tmem_slot;
 
-  if (warp > LT_EPI_WARPS) {
+  if (lt_gather_slot(warp) >= 0) {
     // ===================== x gather: embedding rows (or dense rows) -> hi/lo bf16 ring =====================
     // One warp per ring slot: each has LT_XS step times to cover its id -> row -> convert latency chain.
     const int myl = slen[lane];   // lane <-> sequence row
     const bool vec = (in & 3) == 0 && (x.table ? ((x.E & 3) == 0) : ((x.lda & 3) == 0));
-    const int slot = warp - LT_EPI_WARPS - 1;
+    const int slot = lt_gather_slot(warp);
     for (int step = slot; step < maxlen; step += LT_XS) {
       { LT_T0(); mbar_wait_relaxed(&x_empty[slot], ((step / LT_XS) & 1) ^ 1); LT_ACC(7); }
       const bool active = step < myl;
       const int t = dir ? myl - 1 - step : step;
       const int64_t r = (int64_t)(s0 + lane) * L + (active ? t : 0);
+      if (ximg) {
+        // pre-split table: 12 x 16-byte units per token, no conversion (keeps the gather off the issue slots the
+        // epilogue warps of this SM sub-partition need)
+        uint4 u[2 * (LT_XP / 8)];
+        if (active) {
+          const uint4* srow = reinterpret_cast<const uint4*>(ximg + checked_id(x.ids[r], x.V, x.err) * (2 * LT_XP * 2));
+#pragma unroll
+          for (int i = 0; i < 2 * (LT_XP / 8); ++i) u[i] = __ldg(srow + i);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 2 * (LT_XP / 8); ++i) u[i] = make_uint4(0, 0, 0, 0);
+        }
+        uint8_t* xh = x_img + (size_t)slot * 2 * LT_XIMG + (size_t)lane * 16;
+#pragma unroll
+        for (int pl = 0; pl < LT_XP / 8; ++pl) {
+          if (pl * 8 <= in) {
+            *reinterpret_cast<uint4*>(xh + (size_t)pl * LT_BPLANE) = u[pl];
+            *reinterpret_cast<uint4*>(xh + LT_XIMG + (size_t)pl * LT_BPLANE) = u[LT_XP / 8 + pl];
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) lt_arrive(&x_full[slot]);
+        continue;
+      }
       const float* src = nullptr;
       if (active) src = x.table ? x.table + checked_id(x.ids[r], x.V, x.err) * x.E : x.dense + r * x.lda;
       float v[LT_XP];
@@ -266,7 +319,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
       __syncwarp();
       if (lane == 0) lt_arrive(&x_full[slot]);
     }
-  } else if (warp == LT_EPI_WARPS) {
+  } else if (warp == LT_MMA_WARP) {
     // ===================== MMA issuer (uniform control flow, one elected lane issues) =====================
     mbar_wait(&bar_w, 0);
     const uint32_t issue = elect_one();
@@ -340,7 +393,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     }
     if (dbg && lane == 0 && blockIdx.x == 1 && blockIdx.y == 0 && maxlen > 101)
       for (int i = 0; i < 4; ++i) dbg[16 + i] = ts_m[i];
-  } else {
+  } else if (warp < LT_EPI_WARPS) {
     // ===================== epilogue warps =====================
     // warp -> (TMEM lane quarter q, row tile mt, half of the 32 sequences); lane -> (t0 = lane % 4, j = lane / 4):
     // unit u = 32 mt + 8 q + j, sequences sl[c] = 16 shalf + {2 t0, 2 t0 + 1, 8 + 2 t0, 9 + 2 t0}
@@ -435,7 +488,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
 }
 
 int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, const int64_t* len, int n, int L,
-                    float* out, float* h_n, float* c_n, int* err, cudaStream_t s, const char* rec_name) {
+                    float* out, float* h_n, float* c_n, int* err, cudaStream_t s, const char* rec_name, const uint8_t* ximg) {
   if (n <= 0) return CAIR_OK;
   if (rec_name) prof_mark(rec_name, s);
   uint32_t ks_mask = 0;
@@ -457,7 +510,7 @@ int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, cons
     }
   dim3 grid((n + spc - 1) / spc, p.dirs);
   CAIR_LAUNCH(lstm_tc_kernel, grid, LT_THREADS, smem, s, x, p.wimg, bias, len, n, L, p.in, p.h, p.dirs, ks_mask, spc, out,
-              h_n, c_n, err, g_lstm_dbg);
+              h_n, c_n, err, g_lstm_dbg, x.table ? ximg : nullptr);
   return CAIR_OK;
 }
 

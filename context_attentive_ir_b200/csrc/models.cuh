@@ -68,6 +68,7 @@ struct MtState {
   float* folded = nullptr;  // [V, F] = table W_p^T + b_p  (eval-mode fold of mtensor.py:77-90)
   LstmPack enc_q{}, enc_d{};
   LstmTcPack tc_q{}, tc_d{};  // tensor-core encoders (valid when lstm_tc_supported)
+  uint8_t* folded_img = nullptr;  // folded table pre-split into hi/lo bf16 x-operand rows (lstm_tc_pack_table)
   float *wq = nullptr, *bq = nullptr, *wd = nullptr, *bd = nullptr;  // channel projections
   uint8_t* wd_img = nullptr;  // hi/lo operand image of the doc projection (fused projection + A image kernel)
   MtPack pack{};

@@ -280,6 +280,7 @@ int32_t mt_create_state(Owned& own, const cair_mt_weights& w, MtState* st, cudaS
     CAIR_TRY(lstm_tc_pack(own, &w.query_fwd, dirs == 2 ? &w.query_rev : nullptr, w.featsize, w.nhid_query / dirs, &st->tc_q, s));
   if (lstm && lstm_tc_supported(w.featsize, w.nhid_doc / dirs))
     CAIR_TRY(lstm_tc_pack(own, &w.doc_fwd, dirs == 2 ? &w.doc_rev : nullptr, w.featsize, w.nhid_doc / dirs, &st->tc_d, s));
+  if (st->tc_q.wimg || st->tc_d.wimg) CAIR_TRY(lstm_tc_pack_table(own, st->folded, w.vocab, w.featsize, &st->folded_img, s));
   CAIR_TRY(dev_copy(own, w.query_projection.w, (size_t)w.nchannels * w.nhid_query, &st->wq, s));
   CAIR_TRY(dev_copy(own, w.query_projection.b, (size_t)w.nchannels, &st->bq, s));
   CAIR_TRY(dev_copy(own, w.document_projection.w, (size_t)w.nchannels * w.nhid_doc, &st->wd, s));
@@ -335,7 +336,7 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
   // ---- query side: embedding + projection (folded table) -> BiLSTM (:77-94) -> channel projection (:99) ----
   if (tc_q)
     CAIR_TRY(lstm_tc_run(st.tc_q, st.enc_q.bias, gemm_gather(st.folded, st.V, st.F, qs, 1, 1, 1, err), qlen + qb, (int)nq,
-                         Lq, enc_q, nullptr, nullptr, err, sq, st.side ? nullptr : "query_recurrence"));
+                         Lq, enc_q, nullptr, nullptr, err, sq, st.side ? nullptr : "query_recurrence", st.folded_img));
   else
     CAIR_TRY(lstm_run(st.enc_q, gemm_gather(st.folded, st.V, st.F, qs, 1, 1, 1, err), qlen + qb, (int)nq, Lq, enc_q,
                       nullptr, nullptr, pre_q, err, sq, st.side ? nullptr : "query_recurrence"));
@@ -348,7 +349,7 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
   // ---- document side ----
   if (tc_d)
     CAIR_TRY(lstm_tc_run(st.tc_d, st.enc_d.bias, gemm_gather(st.folded, st.V, st.F, ds, 1, 1, 1, err), dlen + pb, (int)pc,
-                         Ld, enc_d, nullptr, nullptr, err, s, "doc_recurrence"));
+                         Ld, enc_d, nullptr, nullptr, err, s, "doc_recurrence", st.folded_img));
   else
     CAIR_TRY(lstm_run(st.enc_d, gemm_gather(st.folded, st.V, st.F, ds, 1, 1, 1, err), dlen + pb, (int)pc, Ld, enc_d,
                       nullptr, nullptr, pre_d, err, s, "doc_recurrence"));
