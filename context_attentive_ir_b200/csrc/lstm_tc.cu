@@ -405,12 +405,15 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     const bool do01 = shalf * 16 < spc, do23 = shalf * 16 + 8 < spc;
     int sl[4], lk[4];
     float cst[4], hst[4];
+    float* optr[4];   // memory-bank position of this step's h for each cell, advanced by one time step per step
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       sl[c] = shalf * 16 + (c >> 1) * 8 + 2 * t0i + (c & 1);
       lk[c] = slen[sl[c]];
       cst[c] = 0.f, hst[c] = 0.f;
+      optr[c] = out + ((size_t)(s0 + sl[c]) * L + (dir ? max(lk[c] - 1, 0) : 0)) * Hout + dir * h + u;
     }
+    const ptrdiff_t ostep = dir ? -(ptrdiff_t)Hout : (ptrdiff_t)Hout;
     const uint32_t tq = tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * LT_NSEQ + shalf * 16);
     const uint32_t hoff = (uint32_t)(u >> 3) * LT_BPLANE + (uint32_t)(u & 7) * 2;
     long long ts_e[4] = {0, 0, 0, 0};
@@ -457,10 +460,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
       if (uvalid) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          if (step < lk[c]) {
-            const int t = dir ? lk[c] - 1 - step : step;
-            out[((size_t)(s0 + sl[c]) * L + t) * Hout + dir * h + u] = hv[c];
-          }
+          if (step < lk[c]) *optr[c] = hv[c];
+          optr[c] += ostep;
         }
       }
       if (warp == 0) LT_ACC(5);
