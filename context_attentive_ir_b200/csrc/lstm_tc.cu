@@ -444,10 +444,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
           cst[c] = act ? cn : cst[c];
           hst[c] = act ? hn_v : hst[c];
           hv[c] = hn_v;
-          __nv_bfloat16 hi, lo;
-          split_bf16(hst[c], hi, lo);
-          *reinterpret_cast<__nv_bfloat16*>(hn + sl[c] * 16) = hi;
-          *reinterpret_cast<__nv_bfloat16*>(hn + LT_HIMG + sl[c] * 16) = lo;
+          uint32_t hi, lo;
+          split_bf16_alu(hst[c], hi, lo);
+          *reinterpret_cast<uint16_t*>(hn + sl[c] * 16) = (uint16_t)hi;
+          *reinterpret_cast<uint16_t*>(hn + LT_HIMG + sl[c] * 16) = (uint16_t)lo;
         }
       }
       if (step == 100) ts_e[2] = clock64();

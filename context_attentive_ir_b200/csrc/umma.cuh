@@ -198,6 +198,14 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
+// Same split with both conversions on the ALU pipe (F2FP.PACK_AB) instead of one F2F on the quarter-rate XU/MUFU
+// pipe - for kernels whose MUFU pipe is the bottleneck.  Results in the low 16 bits of hi / lo.
+__device__ __forceinline__ void split_bf16_alu(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(0.f), "f"(x));
+  const float r = x - __uint_as_float(hi << 16);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(0.f), "f"(r));
+}
+
 // Two values at once: hi/lo come back as packed bf16x2 words (a in the low half), 6 instructions per pair.
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
