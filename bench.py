@@ -220,20 +220,45 @@ def run_product(args):
     ms_per_step = total_ms / args.steps
     value = pairs_total / (ms_per_step / 1e3)
 
-    # ---- end-to-end: host ids -> H2D -> score -> D2H scores through the C-ABI host entry point ----
-    for _ in range(2):
+    # ---- end-to-end: host ids -> H2D -> score -> D2H scores through the C-ABI host entry points ----
+    # A serving loop over two staging slots (submit_host / wait_host): every step copies its ids from pinned host
+    # memory, scores them and copies the scores back; the copies of step k+1 overlap the kernels of step k.  The L2
+    # flush of every step runs on the compute stream INSIDE the timed region (it costs ~40 us per step).
+    houts = [torch.empty(B, N, dtype=torch.float32).pin_memory() for _ in range(2)]
+    cstream = torch.cuda.Stream(dev)
+
+    def e2e_loop(k):
+        with torch.cuda.stream(cstream):
+            for i in range(k):
+                if i >= 2:
+                    net.wait_host(i & 1)
+                flush.fill_(i & 0xff)
+                net.submit_host(hq, hql, hd, hdl, out=houts[i & 1], slot=i & 1, device=dev, stream=cstream)
+            for i in range(max(0, k - 2), k):
+                net.wait_host(i & 1)
+
+    e2e_loop(4)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e2e_loop(args.steps)
+    e2e_total = time.perf_counter() - t0
+    # the synchronous single-call form (forward_host: one cached CUDA graph per call, returns after the D2H)
+    for _ in range(3):
         net.forward_host(hq, hql, hd, hdl, out=hout, device=dev)
-    e2e_t = []
+    sync_t = []
     for i in range(args.steps):
         flush.fill_(i & 0xff)
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        net.forward_host(hq, hql, hd, hdl, out=hout, device=dev)  # synchronises before returning
-        e2e_t.append(time.perf_counter() - t0)
-    e = torch.tensor([sum(e2e_t)], dtype=torch.float64, device=dev)
+        t1 = time.perf_counter()
+        net.forward_host(hq, hql, hd, hdl, out=hout, device=dev)
+        sync_t.append(time.perf_counter() - t1)
+    e = torch.tensor([e2e_total, sum(sync_t)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e, op=dist.ReduceOp.MAX)
-    e2e_value = pairs_total / (float(e.item()) / args.steps)
+    e2e_value = pairs_total / (float(e[0].item()) / args.steps)
+    e2e_sync_value = pairs_total / (float(e[1].item()) / args.steps)
     h2d = (hq.numel() + hql.numel() + hd.numel() + hdl.numel()) * 8 * world
     d2h = hout.numel() * 4 * world
     if rank == 0:
@@ -297,7 +322,11 @@ def run_product(args):
                        'parallelism': 'doc-parallel x%d, one all-gather of scores' % world,
                        'l2': 'flushed between steps (256 MiB fill outside the per-step events)',
                        'table': 'eval-mode folded [V,40] fp32 table (built once at handle creation)'},
-            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'api': 'submit_host/wait_host over 2 staging slots (H2D of step k+1 overlaps the kernels of step k); '
+                           'L2 flush inside the timed region',
+                    'single_call_value': e2e_sync_value,
+                    'single_call_api': 'forward_host: H2D + kernels + D2H as one cached CUDA graph, synchronous'},
             'gpu_launches': int(launches), 'clocks': sampler.summary(),
             'roofline': roof, 'stages_ms': stages,
             'flops_per_pair_mflop': fl, 'hbm_bytes_per_pair': bytes_per_pair_folded(),

@@ -59,6 +59,15 @@ struct cair_handle {
   cudaStream_t host_stream = nullptr;
   cudaEvent_t host_ev = nullptr;
   int* host_err = nullptr;  // pinned
+  // pipelined host path (cair_ranker_submit_host / cair_ranker_wait_host): two staging slots
+  struct PipeSlot {
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+    cudaEvent_t ev_in = nullptr, ev_done = nullptr;
+    int* err = nullptr;  // pinned
+    bool busy = false;
+  } pipe[2];
+  cudaStream_t copy_stream = nullptr;
 };
 
 namespace {
@@ -134,6 +143,13 @@ int32_t cair_destroy(cair_handle* h) {
   if (h->host_stream) cudaStreamDestroy(h->host_stream);
   if (h->host_ev) cudaEventDestroy(h->host_ev);
   if (h->host_err) cudaFreeHost(h->host_err);
+  for (auto& p : h->pipe) {
+    if (p.stage) cudaFree(p.stage);
+    if (p.ev_in) cudaEventDestroy(p.ev_in);
+    if (p.ev_done) cudaEventDestroy(p.ev_done);
+    if (p.err) cudaFreeHost(p.err);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
   return CAIR_OK;
 }
@@ -545,6 +561,86 @@ int32_t cair_ranker_forward_host(cair_handle* h, const int64_t* q, const int64_t
     if (flags & ERRF_BAD_TOKEN) return fail(CAIR_ERR_BAD_ARG, "token id outside [0, vocab)");
     return fail(CAIR_ERR_BAD_ARG, "sequence length outside [1, padded length]");
   }
+  return CAIR_OK;
+}
+
+int32_t cair_ranker_submit_host(cair_handle* h, const int64_t* q, const int64_t* qlen, const int64_t* d,
+                                const int64_t* dlen, int32_t B, int32_t N, int32_t Lq, int32_t Ld, float* scores,
+                                int32_t slot, void* stream) {
+  CAIR_TRY(check_ranker_args(h, B, N, Lq, Ld));
+  if (!q || !qlen || !d || !dlen || !scores) return fail(CAIR_ERR_BAD_ARG, "ranker_submit_host: null tensor");
+  if (slot < 0 || slot > 1) return fail(CAIR_ERR_BAD_ARG, "ranker_submit_host: slot must be 0 or 1");
+  DeviceGuard g(h->device);
+  cair_handle::PipeSlot& p = h->pipe[slot];
+  if (p.busy) return fail(CAIR_ERR_BAD_ARG, "ranker_submit_host: slot %d submitted again before its wait", slot);
+  const size_t nq = (size_t)B * Lq, nd = (size_t)B * N * Ld, nb = (size_t)B, nbn = (size_t)B * N;
+  const size_t in_bytes = (nq + nb + nd + nbn) * sizeof(int64_t);
+  const size_t need = align_up(in_bytes) + align_up(nbn * sizeof(float));
+  if (!h->host_stream) {
+    CAIR_CUDA(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+    CAIR_CUDA(cudaEventCreateWithFlags(&h->host_ev, cudaEventDisableTiming));
+    CAIR_CUDA(cudaHostAlloc((void**)&h->host_err, sizeof(int), cudaHostAllocDefault));
+  }
+  if (!h->copy_stream) CAIR_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  if (!p.ev_in) {
+    CAIR_CUDA(cudaEventCreateWithFlags(&p.ev_in, cudaEventDisableTiming));
+    CAIR_CUDA(cudaEventCreateWithFlags(&p.ev_done, cudaEventDisableTiming));
+    CAIR_CUDA(cudaHostAlloc((void**)&p.err, sizeof(int), cudaHostAllocDefault));
+    *p.err = 0;
+  }
+  if (need > p.stage_bytes) {   // (re)allocation synchronises; steady state never gets here
+    CAIR_CUDA(cudaStreamSynchronize(h->host_stream));
+    if (p.stage) CAIR_CUDA(cudaFree(p.stage));
+    p.stage = nullptr, p.stage_bytes = 0;
+    CAIR_CUDA(cudaMalloc(&p.stage, need));
+    p.stage_bytes = need;
+  }
+  size_t wsb = 0;
+  CAIR_TRY(cair_ranker_workspace_bytes(h, B, N, Lq, Ld, &wsb));
+  if (wsb > h->ws_bytes) {
+    CAIR_CUDA(cudaStreamSynchronize(h->host_stream));
+    if (h->host_graph) cudaGraphExecDestroy(h->host_graph);   // the cached graph of the synchronous path points into the old workspace
+    h->host_graph = nullptr, h->host_key = cair_handle::HostKey(), h->host_key_hits = 0;
+    if (h->ws) CAIR_CUDA(cudaFree(h->ws));
+    h->ws = nullptr, h->ws_bytes = 0;
+    CAIR_CUDA(cudaMalloc(&h->ws, wsb));
+    h->ws_bytes = wsb;
+  }
+  int64_t* dq = (int64_t*)p.stage;
+  int64_t* dql = dq + nq;
+  int64_t* dd = dql + nb;
+  int64_t* ddl = dd + nd;
+  float* ds = (float*)((char*)p.stage + align_up(in_bytes));
+  cudaStream_t cs = h->copy_stream, hs = stream ? (cudaStream_t)stream : h->host_stream;
+  // ids: host -> this slot's staging area on the copy stream (the slot's previous batch was waited for by the caller)
+  CAIR_CUDA(cudaMemcpyAsync(dq, q, nq * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
+  CAIR_CUDA(cudaMemcpyAsync(dql, qlen, nb * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
+  CAIR_CUDA(cudaMemcpyAsync(dd, d, nd * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
+  CAIR_CUDA(cudaMemcpyAsync(ddl, dlen, nbn * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
+  CAIR_CUDA(cudaEventRecord(p.ev_in, cs));
+  // kernels + scores back on the compute stream, behind the previous batch (shared workspace)
+  CAIR_CUDA(cudaStreamWaitEvent(hs, p.ev_in, 0));
+  CAIR_TRY(cair_ranker_forward(h, dq, dql, dd, ddl, B, N, Lq, Ld, 0, (int64_t)nbn, ds, h->ws, h->ws_bytes, hs));
+  CAIR_CUDA(cudaMemcpyAsync(scores, ds, nbn * sizeof(float), cudaMemcpyDeviceToHost, hs));
+  CAIR_CUDA(cudaMemcpyAsync(p.err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, hs));
+  CAIR_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int), hs));
+  CAIR_CUDA(cudaEventRecord(p.ev_done, hs));
+  p.busy = true;
+  return CAIR_OK;
+}
+
+int32_t cair_ranker_wait_host(cair_handle* h, int32_t slot) {
+  if (!h) return fail(CAIR_ERR_BAD_ARG, "null handle");
+  if (slot < 0 || slot > 1) return fail(CAIR_ERR_BAD_ARG, "ranker_wait_host: slot must be 0 or 1");
+  DeviceGuard g(h->device);
+  cair_handle::PipeSlot& p = h->pipe[slot];
+  if (!p.busy) return fail(CAIR_ERR_BAD_ARG, "ranker_wait_host: nothing submitted on slot %d", slot);
+  CAIR_CUDA(cudaEventSynchronize(p.ev_done));
+  p.busy = false;
+  const int flags = *p.err;
+  *p.err = 0;
+  if (flags & ERRF_BAD_TOKEN) return fail(CAIR_ERR_BAD_ARG, "token id outside [0, vocab)");
+  if (flags) return fail(CAIR_ERR_BAD_ARG, "sequence length outside [1, padded length]");
   return CAIR_OK;
 }
 

@@ -44,6 +44,8 @@ PROTOTYPES = {
     'cair_ranker_workspace_bytes': (i32, [vp, i32, i32, i32, i32, C.POINTER(C.c_size_t)]),
     'cair_ranker_forward': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, vp, vp, C.c_size_t, vp]),
     'cair_ranker_forward_host': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]),
+    'cair_ranker_submit_host': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, i32, vp]),
+    'cair_ranker_wait_host': (i32, [vp, i32]),
     'cair_cars_create': (i32, [C.POINTER(_abi.CarsWeights), i32, C.POINTER(vp)]),
     'cair_cars_workspace_bytes': (i32, [vp, i32, i32, i32, i32, i32, C.POINTER(C.c_size_t)]),
     'cair_cars_forward': (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32,

@@ -197,6 +197,21 @@ class _Ranker(_CairModule):
                                              B, N, Lq, Ld, out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
         return out
 
+    def submit_host(self, q, qlen, d, dlen, out, slot, device=None, stream=None):
+        """Pipelined form of forward_host: enqueue H2D of the (pinned) id tensors, the scoring kernels and the D2H
+        of the scores into `out` (pinned) without waiting; slot 0/1 alternate so that the copies of one batch overlap
+        the kernels of the previous one.  Call wait_host(slot) before reading `out` or re-using the slot."""
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        B, Lq = q.shape
+        _, N, Ld = d.shape
+        h = self._handle_for(dev)
+        lib.check(lib.load().cair_ranker_submit_host(h, q.data_ptr(), qlen.data_ptr(), d.data_ptr(), dlen.data_ptr(),
+                                                     B, N, Lq, Ld, out.data_ptr(), slot,
+                                                     stream.cuda_stream if stream is not None else None))
+
+    def wait_host(self, slot):
+        lib.check(lib.load().cair_ranker_wait_host(self.__dict__['_cair_handle'], slot))
+
     def poll_error(self):
         h = self.__dict__.get('_cair_handle')
         if h is not None:

@@ -265,6 +265,17 @@ CAIR_API int32_t cair_ranker_forward(cair_handle* h, const int64_t* q, const int
 CAIR_API int32_t cair_ranker_forward_host(cair_handle* h, const int64_t* q, const int64_t* qlen,
                                  const int64_t* d, const int64_t* dlen, int32_t B, int32_t N,
                                  int32_t Lq, int32_t Ld, float* scores, void* stream);
+/* Pipelined form of cair_ranker_forward_host for a serving loop (what Ranker.predict does per batch,
+ * neuroir/models/ranker.py:236-258: .cuda(non_blocking) of the ids, forward, scores back to the host):
+ * submit enqueues H2D of the ids on a copy stream, the scoring kernels and the D2H of the scores on the
+ * compute stream (`stream`, or a stream owned by the handle when NULL), and returns without waiting; `slot` (0 or 1) selects one of two device staging
+ * areas, so the copies of batch k+1 overlap the kernels of batch k.  wait blocks until that slot's scores
+ * are in `scores` and reports bad token ids / lengths like the synchronous call.  The host buffers of a
+ * slot must stay valid and unmodified until its wait returns; a slot is re-submitted only after its wait. */
+CAIR_API int32_t cair_ranker_submit_host(cair_handle* h, const int64_t* q, const int64_t* qlen,
+                                const int64_t* d, const int64_t* dlen, int32_t B, int32_t N,
+                                int32_t Lq, int32_t Ld, float* scores, int32_t slot, void* stream);
+CAIR_API int32_t cair_ranker_wait_host(cair_handle* h, int32_t slot);
 
 /* ---- CARS ranking path (neuroir/multitask/cars.py:193-304 encode*, :306-458 encode_session,
  *      :460-540 rank/rank_document, :671-691 apply_pooling; neuroir/modules/maxout.py:70-84) --- */

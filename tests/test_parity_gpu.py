@@ -283,6 +283,17 @@ def test_match_tensor_full_cfg2_properties():
         out.zero_()
         hs = net.forward_host(*host, out=out)
         assert torch.equal(hs, s.cpu())
+    # (4b) pipelined submit/wait over two slots: same scores, several batches in flight
+    outs2 = [torch.zeros(B, N, dtype=torch.float32).pin_memory() for _ in range(2)]
+    for it in range(5):
+        if it >= 2:
+            net.wait_host(it % 2)
+            assert torch.equal(outs2[it % 2], s.cpu())
+            outs2[it % 2].zero_()
+        net.submit_host(*host, out=outs2[it % 2], slot=it % 2)
+    for sl in (1, 0):
+        net.wait_host(sl)
+        assert torch.equal(outs2[sl], s.cpu())
     # (5) the spot-checked oracle agrees on a few pairs of the big batch
     idx = [0, 57, 127]
     ref = ol.run_ranker(cfg, helpers.state_dict_numpy(net), batch['q'][idx], batch['qlen'][idx], batch['d'][idx],
