@@ -37,29 +37,64 @@ constexpr int TC_MAXRA = 264;     // staged A rows: 2*128 + 6 halo rows, rounded
 constexpr int TC_THREADS = 352;   // 8 epilogue warps + B producer + MMA issuer + A producer
 constexpr int TC_EPI_THREADS = 256;
 
-static inline int tc_cp(int C) { return (C + 15) & ~15; }
-static inline size_t tc_slab_bytes(int CP) { return (size_t)2 * (CP / 8) * TC_NROWS * 16; }  // hi + lo, one tap
-static inline size_t tc_a_bytes(int CP) { return (size_t)2 * (CP / 8) * TC_MAXRA * 16; }
+static inline int tc_cp(int C) { return (C + 15) & ~15; }   // channel stride of the packed stencil weights (w7t) and N of the projection GEMM
+
+// K layout of the interaction GEMM.  Channels [0, Cm) (Cm a multiple of 16) are the "main" channels: Cm/16 k-steps per
+// tap over KCm = Cm/8 operand planes.  The remaining r = C - Cm channels (1 <= r <= 8) would cost a whole extra k-step
+// per tap if padded to 16; they are packed ACROSS taps into one extra "tail" plane instead: a 16-byte unit holds tpc
+// taps x rr channel slots (rr = 8 / tpc >= r) - the unit of image row r' carries the tail channels of the document
+// positions r'-3 .. r'-3+tpc-1.  One tail k-step covers 2 tpc taps: its two K chunks are the SAME plane at row shifts 0
+// and tpc (descriptor LBO = tpc rows), so the 7 taps cost ntail = ceil(ceil(7/tpc)/2) k-steps instead of 7.
+// C = 50 (hyparam default): 7 x 3 + 1 = 22 k-steps per column tile instead of 28.
+struct TcK {
+  int Cm, KCm, nkm, r, tpc, rr, ntail, KA;
+};
+__host__ __device__ inline TcK tc_k(int C) {
+  TcK k;
+  k.r = C & 15;
+  if (k.r == 0 || k.r > 8 || C < 16) {
+    k.Cm = (C + 15) & ~15, k.r = 0, k.tpc = 0, k.rr = 0, k.ntail = 0;
+  } else {
+    k.Cm = C & ~15;
+    k.tpc = k.r <= 2 ? 4 : k.r <= 4 ? 2 : 1;
+    k.rr = 8 / k.tpc;
+    k.ntail = ((7 + k.tpc - 1) / k.tpc + 1) / 2;
+  }
+  k.KCm = k.Cm / 8, k.nkm = k.Cm / 16, k.KA = k.KCm + (k.r ? 1 : 0);
+  return k;
+}
+__host__ __device__ inline uint32_t tc_slab_main(const TcK& k) { return 2u * k.KCm * TC_NROWS * 16; }      // hi + lo, one tap
+__host__ __device__ inline uint32_t tc_slab_tail(const TcK& k) { return 2u * 2 * k.ntail * TC_NROWS * 16; }  // hi + lo, all taps
+__host__ __device__ inline uint32_t tc_stage_bytes(const TcK& k) {
+  return tc_slab_main(k) > tc_slab_tail(k) ? tc_slab_main(k) : tc_slab_tail(k);
+}
+__host__ __device__ inline uint32_t tc_timg_per_tile(const TcK& k) { return 7u * tc_slab_main(k) + tc_slab_tail(k); }
+static inline size_t tc_a_bytes(const TcK& k) { return (size_t)2 * k.KA * TC_MAXRA * 16; }
 static inline size_t tc_misc_bytes(const MtPack& p, int Lq) {
   (void)p;
   return (size_t)(MT_TC_MAXM * 8 + 24 * MT_TC_MAXM) * sizeof(float) + (size_t)(TC_MAXRA + 8 + Lq) * sizeof(int);
 }
 static inline int tc_stages(const MtPack& p, int Lq) {
-  const int CP = tc_cp(p.C);
-  size_t fixed = tc_a_bytes(CP) + tc_misc_bytes(p, Lq) + 1024;
-  int s = (int)((226 * 1024 - fixed) / tc_slab_bytes(CP));
+  const TcK k = tc_k(p.C);
+  size_t fixed = tc_a_bytes(k) + tc_misc_bytes(p, Lq) + 1024;
+  int s = (int)((226 * 1024 - fixed) / tc_stage_bytes(k));
   return s > 8 ? 8 : s;
 }
 
-// B slabs for (query qi, column tile nt, tap bt): [hi|lo][plane c/8][row n = il*FP + f][8 x bf16].
-// One thread per 16-byte unit (8 channels of one (i, f, tap)): T = sum_a W7[f,c,a,bt] * cq[i+a-1,c], split to hi/lo.
-__global__ void __launch_bounds__(256) mt_tc_build_t_kernel(const float* __restrict__ cq, MtPack p, int Lq, int CP,
-                                                            int IPT, int ntiles, uint8_t* __restrict__ img) {
-  const int nt = blockIdx.x / 7, bt = blockIdx.x - nt * 7, qi = blockIdx.y;
-  const int C = p.C, FP = p.FP, KC = CP / 8;
-  const size_t half = (size_t)KC * TC_NROWS * 16;
-  uint8_t* out = img + (((size_t)qi * ntiles + nt) * 7 + bt) * 2 * half;
-  for (int u = threadIdx.x; u < KC * TC_NROWS; u += blockDim.x) {
+// B slabs for (query qi, column tile nt): 7 main slabs (one per tap bt) [hi|lo][plane c/8 < KCm][row n = il*FP + f][8 x bf16]
+// followed by the tail slab [hi|lo][chunk ch < 2 ntail][row n][8 x bf16] (element e of chunk ch: tap ch*tpc + e/rr,
+// channel Cm + e%rr).  One thread per 16-byte unit: T = sum_a W7[f,c,a,bt] * cq[i+a-1,c], split to hi/lo.
+__global__ void __launch_bounds__(256) mt_tc_build_t_kernel(const float* __restrict__ cq, MtPack p, int Lq, int IPT,
+                                                            int ntiles, uint8_t* __restrict__ img) {
+  const TcK k = tc_k(p.C);
+  const int nit = 7 + (k.ntail ? 1 : 0);
+  const int nt = blockIdx.x / nit, item = blockIdx.x - nt * nit, qi = blockIdx.y;
+  const int C = p.C, FP = p.FP, CPW = (C + 15) & ~15;
+  const bool tail = item == 7;
+  const int planes = tail ? 2 * k.ntail : k.KCm;
+  const size_t half = (size_t)planes * TC_NROWS * 16;
+  uint8_t* out = img + ((size_t)qi * ntiles + nt) * tc_timg_per_tile(k) + (size_t)item * tc_slab_main(k);
+  for (int u = threadIdx.x; u < planes * TC_NROWS; u += blockDim.x) {
     const int kc = u / TC_NROWS, n = u - kc * TC_NROWS;
     const int il = n / FP, f = n - il * FP, i = nt * IPT + il;
     float v[8];
@@ -70,56 +105,61 @@ __global__ void __launch_bounds__(256) mt_tc_build_t_kernel(const float* __restr
       for (int a = 0; a < 3; ++a) {
         const int ii = i + a - 1;
         if (ii < 0 || ii >= Lq) continue;
-        const float4* w4 = reinterpret_cast<const float4*>(p.w7t + (((size_t)a * 7 + bt) * FP + f) * CP + kc * 8);
-        const float4 wa = w4[0], wb = w4[1];
-        const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-        const float* cr = cq + ((size_t)qi * Lq + ii) * C + kc * 8;
+        if (!tail) {
+          const float4* w4 = reinterpret_cast<const float4*>(p.w7t + (((size_t)a * 7 + item) * FP + f) * CPW + kc * 8);
+          const float4 wa = w4[0], wb = w4[1];
+          const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+          const float* cr = cq + ((size_t)qi * Lq + ii) * C + kc * 8;
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          if (kc * 8 + e < C) v[e] = fmaf(w[e], cr[e], v[e]);
+          for (int e = 0; e < 8; ++e)
+            if (kc * 8 + e < C) v[e] = fmaf(w[e], cr[e], v[e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int bt = kc * k.tpc + e / k.rr, ce = e % k.rr;
+            if (bt < 7 && ce < k.r)
+              v[e] = fmaf(p.w7t[(((size_t)a * 7 + bt) * FP + f) * CPW + k.Cm + ce],
+                          cq[((size_t)qi * Lq + ii) * C + k.Cm + ce], v[e]);
+          }
+        }
       }
     }
     uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(v[2 * e], h0, l0);
-      split_bf16(v[2 * e + 1], h1, l1);
-      hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-      lo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-    }
+    for (int e = 0; e < 4; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
     const size_t off = ((size_t)kc * TC_NROWS + n) * 16;
     *reinterpret_cast<uint4*>(out + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(out + half + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
-// A images: per pair [hi|lo][plane c/8][row r <-> doc position r-3][8 x bf16]; halo / pad rows and pad channels are 0.
+// A images: per pair [hi|lo][plane < KA][row r <-> doc position r-3][8 x bf16]; planes < KCm hold 8 main channels each,
+// plane KCm (if any) is the tail plane (see TcK); halo / pad rows and pad channels are 0.
 // One thread per 16-byte unit; the interaction kernel then loads a whole image with one bulk copy.
-__global__ void __launch_bounds__(256) mt_tc_image_kernel(const float* __restrict__ cd, int C, int Ld, int KC, int RA,
+__global__ void __launch_bounds__(256) mt_tc_image_kernel(const float* __restrict__ cd, int C, int Ld, int RA,
                                                            int64_t pair_count, uint8_t* __restrict__ aimg) {
+  const TcK k = tc_k(C);
   const int64_t pl = blockIdx.x;
   const float* cdp = cd + (size_t)pl * Ld * C;
-  const size_t half = (size_t)KC * RA * 16;
+  const size_t half = (size_t)k.KA * RA * 16;
   uint8_t* out = aimg + (size_t)pl * 2 * half;
-  for (int u = threadIdx.x; u < RA * KC; u += blockDim.x) {
+  for (int u = threadIdx.x; u < RA * k.KA; u += blockDim.x) {
     const int kc = u / RA, r = u - kc * RA;
-    const int j = r - 3;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int c = kc * 8 + e;
-      v[e] = (j >= 0 && j < Ld && c < C) ? cdp[(size_t)j * C + c] : 0.f;
+      int j, c;
+      bool ok;
+      if (kc < k.KCm) {
+        j = r - 3, c = kc * 8 + e, ok = c < C;
+      } else {
+        j = r - 3 + e / k.rr, c = k.Cm + e % k.rr, ok = (e % k.rr) < k.r;
+      }
+      v[e] = (ok && j >= 0 && j < Ld) ? cdp[(size_t)j * C + c] : 0.f;
     }
     uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(v[2 * e], h0, l0);
-      split_bf16(v[2 * e + 1], h1, l1);
-      hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-      lo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-    }
+    for (int e = 0; e < 4; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
     const size_t off = ((size_t)kc * RA + r) * 16;
     *reinterpret_cast<uint4*>(out + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(out + half + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -173,8 +213,9 @@ __global__ void __launch_bounds__(PJ_THREADS, 2)
   uint8_t* a_img = smraw;
   uint8_t* w_img = smraw + 2 * a_half;
   float* bias_s = reinterpret_cast<float*>(w_img + 2 * w_half);
-  const int KC = CP / 8;
-  const size_t o_half = (size_t)KC * RA * 16;
+  const TcK k = tc_k(C);
+  const int KC = k.KCm;   // main planes of the output image; plane KC is the tail plane (k.r > 0)
+  const size_t o_half = (size_t)k.KA * RA * 16;
 
   if (warp == 0) tmem_alloc(&tmem_slot, tcols);
   if (tid == 32) {
@@ -257,6 +298,19 @@ __global__ void __launch_bounds__(PJ_THREADS, 2)
           *reinterpret_cast<uint4*>(out + ((size_t)kc * RA + r) * 16) = zero;
           *reinterpret_cast<uint4*>(out + o_half + ((size_t)kc * RA + r) * 16) = zero;
         }
+    // tail plane: every (row, tap slot) whose document position is outside [0, Ld) is zero; each byte of the plane has
+    // exactly one writer (these threads for the invalid slots, the epilogue thread of position j for the valid ones)
+    if (k.r && (mt == 0 || mt == ntile - 1)) {
+      uint8_t* tp = out + (size_t)KC * RA * 16;
+      for (int idx = tid; idx < RA * k.tpc; idx += PJ_THREADS) {
+        const int r = idx / k.tpc, te = idx - r * k.tpc, pos = r - 3 + te;
+        if ((pos < 0 && mt == 0) || (pos >= Ld && mt == ntile - 1)) {
+          uint16_t* ph = reinterpret_cast<uint16_t*>(tp + (size_t)r * 16) + te * k.rr;
+          uint16_t* plo = reinterpret_cast<uint16_t*>(tp + o_half + (size_t)r * 16) + te * k.rr;
+          for (int ce = 0; ce < k.rr; ++ce) ph[ce] = 0, plo[ce] = 0;
+        }
+      }
+    }
     mbar_wait_relaxed(&acc_full, phase);
     phase ^= 1;
     tc_fence_after();
@@ -268,18 +322,44 @@ __global__ void __launch_bounds__(PJ_THREADS, 2)
       tmem_ld16(tbase + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
       tmem_ld_wait();
       if (j < Ld) {
+        if (c0 < k.Cm) {
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
+          for (int g = 0; g < 2; ++g) {
+            uint32_t hi[4], lo[4];
+            const float4 ba = *reinterpret_cast<const float4*>(bias_s + c0 + g * 8);
+            const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + g * 8 + 4);
+            split_bf16x2(v[g * 8 + 0] + ba.x, v[g * 8 + 1] + ba.y, hi[0], lo[0]);
+            split_bf16x2(v[g * 8 + 2] + ba.z, v[g * 8 + 3] + ba.w, hi[1], lo[1]);
+            split_bf16x2(v[g * 8 + 4] + bb.x, v[g * 8 + 5] + bb.y, hi[2], lo[2]);
+            split_bf16x2(v[g * 8 + 6] + bb.z, v[g * 8 + 7] + bb.w, hi[3], lo[3]);
+            const size_t off = ((size_t)(c0 / 8 + g) * RA + j + 3) * 16;
+            *reinterpret_cast<uint4*>(out + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(out + o_half + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        } else {
+          // tail channels Cm .. Cm+r-1 of position j: slot te of the units of image rows j+3-te, te < tpc
           uint32_t hi[4], lo[4];
-          const float4 ba = *reinterpret_cast<const float4*>(bias_s + c0 + g * 8);
-          const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + g * 8 + 4);
-          split_bf16x2(v[g * 8 + 0] + ba.x, v[g * 8 + 1] + ba.y, hi[0], lo[0]);
-          split_bf16x2(v[g * 8 + 2] + ba.z, v[g * 8 + 3] + ba.w, hi[1], lo[1]);
-          split_bf16x2(v[g * 8 + 4] + bb.x, v[g * 8 + 5] + bb.y, hi[2], lo[2]);
-          split_bf16x2(v[g * 8 + 6] + bb.z, v[g * 8 + 7] + bb.w, hi[3], lo[3]);
-          const size_t off = ((size_t)(c0 / 8 + g) * RA + j + 3) * 16;
-          *reinterpret_cast<uint4*>(out + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(out + o_half + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x0 = 2 * e < k.r ? v[2 * e] + bias_s[c0 + 2 * e] : 0.f;
+            const float x1 = 2 * e + 1 < k.r ? v[2 * e + 1] + bias_s[c0 + 2 * e + 1] : 0.f;
+            split_bf16x2(x0, x1, hi[e], lo[e]);
+          }
+          uint8_t* tp = out + (size_t)KC * RA * 16;
+          for (int te = 0; te < k.tpc; ++te) {
+            uint8_t* dh = tp + (size_t)(j + 3 - te) * 16 + te * k.rr * 2;
+            uint8_t* dl = dh + o_half;
+            if (k.rr == 2) {
+              *reinterpret_cast<uint32_t*>(dh) = hi[0];
+              *reinterpret_cast<uint32_t*>(dl) = lo[0];
+            } else if (k.rr == 4) {
+              *reinterpret_cast<uint2*>(dh) = make_uint2(hi[0], hi[1]);
+              *reinterpret_cast<uint2*>(dl) = make_uint2(lo[0], lo[1]);
+            } else {
+              *reinterpret_cast<uint4*>(dh) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(dl) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
         }
       }
     }
@@ -306,7 +386,7 @@ template <int NF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     mt_tc_interact_kernel(const uint8_t* __restrict__ aimg, const uint8_t* __restrict__ timg, MtPack p,
                           const __grid_constant__ MtEpiConst ec, const int64_t* __restrict__ q,
-                          const int64_t* __restrict__ d, int N, int Lq, int Ld, int CP, int ntiles, int nstages,
+                          const int64_t* __restrict__ d, int N, int Lq, int Ld, int ntiles, int nstages,
                           int64_t pair_begin, int64_t pair_count, int64_t q_begin, float* __restrict__ scores,
                           long long* __restrict__ dbg) {
   constexpr int FP = 3 * NF, FPP = (FP + 3) & ~3, IPT = TC_NROWS / FP;
@@ -314,17 +394,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   __shared__ uint64_t full_b[8], empty_b[8], acc_full[2], acc_empty[2], a_full, a_empty;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int C = p.C, M = p.M, KC = CP / 8;
+  const int M = p.M;
+  const TcK k = tc_k(p.C);
+  const int nit = 7 + (k.ntail ? 1 : 0);            // ring items per column tile: 7 taps (+ the tail slab)
   const int nmt = (Ld + 127) / 128;                 // 1 or 2 row tiles
   const int RA = (nmt * 128 + 6 + 7) & ~7;          // staged rows
   const uint32_t b_plane = TC_NROWS * 16, a_plane = (uint32_t)RA * 16;
-  const uint32_t b_half = (uint32_t)KC * b_plane, a_half = (uint32_t)KC * a_plane;
-  const uint32_t slab = 2 * b_half;
+  const uint32_t b_half = (uint32_t)k.KCm * b_plane, a_half = (uint32_t)k.KA * a_plane;
+  const uint32_t slab = tc_slab_main(k), slab_t = tc_slab_tail(k), stage = tc_stage_bytes(k);
   uint8_t* a_img = smraw;
-  uint8_t* b_ring = a_img + (size_t)2 * KC * TC_MAXRA * 16;  // host side: tc_a_bytes()
+  uint8_t* b_ring = a_img + (size_t)2 * k.KA * TC_MAXRA * 16;  // host side: tc_a_bytes()
   // epilogue weights (exact-match taps, bias, 1x1 conv) come from the constant bank (kernel parameter `ec`):
   // FFMA takes them as immediate c[][] operands, no shared-memory loads in the hot loop
-  float* red = reinterpret_cast<float*>(b_ring + (size_t)nstages * slab);  // [8 warps][32]
+  float* red = reinterpret_cast<float*>(b_ring + (size_t)nstages * stage);  // [8 warps][32]
   float* w1t = red + MT_TC_MAXM * 8;               // [24][32] 1x1 conv weights, transposed (m contiguous)
   int* dids = reinterpret_cast<int*>(w1t + 24 * MT_TC_MAXM);
   int* qids = dids + TC_MAXRA + 8;
@@ -357,13 +439,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       uint32_t it = 0;
       for (int64_t pl = blockIdx.x; pl < pair_count; pl += gridDim.x) {
         const int64_t ql = (pair_begin + pl) / N - q_begin;
-        const uint8_t* src = timg + (size_t)ql * ntiles * 7 * slab;
-        for (int t = 0; t < ntiles * 7; ++t, ++it) {
-          const int s = it % nstages;
-          const uint32_t ph = (it / nstages) & 1;
-          { TC_T0(); mbar_wait_relaxed(&empty_b[s], ph ^ 1); TC_ACC(0); }
-          mbar_arrive_expect_tx(&full_b[s], slab);
-          bulk_g2s(b_ring + (size_t)s * slab, src + (size_t)t * slab, slab, &full_b[s]);
+        const uint8_t* src = timg + (size_t)ql * ntiles * tc_timg_per_tile(k);
+        for (int nt = 0; nt < ntiles; ++nt) {
+          for (int item = 0; item < nit; ++item, ++it) {
+            const int s = it % nstages;
+            const uint32_t ph = (it / nstages) & 1;
+            const uint32_t bytes = item < 7 ? slab : slab_t;
+            { TC_T0(); mbar_wait_relaxed(&empty_b[s], ph ^ 1); TC_ACC(0); }
+            mbar_arrive_expect_tx(&full_b[s], bytes);
+            bulk_g2s(b_ring + (size_t)s * stage, src, bytes, &full_b[s]);
+            src += bytes;
+          }
         }
       }
     }
@@ -387,7 +473,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const uint32_t a0 = smem_u32(a_img), b0 = smem_u32(b_ring);
       const uint64_t ad_hi = smem_desc(a0, a_plane, 128), ad_lo = smem_desc(a0 + a_half, a_plane, 128);
       const uint32_t a_ks = (2 * a_plane) >> 4, b_ks = (2 * b_plane) >> 4, b_lo_off = b_half >> 4;
-      const int nks = CP / 16;
+      const int nks = k.nkm;
+      // tail k-steps: A = the tail plane at row shifts 2 s tpc (+ tpc for the second K chunk: LBO = tpc rows)
+      const uint32_t at0 = a0 + (uint32_t)k.KCm * a_plane;
+      const uint32_t bt_lo_off = (uint32_t)(2 * k.ntail) * b_plane >> 4;
       uint32_t it = 0, tile = 0, pair_it = 0;
       const long long tk0 = dbg ? clock64() : 0;
       for (int64_t pl = blockIdx.x; pl < pair_count; pl += gridDim.x, ++pair_it) {
@@ -398,23 +487,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           const int as = tile & 1;
           { TC_T0(); mbar_wait(&acc_empty[as], ((tile >> 1) & 1) ^ 1); TC_ACC(2); }
           tc_fence_after();
-          for (int bt = 0; bt < 7; ++bt, ++it) {
+          for (int bt = 0; bt < nit; ++bt, ++it) {
             const int s = it % nstages;
             { TC_T0(); mbar_wait(&full_b[s], (it / nstages) & 1); TC_ACC(3); }
             tc_fence_after();
-            const uint64_t bd_hi = smem_desc(b0 + (uint32_t)s * slab, b_plane, 128);
+            const uint64_t bd_hi = smem_desc(b0 + (uint32_t)s * stage, b_plane, 128);
             const uint32_t accf = bt != 0;
+            if (bt < 7) {
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-              if (mt < nmt) {
-                const uint32_t tacc = tbase + (uint32_t)(as * 2 + mt) * TC_NROWS;
-                const uint64_t ah = ad_hi + (uint64_t)(mt * 128 + bt), al = ad_lo + (uint64_t)(mt * 128 + bt);
-                for (int ks = 0; ks < nks; ++ks) {
-                  const uint64_t ahk = ah + (uint64_t)(ks * a_ks), alk = al + (uint64_t)(ks * a_ks);
-                  const uint64_t bhk = bd_hi + (uint64_t)(ks * b_ks), blk = bhk + (uint64_t)b_lo_off;
-                  mma_bf16_ss_w(tacc, ahk, bhk, idesc, accf | (uint32_t)(ks != 0), issue);
-                  mma_bf16_ss_w(tacc, alk, bhk, idesc, 1, issue);
-                  mma_bf16_ss_w(tacc, ahk, blk, idesc, 1, issue);
+              for (int mt = 0; mt < 2; ++mt) {
+                if (mt < nmt) {
+                  const uint32_t tacc = tbase + (uint32_t)(as * 2 + mt) * TC_NROWS;
+                  const uint64_t ah = ad_hi + (uint64_t)(mt * 128 + bt), al = ad_lo + (uint64_t)(mt * 128 + bt);
+                  for (int ks = 0; ks < nks; ++ks) {
+                    const uint64_t ahk = ah + (uint64_t)(ks * a_ks), alk = al + (uint64_t)(ks * a_ks);
+                    const uint64_t bhk = bd_hi + (uint64_t)(ks * b_ks), blk = bhk + (uint64_t)b_lo_off;
+                    mma_bf16_ss_w(tacc, ahk, bhk, idesc, accf | (uint32_t)(ks != 0), issue);
+                    mma_bf16_ss_w(tacc, alk, bhk, idesc, 1, issue);
+                    mma_bf16_ss_w(tacc, ahk, blk, idesc, 1, issue);
+                  }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt) {
+                if (mt < nmt) {
+                  const uint32_t tacc = tbase + (uint32_t)(as * 2 + mt) * TC_NROWS;
+                  for (int ts = 0; ts < k.ntail; ++ts) {
+                    const uint32_t arow = at0 + (uint32_t)(mt * 128 + 2 * ts * k.tpc) * 16;
+                    const uint64_t ahk = smem_desc(arow, (uint32_t)k.tpc * 16, 128);
+                    const uint64_t alk = smem_desc(arow + a_half, (uint32_t)k.tpc * 16, 128);
+                    const uint64_t bhk = bd_hi + (uint64_t)(ts * b_ks), blk = bhk + (uint64_t)bt_lo_off;
+                    mma_bf16_ss_w(tacc, ahk, bhk, idesc, 1, issue);
+                    mma_bf16_ss_w(tacc, alk, bhk, idesc, 1, issue);
+                    mma_bf16_ss_w(tacc, ahk, blk, idesc, 1, issue);
+                  }
                 }
               }
             }
@@ -566,10 +673,10 @@ bool mt_tc_supported(const MtPack& p, int Lq, int Ld) {
 static inline int tc_ra(int Ld) { return (((Ld + 127) / 128) * 128 + 6 + 7) & ~7; }
 
 void mt_tc_workspace(const MtPack& p, int64_t nq, int64_t pc, int Lq, int Ld, size_t* timg_bytes, size_t* aimg_bytes) {
-  const int CP = tc_cp(p.C);
+  const TcK k = tc_k(p.C);
   const int IPT = TC_NROWS / p.FP, ntiles = (Lq + IPT - 1) / IPT;
-  *timg_bytes = (size_t)nq * ntiles * 7 * tc_slab_bytes(CP);
-  *aimg_bytes = (size_t)pc * 2 * (CP / 8) * tc_ra(Ld) * 16;
+  *timg_bytes = (size_t)nq * ntiles * tc_timg_per_tile(k);
+  *aimg_bytes = (size_t)pc * 2 * k.KA * tc_ra(Ld) * 16;
 }
 
 // Host copy of the epilogue weights (exact-match taps, bias, 1x1 conv) for the constant-bank kernel parameter.
@@ -594,16 +701,17 @@ int32_t mt_epi_const(const MtPack& p, MtEpiConst* out, cudaStream_t s) {
 
 int32_t mt_tc_build_t(const MtPack& p, const float* cq, uint8_t* timg, int Lq, int64_t nq, cudaStream_t s) {
   if (nq <= 0) return CAIR_OK;
-  const int CP = tc_cp(p.C);
+  const TcK k = tc_k(p.C);
   const int IPT = TC_NROWS / p.FP, ntiles = (Lq + IPT - 1) / IPT;
-  CAIR_LAUNCH(mt_tc_build_t_kernel, dim3(ntiles * 7, (unsigned)nq), 256, 0, s, cq, p, Lq, CP, IPT, ntiles, timg);
+  CAIR_LAUNCH(mt_tc_build_t_kernel, dim3(ntiles * (7 + (k.ntail ? 1 : 0)), (unsigned)nq), 256, 0, s, cq, p, Lq, IPT, ntiles,
+              timg);
   return CAIR_OK;
 }
 
 int32_t mt_tc_doc_image(const MtPack& p, const float* cd, uint8_t* aimg, int Ld, int64_t pair_count, cudaStream_t s) {
   if (pair_count <= 0) return CAIR_OK;
   prof_mark("doc_image", s);
-  CAIR_LAUNCH(mt_tc_image_kernel, (unsigned)pair_count, 256, 0, s, cd, p.C, Ld, tc_cp(p.C) / 8, tc_ra(Ld), pair_count, aimg);
+  CAIR_LAUNCH(mt_tc_image_kernel, (unsigned)pair_count, 256, 0, s, cd, p.C, Ld, tc_ra(Ld), pair_count, aimg);
   return CAIR_OK;
 }
 
@@ -642,19 +750,19 @@ int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const uint8_t* tim
                        int64_t nq, float* scores, cudaStream_t s) {
   (void)nq;
   if (pair_count <= 0) return CAIR_OK;
-  const int CP = tc_cp(p.C);
+  const TcK k = tc_k(p.C);
   const int IPT = TC_NROWS / p.FP, ntiles = (Lq + IPT - 1) / IPT;
   const int nstages = tc_stages(p, Lq);
-  const size_t smem = tc_a_bytes(CP) + (size_t)nstages * tc_slab_bytes(CP) + tc_misc_bytes(p, Lq);
+  const size_t smem = tc_a_bytes(k) + (size_t)nstages * tc_stage_bytes(k) + tc_misc_bytes(p, Lq);
   prof_mark("interact", s);
   const unsigned grid = (unsigned)(pair_count < kSMs ? pair_count : kSMs);
   if (p.nf == 6) {
     CAIR_CUDA(cudaFuncSetAttribute(mt_tc_interact_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CAIR_LAUNCH(mt_tc_interact_kernel<6>, grid, TC_THREADS, smem, s, aimg, timg, p, ec, q, d, N, Lq, Ld, CP, ntiles,
+    CAIR_LAUNCH(mt_tc_interact_kernel<6>, grid, TC_THREADS, smem, s, aimg, timg, p, ec, q, d, N, Lq, Ld, ntiles,
                 nstages, pair_begin, pair_count, q_begin, scores, g_mt_dbg);
   } else {
     CAIR_CUDA(cudaFuncSetAttribute(mt_tc_interact_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CAIR_LAUNCH(mt_tc_interact_kernel<4>, grid, TC_THREADS, smem, s, aimg, timg, p, ec, q, d, N, Lq, Ld, CP, ntiles,
+    CAIR_LAUNCH(mt_tc_interact_kernel<4>, grid, TC_THREADS, smem, s, aimg, timg, p, ec, q, d, N, Lq, Ld, ntiles,
                 nstages, pair_begin, pair_count, q_begin, scores, g_mt_dbg);
   }
   return CAIR_OK;

@@ -216,6 +216,21 @@ def test_match_tensor_cfg2_shapes_vs_oracle():
     assert _max_rel(s, ref) < TOL
 
 
+@pytest.mark.parametrize('C', [16, 17, 20, 22, 33, 50, 64])
+def test_match_tensor_channel_counts_vs_oracle(C):
+    """K layouts of the tcgen05 interaction GEMM: C % 16 in {1,2} / {3,4} / {5..8} tail channels packed 4 / 2 / 1
+    taps per 16-byte unit, and the plain padded layout (C % 16 == 0 or > 8)."""
+    cfg = dict(MT_CFG2, src_vocab_size=300, nchannels=C)
+    for impl in ('tc', 'tc_split'):
+        torch.manual_seed(5)
+        net = helpers.build_module(cfg).to(DEV).set_interaction_impl(impl)
+        batch = synth.ranker_batch(9, 2, 3, 20, 200, 300, bos_eos=True, overlap=0.05)
+        with torch.no_grad():
+            s = net(*helpers.to_dev(batch, DEV)).cpu().numpy()
+        ref = ol.run_ranker(cfg, helpers.state_dict_numpy(net), batch['q'], batch['qlen'], batch['d'], batch['dlen'])['scores']
+        assert _max_rel(s, ref) < TOL, (C, impl)
+
+
 def test_match_tensor_ragged_and_minimal_lengths():
     cfg = dict(MT_CFG2, src_vocab_size=500)
     torch.manual_seed(3)
