@@ -371,6 +371,16 @@ __global__ void __launch_bounds__(PJ_THREADS, 2)
   if (warp == 0) tmem_dealloc(tbase, tcols);
 }
 
+// acc.{x,y} += w.{x,y} * y  as ONE packed instruction (fma.rn.f32x2, SASS FFMA2 with a broadcast scalar operand)
+__device__ __forceinline__ void ffma2(float2& acc, float2 w, float y) {
+  unsigned long long a, c, yy;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(w.x), "f"(w.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(acc.x), "f"(acc.y));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(yy) : "f"(y));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(yy));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(c));
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -594,25 +604,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               // 1x1 conv: f outer, m inner -> independent accumulators (no dependent-FMA stalls); the weights
               // come from shared memory as broadcast LDS.128 (w1t[f][m], m contiguous).  Outputs m >= M see zero
               // weights and are ignored at the end.
-              float z[MT_TC_MAXM];
-#pragma unroll
-              for (int m = 0; m < MT_TC_MAXM; ++m) z[m] = ec.b1[m];
               if (M <= 20) {
+                // packed fp32x2 FMAs (FFMA2: two output channels per instruction, y[f] as the broadcast scalar operand)
+                float2 zz[10];
+#pragma unroll
+                for (int m2 = 0; m2 < 10; ++m2) zz[m2] = make_float2(ec.b1[2 * m2], ec.b1[2 * m2 + 1]);
 #pragma unroll
                 for (int f = 0; f < FP; ++f) {
                   const float4* wr = reinterpret_cast<const float4*>(w1t + f * MT_TC_MAXM);
 #pragma unroll
                   for (int m4 = 0; m4 < 5; ++m4) {
                     const float4 w4 = wr[m4];
-                    z[4 * m4 + 0] = fmaf(w4.x, y[f], z[4 * m4 + 0]);
-                    z[4 * m4 + 1] = fmaf(w4.y, y[f], z[4 * m4 + 1]);
-                    z[4 * m4 + 2] = fmaf(w4.z, y[f], z[4 * m4 + 2]);
-                    z[4 * m4 + 3] = fmaf(w4.w, y[f], z[4 * m4 + 3]);
+                    ffma2(zz[2 * m4], make_float2(w4.x, w4.y), y[f]);
+                    ffma2(zz[2 * m4 + 1], make_float2(w4.z, w4.w), y[f]);
                   }
                 }
 #pragma unroll
-                for (int m = 0; m < 20; ++m) mx[m] = fmaxf(mx[m], z[m]);
+                for (int m2 = 0; m2 < 10; ++m2) {
+                  mx[2 * m2] = fmaxf(mx[2 * m2], zz[m2].x);
+                  mx[2 * m2 + 1] = fmaxf(mx[2 * m2 + 1], zz[m2].y);
+                }
               } else {
+                float z[MT_TC_MAXM];
+#pragma unroll
+                for (int m = 0; m < MT_TC_MAXM; ++m) z[m] = ec.b1[m];
 #pragma unroll
                 for (int f = 0; f < FP; ++f) {
                   const float4* wr = reinterpret_cast<const float4*>(w1t + f * MT_TC_MAXM);
