@@ -34,8 +34,10 @@ using namespace umma;
 constexpr int TC_NROWS = 96;      // N of the MMA (columns of one accumulator tile)
 constexpr int TC_TCOLS = 512;     // TMEM columns allocated: 2 stages x 2 row tiles x 96 (384) -> next power of two
 constexpr int TC_MAXRA = 264;     // staged A rows: 2*128 + 6 halo rows, rounded up to 8
-constexpr int TC_THREADS = 352;   // 8 epilogue warps + B producer + MMA issuer + A producer
-constexpr int TC_EPI_THREADS = 256;
+constexpr int TC_EPI_WARPS = 12;  // 3 per SM sub-partition (= TMEM lane quarter)
+constexpr int TC_NI = 1;          // query positions per epilogue work unit (2 = shared weight loads; measured slower: 0.344 vs 0.295 ms)
+constexpr int TC_THREADS = (TC_EPI_WARPS + 3) * 32;   // epilogue warps + B producer + MMA issuer + A producer
+constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 
 static inline int tc_cp(int C) { return (C + 15) & ~15; }   // channel stride of the packed stencil weights (w7t) and N of the projection GEMM
 
@@ -72,7 +74,7 @@ __host__ __device__ inline uint32_t tc_timg_per_tile(const TcK& k) { return 7u *
 static inline size_t tc_a_bytes(const TcK& k) { return (size_t)2 * k.KA * TC_MAXRA * 16; }
 static inline size_t tc_misc_bytes(const MtPack& p, int Lq) {
   (void)p;
-  return (size_t)(MT_TC_MAXM * 8 + 24 * MT_TC_MAXM) * sizeof(float) + (size_t)(TC_MAXRA + 8 + Lq) * sizeof(int);
+  return (size_t)(MT_TC_MAXM * TC_EPI_WARPS + 24 * MT_TC_MAXM) * sizeof(float) + (size_t)(TC_MAXRA + 8 + Lq) * sizeof(int);
 }
 static inline int tc_stages(const MtPack& p, int Lq) {
   const TcK k = tc_k(p.C);
@@ -392,6 +394,142 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 #define TC_T0() long long t0_ = dbg ? clock64() : 0
 #define TC_ACC(slot) do { if (dbg && blockIdx.x == 0 && lane == 0) dbg[slot] += clock64() - t0_; } while (0)
 
+// TMEM -> registers, FP (= 12 or 18) consecutive fp32 columns of this thread's lane
+template <int FP>
+__device__ __forceinline__ void tmem_ld_fp(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  if constexpr (FP == 18) {
+    tmem_ld16(taddr, v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[16]), "=r"(r[17]) : "r"(taddr + 16) : "memory");
+  } else {
+    static_assert(FP == 12, "FP must be 12 or 18");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11])
+                 : "r"(taddr + 8)
+                 : "memory");
+  }
+}
+
+// y[f] = relu(conv accumulator + bias + exact-match taps) of (query position i, this thread's document row)
+// exact-match channel: alpha * W7[f, C, a, bt] wherever q[i+a-1] == d[j+bt-3] (PAD==PAD counts); dj = dids + jrow
+template <int FP>
+__device__ __forceinline__ void mt_epi_prep(float* y, int i, int Lq, const int* dj, const int* qids, const MtEpiConst& ec) {
+#pragma unroll
+  for (int f = 0; f < FP; ++f) y[f] += ec.bias[f];
+  // Matches are rare (a few cells per pair): test all 21 (a, bt) taps branch-free first (one predicate-accumulating
+  // compare each) and enter the tap loop only on a hit.  Out-of-range query positions are -2, out-of-range document
+  // positions -1: they never match.
+  int qv[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int ii = i + a - 1;
+    qv[a] = (ii >= 0 && ii < Lq) ? qids[ii] : -2;
+  }
+  bool hit = false;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int bt = 0; bt < 7; ++bt) hit |= dj[bt] == qv[a];
+  if (hit) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+      for (int bt = 0; bt < 7; ++bt) {
+        if (dj[bt] == qv[a]) {
+#pragma unroll
+          for (int f = 0; f < FP; ++f) y[f] += ec.wem[a * 7 + bt][f];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < FP; ++f) y[f] = fmaxf(y[f], 0.f);
+}
+
+// One epilogue work unit: NI (1 or 2) consecutive query positions of one document row; M <= 20 outputs.
+// 1x1 conv: f outer, output-channel pairs inner -> independent accumulators; packed fp32x2 FMAs (FFMA2) with y[f] as the
+// broadcast scalar operand; the weights come from shared memory as broadcast LDS.128 (w1t[f][m], m contiguous), shared
+// by the NI positions.  Outputs m >= M see zero weights and are ignored at the end.
+template <int NF, int NI>
+__device__ __forceinline__ void mt_epi_unit(uint32_t tacc, int i0, int Lq, bool row_ok, const int* djp, const int* qids,
+                                            const MtEpiConst& ec, const float* w1t, float* mx) {
+  constexpr int FP = 3 * NF;
+  float y[NI][FP];
+#pragma unroll
+  for (int n = 0; n < NI; ++n) tmem_ld_fp<FP>(tacc + n * FP, y[n]);
+  tmem_ld_wait();
+  if (!row_ok || i0 >= Lq) return;
+  int dj[7];
+#pragma unroll
+  for (int bt = 0; bt < 7; ++bt) dj[bt] = djp[bt];
+#pragma unroll
+  for (int n = 0; n < NI; ++n) mt_epi_prep<FP>(y[n], i0 + n, Lq, dj, qids, ec);
+  float2 zz[NI][10];
+#pragma unroll
+  for (int n = 0; n < NI; ++n)
+#pragma unroll
+    for (int m2 = 0; m2 < 10; ++m2) zz[n][m2] = make_float2(ec.b1[2 * m2], ec.b1[2 * m2 + 1]);
+#pragma unroll
+  for (int f = 0; f < FP; ++f) {
+    const float4* wr = reinterpret_cast<const float4*>(w1t + f * MT_TC_MAXM);
+#pragma unroll
+    for (int m4 = 0; m4 < 5; ++m4) {
+      const float4 w4 = wr[m4];
+#pragma unroll
+      for (int n = 0; n < NI; ++n) {
+        ffma2(zz[n][2 * m4], make_float2(w4.x, w4.y), y[n][f]);
+        ffma2(zz[n][2 * m4 + 1], make_float2(w4.z, w4.w), y[n][f]);
+      }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < NI; ++n) {
+    if (i0 + n < Lq) {
+#pragma unroll
+      for (int m2 = 0; m2 < 10; ++m2) {
+        mx[2 * m2] = fmaxf(mx[2 * m2], zz[n][m2].x);
+        mx[2 * m2 + 1] = fmaxf(mx[2 * m2 + 1], zz[n][m2].y);
+      }
+    }
+  }
+}
+
+// General-M (20 < M <= MT_TC_MAXM) unit, one query position, scalar FMAs.
+template <int NF>
+__device__ __forceinline__ void mt_epi_unit_wide(uint32_t tacc, int i, int Lq, bool row_ok, const int* djp, const int* qids,
+                                                 const MtEpiConst& ec, const float* w1t, float* mx) {
+  constexpr int FP = 3 * NF;
+  float y[FP];
+  tmem_ld_fp<FP>(tacc, y);
+  tmem_ld_wait();
+  if (!row_ok || i >= Lq) return;
+  int dj[7];
+#pragma unroll
+  for (int bt = 0; bt < 7; ++bt) dj[bt] = djp[bt];
+  mt_epi_prep<FP>(y, i, Lq, dj, qids, ec);
+  float z[MT_TC_MAXM];
+#pragma unroll
+  for (int m = 0; m < MT_TC_MAXM; ++m) z[m] = ec.b1[m];
+#pragma unroll
+  for (int f = 0; f < FP; ++f) {
+    const float4* wr = reinterpret_cast<const float4*>(w1t + f * MT_TC_MAXM);
+#pragma unroll
+    for (int m4 = 0; m4 < MT_TC_MAXM / 4; ++m4) {
+      const float4 w4 = wr[m4];
+      z[4 * m4 + 0] = fmaf(w4.x, y[f], z[4 * m4 + 0]);
+      z[4 * m4 + 1] = fmaf(w4.y, y[f], z[4 * m4 + 1]);
+      z[4 * m4 + 2] = fmaf(w4.z, y[f], z[4 * m4 + 2]);
+      z[4 * m4 + 3] = fmaf(w4.w, y[f], z[4 * m4 + 3]);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MT_TC_MAXM; ++m) mx[m] = fmaxf(mx[m], z[m]);
+}
+
 template <int NF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     mt_tc_interact_kernel(const uint8_t* __restrict__ aimg, const uint8_t* __restrict__ timg, MtPack p,
@@ -417,19 +555,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   // epilogue weights (exact-match taps, bias, 1x1 conv) come from the constant bank (kernel parameter `ec`):
   // FFMA takes them as immediate c[][] operands, no shared-memory loads in the hot loop
   float* red = reinterpret_cast<float*>(b_ring + (size_t)nstages * stage);  // [8 warps][32]
-  float* w1t = red + MT_TC_MAXM * 8;               // [24][32] 1x1 conv weights, transposed (m contiguous)
+  float* w1t = red + MT_TC_MAXM * TC_EPI_WARPS;               // [24][32] 1x1 conv weights, transposed (m contiguous)
   int* dids = reinterpret_cast<int*>(w1t + 24 * MT_TC_MAXM);
   int* qids = dids + TC_MAXRA + 8;
 
   if (warp == 0) tmem_alloc(&tmem_slot, TC_TCOLS);
-  if (tid == 288) {
+  if (tid == TC_EPI_WARPS * 32) {
     for (int s = 0; s < nstages; ++s) {
       mbar_init(&full_b[s], 1);
       mbar_init(&empty_b[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 8);   // one arrive per epilogue warp
+      mbar_init(&acc_empty[s], TC_EPI_WARPS);   // one arrive per epilogue warp
     }
     mbar_init(&a_full, 1);
     mbar_init(&a_empty, 1);
@@ -442,8 +580,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t tbase = tmem_slot;
 
   // Warp roles: the scheduler favours the highest warp id of an SM sub-partition (wid % 4), so the two latency-
-  // critical single-lane roles are the LAST warps of their sub-partitions: warp 8 = producer, warp 9 = MMA issuer.
-  if (warp == 8) {
+  // critical single-lane roles are the LAST warps of their sub-partitions: warp 12 = producer, warp 13 = MMA issuer.
+  if (warp == TC_EPI_WARPS) {
     // ================= producer: B slabs through the ring =================
     if (lane == 0) {
       uint32_t it = 0;
@@ -463,7 +601,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == TC_EPI_WARPS + 2) {
     // ================= A producer: one bulk copy of the pair's document image, as soon as the previous pair's MMAs retired ======
     if (lane == 0) {
       uint32_t pair_it = 0;
@@ -475,7 +613,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (uint32_t o = 0; o < bytes; o += 16896) bulk_g2s(a_img + o, src + o, min(16896u, bytes - o), &a_full);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == TC_EPI_WARPS + 1) {
     // ================= MMA issuer (whole warp runs the uniform control flow, one elected lane issues) =========
     {
       const uint32_t issue = elect_one();
@@ -544,10 +682,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   } else {
     // ================= epilogue warpgroups (+ A staging) =================
-    const int et = tid;                           // 0..255 (warps 0-7)
-    const int mt = warp >> 2;                     // row tile owned by this warpgroup
+    const int et = tid;                           // 0..TC_EPI_THREADS-1
     const int lane_base = (warp & 3) * 32;        // TMEM lane quarter this warp may read
-    const int jrow = mt * 128 + lane_base + lane; // doc position of this thread
+    const int wq = warp >> 2;                     // this warp's index among the TC_EPI_WARPS/4 warps of its quarter
+    const int nun = nmt * IPT;                    // work units (row tile mt, query position il) of one column tile
     uint32_t tile = 0;
     for (int64_t pl = blockIdx.x; pl < pair_count; pl += gridDim.x) {
       const int64_t pg = pair_begin + pl;
@@ -565,84 +703,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       float mx[MT_TC_MAXM];
 #pragma unroll
       for (int m = 0; m < MT_TC_MAXM; ++m) mx[m] = -INFINITY;
-      int dj[7];
-#pragma unroll
-      for (int bt = 0; bt < 7; ++bt) dj[bt] = dids[jrow + bt];
 
       for (int nt = 0; nt < ntiles; ++nt, ++tile) {
         const int as = tile & 1;
         { TC_T0(); mbar_wait_relaxed(&acc_full[as], (tile >> 1) & 1); if (warp == 0) TC_ACC(4); }
         tc_fence_after();
         const long long te0_ = dbg ? clock64() : 0;
-        if (mt < nmt) {
-          const uint32_t tacc = tbase + ((uint32_t)lane_base << 16) + (uint32_t)(as * 2 + mt) * TC_NROWS;
+        {
+          // Work unit = (row tile mt, TC_NI query positions from il0); units are dealt round-robin to the warps of a quarter.
+          constexpr int G = (IPT + TC_NI - 1) / TC_NI;
 #pragma unroll 1
-          for (int il = 0; il < IPT; ++il) {
-            const int i = nt * IPT + il;
-            float y[32];
-            tmem_ld32(tacc + il * FP, y);   // FP used columns (+ harmless spill-over into allocated columns)
-            tmem_ld_wait();
-            if (i < Lq && jrow < Ld) {
-#pragma unroll
-              for (int f = 0; f < FPP; ++f) y[f] = (f < FP) ? y[f] + ec.bias[f] : 0.f;
-              // exact-match channel: alpha * W7[f, C, a, bt] wherever q[i+a-1] == d[j+bt-3] (PAD==PAD counts)
-#pragma unroll
-              for (int a = 0; a < 3; ++a) {
-                const int ii = i + a - 1;
-                if (ii < 0 || ii >= Lq) continue;
-                const int qi = qids[ii];
-#pragma unroll
-                for (int bt = 0; bt < 7; ++bt) {
-                  if (dj[bt] == qi) {
-#pragma unroll
-                    for (int f = 0; f < FP; ++f) y[f] += ec.wem[a * 7 + bt][f];
-                  }
-                }
-              }
-#pragma unroll
-              for (int f = 0; f < FPP; ++f) y[f] = fmaxf(y[f], 0.f);
-              // 1x1 conv: f outer, m inner -> independent accumulators (no dependent-FMA stalls); the weights
-              // come from shared memory as broadcast LDS.128 (w1t[f][m], m contiguous).  Outputs m >= M see zero
-              // weights and are ignored at the end.
-              if (M <= 20) {
-                // packed fp32x2 FMAs (FFMA2: two output channels per instruction, y[f] as the broadcast scalar operand)
-                float2 zz[10];
-#pragma unroll
-                for (int m2 = 0; m2 < 10; ++m2) zz[m2] = make_float2(ec.b1[2 * m2], ec.b1[2 * m2 + 1]);
-#pragma unroll
-                for (int f = 0; f < FP; ++f) {
-                  const float4* wr = reinterpret_cast<const float4*>(w1t + f * MT_TC_MAXM);
-#pragma unroll
-                  for (int m4 = 0; m4 < 5; ++m4) {
-                    const float4 w4 = wr[m4];
-                    ffma2(zz[2 * m4], make_float2(w4.x, w4.y), y[f]);
-                    ffma2(zz[2 * m4 + 1], make_float2(w4.z, w4.w), y[f]);
-                  }
-                }
-#pragma unroll
-                for (int m2 = 0; m2 < 10; ++m2) {
-                  mx[2 * m2] = fmaxf(mx[2 * m2], zz[m2].x);
-                  mx[2 * m2 + 1] = fmaxf(mx[2 * m2 + 1], zz[m2].y);
-                }
-              } else {
-                float z[MT_TC_MAXM];
-#pragma unroll
-                for (int m = 0; m < MT_TC_MAXM; ++m) z[m] = ec.b1[m];
-#pragma unroll
-                for (int f = 0; f < FP; ++f) {
-                  const float4* wr = reinterpret_cast<const float4*>(w1t + f * MT_TC_MAXM);
-#pragma unroll
-                  for (int m4 = 0; m4 < MT_TC_MAXM / 4; ++m4) {
-                    const float4 w4 = wr[m4];
-                    z[4 * m4 + 0] = fmaf(w4.x, y[f], z[4 * m4 + 0]);
-                    z[4 * m4 + 1] = fmaf(w4.y, y[f], z[4 * m4 + 1]);
-                    z[4 * m4 + 2] = fmaf(w4.z, y[f], z[4 * m4 + 2]);
-                    z[4 * m4 + 3] = fmaf(w4.w, y[f], z[4 * m4 + 3]);
-                  }
-                }
-#pragma unroll
-                for (int m = 0; m < MT_TC_MAXM; ++m) mx[m] = fmaxf(mx[m], z[m]);
-              }
+          for (int un = wq; un < nmt * G; un += TC_EPI_WARPS / 4) {
+            const int mt = un % nmt, il0 = TC_NI * (un / nmt);
+            const int jrow = mt * 128 + lane_base + lane;   // doc position of this thread
+            const uint32_t tacc = tbase + ((uint32_t)lane_base << 16) + (uint32_t)(as * 2 + mt) * TC_NROWS + il0 * FP;
+            const int i0 = nt * IPT + il0;
+            if (M <= 20 && TC_NI == 2 && il0 + 1 < IPT)
+              mt_epi_unit<NF, TC_NI>(tacc, i0, Lq, jrow < Ld, dids + jrow, qids, ec, w1t, mx);
+            else if (M <= 20)
+              mt_epi_unit<NF, 1>(tacc, i0, Lq, jrow < Ld, dids + jrow, qids, ec, w1t, mx);
+            else {
+              for (int n = 0; n < TC_NI && il0 + n < IPT; ++n)
+                mt_epi_unit_wide<NF>(tacc + n * FP, i0 + n, Lq, jrow < Ld, dids + jrow, qids, ec, w1t, mx);
             }
           }
         }
@@ -663,7 +745,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (lane < M) {
           float best = red[lane];
 #pragma unroll
-          for (int w = 1; w < 8; ++w) best = fmaxf(best, red[w * MT_TC_MAXM + lane]);
+          for (int w = 1; w < TC_EPI_WARPS; ++w) best = fmaxf(best, red[w * MT_TC_MAXM + lane]);
           v = best * p.wo[lane];
         }
         v = warp_sum(v);
