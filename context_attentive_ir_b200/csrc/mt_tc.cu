@@ -34,8 +34,8 @@ using namespace umma;
 constexpr int TC_NROWS = 96;      // N of the MMA (columns of one accumulator tile)
 constexpr int TC_TCOLS = 512;     // TMEM columns allocated: 2 stages x 2 row tiles x 96 (384) -> next power of two
 constexpr int TC_MAXRA = 264;     // staged A rows: 2*128 + 6 halo rows, rounded up to 8
-constexpr int TC_EPI_WARPS = 12;  // 3 per SM sub-partition (= TMEM lane quarter)
-constexpr int TC_NI = 1;          // query positions per epilogue work unit (2 = shared weight loads; measured slower: 0.344 vs 0.295 ms)
+constexpr int TC_EPI_WARPS = 8;  // 3 per SM sub-partition (= TMEM lane quarter)
+constexpr int TC_NI = 2;          // query positions per epilogue work unit (2 = shared weight loads; measured slower: 0.344 vs 0.295 ms)
 constexpr int TC_THREADS = (TC_EPI_WARPS + 3) * 32;   // epilogue warps + B producer + MMA issuer + A producer
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 
