@@ -44,7 +44,7 @@ constexpr int MT_TC_MAXM = 32;  // match_filter_size bound of the tcgen05 intera
 struct MtEpiConst {
   float wem[21][24];        // alpha * W7[f, C, a, bt], index a*7+bt
   float bias[24];           // merged conv bias
-  float w1[MT_TC_MAXM][24]; // 1x1 conv
+  float w1t[24][MT_TC_MAXM]; // 1x1 conv, transposed: [f][m] (m contiguous: one 128-bit constant load = 4 output channels)
   float b1[MT_TC_MAXM];
 };
 bool mt_tc_supported(const MtPack& p, int Lq, int Ld);

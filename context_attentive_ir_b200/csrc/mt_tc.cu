@@ -475,15 +475,13 @@ __device__ __forceinline__ void mt_epi_unit(uint32_t tacc, int i0, int Lq, bool 
     for (int m2 = 0; m2 < 10; ++m2) zz[n][m2] = make_float2(ec.b1[2 * m2], ec.b1[2 * m2 + 1]);
 #pragma unroll
   for (int f = 0; f < FP; ++f) {
-    const float4* wr = reinterpret_cast<const float4*>(w1t + f * MT_TC_MAXM);
 #pragma unroll
-    for (int m4 = 0; m4 < 5; ++m4) {
-      const float4 w4 = wr[m4];
+    for (int m2 = 0; m2 < 10; ++m2) {
+      // weights straight from the constant bank (LDCU.128 -> uniform registers -> FFMA2 operand): no shared-memory
+      // traffic - the MMA operand fetches need that bandwidth
+      const float2 w2 = make_float2(ec.w1t[f][2 * m2], ec.w1t[f][2 * m2 + 1]);
 #pragma unroll
-      for (int n = 0; n < NI; ++n) {
-        ffma2(zz[n][2 * m4], make_float2(w4.x, w4.y), y[n][f]);
-        ffma2(zz[n][2 * m4 + 1], make_float2(w4.z, w4.w), y[n][f]);
-      }
+      for (int n = 0; n < NI; ++n) ffma2(zz[n][m2], w2, y[n][f]);
     }
   }
 #pragma unroll
@@ -573,7 +571,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     mbar_init(&a_empty, 1);
     fence_mbar_init();
   }
-  for (int i = tid; i < 24 * MT_TC_MAXM; i += TC_THREADS) w1t[i] = ec.w1[i % MT_TC_MAXM][i / MT_TC_MAXM];
+  for (int i = tid; i < 24 * MT_TC_MAXM; i += TC_THREADS) w1t[i] = ec.w1t[i / MT_TC_MAXM][i % MT_TC_MAXM];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -791,7 +789,7 @@ int32_t mt_epi_const(const MtPack& p, MtEpiConst* out, cudaStream_t s) {
   for (int f = 0; f < p.FPP; ++f) out->bias[f] = bias[f];
   for (int m = 0; m < p.M; ++m) {
     out->b1[m] = b1[m];
-    for (int f = 0; f < p.FPP; ++f) out->w1[m][f] = w1[(size_t)m * p.FPP + f];
+    for (int f = 0; f < p.FPP; ++f) out->w1t[f][m] = w1[(size_t)m * p.FPP + f];
   }
   return CAIR_OK;
 }

@@ -133,13 +133,13 @@ extern "C" int32_t cair_umma_selftest(const float* A, const float* B, float* D, 
 namespace cair {
 using namespace umma;
 __global__ void __launch_bounds__(160) umma_bench_kernel(int N, int K, int reps, int uniform, int nwarps, uint32_t tcols,
-                                                         long long* __restrict__ cycles) {
+                                                         int shift, long long* __restrict__ cycles) {
   extern __shared__ __align__(128) uint8_t sm[];
   __shared__ uint64_t bar[4];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int KC = K / 8;
-  const uint32_t a_plane = 128 * 16, b_plane = N * 16;
+  const uint32_t a_plane = 144 * 16, b_plane = N * 16;
   for (int i = tid; i < (int)((size_t)KC * (a_plane + b_plane) / 16); i += 160) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 0) tmem_alloc(&tmem_slot, tcols);
   if (tid == 0) {
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(160) umma_bench_kernel(int N, int K, int reps,
     long long t0 = clock64();
     if (uniform) {
       const uint32_t issue = elect_one();
-      const uint64_t ad = smem_desc(a0, a_plane, 128), bd = smem_desc(b0, b_plane, 128);
+      const uint64_t ad = smem_desc(a0 + (uint32_t)shift * 16, a_plane, 128), bd = smem_desc(b0, b_plane, 128);
       if (uniform & 2) {
         const uint32_t acol = tmem_slot + 256;  // operand columns (contents irrelevant for timing)
         for (int r = 0; r < reps; ++r)
@@ -193,15 +193,17 @@ __global__ void __launch_bounds__(160) umma_bench_kernel(int N, int K, int reps,
 extern "C" CAIR_API int32_t cair_umma_bench(int32_t N, int32_t K, int32_t reps, int32_t uniform, long long* cycles,
                                             void* stream) {
   using namespace cair;
-  // uniform: bit 0 = warp-uniform issue loop, bits 4.. = number of concurrently issuing warps (default 1)
+  // uniform: bit 0 = warp-uniform issue loop, bits 4..7 = number of concurrently issuing warps (default 1),
+  // bits 8..11 = row shift of the A descriptor (the row-shifted conv taps of the Match-Tensor kernel)
   int nwarps = (uniform >> 4) & 15;
+  const int shift = (uniform >> 8) & 15;
   if (nwarps < 1) nwarps = 1;
   if (nwarps > 4 || nwarps * N > 512) return fail(CAIR_ERR_BAD_ARG, "umma_bench: too many warps / columns");
-  size_t smem = (size_t)(K / 8) * 16 * (128 + N);
+  size_t smem = (size_t)(K / 8) * 16 * (144 + N);
   uint32_t tcols = 32;
   while ((int)tcols < nwarps * N) tcols <<= 1;
   if (uniform & 2) tcols = 512;
   CAIR_CUDA(cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CAIR_LAUNCH(umma_bench_kernel, 1, 160, smem, (cudaStream_t)stream, N, K, reps, uniform & 3, nwarps, tcols, cycles);
+  CAIR_LAUNCH(umma_bench_kernel, 1, 160, smem, (cudaStream_t)stream, N, K, reps, uniform & 3, nwarps, tcols, shift, cycles);
   return CAIR_OK;
 }

@@ -17,6 +17,15 @@ for nw in (1, 2, 4):
         print('warps=%d N=%3d: per-warp issue %.1f cyc/MMA, all retired after %.1f cyc per (MMA of one warp) => %.1f cyc/MMA aggregate (floor %.0f)' % (
             nw, N, o[0] / n, max(o[1:2 * nw:2]) / n, max(o[1:2 * nw:2]) / n / nw, 128 * N / 256))
 
+print('row-shifted A descriptor (start address + 16*shift bytes), N=96, one warp:')
+for shift in range(8):
+    reps, K = 200, 64
+    L.cair_umma_bench(96, K, reps, 1 | (1 << 4) | (shift << 8), C.c_void_p(out.data_ptr()), None)
+    torch.cuda.synchronize()
+    n = reps * K // 16
+    o = out.cpu().tolist()
+    print('  shift=%d: issue %.1f cyc/MMA, retired after %.1f cyc/MMA' % (shift, o[0] / n, o[1] / n))
+
 print('A operand from tensor memory (.ts form):')
 for N in (16, 32, 64, 96, 128, 256):
     reps, K = 200, 64
