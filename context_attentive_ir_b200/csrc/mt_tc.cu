@@ -640,17 +640,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const uint64_t bd_hi = smem_desc(b0 + (uint32_t)s * stage, b_plane, 128);
             const uint32_t accf = bt != 0;
             if (bt < 7) {
+              // 32-bit arithmetic on the descriptor low words (the high words are loop-invariant)
+              const uint32_t dhi = (uint32_t)(ad_hi >> 32), bhi = (uint32_t)(bd_hi >> 32);
+              const uint32_t bl0 = (uint32_t)bd_hi;
 #pragma unroll
               for (int mt = 0; mt < 2; ++mt) {
                 if (mt < nmt) {
                   const uint32_t tacc = tbase + (uint32_t)(as * 2 + mt) * TC_NROWS;
-                  const uint64_t ah = ad_hi + (uint64_t)(mt * 128 + bt), al = ad_lo + (uint64_t)(mt * 128 + bt);
+                  const uint32_t ah0 = (uint32_t)ad_hi + (uint32_t)(mt * 128 + bt), al0 = (uint32_t)ad_lo + (uint32_t)(mt * 128 + bt);
+#pragma unroll 4
                   for (int ks = 0; ks < nks; ++ks) {
-                    const uint64_t ahk = ah + (uint64_t)(ks * a_ks), alk = al + (uint64_t)(ks * a_ks);
-                    const uint64_t bhk = bd_hi + (uint64_t)(ks * b_ks), blk = bhk + (uint64_t)b_lo_off;
-                    mma_bf16_ss_w(tacc, ahk, bhk, idesc, accf | (uint32_t)(ks != 0), issue);
-                    mma_bf16_ss_w(tacc, alk, bhk, idesc, 1, issue);
-                    mma_bf16_ss_w(tacc, ahk, blk, idesc, 1, issue);
+                    const uint32_t ahk = ah0 + (uint32_t)ks * a_ks, alk = al0 + (uint32_t)ks * a_ks;
+                    const uint32_t bhk = bl0 + (uint32_t)ks * b_ks, blk = bhk + b_lo_off;
+                    mma_bf16_ss_w32(tacc, ahk, dhi, bhk, bhi, idesc, accf | (uint32_t)(ks != 0), issue);
+                    mma_bf16_ss_w32(tacc, alk, dhi, bhk, bhi, idesc, 1, issue);
+                    mma_bf16_ss_w32(tacc, ahk, dhi, blk, bhi, idesc, 1, issue);
                   }
                 }
               }
@@ -712,6 +716,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           constexpr int G = (IPT + TC_NI - 1) / TC_NI;
 #pragma unroll 1
           for (int un = wq; un < nmt * G; un += TC_EPI_WARPS / 4) {
+            if (dbg && dbg[15]) continue;   // timing experiment (tools/mt_timing.py): MMA stream without the epilogue math
             const int mt = un % nmt, il0 = TC_NI * (un / nmt);
             const int jrow = mt * 128 + lane_base + lane;   // doc position of this thread
             const uint32_t tacc = tbase + ((uint32_t)lane_base << 16) + (uint32_t)(as * 2 + mt) * TC_NROWS + il0 * FP;

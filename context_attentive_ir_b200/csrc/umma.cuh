@@ -131,6 +131,21 @@ __device__ __forceinline__ void mma_bf16_ss_w(uint32_t tmem_d, uint64_t adesc, u
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue)
       : "memory");
 }
+// Same with the descriptors given as (low word, high word): all address arithmetic of an issue loop then stays in
+// 32-bit uniform adds on the low words (start address >> 4 in bits 0-13, LBO in bits 16-29; the high word - SBO, version,
+// layout - is loop-invariant), instead of 64-bit add/carry pairs per descriptor.
+__device__ __forceinline__ void mma_bf16_ss_w32(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                                uint32_t idesc, uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 ad, bd;\n\t"
+      "mov.b64 ad, {%1, %2};\n\t"
+      "mov.b64 bd, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
 __device__ __forceinline__ void mma_commit_w(uint64_t* bar, uint32_t issue) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"

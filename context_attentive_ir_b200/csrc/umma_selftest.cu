@@ -157,16 +157,23 @@ __global__ void __launch_bounds__(160) umma_bench_kernel(int N, int K, int reps,
     long long t0 = clock64();
     if (uniform) {
       const uint32_t issue = elect_one();
-      const uint64_t ad = smem_desc(a0 + (uint32_t)shift * 16, a_plane, 128), bd = smem_desc(b0, b_plane, 128);
+      const uint64_t ad = smem_desc(a0 + (uint32_t)(shift & 15) * 16, a_plane, 128), bd = smem_desc(b0, b_plane, 128);
       if (uniform & 2) {
         const uint32_t acol = tmem_slot + 256;  // operand columns (contents irrelevant for timing)
         for (int r = 0; r < reps; ++r)
           for (int ks = 0; ks < K / 16; ++ks)
             mma_bf16_ts_w(tbase, acol + (uint32_t)(ks * 8), bd + (uint64_t)(ks * ((2 * b_plane) >> 4)), idesc, 1, issue);
       } else {
+        const int cperiod = shift >> 8;
+        int since = 0;
         for (int r = 0; r < reps; ++r)
-          for (int ks = 0; ks < K / 16; ++ks)
+          for (int ks = 0; ks < K / 16; ++ks) {
             mma_bf16_ss_w(tbase, ad + (uint64_t)(ks * ((2 * a_plane) >> 4)), bd + (uint64_t)(ks * ((2 * b_plane) >> 4)), idesc, 1, issue);
+            if (cperiod && ++since == cperiod) {
+              since = 0;
+              mma_commit_w(&bar[3], issue);   // nobody waits on it: cost of the commit itself in the MMA stream
+            }
+          }
       }
       long long t1 = clock64();
       mma_commit_w(&bar[warp - 1], issue);
@@ -197,6 +204,7 @@ extern "C" CAIR_API int32_t cair_umma_bench(int32_t N, int32_t K, int32_t reps, 
   // bits 8..11 = row shift of the A descriptor (the row-shifted conv taps of the Match-Tensor kernel)
   int nwarps = (uniform >> 4) & 15;
   const int shift = (uniform >> 8) & 15;
+  const int cperiod = (uniform >> 12) & 255;   // bits 12..19: tcgen05.commit (to a spare mbarrier) after every cperiod MMAs, 0 = never
   if (nwarps < 1) nwarps = 1;
   if (nwarps > 4 || nwarps * N > 512) return fail(CAIR_ERR_BAD_ARG, "umma_bench: too many warps / columns");
   size_t smem = (size_t)(K / 8) * 16 * (144 + N);
@@ -204,6 +212,6 @@ extern "C" CAIR_API int32_t cair_umma_bench(int32_t N, int32_t K, int32_t reps, 
   while ((int)tcols < nwarps * N) tcols <<= 1;
   if (uniform & 2) tcols = 512;
   CAIR_CUDA(cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CAIR_LAUNCH(umma_bench_kernel, 1, 160, smem, (cudaStream_t)stream, N, K, reps, uniform & 3, nwarps, tcols, shift, cycles);
+  CAIR_LAUNCH(umma_bench_kernel, 1, 160, smem, (cudaStream_t)stream, N, K, reps, uniform & 3, nwarps, tcols, shift | (cperiod << 8), cycles);
   return CAIR_OK;
 }

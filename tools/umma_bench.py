@@ -26,6 +26,15 @@ for shift in range(8):
     o = out.cpu().tolist()
     print('  shift=%d: issue %.1f cyc/MMA, retired after %.1f cyc/MMA' % (shift, o[0] / n, o[1] / n))
 
+print('tcgen05.commit every P MMAs (N=96, one warp):')
+for P in (0, 36, 18, 9, 3, 1):
+    reps, K = 200, 64
+    L.cair_umma_bench(96, K, reps, 1 | (1 << 4) | (P << 12), C.c_void_p(out.data_ptr()), None)
+    torch.cuda.synchronize()
+    n = reps * K // 16
+    o = out.cpu().tolist()
+    print('  P=%2d: issue %.1f cyc/MMA, retired after %.1f cyc/MMA' % (P, o[0] / n, o[1] / n))
+
 print('A operand from tensor memory (.ts form):')
 for N in (16, 32, 64, 96, 128, 256):
     reps, K = 200, 64
