@@ -36,7 +36,7 @@ constexpr int TC_TCOLS = 512;     // TMEM columns allocated: 2 stages x 2 row ti
 constexpr int TC_MAXRA = 264;     // staged A rows: 2*128 + 6 halo rows, rounded up to 8
 constexpr int TC_EPI_WARPS = 8;  // 3 per SM sub-partition (= TMEM lane quarter)
 constexpr int TC_NI = 2;          // query positions per epilogue work unit (2 = shared weight loads; measured slower: 0.344 vs 0.295 ms)
-constexpr int TC_THREADS = (TC_EPI_WARPS + 3) * 32;   // epilogue warps + B producer + MMA issuer + A producer
+constexpr int TC_THREADS = (TC_EPI_WARPS + 4) * 32;   // epilogue warps + B producer + MMA issuer 0 + A producer + MMA issuer 1
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 
 static inline int tc_cp(int C) { return (C + 15) & ~15; }   // channel stride of the packed stencil weights (w7t) and N of the projection GEMM
@@ -561,14 +561,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (tid == TC_EPI_WARPS * 32) {
     for (int s = 0; s < nstages; ++s) {
       mbar_init(&full_b[s], 1);
-      mbar_init(&empty_b[s], 1);
+      mbar_init(&empty_b[s], nmt);    // one commit per MMA issuer (= per row tile)
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_full[s], nmt);
       mbar_init(&acc_empty[s], TC_EPI_WARPS);   // one arrive per epilogue warp
     }
     mbar_init(&a_full, 1);
-    mbar_init(&a_empty, 1);
+    mbar_init(&a_empty, nmt);
     fence_mbar_init();
   }
   for (int i = tid; i < 24 * MT_TC_MAXM; i += TC_THREADS) w1t[i] = ec.w1t[i / MT_TC_MAXM][i % MT_TC_MAXM];
@@ -611,9 +611,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (uint32_t o = 0; o < bytes; o += 16896) bulk_g2s(a_img + o, src + o, min(16896u, bytes - o), &a_full);
       }
     }
-  } else if (warp == TC_EPI_WARPS + 1) {
-    // ================= MMA issuer (whole warp runs the uniform control flow, one elected lane issues) =========
-    {
+  } else if (warp == TC_EPI_WARPS + 1 || warp == TC_EPI_WARPS + 3) {
+    // ================= MMA issuers (whole warp runs the uniform control flow, one elected lane issues) =========
+    // One issuer warp per 128-row tile: a single warp sustains only one MMA per ~80 cycles through this loop (the
+    // uniform-datapath descriptor arithmetic is on its critical path; tools/umma_bench.py), the tensor pipe takes an
+    // N = 96 MMA every 56 - two independent issue streams keep it fed.  Both read the same B stage and document
+    // image, each commits to the shared barriers (count = number of row tiles).
+    const int mi = warp == TC_EPI_WARPS + 1 ? 0 : 1;
+    if (mi < nmt) {
       const uint32_t issue = elect_one();
       const uint32_t idesc = idesc_bf16_f32(128, TC_NROWS);
       const uint32_t a0 = smem_u32(a_img), b0 = smem_u32(b_ring);
@@ -626,7 +631,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       uint32_t it = 0, tile = 0, pair_it = 0;
       const long long tk0 = dbg ? clock64() : 0;
       for (int64_t pl = blockIdx.x; pl < pair_count; pl += gridDim.x, ++pair_it) {
-        if (dbg && blockIdx.x == 0 && lane == 0) dbg[7] = clock64() - tk0, dbg[8] = pair_it;
+        if (dbg && blockIdx.x == 0 && lane == 0 && mi == 0) dbg[7] = clock64() - tk0, dbg[8] = pair_it;
         { TC_T0(); mbar_wait(&a_full, pair_it & 1); TC_ACC(1); }
         tc_fence_after();
         for (int nt = 0; nt < ntiles; ++nt, ++tile) {
@@ -643,9 +648,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               // 32-bit arithmetic on the descriptor low words (the high words are loop-invariant)
               const uint32_t dhi = (uint32_t)(ad_hi >> 32), bhi = (uint32_t)(bd_hi >> 32);
               const uint32_t bl0 = (uint32_t)bd_hi;
-#pragma unroll
-              for (int mt = 0; mt < 2; ++mt) {
-                if (mt < nmt) {
+              {
+                const int mt = mi;
+                {
                   const uint32_t tacc = tbase + (uint32_t)(as * 2 + mt) * TC_NROWS;
                   const uint32_t ah0 = (uint32_t)ad_hi + (uint32_t)(mt * 128 + bt), al0 = (uint32_t)ad_lo + (uint32_t)(mt * 128 + bt);
 #pragma unroll 4
@@ -659,9 +664,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 }
               }
             } else {
-#pragma unroll
-              for (int mt = 0; mt < 2; ++mt) {
-                if (mt < nmt) {
+              {
+                const int mt = mi;
+                {
                   const uint32_t tacc = tbase + (uint32_t)(as * 2 + mt) * TC_NROWS;
                   for (int ts = 0; ts < k.ntail; ++ts) {
                     const uint32_t arow = at0 + (uint32_t)(mt * 128 + 2 * ts * k.tpc) * 16;
