@@ -56,31 +56,67 @@ def bytes_per_pair_folded():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons sampled DURING the timed regions: NVML in-process (a query takes well under a
+    millisecond; nvidia-smi as a subprocess takes longer than the whole timed region), nvidia-smi as the fallback."""
+
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.active, self.source = index, [], False, False, 'nvml'
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: map through CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(',')[index])
+                except Exception:
+                    phys = index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.source = 'nvidia-smi'
 
-    def run(self):
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flags = [bool(r & n.nvmlClocksThrottleReasonHwSlowdown), bool(r & n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 bool(r & n.nvmlClocksThrottleReasonSwThermalSlowdown), bool(r & n.nvmlClocksThrottleReasonSwPowerCap)]
+        return [sm, mx] + flags
+
+    def _sample_smi(self):
         q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                             capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(',')]
+        return [float(f[0]), float(f[1])] + [x.lower().startswith('active') for x in f[2:6]]
+
+    def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(',')]
-                if len(f) >= 6:
-                    self.rows.append(f)
+                row = self._sample_nvml() if self.nvml else self._sample_smi()
+                if self.active or not self.nvml:
+                    self.rows.append(row)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.001 if self.nvml else 0.05)
 
     def summary(self):
         if not self.rows:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['no clock samples'], source=self.source)
         sm = sorted(float(r[0]) for r in self.rows)
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith('active') for r in self.rows)]
-        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(self.rows[0][1]), reasons=reasons, samples=len(self.rows))
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i] for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_min_mhz=sm[0], sm_max_mhz=float(self.rows[0][1]), reasons=reasons,
+                    samples=len(self.rows), source=self.source + ' (sampled only while a timed region is running)')
 
 
 def make_batch(seed):
@@ -196,12 +232,14 @@ def run_product(args):
         dist.barrier()
     torch.cuda.synchronize()
     n0 = lib.launch_count()
+    sampler.active = True
     for i in range(args.steps):
         flush.fill_(i & 0xff)
         ev[i][0].record(stream)
         step()
         ev[i][1].record(stream)
     torch.cuda.synchronize()
+    sampler.active = False
     launches = lib.launch_count() - n0
     if world > 1:
         dist.barrier()
@@ -241,9 +279,11 @@ def run_product(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    sampler.active = True
     t0 = time.perf_counter()
     e2e_loop(args.steps)
     e2e_total = time.perf_counter() - t0
+    sampler.active = False
     # the synchronous single-call form (forward_host: one cached CUDA graph per call, returns after the D2H)
     for _ in range(3):
         net.forward_host(hq, hql, hd, hdl, out=hout, device=dev)
@@ -342,8 +382,8 @@ def run_product(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-sample-queries', type=int, default=32)
     ap.add_argument('--cpu-sample-seconds', type=float, default=12.0)
