@@ -277,6 +277,18 @@ CAIR_API int32_t cair_ranker_submit_host(cair_handle* h, const int64_t* q, const
                                 int32_t Lq, int32_t Ld, float* scores, int32_t slot, void* stream);
 CAIR_API int32_t cair_ranker_wait_host(cair_handle* h, int32_t slot);
 
+/* ---- ranking metrics of the evaluation loops, on the device ----------
+ * Replaces, per batch, `scores.cpu()` + `np.argsort(-scores)` + MAP / MRR / precision_at_k(1,3,5)
+ * (main/ranker.py:257-264, main/multitask.py:286-293; neuroir/eval/ltorank.py:4-26, 29-47, 104-123)
+ * and, when apply_softmax != 0, the `f.softmax(scores, dim=-1)` of Ranker.predict (models/ranker.py:257-258).
+ * scores [B,N] fp32 and labels [B,N] int64 are DEVICE pointers.  per_row [B,5] (device, float64) receives
+ * average precision, reciprocal rank, precision@1, @3, @5 of every query; batch_mean [5] (device, float64,
+ * may be NULL) their means = the values the reference feeds to its AverageMeters.  Ties are ranked in index
+ * order (numpy's default argsort is unstable: the reference's order inside a tie is implementation-defined).  A row without a relevant document gives NaN (the reference
+ * divides by zero there).  N < 5 is CAIR_ERR_BAD_SHAPE (ltorank.py:41 asserts).  Enqueued on `stream`. */
+CAIR_API int32_t cair_rank_metrics(const float* scores, const int64_t* labels, int32_t B, int32_t N,
+                          int32_t apply_softmax, double* per_row, double* batch_mean, void* stream);
+
 /* ---- CARS ranking path (neuroir/multitask/cars.py:193-304 encode*, :306-458 encode_session,
  *      :460-540 rank/rank_document, :671-691 apply_pooling; neuroir/modules/maxout.py:70-84) --- */
 typedef struct {

@@ -233,6 +233,39 @@ def gen_cars(name, seed, B, S, N, Lq, Ld, E, V, Hq, Hd, Hs, max_clicks=1, **kw):
                                         clicks=clicks, sess_q_attn=sess_attn[0], sess_d_attn=sess_attn[1]))
 
 
+# ------------------------------------------------------------------ ranking metrics (eval/ltorank.py)
+def gen_rank_metrics(name, seed, B, N, max_rel=1, ties=False):
+    """scores -> f.softmax (models/ranker.py:258) -> np.argsort(-scores) -> MAP / MRR / precision_at_k exactly as
+    main/ranker.py:257-264 does, with the reference's own neuroir.eval.ltorank functions."""
+    import torch.nn.functional as f
+    from neuroir.eval.ltorank import MAP, MRR, precision_at_k
+    rng = np.random.RandomState(seed)
+    scores = (rng.randn(B, N) * 3).astype(np.float32)
+    cand = np.arange(N)
+    if ties:
+        # Exact ties.  numpy's default argsort is NOT stable (since 1.25 float keys go through the AVX-512 / AVX2
+        # x86-simd-sort kernels even for a dozen elements), so the reference's order inside a tie is implementation-
+        # defined; the tied documents are kept non-relevant here, which makes every metric independent of that order.
+        scores[:, 1] = scores[:, 0]
+        scores[:, -1] = scores[:, 2]
+        cand = np.arange(3, N - 1)
+    labels = np.zeros((B, N), dtype=np.int64)
+    for b in range(B):
+        k = rng.randint(1, max_rel + 1)
+        labels[b, rng.choice(cand, size=k, replace=False)] = 1
+    probs = f.softmax(torch.from_numpy(scores), dim=-1).numpy()
+    pred = np.argsort(-probs)
+    out = dict(map=np.float64(MAP(pred, labels)), mrr=np.float64(MRR(pred, labels)),
+               p1=np.float64(precision_at_k(pred, labels, 1)), p3=np.float64(precision_at_k(pred, labels, 3)),
+               p5=np.float64(precision_at_k(pred, labels, 5)), predictions=pred.astype(np.int64), probs=probs)
+    os.makedirs(OUT, exist_ok=True)
+    meta = dict(cfg=dict(model='rank_metrics', B=B, N=N), torch=torch.__version__, numpy=np.__version__)
+    arrays = {'meta': np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), 'in/scores': scores, 'in/labels': labels}
+    arrays.update({'out/' + k: np.asarray(v) for k, v in out.items()})
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **arrays)
+    print('wrote', name, 'MAP %.6f MRR %.6f' % (out['map'], out['mrr']))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     _apply_shims()
@@ -240,7 +273,7 @@ def main():
     only = sys.argv[1:]  # optional: fixture-name prefixes to (re)generate
     if only:
         g = globals()
-        for fn in ('gen_esm', 'gen_mt', 'gen_drmm', 'gen_duet', 'gen_cars', 'gen_dssm', 'gen_arc'):
+        for fn in ('gen_esm', 'gen_mt', 'gen_drmm', 'gen_duet', 'gen_cars', 'gen_dssm', 'gen_arc', 'gen_rank_metrics'):
             g[fn] = (lambda f: (lambda name, *a, **k: f(name, *a, **k) if any(name.startswith(o) for o in only) else None))(g[fn])
     # BASELINE configs[0]: the reference's own CPU-runnable case (vocab cut 10k -> 1k to keep the file small)
     gen_esm('esm_cfg1', 1235, B=8, N=5, Lq=10, Ld=50, E=64, V=1000)
@@ -276,6 +309,10 @@ def main():
     # DUET (force_pad shapes: every batch padded to max lens, lengths still variable)
     gen_duet('duet_tiny', 41, B=2, N=3, Lq=8, Ld=30, E=24, V=120, nf=16, overlap=0.2)
     gen_duet('duet_e300', 1239, B=2, N=3, Lq=20, Ld=200, E=300, V=400, nf=64, bos_eos=True, overlap=0.1)
+    # ranking metrics of the evaluation loops (main/ranker.py:257-264)
+    gen_rank_metrics('rank_metrics_n10', 81, B=64, N=10, max_rel=1)
+    gen_rank_metrics('rank_metrics_ties', 82, B=32, N=12, max_rel=3, ties=True)
+    gen_rank_metrics('rank_metrics_n100', 83, B=16, N=100, max_rel=5)
     # CARS ranking path
     gen_cars('cars_tiny', 51, B=2, S=3, N=4, Lq=6, Ld=17, E=24, V=150, Hq=16, Hd=16, Hs=24, max_clicks=1)
     gen_cars('cars_clicks', 52, B=3, S=4, N=5, Lq=8, Ld=30, E=32, V=200, Hq=32, Hd=32, Hs=48, max_clicks=3)

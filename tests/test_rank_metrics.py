@@ -1,0 +1,74 @@
+"""Ranking metrics: oracle vs the reference's own eval/ltorank.py (golden fixtures), CUDA vs oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import oracle_lib as ol
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+import rank_metrics_oracle as rmo  # noqa: E402
+
+FIXTURES = ['rank_metrics_n10', 'rank_metrics_ties', 'rank_metrics_n100']
+
+
+@pytest.mark.parametrize('name', FIXTURES)
+def test_oracle_matches_reference_functions(name):
+    _, ins, _, outs = ol.load_golden(name)
+    mean, rows, pred = rmo.rank_metrics(ins['scores'], ins['labels'])
+    # same ranking as the reference's np.argsort(-softmax) up to the (implementation-defined) order inside exact ties
+    probs = outs['probs']
+    assert np.array_equal(np.take_along_axis(probs, pred, 1), np.take_along_axis(probs, outs['predictions'], 1))
+    if 'ties' not in name:
+        assert np.array_equal(pred, outs['predictions'])
+    ref = np.array([outs['map'], outs['mrr'], outs['p1'], outs['p3'], outs['p5']], dtype=np.float64)
+    assert np.abs(mean - ref).max() < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', FIXTURES)
+def test_cuda_matches_reference_golden(name):
+    from context_attentive_ir_b200.metrics import rank_metrics, rank_metrics_device
+    _, ins, _, outs = ol.load_golden(name)
+    s = torch.from_numpy(ins['scores']).cuda()
+    lab = torch.from_numpy(ins['labels']).cuda()
+    m = rank_metrics(s, lab)
+    ref = dict(zip(('map', 'mrr', 'prec@1', 'prec@3', 'prec@5'), (outs['map'], outs['mrr'], outs['p1'], outs['p3'], outs['p5'])))
+    for k in ref:
+        assert abs(m[k] - float(ref[k])) < 1e-12, (k, m[k], ref[k])
+    _, rows = rank_metrics_device(s, lab)
+    _, orows, _ = rmo.rank_metrics(ins['scores'], ins['labels'])
+    assert np.abs(rows.cpu().numpy() - orows).max() < 1e-12
+
+
+@pytest.mark.gpu
+def test_cuda_vs_oracle_large_and_edge_cases():
+    from context_attentive_ir_b200 import lib
+    from context_attentive_ir_b200.metrics import rank_metrics_device
+    rng = np.random.RandomState(5)
+    for B, N, nrel in [(1280, 10, 1), (37, 500, 7), (3, 4096, 20), (5, 5, 5)]:
+        scores = (rng.randn(B, N) * 4).astype(np.float32)
+        scores[:, N // 2] = scores[:, 0]                       # exact ties
+        labels = np.zeros((B, N), dtype=np.int64)
+        for b in range(B):
+            labels[b, rng.choice(N, size=min(nrel, N), replace=False)] = 1
+        labels[0, 1] = 2                                       # non-binary label: precision counts it, MAP / MRR do not
+        mean, rows = rank_metrics_device(torch.from_numpy(scores).cuda(), torch.from_numpy(labels).cuda())
+        omean, orows, _ = rmo.rank_metrics(scores, labels)
+        assert np.abs(rows.cpu().numpy() - orows).max() < 1e-12, (B, N)
+        assert np.abs(mean.cpu().numpy() - omean).max() < 1e-12, (B, N)
+    # no softmax: rank the given values as they are; a row without a relevant document is NaN, not a crash
+    scores = rng.randn(4, 8).astype(np.float32)
+    labels = np.zeros((4, 8), dtype=np.int64)
+    labels[1:, 3] = 1
+    _, rows = rank_metrics_device(torch.from_numpy(scores).cuda(), torch.from_numpy(labels).cuda(), apply_softmax=False)
+    _, orows, _ = rmo.rank_metrics(scores, labels, apply_softmax=False)
+    r = rows.cpu().numpy()
+    assert np.isnan(r[0, 0]) and np.isnan(orows[0, 0])
+    assert np.abs(r[1:] - orows[1:]).max() < 1e-12 and np.array_equal(r[0, 1:], orows[0, 1:])
+    # fewer than 5 candidates: the reference asserts in precision_at_k(…, 5)
+    with pytest.raises(lib.CairError):
+        rank_metrics_device(torch.zeros(2, 4).cuda(), torch.zeros(2, 4, dtype=torch.int64).cuda())
