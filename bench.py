@@ -259,23 +259,24 @@ def run_product(args):
     value = pairs_total / (ms_per_step / 1e3)
 
     # ---- end-to-end: host ids -> H2D -> score -> D2H scores through the C-ABI host entry points ----
-    # A serving loop over two staging slots (submit_host / wait_host): every step copies its ids from pinned host
-    # memory, scores them and copies the scores back; the copies of step k+1 overlap the kernels of step k.  The L2
-    # flush of every step runs on the compute stream INSIDE the timed region (it costs ~40 us per step).
-    houts = [torch.empty(B, N, dtype=torch.float32).pin_memory() for _ in range(2)]
+    # A serving loop over three staging slots (submit_host / wait_host): every step copies its ids from pinned host
+    # memory, scores them and copies the scores back; up to three steps are in flight (copies of step k+1 and its
+    # document encoder overlap the interaction kernel of step k).  The L2 flush of every step is enqueued ahead of the
+    # step INSIDE the timed region (it costs ~40 us of GPU time per step).
+    houts = [torch.empty(B, N, dtype=torch.float32).pin_memory() for _ in range(3)]
     cstream = torch.cuda.Stream(dev)
 
     def e2e_loop(k):
         with torch.cuda.stream(cstream):
             for i in range(k):
-                if i >= 2:
-                    net.wait_host(i & 1)
+                if i >= 3:
+                    net.wait_host(i % 3)     # scores of step i-3 are on the host; its slot is free again
                 flush.fill_(i & 0xff)
-                net.submit_host(hq, hql, hd, hdl, out=houts[i & 1], slot=i & 1, device=dev, stream=cstream)
-            for i in range(max(0, k - 2), k):
-                net.wait_host(i & 1)
+                net.submit_host(hq, hql, hd, hdl, out=houts[i % 3], slot=i % 3, device=dev, stream=cstream)
+            for i in range(max(0, k - 3), k):
+                net.wait_host(i % 3)
 
-    e2e_loop(4)
+    e2e_loop(7)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -363,8 +364,8 @@ def run_product(args):
                        'l2': 'flushed between steps (256 MiB fill outside the per-step events)',
                        'table': 'eval-mode folded [V,40] fp32 table (built once at handle creation)'},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'api': 'submit_host/wait_host over 2 staging slots (H2D of step k+1 overlaps the kernels of step k); '
-                           'L2 flush inside the timed region',
+                    'api': 'submit_host/wait_host over 3 staging slots: H2D of step k+1 and its document encoder overlap the '
+                           'interaction kernel of step k; L2 flush inside the timed region',
                     'single_call_value': e2e_sync_value,
                     'single_call_api': 'forward_host: H2D + kernels + D2H as one cached CUDA graph, synchronous'},
             'gpu_launches': int(launches), 'clocks': sampler.summary(),

@@ -59,14 +59,22 @@ struct cair_handle {
   cudaStream_t host_stream = nullptr;
   cudaEvent_t host_ev = nullptr;
   int* host_err = nullptr;  // pinned
-  // pipelined host path (cair_ranker_submit_host / cair_ranker_wait_host): two staging slots
+  // pipelined host path (cair_ranker_submit_host / cair_ranker_wait_host): CAIR_PIPE_SLOTS staging slots + workspaces
   struct PipeSlot {
     void* stage = nullptr;
     size_t stage_bytes = 0;
-    cudaEvent_t ev_in = nullptr, ev_done = nullptr;
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    cudaEvent_t ev_in = nullptr, ev_enc = nullptr, ev_done = nullptr;
     int* err = nullptr;  // pinned
     bool busy = false;
-  } pipe[2];
+    bool tail_pending = false;   // encoder enqueued, interaction not yet (cross-batch software pipeline)
+    int B = 0, N = 0, Lq = 0, Ld = 0;
+    float* scores_host = nullptr;
+  } pipe[3];
+  int pipe_last = -1, pipe_last2 = -1;   // slots of the two most recently submitted batches
+  float pipe_frac = 0.33f;               // share of a batch's pairs scored under the NEXT batch's document encoder
+  cudaStream_t hi_stream = nullptr, lo_stream = nullptr;
   cudaStream_t copy_stream = nullptr;
 };
 
@@ -145,11 +153,15 @@ int32_t cair_destroy(cair_handle* h) {
   if (h->host_err) cudaFreeHost(h->host_err);
   for (auto& p : h->pipe) {
     if (p.stage) cudaFree(p.stage);
+    if (p.ws) cudaFree(p.ws);
     if (p.ev_in) cudaEventDestroy(p.ev_in);
+    if (p.ev_enc) cudaEventDestroy(p.ev_enc);
     if (p.ev_done) cudaEventDestroy(p.ev_done);
     if (p.err) cudaFreeHost(p.err);
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->hi_stream) cudaStreamDestroy(h->hi_stream);
+  if (h->lo_stream) cudaStreamDestroy(h->lo_stream);
   delete h;
   return CAIR_OK;
 }
@@ -564,12 +576,54 @@ int32_t cair_ranker_forward_host(cair_handle* h, const int64_t* q, const int64_t
   return CAIR_OK;
 }
 
+namespace {
+
+struct PipeView {
+  int64_t *dq, *dql, *dd, *ddl;
+  float* ds;
+};
+PipeView pipe_view(const cair_handle::PipeSlot& p) {
+  const size_t nq = (size_t)p.B * p.Lq, nd = (size_t)p.B * p.N * p.Ld, nb = (size_t)p.B, nbn = (size_t)p.B * p.N;
+  PipeView v;
+  v.dq = (int64_t*)p.stage;
+  v.dql = v.dq + nq;
+  v.dd = v.dql + nb;
+  v.ddl = v.dd + nd;
+  v.ds = (float*)((char*)p.stage + align_up((nq + nb + nd + nbn) * sizeof(int64_t)));
+  return v;
+}
+
+// Interaction phase of the batch in slot `sl` over the pair sub-range [ib, ib+ic) on stream `st`.
+int32_t pipe_interact(cair_handle* h, int sl, int64_t ib, int64_t ic, int max_ctas, bool join, cudaStream_t st) {
+  cair_handle::PipeSlot& p = h->pipe[sl];
+  const PipeView v = pipe_view(p);
+  Arena ws(p.ws, p.ws_bytes);
+  MtPhase ph;
+  ph.phase = MT_INTERACT, ph.ib = ib, ph.ic = ic, ph.max_ctas = max_ctas, ph.join = join;
+  return mt_forward(h->mt, v.dq, v.dql, v.dd, v.ddl, p.B, p.N, p.Lq, p.Ld, 0, (int64_t)p.B * p.N, v.ds, ws, h->d_err, st,
+                    false, ph);
+}
+
+// Scores + error flag of slot `sl` back to the host on stream `st`, completion event.
+int32_t pipe_finish(cair_handle* h, int sl, cudaStream_t st) {
+  cair_handle::PipeSlot& p = h->pipe[sl];
+  const PipeView v = pipe_view(p);
+  CAIR_CUDA(cudaMemcpyAsync(p.scores_host, v.ds, (size_t)p.B * p.N * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CAIR_CUDA(cudaMemcpyAsync(p.err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CAIR_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int), st));
+  CAIR_CUDA(cudaEventRecord(p.ev_done, st));
+  p.tail_pending = false;
+  return CAIR_OK;
+}
+
+}  // namespace
+
 int32_t cair_ranker_submit_host(cair_handle* h, const int64_t* q, const int64_t* qlen, const int64_t* d,
                                 const int64_t* dlen, int32_t B, int32_t N, int32_t Lq, int32_t Ld, float* scores,
                                 int32_t slot, void* stream) {
   CAIR_TRY(check_ranker_args(h, B, N, Lq, Ld));
   if (!q || !qlen || !d || !dlen || !scores) return fail(CAIR_ERR_BAD_ARG, "ranker_submit_host: null tensor");
-  if (slot < 0 || slot > 1) return fail(CAIR_ERR_BAD_ARG, "ranker_submit_host: slot must be 0 or 1");
+  if (slot < 0 || slot > 2) return fail(CAIR_ERR_BAD_ARG, "ranker_submit_host: slot must be 0, 1 or 2");
   DeviceGuard g(h->device);
   cair_handle::PipeSlot& p = h->pipe[slot];
   if (p.busy) return fail(CAIR_ERR_BAD_ARG, "ranker_submit_host: slot %d submitted again before its wait", slot);
@@ -581,66 +635,128 @@ int32_t cair_ranker_submit_host(cair_handle* h, const int64_t* q, const int64_t*
     CAIR_CUDA(cudaEventCreateWithFlags(&h->host_ev, cudaEventDisableTiming));
     CAIR_CUDA(cudaHostAlloc((void**)&h->host_err, sizeof(int), cudaHostAllocDefault));
   }
-  if (!h->copy_stream) CAIR_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  if (!h->copy_stream) {
+    int lo = 0, hi = 0;
+    CAIR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // numerically lowest = highest priority
+    CAIR_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CAIR_CUDA(cudaStreamCreateWithPriority(&h->hi_stream, cudaStreamNonBlocking, hi));
+    CAIR_CUDA(cudaStreamCreateWithPriority(&h->lo_stream, cudaStreamNonBlocking, lo));
+  }
   if (!p.ev_in) {
     CAIR_CUDA(cudaEventCreateWithFlags(&p.ev_in, cudaEventDisableTiming));
+    CAIR_CUDA(cudaEventCreateWithFlags(&p.ev_enc, cudaEventDisableTiming));
     CAIR_CUDA(cudaEventCreateWithFlags(&p.ev_done, cudaEventDisableTiming));
     CAIR_CUDA(cudaHostAlloc((void**)&p.err, sizeof(int), cudaHostAllocDefault));
     *p.err = 0;
   }
-  if (need > p.stage_bytes) {   // (re)allocation synchronises; steady state never gets here
-    CAIR_CUDA(cudaStreamSynchronize(h->host_stream));
-    if (p.stage) CAIR_CUDA(cudaFree(p.stage));
-    p.stage = nullptr, p.stage_bytes = 0;
-    CAIR_CUDA(cudaMalloc(&p.stage, need));
-    p.stage_bytes = need;
-  }
   size_t wsb = 0;
   CAIR_TRY(cair_ranker_workspace_bytes(h, B, N, Lq, Ld, &wsb));
-  if (wsb > h->ws_bytes) {
-    CAIR_CUDA(cudaStreamSynchronize(h->host_stream));
-    if (h->host_graph) cudaGraphExecDestroy(h->host_graph);   // the cached graph of the synchronous path points into the old workspace
-    h->host_graph = nullptr, h->host_key = cair_handle::HostKey(), h->host_key_hits = 0;
-    if (h->ws) CAIR_CUDA(cudaFree(h->ws));
-    h->ws = nullptr, h->ws_bytes = 0;
-    CAIR_CUDA(cudaMalloc(&h->ws, wsb));
-    h->ws_bytes = wsb;
+  if (need > p.stage_bytes || wsb > p.ws_bytes) {   // (re)allocation synchronises; steady state never gets here
+    CAIR_CUDA(cudaDeviceSynchronize());
+    if (need > p.stage_bytes) {
+      if (p.stage) CAIR_CUDA(cudaFree(p.stage));
+      p.stage = nullptr, p.stage_bytes = 0;
+      CAIR_CUDA(cudaMalloc(&p.stage, need));
+      p.stage_bytes = need;
+    }
+    if (wsb > p.ws_bytes) {
+      if (p.ws) CAIR_CUDA(cudaFree(p.ws));
+      p.ws = nullptr, p.ws_bytes = 0;
+      CAIR_CUDA(cudaMalloc(&p.ws, wsb));
+      p.ws_bytes = wsb;
+    }
   }
-  int64_t* dq = (int64_t*)p.stage;
-  int64_t* dql = dq + nq;
-  int64_t* dd = dql + nb;
-  int64_t* ddl = dd + nd;
-  float* ds = (float*)((char*)p.stage + align_up(in_bytes));
-  cudaStream_t cs = h->copy_stream, hs = stream ? (cudaStream_t)stream : h->host_stream;
-  // ids: host -> this slot's staging area on the copy stream (the slot's previous batch was waited for by the caller)
-  CAIR_CUDA(cudaMemcpyAsync(dq, q, nq * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
-  CAIR_CUDA(cudaMemcpyAsync(dql, qlen, nb * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
-  CAIR_CUDA(cudaMemcpyAsync(dd, d, nd * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
-  CAIR_CUDA(cudaMemcpyAsync(ddl, dlen, nbn * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
+  p.B = B, p.N = N, p.Lq = Lq, p.Ld = Ld, p.scores_host = scores;
+  const PipeView v = pipe_view(p);
+  cudaStream_t us = (cudaStream_t)stream;
+  // everything below is ordered after the work already queued on the caller's stream
+  CAIR_CUDA(cudaEventRecord(h->host_ev, us));
+  cudaStream_t cs = h->copy_stream;
+  CAIR_CUDA(cudaStreamWaitEvent(cs, h->host_ev, 0));
+  CAIR_CUDA(cudaMemcpyAsync(v.dq, q, nq * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
+  CAIR_CUDA(cudaMemcpyAsync(v.dql, qlen, nb * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
+  CAIR_CUDA(cudaMemcpyAsync(v.dd, d, nd * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
+  CAIR_CUDA(cudaMemcpyAsync(v.ddl, dlen, nbn * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
   CAIR_CUDA(cudaEventRecord(p.ev_in, cs));
-  // kernels + scores back on the compute stream, behind the previous batch (shared workspace)
-  CAIR_CUDA(cudaStreamWaitEvent(hs, p.ev_in, 0));
-  CAIR_TRY(cair_ranker_forward(h, dq, dql, dd, ddl, B, N, Lq, Ld, 0, (int64_t)nbn, ds, h->ws, h->ws_bytes, hs));
-  CAIR_CUDA(cudaMemcpyAsync(scores, ds, nbn * sizeof(float), cudaMemcpyDeviceToHost, hs));
-  CAIR_CUDA(cudaMemcpyAsync(p.err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, hs));
-  CAIR_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int), hs));
-  CAIR_CUDA(cudaEventRecord(p.ev_done, hs));
+
+  const bool pipelined = h->model == CAIR_MODEL_MT && mt_can_pipeline(h->mt, Lq, Ld) && !h->prof.on;
+  if (!pipelined) {
+    // plain form: kernels + scores back on one compute stream, behind the previous batch
+    cudaStream_t hs = us ? us : h->host_stream;
+    CAIR_CUDA(cudaStreamWaitEvent(hs, p.ev_in, 0));
+    CAIR_TRY(cair_ranker_forward(h, v.dq, v.dql, v.dd, v.ddl, B, N, Lq, Ld, 0, (int64_t)nbn, v.ds, p.ws, p.ws_bytes, hs));
+    CAIR_TRY(pipe_finish(h, slot, hs));
+    p.busy = true;
+    return CAIR_OK;
+  }
+  // ---- cross-batch software pipeline (Match-Tensor, tcgen05 path) ----
+  // The document encoder is a 200-step dependency chain on ~108 of the 148 SMs; the interaction kernel of the PREVIOUS
+  // batch has no such chain.  Per submit:  lo: interaction part 1 of the previous batch on the SMs the encoder leaves
+  // free  ||  hi: this batch's encoder + projection;  then lo: interaction part 2 of the previous batch on all SMs,
+  // its scores back to the host.  This batch's own interaction is enqueued by the next submit (or by its wait).
+  cudaStream_t H = h->hi_stream, L = h->lo_stream;
+  const int prev = (h->pipe_last >= 0 && h->pipe[h->pipe_last].tail_pending) ? h->pipe_last : -1;
+  int64_t c1 = 0;
+  int free_sms = 0;
+  if (prev >= 0) {
+    cair_handle::PipeSlot& pp = h->pipe[prev];
+    const int64_t pcp = (int64_t)pp.B * pp.N;
+    free_sms = kSMs - lstm_tc_ctas((int)nbn, h->mt.tc_d.dirs);
+    if (free_sms >= 8) c1 = (int64_t)((double)pcp * h->pipe_frac);
+    CAIR_CUDA(cudaStreamWaitEvent(L, pp.ev_enc, 0));
+    if (c1 > 0) CAIR_TRY(pipe_interact(h, prev, 0, c1, free_sms, true, L));   // joins the previous batch's query side
+  }
+  CAIR_CUDA(cudaStreamWaitEvent(H, p.ev_in, 0));
+  // the encoder must not start while the batch before the previous one still holds the machine with its part 2
+  if (h->pipe_last2 >= 0 && h->pipe_last2 != slot && h->pipe[h->pipe_last2].busy)
+    CAIR_CUDA(cudaStreamWaitEvent(H, h->pipe[h->pipe_last2].ev_done, 0));
+  {
+    Arena ws(p.ws, p.ws_bytes);
+    MtPhase ph;
+    ph.phase = MT_ENCODE;
+    CAIR_TRY(mt_forward(h->mt, v.dq, v.dql, v.dd, v.ddl, B, N, Lq, Ld, 0, (int64_t)nbn, v.ds, ws, h->d_err, H, false, ph));
+  }
+  CAIR_CUDA(cudaEventRecord(p.ev_enc, H));
+  if (prev >= 0) {
+    cair_handle::PipeSlot& pp = h->pipe[prev];
+    const int64_t pcp = (int64_t)pp.B * pp.N;
+    CAIR_CUDA(cudaStreamWaitEvent(L, p.ev_enc, 0));   // part 2 gets the whole machine: after this batch's encoder
+    CAIR_TRY(pipe_interact(h, prev, c1, pcp - c1, 0, c1 == 0, L));
+    CAIR_TRY(pipe_finish(h, prev, L));
+  }
+  p.tail_pending = true;
   p.busy = true;
+  h->pipe_last2 = h->pipe_last;
+  h->pipe_last = slot;
   return CAIR_OK;
 }
 
 int32_t cair_ranker_wait_host(cair_handle* h, int32_t slot) {
   if (!h) return fail(CAIR_ERR_BAD_ARG, "null handle");
-  if (slot < 0 || slot > 1) return fail(CAIR_ERR_BAD_ARG, "ranker_wait_host: slot must be 0 or 1");
+  if (slot < 0 || slot > 2) return fail(CAIR_ERR_BAD_ARG, "ranker_wait_host: slot must be 0, 1 or 2");
   DeviceGuard g(h->device);
   cair_handle::PipeSlot& p = h->pipe[slot];
   if (!p.busy) return fail(CAIR_ERR_BAD_ARG, "ranker_wait_host: nothing submitted on slot %d", slot);
+  if (p.tail_pending) {
+    // no later submit took care of this batch's interaction: run it now on the whole machine
+    cudaStream_t L = h->lo_stream;
+    CAIR_CUDA(cudaStreamWaitEvent(L, p.ev_enc, 0));
+    CAIR_TRY(pipe_interact(h, slot, 0, (int64_t)p.B * p.N, 0, true, L));
+    CAIR_TRY(pipe_finish(h, slot, L));
+  }
   CAIR_CUDA(cudaEventSynchronize(p.ev_done));
   p.busy = false;
   const int flags = *p.err;
   *p.err = 0;
   if (flags & ERRF_BAD_TOKEN) return fail(CAIR_ERR_BAD_ARG, "token id outside [0, vocab)");
   if (flags) return fail(CAIR_ERR_BAD_ARG, "sequence length outside [1, padded length]");
+  return CAIR_OK;
+}
+
+int32_t cair_ranker_set_pipeline_split(cair_handle* h, float frac) {
+  if (!h) return fail(CAIR_ERR_BAD_ARG, "null handle");
+  if (!(frac >= 0.f && frac <= 0.9f)) return fail(CAIR_ERR_BAD_ARG, "pipeline split must be in [0, 0.9]");
+  h->pipe_frac = frac;
   return CAIR_OK;
 }
 

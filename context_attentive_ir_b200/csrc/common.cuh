@@ -263,6 +263,8 @@ struct LstmTcPack {
 };
 extern long long* g_lstm_dbg;  // optional role-timing counters (debug)
 bool lstm_tc_supported(int in, int h);
+int lstm_tc_seqs_per_cta(int n, int dirs);
+int lstm_tc_ctas(int n, int dirs);   // grid size lstm_tc_run uses for n sequences
 int32_t lstm_tc_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, int in, int h, LstmTcPack* out,
                      cudaStream_t s);
 // bias: [dirs][4h] = b_ih + b_hh (LstmPack::bias)

@@ -488,6 +488,18 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
   if (warp == 0) tmem_dealloc(tbase, LT_TCOLS);
 }
 
+// Sequences per CTA: the per-step cost is latency + the cell updates of one SM (MUFU / issue bound), not the MMAs
+// (an N = 32 MMA costs the same as a narrower one), so use the fewest sequences per CTA that still fit one wave.
+int lstm_tc_seqs_per_cta(int n, int dirs) {
+  for (int c = 8; c < LT_NSEQ; c += 8)
+    if ((int64_t)((n + c - 1) / c) * dirs <= kSMs) return c;
+  return LT_NSEQ;
+}
+int lstm_tc_ctas(int n, int dirs) {
+  const int spc = lstm_tc_seqs_per_cta(n, dirs);
+  return ((n + spc - 1) / spc) * dirs;
+}
+
 int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, const int64_t* len, int n, int L,
                     float* out, float* h_n, float* c_n, int* err, cudaStream_t s, const char* rec_name, const uint8_t* ximg) {
   if (n <= 0) return CAIR_OK;
@@ -503,12 +515,7 @@ int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, cons
   CAIR_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // Sequences per CTA: the per-step cost is latency + the cell updates of one SM (MUFU / issue bound), not the MMAs
   // (an N = 32 MMA costs the same as a narrower one), so use the fewest sequences per CTA that still fit one wave.
-  int spc = LT_NSEQ;
-  for (int c = 8; c < LT_NSEQ; c += 8)
-    if ((int64_t)((n + c - 1) / c) * p.dirs <= kSMs) {
-      spc = c;
-      break;
-    }
+  const int spc = lstm_tc_seqs_per_cta(n, p.dirs);
   dim3 grid((n + spc - 1) / spc, p.dirs);
   CAIR_LAUNCH(lstm_tc_kernel, grid, LT_THREADS, smem, s, x, p.wimg, bias, len, n, L, p.in, p.h, p.dirs, ks_mask, spc, out,
               h_n, c_n, err, g_lstm_dbg, x.table ? ximg : nullptr);

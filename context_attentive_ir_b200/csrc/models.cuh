@@ -58,7 +58,8 @@ int32_t mt_tc_proj_image(const MtPack& p, const float* enc_d, int Hd, const uint
                          uint8_t* aimg, int Ld, int64_t pair_count, cudaStream_t s);
 int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const uint8_t* timg, const uint8_t* aimg,
                        const int64_t* q, const int64_t* d, int N, int Lq, int Ld, int64_t pair_begin,
-                       int64_t pair_count, int64_t q_begin, int64_t nq, float* scores, cudaStream_t s);
+                       int64_t pair_count, int64_t q_begin, int64_t nq, float* scores, cudaStream_t s,
+                       int max_ctas = 0);
 
 extern long long* g_mt_dbg;  // optional role-timing counters of the tcgen05 interaction kernel (debug)
 enum { MT_IMPL_FP32 = 0, MT_IMPL_TC = 1, MT_IMPL_TC_SPLIT = 2 };  // 2: tcgen05 interaction, fp32 doc projection + image kernel
@@ -78,9 +79,21 @@ struct MtState {
   float *dbg_enc_q = nullptr, *dbg_enc_d = nullptr;
 };
 int32_t mt_create_state(Owned& own, const cair_mt_weights& w, MtState* st, cudaStream_t s);
+// Phases of one forward, for the cross-batch software pipeline of cair_ranker_submit_host: MT_ALL = everything on `s`;
+// MT_ENCODE = query side (forked stream) + document encoder + channel projection / operand image; MT_INTERACT = the
+// interaction kernel over the sub-range [ib, ib+ic) of the pair slice, on at most max_ctas CTAs (0 = all SMs), after
+// joining the query side when `join` is set.  The workspace layout is identical in all phases.
+enum { MT_ALL = 0, MT_ENCODE = 1, MT_INTERACT = 2 };
+struct MtPhase {
+  int phase = MT_ALL;
+  int64_t ib = 0, ic = -1;
+  int max_ctas = 0;
+  bool join = true;
+};
+bool mt_can_pipeline(const MtState& st, int Lq, int Ld);
 int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, const int64_t* d, const int64_t* dlen,
                    int B, int N, int Lq, int Ld, int64_t pb, int64_t pc, float* scores, Arena& ws, int* err,
-                   cudaStream_t s, bool dry);
+                   cudaStream_t s, bool dry, MtPhase ph = MtPhase());
 
 // ---- DSSM / CDSSM ----
 struct DssmState {

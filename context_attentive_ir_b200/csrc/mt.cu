@@ -296,7 +296,7 @@ int32_t mt_create_state(Owned& own, const cair_mt_weights& w, MtState* st, cudaS
 
 int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, const int64_t* d, const int64_t* dlen,
                    int B, int N, int Lq, int Ld, int64_t pb, int64_t pc, float* scores, Arena& ws, int* err,
-                   cudaStream_t s, bool dry) {
+                   cudaStream_t s, bool dry, MtPhase ph) {
   (void)B;
   // queries touched by the pair slice [pb, pb+pc)
   const int64_t qb = pc > 0 ? pb / N : 0;
@@ -323,6 +323,17 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
   }
   if (dry || pc <= 0) return CAIR_OK;
   if (!ws.ok()) return fail(CAIR_ERR_WORKSPACE, "match_tensor: workspace too small");
+  if (ph.phase != MT_ALL && !(use_tc && st.wd_img && st.impl == MT_IMPL_TC))
+    return fail(CAIR_ERR_UNSUPPORTED, "match_tensor: phased forward needs the tcgen05 path");
+  if (ph.phase == MT_INTERACT) {
+    const int64_t ic = ph.ic < 0 ? pc - ph.ib : ph.ic;
+    if (ph.ib < 0 || ic < 0 || ph.ib + ic > pc) return fail(CAIR_ERR_BAD_ARG, "match_tensor: bad interaction sub-range");
+    if (ph.join && st.side) CAIR_CUDA(cudaStreamWaitEvent(s, st.ev_join, 0));
+    size_t tb, ab;
+    mt_tc_workspace(st.pack, nq, pc, Lq, Ld, &tb, &ab);
+    return mt_tc_interact(st.pack, st.epi, timg, aimg + (size_t)ph.ib * (ab / (size_t)pc), q, d, N, Lq, Ld, pb + ph.ib, ic,
+                          qb, nq, scores, s, ph.max_ctas);
+  }
   const int64_t* qs = q + qb * Lq;
   const int64_t* ds = d + pb * Ld;
   // The query side (encoder, channel projection, T operand) depends only on the queries: it runs on the handle's
@@ -362,6 +373,7 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
     if (st.wd_img && st.impl == MT_IMPL_TC) {
       // tcgen05 projection written straight into the interaction kernel's operand image
       CAIR_TRY(mt_tc_proj_image(st.pack, enc_d, st.Hd, st.wd_img, st.bd, aimg, Ld, pc, s));
+      if (ph.phase == MT_ENCODE) return CAIR_OK;   // the interaction phase joins the query side
     } else {
       CAIR_TRY(gemm_f32(gemm_dense(enc_d, st.Hd), st.wd, st.bd, cd, st.C, pc * Ld, st.C, st.Hd, ACT_NONE, s));
       CAIR_TRY(mt_tc_doc_image(st.pack, cd, aimg, Ld, pc, s));
@@ -373,6 +385,10 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
   CAIR_TRY(gemm_f32(gemm_dense(enc_d, st.Hd), st.wd, st.bd, cd, st.C, pc * Ld, st.C, st.Hd, ACT_NONE, s));
   if (st.side) CAIR_CUDA(cudaStreamWaitEvent(s, st.ev_join, 0));
   return mt_interact(st.pack, cq, cd, T, q, d, N, Lq, Ld, pb, pc, qb, nq, scores, s);
+}
+
+bool mt_can_pipeline(const MtState& st, int Lq, int Ld) {
+  return st.impl == MT_IMPL_TC && st.wd_img != nullptr && st.side != nullptr && mt_tc_supported(st.pack, Lq, Ld);
 }
 
 }  // namespace cair

@@ -852,7 +852,7 @@ int32_t mt_tc_proj_image(const MtPack& p, const float* enc_d, int Hd, const uint
 
 int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const uint8_t* timg, const uint8_t* aimg, const int64_t* q,
                        const int64_t* d, int N, int Lq, int Ld, int64_t pair_begin, int64_t pair_count, int64_t q_begin,
-                       int64_t nq, float* scores, cudaStream_t s) {
+                       int64_t nq, float* scores, cudaStream_t s, int max_ctas) {
   (void)nq;
   if (pair_count <= 0) return CAIR_OK;
   const TcK k = tc_k(p.C);
@@ -860,7 +860,8 @@ int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const uint8_t* tim
   const int nstages = tc_stages(p, Lq);
   const size_t smem = tc_a_bytes(k) + (size_t)nstages * tc_stage_bytes(k) + tc_misc_bytes(p, Lq);
   prof_mark("interact", s);
-  const unsigned grid = (unsigned)(pair_count < kSMs ? pair_count : kSMs);
+  unsigned grid = (unsigned)(pair_count < kSMs ? pair_count : kSMs);
+  if (max_ctas > 0 && grid > (unsigned)max_ctas) grid = (unsigned)max_ctas;
   if (p.nf == 6) {
     CAIR_CUDA(cudaFuncSetAttribute(mt_tc_interact_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CAIR_LAUNCH(mt_tc_interact_kernel<6>, grid, TC_THREADS, smem, s, aimg, timg, p, ec, q, d, N, Lq, Ld, ntiles,

@@ -199,8 +199,10 @@ class _Ranker(_CairModule):
 
     def submit_host(self, q, qlen, d, dlen, out, slot, device=None, stream=None):
         """Pipelined form of forward_host: enqueue H2D of the (pinned) id tensors, the scoring kernels and the D2H
-        of the scores into `out` (pinned) without waiting; slot 0/1 alternate so that the copies of one batch overlap
-        the kernels of the previous one.  Call wait_host(slot) before reading `out` or re-using the slot."""
+        of the scores into `out` (pinned) without waiting; up to three batches (slots 0, 1, 2) are in flight, so the copies
+        of one batch overlap the kernels of the previous one and, for Match-Tensor, the interaction kernel of batch k
+        runs partly under the document encoder of batch k+1.  Call wait_host(slot) before reading `out` or re-using
+        the slot."""
         dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         B, Lq = q.shape
         _, N, Ld = d.shape

@@ -265,17 +265,23 @@ CAIR_API int32_t cair_ranker_forward(cair_handle* h, const int64_t* q, const int
 CAIR_API int32_t cair_ranker_forward_host(cair_handle* h, const int64_t* q, const int64_t* qlen,
                                  const int64_t* d, const int64_t* dlen, int32_t B, int32_t N,
                                  int32_t Lq, int32_t Ld, float* scores, void* stream);
-/* Pipelined form of cair_ranker_forward_host for a serving loop (what Ranker.predict does per batch,
- * neuroir/models/ranker.py:236-258: .cuda(non_blocking) of the ids, forward, scores back to the host):
- * submit enqueues H2D of the ids on a copy stream, the scoring kernels and the D2H of the scores on the
- * compute stream (`stream`, or a stream owned by the handle when NULL), and returns without waiting; `slot` (0 or 1) selects one of two device staging
- * areas, so the copies of batch k+1 overlap the kernels of batch k.  wait blocks until that slot's scores
- * are in `scores` and reports bad token ids / lengths like the synchronous call.  The host buffers of a
- * slot must stay valid and unmodified until its wait returns; a slot is re-submitted only after its wait. */
+/* Pipelined form of cair_ranker_forward_host for a serving loop (what the reference does per batch in
+ * main/ranker.py:252-264: Ranker.predict = .cuda(non_blocking) of the ids, forward, scores back to the host).
+ * submit enqueues the H2D copies of the ids (copy stream), the scoring kernels and the D2H copy of the scores,
+ * ordered after the work already queued on `stream`, and returns without waiting.  `slot` (0, 1 or 2) selects
+ * one of three device staging areas + workspaces, so up to three batches are in flight: the copies of batch k+1
+ * overlap the kernels of batch k, and for Match-Tensor (tcgen05 path) the batches are software-pipelined on the
+ * device as well - the interaction kernel of batch k runs partly on the SMs that the 200-step document-encoder
+ * recurrence of batch k+1 leaves idle (internal high / low priority streams; cair_ranker_set_pipeline_split
+ * sets the share of a batch's pairs scored there, default 0.33).  wait blocks until that slot's scores are in
+ * `scores` and reports bad token ids / lengths like the synchronous call (with several batches in flight a bad
+ * id is reported by the first wait after it was detected).  The host buffers of a slot must stay valid and
+ * unmodified until its wait returns; a slot is re-submitted only after its wait. */
 CAIR_API int32_t cair_ranker_submit_host(cair_handle* h, const int64_t* q, const int64_t* qlen,
                                 const int64_t* d, const int64_t* dlen, int32_t B, int32_t N,
                                 int32_t Lq, int32_t Ld, float* scores, int32_t slot, void* stream);
 CAIR_API int32_t cair_ranker_wait_host(cair_handle* h, int32_t slot);
+CAIR_API int32_t cair_ranker_set_pipeline_split(cair_handle* h, float frac);
 
 /* ---- ranking metrics of the evaluation loops, on the device ----------
  * Replaces, per batch, `scores.cpu()` + `np.argsort(-scores)` + MAP / MRR / precision_at_k(1,3,5)

@@ -298,17 +298,27 @@ def test_match_tensor_full_cfg2_properties():
         out.zero_()
         hs = net.forward_host(*host, out=out)
         assert torch.equal(hs, s.cpu())
-    # (4b) pipelined submit/wait over two slots: same scores, several batches in flight
-    outs2 = [torch.zeros(B, N, dtype=torch.float32).pin_memory() for _ in range(2)]
-    for it in range(5):
-        if it >= 2:
-            net.wait_host(it % 2)
-            assert torch.equal(outs2[it % 2], s.cpu())
-            outs2[it % 2].zero_()
-        net.submit_host(*host, out=outs2[it % 2], slot=it % 2)
-    for sl in (1, 0):
-        net.wait_host(sl)
-        assert torch.equal(outs2[sl], s.cpu())
+    # (4b) pipelined submit/wait: same scores with 1, 2 and 3 batches in flight (the cross-batch software pipeline
+    # scores part of batch k under the document encoder of batch k+1), for several pipeline splits, on fresh inputs
+    outs3 = [torch.zeros(B, N, dtype=torch.float32).pin_memory() for _ in range(3)]
+    batch2 = synth.ranker_batch(4321, B, N, 20, 200, cfg['src_vocab_size'], variable=True)
+    host2 = [torch.from_numpy(batch2[k]).pin_memory() for k in ('q', 'qlen', 'd', 'dlen')]
+    with torch.no_grad():
+        s2 = net(*helpers.to_dev(batch2, DEV)).cpu()
+    feeds, refs = [host, host2], [s.cpu(), s2]
+    for frac in (0.33, 0.0, 0.6):
+        lib.check(lib.load().cair_ranker_set_pipeline_split(net._cair_handle, frac))
+        for depth in (1, 2, 3):
+            n_it = 7
+            for it in range(n_it + depth):
+                if it >= depth:
+                    j = it - depth
+                    net.wait_host(j % 3)
+                    assert torch.equal(outs3[j % 3], refs[j % 2]), (frac, depth, j)
+                    outs3[j % 3].zero_()
+                if it < n_it:
+                    net.submit_host(*feeds[it % 2], out=outs3[it % 3], slot=it % 3)
+    lib.check(lib.load().cair_ranker_set_pipeline_split(net._cair_handle, 0.33))
     # (5) the spot-checked oracle agrees on a few pairs of the big batch
     idx = [0, 57, 127]
     ref = ol.run_ranker(cfg, helpers.state_dict_numpy(net), batch['q'][idx], batch['qlen'][idx], batch['d'][idx],
