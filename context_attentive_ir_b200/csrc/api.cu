@@ -65,13 +65,15 @@ struct cair_handle {
     size_t stage_bytes = 0;
     void* ws = nullptr;
     size_t ws_bytes = 0;
-    cudaEvent_t ev_in = nullptr, ev_enc = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_enc = nullptr, ev_done = nullptr, ev_int = nullptr;   // ev_int: interaction kernels done
     int* err = nullptr;  // pinned
     bool busy = false;
     bool tail_pending = false;   // encoder enqueued, interaction not yet (cross-batch software pipeline)
     int B = 0, N = 0, Lq = 0, Ld = 0;
     float* scores_host = nullptr;
+    cudaEvent_t tr[8] = {};   // optional trace (timing events): enc begin/end, part 1 begin/end, part 2 begin/end, finish
   } pipe[3];
+  bool pipe_trace = false;
   int pipe_last = -1, pipe_last2 = -1;   // slots of the two most recently submitted batches
   float pipe_frac = 0.33f;               // share of a batch's pairs scored under the NEXT batch's document encoder
   cudaStream_t hi_stream = nullptr, lo_stream = nullptr;
@@ -157,6 +159,9 @@ int32_t cair_destroy(cair_handle* h) {
     if (p.ev_in) cudaEventDestroy(p.ev_in);
     if (p.ev_enc) cudaEventDestroy(p.ev_enc);
     if (p.ev_done) cudaEventDestroy(p.ev_done);
+    if (p.ev_int) cudaEventDestroy(p.ev_int);
+    for (auto& e : p.tr)
+      if (e) cudaEventDestroy(e);
     if (p.err) cudaFreeHost(p.err);
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -593,6 +598,14 @@ PipeView pipe_view(const cair_handle::PipeSlot& p) {
   return v;
 }
 
+int32_t pipe_mark(cair_handle* h, int sl, int i, cudaStream_t st) {
+  if (!h->pipe_trace) return CAIR_OK;
+  cair_handle::PipeSlot& p = h->pipe[sl];
+  if (!p.tr[i]) CAIR_CUDA(cudaEventCreate(&p.tr[i]));
+  CAIR_CUDA(cudaEventRecord(p.tr[i], st));
+  return CAIR_OK;
+}
+
 // Interaction phase of the batch in slot `sl` over the pair sub-range [ib, ib+ic) on stream `st`.
 int32_t pipe_interact(cair_handle* h, int sl, int64_t ib, int64_t ic, int max_ctas, bool join, cudaStream_t st) {
   cair_handle::PipeSlot& p = h->pipe[sl];
@@ -608,6 +621,7 @@ int32_t pipe_interact(cair_handle* h, int sl, int64_t ib, int64_t ic, int max_ct
 int32_t pipe_finish(cair_handle* h, int sl, cudaStream_t st) {
   cair_handle::PipeSlot& p = h->pipe[sl];
   const PipeView v = pipe_view(p);
+  CAIR_CUDA(cudaEventRecord(p.ev_int, st));   // the machine is free again: the next encoder need not wait for the copies
   CAIR_CUDA(cudaMemcpyAsync(p.scores_host, v.ds, (size_t)p.B * p.N * sizeof(float), cudaMemcpyDeviceToHost, st));
   CAIR_CUDA(cudaMemcpyAsync(p.err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
   CAIR_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int), st));
@@ -646,6 +660,7 @@ int32_t cair_ranker_submit_host(cair_handle* h, const int64_t* q, const int64_t*
     CAIR_CUDA(cudaEventCreateWithFlags(&p.ev_in, cudaEventDisableTiming));
     CAIR_CUDA(cudaEventCreateWithFlags(&p.ev_enc, cudaEventDisableTiming));
     CAIR_CUDA(cudaEventCreateWithFlags(&p.ev_done, cudaEventDisableTiming));
+    CAIR_CUDA(cudaEventCreateWithFlags(&p.ev_int, cudaEventDisableTiming));
     CAIR_CUDA(cudaHostAlloc((void**)&p.err, sizeof(int), cudaHostAllocDefault));
     *p.err = 0;
   }
@@ -704,25 +719,32 @@ int32_t cair_ranker_submit_host(cair_handle* h, const int64_t* q, const int64_t*
     free_sms = kSMs - lstm_tc_ctas((int)nbn, h->mt.tc_d.dirs);
     if (free_sms >= 8) c1 = (int64_t)((double)pcp * h->pipe_frac);
     CAIR_CUDA(cudaStreamWaitEvent(L, pp.ev_enc, 0));
+    CAIR_TRY(pipe_mark(h, prev, 2, L));
     if (c1 > 0) CAIR_TRY(pipe_interact(h, prev, 0, c1, free_sms, true, L));   // joins the previous batch's query side
+    CAIR_TRY(pipe_mark(h, prev, 3, L));
   }
   CAIR_CUDA(cudaStreamWaitEvent(H, p.ev_in, 0));
   // the encoder must not start while the batch before the previous one still holds the machine with its part 2
   if (h->pipe_last2 >= 0 && h->pipe_last2 != slot && h->pipe[h->pipe_last2].busy)
-    CAIR_CUDA(cudaStreamWaitEvent(H, h->pipe[h->pipe_last2].ev_done, 0));
+    CAIR_CUDA(cudaStreamWaitEvent(H, h->pipe[h->pipe_last2].ev_int, 0));
+  CAIR_TRY(pipe_mark(h, slot, 0, H));
   {
     Arena ws(p.ws, p.ws_bytes);
     MtPhase ph;
     ph.phase = MT_ENCODE;
     CAIR_TRY(mt_forward(h->mt, v.dq, v.dql, v.dd, v.ddl, B, N, Lq, Ld, 0, (int64_t)nbn, v.ds, ws, h->d_err, H, false, ph));
   }
+  CAIR_TRY(pipe_mark(h, slot, 1, H));
   CAIR_CUDA(cudaEventRecord(p.ev_enc, H));
   if (prev >= 0) {
     cair_handle::PipeSlot& pp = h->pipe[prev];
     const int64_t pcp = (int64_t)pp.B * pp.N;
     CAIR_CUDA(cudaStreamWaitEvent(L, p.ev_enc, 0));   // part 2 gets the whole machine: after this batch's encoder
+    CAIR_TRY(pipe_mark(h, prev, 4, L));
     CAIR_TRY(pipe_interact(h, prev, c1, pcp - c1, 0, c1 == 0, L));
+    CAIR_TRY(pipe_mark(h, prev, 5, L));
     CAIR_TRY(pipe_finish(h, prev, L));
+    CAIR_TRY(pipe_mark(h, prev, 6, L));
   }
   p.tail_pending = true;
   p.busy = true;
@@ -750,6 +772,25 @@ int32_t cair_ranker_wait_host(cair_handle* h, int32_t slot) {
   *p.err = 0;
   if (flags & ERRF_BAD_TOKEN) return fail(CAIR_ERR_BAD_ARG, "token id outside [0, vocab)");
   if (flags) return fail(CAIR_ERR_BAD_ARG, "sequence length outside [1, padded length]");
+  return CAIR_OK;
+}
+
+// Debug: with on != 0 the pipelined submits record timing events; cair_ranker_pipeline_trace returns, for a slot whose
+// wait has returned, the times in ms relative to the begin of its encoder: encoder end, part 1 begin / end,
+// part 2 begin / end, finish (scores on the host).
+extern "C" __attribute__((visibility("default"))) int32_t cair_ranker_pipeline_trace(cair_handle* h, int32_t on, int32_t slot,
+                                                                                      float* ms6) {
+  if (!h) return fail(CAIR_ERR_BAD_ARG, "null handle");
+  h->pipe_trace = on != 0;
+  if (!ms6 || slot < 0 || slot > 2) return CAIR_OK;
+  cair_handle::PipeSlot& p = h->pipe[slot];
+  for (int i = 1; i <= 6; ++i) {
+    ms6[i - 1] = -1.f;
+    if (p.tr[0] && p.tr[i] && cudaEventElapsedTime(&ms6[i - 1], p.tr[0], p.tr[i]) != cudaSuccess) {
+      ms6[i - 1] = -1.f;
+      cudaGetLastError();
+    }
+  }
   return CAIR_OK;
 }
 
