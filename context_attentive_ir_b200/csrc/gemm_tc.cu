@@ -5,10 +5,11 @@
 //
 // One CTA computes a 128-row x NT-column tile (NT <= 256): the weights are pre-packed ONCE (gemm_tc_pack) as bf16
 // hi/lo operand images per (column tile, 64-wide K chunk) and streamed with cp.async.bulk; the A chunk is loaded
-// fp32 by 128 loader threads (thread <-> row, 16 independent 128-bit loads in flight), split into hi/lo bf16 and
+// fp32 by 256 loader threads (two per row, 8 independent 128-bit loads in flight each), split into hi/lo bf16 and
 // written in operand-image order; one elected lane issues 4 k-steps x 3 passes of tcgen05.mma per chunk; the
-// epilogue reads TMEM (thread <-> row), adds bias, applies the activation and stores 128-byte row segments.
-// Ring of 2 stages: loads of chunk k+1 overlap the MMAs of chunk k.
+// epilogue reads TMEM (thread <-> row), transposes the tile through shared memory, adds bias, applies the
+// activation and stores coalesced 128-byte row segments.
+// Ring of 2-4 stages (as many as fit): the loads of the next chunks overlap the MMAs of chunk k.
 #include "models.cuh"
 #include "umma.cuh"
 
@@ -18,8 +19,9 @@ using namespace umma;
 
 constexpr int GT_BM = 128;        // rows per CTA
 constexpr int GT_BK = 64;         // K chunk
-constexpr int GT_STAGES = 2;
-constexpr int GT_THREADS = 192;   // warps 0-3 loaders + epilogue, warp 4 W producer, warp 5 MMA issuer
+constexpr int GT_MAXSTAGES = 4;   // ring depth: as many (A chunk + W chunk) stages as fit in shared memory, 2..4
+constexpr int GT_LWARPS = 8;      // loader / epilogue warps: two threads per row (32 K elements each)
+constexpr int GT_THREADS = (GT_LWARPS + 2) * 32;   // + W producer warp + MMA issuer warp
 constexpr uint32_t GT_APLANE = GT_BM * 16;
 constexpr uint32_t GT_AIMG = (GT_BK / 8) * GT_APLANE;  // one (hi|lo) A chunk image: 16 KB
 
@@ -72,21 +74,21 @@ __device__ __forceinline__ void gt_arrive(uint64_t* bar) {
 // smem: A ring [stages][hi|lo] | W ring [stages][hi|lo]
 __global__ void __launch_bounds__(GT_THREADS, 1)
     gemm_tc_kernel(GemmA a, const uint8_t* __restrict__ wimg, const float* __restrict__ bias, float* __restrict__ c,
-                   int64_t ldc, int64_t M, int N, int K, int NT, int nkc, int act, uint32_t tcols) {
+                   int64_t ldc, int64_t M, int N, int K, int NT, int nkc, int act, uint32_t tcols, int nst) {
   extern __shared__ __align__(128) uint8_t smraw[];
-  __shared__ uint64_t a_full[GT_STAGES], w_full[GT_STAGES], empty[GT_STAGES], acc_full;
+  __shared__ uint64_t a_full[GT_MAXSTAGES], w_full[GT_MAXSTAGES], empty[GT_MAXSTAGES], acc_full;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t m0 = (int64_t)blockIdx.x * GT_BM;
   const int ct = blockIdx.y;
   const uint32_t w_plane = (uint32_t)NT * 16, w_half = (GT_BK / 8) * w_plane;
   uint8_t* a_ring = smraw;
-  uint8_t* w_ring = a_ring + GT_STAGES * 2 * GT_AIMG;
+  uint8_t* w_ring = a_ring + (size_t)nst * 2 * GT_AIMG;
 
   if (warp == 0) tmem_alloc(&tmem_slot, tcols);
-  if (tid == 160) {
-    for (int s = 0; s < GT_STAGES; ++s) {
-      mbar_init(&a_full[s], 4);   // one arrive per loader warp
+  if (tid == GT_LWARPS * 32) {
+    for (int s = 0; s < nst; ++s) {
+      mbar_init(&a_full[s], GT_LWARPS);   // one arrive per loader warp
       mbar_init(&w_full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -98,28 +100,28 @@ __global__ void __launch_bounds__(GT_THREADS, 1)
   tc_fence_after();
   const uint32_t tbase = tmem_slot;
 
-  if (warp == 4) {
+  if (warp == GT_LWARPS) {
     // ---- W producer ----
     if (lane == 0) {
       const uint8_t* src = wimg + (size_t)ct * nkc * 2 * w_half;
       for (int kc = 0; kc < nkc; ++kc) {
-        const int s = kc % GT_STAGES;
-        mbar_wait_relaxed(&empty[s], ((kc / GT_STAGES) & 1) ^ 1);
+        const int s = kc % nst;
+        mbar_wait_relaxed(&empty[s], ((kc / nst) & 1) ^ 1);
         const uint32_t bytes = 2 * w_half;
         mbar_arrive_expect_tx(&w_full[s], bytes);
         uint8_t* dst = w_ring + (size_t)s * bytes;
         for (uint32_t o = 0; o < bytes; o += 32768) bulk_g2s(dst + o, src + (size_t)kc * bytes + o, min(32768u, bytes - o), &w_full[s]);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == GT_LWARPS + 1) {
     // ---- MMA issuer ----
     const uint32_t issue = elect_one();
     const uint32_t idesc = idesc_bf16_f32(128, NT);
     const uint64_t ad0 = smem_desc(smem_u32(a_ring), GT_APLANE, 128);
     const uint64_t wd0 = smem_desc(smem_u32(w_ring), w_plane, 128);
     for (int kc = 0; kc < nkc; ++kc) {
-      const int s = kc % GT_STAGES;
-      const uint32_t ph = (kc / GT_STAGES) & 1;
+      const int s = kc % nst;
+      const uint32_t ph = (kc / nst) & 1;
       mbar_wait(&a_full[s], ph);
       mbar_wait(&w_full[s], ph);
       tc_fence_after();
@@ -137,32 +139,56 @@ __global__ void __launch_bounds__(GT_THREADS, 1)
     mma_commit_w(&acc_full, issue);
   } else {
     // ---- A loaders (thread <-> row), then epilogue ----
-    const int64_t r = m0 + tid;
+    // thread <-> (row, half of the K chunk): 8 independent 128-bit loads in flight per thread
+    const int row = tid & (GT_BM - 1), hp = tid >> 7;
+    const int64_t r = m0 + row;
     const bool rvalid = r < M;
+    constexpr int NV = GT_BK / 8;   // float4 slices per thread
+    // gathered rows: (sequence, first position) of this thread's row, hoisted out of the chunk loop
+    const int64_t gseq = a.table ? r / a.T : 0;
+    const int gt0 = a.table ? (int)(r - gseq * a.T) - a.pad : 0;
+    bool bad_id = false;
     for (int kc = 0; kc < nkc; ++kc) {
-      const int s = kc % GT_STAGES;
-      mbar_wait_relaxed(&empty[s], ((kc / GT_STAGES) & 1) ^ 1);
-      float4 v[GT_BK / 4];
+      const int s = kc % nst;
+      mbar_wait_relaxed(&empty[s], ((kc / nst) & 1) ^ 1);
+      float4 v[NV];
+      if (a.table) {
+        // Two passes, both branch-free: first ALL token ids of the slice (independent loads), then ALL row slices.
+        // Going through gemm_a_load4 chains id -> row once per slice (the id check's atomic keeps the compiler from
+        // batching the loads): measured 17 k cycles per chunk, i.e. the loader, not the tensor pipe, set the pace.
+        const float* src[NV];
 #pragma unroll
-      for (int i = 0; i < GT_BK / 4; ++i) {
-        const int kk = kc * GT_BK + i * 4;
-        v[i] = (rvalid && kk < K) ? gemm_a_load4(a, r, kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < NV; ++i) {
+          const int kk = kc * GT_BK + (hp * NV + i) * 4;
+          const int seg = kk / a.E;
+          const int pos = gt0 + seg;
+          const bool ok = rvalid && kk < K && pos >= 0 && pos < a.L;
+          int64_t id = a.ids[ok ? gseq * a.L + pos : 0];
+          const bool inr = id >= 0 && id < a.V;
+          bad_id |= ok && !inr;
+          id = inr ? id : 0;
+          src[i] = ok ? a.table + id * a.E + (kk - seg * a.E) : nullptr;
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          v[i] = src[i] ? *reinterpret_cast<const float4*>(src[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int kk = kc * GT_BK + (hp * NV + i) * 4;
+          v[i] = (rvalid && kk < K) ? gemm_a_load4(a, r, kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
       uint8_t* ah = a_ring + (size_t)s * 2 * GT_AIMG;
 #pragma unroll
-      for (int pl = 0; pl < GT_BK / 8; ++pl) {
-        const float x[8] = {v[2 * pl].x, v[2 * pl].y, v[2 * pl].z, v[2 * pl].w,
-                            v[2 * pl + 1].x, v[2 * pl + 1].y, v[2 * pl + 1].z, v[2 * pl + 1].w};
+      for (int p2 = 0; p2 < NV / 2; ++p2) {
+        const int pl = hp * (NV / 2) + p2;
+        const float x[8] = {v[2 * p2].x, v[2 * p2].y, v[2 * p2].z, v[2 * p2].w,
+                            v[2 * p2 + 1].x, v[2 * p2 + 1].y, v[2 * p2 + 1].z, v[2 * p2 + 1].w};
         uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(x[2 * e], h0, l0);
-          split_bf16(x[2 * e + 1], h1, l1);
-          hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-          lo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-        }
-        const size_t off = (size_t)pl * GT_APLANE + (size_t)tid * 16;
+        for (int e = 0; e < 4; ++e) split_bf16x2(x[2 * e], x[2 * e + 1], hi[e], lo[e]);
+        const size_t off = (size_t)pl * GT_APLANE + (size_t)row * 16;
         *reinterpret_cast<uint4*>(ah + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(ah + GT_AIMG + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
@@ -170,27 +196,36 @@ __global__ void __launch_bounds__(GT_THREADS, 1)
       __syncwarp();
       if (lane == 0) gt_arrive(&a_full[s]);
     }
+    if (bad_id && a.err) atomicOr(a.err, ERRF_BAD_TOKEN);
     // ---- epilogue ----
+    // TMEM hands every thread 32 consecutive columns of ITS row; storing those directly makes each store instruction
+    // touch 32 different rows (32 sectors).  The tile goes through shared memory instead (the A ring is free once all
+    // MMAs have retired; row stride 33 floats = conflict-free both ways, and a warp only re-reads the 32 rows its own
+    // lanes wrote, so a __syncwarp suffices): every store instruction then writes one 128-byte row segment.
     mbar_wait_relaxed(&acc_full, 0);
     tc_fence_after();
     const int n0 = ct * NT;
-    for (int c0 = 0; c0 < NT; c0 += 32) {
+    const int qt = warp & 3;   // TMEM lane quarter of this warp; warps 0-3 / 4-7 take alternate 32-column chunks
+    float* stage = reinterpret_cast<float*>(a_ring) + (size_t)warp * 32 * 33;
+    for (int c0 = (warp >> 2) * 32; c0 < NT; c0 += 64) {
       float v[32];
-      tmem_ld32(tbase + ((uint32_t)(warp * 32) << 16) + c0, v);
+      tmem_ld32(tbase + ((uint32_t)(qt * 32) << 16) + c0, v);
       tmem_ld_wait();
-      if (rvalid) {
-        float* crow = c + r * ldc + n0 + c0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = n0 + c0 + j;
-          if (c0 + j < NT && col < N) {
-            float x = v[j] + (bias ? bias[col] : 0.f);
-            if (act == ACT_TANH) x = tanhf(x);
-            if (act == ACT_RELU) x = fmaxf(x, 0.f);
-            crow[j] = x;
-          }
-        }
+      for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];
+      __syncwarp();
+      const int col = n0 + c0 + lane;
+      const bool cvalid = c0 + lane < NT && col < N;
+      const float bcol = (bias && cvalid) ? bias[col] : 0.f;
+      const int64_t rbase = m0 + qt * 32;
+#pragma unroll 8
+      for (int rr = 0; rr < 32; ++rr) {
+        float x = stage[rr * 33 + lane] + bcol;
+        if (act == ACT_TANH) x = tanhf(x);
+        if (act == ACT_RELU) x = fmaxf(x, 0.f);
+        if (cvalid && rbase + rr < M) c[(rbase + rr) * ldc + col] = x;
       }
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -210,12 +245,17 @@ int32_t gemm_tc(const GemmA& a, const GemmTcW& w, const float* bias, float* c, i
                 cudaStream_t s) {
   if (M <= 0) return CAIR_OK;
   if ((a.table || a.dwin) && w.K != a.win * a.E) return fail(CAIR_ERR_BAD_ARG, "gemm_tc: K != win*E");
-  const size_t smem = (size_t)GT_STAGES * 2 * GT_AIMG + (size_t)GT_STAGES * 2 * (GT_BK / 8) * w.NT * 16;
+  const size_t stage_bytes = (size_t)2 * GT_AIMG + (size_t)2 * (GT_BK / 8) * w.NT * 16;
+  int nst = (int)((220 * 1024) / stage_bytes);
+  nst = nst > GT_MAXSTAGES ? GT_MAXSTAGES : nst;
+  if (nst > w.nkc) nst = w.nkc < 2 ? 2 : w.nkc;
+  size_t smem = (size_t)nst * stage_bytes;
+  if (smem < (size_t)GT_LWARPS * 32 * 33 * 4 + 1024) smem = (size_t)GT_LWARPS * 32 * 33 * 4 + 1024;   // epilogue staging lives in the A ring
   uint32_t tcols = 32;
   while ((int)tcols < ((w.NT + 31) & ~31)) tcols <<= 1;
   CAIR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((M + GT_BM - 1) / GT_BM), (unsigned)w.nct);
-  CAIR_LAUNCH(gemm_tc_kernel, grid, GT_THREADS, smem, s, a, w.img, bias, c, ldc, M, w.N, w.K, w.NT, w.nkc, (int)act, tcols);
+  CAIR_LAUNCH(gemm_tc_kernel, grid, GT_THREADS, smem, s, a, w.img, bias, c, ldc, M, w.N, w.K, w.NT, w.nkc, (int)act, tcols, nst);
   return CAIR_OK;
 }
 
