@@ -247,6 +247,7 @@ struct LstmPack {
   float* w_ih;    // [dirs*4h, in]  (fwd rows then rev rows): the pre-gate GEMM's W
   float* bias;    // [dirs*4h]      b_ih + b_hh
   float* w_hh_t;  // [dirs][h][4h]  k-major recurrent weights
+  float* w_hh = nullptr;  // [dirs][4h][h] torch layout, kept only when W_hh does not fit in shared memory (stepwise path)
   GemmTcW w_ih_tc;  // tensor-core image of w_ih (pre-gate GEMM)
 };
 int32_t lstm_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, int in, int h, LstmPack* out,
