@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(REC_THREADS) rnn_rec_kernel(const float* __res
 // gate columns of HALF the hidden units resident (h x 4 (h/2) floats = 128 KB), compute the gates and the cell update of
 // their units for the same TS sequences, and write the new h values into BOTH CTAs' next-step buffers (distributed
 // shared memory); one cluster barrier per step.  smem: W half | hprev [2 parities][TS][h] | c [TS][hh] | gates [TS][4hh].
-constexpr int REC2_TS = 8;
+constexpr int REC2_TS = 16;   // sequences per cluster: amortises the per-step fixed costs (pre-gate loads, barriers) over more work
 
 __device__ __forceinline__ uint32_t rec2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void rec2_st_peer(float* local_ptr, uint32_t peer_rank, float v) {
@@ -317,22 +317,36 @@ __global__ void __launch_bounds__(REC_THREADS, 1)
   const int maxlen = smaxlen;   // identical in both CTAs (same sequences)
   const int PG = dirs * G;
 
+  // pre-gates of this thread's gate row (GH == REC_THREADS: one row per thread) are prefetched one step ahead, so their
+  // L2 / HBM latency overlaps the cell update and the cluster barrier of the previous step
+  const bool one_row = GH == REC_THREADS;
+  float nxt[TS];
+  auto load_pre = [&](int step, int r, float* v) {
+    const int type = r / hh, ul = r - type * hh;
+    const int grow = type * h + half * hh + ul;
+#pragma unroll
+    for (int s = 0; s < TS; ++s) {
+      const int l = slen[s];
+      float x = 0.f;
+      if (step < l) {
+        const int t = dir ? l - 1 - step : step;
+        x = pre[((size_t)(s0 + s) * L + t) * PG + dir * G + grow];
+      }
+      v[s] = x;
+    }
+  };
+  if (one_row && maxlen > 0) load_pre(0, tid, nxt);
   for (int step = 0; step < maxlen; ++step) {
     const float* hp = hprev + (size_t)(step & 1) * TS * h;
     float* hn = hprev + (size_t)((step & 1) ^ 1) * TS * h;
     for (int r = tid; r < GH; r += REC_THREADS) {
-      const int type = r / hh, ul = r - type * hh;
-      const int grow = type * h + half * hh + ul;
       float acc[TS];
+      if (one_row) {
 #pragma unroll
-      for (int s = 0; s < TS; ++s) {
-        const int l = slen[s];
-        float v = 0.f;
-        if (step < l) {
-          const int t = dir ? l - 1 - step : step;
-          v = pre[((size_t)(s0 + s) * L + t) * PG + dir * G + grow];
-        }
-        acc[s] = v;
+        for (int s = 0; s < TS; ++s) acc[s] = nxt[s];
+        if (step + 1 < maxlen) load_pre(step + 1, r, nxt);
+      } else {
+        load_pre(step, r, acc);
       }
 #pragma unroll 4
       for (int k = 0; k < h; k += 4) {
