@@ -137,6 +137,7 @@ def cpu_oracle_rate(sample_queries, threads=None):
     sl = slice(0, sample_queries)
     cores = threads or os.cpu_count()
     os.environ['OMP_NUM_THREADS'] = str(cores)
+    cores = int(ol.lib().cair_oracle_set_threads(int(cores)))   # torchrun exports OMP_NUM_THREADS=1; set it explicitly
     t0 = time.perf_counter()
     ol.run_ranker(small, sd, batch['q'][sl], batch['qlen'][sl], batch['d'][sl], batch['dlen'][sl])
     dt = time.perf_counter() - t0

@@ -980,3 +980,18 @@ ORA_API int cair_oracle_arcii(const cair_arcii_weights* w, const int64_t* q, con
   }
   return rc_all;
 }
+
+/* Number of OpenMP threads of the following calls (bench.py's CPU-baseline legs: torchrun exports OMP_NUM_THREADS=1,
+ * and libgomp reads the environment only once at load time). */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+__attribute__((visibility("default"))) int cair_oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
