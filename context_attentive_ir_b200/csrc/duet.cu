@@ -110,6 +110,26 @@ __global__ void __launch_bounds__(256) duet_local_kernel(const int64_t* __restri
   }
 }
 
+// max_pool1d(win, stride 1) over time (duet.py:168): out[b, t, f] = max_{k<win} x[b, t+k, f], one thread per 4 channels.
+// Materialising the pooled tensor (76 MB at cfg5 N=10) costs ~30 us; pooling inside the GEMM's A loader multiplied its
+// loads by `win` and made conv_d2 the slowest kernel of the model.
+__global__ void timepool4_kernel(const float4* __restrict__ x, int T, int Tp, int win, int nf4, int64_t total,
+                                 float4* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)(i % nf4);
+    const int64_t bt = i / nf4;
+    const int t = (int)(bt % Tp);
+    const int64_t b = bt / Tp;
+    const float4* src = x + ((size_t)b * T + t) * nf4 + f;
+    float4 m = src[0];
+    for (int k = 1; k < win; ++k) {
+      const float4 v = src[(size_t)k * nf4];
+      m.x = fmaxf(m.x, v.x), m.y = fmaxf(m.y, v.y), m.z = fmaxf(m.z, v.z), m.w = fmaxf(m.w, v.w);
+    }
+    out[i] = m;
+  }
+}
+
 // column max over time: out[b, f] = max_t x[b, t, f]   (max_pool1d over the whole length, duet.py:178)
 __global__ void colmax_kernel(const float* __restrict__ x, int T, int nf, float* __restrict__ out) {
   const int b = blockIdx.x;
@@ -169,6 +189,7 @@ int32_t duet_forward(const DuetState& st, const int64_t* q, const int64_t* d, in
   float* rq = ws.take<float>((size_t)nq * nf);
   float* cdv = ws.take<float>((size_t)pc * Td * nf);
   float* rd = ws.take<float>((size_t)pc * Tp * nf);
+  float* pooled = ws.take<float>((nf & 3) ? 0 : (size_t)pc * Tp * nf);
   float* m1d = ws.take<float>((size_t)pc * nf);
   float* m2d = ws.take<float>((size_t)pc * nf);
   if (dry || pc <= 0) return CAIR_OK;
@@ -189,8 +210,15 @@ int32_t duet_forward(const DuetState& st, const int64_t* q, const int64_t* d, in
   // distributed model, document side
   CAIR_TRY(gemm_auto(gemm_gather(st.table, st.V, E, d + pb * Ld, 3, Ld, Td, err), st.cd1_w, st.cd1_tc, st.cd1_b, cdv, nf,
                      pc * Td, nf, 3 * E, ACT_TANH, s));
-  CAIR_TRY(gemm_auto(gemm_pooled(cdv, nf, st.pool, Td, Tp), st.cd2_w, st.cd2_tc, st.cd2_b, rd, nf, pc * Tp, nf, nf,
-                     ACT_TANH, s));
+  if ((nf & 3) == 0) {
+    const int64_t total = (int64_t)pc * Tp * (nf / 4);
+    CAIR_LAUNCH(timepool4_kernel, (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16), 256, 0, s,
+                reinterpret_cast<const float4*>(cdv), Td, Tp, st.pool, nf / 4, total, reinterpret_cast<float4*>(pooled));
+    CAIR_TRY(gemm_auto(gemm_dense(pooled, nf), st.cd2_w, st.cd2_tc, st.cd2_b, rd, nf, pc * Tp, nf, nf, ACT_TANH, s));
+  } else {
+    CAIR_TRY(gemm_auto(gemm_pooled(cdv, nf, st.pool, Td, Tp), st.cd2_w, st.cd2_tc, st.cd2_b, rd, nf, pc * Tp, nf, nf,
+                       ACT_TANH, s));
+  }
   CAIR_LAUNCH(duet_hadamard_kernel, dim3((unsigned)pc, (nf + 127) / 128), 128, 0, s, rd, rq, st.fc2_w, st.fc2_b, N, Tp,
               nf, pb, qb, m1d);
   CAIR_TRY(gemm_f32(gemm_dense(m1d, nf), st.fc3_w, st.fc3_b, m2d, nf, pc, nf, nf, ACT_TANH, s));

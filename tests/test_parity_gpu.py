@@ -355,9 +355,16 @@ def test_cars_cfg4_architecture_vs_oracle(gemm_engine):
     assert _max_rel(s, ref['scores']) < TOL
 
 
-def test_lstm_entry_point_vs_oracle():
+@pytest.mark.parametrize('n,L,inp,h', [
+    (37, 23, 40, 64),      # tcgen05 recurrence (in < 48, h <= 64), 16 sequences per CTA
+    (5, 9, 17, 24),        # tcgen05, one row tile, 8 sequences per CTA, odd sizes
+    (300, 12, 40, 64),     # tcgen05, 32 sequences per CTA (more than one wave otherwise)
+    (21, 15, 96, 96),      # fp32 recurrence, W_hh in shared memory
+    (37, 11, 300, 128),    # fp32 recurrence split over 2-CTA clusters (DSMEM h exchange), tensor-core pre-gate GEMM
+    (32, 7, 256, 512),     # stepwise path: one GEMM + cell kernel per step (CARS session encoders)
+])
+def test_lstm_entry_point_vs_oracle(n, L, inp, h):
     rng = np.random.default_rng(9)
-    n, L, inp, h = 37, 23, 40, 64
     x = rng.standard_normal((n, L, inp)).astype(np.float32)
     lens = rng.integers(1, L + 1, n).astype(np.int64)
     lens[0] = L
