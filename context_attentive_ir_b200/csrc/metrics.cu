@@ -133,3 +133,41 @@ extern "C" CAIR_API int32_t cair_rank_metrics(const float* scores, const int64_t
   if (batch_mean) CAIR_LAUNCH(rank_metrics_mean_kernel, 1, RM_THREADS, 0, s, per_row, B, batch_mean);
   return CAIR_OK;
 }
+
+// ---- batchify on the device -------------------------------------------------------
+// The reference pads every example on the host with per-example copy_ loops (inputters/ranker/vector.py:39-90) and
+// ships padded int64 tensors.  Here the host ships the RAGGED batch (concatenated int32 token ids + int64 offsets,
+// 4 bytes per real token) and one kernel writes the padded int64 [B,Lq] / [B,N,Ld] id tensors and the length tensors
+// the scoring entry points take: PAD (0) beyond each length, lengths = token counts.
+namespace cair {
+__global__ void batchify_kernel(const int32_t* __restrict__ tokens, const int64_t* __restrict__ offsets, int64_t nseq, int L,
+                                int64_t* __restrict__ ids, int64_t* __restrict__ lens, int* err) {
+  const int64_t total = nseq * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = i / L;
+    const int l = (int)(i - s * L);
+    const int64_t o0 = offsets[s], n = offsets[s + 1] - o0;
+    if (l == 0) {
+      lens[s] = n;
+      if (n < 1 || n > L) atomicOr(err, ERRF_BAD_LENGTH);   // the reference's copy_ raises on a longer example
+    }
+    ids[i] = (l < n) ? (int64_t)tokens[o0 + l] : 0;
+  }
+}
+}  // namespace cair
+
+extern "C" CAIR_API int32_t cair_batchify_ranker(const int32_t* q_tokens, const int64_t* q_offsets, const int32_t* d_tokens,
+                                                 const int64_t* d_offsets, int32_t B, int32_t N, int32_t Lq, int32_t Ld,
+                                                 int64_t* q, int64_t* qlen, int64_t* d, int64_t* dlen, int32_t* err_flag,
+                                                 void* stream) {
+  using namespace cair;
+  if (!q_tokens || !q_offsets || !d_tokens || !d_offsets || !q || !qlen || !d || !dlen || !err_flag)
+    return fail(CAIR_ERR_BAD_ARG, "batchify_ranker: null tensor");
+  if (B <= 0 || N <= 0 || Lq <= 0 || Ld <= 0) return fail(CAIR_ERR_BAD_SHAPE, "batchify_ranker: B, N, Lq, Ld must be positive");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t tq = (int64_t)B * Lq, td = (int64_t)B * N * Ld;
+  const auto blocks = [](int64_t t) { return (unsigned)((t + 255) / 256 < 148 * 16 ? (t + 255) / 256 : 148 * 16); };
+  CAIR_LAUNCH(batchify_kernel, blocks(tq), 256, 0, s, q_tokens, q_offsets, (int64_t)B, Lq, q, qlen, err_flag);
+  CAIR_LAUNCH(batchify_kernel, blocks(td), 256, 0, s, d_tokens, d_offsets, (int64_t)B * N, Ld, d, dlen, err_flag);
+  return CAIR_OK;
+}

@@ -47,6 +47,7 @@ PROTOTYPES = {
     'cair_ranker_submit_host': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, i32, vp]),
     'cair_ranker_wait_host': (i32, [vp, i32]),
     'cair_ranker_set_pipeline_split': (i32, [vp, C.c_float]),
+    'cair_batchify_ranker': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
     'cair_rank_metrics': (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
     'cair_cars_create': (i32, [C.POINTER(_abi.CarsWeights), i32, C.POINTER(vp)]),
     'cair_cars_workspace_bytes': (i32, [vp, i32, i32, i32, i32, i32, C.POINTER(C.c_size_t)]),

@@ -295,6 +295,20 @@ CAIR_API int32_t cair_ranker_set_pipeline_split(cair_handle* h, float frac);
 CAIR_API int32_t cair_rank_metrics(const float* scores, const int64_t* labels, int32_t B, int32_t N,
                           int32_t apply_softmax, double* per_row, double* batch_mean, void* stream);
 
+/* ---- batchify on the device ----------------------------------------
+ * Replaces the host-side padding loops of batchify (neuroir/inputters/ranker/vector.py:39-90): the batch arrives
+ * RAGGED - q_tokens / d_tokens are the concatenated int32 token ids of the B queries / B*N documents, q_offsets
+ * [B+1] / d_offsets [B*N+1] their int64 start offsets (all DEVICE pointers; 4 bytes per real token cross the bus
+ * instead of 8 bytes per padded position) - and leaves as the padded int64 tensors the scoring entry points
+ * take: q [B,Lq], qlen [B], d [B,N,Ld], dlen [B,N], PAD = 0 beyond each length.  Lq / Ld are the batch maxima
+ * (or max_query_len / max_doc_len under force_pad, vector.py:18-21), chosen by the caller.  A sequence that is
+ * empty or longer than its padded length ORs 2 (bad length) into *err_flag (device int32; the reference's
+ * copy_ raises there).  Enqueued on `stream`, nothing is synchronised. */
+CAIR_API int32_t cair_batchify_ranker(const int32_t* q_tokens, const int64_t* q_offsets, const int32_t* d_tokens,
+                             const int64_t* d_offsets, int32_t B, int32_t N, int32_t Lq, int32_t Ld,
+                             int64_t* q, int64_t* qlen, int64_t* d, int64_t* dlen, int32_t* err_flag,
+                             void* stream);
+
 /* ---- CARS ranking path (neuroir/multitask/cars.py:193-304 encode*, :306-458 encode_session,
  *      :460-540 rank/rank_document, :671-691 apply_pooling; neuroir/modules/maxout.py:70-84) --- */
 typedef struct {

@@ -266,6 +266,40 @@ def gen_rank_metrics(name, seed, B, N, max_rel=1, ties=False):
     print('wrote', name, 'MAP %.6f MRR %.6f' % (out['map'], out['mrr']))
 
 
+# ------------------------------------------------------------------ batchify (inputters/ranker/vector.py:39-90)
+def gen_batchify(name, seed, B, N, max_q, max_d, V):
+    """Runs the reference's own batchify on vectorised examples (the dicts vectorize() returns, vector.py:24-36) and
+    freezes the ragged inputs (flat token arrays + offsets) next to its padded outputs."""
+    from neuroir.inputters.ranker.vector import batchify
+    rng = np.random.RandomState(seed)
+    batch, q_tok, d_tok, q_off, d_off = [], [], [], [0], [0]
+    for b in range(B):
+        ql = rng.randint(2, max_q + 1)
+        qw = rng.randint(4, V, size=ql)
+        docs = []
+        for n in range(N):
+            dl = rng.randint(2, max_d + 1)
+            docs.append(rng.randint(4, V, size=dl))
+        q_tok.append(qw)
+        q_off.append(q_off[-1] + ql)
+        for dw in docs:
+            d_tok.append(dw)
+            d_off.append(d_off[-1] + len(dw))
+        batch.append({'id': 'q%d' % b, 'query_words': torch.LongTensor(qw), 'doc_words': [torch.LongTensor(x) for x in docs],
+                      'label': torch.LongTensor(rng.randint(0, 2, size=N)), 'num_candidates': N,
+                      'max_doc_len': max(len(x) for x in docs), 'max_query_len': ql})
+    out = batchify(batch)
+    os.makedirs(OUT, exist_ok=True)
+    meta = dict(cfg=dict(model='batchify', B=B, N=N), torch=torch.__version__, numpy=np.__version__)
+    arrays = {'meta': np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8),
+              'in/q_tokens': np.concatenate(q_tok).astype(np.int32), 'in/q_offsets': np.asarray(q_off, np.int64),
+              'in/d_tokens': np.concatenate(d_tok).astype(np.int32), 'in/d_offsets': np.asarray(d_off, np.int64),
+              'out/q': out['que_rep'].numpy(), 'out/qlen': out['que_len'].numpy(), 'out/d': out['doc_rep'].numpy(),
+              'out/dlen': out['doc_len'].numpy()}
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **arrays)
+    print('wrote', name, tuple(out['doc_rep'].shape))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     _apply_shims()
@@ -273,7 +307,7 @@ def main():
     only = sys.argv[1:]  # optional: fixture-name prefixes to (re)generate
     if only:
         g = globals()
-        for fn in ('gen_esm', 'gen_mt', 'gen_drmm', 'gen_duet', 'gen_cars', 'gen_dssm', 'gen_arc', 'gen_rank_metrics'):
+        for fn in ('gen_esm', 'gen_mt', 'gen_drmm', 'gen_duet', 'gen_cars', 'gen_dssm', 'gen_arc', 'gen_rank_metrics', 'gen_batchify'):
             g[fn] = (lambda f: (lambda name, *a, **k: f(name, *a, **k) if any(name.startswith(o) for o in only) else None))(g[fn])
     # BASELINE configs[0]: the reference's own CPU-runnable case (vocab cut 10k -> 1k to keep the file small)
     gen_esm('esm_cfg1', 1235, B=8, N=5, Lq=10, Ld=50, E=64, V=1000)
@@ -309,6 +343,9 @@ def main():
     # DUET (force_pad shapes: every batch padded to max lens, lengths still variable)
     gen_duet('duet_tiny', 41, B=2, N=3, Lq=8, Ld=30, E=24, V=120, nf=16, overlap=0.2)
     gen_duet('duet_e300', 1239, B=2, N=3, Lq=20, Ld=200, E=300, V=400, nf=64, bos_eos=True, overlap=0.1)
+    # batchify of ragged examples (inputters/ranker/vector.py:39-90)
+    gen_batchify('batchify_small', 91, B=5, N=3, max_q=9, max_d=31, V=500)
+    gen_batchify('batchify_cfg2', 92, B=16, N=10, max_q=20, max_d=200, V=30000)
     # ranking metrics of the evaluation loops (main/ranker.py:257-264)
     gen_rank_metrics('rank_metrics_n10', 81, B=64, N=10, max_rel=1)
     gen_rank_metrics('rank_metrics_ties', 82, B=32, N=12, max_rel=3, ties=True)

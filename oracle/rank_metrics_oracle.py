@@ -53,3 +53,27 @@ def rank_metrics(scores, labels, apply_softmax=True):
     pred = predictions(p)
     rows = per_row(pred, np.asarray(labels))
     return rows.mean(axis=0), rows, pred
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# batchify, restated for flat token arrays.
+#   inputters/ranker/vector.py:39-90   doc_word [B,N,max_doc_len] / que_word [B,max_que_len] zero (PAD) filled,
+#                                      doc_len [B,N] / que_len [B] = token counts, max lens = batch maxima
+#                                      (or args.max_doc_len / max_query_len under force_pad, :18-21)
+def batchify_flat(q_tokens, q_offsets, d_tokens, d_offsets, B, N, Lq=None, Ld=None):
+    """q_tokens / d_tokens: concatenated token ids; *_offsets: [B+1] / [B*N+1] starts.  Returns the four int64 tensors
+    of the reference's batch dict (que_rep, que_len, doc_rep, doc_len)."""
+    q_offsets = np.asarray(q_offsets, dtype=np.int64)
+    d_offsets = np.asarray(d_offsets, dtype=np.int64)
+    qlen = np.diff(q_offsets)
+    dlen = np.diff(d_offsets).reshape(B, N)
+    Lq = int(qlen.max()) if Lq is None else Lq
+    Ld = int(dlen.max()) if Ld is None else Ld
+    q = np.zeros((B, Lq), dtype=np.int64)
+    d = np.zeros((B, N, Ld), dtype=np.int64)
+    for b in range(B):
+        q[b, :qlen[b]] = q_tokens[q_offsets[b]:q_offsets[b + 1]]
+        for n in range(N):
+            i = b * N + n
+            d[b, n, :dlen[b, n]] = d_tokens[d_offsets[i]:d_offsets[i + 1]]
+    return q, qlen.astype(np.int64), d, dlen.astype(np.int64)

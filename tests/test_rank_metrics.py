@@ -72,3 +72,34 @@ def test_cuda_vs_oracle_large_and_edge_cases():
     # fewer than 5 candidates: the reference asserts in precision_at_k(…, 5)
     with pytest.raises(lib.CairError):
         rank_metrics_device(torch.zeros(2, 4).cuda(), torch.zeros(2, 4, dtype=torch.int64).cuda())
+
+
+# ---- batchify ----------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['batchify_small', 'batchify_cfg2'])
+def test_batchify_oracle_matches_reference(name):
+    cfg, ins, _, outs = ol.load_golden(name)
+    q, ql, d, dl = rmo.batchify_flat(ins['q_tokens'], ins['q_offsets'], ins['d_tokens'], ins['d_offsets'], cfg['B'], cfg['N'])
+    for a, k in ((q, 'q'), (ql, 'qlen'), (d, 'd'), (dl, 'dlen')):
+        assert a.dtype == np.int64 and np.array_equal(a, outs[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['batchify_small', 'batchify_cfg2'])
+def test_batchify_cuda_matches_reference(name):
+    from context_attentive_ir_b200 import lib
+    from context_attentive_ir_b200.inputters import batchify_ranker
+    cfg, ins, _, outs = ol.load_golden(name)
+    t = {k: torch.from_numpy(v).cuda() for k, v in ins.items()}
+    got = batchify_ranker(t['q_tokens'], t['q_offsets'], t['d_tokens'], t['d_offsets'], cfg['B'], cfg['N'])
+    for a, k in zip(got, ('q', 'qlen', 'd', 'dlen')):
+        assert a.dtype == torch.int64 and np.array_equal(a.cpu().numpy(), outs[k]), k
+    # force_pad: longer padded lengths keep the same content, PAD beyond
+    Lq, Ld = outs['q'].shape[1] + 3, outs['d'].shape[2] + 5
+    q2, ql2, d2, dl2 = batchify_ranker(t['q_tokens'], t['q_offsets'], t['d_tokens'], t['d_offsets'], cfg['B'], cfg['N'], Lq, Ld)
+    oq, oql, od, odl = rmo.batchify_flat(ins['q_tokens'], ins['q_offsets'], ins['d_tokens'], ins['d_offsets'], cfg['B'], cfg['N'], Lq, Ld)
+    assert np.array_equal(q2.cpu().numpy(), oq) and np.array_equal(d2.cpu().numpy(), od)
+    assert np.array_equal(ql2.cpu().numpy(), oql) and np.array_equal(dl2.cpu().numpy(), odl)
+    # an example longer than the padded length is reported (the reference's copy_ raises)
+    with pytest.raises(lib.CairError):
+        batchify_ranker(t['q_tokens'], t['q_offsets'], t['d_tokens'], t['d_offsets'], cfg['B'], cfg['N'], outs['q'].shape[1],
+                        outs['d'].shape[2] - 1)
