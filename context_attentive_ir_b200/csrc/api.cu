@@ -75,7 +75,8 @@ struct cair_handle {
   } pipe[3];
   bool pipe_trace = false;
   int pipe_last = -1, pipe_last2 = -1;   // slots of the two most recently submitted batches
-  float pipe_frac = 0.33f;               // share of a batch's pairs scored under the NEXT batch's document encoder
+  float pipe_frac = 0.45f;               // share of a batch's pairs scored under the NEXT batch's document encoder
+  int pipe_spc = 32;                     // document-encoder sequences per CTA in the pipeline (80 CTAs at cfg2: 68 SMs stay free)
   cudaStream_t hi_stream = nullptr, lo_stream = nullptr;
   cudaStream_t copy_stream = nullptr;
 };
@@ -275,6 +276,13 @@ int32_t cair_mt_set_impl(cair_handle* h, int32_t impl) {
 // debugging aid (not in the public header): role-timing counters of the tcgen05 interaction kernel
 extern "C" __attribute__((visibility("default"))) int32_t cair_mt_debug_timing(long long* dev_counters) {
   cair::g_mt_dbg = dev_counters;
+  return CAIR_OK;
+}
+
+// Tuning knob (tools/pipe_tune.py): smallest number of sequences per CTA the tcgen05 LSTM may choose (8, 16, 24 or 32).
+extern "C" __attribute__((visibility("default"))) int32_t cair_lstm_set_min_seqs_per_cta(int32_t spc) {
+  if (spc != 8 && spc != 16 && spc != 24 && spc != 32) return fail(CAIR_ERR_BAD_ARG, "seqs per CTA must be 8, 16, 24 or 32");
+  cair::g_lstm_spc_min = spc;
   return CAIR_OK;
 }
 
@@ -716,7 +724,7 @@ int32_t cair_ranker_submit_host(cair_handle* h, const int64_t* q, const int64_t*
   if (prev >= 0) {
     cair_handle::PipeSlot& pp = h->pipe[prev];
     const int64_t pcp = (int64_t)pp.B * pp.N;
-    free_sms = kSMs - lstm_tc_ctas((int)nbn, h->mt.tc_d.dirs);
+    free_sms = kSMs - lstm_tc_ctas((int)nbn, h->mt.tc_d.dirs, h->pipe_spc);
     if (free_sms >= 8) c1 = (int64_t)((double)pcp * h->pipe_frac);
     CAIR_CUDA(cudaStreamWaitEvent(L, pp.ev_enc, 0));
     CAIR_TRY(pipe_mark(h, prev, 2, L));
@@ -732,6 +740,7 @@ int32_t cair_ranker_submit_host(cair_handle* h, const int64_t* q, const int64_t*
     Arena ws(p.ws, p.ws_bytes);
     MtPhase ph;
     ph.phase = MT_ENCODE;
+    ph.doc_min_spc = h->pipe_spc;
     CAIR_TRY(mt_forward(h->mt, v.dq, v.dql, v.dd, v.ddl, B, N, Lq, Ld, 0, (int64_t)nbn, v.ds, ws, h->d_err, H, false, ph));
   }
   CAIR_TRY(pipe_mark(h, slot, 1, H));

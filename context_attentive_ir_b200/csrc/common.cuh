@@ -264,8 +264,9 @@ struct LstmTcPack {
 };
 extern long long* g_lstm_dbg;  // optional role-timing counters (debug)
 bool lstm_tc_supported(int in, int h);
-int lstm_tc_seqs_per_cta(int n, int dirs);
-int lstm_tc_ctas(int n, int dirs);   // grid size lstm_tc_run uses for n sequences
+extern int g_lstm_spc_min;
+int lstm_tc_seqs_per_cta(int n, int dirs, int min_spc = 8);
+int lstm_tc_ctas(int n, int dirs, int min_spc = 8);   // grid size lstm_tc_run uses for n sequences
 int32_t lstm_tc_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, int in, int h, LstmTcPack* out,
                      cudaStream_t s);
 // bias: [dirs][4h] = b_ih + b_hh (LstmPack::bias)
@@ -273,7 +274,7 @@ int32_t lstm_tc_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* 
 // then copy 16-byte units instead of converting fp32 rows on every step.
 int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, const int64_t* len, int n, int L,
                     float* out, float* h_n, float* c_n, int* err, cudaStream_t s, const char* rec_name,
-                    const uint8_t* ximg = nullptr);
+                    const uint8_t* ximg = nullptr, int min_spc = 8);   // min_spc: fewest sequences per CTA to consider
 // table [V, in] fp32 -> image [V][hi|lo][48 x bf16] (constant 1 in K slot `in` = the bias column, zero padding)
 int32_t lstm_tc_pack_table(Owned& own, const float* table, int V, int in, uint8_t** img, cudaStream_t s);
 

@@ -490,18 +490,21 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
 
 // Sequences per CTA: the per-step cost is latency + the cell updates of one SM (MUFU / issue bound), not the MMAs
 // (an N = 32 MMA costs the same as a narrower one), so use the fewest sequences per CTA that still fit one wave.
-int lstm_tc_seqs_per_cta(int n, int dirs) {
-  for (int c = 8; c < LT_NSEQ; c += 8)
+int g_lstm_spc_min = 8;   // process-wide floor of the sequences per CTA (tuning knob, tools/pipe_tune.py)
+int lstm_tc_seqs_per_cta(int n, int dirs, int min_spc) {
+  if (min_spc < g_lstm_spc_min) min_spc = g_lstm_spc_min;
+  for (int c = min_spc; c < LT_NSEQ; c += 8)
     if ((int64_t)((n + c - 1) / c) * dirs <= kSMs) return c;
   return LT_NSEQ;
 }
-int lstm_tc_ctas(int n, int dirs) {
-  const int spc = lstm_tc_seqs_per_cta(n, dirs);
+int lstm_tc_ctas(int n, int dirs, int min_spc) {
+  const int spc = lstm_tc_seqs_per_cta(n, dirs, min_spc);
   return ((n + spc - 1) / spc) * dirs;
 }
 
 int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, const int64_t* len, int n, int L,
-                    float* out, float* h_n, float* c_n, int* err, cudaStream_t s, const char* rec_name, const uint8_t* ximg) {
+                    float* out, float* h_n, float* c_n, int* err, cudaStream_t s, const char* rec_name, const uint8_t* ximg,
+                    int min_spc) {
   if (n <= 0) return CAIR_OK;
   if (rec_name) prof_mark(rec_name, s);
   uint32_t ks_mask = 0;
@@ -515,7 +518,7 @@ int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, cons
   CAIR_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // Sequences per CTA: the per-step cost is latency + the cell updates of one SM (MUFU / issue bound), not the MMAs
   // (an N = 32 MMA costs the same as a narrower one), so use the fewest sequences per CTA that still fit one wave.
-  const int spc = lstm_tc_seqs_per_cta(n, p.dirs);
+  const int spc = lstm_tc_seqs_per_cta(n, p.dirs, min_spc);
   dim3 grid((n + spc - 1) / spc, p.dirs);
   CAIR_LAUNCH(lstm_tc_kernel, grid, LT_THREADS, smem, s, x, p.wimg, bias, len, n, L, p.in, p.h, p.dirs, ks_mask, spc, out,
               h_n, c_n, err, g_lstm_dbg, x.table ? ximg : nullptr);

@@ -89,6 +89,8 @@ struct MtPhase {
   int64_t ib = 0, ic = -1;
   int max_ctas = 0;
   bool join = true;
+  int doc_min_spc = 8;   // MT_ENCODE: fewest sequences per CTA of the document encoder (32 in the serving pipeline: fewer,
+                         // slightly slower encoder CTAs leave more SMs to the previous batch's interaction)
 };
 bool mt_can_pipeline(const MtState& st, int Lq, int Ld);
 int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, const int64_t* d, const int64_t* dlen,

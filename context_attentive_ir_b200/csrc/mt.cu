@@ -360,7 +360,7 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
   // ---- document side ----
   if (tc_d)
     CAIR_TRY(lstm_tc_run(st.tc_d, st.enc_d.bias, gemm_gather(st.folded, st.V, st.F, ds, 1, 1, 1, err), dlen + pb, (int)pc,
-                         Ld, enc_d, nullptr, nullptr, err, s, "doc_recurrence", st.folded_img));
+                         Ld, enc_d, nullptr, nullptr, err, s, "doc_recurrence", st.folded_img, ph.doc_min_spc));
   else
     CAIR_TRY(lstm_run(st.enc_d, gemm_gather(st.folded, st.V, st.F, ds, 1, 1, 1, err), dlen + pb, (int)pc, Ld, enc_d,
                       nullptr, nullptr, pre_d, err, s, "doc_recurrence"));

@@ -29,14 +29,18 @@ def loop(k, do_flush, depth=3):
             net.wait_host(i % 3)
 
 
+import ctypes as C
+Lb = C.CDLL(lib.LIB_PATH)
 loop(6, True)
-for do_flush in (True, False):
-    for depth in (2, 3):
-        for frac in (0.0, 0.2, 0.27, 0.33, 0.4, 0.5):
+for spc, fracs in ((8, (0.0, 0.33)), (32, (0.33, 0.45, 0.55, 0.65, 0.75))):
+  Lb.cair_lstm_set_min_seqs_per_cta(spc)
+  for do_flush in (True, False):
+    for depth in (3,):
+        for frac in fracs:
             lib.check(L.cair_ranker_set_pipeline_split(net._cair_handle, frac))
             loop(6, do_flush, depth)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             loop(200, do_flush, depth)
             dt = time.perf_counter() - t0
-            print('flush=%d depth=%d frac=%.2f: %.3f ms/step  %.3f M pairs/s' % (do_flush, depth, frac, dt / 200 * 1e3, bench.B * bench.N * 200 / dt / 1e6), flush=True)
+            print('min seqs/CTA=%d flush=%d depth=%d frac=%.2f: %.3f ms/step  %.3f M pairs/s' % (spc, do_flush, depth, frac, dt / 200 * 1e3, bench.B * bench.N * 200 / dt / 1e6), flush=True)
