@@ -143,6 +143,7 @@ int64_t cair_launch_count(void) { return g_launches.load(); }
 int32_t cair_destroy(cair_handle* h) {
   if (!h) return CAIR_OK;
   DeviceGuard g(h->device);
+  cudaDeviceSynchronize();   // batches submitted through the pipelined entry points may still be in flight
   h->own.release();
   h->prof.release();
   if (h->mt.side) cudaStreamDestroy(h->mt.side);

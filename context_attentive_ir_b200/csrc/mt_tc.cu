@@ -85,53 +85,102 @@ static inline int tc_stages(const MtPack& p, int Lq) {
 
 // B slabs for (query qi, column tile nt): 7 main slabs (one per tap bt) [hi|lo][plane c/8 < KCm][row n = il*FP + f][8 x bf16]
 // followed by the tail slab [hi|lo][chunk ch < 2 ntail][row n][8 x bf16] (element e of chunk ch: tap ch*tpc + e/rr,
-// channel Cm + e%rr).  One thread per 16-byte unit: T = sum_a W7[f,c,a,bt] * cq[i+a-1,c], split to hi/lo.
-__global__ void __launch_bounds__(256) mt_tc_build_t_kernel(const float* __restrict__ cq, MtPack p, int Lq, int IPT,
-                                                            int ntiles, uint8_t* __restrict__ img) {
+// channel Cm + e%rr).  T = sum_a W7[f,c,a,bt] * cq[i+a-1,c], split to hi/lo.
+// One CTA per (query, column tile): the IPT + 2 query rows the tile needs are staged once in shared memory (zero rows
+// outside the query, zero pad channels); a thread owns one (tap, channel plane, filter) combination, keeps its 3 x 8
+// stencil weights in registers and walks the IPT query positions (6 LDS.128 + 24 FMA + split + 2 x 16-byte stores per unit;
+// the first version re-read weights and query rows from global memory for every unit and was instruction-bound).
+constexpr int BT_THREADS = 256;
+__global__ void __launch_bounds__(BT_THREADS) mt_tc_build_t_kernel(const float* __restrict__ cq, MtPack p, int Lq, int IPT,
+                                                                   int ntiles, uint8_t* __restrict__ img) {
+  extern __shared__ __align__(16) float bt_cq[];   // [IPT + 2][CPW]
   const TcK k = tc_k(p.C);
-  const int nit = 7 + (k.ntail ? 1 : 0);
-  const int nt = blockIdx.x / nit, item = blockIdx.x - nt * nit, qi = blockIdx.y;
+  const int nt = blockIdx.x, qi = blockIdx.y;
   const int C = p.C, FP = p.FP, CPW = (C + 15) & ~15;
-  const bool tail = item == 7;
-  const int planes = tail ? 2 * k.ntail : k.KCm;
-  const size_t half = (size_t)planes * TC_NROWS * 16;
-  uint8_t* out = img + ((size_t)qi * ntiles + nt) * tc_timg_per_tile(k) + (size_t)item * tc_slab_main(k);
-  for (int u = threadIdx.x; u < planes * TC_NROWS; u += blockDim.x) {
-    const int kc = u / TC_NROWS, n = u - kc * TC_NROWS;
-    const int il = n / FP, f = n - il * FP, i = nt * IPT + il;
-    float v[8];
+  const int i0 = nt * IPT;
+  for (int idx = threadIdx.x; idx < (IPT + 2) * CPW; idx += BT_THREADS) {
+    const int r = idx / CPW, c = idx - r * CPW;
+    const int ii = i0 - 1 + r;
+    bt_cq[idx] = (ii >= 0 && ii < Lq && c < C) ? cq[((size_t)qi * Lq + ii) * C + c] : 0.f;
+  }
+  __syncthreads();
+  uint8_t* tile_out = img + ((size_t)qi * ntiles + nt) * tc_timg_per_tile(k);
+  // ---- main slabs: work item = (tap bt, plane kc, filter f) ----
+  const size_t half = (size_t)k.KCm * TC_NROWS * 16;
+  const int nwork = 7 * k.KCm * FP;
+  for (int wi = threadIdx.x; wi < nwork; wi += BT_THREADS) {
+    const int bt = wi / (k.KCm * FP), rem = wi - bt * (k.KCm * FP);
+    const int kc = rem / FP, f = rem - kc * FP;
+    float w[3][8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = 0.f;
-    if (il < IPT && i < Lq) {
+    for (int a = 0; a < 3; ++a) {
+      const float4* w4 = reinterpret_cast<const float4*>(p.w7t + (((size_t)a * 7 + bt) * FP + f) * CPW + kc * 8);
+      const float4 wa = w4[0], wb = w4[1];
+      w[a][0] = wa.x, w[a][1] = wa.y, w[a][2] = wa.z, w[a][3] = wa.w;
+      w[a][4] = wb.x, w[a][5] = wb.y, w[a][6] = wb.z, w[a][7] = wb.w;
+    }
+    uint8_t* out = tile_out + (size_t)bt * tc_slab_main(k);
+    for (int il = 0; il < IPT; ++il) {
+      float v[8];
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        const int ii = i + a - 1;
-        if (ii < 0 || ii >= Lq) continue;
-        if (!tail) {
-          const float4* w4 = reinterpret_cast<const float4*>(p.w7t + (((size_t)a * 7 + item) * FP + f) * CPW + kc * 8);
-          const float4 wa = w4[0], wb = w4[1];
-          const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-          const float* cr = cq + ((size_t)qi * Lq + ii) * C + kc * 8;
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      if (i0 + il < Lq) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if (kc * 8 + e < C) v[e] = fmaf(w[e], cr[e], v[e]);
-        } else {
+        for (int a = 0; a < 3; ++a) {   // staged row index of query position i0 + il + a - 1 is il + a
+          const float4* c4 = reinterpret_cast<const float4*>(bt_cq + (size_t)(il + a) * CPW + kc * 8);
+          const float4 ca = c4[0], cb = c4[1];
+          v[0] = fmaf(w[a][0], ca.x, v[0]), v[1] = fmaf(w[a][1], ca.y, v[1]);
+          v[2] = fmaf(w[a][2], ca.z, v[2]), v[3] = fmaf(w[a][3], ca.w, v[3]);
+          v[4] = fmaf(w[a][4], cb.x, v[4]), v[5] = fmaf(w[a][5], cb.y, v[5]);
+          v[6] = fmaf(w[a][6], cb.z, v[6]), v[7] = fmaf(w[a][7], cb.w, v[7]);
+        }
+      }
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+      const size_t off = ((size_t)kc * TC_NROWS + il * FP + f) * 16;
+      *reinterpret_cast<uint4*>(out + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(out + half + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+  // rows n >= IPT*FP of every plane (MMA N padding) are zero
+  const int npad = TC_NROWS - IPT * FP;
+  for (int idx = threadIdx.x; idx < 7 * k.KCm * npad; idx += BT_THREADS) {
+    const int bt = idx / (k.KCm * npad), rem = idx - bt * (k.KCm * npad);
+    const int kc = rem / npad, n = IPT * FP + (rem - kc * npad);
+    uint8_t* out = tile_out + (size_t)bt * tc_slab_main(k) + ((size_t)kc * TC_NROWS + n) * 16;
+    *reinterpret_cast<uint4*>(out) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(out + half) = make_uint4(0, 0, 0, 0);
+  }
+  // ---- tail slab: one thread per 16-byte unit ----
+  if (k.ntail) {
+    const int planes = 2 * k.ntail;
+    const size_t thalf = (size_t)planes * TC_NROWS * 16;
+    uint8_t* out = tile_out + (size_t)7 * tc_slab_main(k);
+    for (int u = threadIdx.x; u < planes * TC_NROWS; u += BT_THREADS) {
+      const int kc = u / TC_NROWS, n = u - kc * TC_NROWS;
+      const int il = n / FP, f = n - il * FP;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      if (il < IPT && i0 + il < Lq) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int bt = kc * k.tpc + e / k.rr, ce = e % k.rr;
             if (bt < 7 && ce < k.r)
-              v[e] = fmaf(p.w7t[(((size_t)a * 7 + bt) * FP + f) * CPW + k.Cm + ce],
-                          cq[((size_t)qi * Lq + ii) * C + k.Cm + ce], v[e]);
+              v[e] = fmaf(p.w7t[(((size_t)a * 7 + bt) * FP + f) * CPW + k.Cm + ce], bt_cq[(size_t)(il + a) * CPW + k.Cm + ce], v[e]);
           }
         }
       }
-    }
-    uint32_t hi[4], lo[4];
+      uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-    const size_t off = ((size_t)kc * TC_NROWS + n) * 16;
-    *reinterpret_cast<uint4*>(out + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(out + half + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      for (int e = 0; e < 4; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+      const size_t off = ((size_t)kc * TC_NROWS + n) * 16;
+      *reinterpret_cast<uint4*>(out + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(out + thalf + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
   }
 }
 
@@ -808,8 +857,9 @@ int32_t mt_tc_build_t(const MtPack& p, const float* cq, uint8_t* timg, int Lq, i
   if (nq <= 0) return CAIR_OK;
   const TcK k = tc_k(p.C);
   const int IPT = TC_NROWS / p.FP, ntiles = (Lq + IPT - 1) / IPT;
-  CAIR_LAUNCH(mt_tc_build_t_kernel, dim3(ntiles * (7 + (k.ntail ? 1 : 0)), (unsigned)nq), 256, 0, s, cq, p, Lq, IPT, ntiles,
-              timg);
+  const size_t smem = (size_t)(IPT + 2) * tc_cp(p.C) * sizeof(float);
+  (void)k;
+  CAIR_LAUNCH(mt_tc_build_t_kernel, dim3(ntiles, (unsigned)nq), BT_THREADS, smem, s, cq, p, Lq, IPT, ntiles, timg);
   return CAIR_OK;
 }
 
