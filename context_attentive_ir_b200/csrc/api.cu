@@ -75,7 +75,7 @@ struct cair_handle {
   } pipe[3];
   bool pipe_trace = false;
   int pipe_last = -1, pipe_last2 = -1;   // slots of the two most recently submitted batches
-  float pipe_frac = 0.45f;               // share of a batch's pairs scored under the NEXT batch's document encoder
+  float pipe_frac = 0.5f;                // share of a batch's pairs scored under the NEXT batch's document encoder
   int pipe_spc = 32;                     // document-encoder sequences per CTA in the pipeline (80 CTAs at cfg2: 68 SMs stay free)
   cudaStream_t hi_stream = nullptr, lo_stream = nullptr;
   cudaStream_t copy_stream = nullptr;

@@ -273,7 +273,7 @@ CAIR_API int32_t cair_ranker_forward_host(cair_handle* h, const int64_t* q, cons
  * overlap the kernels of batch k, and for Match-Tensor (tcgen05 path) the batches are software-pipelined on the
  * device as well - the interaction kernel of batch k runs partly on the SMs that the 200-step document-encoder
  * recurrence of batch k+1 leaves idle (internal high / low priority streams; cair_ranker_set_pipeline_split
- * sets the share of a batch's pairs scored there, default 0.45).  wait blocks until that slot's scores are in
+ * sets the share of a batch's pairs scored there, default 0.5).  wait blocks until that slot's scores are in
  * `scores` and reports bad token ids / lengths like the synchronous call (with several batches in flight a bad
  * id is reported by the first wait after it was detected).  The host buffers of a slot must stay valid and
  * unmodified until its wait returns; a slot is re-submitted only after its wait. */

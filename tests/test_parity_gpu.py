@@ -318,7 +318,7 @@ def test_match_tensor_full_cfg2_properties():
                     outs3[j % 3].zero_()
                 if it < n_it:
                     net.submit_host(*feeds[it % 2], out=outs3[it % 3], slot=it % 3)
-    lib.check(lib.load().cair_ranker_set_pipeline_split(net._cair_handle, 0.45))
+    lib.check(lib.load().cair_ranker_set_pipeline_split(net._cair_handle, 0.5))
     # (5) the spot-checked oracle agrees on a few pairs of the big batch
     idx = [0, 57, 127]
     ref = ol.run_ranker(cfg, helpers.state_dict_numpy(net), batch['q'][idx], batch['qlen'][idx], batch['d'][idx],
