@@ -149,6 +149,187 @@ __global__ void __launch_bounds__(DR_THREADS) drmm_kernel(const float* __restric
     for (int i = tid; i < Lq * 5; i += DR_THREADS) hist_out[p * Lq * 5 + i] = hist[i];
 }
 
+// ---- register-tiled variant (E % 4 == 0, Lq <= 20, Ld <= 200) --------------------------------------------------
+// drmm_kernel is bound by shared-memory wavefronts: one thread = one document token x 4 query rows needs 5 LDS.128
+// per 16 FMAs.  Here a thread owns a 4 x 4 tile (4 query rows x 4 tokens: 8 LDS.128 per 64 FMAs), which needs all
+// Ld tokens of the pair side by side; whole normalised rows of all tokens do not fit in shared memory, so the K
+// dimension is chunked instead: pass 1 computes the row norms (the rows come from HBM once), pass 2 streams the rows
+// again in 64-float K chunks (from L2), normalises them on the way into shared memory and accumulates.
+// Every cell is still the SAME sequential fp32 FMA chain over k (k ascending, x, y, z, w), on the same normalised
+// values (v * inv, inv from the same lane-strided partial sums + butterfly), as in drmm_kernel: the bins are identical.
+constexpr int D2_TOK = 200;        // tokens per pair held side by side (Ld <= D2_TOK)
+constexpr int D2_TG = D2_TOK / 4;  // token groups: thread tg owns tokens tg, tg + 50, tg + 100, tg + 150
+constexpr int D2_QG = 5;           // query-row groups of 4 (Lq <= 20)
+constexpr int D2_KC = 16;          // float4 per K chunk
+constexpr int D2_RS = D2_KC + 1;   // row stride of the chunk tile in float4 (odd: conflict-free LDS.128 across tokens)
+
+// smem: qn[20][ES] | dt[D2_TOK][D2_RS] float4 | inv[D2_TOK] | ids[D2_TOK] (int) | gate[32] | hist[20*5] (int)
+__global__ void __launch_bounds__(DR_THREADS, 2)
+    drmm2_kernel(const float* __restrict__ table, int V, int E, int ES, const int64_t* __restrict__ q,
+                 const int64_t* __restrict__ d, int N, int Lq, int Ld, int64_t pair_begin, const float* __restrict__ wg,
+                 const float* __restrict__ bg, const float* __restrict__ w0, const float* __restrict__ b0,
+                 const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ wo,
+                 const float* __restrict__ bo, float* __restrict__ scores, int32_t* __restrict__ hist_out, int* err) {
+  extern __shared__ __align__(16) float sm[];
+  float* qn = sm;
+  float4* dt = reinterpret_cast<float4*>(qn + (size_t)20 * ES);
+  float* inv = reinterpret_cast<float*>(dt + (size_t)D2_TOK * D2_RS);
+  int* ids = reinterpret_cast<int*>(inv + D2_TOK);
+  float* gate = reinterpret_cast<float*>(ids + D2_TOK);
+  int* hist = reinterpret_cast<int*>(gate + DR_MAXLQ);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t p = pair_begin + blockIdx.x;
+  const int64_t b = p / N;
+  const int E4 = E >> 2, ES4 = ES >> 2;
+
+  for (int i = tid; i < 20 * 5; i += DR_THREADS) hist[i] = 0;
+  // ---- query rows: gather, gate logit on the raw row, normalise by max(||x||, eps) (identical to drmm_kernel) ----
+  for (int i = warp; i < 20; i += DR_THREADS / 32) {
+    if (i < Lq) {
+      int64_t id = checked_id(q[b * Lq + i], V, err);
+      const float* src = table + id * E;
+      float ss = 0.f, gl = 0.f;
+      for (int e = lane; e < E; e += 32) {
+        float v = src[e];
+        qn[(size_t)i * ES + e] = v;
+        ss += v * v;
+        gl += v * wg[e];
+      }
+      ss = warp_sum(ss);
+      gl = warp_sum(gl);
+      float iv = 1.0f / fmaxf(sqrtf(ss), 1e-8f);
+      for (int e = lane; e < E; e += 32) qn[(size_t)i * ES + e] *= iv;
+      for (int e = E + lane; e < ES; e += 32) qn[(size_t)i * ES + e] = 0.f;
+      if (lane == 0) gate[i] = gl + bg[0];
+    } else {
+      for (int e = lane; e < ES; e += 32) qn[(size_t)i * ES + e] = 0.f;   // rows beyond Lq: zero (their cells are never counted)
+    }
+  }
+  // ---- pass 1: token ids and row norms (same lane-strided partial sums + butterfly as drmm_kernel) ----
+  // 5 rows per warp iteration: all their loads are issued before the first reduction (the gather is latency-bound)
+  constexpr int P1 = 5;
+  for (int j0 = warp * P1; j0 < D2_TOK; j0 += (DR_THREADS / 32) * P1) {
+    int64_t id[P1];
+    float4 v[P1][3];
+#pragma unroll
+    for (int r = 0; r < P1; ++r) id[r] = (j0 + r < Ld) ? checked_id(d[p * Ld + j0 + r], V, err) : 0;
+#pragma unroll
+    for (int r = 0; r < P1; ++r) {
+      const float4* s4 = reinterpret_cast<const float4*>(table + id[r] * E);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int e4 = lane + 32 * c;
+        v[r][c] = (j0 + r < Ld && e4 < E4) ? ldg_stream(s4 + e4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < P1; ++r) {
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        if (lane + 32 * c < E4) ss += v[r][c].x * v[r][c].x + v[r][c].y * v[r][c].y + v[r][c].z * v[r][c].z + v[r][c].w * v[r][c].w;
+      for (int e4 = lane + 96; e4 < E4; e4 += 32) {   // rows longer than 384 floats
+        const float4 x = ldg_stream(reinterpret_cast<const float4*>(table + id[r] * E) + e4);
+        if (j0 + r < Ld) ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+      }
+      ss = warp_sum(ss);
+      if (lane == 0 && j0 + r < D2_TOK) {
+        inv[j0 + r] = (j0 + r < Ld) ? 1.0f / fmaxf(sqrtf(ss), 1e-8f) : 0.f;
+        ids[j0 + r] = (int)id[r];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- pass 2: K chunks ----
+  const int tg = tid % D2_TG, qg = tid / D2_TG;   // qg == 5 for the last 6 threads: loaders only
+  float acc[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc[u][t] = 0.f;
+  for (int k0 = 0; k0 < ES4; k0 += D2_KC) {
+    const int nk = min(D2_KC, ES4 - k0);
+    // normalised chunk of every token: dt[token][f4] = table[id][k0 + f4] * inv (zeros beyond E, zero rows beyond Ld);
+    // all loads of a thread are issued before the first store (latency-bound gather from L2)
+    constexpr int P2 = (D2_TOK * D2_KC + DR_THREADS - 1) / DR_THREADS;   // 13
+    float4 lv[P2];
+#pragma unroll
+    for (int it = 0; it < P2; ++it) {
+      const int idx = tid + it * DR_THREADS;
+      const int j = idx / D2_KC, f4 = idx - j * D2_KC;
+      lv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < D2_TOK * D2_KC && j < Ld && k0 + f4 < E4)
+        lv[it] = *reinterpret_cast<const float4*>(table + (size_t)ids[j] * E + (size_t)(k0 + f4) * 4);
+    }
+#pragma unroll
+    for (int it = 0; it < P2; ++it) {
+      const int idx = tid + it * DR_THREADS;
+      if (idx < D2_TOK * D2_KC) {
+        const int j = idx / D2_KC, f4 = idx - j * D2_KC;
+        const float iv = inv[j];
+        float4 v = lv[it];
+        v.x *= iv, v.y *= iv, v.z *= iv, v.w *= iv;
+        dt[(size_t)j * D2_RS + f4] = v;
+      }
+    }
+    __syncthreads();
+    if (qg < D2_QG) {
+      const float4* q0 = reinterpret_cast<const float4*>(qn + (size_t)(4 * qg) * ES) + k0;
+      for (int f4 = 0; f4 < nk; ++f4) {
+        float4 dv[4], qv[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) dv[t] = dt[(size_t)(tg + D2_TG * t) * D2_RS + f4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) qv[u] = q0[(size_t)u * ES4 + f4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            acc[u][t] = fmaf(qv[u].x, dv[t].x, acc[u][t]);
+            acc[u][t] = fmaf(qv[u].y, dv[t].y, acc[u][t]);
+            acc[u][t] = fmaf(qv[u].z, dv[t].z, acc[u][t]);
+            acc[u][t] = fmaf(qv[u].w, dv[t].w, acc[u][t]);
+          }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- histograms ----
+  if (qg < D2_QG) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = 4 * qg + u;
+      if (i >= Lq) continue;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int j = tg + D2_TG * t;
+        const int bin = j < Ld ? drmm_bin(acc[u][t]) : -1;
+        if (bin >= 0) atomicAdd(&hist[i * 5 + bin], 1);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- epilogue: softmax gate over ALL Lq positions, ffnn(5->1->1), weighted sum, output (identical to drmm_kernel) ----
+  if (warp == 0) {
+    float g = (lane < Lq) ? gate[lane] : -INFINITY;
+    float mx = warp_max(g);
+    float ex = (lane < Lq) ? __expf(g - mx) : 0.f;
+    float den = warp_sum(ex);
+    float f = 0.f;
+    if (lane < Lq) {
+      float f0 = b0[0];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) f0 = fmaf(w0[k], (float)hist[lane * 5 + k], f0);
+      f = (w1[0] * f0 + b1[0]) * (ex / den);
+    }
+    f = warp_sum(f);
+    if (lane == 0) scores[p] = wo[0] * f + bo[0];
+  }
+  if (hist_out)
+    for (int i = tid; i < Lq * 5; i += DR_THREADS) hist_out[p * Lq * 5 + i] = hist[i];
+}
+
 int32_t drmm_forward(const cair_drmm_weights& w, const int64_t* q, const int64_t* d, int N, int Lq, int Ld,
                      int64_t pair_begin, int64_t pair_count, float* scores, int32_t* hist_out, int* err,
                      cudaStream_t s) {
@@ -157,6 +338,15 @@ int32_t drmm_forward(const cair_drmm_weights& w, const int64_t* q, const int64_t
   const int E = w.emsize;
   int ES = (E + 3) & ~3;
   if (((ES / 4) & 1) == 0) ES += 4;  // odd number of 16-byte groups per row: conflict-free LDS.128
+  if ((E & 3) == 0 && Lq <= 4 * D2_QG && Ld <= D2_TOK && ((uintptr_t)w.table & 15) == 0) {
+    const size_t smem2 = (size_t)20 * ES * sizeof(float) + (size_t)D2_TOK * D2_RS * sizeof(float4) +
+                         (size_t)D2_TOK * (sizeof(float) + sizeof(int)) + DR_MAXLQ * sizeof(float) + 20 * 5 * sizeof(int);
+    CAIR_CUDA(cudaFuncSetAttribute(drmm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    CAIR_LAUNCH(drmm2_kernel, (unsigned)pair_count, DR_THREADS, smem2, s, w.table, w.vocab, E, ES, q, d, N, Lq, Ld,
+                pair_begin, w.gating.w, w.gating.b, w.ffnn0.w, w.ffnn0.b, w.ffnn1.w, w.ffnn1.b, w.output.w,
+                w.output.b, scores, hist_out, err);
+    return CAIR_OK;
+  }
   size_t smem = ((size_t)(Lq + DR_CHUNK) * ES + DR_MAXLQ) * sizeof(float) + (size_t)Lq * 5 * sizeof(int);
   if (smem > 220 * 1024) return fail(CAIR_ERR_UNSUPPORTED, "drmm: emsize %d too large", E);
   CAIR_CUDA(cudaFuncSetAttribute(drmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
