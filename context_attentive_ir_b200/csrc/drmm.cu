@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(DR_THREADS) drmm_kernel(const float* __restric
 constexpr int D2_TOK = 200;        // tokens per pair held side by side (Ld <= D2_TOK)
 constexpr int D2_TG = D2_TOK / 4;  // token groups: thread tg owns tokens tg, tg + 50, tg + 100, tg + 150
 constexpr int D2_QG = 5;           // query-row groups of 4 (Lq <= 20)
-constexpr int D2_KC = 16;          // float4 per K chunk
+constexpr int D2_KC = 8;           // float4 per K chunk
 constexpr int D2_RS = D2_KC + 1;   // row stride of the chunk tile in float4 (odd: conflict-free LDS.128 across tokens)
 
 // smem: qn[20][ES] | dt[D2_TOK][D2_RS] float4 | inv[D2_TOK] | ids[D2_TOK] (int) | gate[32] | hist[20*5] (int)
@@ -248,12 +248,11 @@ __global__ void __launch_bounds__(DR_THREADS, 2)
   for (int u = 0; u < 4; ++u)
 #pragma unroll
     for (int t = 0; t < 4; ++t) acc[u][t] = 0.f;
-  for (int k0 = 0; k0 < ES4; k0 += D2_KC) {
-    const int nk = min(D2_KC, ES4 - k0);
-    // normalised chunk of every token: dt[token][f4] = table[id][k0 + f4] * inv (zeros beyond E, zero rows beyond Ld);
-    // all loads of a thread are issued before the first store (latency-bound gather from L2)
-    constexpr int P2 = (D2_TOK * D2_KC + DR_THREADS - 1) / DR_THREADS;   // 13
-    float4 lv[P2];
+  // Software pipeline through registers: the gather of chunk c+1 is issued before the dot product of chunk c, so its L2
+  // latency is hidden behind ~600 FMA instructions; all loads of a thread are issued before its first store.
+  constexpr int P2 = (D2_TOK * D2_KC + DR_THREADS - 1) / DR_THREADS;   // 7
+  float4 lv[P2];
+  auto gather = [&](int k0) {
 #pragma unroll
     for (int it = 0; it < P2; ++it) {
       const int idx = tid + it * DR_THREADS;
@@ -262,6 +261,11 @@ __global__ void __launch_bounds__(DR_THREADS, 2)
       if (idx < D2_TOK * D2_KC && j < Ld && k0 + f4 < E4)
         lv[it] = *reinterpret_cast<const float4*>(table + (size_t)ids[j] * E + (size_t)(k0 + f4) * 4);
     }
+  };
+  gather(0);
+  for (int k0 = 0; k0 < ES4; k0 += D2_KC) {
+    const int nk = min(D2_KC, ES4 - k0);
+    // normalised chunk of every token: dt[token][f4] = table[id][k0 + f4] * inv (zeros beyond E, zero rows beyond Ld)
 #pragma unroll
     for (int it = 0; it < P2; ++it) {
       const int idx = tid + it * DR_THREADS;
@@ -274,8 +278,10 @@ __global__ void __launch_bounds__(DR_THREADS, 2)
       }
     }
     __syncthreads();
+    if (k0 + D2_KC < ES4) gather(k0 + D2_KC);
     if (qg < D2_QG) {
       const float4* q0 = reinterpret_cast<const float4*>(qn + (size_t)(4 * qg) * ES) + k0;
+#pragma unroll 2
       for (int f4 = 0; f4 < nk; ++f4) {
         float4 dv[4], qv[4];
 #pragma unroll
