@@ -149,6 +149,16 @@ __global__ void __launch_bounds__(DR_THREADS) drmm_kernel(const float* __restric
     for (int i = tid; i < Lq * 5; i += DR_THREADS) hist_out[p * Lq * 5 + i] = hist[i];
 }
 
+// acc.{x,y} = fma(w.{x,y}, y, acc.{x,y}) as one packed instruction (fma.rn.f32x2: two independent IEEE FMAs)
+__device__ __forceinline__ void ffma2_d(float2& acc, float2 w, float y) {
+  unsigned long long a, c, yy;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(w.x), "f"(w.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(acc.x), "f"(acc.y));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(yy) : "f"(y));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(yy));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(c));
+}
+
 // ---- register-tiled variant (E % 4 == 0, Lq <= 20, Ld <= 200) --------------------------------------------------
 // drmm_kernel is bound by shared-memory wavefronts: one thread = one document token x 4 query rows needs 5 LDS.128
 // per 16 FMAs.  Here a thread owns a 4 x 4 tile (4 query rows x 4 tokens: 8 LDS.128 per 64 FMAs), which needs all
@@ -163,7 +173,8 @@ constexpr int D2_QG = 5;           // query-row groups of 4 (Lq <= 20)
 constexpr int D2_KC = 8;           // float4 per K chunk
 constexpr int D2_RS = D2_KC + 1;   // row stride of the chunk tile in float4 (odd: conflict-free LDS.128 across tokens)
 
-// smem: qn[20][ES] | dt[D2_TOK][D2_RS] float4 | inv[D2_TOK] | ids[D2_TOK] (int) | gate[32] | hist[20*5] (int)
+// smem: qn[20][ES] | qn2[10][ES][2] (row pairs interleaved) | dt[D2_TOK][D2_RS] float4 | inv[D2_TOK] | ids[D2_TOK] (int) |
+//       gate[32] | hist[20*5] (int)
 __global__ void __launch_bounds__(DR_THREADS, 2)
     drmm2_kernel(const float* __restrict__ table, int V, int E, int ES, const int64_t* __restrict__ q,
                  const int64_t* __restrict__ d, int N, int Lq, int Ld, int64_t pair_begin, const float* __restrict__ wg,
@@ -172,7 +183,8 @@ __global__ void __launch_bounds__(DR_THREADS, 2)
                  const float* __restrict__ bo, float* __restrict__ scores, int32_t* __restrict__ hist_out, int* err) {
   extern __shared__ __align__(16) float sm[];
   float* qn = sm;
-  float4* dt = reinterpret_cast<float4*>(qn + (size_t)20 * ES);
+  float* qn2 = qn + (size_t)20 * ES;
+  float4* dt = reinterpret_cast<float4*>(qn2 + (size_t)20 * ES);
   float* inv = reinterpret_cast<float*>(dt + (size_t)D2_TOK * D2_RS);
   int* ids = reinterpret_cast<int*>(inv + D2_TOK);
   float* gate = reinterpret_cast<float*>(ids + D2_TOK);
@@ -241,66 +253,90 @@ __global__ void __launch_bounds__(DR_THREADS, 2)
   }
   __syncthreads();
 
+  for (int idx = tid; idx < 10 * ES; idx += DR_THREADS) {   // interleave the normalised query rows in pairs
+    const int r = idx / ES, k = idx - r * ES;
+    qn2[(size_t)idx * 2] = qn[(size_t)(2 * r) * ES + k];
+    qn2[(size_t)idx * 2 + 1] = qn[(size_t)(2 * r + 1) * ES + k];
+  }
+  __syncthreads();
   // ---- pass 2: K chunks ----
   const int tg = tid % D2_TG, qg = tid / D2_TG;   // qg == 5 for the last 6 threads: loaders only
-  float acc[4][4];
+  float2 acc2[2][4];   // [row pair][token]: .x = row 4qg + 2up, .y = row 4qg + 2up + 1
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int up = 0; up < 2; ++up)
 #pragma unroll
-    for (int t = 0; t < 4; ++t) acc[u][t] = 0.f;
+    for (int t = 0; t < 4; ++t) acc2[up][t] = make_float2(0.f, 0.f);
   // Software pipeline through registers: the gather of chunk c+1 is issued before the dot product of chunk c, so its L2
-  // latency is hidden behind ~600 FMA instructions; all loads of a thread are issued before its first store.
+  // latency is hidden behind the FMAs; all loads of a thread are issued before its first store.  A thread's P2 gather
+  // slots (token, float4 column) are the same in every chunk: row pointers, tile offsets and 1/norm are computed once.
   constexpr int P2 = (D2_TOK * D2_KC + DR_THREADS - 1) / DR_THREADS;   // 7
+  const float4* gsrc[P2];
+  int goff[P2];
+  float ginv[P2];
+#pragma unroll
+  for (int it = 0; it < P2; ++it) {
+    const int idx = tid + it * DR_THREADS;
+    const int j = idx / D2_KC, f4 = idx - j * D2_KC;
+    const bool ok = idx < D2_TOK * D2_KC && j < Ld;
+    gsrc[it] = ok ? reinterpret_cast<const float4*>(table + (size_t)ids[j] * E) + f4 : nullptr;
+    goff[it] = idx < D2_TOK * D2_KC ? j * D2_RS + f4 : -1;
+    ginv[it] = ok ? inv[j] : 0.f;
+  }
   float4 lv[P2];
   auto gather = [&](int k0) {
 #pragma unroll
     for (int it = 0; it < P2; ++it) {
-      const int idx = tid + it * DR_THREADS;
-      const int j = idx / D2_KC, f4 = idx - j * D2_KC;
-      lv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (idx < D2_TOK * D2_KC && j < Ld && k0 + f4 < E4)
-        lv[it] = *reinterpret_cast<const float4*>(table + (size_t)ids[j] * E + (size_t)(k0 + f4) * 4);
+      const int f4 = (tid + it * DR_THREADS) % D2_KC;
+      lv[it] = (gsrc[it] && k0 + f4 < E4) ? gsrc[it][k0] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
   gather(0);
+  // the thread's two query-row pairs, interleaved in shared memory as (row 2r, row 2r+1) per k: one packed FFMA2 updates
+  // the same cell of both rows (fma.rn.f32x2 = two independent IEEE FMAs: every cell keeps its sequential chain over k)
+  const float2* qp = reinterpret_cast<const float2*>(qn2) + (size_t)(2 * qg) * ES;
   for (int k0 = 0; k0 < ES4; k0 += D2_KC) {
     const int nk = min(D2_KC, ES4 - k0);
     // normalised chunk of every token: dt[token][f4] = table[id][k0 + f4] * inv (zeros beyond E, zero rows beyond Ld)
 #pragma unroll
     for (int it = 0; it < P2; ++it) {
-      const int idx = tid + it * DR_THREADS;
-      if (idx < D2_TOK * D2_KC) {
-        const int j = idx / D2_KC, f4 = idx - j * D2_KC;
-        const float iv = inv[j];
+      if (goff[it] >= 0) {
+        const float iv = ginv[it];
         float4 v = lv[it];
         v.x *= iv, v.y *= iv, v.z *= iv, v.w *= iv;
-        dt[(size_t)j * D2_RS + f4] = v;
+        dt[goff[it]] = v;
       }
     }
     __syncthreads();
     if (k0 + D2_KC < ES4) gather(k0 + D2_KC);
     if (qg < D2_QG) {
-      const float4* q0 = reinterpret_cast<const float4*>(qn + (size_t)(4 * qg) * ES) + k0;
 #pragma unroll 2
       for (int f4 = 0; f4 < nk; ++f4) {
-        float4 dv[4], qv[4];
+        float4 dv[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) dv[t] = dt[(size_t)(tg + D2_TG * t) * D2_RS + f4];
+        const int k = (k0 + f4) * 4;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) qv[u] = q0[(size_t)u * ES4 + f4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int up = 0; up < 2; ++up) {
+          // (row 4qg+2up, row 4qg+2up+1) at k .. k+3: two 16-byte loads
+          const float4 qa = *reinterpret_cast<const float4*>(qp + (size_t)up * ES + k);
+          const float4 qb = *reinterpret_cast<const float4*>(qp + (size_t)up * ES + k + 2);
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            acc[u][t] = fmaf(qv[u].x, dv[t].x, acc[u][t]);
-            acc[u][t] = fmaf(qv[u].y, dv[t].y, acc[u][t]);
-            acc[u][t] = fmaf(qv[u].z, dv[t].z, acc[u][t]);
-            acc[u][t] = fmaf(qv[u].w, dv[t].w, acc[u][t]);
+            ffma2_d(acc2[up][t], make_float2(qa.x, qa.y), dv[t].x);
+            ffma2_d(acc2[up][t], make_float2(qa.z, qa.w), dv[t].y);
+            ffma2_d(acc2[up][t], make_float2(qb.x, qb.y), dv[t].z);
+            ffma2_d(acc2[up][t], make_float2(qb.z, qb.w), dv[t].w);
           }
+        }
       }
     }
     __syncthreads();
   }
+  float acc[4][4];
+#pragma unroll
+  for (int up = 0; up < 2; ++up)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc[2 * up][t] = acc2[up][t].x, acc[2 * up + 1][t] = acc2[up][t].y;
   // ---- histograms ----
   if (qg < D2_QG) {
 #pragma unroll
@@ -345,7 +381,7 @@ int32_t drmm_forward(const cair_drmm_weights& w, const int64_t* q, const int64_t
   int ES = (E + 3) & ~3;
   if (((ES / 4) & 1) == 0) ES += 4;  // odd number of 16-byte groups per row: conflict-free LDS.128
   if ((E & 3) == 0 && Lq <= 4 * D2_QG && Ld <= D2_TOK && ((uintptr_t)w.table & 15) == 0) {
-    const size_t smem2 = (size_t)20 * ES * sizeof(float) + (size_t)D2_TOK * D2_RS * sizeof(float4) +
+    const size_t smem2 = (size_t)40 * ES * sizeof(float) + (size_t)D2_TOK * D2_RS * sizeof(float4) +
                          (size_t)D2_TOK * (sizeof(float) + sizeof(int)) + DR_MAXLQ * sizeof(float) + 20 * 5 * sizeof(int);
     CAIR_CUDA(cudaFuncSetAttribute(drmm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     CAIR_LAUNCH(drmm2_kernel, (unsigned)pair_count, DR_THREADS, smem2, s, w.table, w.vocab, E, ES, q, d, N, Lq, Ld,
