@@ -35,3 +35,11 @@ def batchify_ranker(q_tokens, q_offsets, d_tokens, d_offsets, B, N, max_query_le
     if check and int(err.item()):
         raise lib.CairError(-1, 'batchify_ranker: a sequence is empty or longer than its padded length')
     return q, qlen, d, dlen
+
+
+def batchify_sessions(q_tokens, q_offsets, d_tokens, d_offsets, B, S, N, max_query_len=None, max_doc_len=None, check=True):
+    """The ranking-side tensors of the multitask batch (neuroir/inputters/multitask/vector.py:82-149: source_words
+    [B,S,Lq], source_lens [B,S], document_words [B,S,N,Ld], document_lens [B,S,N]) from the ragged batch of B sessions
+    of S queries with N candidates each: the same kernel over B*S queries."""
+    q, qlen, d, dlen = batchify_ranker(q_tokens, q_offsets, d_tokens, d_offsets, B * S, N, max_query_len, max_doc_len, check)
+    return q.view(B, S, -1), qlen.view(B, S), d.view(B, S, N, -1), dlen.view(B, S, N)

@@ -303,7 +303,9 @@ CAIR_API int32_t cair_rank_metrics(const float* scores, const int64_t* labels, i
  * take: q [B,Lq], qlen [B], d [B,N,Ld], dlen [B,N], PAD = 0 beyond each length.  Lq / Ld are the batch maxima
  * (or max_query_len / max_doc_len under force_pad, vector.py:18-21), chosen by the caller.  A sequence that is
  * empty or longer than its padded length ORs 2 (bad length) into *err_flag (device int32; the reference's
- * copy_ raises there).  Enqueued on `stream`, nothing is synchronised. */
+ * copy_ raises there).  The ranking-side tensors of the multitask batch (inputters/multitask/vector.py:82-149:
+ * source_words [B,S,Lq], document_words [B,S,N,Ld] and their lengths) are the same call with B*S queries.
+ * Enqueued on `stream`, nothing is synchronised. */
 CAIR_API int32_t cair_batchify_ranker(const int32_t* q_tokens, const int64_t* q_offsets, const int32_t* d_tokens,
                              const int64_t* d_offsets, int32_t B, int32_t N, int32_t Lq, int32_t Ld,
                              int64_t* q, int64_t* qlen, int64_t* d, int64_t* dlen, int32_t* err_flag,

@@ -103,3 +103,20 @@ def test_batchify_cuda_matches_reference(name):
     with pytest.raises(lib.CairError):
         batchify_ranker(t['q_tokens'], t['q_offsets'], t['d_tokens'], t['d_offsets'], cfg['B'], cfg['N'], outs['q'].shape[1],
                         outs['d'].shape[2] - 1)
+
+
+@pytest.mark.gpu
+def test_batchify_sessions_cuda_vs_oracle():
+    from context_attentive_ir_b200.inputters import batchify_sessions
+    rng = np.random.RandomState(3)
+    B, S, N = 3, 4, 5
+    ql = rng.randint(1, 12, size=B * S)
+    dl = rng.randint(1, 40, size=B * S * N)
+    qt = rng.randint(4, 999, size=ql.sum()).astype(np.int32)
+    dtok = rng.randint(4, 999, size=dl.sum()).astype(np.int32)
+    qo = np.concatenate([[0], np.cumsum(ql)]).astype(np.int64)
+    do = np.concatenate([[0], np.cumsum(dl)]).astype(np.int64)
+    got = batchify_sessions(*[torch.from_numpy(x).cuda() for x in (qt, qo, dtok, do)], B, S, N)
+    oq, oql, od, odl = rmo.batchify_flat(qt, qo, dtok, do, B * S, N)
+    assert np.array_equal(got[0].cpu().numpy(), oq.reshape(B, S, -1)) and np.array_equal(got[1].cpu().numpy(), oql.reshape(B, S))
+    assert np.array_equal(got[2].cpu().numpy(), od.reshape(B, S, N, -1)) and np.array_equal(got[3].cpu().numpy(), odl.reshape(B, S, N))
