@@ -326,6 +326,81 @@ def test_match_tensor_full_cfg2_properties():
     assert _max_rel(s[idx].cpu().numpy(), ref) < TOL
 
 
+def _ranker_properties(cfg, seed, B, N, Lq, Ld, spot=(0, 1), tol_eq=1e-5, **kw):
+    """Size-independent properties at a BASELINE.json shape: candidate-permutation equivariance, batch-composition
+    independence, doc-parallel slices assembling to the full result, and the oracle on a few spot queries."""
+    torch.manual_seed(seed)
+    net = helpers.build_module(cfg).to(DEV)
+    batch = synth.ranker_batch(seed, B, N, Lq, Ld, cfg['src_vocab_size'], **kw)
+    q, ql, d, dl = helpers.to_dev(batch, DEV)
+    with torch.no_grad():
+        s = net(q, ql, d, dl)
+        perm = torch.randperm(N, device=DEV)
+        sp = net(q, ql, d[:, perm].contiguous(), dl[:, perm].contiguous())
+        sub = net(q[:3], ql[:3], d[:3], dl[:3])
+        cut = B * N // 2 + 3
+        a = net(q, ql, d, dl, pair_slice=(0, cut))
+        b = net(q, ql, d, dl, pair_slice=(cut, B * N - cut))
+    torch.cuda.synchronize()
+    net.poll_error()
+    assert torch.isfinite(s).all()
+    scale = max(s.abs().max().item(), 1e-12)
+    assert (sp - s[:, perm]).abs().max().item() <= tol_eq * scale
+    assert (sub - s[:3]).abs().max().item() <= tol_eq * scale
+    assert (a + b - s).abs().max().item() <= tol_eq * scale
+    idx = list(spot)
+    ref = ol.run_ranker(cfg, helpers.state_dict_numpy(net), batch['q'][idx], batch['qlen'][idx], batch['d'][idx],
+                        batch['dlen'][idx])['scores']
+    return s[idx].cpu().numpy(), ref
+
+
+def test_drmm_full_cfg3_properties():
+    """BASELINE configs[2]: B=256, Lq=20, Ld=200, N=10, E=300.  Disjoint query / document ids keep the cosines away from
+    the exact-match bin edge, so the histograms - and hence the scores - are exactly permutation- and
+    batch-invariant."""
+    cfg = dict(model='drmm', emsize=300, src_vocab_size=131072, dropout_emb=0.2, nbins=5)
+    got, ref = _ranker_properties(cfg, 1237, 256, 10, 20, 200, spot=(0, 100, 255), tol_eq=0.0, disjoint=True)
+    assert _max_rel(got, ref) < TOL
+
+
+@pytest.mark.parametrize('N', [10, 50])
+def test_duet_full_cfg5_properties(N):
+    """BASELINE configs[4]: B=32, Lq=20, Ld=200, E=300, 300 filters, candidate sweep (N = 500 runs in tools/bench_models.py)."""
+    cfg = dict(model='duet', emsize=300, src_vocab_size=131072, dropout_emb=0.2, dropout=0.2, use_word=True,
+               nfilters=300, local_filter_size=1, dist_filter_size=3, pool_size=5, max_doc_len=200, max_query_len=20)
+    got, ref = _ranker_properties(cfg, 1239, 32, N, 20, 200, spot=(0, 31), overlap=0.1)
+    assert _max_rel(got, ref) < TOL
+
+
+def test_cars_full_cfg4_properties():
+    """BASELINE configs[3]: CARS B=32, S=7, N=10, Lq=20, Ld=200, E=300, H=256 - session sharding assembles to the full
+    result and a sub-batch of sessions scores the same (the click-mask width is batch-global, so the sub-batch keeps the
+    session that carries the batch maximum of clicks); oracle on that sub-batch."""
+    cfg = dict(model='cars', emsize=300, src_vocab_size=131072, tgt_vocab_size=50, dropout_emb=0.2, dropout=0.2, rnn_type='LSTM',
+               bidirection=True, nlayers=1, nhid_query=256, nhid_document=256, nhid_click=512, nhid_session_query=512,
+               nhid_session_document=512, nhid_decoder=512, query_session_off=False, doc_session_off=False, dropout_rnn=0.2,
+               attn_type='general', mlp_nhid=150, pool_type='attn', regularize_coeff=0.1, alpha=0.1, lambda1=0.01,
+               lambda2=0.0001, turn_ranker_off=False, turn_recommender_off=False)
+    torch.manual_seed(11)
+    net = helpers.build_module(cfg).to(DEV)
+    B, S, N = 32, 7, 10
+    batch = synth.session_batch(1238, B, S, N, 20, 200, cfg['src_vocab_size'], max_clicks=1)
+    args = helpers.to_dev(batch, DEV, ('q', 'qlen', 'd', 'dlen', 'label'))
+    with torch.no_grad():
+        s = net.score(*args)['scores']
+        a = net.score(*args, session_slice=(0, 13))['scores']
+        b = net.score(*args, session_slice=(13, B - 13))['scores']
+        sub = net.score(*[t[:2].contiguous() for t in args])['scores']
+    torch.cuda.synchronize()
+    assert torch.isfinite(s).all()
+    scale = s.abs().max().item()
+    assert (a + b - s).abs().max().item() <= 1e-5 * scale
+    assert (sub - s[:2]).abs().max().item() <= 1e-5 * scale     # max_clicks=1: every row has exactly one click
+    ref = ol.run_cars(cfg, helpers.state_dict_numpy(net), batch['q'][:2], batch['qlen'][:2], batch['d'][:2], batch['dlen'][:2],
+                      batch['label'][:2])
+    assert _max_rel(s[:2].cpu().numpy(), ref['scores']) < TOL
+
+
 def test_bad_token_id_is_reported():
     cfg, ins, sd, outs = ol.load_golden('esm_cfg1')
     net = helpers.build_module(cfg, sd, DEV)
