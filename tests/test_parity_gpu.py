@@ -401,6 +401,22 @@ def test_cars_full_cfg4_properties():
     assert _max_rel(s[:2].cpu().numpy(), ref['scores']) < TOL
 
 
+@pytest.mark.parametrize('V,E,T', [(1000, 64, 400), (5000, 300, 12345), (300, 50, 77)])
+def test_embed_gather_entry_point(V, E, T):
+    """cair_embed_gather (modules/embeddings.py:243-252): out[t] = table[ids[t]], bit-exact, PAD row included."""
+    rng = np.random.default_rng(V + E)
+    table = rng.standard_normal((V, E)).astype(np.float32)
+    table[0] = 0
+    ids = rng.integers(0, V, T).astype(np.int64)
+    ids[:5] = 0
+    tt, ti = torch.from_numpy(table).to(DEV), torch.from_numpy(ids).to(DEV)
+    out = torch.full((T, E), float('nan'), device=DEV)
+    lib.check(lib.load().cair_embed_gather(tt.data_ptr(), V, E, ti.data_ptr(), T, out.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), table[ids])
+
+
 def test_bad_token_id_is_reported():
     cfg, ins, sd, outs = ol.load_golden('esm_cfg1')
     net = helpers.build_module(cfg, sd, DEV)

@@ -13,7 +13,7 @@ from context_attentive_ir_b200 import synth
 ap = argparse.ArgumentParser()
 ap.add_argument('--steps', type=int, default=20)
 ap.add_argument('--warmup', type=int, default=3)
-ap.add_argument('--models', default='esm,esm300,drmm,duet,cars')
+ap.add_argument('--models', default='gather,esm,esm300,drmm,duet,cars')
 args = ap.parse_args()
 dev = 'cuda:0'
 peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
@@ -53,8 +53,27 @@ def ranker(name, cfg, B, N, Lq, Ld, bytes_per_pair=None, **kw):
 def bpp(E, Lq, Ld, N):  # int64 ids, fp32 table rows, one fp32 score
     return Ld * (8 + E * 4) + (Lq * (8 + E * 4) + 8) / N + 12
 
+def gather_bench(V, E, T):
+    import ctypes as C
+    from context_attentive_ir_b200 import lib
+    torch.manual_seed(3)
+    table = torch.randn(V, E, device=dev)
+    ids = torch.randint(4, V, (T,), device=dev, dtype=torch.int64)
+    out = torch.empty(T, E, device=dev)
+    L = lib.load()
+    fn = lambda: lib.check(L.cair_embed_gather(table.data_ptr(), V, E, ids.data_ptr(), T, out.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream))
+    mean, best = timeit(fn)
+    moved = T * (8 + 2 * E * 4)   # id + row read + row written
+    print(json.dumps(dict(model='embed_gather', config=dict(V=V, E=E, tokens=T), tokens_per_s=T / (mean / 1e3), ms_per_step=mean,
+                          ms_best=best, hbm_gbs=moved / (mean / 1e3) / 1e9, hbm_peak_gbs=HBM, hbm_frac=moved / (mean / 1e3) / 1e9 / HBM,
+                          bytes_moved=moved)), flush=True)
+
+
 for m in args.models.split(','):
-    if m == 'esm':
+    if m == 'gather':
+        gather_bench(131072, 300, 512000)   # the doc tokens of cfg3 (B=256, N=10, Ld=200)
+    elif m == 'esm':
         ranker('esm cfg1', dict(model='esm', emsize=64, src_vocab_size=10000), 8, 5, 10, 50, bpp(64, 10, 50, 5))
     elif m == 'esm300':
         ranker('esm E=300 (cfg3 shape)', dict(model='esm', emsize=300, src_vocab_size=131072), 256, 10, 20, 200, bpp(300, 20, 200, 10))
