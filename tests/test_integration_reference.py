@@ -1,0 +1,73 @@
+"""Drop-in check against the UNMODIFIED reference wrappers (only where /root/reference exists, i.e. in the build
+container; the GPU box has no reference tree): after integration.install() the reference's own Ranker / Multitask
+wrappers construct the B200 networks, and a checkpoint written by the reference's stock network loads into ours through
+the wrapper's own save / load code (.mdl format, neuroir/models/ranker.py:266-327)."""
+import argparse
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+import oracle_lib as ol
+
+REF = '/root/reference'
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'neuroir')), reason='reference tree not present')
+
+
+def _import_reference():
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    if 'prettytable' not in sys.modules:   # models/ranker.py imports it for a parameter table only
+        stub = types.ModuleType('prettytable')
+        stub.PrettyTable = type('PrettyTable', (), {'__init__': lambda self, *a, **k: None})
+        sys.modules['prettytable'] = stub
+    import neuroir.models.ranker as ref_ranker
+    return ref_ranker
+
+
+def _args(cfg):
+    ns = argparse.Namespace(**{k: v for k, v in cfg.items() if k != 'model'})
+    ns.model_type = cfg['model']
+    return ns
+
+
+class _Dict(dict):
+    """Stand-in for the reference's vocabulary object: the wrapper only calls len() on it here."""
+
+
+@pytest.mark.parametrize('name', ['mt_tiny', 'drmm_overlap', 'duet_tiny', 'esm_cfg1'])
+def test_reference_wrapper_builds_b200_networks_and_round_trips_mdl(name, tmp_path):
+    ref_ranker = _import_reference()
+    import importlib
+    stock = importlib.reload(ref_ranker)                      # pristine class bindings
+    cfg, ins, sd, outs = ol.load_golden(name)
+    vocab = _Dict((i, i) for i in range(cfg['src_vocab_size']))
+    # 1. the reference's stock network, written to a .mdl by the reference's own save()
+    ref_model = stock.Ranker(_args(cfg), vocab, {k: torch.from_numpy(v) for k, v in sd.items()})
+    stock_cls = type(ref_model.network)
+    path = str(tmp_path / 'model.mdl')
+    ref_model.save(path)
+    # 2. install() rebinds the class names the wrapper imported; the same wrapper code now builds our module
+    import context_attentive_ir_b200.integration as integ
+    from context_attentive_ir_b200 import rankers
+    done = integ.install()
+    assert any(x.startswith('neuroir.models.ranker.') for x in done)
+    orig_load = torch.load
+    torch.load = lambda *a, **k: orig_load(*a, **{**k, 'weights_only': False})   # SURVEY App. C5 (torch >= 2.6 default)
+    try:
+        mine = stock.Ranker.load(path)
+    finally:
+        torch.load = orig_load
+    assert isinstance(mine.network, rankers._Ranker) and not isinstance(mine.network, stock_cls)
+    got = mine.network.state_dict()
+    assert sorted(got) == sorted(sd)
+    for k in sd:
+        assert torch.equal(got[k], torch.from_numpy(sd[k])), k
+    # 3. no silent CPU path: the wrapper's predict() on CPU tensors fails loudly instead of falling back
+    ex = {'que_rep': torch.from_numpy(ins['q']), 'que_len': torch.from_numpy(ins['qlen']),
+          'doc_rep': torch.from_numpy(ins['d']), 'doc_len': torch.from_numpy(ins['dlen'])}
+    with pytest.raises(RuntimeError, match='CUDA'):
+        mine.predict(ex)
+    importlib.reload(ref_ranker)                               # leave the reference module pristine for other tests
