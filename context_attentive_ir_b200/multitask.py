@@ -151,6 +151,29 @@ class CARS(_CairModule):
 DECODER_PREFIXES = ('decoder.', 'token_prob_predictor', 'dec_attn', 'transform_', 'private_session_projector2')
 
 
+def _carry_load_state_dict(self, state_dict, strict=True, **kw):
+    """nn.Module.load_state_dict for a reference checkpoint: the decoder-side tensors (suggestion path) are not parameters
+    of this module; they are kept untouched and handed back by state_dict(), so a checkpoint loaded and saved through the
+    reference's Multitask wrapper (models/multitask.py:49-58, 330-352) keeps every key."""
+    carried = {k: v for k, v in state_dict.items() if k.startswith(DECODER_PREFIXES)}
+    mine = {k: v for k, v in state_dict.items() if k not in carried}
+    out = nn.Module.load_state_dict(self, mine, strict=strict, **kw)
+    self.__dict__['_carried_decoder_state'] = carried
+    return out
+
+
+def _carry_state_dict(self, *args, **kw):
+    sd = nn.Module.state_dict(self, *args, **kw)
+    prefix = kw.get('prefix', args[1] if len(args) > 1 else '')
+    for k, v in self.__dict__.get('_carried_decoder_state', {}).items():
+        sd[prefix + k] = v
+    return sd
+
+
+CARS.load_state_dict = _carry_load_state_dict
+CARS.state_dict = _carry_state_dict
+
+
 def ranking_state_dict(reference_state_dict):
     """Filters a reference CARS state_dict down to the ranking-path keys this module owns."""
     return {k: v for k, v in reference_state_dict.items() if not k.startswith(DECODER_PREFIXES)}

@@ -71,3 +71,37 @@ def test_reference_wrapper_builds_b200_networks_and_round_trips_mdl(name, tmp_pa
     with pytest.raises(RuntimeError, match='CUDA'):
         mine.predict(ex)
     importlib.reload(ref_ranker)                               # leave the reference module pristine for other tests
+
+
+def test_reference_multitask_wrapper_builds_b200_cars_and_keeps_decoder_keys(tmp_path):
+    """CARS under the reference's Multitask wrapper: the FULL reference state_dict (ranking + suggestion-decoder keys)
+    loads through the wrapper's strict load_state_dict, the ranking tensors land in the B200 module, and the decoder-side
+    tensors are carried through unchanged into the next save()."""
+    _import_reference()
+    import importlib
+    import neuroir.models.multitask as ref_mt
+    ref_mt = importlib.reload(ref_mt)
+    from neuroir.multitask.cars import CARS as RefCARS
+    cfg, ins, sd, outs = ol.load_golden('cars_tiny')
+    args = _args(cfg)
+    src = _Dict((i, i) for i in range(cfg['src_vocab_size']))
+    tgt = _Dict((i, i) for i in range(cfg['tgt_vocab_size']))
+    torch.manual_seed(1013)
+    stock = ref_mt.Multitask(argparse.Namespace(**vars(args)), src, tgt)
+    assert isinstance(stock.network, RefCARS)
+    full = stock.network.state_dict()
+    for k, v in sd.items():                                    # the fixture's ranking weights into the stock network
+        if k in full:
+            full[k] = torch.from_numpy(v)
+    import context_attentive_ir_b200.integration as integ
+    from context_attentive_ir_b200 import multitask
+    assert 'neuroir.models.multitask.CARS' in integ.install()
+    mine = ref_mt.Multitask(argparse.Namespace(**vars(args)), src, tgt, dict(full))
+    assert isinstance(mine.network, multitask.CARS)
+    got = mine.network.state_dict()
+    assert sorted(got) == sorted(full)
+    decoder_keys = [k for k in full if k.startswith(multitask.DECODER_PREFIXES)]
+    assert decoder_keys
+    for k in full:
+        assert torch.equal(got[k], full[k]), k
+    importlib.reload(ref_mt)
