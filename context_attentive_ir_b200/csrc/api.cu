@@ -194,25 +194,34 @@ int32_t cair_embed_gather(const float* table, int32_t V, int32_t E, const int64_
   return embed_gather(table, V, E, ids, T, out, nullptr, (cudaStream_t)stream);
 }
 
-int32_t cair_lstm_forward(const float* x, const int64_t* len, int32_t n, int32_t L, int32_t in, int32_t h,
-                          const cair_lstm_dir* fwd, const cair_lstm_dir* rev, float* out, float* h_n, float* c_n,
-                          void* stream) {
-  if (!x || !len || !out || !fwd || n < 0 || L <= 0) return fail(CAIR_ERR_BAD_ARG, "lstm_forward: bad argument");
+int32_t cair_rnn_forward(int32_t rnn_type, const float* x, const int64_t* len, int32_t n, int32_t L, int32_t in, int32_t h,
+                         const cair_lstm_dir* fwd, const cair_lstm_dir* rev, float* out, float* h_n, float* c_n,
+                         void* stream) {
+  if (!x || !len || !out || !fwd || n < 0 || L <= 0) return fail(CAIR_ERR_BAD_ARG, "rnn_forward: bad argument");
+  if (rnn_type != CAIR_RNN_LSTM && rnn_type != CAIR_RNN_GRU) return fail(CAIR_ERR_BAD_ARG, "rnn_forward: rnn_type must be LSTM or GRU");
   // unit-test entry point: packs the weights and allocates its scratch on every call
   cudaStream_t s = (cudaStream_t)stream;
   Owned own;
   LstmPack p;
-  int32_t rc = lstm_pack(own, fwd, rev, in, h, &p, s);
+  int32_t rc = lstm_pack(own, fwd, rev, in, h, &p, s, rnn_type);
   float* pre = nullptr;
   int* err = nullptr;
-  const bool tc = lstm_tc_supported(in, h);  // tensor-core kernel when the shape fits, fp32 kernel otherwise
+  // engine: cluster-split tcgen05 kernel when the shape fits (h <= 128), else / on request the round-1 tcgen05 kernel
+  // (LSTM, in < 48, h <= 64) or the fp32 kernels
+  const bool rt = g_rnn_impl == RNN_IMPL_CLUSTER && rnn_tc_supported(in, h);
+  const bool tc = !rt && g_rnn_impl != RNN_IMPL_FP32 && rnn_type == CAIR_RNN_LSTM && lstm_tc_supported(in, h);
+  RnnTcPack rp;
   LstmTcPack tp;
+  if (rc == CAIR_OK && rt) rc = rnn_tc_pack(own, fwd, rev, in, h, rnn_type, &rp, s);
   if (rc == CAIR_OK && tc) rc = lstm_tc_pack(own, fwd, rev, in, h, &tp, s);
-  if (rc == CAIR_OK && !tc && own.alloc(&pre, lstm_workspace_floats(p, n, L)) != cudaSuccess) rc = fail(CAIR_ERR_CUDA, "lstm_forward: out of memory");
-  if (rc == CAIR_OK && own.alloc(&err, 1) != cudaSuccess) rc = fail(CAIR_ERR_CUDA, "lstm_forward: out of memory");
+  const size_t pre_floats = rt ? rnn_tc_workspace_floats(rp, n, L) : tc ? 0 : lstm_workspace_floats(p, n, L);
+  if (rc == CAIR_OK && pre_floats && own.alloc(&pre, pre_floats) != cudaSuccess) rc = fail(CAIR_ERR_CUDA, "rnn_forward: out of memory");
+  if (rc == CAIR_OK && own.alloc(&err, 1) != cudaSuccess) rc = fail(CAIR_ERR_CUDA, "rnn_forward: out of memory");
   if (rc == CAIR_OK) {
     cudaMemsetAsync(err, 0, sizeof(int), s);
-    if (tc)
+    if (rt)
+      rc = rnn_tc_run(rp, gemm_dense(x, in), len, n, L, out, h_n, c_n, pre, err, s, "lstm_recurrence");
+    else if (tc)
       rc = lstm_tc_run(tp, p.bias, gemm_dense(x, in), len, n, L, out, h_n, c_n, err, s, "lstm_recurrence");
     else
       rc = lstm_run(p, gemm_dense(x, in), len, n, L, out, h_n, c_n, pre, err, s);
@@ -221,9 +230,33 @@ int32_t cair_lstm_forward(const float* x, const int64_t* len, int32_t n, int32_t
   if (rc == CAIR_OK) cudaMemcpyAsync(&flags, err, sizeof(int), cudaMemcpyDeviceToHost, s);
   cudaError_t e = cudaStreamSynchronize(s);
   own.release();
-  if (rc == CAIR_OK && e != cudaSuccess) rc = fail(CAIR_ERR_CUDA, "lstm_forward: %s", cudaGetErrorString(e));
-  if (rc == CAIR_OK && flags) rc = fail(CAIR_ERR_BAD_ARG, "lstm_forward: length outside [1, L]");
+  if (rc == CAIR_OK && e != cudaSuccess) rc = fail(CAIR_ERR_CUDA, "rnn_forward: %s", cudaGetErrorString(e));
+  if (rc == CAIR_OK && flags) rc = fail(CAIR_ERR_BAD_ARG, "rnn_forward: length outside [1, L]");
   return rc;
+}
+
+int32_t cair_lstm_forward(const float* x, const int64_t* len, int32_t n, int32_t L, int32_t in, int32_t h,
+                          const cair_lstm_dir* fwd, const cair_lstm_dir* rev, float* out, float* h_n, float* c_n,
+                          void* stream) {
+  return cair_rnn_forward(CAIR_RNN_LSTM, x, len, n, L, in, h, fwd, rev, out, h_n, c_n, stream);
+}
+
+int32_t cair_set_rnn_impl(int32_t impl) {
+  if (impl < RNN_IMPL_FP32 || impl > RNN_IMPL_CLUSTER)
+    return fail(CAIR_ERR_BAD_ARG, "set_rnn_impl: 0 (fp32 CUDA cores), 1 (round-1 tcgen05 kernel) or 2 (cluster-split tcgen05 kernel)");
+  g_rnn_impl = impl;
+  return CAIR_OK;
+}
+
+// debugging / tuning aids (not in the public header)
+extern "C" __attribute__((visibility("default"))) int32_t cair_rnn_debug_timing(long long* dev_counters) {
+  cair::g_rnn_dbg = dev_counters;
+  return CAIR_OK;
+}
+extern "C" __attribute__((visibility("default"))) int32_t cair_rnn_set_seqs_per_cluster(int32_t min_spc, int32_t force_spc) {
+  cair::g_rnn_spc_min = min_spc > 0 ? min_spc : 8;
+  cair::g_rnn_spc_force = force_spc > 0 ? force_spc : 0;
+  return CAIR_OK;
 }
 
 // ---- create ------------------------------------------------------------------------------------
@@ -725,7 +758,8 @@ int32_t cair_ranker_submit_host(cair_handle* h, const int64_t* q, const int64_t*
   if (prev >= 0) {
     cair_handle::PipeSlot& pp = h->pipe[prev];
     const int64_t pcp = (int64_t)pp.B * pp.N;
-    free_sms = kSMs - lstm_tc_ctas((int)nbn, h->mt.tc_d.dirs, h->pipe_spc);
+    free_sms = kSMs - ((g_rnn_impl == RNN_IMPL_CLUSTER && h->mt.rt_d.wimg) ? rnn_tc_plan(h->mt.rt_d, (int)nbn, h->pipe_spc).ctas
+                                                                            : lstm_tc_ctas((int)nbn, h->mt.tc_d.dirs, h->pipe_spc));
     if (free_sms >= 8) c1 = (int64_t)((double)pcp * h->pipe_frac);
     CAIR_CUDA(cudaStreamWaitEvent(L, pp.ev_enc, 0));
     CAIR_TRY(pipe_mark(h, prev, 2, L));

@@ -42,6 +42,8 @@ int32_t cars_create_state(Owned& own, const cair_cars_weights& w, CarsState* st,
   CAIR_TRY(dev_copy(own, w.table, (size_t)w.vocab * w.emsize, &st->table, s));
   CAIR_TRY(lstm_pack(own, &w.query_fwd, &w.query_rev, w.emsize, st->Hq / 2, &st->enc_q, s));
   CAIR_TRY(lstm_pack(own, &w.doc_fwd, &w.doc_rev, w.emsize, st->Hd / 2, &st->enc_d, s));
+  if (rnn_tc_supported(w.emsize, st->Hq / 2)) CAIR_TRY(rnn_tc_pack(own, &w.query_fwd, &w.query_rev, w.emsize, st->Hq / 2, CAIR_RNN_LSTM, &st->rt_q, s));
+  if (rnn_tc_supported(w.emsize, st->Hd / 2)) CAIR_TRY(rnn_tc_pack(own, &w.doc_fwd, &w.doc_rev, w.emsize, st->Hd / 2, CAIR_RNN_LSTM, &st->rt_d, s));
   CAIR_TRY(lstm_pack(own, &w.session_query, nullptr, st->Hq, st->Hsq, &st->sess_q, s));
   CAIR_TRY(lstm_pack(own, &w.session_doc, nullptr, st->Hd, st->Hsd, &st->sess_d, s));
   CAIR_TRY(attn_copy(own, w.q_attn, st->Hq, &st->q_attn, s));
@@ -361,12 +363,17 @@ __global__ void fill_len_kernel(int64_t* len, int n, int64_t v) {
   if (i < n) len[i] = v;
 }
 
-static int32_t encode_pool(const CarsState& st, const LstmPack& lp, const AttnPack& ap, const int64_t* ids,
+static int32_t encode_pool(const CarsState& st, const LstmPack& lp, const RnnTcPack& rt, const AttnPack& ap, const int64_t* ids,
                            const int64_t* len, int64_t n, int L, float* pre, float* enc, float* hid, float* pooled,
-                           int* err, cudaStream_t s) {
+                           int* err, cudaStream_t s, const char* rec_name) {
   const int H = ap.H;
-  CAIR_TRY(lstm_run(lp, gemm_gather(st.table, st.V, st.E, ids, 1, 1, 1, err), len, (int)n, L, enc, nullptr, nullptr,
-                    pre, err, s));
+  if (g_rnn_impl == RNN_IMPL_CLUSTER && rt.wimg)   // tcgen05 recurrence (pre-gates from the gathered tcgen05 GEMM)
+    CAIR_TRY(rnn_tc_run(rt, gemm_gather(st.table, st.V, st.E, ids, 1, 1, 1, err), len, (int)n, L, enc, nullptr, nullptr, pre,
+                        err, s, rec_name));
+  else
+    CAIR_TRY(lstm_run(lp, gemm_gather(st.table, st.V, st.E, ids, 1, 1, 1, err), len, (int)n, L, enc, nullptr, nullptr,
+                      pre, err, s, rec_name));
+  prof_mark("attention_pool", s);
   CAIR_TRY(gemm_auto(gemm_dense(enc, H), ap.w0, ap.w0_tc, ap.b0, hid, H, n * L, H, H, ACT_TANH, s));
   CAIR_LAUNCH(attn_pool_kernel, (unsigned)n, 256, (size_t)L * sizeof(float), s, enc, hid, len, L, H, ap.w3, ap.b3,
               pooled);
@@ -404,8 +411,11 @@ int32_t cars_forward(const CarsState& st, const CarsIO& io, int B, int S, int N,
   if (!ws.ok()) return fail(CAIR_ERR_WORKSPACE, "cars: workspace too small");
 
   // 1. encode + attention pooling
-  CAIR_TRY(encode_pool(st, st.enc_q, st.q_attn, io.q + r0 * Lq, io.qlen + r0, nrows, Lq, pre_q, enc_q, hid_q, pq, err, s));
-  CAIR_TRY(encode_pool(st, st.enc_d, st.d_attn, io.d + r0 * N * Ld, io.dlen + r0 * N, ndocs, Ld, pre_d, enc_d, hid_d, pd, err, s));
+  prof_mark("query_pregates", s);
+  CAIR_TRY(encode_pool(st, st.enc_q, st.rt_q, st.q_attn, io.q + r0 * Lq, io.qlen + r0, nrows, Lq, pre_q, enc_q, hid_q, pq, err, s, "query_recurrence"));
+  prof_mark("doc_pregates", s);
+  CAIR_TRY(encode_pool(st, st.enc_d, st.rt_d, st.d_attn, io.d + r0 * N * Ld, io.dlen + r0 * N, ndocs, Ld, pre_d, enc_d, hid_d, pd, err, s, "doc_recurrence"));
+  prof_mark("session", s);
   // 2. click vectors
   CAIR_CUDA(cudaMemsetAsync(mwidth, 0, sizeof(int), s));
   CAIR_LAUNCH(click_width_kernel, (B * S + 255) / 256, 256, 0, s, io.labels, B * S, N, mwidth);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <string>
@@ -277,5 +278,30 @@ int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, cons
                     const uint8_t* ximg = nullptr, int min_spc = 8);   // min_spc: fewest sequences per CTA to consider
 // table [V, in] fp32 -> image [V][hi|lo][48 x bf16] (constant 1 in K slot `in` = the bias column, zero padding)
 int32_t lstm_tc_pack_table(Owned& own, const float* table, int V, int in, uint8_t** img, cudaStream_t s);
+
+// tcgen05 recurrence, gate rows split over a thread-block cluster (rnn_tc.cu): LSTM and GRU, h <= 128 per direction.
+struct RnnTcPack {
+  int in = 0, h = 0, dirs = 0, cs = 0, gru = 0, fused = 0, planes = 0;
+  size_t img_bytes = 0;      // one (dir, rank) weight image
+  uint8_t* wimg = nullptr;   // [dirs][cs] images
+  float *wp = nullptr, *bp = nullptr;   // PRE mode (in >= 48): permuted + pre-scaled W_ih [dirs 4h, in] and bias
+  GemmTcW wp_tc;
+};
+struct RnnTcPlan {
+  int spc = 0, npad = 0, groups = 0, ctas = 0, nb = 0;
+};
+enum { RNN_IMPL_FP32 = 0, RNN_IMPL_TC_R1 = 1, RNN_IMPL_CLUSTER = 2 };
+extern int g_rnn_impl;   // recurrence engine: 2 (default) cluster-split tcgen05 kernel, 1 round-1 tcgen05 kernel, 0 fp32 CUDA cores
+extern long long* g_rnn_dbg;
+extern int g_rnn_spc_min, g_rnn_spc_force;
+bool rnn_tc_supported(int in, int h);
+int32_t rnn_tc_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, int in, int h, int rnn_type,
+                    RnnTcPack* out, cudaStream_t s);
+int32_t rnn_tc_pack_table(Owned& own, const float* table, int V, int in, uint8_t** img, cudaStream_t s);
+RnnTcPlan rnn_tc_plan(const RnnTcPack& p, int n, int min_spc = 8);
+size_t rnn_tc_workspace_floats(const RnnTcPack& p, int64_t n, int L);   // PRE mode pre-gates
+// x: dense rows or gathered table rows; ws_pre: rnn_tc_workspace_floats floats (PRE mode); ximg: pre-split table (FUSED, gathered)
+int32_t rnn_tc_run(const RnnTcPack& p, const GemmA& x, const int64_t* len, int n, int L, float* out, float* h_n, float* c_n,
+                   float* ws_pre, int* err, cudaStream_t s, const char* rec_name, const uint8_t* ximg = nullptr, int min_spc = 8);
 
 }  // namespace cair

@@ -68,7 +68,8 @@ struct MtState {
   int impl = MT_IMPL_TC;  // interaction kernel: tcgen05 bf16x3 (default) or the fp32 CUDA-core kernel
   float* folded = nullptr;  // [V, F] = table W_p^T + b_p  (eval-mode fold of mtensor.py:77-90)
   LstmPack enc_q{}, enc_d{};
-  LstmTcPack tc_q{}, tc_d{};  // tensor-core encoders (valid when lstm_tc_supported)
+  LstmTcPack tc_q{}, tc_d{};  // round-1 tensor-core encoders (LSTM, h <= 64, in < 48; kept for A/B runs)
+  RnnTcPack rt_q{}, rt_d{};   // cluster-split tensor-core encoders (LSTM + GRU, h <= 128)
   uint8_t* folded_img = nullptr;  // folded table pre-split into hi/lo bf16 x-operand rows (lstm_tc_pack_table)
   float *wq = nullptr, *bq = nullptr, *wd = nullptr, *bd = nullptr;  // channel projections
   uint8_t* wd_img = nullptr;  // hi/lo operand image of the doc projection (fused projection + A image kernel)
@@ -169,6 +170,7 @@ struct CarsState {
   int rd[3] = {0, 0, 0}, pool = 2;
   float* table = nullptr;
   LstmPack enc_q{}, enc_d{}, sess_q{}, sess_d{};
+  RnnTcPack rt_q{}, rt_d{};   // tcgen05 recurrence of the query / document BiLSTM (h <= 128 per direction)
   AttnPack q_attn, d_attn, click_attn, sq_inner, sd_inner;
   float *sqa_w = nullptr, *sqa_b = nullptr, *sda_w = nullptr, *sda_b = nullptr;  // session_{query,doc}_attn
   float *qp_w = nullptr, *qp_b = nullptr;  // q_projection

@@ -275,12 +275,18 @@ int32_t mt_create_state(Owned& own, const cair_mt_weights& w, MtState* st, cudaS
                     w.featsize, w.vocab, w.featsize, w.emsize, ACT_NONE, s));
   CAIR_TRY(lstm_pack(own, &w.query_fwd, dirs == 2 ? &w.query_rev : nullptr, w.featsize, w.nhid_query / dirs, &st->enc_q, s, w.rnn_type));
   CAIR_TRY(lstm_pack(own, &w.doc_fwd, dirs == 2 ? &w.doc_rev : nullptr, w.featsize, w.nhid_doc / dirs, &st->enc_d, s, w.rnn_type));
-  const bool lstm = w.rnn_type == CAIR_RNN_LSTM;  // the tensor-core recurrence implements the LSTM cell; GRU runs on the fp32 kernel
+  // tcgen05 recurrence (rnn_tc.cu): LSTM and GRU, h <= 128 per direction; round-1 kernel (lstm_tc.cu) kept for A/B runs
+  if (rnn_tc_supported(w.featsize, w.nhid_query / dirs))
+    CAIR_TRY(rnn_tc_pack(own, &w.query_fwd, dirs == 2 ? &w.query_rev : nullptr, w.featsize, w.nhid_query / dirs, w.rnn_type, &st->rt_q, s));
+  if (rnn_tc_supported(w.featsize, w.nhid_doc / dirs))
+    CAIR_TRY(rnn_tc_pack(own, &w.doc_fwd, dirs == 2 ? &w.doc_rev : nullptr, w.featsize, w.nhid_doc / dirs, w.rnn_type, &st->rt_d, s));
+  const bool lstm = w.rnn_type == CAIR_RNN_LSTM;
   if (lstm && lstm_tc_supported(w.featsize, w.nhid_query / dirs))
     CAIR_TRY(lstm_tc_pack(own, &w.query_fwd, dirs == 2 ? &w.query_rev : nullptr, w.featsize, w.nhid_query / dirs, &st->tc_q, s));
   if (lstm && lstm_tc_supported(w.featsize, w.nhid_doc / dirs))
     CAIR_TRY(lstm_tc_pack(own, &w.doc_fwd, dirs == 2 ? &w.doc_rev : nullptr, w.featsize, w.nhid_doc / dirs, &st->tc_d, s));
-  if (st->tc_q.wimg || st->tc_d.wimg) CAIR_TRY(lstm_tc_pack_table(own, st->folded, w.vocab, w.featsize, &st->folded_img, s));
+  if ((st->rt_q.wimg && st->rt_q.fused) || (st->rt_d.wimg && st->rt_d.fused) || st->tc_q.wimg || st->tc_d.wimg)
+    CAIR_TRY(rnn_tc_pack_table(own, st->folded, w.vocab, w.featsize, &st->folded_img, s));   // same row format for both kernels
   CAIR_TRY(dev_copy(own, w.query_projection.w, (size_t)w.nchannels * w.nhid_query, &st->wq, s));
   CAIR_TRY(dev_copy(own, w.query_projection.b, (size_t)w.nchannels, &st->bq, s));
   CAIR_TRY(dev_copy(own, w.document_projection.w, (size_t)w.nchannels * w.nhid_doc, &st->wd, s));
@@ -301,11 +307,13 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
   // queries touched by the pair slice [pb, pb+pc)
   const int64_t qb = pc > 0 ? pb / N : 0;
   const int64_t nq = pc > 0 ? (pb + pc - 1) / N - qb + 1 : 0;
-  const bool tc_q = st.impl != MT_IMPL_FP32 && st.tc_q.wimg != nullptr;
-  const bool tc_d = st.impl != MT_IMPL_FP32 && st.tc_d.wimg != nullptr;
-  float* pre_q = ws.take<float>(tc_q ? 0 : lstm_workspace_floats(st.enc_q, nq, Lq));
+  const bool rt_q = st.impl != MT_IMPL_FP32 && g_rnn_impl == RNN_IMPL_CLUSTER && st.rt_q.wimg != nullptr;
+  const bool rt_d = st.impl != MT_IMPL_FP32 && g_rnn_impl == RNN_IMPL_CLUSTER && st.rt_d.wimg != nullptr;
+  const bool tc_q = !rt_q && st.impl != MT_IMPL_FP32 && g_rnn_impl != RNN_IMPL_FP32 && st.tc_q.wimg != nullptr;
+  const bool tc_d = !rt_d && st.impl != MT_IMPL_FP32 && g_rnn_impl != RNN_IMPL_FP32 && st.tc_d.wimg != nullptr;
+  float* pre_q = ws.take<float>(rt_q ? rnn_tc_workspace_floats(st.rt_q, nq, Lq) : tc_q ? 0 : lstm_workspace_floats(st.enc_q, nq, Lq));
   float* enc_q = ws.take<float>((size_t)nq * Lq * st.Hq);
-  float* pre_d = ws.take<float>(tc_d ? 0 : lstm_workspace_floats(st.enc_d, pc, Ld));
+  float* pre_d = ws.take<float>(rt_d ? rnn_tc_workspace_floats(st.rt_d, pc, Ld) : tc_d ? 0 : lstm_workspace_floats(st.enc_d, pc, Ld));
   float* enc_d = ws.take<float>((size_t)pc * Ld * st.Hd);
   float* cq = ws.take<float>((size_t)nq * Lq * st.C);
   float* cd = ws.take<float>((size_t)pc * Ld * st.C);
@@ -345,7 +353,10 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
     CAIR_CUDA(cudaStreamWaitEvent(st.side, st.ev_fork, 0));
   }
   // ---- query side: embedding + projection (folded table) -> BiLSTM (:77-94) -> channel projection (:99) ----
-  if (tc_q)
+  if (rt_q)
+    CAIR_TRY(rnn_tc_run(st.rt_q, gemm_gather(st.folded, st.V, st.F, qs, 1, 1, 1, err), qlen + qb, (int)nq, Lq, enc_q, nullptr,
+                        nullptr, pre_q, err, sq, st.side ? nullptr : "query_recurrence", st.folded_img));
+  else if (tc_q)
     CAIR_TRY(lstm_tc_run(st.tc_q, st.enc_q.bias, gemm_gather(st.folded, st.V, st.F, qs, 1, 1, 1, err), qlen + qb, (int)nq,
                          Lq, enc_q, nullptr, nullptr, err, sq, st.side ? nullptr : "query_recurrence", st.folded_img));
   else
@@ -358,7 +369,10 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
   if (use_tc) CAIR_TRY(mt_tc_build_t(st.pack, cq, timg, Lq, nq, sq));
   if (st.side) CAIR_CUDA(cudaEventRecord(st.ev_join, st.side));
   // ---- document side ----
-  if (tc_d)
+  if (rt_d)
+    CAIR_TRY(rnn_tc_run(st.rt_d, gemm_gather(st.folded, st.V, st.F, ds, 1, 1, 1, err), dlen + pb, (int)pc, Ld, enc_d, nullptr,
+                        nullptr, pre_d, err, s, "doc_recurrence", st.folded_img, ph.doc_min_spc));
+  else if (tc_d)
     CAIR_TRY(lstm_tc_run(st.tc_d, st.enc_d.bias, gemm_gather(st.folded, st.V, st.F, ds, 1, 1, 1, err), dlen + pb, (int)pc,
                          Ld, enc_d, nullptr, nullptr, err, s, "doc_recurrence", st.folded_img, ph.doc_min_spc));
   else

@@ -27,6 +27,9 @@ PROTOTYPES = {
     'cair_embed_gather': (i32, [vp, i32, i32, vp, i64, vp, vp]),
     'cair_lstm_forward': (i32, [vp, vp, i32, i32, i32, i32, C.POINTER(_abi.LstmDir), C.POINTER(_abi.LstmDir),
                                 vp, vp, vp, vp]),
+    'cair_rnn_forward': (i32, [i32, vp, vp, i32, i32, i32, i32, C.POINTER(_abi.LstmDir), C.POINTER(_abi.LstmDir),
+                               vp, vp, vp, vp]),
+    'cair_set_rnn_impl': (i32, [i32]),
     'cair_umma_selftest': (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
     'cair_umma_bench': (i32, [i32, i32, i32, i32, vp, vp]),
     'cair_esm_create': (i32, [C.POINTER(_abi.EsmWeights), i32, C.POINTER(vp)]),

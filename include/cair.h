@@ -122,6 +122,18 @@ CAIR_API int32_t cair_lstm_forward(const float* x, const int64_t* len, int32_t n
                           int32_t h, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, float* out,
                           float* h_n, float* c_n, void* stream);
 
+/* Same for either cell type (rnn_type = CAIR_RNN_LSTM | CAIR_RNN_GRU; GRU weights [3h,*], gate rows r,z,n, and
+ * n = tanh(W_in x + b_in + r * (W_hn h + b_hn)); c_n is not written for GRU).
+ * Replaces getattr(nn, rnn_type) at neuroir/encoders/rnn_encoder.py:45-53 (called :100-102). */
+CAIR_API int32_t cair_rnn_forward(int32_t rnn_type, const float* x, const int64_t* len, int32_t n, int32_t L,
+                          int32_t in, int32_t h, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, float* out,
+                          float* h_n, float* c_n, void* stream);
+
+/* Process-wide recurrence engine (A/B runs and on-device cross-checks): 2 = cluster-split tcgen05 kernel
+ * (default; LSTM and GRU, h <= 128 per direction, any input size), 1 = round-1 tcgen05 kernel (LSTM, in < 48,
+ * h <= 64), 0 = fp32 CUDA-core kernels.  Shapes an engine does not cover fall through to the next one. */
+CAIR_API int32_t cair_set_rnn_impl(int32_t impl);
+
 /* On-device self test of the tcgen05 operand/descriptor conventions (csrc/umma.cuh):
  * D[m][n] = sum_k A[m+shift][k] * B[n][k] for m < 128; A [(128+shift),K], B [N,K], D [128,N] fp32 device
  * pointers; split=0: plain bf16 operands, split=1: bf16x3 split precision (~fp32 accuracy). */

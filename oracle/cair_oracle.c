@@ -95,6 +95,15 @@ ORA_API int cair_oracle_lstm(const float* x, const int64_t* len, int n, int L, i
   return oracle_rnn(CAIR_RNN_LSTM, x, len, n, L, in, h, fwd, rev, out, h_n, c_n);
 }
 
+/* Same with the cell type as an argument (getattr(nn, rnn_type), encoders/rnn_encoder.py:45-53); c_n is left
+ * untouched for GRU. */
+ORA_API int cair_oracle_rnn(int rnn_type, const float* x, const int64_t* len, int n, int L, int in, int h,
+                            const cair_lstm_dir* fwd, const cair_lstm_dir* rev, float* out,
+                            float* h_n, float* c_n) {
+  if (rnn_type != CAIR_RNN_LSTM && rnn_type != CAIR_RNN_GRU) return CAIR_ERR_UNSUPPORTED;
+  return oracle_rnn(rnn_type, x, len, n, L, in, h, fwd, rev, out, h_n, rnn_type == CAIR_RNN_GRU ? NULL : c_n);
+}
+
 static int oracle_rnn(int rnn_type, const float* x, const int64_t* len, int n, int L, int in, int h,
                       const cair_lstm_dir* fwd, const cair_lstm_dir* rev, float* out, float* h_n, float* c_n) {
   int dirs = rev ? 2 : 1;

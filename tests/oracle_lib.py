@@ -118,8 +118,8 @@ def run_cars(cfg, sd, q, qlen, d, dlen, label):
     return out
 
 
-def run_lstm(x, lens, fwd, rev, h):
-    """fwd/rev: dict(w_ih,w_hh,b_ih,b_hh) of float32 arrays (rev may be None)."""
+def run_lstm(x, lens, fwd, rev, h, rnn_type=0):
+    """fwd/rev: dict(w_ih,w_hh,b_ih,b_hh) of float32 arrays (rev may be None); rnn_type 0 = LSTM, 1 = GRU."""
     L = lib()
     n, T, inp = x.shape
     x = np.ascontiguousarray(x, np.float32)
@@ -134,8 +134,8 @@ def run_lstm(x, lens, fwd, rev, h):
     out = np.zeros((n, T, dirs * h), np.float32)
     hn = np.zeros((dirs, n, h), np.float32)
     cn = np.zeros((dirs, n, h), np.float32)
-    _check(L.cair_oracle_lstm(_f32(x), lp, n, T, inp, h, C.byref(f), C.byref(r) if r is not None else None,
-                              _f32(out), _f32(hn), _f32(cn)), 'lstm')
+    _check(L.cair_oracle_rnn(rnn_type, _f32(x), lp, n, T, inp, h, C.byref(f), C.byref(r) if r is not None else None,
+                             _f32(out), _f32(hn), _f32(cn)), 'rnn')
     del keep
     return out, hn, cn
 

@@ -446,15 +446,34 @@ def test_cars_cfg4_architecture_vs_oracle(gemm_engine):
     assert _max_rel(s, ref['scores']) < TOL
 
 
+@pytest.fixture(params=['cluster', 'r1', 'fp32'])
+def rnn_engine(request):
+    """Recurrence engine under test: the cluster-split tcgen05 kernel (default), the round-1 tcgen05 kernel, fp32 kernels.
+    Shapes an engine does not cover fall through to the next one (cair_set_rnn_impl)."""
+    L = lib.load()
+    lib.check(L.cair_set_rnn_impl({'fp32': 0, 'r1': 1, 'cluster': 2}[request.param]))
+    yield request.param
+    lib.check(L.cair_set_rnn_impl(2))
+
+
+@pytest.mark.parametrize('rnn', ['LSTM', 'GRU'])
 @pytest.mark.parametrize('n,L,inp,h', [
-    (37, 23, 40, 64),      # tcgen05 recurrence (in < 48, h <= 64), 16 sequences per CTA
-    (5, 9, 17, 24),        # tcgen05, one row tile, 8 sequences per CTA, odd sizes
-    (300, 12, 40, 64),     # tcgen05, 32 sequences per CTA (more than one wave otherwise)
-    (21, 15, 96, 96),      # fp32 recurrence, W_hh in shared memory
-    (37, 11, 300, 128),    # fp32 recurrence split over 2-CTA clusters (DSMEM h exchange), tensor-core pre-gate GEMM
-    (32, 7, 256, 512),     # stepwise path: one GEMM + cell kernel per step (CARS session encoders)
+    (37, 23, 40, 64),      # cfg2 document encoder shape: 2-CTA cluster, fused x part
+    (5, 9, 17, 24),        # one CTA, odd sizes
+    (300, 12, 40, 64),     # several clusters
+    (61, 17, 40, 70),      # reference stock Match-Tensor (nhid_doc 140): 3-CTA cluster, partly filled last block
+    (33, 20, 40, 15),      # reference stock query encoder (nhid_query 30)
+    (21, 15, 96, 96),      # pre-gate mode (in >= 48), 3-CTA cluster
+    (37, 11, 300, 128),    # CARS document encoder: 4-CTA cluster, tensor-core pre-gate GEMM
+    (150, 9, 300, 128),    # more than 128 sequences per direction: several clusters, 8 cells per thread
+    (32, 7, 256, 512),     # h > 128: stepwise fp32 path (CARS session encoders)
 ])
-def test_lstm_entry_point_vs_oracle(n, L, inp, h):
+def test_lstm_entry_point_vs_oracle(n, L, inp, h, rnn, rnn_engine):
+    if rnn == 'GRU' and h > 128:
+        pytest.skip('GRU beyond h = 128 is not used by any model')
+    if rnn_engine != 'cluster' and (n, L) not in ((37, 23), (21, 15), (37, 11), (32, 7)):
+        pytest.skip('fallback engines: one shape per code path is enough')
+    G = 4 if rnn == 'LSTM' else 3
     rng = np.random.default_rng(9)
     x = rng.standard_normal((n, L, inp)).astype(np.float32)
     lens = rng.integers(1, L + 1, n).astype(np.int64)
@@ -462,11 +481,12 @@ def test_lstm_entry_point_vs_oracle(n, L, inp, h):
 
     def mk():
         k = 1.0 / np.sqrt(h)
-        return dict(w_ih=rng.uniform(-k, k, (4 * h, inp)).astype(np.float32),
-                    w_hh=rng.uniform(-k, k, (4 * h, h)).astype(np.float32),
-                    b_ih=rng.uniform(-k, k, 4 * h).astype(np.float32), b_hh=rng.uniform(-k, k, 4 * h).astype(np.float32))
+        return dict(w_ih=rng.uniform(-k, k, (G * h, inp)).astype(np.float32),
+                    w_hh=rng.uniform(-k, k, (G * h, h)).astype(np.float32),
+                    b_ih=rng.uniform(-k, k, G * h).astype(np.float32), b_hh=rng.uniform(-k, k, G * h).astype(np.float32))
     fwd, rev = mk(), mk()
-    ref, hn, cn = ol.run_lstm(x, lens, fwd, rev, h)
+    rt = 0 if rnn == 'LSTM' else 1
+    ref, hn, cn = ol.run_lstm(x, lens, fwd, rev, h, rt)
     import ctypes as C
     from context_attentive_ir_b200 import _abi
     t = {k: torch.from_numpy(v).to(DEV) for k, v in dict(x=x, lens=lens).items()}
@@ -479,9 +499,31 @@ def test_lstm_entry_point_vs_oracle(n, L, inp, h):
     hn_d = torch.zeros(2, n, h, device=DEV)
     cn_d = torch.zeros(2, n, h, device=DEV)
     f, r = sd(wf), sd(wr)
-    lib.check(lib.load().cair_lstm_forward(t['x'].data_ptr(), t['lens'].data_ptr(), n, L, inp, h, C.byref(f), C.byref(r),
-                                           out.data_ptr(), hn_d.data_ptr(), cn_d.data_ptr(),
-                                           torch.cuda.current_stream().cuda_stream))
+    lib.check(lib.load().cair_rnn_forward(rt, t['x'].data_ptr(), t['lens'].data_ptr(), n, L, inp, h, C.byref(f), C.byref(r),
+                                          out.data_ptr(), hn_d.data_ptr(), cn_d.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream))
     assert np.abs(out.cpu().numpy() - ref).max() < 1e-4
     assert np.abs(hn_d.cpu().numpy() - hn).max() < 1e-4
-    assert np.abs(cn_d.cpu().numpy() - cn).max() < 1e-4
+    if rnn == 'LSTM':
+        assert np.abs(cn_d.cpu().numpy() - cn).max() < 1e-4
+
+
+def test_rnn_unidirectional_and_single_sequence():
+    """rev = NULL (one direction) and n = 1: the smallest launch of the cluster-split kernel."""
+    import ctypes as C
+    from context_attentive_ir_b200 import _abi
+    rng = np.random.default_rng(4)
+    for n, L, inp, h in ((1, 5, 40, 64), (9, 6, 300, 128)):
+        x = rng.standard_normal((n, L, inp)).astype(np.float32)
+        lens = np.full(n, L, np.int64)
+        k = 1.0 / np.sqrt(h)
+        fwd = dict(w_ih=rng.uniform(-k, k, (4 * h, inp)).astype(np.float32), w_hh=rng.uniform(-k, k, (4 * h, h)).astype(np.float32),
+                   b_ih=rng.uniform(-k, k, 4 * h).astype(np.float32), b_hh=rng.uniform(-k, k, 4 * h).astype(np.float32))
+        ref, hn, cn = ol.run_lstm(x, lens, fwd, None, h)
+        w = {kk: torch.from_numpy(v).to(DEV) for kk, v in fwd.items()}
+        f = _abi.LstmDir(*[C.cast(w[kk].data_ptr(), _abi.f32p) for kk in ('w_ih', 'w_hh', 'b_ih', 'b_hh')])
+        xd, ld = torch.from_numpy(x).to(DEV), torch.from_numpy(lens).to(DEV)
+        out = torch.full((n, L, h), float('nan'), device=DEV)
+        lib.check(lib.load().cair_rnn_forward(0, xd.data_ptr(), ld.data_ptr(), n, L, inp, h, C.byref(f), None, out.data_ptr(),
+                                              None, None, torch.cuda.current_stream().cuda_stream))
+        assert np.abs(out.cpu().numpy() - ref).max() < 1e-4
