@@ -208,7 +208,8 @@ int32_t cair_rnn_forward(int32_t rnn_type, const float* x, const int64_t* len, i
   int* err = nullptr;
   // engine: cluster-split tcgen05 kernel when the shape fits (h <= 128), else / on request the round-1 tcgen05 kernel
   // (LSTM, in < 48, h <= 64) or the fp32 kernels
-  const bool rt = g_rnn_impl == RNN_IMPL_CLUSTER && rnn_tc_supported(in, h);
+  const bool rt = rnn_tc_supported(in, h) &&
+                  (g_rnn_impl == RNN_IMPL_CLUSTER || (g_rnn_impl == RNN_IMPL_AUTO && !rnn_prefers_r1(rnn_type, in, h)));
   const bool tc = !rt && g_rnn_impl != RNN_IMPL_FP32 && rnn_type == CAIR_RNN_LSTM && lstm_tc_supported(in, h);
   RnnTcPack rp;
   LstmTcPack tp;
@@ -243,7 +244,7 @@ int32_t cair_lstm_forward(const float* x, const int64_t* len, int32_t n, int32_t
 
 int32_t cair_set_rnn_impl(int32_t impl) {
   if (impl < RNN_IMPL_FP32 || impl > RNN_IMPL_CLUSTER)
-    return fail(CAIR_ERR_BAD_ARG, "set_rnn_impl: 0 (fp32 CUDA cores), 1 (round-1 tcgen05 kernel) or 2 (cluster-split tcgen05 kernel)");
+    return fail(CAIR_ERR_BAD_ARG, "set_rnn_impl: 0 (fp32 CUDA cores), 1 (single-CTA tcgen05 kernel), 2 (auto) or 3 (cluster-split tcgen05 kernel)");
   g_rnn_impl = impl;
   return CAIR_OK;
 }
@@ -758,8 +759,8 @@ int32_t cair_ranker_submit_host(cair_handle* h, const int64_t* q, const int64_t*
   if (prev >= 0) {
     cair_handle::PipeSlot& pp = h->pipe[prev];
     const int64_t pcp = (int64_t)pp.B * pp.N;
-    free_sms = kSMs - ((g_rnn_impl == RNN_IMPL_CLUSTER && h->mt.rt_d.wimg) ? rnn_tc_plan(h->mt.rt_d, (int)nbn, h->pipe_spc).ctas
-                                                                            : lstm_tc_ctas((int)nbn, h->mt.tc_d.dirs, h->pipe_spc));
+    free_sms = kSMs - (mt_doc_uses_cluster_kernel(h->mt) ? rnn_tc_plan(h->mt.rt_d, (int)nbn, h->pipe_spc).ctas
+                                                         : lstm_tc_ctas((int)nbn, h->mt.tc_d.dirs, h->pipe_spc));
     if (free_sms >= 8) c1 = (int64_t)((double)pcp * h->pipe_frac);
     CAIR_CUDA(cudaStreamWaitEvent(L, pp.ev_enc, 0));
     CAIR_TRY(pipe_mark(h, prev, 2, L));
@@ -875,7 +876,13 @@ int32_t cair_cars_forward(cair_handle* h, const int64_t* q, const int64_t* qlen,
   if (probe.off > workspace_bytes || (probe.off > 0 && !workspace))
     return fail(CAIR_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", probe.off, workspace_bytes);
   Arena ws(workspace, workspace_bytes);
-  return cars_forward(h->cars, io, B, S, N, Lq, Ld, session_begin, session_count, ws, h->d_err, (cudaStream_t)stream, false);
+  h->prof.reset();
+  g_prof = &h->prof;
+  prof_mark("begin", (cudaStream_t)stream);
+  int32_t rc = cars_forward(h->cars, io, B, S, N, Lq, Ld, session_begin, session_count, ws, h->d_err, (cudaStream_t)stream, false);
+  prof_mark("end", (cudaStream_t)stream);
+  g_prof = nullptr;
+  return rc;
 }
 
 }  // extern "C"

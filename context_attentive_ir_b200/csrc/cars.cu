@@ -367,7 +367,7 @@ static int32_t encode_pool(const CarsState& st, const LstmPack& lp, const RnnTcP
                            const int64_t* len, int64_t n, int L, float* pre, float* enc, float* hid, float* pooled,
                            int* err, cudaStream_t s, const char* rec_name) {
   const int H = ap.H;
-  if (g_rnn_impl == RNN_IMPL_CLUSTER && rt.wimg)   // tcgen05 recurrence (pre-gates from the gathered tcgen05 GEMM)
+  if (g_rnn_impl >= RNN_IMPL_AUTO && rt.wimg)   // tcgen05 recurrence (pre-gates from the gathered tcgen05 GEMM)
     CAIR_TRY(rnn_tc_run(rt, gemm_gather(st.table, st.V, st.E, ids, 1, 1, 1, err), len, (int)n, L, enc, nullptr, nullptr, pre,
                         err, s, rec_name));
   else
@@ -415,8 +415,8 @@ int32_t cars_forward(const CarsState& st, const CarsIO& io, int B, int S, int N,
   CAIR_TRY(encode_pool(st, st.enc_q, st.rt_q, st.q_attn, io.q + r0 * Lq, io.qlen + r0, nrows, Lq, pre_q, enc_q, hid_q, pq, err, s, "query_recurrence"));
   prof_mark("doc_pregates", s);
   CAIR_TRY(encode_pool(st, st.enc_d, st.rt_d, st.d_attn, io.d + r0 * N * Ld, io.dlen + r0 * N, ndocs, Ld, pre_d, enc_d, hid_d, pd, err, s, "doc_recurrence"));
-  prof_mark("session", s);
   // 2. click vectors
+  prof_mark("clicks", s);
   CAIR_CUDA(cudaMemsetAsync(mwidth, 0, sizeof(int), s));
   CAIR_LAUNCH(click_width_kernel, (B * S + 255) / 256, 256, 0, s, io.labels, B * S, N, mwidth);
   CAIR_TRY(gemm_auto(gemm_dense(pd, Hd), st.click_attn.w0, st.click_attn.w0_tc, st.click_attn.b0, hid_c, Hd, ndocs, Hd, Hd,
@@ -424,10 +424,12 @@ int32_t cars_forward(const CarsState& st, const CarsIO& io, int B, int S, int N,
   CAIR_LAUNCH(rowdot_kernel, (unsigned)((ndocs + 7) / 8), 256, 0, s, hid_c, ndocs, Hd, st.click_attn.w3, st.click_attn.b3, att_c);
   CAIR_LAUNCH(clicks_kernel, (unsigned)nrows, 128, (size_t)N * 8, s, pd, att_c, io.labels, N, Hd, mwidth, r0, clk);
   // 3. session LSTMs over the pooled queries / click vectors (zero initial state, S steps each)
+  prof_mark("session_encoders", s);
   CAIR_LAUNCH(fill_len_kernel, (sc + 255) / 256, 256, 0, s, slen, sc, (int64_t)S);
   CAIR_TRY(lstm_run(st.sess_q, gemm_dense(pq, Hq), slen, sc, S, Qs, nullptr, nullptr, pre_sq, err, s));
   CAIR_TRY(lstm_run(st.sess_d, gemm_dense(clk, Hd), slen, sc, S, Ds, nullptr, nullptr, pre_sd, err, s));
   // 4. session attention + rank head
+  prof_mark("rank_head", s);
   {
     const int Hs = Hsq + Hsd;
     const int Hu = Hsmax > Hd ? Hsmax : Hd;

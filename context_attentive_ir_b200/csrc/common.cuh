@@ -290,8 +290,12 @@ struct RnnTcPack {
 struct RnnTcPlan {
   int spc = 0, npad = 0, groups = 0, ctas = 0, nb = 0;
 };
-enum { RNN_IMPL_FP32 = 0, RNN_IMPL_TC_R1 = 1, RNN_IMPL_CLUSTER = 2 };
-extern int g_rnn_impl;   // recurrence engine: 2 (default) cluster-split tcgen05 kernel, 1 round-1 tcgen05 kernel, 0 fp32 CUDA cores
+enum { RNN_IMPL_FP32 = 0, RNN_IMPL_TC_R1 = 1, RNN_IMPL_AUTO = 2, RNN_IMPL_CLUSTER = 3 };
+// recurrence engine: 2 (default) = per shape the faster tcgen05 kernel (single-CTA lstm_tc.cu for LSTM, in < 48,
+// 32 < h <= 64; cluster-split rnn_tc.cu otherwise), 3 = rnn_tc.cu wherever it applies, 1 = lstm_tc.cu where it applies,
+// 0 = fp32 CUDA cores
+extern int g_rnn_impl;
+inline bool rnn_prefers_r1(int rnn_type, int in, int h) { return rnn_type == CAIR_RNN_LSTM && in < 48 && h > 32 && h <= 64; }
 extern long long* g_rnn_dbg;
 extern int g_rnn_spc_min, g_rnn_spc_force;
 bool rnn_tc_supported(int in, int h);

@@ -94,6 +94,7 @@ struct MtPhase {
                          // slightly slower encoder CTAs leave more SMs to the previous batch's interaction)
 };
 bool mt_can_pipeline(const MtState& st, int Lq, int Ld);
+bool mt_doc_uses_cluster_kernel(const MtState& st);
 int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, const int64_t* d, const int64_t* dlen,
                    int B, int N, int Lq, int Ld, int64_t pb, int64_t pc, float* scores, Arena& ws, int* err,
                    cudaStream_t s, bool dry, MtPhase ph = MtPhase());

@@ -300,6 +300,14 @@ int32_t mt_create_state(Owned& own, const cair_mt_weights& w, MtState* st, cudaS
   return CAIR_OK;
 }
 
+// engine of one encoder under the process-wide g_rnn_impl switch (see common.cuh)
+static bool mt_uses_cluster_kernel(const RnnTcPack& rt, const LstmTcPack& r1) {
+  if (!rt.wimg) return false;
+  if (g_rnn_impl == RNN_IMPL_CLUSTER) return true;
+  return g_rnn_impl == RNN_IMPL_AUTO && !(r1.wimg && rnn_prefers_r1(rt.gru ? CAIR_RNN_GRU : CAIR_RNN_LSTM, rt.in, rt.h));
+}
+bool mt_doc_uses_cluster_kernel(const MtState& st) { return st.impl != MT_IMPL_FP32 && mt_uses_cluster_kernel(st.rt_d, st.tc_d); }
+
 int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, const int64_t* d, const int64_t* dlen,
                    int B, int N, int Lq, int Ld, int64_t pb, int64_t pc, float* scores, Arena& ws, int* err,
                    cudaStream_t s, bool dry, MtPhase ph) {
@@ -307,8 +315,8 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
   // queries touched by the pair slice [pb, pb+pc)
   const int64_t qb = pc > 0 ? pb / N : 0;
   const int64_t nq = pc > 0 ? (pb + pc - 1) / N - qb + 1 : 0;
-  const bool rt_q = st.impl != MT_IMPL_FP32 && g_rnn_impl == RNN_IMPL_CLUSTER && st.rt_q.wimg != nullptr;
-  const bool rt_d = st.impl != MT_IMPL_FP32 && g_rnn_impl == RNN_IMPL_CLUSTER && st.rt_d.wimg != nullptr;
+  const bool rt_q = st.impl != MT_IMPL_FP32 && mt_uses_cluster_kernel(st.rt_q, st.tc_q);
+  const bool rt_d = st.impl != MT_IMPL_FP32 && mt_uses_cluster_kernel(st.rt_d, st.tc_d);
   const bool tc_q = !rt_q && st.impl != MT_IMPL_FP32 && g_rnn_impl != RNN_IMPL_FP32 && st.tc_q.wimg != nullptr;
   const bool tc_d = !rt_d && st.impl != MT_IMPL_FP32 && g_rnn_impl != RNN_IMPL_FP32 && st.tc_d.wimg != nullptr;
   float* pre_q = ws.take<float>(rt_q ? rnn_tc_workspace_floats(st.rt_q, nq, Lq) : tc_q ? 0 : lstm_workspace_floats(st.enc_q, nq, Lq));

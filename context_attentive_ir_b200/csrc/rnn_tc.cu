@@ -10,10 +10,19 @@
 // bf16x3 split precision (hi*hi + lo*hi + hi*lo) so the 200-step recurrence stays at fp32 accuracy.
 // Compared with one CTA holding all 4h gate rows (round 1: 2 row tiles, 24 recurrent MMAs per step at h = 64), every SM
 // issues only the MMAs of its own 128 rows (6 CS per step: 12 at h = 64) and runs only its own 32 units' cell updates
-// (the MUFU-bound part); the price is the exchange of h: every CTA writes the bf16 hi/lo operand rows of its 32
-// units into the next-step operand buffer of EVERY CTA of the cluster (st.shared::cluster, 8-byte units assembled by
-// two warp shuffles) and signals one mbarrier per (destination, source block); the MMA warp consumes the blocks in
-// arrival order (own block first).
+// (the MUFU-bound part); the price is the exchange of h: every epilogue warp writes the bf16 hi/lo operand rows of its
+// cells (8-byte units assembled by two warp shuffles, 256 contiguous bytes per warp and column block) into the
+// next-step operand buffer of its OWN CTA and forwards that chunk to every other CTA of the cluster with one bulk
+// copy shared -> distributed shared memory (cp.async.bulk.shared::cluster.shared::cta, SASS UBLKCP.S.S) whose bytes
+// are counted on an mbarrier of the destination (complete_tx); the MMA warp consumes the blocks in arrival order (own
+// block first).  Measured alternatives (profiles/r02_rnn_exchange_modes.txt): st.async per 8-byte unit (1280
+// transactions per step: the block arrives ~1000 cycles late), remote st.shared::cluster + mbarrier.arrive.release.cluster
+// (the cluster-scope release alone costs ~1500 cycles per step), one bulk copy per TMEM quarter or one per CTA and
+// destination issued by the MMA thread (no faster: the transfer, not the issue, is the cost; chunks sent as each warp
+// finishes overlap it with the other warps' cell updates).
+// The hop costs 400-850 cycles per step (pair dependent), which is why at h = 64 / 1280 x 2 sequences (cfg2: a pure
+// latency chain of 200 steps) the single-CTA round-1 kernel (lstm_tc.cu) is still faster and stays the AUTO choice
+// there; this kernel carries GRU, h > 64 (stock Match-Tensor 70 / direction, CARS 128) and in >= 48.
 // GRU uses the same tile: per unit the four rows are r, z, n_x (input part of the candidate, W_in x + b_in) and
 // n_h (hidden part, W_hn h + b_hn), so  n = tanh(n_x + r * n_h)  needs no second GEMM.
 // Two input modes:
@@ -24,9 +33,9 @@
 //     are permuted to [dir][unit][4] and pre-scaled, so a cell reads its four pre-gates as ONE 16-byte load, prefetched a
 //     step ahead.
 // Every weight row is pre-scaled by -log2(e) (-2 log2(e) for the tanh rows): accumulators are exp2 arguments.
-// Warp roles: warps 0-15 epilogue (TMEM quarter = warp % 4 -> 8 units, column blocks of 8 sequences round-robin over
-// warp / 4; all four gates of a unit land in one thread via tcgen05.ld.16x256b on permuted rows), warp 17 MMA issuer,
-// warps 18, 19, 22, 23 gather (FUSED).
+// Warp roles: warps 0-19 epilogue (TMEM quarter = warp % 4 -> 8 units, column blocks of 8 sequences round-robin over
+// warp / 4; all four gates of a unit land in one thread via tcgen05.ld.16x256b on permuted rows), warp 20 MMA issuer,
+// warps 21-23 gather (FUSED).
 #include "models.cuh"
 #include "umma.cuh"
 
@@ -37,18 +46,18 @@ using namespace umma;
 constexpr int RT_XP = 48;              // K slots of the fused x part (in + bias column <= 48)
 constexpr int RT_UPC = 32;             // hidden units per CTA
 constexpr int RT_MAXCS = 4;            // cluster size limit: h <= 128 per direction
-constexpr int RT_EPI_WARPS = 16;
-constexpr int RT_XS = 4;               // x-operand ring slots = gather warps
-constexpr int RT_MMA_WARP = 17;
+constexpr int RT_EPI_WARPS = 20;       // 5 per SM sub-partition: at 33..40 sequences per cluster every warp owns exactly one column block
+constexpr int RT_CW = RT_EPI_WARPS / 4; // column-block lanes
+constexpr int RT_XS = 3;               // x-operand ring slots = gather warps
+constexpr int RT_MMA_WARP = 20;
 constexpr int RT_THREADS_FUSED = 24 * 32;
-constexpr int RT_THREADS_PRE = 20 * 32;
+constexpr int RT_THREADS_PRE = 21 * 32;
 constexpr int RT_MAXN = 128;           // sequences per cluster (MMA N)
 constexpr uint32_t RT_APLANE = 128 * 16;
 constexpr float RT_LOG2E = 1.4426950408889634f;
 
-__device__ __forceinline__ int rt_gather_slot(int warp) {
-  return warp == 18 ? 0 : warp == 19 ? 1 : warp == 22 ? 2 : warp == 23 ? 3 : -1;
-}
+// warp 20 (sub-partition 0) issues the MMAs; the gather warps 21, 22, 23 sit on the other three sub-partitions
+__device__ __forceinline__ int rt_gather_slot(int warp) { return warp >= 21 && warp < 21 + RT_XS ? warp - 21 : -1; }
 
 bool rnn_tc_supported(int in, int h) { return in >= 1 && h >= 1 && h <= RT_UPC * RT_MAXCS; }
 
@@ -195,11 +204,13 @@ __device__ __forceinline__ uint32_t rt_mapa(uint32_t saddr, uint32_t cta) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
   return r;
 }
-__device__ __forceinline__ void rt_st_cluster_v2(uint32_t raddr, uint32_t a, uint32_t b) {
-  asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(raddr), "r"(a), "r"(b) : "memory");
-}
-__device__ __forceinline__ void rt_arrive_cluster(uint32_t raddr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+// Bulk copy own shared memory -> shared memory of another CTA of the cluster (async proxy, SASS UBLKCP); the bytes are
+// counted on an mbarrier of the DESTINATION CTA (complete_tx): data and signal travel together, the producer never
+// waits for the round trip and needs no cluster-scope release fence.
+__device__ __forceinline__ void rt_bulk_s2c(uint32_t rdst, uint32_t lsrc, uint32_t bytes, uint32_t rbar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rdst),
+               "r"(lsrc), "r"(bytes), "r"(rbar)
+               : "memory");
 }
 __device__ __forceinline__ void rt_arrive_local(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -210,20 +221,6 @@ __device__ __forceinline__ void rt_wait(uint64_t* bar, uint32_t parity) {
   uint32_t n = 0;
   while (!mbar_try_wait(bar, parity))
     if (++n > RT_SPIN_LIMIT) __trap();
-}
-__device__ __forceinline__ void rt_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0, n = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (++n > RT_SPIN_LIMIT) __trap();
-  }
 }
 __device__ __forceinline__ void rt_wait_relaxed(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0, n = 0;
@@ -238,7 +235,6 @@ __device__ __forceinline__ void rt_wait_relaxed(uint64_t* bar, uint32_t parity) 
     if (!ok && ++n > (1u << 22)) __trap();
   }
 }
-__device__ __forceinline__ void rt_fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // tcgen05.ld.16x256b.x1: 16 TMEM lanes x 8 columns per warp; thread (t0 = lane % 4, t1 = lane / 4) receives
 // r0,r1 = (lane t1, cols 2 t0, 2 t0 + 1), r2,r3 = (lane t1 + 8, same cols).
 __device__ __forceinline__ void rt_tmem_ld_16x256b(uint32_t taddr, float* v) {
@@ -283,7 +279,7 @@ __device__ __forceinline__ float rt_gru_cell(float tr, float tz, float tnx, floa
 }
 
 long long* g_rnn_dbg = nullptr;
-int g_rnn_impl = RNN_IMPL_CLUSTER;
+int g_rnn_impl = RNN_IMPL_AUTO;
 #define RT_T0() long long t0_ = a.dbg ? clock64() : 0
 #define RT_ACC(slot) do { if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) a.dbg[slot] += clock64() - t0_; } while (0)
 
@@ -329,7 +325,8 @@ __global__ void __launch_bounds__(FUSED ? RT_THREADS_FUSED : RT_THREADS_PRE, 1) 
     mbar_init(&bar_w, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_acc[i], 1);
-      for (int b = 0; b < RT_MAXCS; ++b) mbar_init(&bar_h[i][b], RT_EPI_WARPS);   // the 16 epilogue warps of CTA b
+      // own block: the 16 epilogue warps arrive; blocks of the other CTAs: armed by the MMA thread, completed by their bytes
+      for (int b = 0; b < RT_MAXCS; ++b) mbar_init(&bar_h[i][b], b == rank ? RT_EPI_WARPS : 1);
     }
     for (int i = 0; i < RT_XS; ++i) {
       mbar_init(&x_full[i], 1);
@@ -458,9 +455,11 @@ __global__ void __launch_bounds__(FUSED ? RT_THREADS_FUSED : RT_THREADS_PRE, 1) 
     const uint32_t issue = elect_one();
     const uint32_t idesc = idesc_bf16_f32(128, npad);
     const uint64_t wd0 = smem_desc(smem_u32(w_img), RT_APLANE, 128);
-    const uint64_t hd0 = smem_desc(smem_u32(h_img), bplane, 128);
+    // h operand: [blk][plane][8-row group][hi|lo][8 rows][16 B] - K chunks 2 bplane apart, 8-row groups 256 B apart
+    const uint64_t hd0 = smem_desc(smem_u32(h_img), 2 * bplane, 256);
+    const uint32_t hhi_h = (uint32_t)(hd0 >> 32);
     const uint64_t xd0 = smem_desc(smem_u32(x_img), bplane, 128);
-    const uint32_t whi = (uint32_t)(wd0 >> 32), hhi = (uint32_t)(hd0 >> 32);
+    const uint32_t whi = (uint32_t)(wd0 >> 32), hhi = (uint32_t)(xd0 >> 32);
     const uint32_t wlo0 = (uint32_t)wd0, hlo0 = (uint32_t)hd0, xlo0 = (uint32_t)xd0;
     const uint32_t whalf = ((uint32_t)a.planes * RT_APLANE) >> 4;   // hi -> lo weight image
     const int xpl = FUSED ? RT_XP / 8 : 0;
@@ -484,6 +483,12 @@ __global__ void __launch_bounds__(FUSED ? RT_THREADS_FUSED : RT_THREADS_PRE, 1) 
         }
       }
     };
+    long long ts_m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // bytes one source CTA delivers per step: (column blocks in use) x 4 quarter warps x 256 B
+    const uint32_t blk_bytes = (uint32_t)((spc + 7) / 8) * 1024u;
+    if (maxlen > 0 && lane == 0)   // h_0 = 0 is already in operand buffer 0: complete the first phase of the remote blocks
+      for (int b = 0; b < cs; ++b)
+        if (b != rank) rt_arrive_local(&bar_h[0][b]);
     if (FUSED && maxlen > 0) {
       { RT_T0(); rt_wait(&x_full[0], 0); RT_ACC(0); }
       tc_fence_after();
@@ -494,23 +499,29 @@ __global__ void __launch_bounds__(FUSED ? RT_THREADS_FUSED : RT_THREADS_PRE, 1) 
       const uint32_t ph = (uint32_t)(step >> 1) & 1;
       const uint32_t tacc = tbase + (uint32_t)par * npad;
       uint32_t acc = FUSED ? 1u : 0u;
+      if (step + 1 < maxlen && lane == 0)   // arm the barriers of the NEXT step's h blocks (their bytes may already be landing)
+        for (int b = 0; b < cs; ++b)
+          if (b != rank) mbar_arrive_expect_tx(&bar_h[par ^ 1][b], blk_bytes);
       // h part: the 32-unit blocks of h_{step-1} in arrival order - own block first (its wait also guarantees that this
       // CTA's epilogue has finished reading the accumulator the next x part / PRE-mode MMA overwrites).
+      if (step == 100 || step == 101) ts_m[(step - 100) * 4] = clock64();
       for (int bi = 0; bi < cs; ++bi) {
         int blk = rank + bi;
         blk = blk >= cs ? blk - cs : blk;
-        { RT_T0(); rt_wait_cluster(&bar_h[par][blk], ph); RT_ACC(1); }
+        // own block: generic-proxy stores fenced by the writers; other blocks: async-proxy bulk copies (complete_tx)
+        { RT_T0(); rt_wait(&bar_h[par][blk], ph); RT_ACC(1); }
+        if ((step == 100 || step == 101) && bi < 2) ts_m[(step - 100) * 4 + 1 + bi] = clock64();
         tc_fence_after();
         RT_T0();
         const uint32_t wb = wlo0 + (uint32_t)(xpl + 4 * blk) * (RT_APLANE >> 4);
-        const uint32_t hb = hlo0 + (((uint32_t)par * hpar + (uint32_t)blk * 2 * himg) >> 4);
+        const uint32_t hb = hlo0 + (((uint32_t)par * hpar + (uint32_t)blk * 8 * bplane) >> 4);
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
           const uint32_t wp = wb + (pass == 1 ? whalf : 0);
-          const uint32_t bp = hb + (pass == 2 ? (himg >> 4) : 0);
+          const uint32_t bp = hb + (pass == 2 ? (128u >> 4) : 0);
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
-            mma_bf16_ss_w32(tacc, wp + (uint32_t)(2 * ks) * (RT_APLANE >> 4), whi, bp + (uint32_t)(2 * ks) * (bplane >> 4), hhi,
+            mma_bf16_ss_w32(tacc, wp + (uint32_t)(2 * ks) * (RT_APLANE >> 4), whi, bp + (uint32_t)(2 * ks) * (2 * bplane >> 4), hhi_h,
                             idesc, acc, issue);
             acc = 1;
           }
@@ -518,6 +529,7 @@ __global__ void __launch_bounds__(FUSED ? RT_THREADS_FUSED : RT_THREADS_PRE, 1) 
         RT_ACC(2);
       }
       mma_commit_w(&bar_acc[par], issue);
+      if (step == 100 || step == 101) ts_m[(step - 100) * 4 + 3] = clock64();
       if (FUSED) {
         mma_commit_w(&x_empty[step % RT_XS], issue);
         if (step + 1 < maxlen) {
@@ -528,6 +540,8 @@ __global__ void __launch_bounds__(FUSED ? RT_THREADS_FUSED : RT_THREADS_PRE, 1) 
         }
       }
     }
+    if (a.dbg && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && maxlen > 101)
+      for (int i = 0; i < 8; ++i) a.dbg[16 + i] = ts_m[i];
   } else if (warp < RT_EPI_WARPS) {
     // ===================== epilogue warps =====================
     // warp -> (TMEM lane quarter q = 8 units, column-block lane cw); lane -> (t0 = lane % 4, j = lane / 4):
@@ -549,7 +563,7 @@ __global__ void __launch_bounds__(FUSED ? RT_THREADS_FUSED : RT_THREADS_PRE, 1) 
     for (int k = 0; k < NB; ++k)
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const int sq = 8 * (cw + 4 * k) + 2 * t0i + c;
+        const int sq = 8 * (cw + RT_CW * k) + 2 * t0i + c;
         const int l = sq < RT_MAXN ? slen[sq] : 0;
         lk[2 * k + c] = l;
         cst[2 * k + c] = 0.f, hst[2 * k + c] = 0.f;
@@ -562,7 +576,7 @@ __global__ void __launch_bounds__(FUSED ? RT_THREADS_FUSED : RT_THREADS_PRE, 1) 
         for (int k = 0; k < NB; ++k)
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            const int sq = 8 * (cw + 4 * k) + 2 * t0i + c;
+            const int sq = 8 * (cw + RT_CW * k) + 2 * t0i + c;
             const int l = lk[2 * k + c];
             if (uvalid && step < l) {
               const int t = dir ? l - 1 - step : step;
@@ -572,19 +586,20 @@ __global__ void __launch_bounds__(FUSED ? RT_THREADS_FUSED : RT_THREADS_PRE, 1) 
       }
     };
     // destination windows of the h operand buffer in every CTA of the cluster
-    uint32_t hdst[RT_MAXCS];
-#pragma unroll
-    for (int d = 0; d < RT_MAXCS; ++d) hdst[d] = (cs > 1 && d < cs) ? rt_mapa(smem_u32(h_img), (uint32_t)d) : smem_u32(h_img);
-    // lane d < cs signals CTA d: "block `rank` of the operand buffer of parity p is complete"
-    const uint32_t bdst = rt_mapa(smem_u32(&bar_h[0][rank]), (uint32_t)(lane < cs ? lane : 0));
-    // this lane's 8-byte unit after the butterfly: cell b0, hi (b1 = 0) | lo (b1 = 1), units 4 b2 .. 4 b2 + 3 of plane q
-    const uint32_t hoff_lane = (uint32_t)rank * 2 * himg + (uint32_t)b1 * himg + (uint32_t)q * bplane + (uint32_t)b2 * 8;
+    // lane i < cs - 1 forwards this warp's chunks to CTA (rank + 1 + i) % cs: that CTA's operand buffer and its
+    // completion barrier of block `rank` (parity 0)
+    const int fdst = (rank + 1 + lane) % cs;
+    const uint32_t fwd_h = (cs > 1 && lane < cs - 1) ? rt_mapa(smem_u32(h_img), (uint32_t)fdst) : 0;
+    const uint32_t fwd_b = (cs > 1 && lane < cs - 1) ? rt_mapa(smem_u32(&bar_h[0][rank]), (uint32_t)fdst) : 0;
+    // block chunk (rank, plane q, group blk8) = 256 contiguous bytes: [hi|lo][8 rows][16 B]
+    const uint32_t hoff_warp = (uint32_t)rank * 8 * bplane + (uint32_t)q * 2 * bplane;
+    const uint32_t hoff_lane = (uint32_t)b1 * 128 + (uint32_t)(2 * t0i + b0) * 16 + (uint32_t)b2 * 8;
     const uint32_t tq = tbase + ((uint32_t)(q * 32) << 16);
     if (maxlen > 0) {
-      // h_0 = 0 is already in operand buffer 0 of every CTA
-      if (lane < cs) rt_arrive_cluster(bdst);
+      if (lane == 0) rt_arrive_local(&bar_h[0][rank]);   // h_0 = 0 is already in operand buffer 0
       load_pre(0);
     }
+    long long ts_e[6] = {0, 0, 0, 0, 0, 0};
     for (int step = 0; step < maxlen; ++step) {
       const int par = step & 1;
       float4 pgc[2 * NB];
@@ -594,12 +609,13 @@ __global__ void __launch_bounds__(FUSED ? RT_THREADS_FUSED : RT_THREADS_PRE, 1) 
         if (step + 1 < maxlen) load_pre(step + 1);
       }
       { RT_T0(); rt_wait(&bar_acc[par], (uint32_t)(step >> 1) & 1); if (warp == 0) RT_ACC(3); }
+      if (step == 100) ts_e[0] = clock64();
       tc_fence_after();
       RT_T0();
       float hv[2 * NB];
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
-        const int blk8 = cw + 4 * k;
+        const int blk8 = cw + RT_CW * k;
         hv[2 * k] = 0.f, hv[2 * k + 1] = 0.f;
         if (blk8 * 8 < spc) {   // warp-uniform
           float ga[4], gb[4];   // ga: gate types 0 (cells 0,1) and 1; gb: types 2 and 3
@@ -607,6 +623,8 @@ __global__ void __launch_bounds__(FUSED ? RT_THREADS_FUSED : RT_THREADS_PRE, 1) 
           rt_tmem_ld_16x256b(ta, ga);
           rt_tmem_ld_16x256b(ta + (16u << 16), gb);
           tmem_ld_wait();
+          tc_fence_before();
+          if (step == 100 && k == 0) ts_e[1] = clock64();
           uint32_t w[2];
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -635,20 +653,30 @@ __global__ void __launch_bounds__(FUSED ? RT_THREADS_FUSED : RT_THREADS_PRE, 1) 
           const uint32_t HH = __byte_perm(ulo, uhi, 0x5410), LL = __byte_perm(ulo, uhi, 0x7632);
           const uint32_t rB = __shfl_xor_sync(0xffffffffu, b1 ? HH : LL, 8);
           const uint32_t w0 = b1 ? rB : HH, w1 = b1 ? LL : rB;
-          const uint32_t off = (uint32_t)(par ^ 1) * hpar + hoff_lane + (uint32_t)(blk8 * 8 + 2 * t0i + b0) * 16;
-          if (cs == 1) {
-            *reinterpret_cast<uint2*>(h_img + off) = make_uint2(w0, w1);
-          } else {
-#pragma unroll
-            for (int d = 0; d < RT_MAXCS; ++d)
-              if (d < cs) rt_st_cluster_v2(hdst[d] + off, w0, w1);
-          }
+          const uint32_t off = (uint32_t)(par ^ 1) * hpar + hoff_warp + (uint32_t)blk8 * 256 + hoff_lane;
+          *reinterpret_cast<uint2*>(h_img + off) = make_uint2(w0, w1);
         }
       }
-      tc_fence_before();
-      if (cs == 1) fence_proxy_async(); else rt_fence_proxy_async_all();
+      // hand the new h over: generic-proxy stores -> async proxy (the MMAs of this CTA and its bulk copies to the others)
+      if (step == 100) ts_e[3] = clock64();
+      fence_proxy_async();
       __syncwarp();
-      if (step + 1 < maxlen && lane < cs) rt_arrive_cluster(bdst + (uint32_t)((par ^ 1) * RT_MAXCS * 8));
+      if (step == 100) ts_e[4] = clock64();
+      if (step + 1 < maxlen) {
+        if (lane < cs - 1) {
+#pragma unroll
+          for (int k = 0; k < NB; ++k) {
+            const int blk8 = cw + RT_CW * k;
+            if (blk8 * 8 < spc) {
+              const uint32_t off = (uint32_t)(par ^ 1) * hpar + hoff_warp + (uint32_t)blk8 * 256;
+              rt_bulk_s2c(fwd_h + off, smem_u32(h_img) + off, 256u, fwd_b + (uint32_t)((par ^ 1) * RT_MAXCS * 8));
+            }
+          }
+        }
+        if (step == 100) ts_e[5] = clock64();
+        if (lane == 0) rt_arrive_local(&bar_h[par ^ 1][rank]);
+      }
+      if (step == 100) ts_e[2] = clock64();
       if (warp == 0) RT_ACC(4);
       // memory bank (fp32), off the critical path: 8 consecutive units x 8 sequences per warp store
 #pragma unroll
@@ -658,12 +686,14 @@ __global__ void __launch_bounds__(FUSED ? RT_THREADS_FUSED : RT_THREADS_PRE, 1) 
       }
       if (warp == 0) RT_ACC(5);
     }
+    if (a.dbg && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && maxlen > 101)
+      for (int i = 0; i < 6; ++i) a.dbg[24 + warp * 6 + i] = ts_e[i];
     if (uvalid && (a.h_n || a.c_n)) {
 #pragma unroll
       for (int k = 0; k < NB; ++k)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          const int sq = 8 * (cw + 4 * k) + 2 * t0i + c;
+          const int sq = 8 * (cw + RT_CW * k) + 2 * t0i + c;
           if (sq >= spc || s0 + sq >= a.n) continue;
           if (a.h_n) a.h_n[((size_t)dir * a.n + s0 + sq) * h + u] = hst[2 * k + c];
           if (a.c_n && !GRU) a.c_n[((size_t)dir * a.n + s0 + sq) * h + u] = cst[2 * k + c];
@@ -690,21 +720,47 @@ static int rt_max_npad(const RnnTcPack& p) {
 int g_rnn_spc_min = 8;   // process-wide floor of the sequences per cluster (tuning knob)
 int g_rnn_spc_force = 0; // > 0: use exactly this many sequences per cluster (tools)
 
-// Sequences per cluster.  A step costs (recurrent MMAs) x (32 + N/4) cycles + the cell updates of 32 units x spc
-// sequences on one SM (MUFU-bound, ~0.45 cycles per cell) + fixed hand-over latencies; a wave holds 148 / cs clusters.
+// Sequences per cluster.  Measured per-step cost (profiles/r02_cars_spc_sweep.txt, r02_rnn_exchange_modes.txt): fixed
+// hand-over latencies (~1200 cycles) + per "round" of column blocks (20 epilogue warps = 5 blocks of 8 sequences per
+// round) the MMAs and cell updates (~800 cycles) and the DSMEM exchange (~900 cycles per destination); more than two
+// rounds per step spill the per-cell state.  A wave holds as many clusters as the hardware co-schedules
+// (cudaOccupancyMaxActiveClusters; 148 / cs at best).
+template <bool GRU, bool FUSED, int NB>
+static int rt_max_clusters(int cs, size_t smem) {
+  static int cache[RT_MAXCS + 1] = {0, 0, 0, 0, 0};
+  if (cache[cs] > 0) return cache[cs];
+  auto kern = rnn_tc_kernel<GRU, FUSED, NB>;
+  int n = 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(cs * (kSMs / cs)), 1);
+    cfg.blockDim = dim3(FUSED ? RT_THREADS_FUSED : RT_THREADS_PRE);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) n = 0;
+    (void)cudaGetLastError();
+  }
+  if (n <= 0) n = kSMs / cs;
+  return cache[cs] = n;
+}
+
 RnnTcPlan rnn_tc_plan(const RnnTcPack& p, int n, int min_spc) {
   RnnTcPlan pl;
   const int maxn = rt_max_npad(p);
-  const int maxcl = kSMs / p.cs;
+  const int maxcl = p.fused ? rt_max_clusters<false, true, 1>(p.cs, rt_smem_bytes(p, 48))
+                            : rt_max_clusters<false, false, 1>(p.cs, rt_smem_bytes(p, 48));
   if (min_spc < g_rnn_spc_min) min_spc = g_rnn_spc_min;
   if (min_spc > maxn) min_spc = maxn;
   double best = 1e30;
   int best_spc = min_spc;
   for (int spc = min_spc; spc <= maxn; ++spc) {
-    const int npad = (spc + 15) / 16 * 16;
+    const int rounds = ((spc + 7) / 8 + RT_CW - 1) / RT_CW;
     const int64_t groups = (int64_t)((n + spc - 1) / spc) * p.dirs;
     const int64_t waves = (groups + maxcl - 1) / maxcl;
-    const double step = 6.0 * p.cs * (32.0 + npad / 4.0) + 0.45 * 32.0 * spc + 500.0;
+    const double step = 1200.0 + rounds * (800.0 + 900.0 * (p.cs - 1)) * (rounds > 2 ? 1.5 : 1.0);
     const double cost = (double)waves * step;
     if (cost < best * 0.999) best = cost, best_spc = spc;
   }
@@ -713,7 +769,7 @@ RnnTcPlan rnn_tc_plan(const RnnTcPack& p, int n, int min_spc) {
   pl.npad = (best_spc + 15) / 16 * 16;
   pl.groups = (n + best_spc - 1) / best_spc;
   pl.ctas = pl.groups * p.dirs * p.cs;
-  pl.nb = ((best_spc + 7) / 8 + 3) / 4;
+  pl.nb = ((best_spc + 7) / 8 + RT_CW - 1) / RT_CW;
   return pl;
 }
 
@@ -763,6 +819,7 @@ int32_t rnn_tc_run(const RnnTcPack& p, const GemmA& x, const int64_t* len, int n
   a.x = x, a.ximg = (p.fused && x.table) ? ximg : nullptr, a.pre = p.fused ? nullptr : ws_pre, a.wimg = p.wimg, a.len = len;
   a.n = n, a.L = L, a.in = p.in, a.h = p.h, a.dirs = p.dirs, a.cs = p.cs, a.spc = pl.spc, a.npad = pl.npad, a.planes = p.planes;
   a.out = out, a.h_n = h_n, a.c_n = c_n, a.err = err, a.dbg = g_rnn_dbg;
+
   const size_t smem = rt_smem_bytes(p, pl.npad);
   if (p.gru) return p.fused ? rt_launch_nb<true, true>(a, pl, p.dirs, smem, s) : rt_launch_nb<true, false>(a, pl, p.dirs, smem, s);
   return p.fused ? rt_launch_nb<false, true>(a, pl, p.dirs, smem, s) : rt_launch_nb<false, false>(a, pl, p.dirs, smem, s);

@@ -47,7 +47,8 @@ class Embeddings(nn.Module):
             tok = vocabulary.ind2tok[i]
             if tok in embeddings_index:
                 pretrained[i] = embeddings_index[tok]
-        self.word_lut.weight.data.copy_(pretrained)
+        with torch.no_grad():   # in-place copy that bumps the parameter version: the libcair handle is rebuilt on next use
+            self.word_lut.weight.copy_(pretrained)
         if fixed:
             self.word_lut.weight.requires_grad = False
 
@@ -79,9 +80,28 @@ class RNNEncoder(nn.Module):
         self.dropout = nn.Dropout(dropout)
 
 
+def _named_tensors(module, prefix=''):
+    """(name, tensor) of every parameter and buffer, including the plain-tensor parameter copies that
+    nn.DataParallel's replicate() leaves in `_former_parameters` of a replica (a replica has no Parameters)."""
+    for name, p in module._parameters.items():
+        if p is not None:
+            yield prefix + name, p
+    for name, p in getattr(module, '_former_parameters', {}).items():
+        if p is not None:
+            yield prefix + name, p
+    for name, b in module._buffers.items():
+        if b is not None:
+            yield prefix + name, b
+    for name, child in module._modules.items():
+        if child is not None:
+            yield from _named_tensors(child, prefix + name + '.')
+
+
+_HANDLE_KEYS = ('_cair_handle', '_cair_key', '_cair_ws')
+
+
 def _ptr_getter(module, keep):
-    sd = dict(module.named_parameters())
-    sd.update(dict(module.named_buffers()))
+    sd = dict(_named_tensors(module))
 
     def get(key):
         t = sd[key]
@@ -103,7 +123,29 @@ class _CairModule(nn.Module):
         raise NotImplementedError
 
     def _state_key(self):
-        return tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters())
+        """Storage, version counter and device of every weight.  In-place ops (optimizer steps, `copy_`, `load_state_dict`)
+        bump the version; writes through `.data` do NOT - call invalidate() after editing a parameter that way."""
+        return tuple((t.data_ptr(), t._version, str(t.device)) for _, t in _named_tensors(self))
+
+    def invalidate(self):
+        """Drop the native handle so the next call re-reads (and re-packs) the weights; needed only after a weight was
+        modified through `.data`, which torch's version counters cannot see."""
+        self._release()
+        return self
+
+    # The native handle belongs to exactly one Python object: copies (copy.copy / deepcopy / pickle / DataParallel
+    # replicas) start without one and create their own on first use.
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        for k in _HANDLE_KEYS:
+            state.pop(k, None)
+        return state
+
+    def _replicate_for_data_parallel(self):
+        replica = super()._replicate_for_data_parallel()
+        for k in _HANDLE_KEYS:
+            replica.__dict__.pop(k, None)
+        return replica
 
     def _handle_for(self, device):
         key = (self._state_key(), device.index)
@@ -111,7 +153,7 @@ class _CairModule(nn.Module):
         if h is not None and self.__dict__.get('_cair_key') == key:
             return h
         self._release()
-        if any(not p.is_cuda for p in self.parameters()):
+        if any(not t.is_cuda for _, t in _named_tensors(self)):
             raise RuntimeError('%s parameters must be on a CUDA device (call .cuda()); no CPU path exists'
                                % type(self).__name__)
         keep = []
@@ -183,10 +225,32 @@ class _Ranker(_CairModule):
                                         begin, count, scores.data_ptr(), ws.data_ptr(), ws.numel(), stream))
         return scores
 
+    @staticmethod
+    def _host_args(q, qlen, d, dlen, out, need_pinned):
+        """The host entry points take raw pointers: insist on CPU int64 contiguous ids / lengths of the documented shapes
+        and a CPU float32 [B, N] result buffer (pinned where the copy is asynchronous)."""
+        for name, t in (('q', q), ('qlen', qlen), ('d', d), ('dlen', dlen)):
+            if not torch.is_tensor(t) or t.is_cuda or t.dtype != torch.int64 or not t.is_contiguous():
+                raise ValueError('%s must be a contiguous CPU int64 tensor' % name)
+            if need_pinned and not t.is_pinned():
+                raise ValueError('%s must be in pinned host memory (asynchronous copy)' % name)
+        if q.dim() != 2 or d.dim() != 3 or d.shape[0] != q.shape[0]:
+            raise ValueError('q must be [B, Lq] and d [B, N, Ld]')
+        B, N = d.shape[0], d.shape[1]
+        if qlen.numel() != B or dlen.numel() != B * N:
+            raise ValueError('qlen must hold B and dlen B*N lengths')
+        if out is not None:
+            if (not torch.is_tensor(out) or out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous()
+                    or out.numel() != B * N):
+                raise ValueError('out must be a contiguous CPU float32 tensor with B*N elements')
+            if need_pinned and not out.is_pinned():
+                raise ValueError('out must be in pinned host memory (asynchronous copy)')
+
     def forward_host(self, q, qlen, d, dlen, out=None, device=None):
         """End-to-end entry point on HOST tensors (pinned recommended): ids are copied host->device,
         scored, and the scores copied back; returns a CPU tensor.  Raises on bad token ids / lengths."""
         dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self._host_args(q, qlen, d, dlen, out, need_pinned=False)
         B, Lq = q.shape
         _, N, Ld = d.shape
         if out is None:
@@ -204,6 +268,9 @@ class _Ranker(_CairModule):
         runs partly under the document encoder of batch k+1.  Call wait_host(slot) before reading `out` or re-using
         the slot."""
         dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        if out is None:
+            raise ValueError('submit_host needs a pinned float32 result buffer')
+        self._host_args(q, qlen, d, dlen, out, need_pinned=True)
         B, Lq = q.shape
         _, N, Ld = d.shape
         h = self._handle_for(dev)
@@ -212,7 +279,10 @@ class _Ranker(_CairModule):
                                                      stream.cuda_stream if stream is not None else None))
 
     def wait_host(self, slot):
-        lib.check(lib.load().cair_ranker_wait_host(self.__dict__['_cair_handle'], slot))
+        h = self.__dict__.get('_cair_handle')
+        if h is None:
+            raise RuntimeError('wait_host(%d): nothing was submitted (no native handle yet)' % slot)
+        lib.check(lib.load().cair_ranker_wait_host(h, slot))
 
     def poll_error(self):
         h = self.__dict__.get('_cair_handle')

@@ -129,9 +129,11 @@ CAIR_API int32_t cair_rnn_forward(int32_t rnn_type, const float* x, const int64_
                           int32_t in, int32_t h, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, float* out,
                           float* h_n, float* c_n, void* stream);
 
-/* Process-wide recurrence engine (A/B runs and on-device cross-checks): 2 = cluster-split tcgen05 kernel
- * (default; LSTM and GRU, h <= 128 per direction, any input size), 1 = round-1 tcgen05 kernel (LSTM, in < 48,
- * h <= 64), 0 = fp32 CUDA-core kernels.  Shapes an engine does not cover fall through to the next one. */
+/* Process-wide recurrence engine (A/B runs and on-device cross-checks): 2 = auto (default): per shape the faster
+ * tcgen05 kernel - the single-CTA kernel for LSTM with in < 48 and 32 < h <= 64 (a pure latency chain at cfg2),
+ * the cluster-split kernel (LSTM and GRU, h <= 128 per direction, any input size) otherwise; 3 = cluster-split kernel
+ * wherever it applies; 1 = single-CTA kernel where it applies; 0 = fp32 CUDA-core kernels.  Shapes an engine does not
+ * cover fall through to the next one. */
 CAIR_API int32_t cair_set_rnn_impl(int32_t impl);
 
 /* On-device self test of the tcgen05 operand/descriptor conventions (csrc/umma.cuh):

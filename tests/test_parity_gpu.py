@@ -451,7 +451,7 @@ def rnn_engine(request):
     """Recurrence engine under test: the cluster-split tcgen05 kernel (default), the round-1 tcgen05 kernel, fp32 kernels.
     Shapes an engine does not cover fall through to the next one (cair_set_rnn_impl)."""
     L = lib.load()
-    lib.check(L.cair_set_rnn_impl({'fp32': 0, 'r1': 1, 'cluster': 2}[request.param]))
+    lib.check(L.cair_set_rnn_impl({'fp32': 0, 'r1': 1, 'cluster': 3}[request.param]))
     yield request.param
     lib.check(L.cair_set_rnn_impl(2))
 

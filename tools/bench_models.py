@@ -35,6 +35,28 @@ def timeit(fn):
     return float(np.mean(ms)), float(np.min(ms))
 
 
+def stages_of(net, fn, reps=3):
+    """Per-stage CUDA-event times (ms) of the library's own profiler, averaged over a few flushed steps."""
+    import ctypes as C
+    from context_attentive_ir_b200 import lib
+    L = lib.load()
+    h = net.__dict__['_cair_handle']
+    lib.check(L.cair_profile_enable(h, 1))
+    acc = {}
+    for i in range(reps):
+        flush.fill_(i)
+        fn()
+        torch.cuda.synchronize()
+        names = C.create_string_buffer(2048)
+        ms = (C.c_float * 64)()
+        cnt = C.c_int32()
+        lib.check(L.cair_profile_read(h, names, 2048, ms, 64, C.byref(cnt)))
+        for nm, v in zip(names.value.decode().split(','), list(ms)[:cnt.value]):
+            acc.setdefault(nm, []).append(v)
+    lib.check(L.cair_profile_enable(h, 0))
+    return {k: round(float(np.mean(v)), 4) for k, v in acc.items()}
+
+
 def ranker(name, cfg, B, N, Lq, Ld, bytes_per_pair=None, **kw):
     torch.manual_seed(1013)
     net = helpers.build_module(cfg).to(dev)
@@ -98,5 +120,6 @@ for m in args.models.split(','):
         t = helpers.to_dev(batch, dev, ('q', 'qlen', 'd', 'dlen', 'label'))
         with torch.no_grad():
             mean, best = timeit(lambda: net.score(*t))
+            st = stages_of(net, lambda: net.score(*t))
         print(json.dumps(dict(model='cars cfg4 (ranking path)', config=dict(B=B, S=S, N=N, Lq=Lq, Ld=Ld, E=300, H=256),
-                              pairs_per_s=B * S * N / (mean / 1e3), ms_per_step=mean, ms_best=best)), flush=True)
+                              pairs_per_s=B * S * N / (mean / 1e3), ms_per_step=mean, ms_best=best, stages_ms=st)), flush=True)
