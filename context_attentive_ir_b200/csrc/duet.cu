@@ -199,17 +199,21 @@ int32_t duet_forward(const DuetState& st, const int64_t* q, const int64_t* d, in
   if (smem > 200 * 1024) return fail(CAIR_ERR_UNSUPPORTED, "duet: Lq*Ld too large for the local model kernel");
   if (smem > 48 * 1024)
     CAIR_CUDA(cudaFuncSetAttribute(duet_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prof_mark("local_model", s);
   CAIR_LAUNCH(duet_local_kernel, (unsigned)pc, 256, smem, s, q, d, N, Lq, Ld, nf, pb, st.lconv_t, st.lconv_b,
               st.lfc1_w, st.lfc1_b, m1l);
   CAIR_TRY(gemm_f32(gemm_dense(m1l, nf), st.lfc2_w, st.lfc2_b, m2l, nf, pc, nf, nf, ACT_TANH, s));
   // distributed model, query side
+  prof_mark("query_conv", s);
   CAIR_TRY(gemm_auto(gemm_gather(st.table, st.V, E, q + qb * Lq, 3, Lq, Tq, err), st.cq_w, st.cq_tc, st.cq_b, cqv, nf,
                      nq * Tq, nf, 3 * E, ACT_TANH, s));
   CAIR_LAUNCH(colmax_kernel, (unsigned)nq, 256, 0, s, cqv, Tq, nf, mq);
   CAIR_TRY(gemm_f32(gemm_dense(mq, nf), st.fc1_w, st.fc1_b, rq, nf, nq, nf, nf, ACT_TANH, s));
   // distributed model, document side
+  prof_mark("conv_d1", s);
   CAIR_TRY(gemm_auto(gemm_gather(st.table, st.V, E, d + pb * Ld, 3, Ld, Td, err), st.cd1_w, st.cd1_tc, st.cd1_b, cdv, nf,
                      pc * Td, nf, 3 * E, ACT_TANH, s));
+  prof_mark("pool_conv_d2", s);
   if ((nf & 3) == 0) {
     const int64_t total = (int64_t)pc * Tp * (nf / 4);
     CAIR_LAUNCH(timepool4_kernel, (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16), 256, 0, s,
@@ -219,6 +223,7 @@ int32_t duet_forward(const DuetState& st, const int64_t* q, const int64_t* d, in
     CAIR_TRY(gemm_auto(gemm_pooled(cdv, nf, st.pool, Td, Tp), st.cd2_w, st.cd2_tc, st.cd2_b, rd, nf, pc * Tp, nf, nf,
                        ACT_TANH, s));
   }
+  prof_mark("head", s);
   CAIR_LAUNCH(duet_hadamard_kernel, dim3((unsigned)pc, (nf + 127) / 128), 128, 0, s, rd, rq, st.fc2_w, st.fc2_b, N, Tp,
               nf, pb, qb, m1d);
   CAIR_TRY(gemm_f32(gemm_dense(m1d, nf), st.fc3_w, st.fc3_b, m2d, nf, pc, nf, nf, ACT_TANH, s));
