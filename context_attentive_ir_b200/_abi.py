@@ -97,6 +97,16 @@ class CarsWeights(C.Structure):
         ('q_projection', Linear), ('ranknet', Linear * 3)]
 
 
+class CarsOutputs(C.Structure):
+    _fields_ = [(k, f32p) for k in ('pooled_q', 'pooled_d', 'clicks', 'sess_q_attn', 'sess_d_attn', 'enc_q', 'sess_h', 'sess_c')]
+
+
+class CarsDecoderWeights(C.Structure):
+    _fields_ = [('nhid_decoder', C.c_int32), ('tgt_vocab', C.c_int32), ('transform_hid', Linear), ('transform_cell', Linear),
+                ('rnn', LstmDir), ('attn_in', Linear), ('attn_out', Linear), ('dec_attn', Linear), ('predictor1', Linear),
+                ('predictor2', Linear), ('private_session_projector2', Linear)]
+
+
 TABLE_KEY = 'word_embeddings.make_embedding.emb_luts.0.weight'
 
 
@@ -228,6 +238,21 @@ def pack_cars(cfg, get):
     w.q_projection = _lin(get, 'q_projection.linear')
     for i in range(3):
         w.ranknet[i] = _lin(get, 'ranknet._linear_layers.%d' % i)
+    return w
+
+
+def pack_cars_decoder(cfg, get):
+    """Decoder-side modules of CARS (multitask/cars.py:605-657), attn_type 'general'."""
+    w = CarsDecoderWeights(cfg['nhid_decoder'], cfg['tgt_vocab_size'])
+    w.transform_hid = _lin(get, 'transform_hid.linear')
+    w.transform_cell = _lin(get, 'transform_cell.linear')
+    w.rnn = _lstm(get, 'decoder.decoder.rnn')
+    w.attn_in = _lin(get, 'decoder.decoder.attn.linear_in', bias=False)
+    w.attn_out = _lin(get, 'decoder.decoder.attn.linear_out', bias=False)
+    w.dec_attn = _lin(get, 'dec_attn', bias=False)
+    w.predictor1 = _lin(get, 'token_prob_predictor1', bias=False)
+    w.predictor2 = _lin(get, 'token_prob_predictor2', bias=False)
+    w.private_session_projector2 = _lin(get, 'private_session_projector2.linear', bias=False)
     return w
 
 

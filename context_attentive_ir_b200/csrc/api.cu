@@ -67,6 +67,7 @@ struct cair_handle {
     size_t ws_bytes = 0;
     cudaEvent_t ev_in = nullptr, ev_enc = nullptr, ev_done = nullptr, ev_int = nullptr;   // ev_int: interaction kernels done
     int* err = nullptr;  // pinned
+    int* d_err = nullptr;  // this slot's own device error word: up to three batches are in flight on different streams
     bool busy = false;
     bool tail_pending = false;   // encoder enqueued, interaction not yet (cross-batch software pipeline)
     int B = 0, N = 0, Lq = 0, Ld = 0;
@@ -656,7 +657,7 @@ int32_t pipe_interact(cair_handle* h, int sl, int64_t ib, int64_t ic, int max_ct
   Arena ws(p.ws, p.ws_bytes);
   MtPhase ph;
   ph.phase = MT_INTERACT, ph.ib = ib, ph.ic = ic, ph.max_ctas = max_ctas, ph.join = join;
-  return mt_forward(h->mt, v.dq, v.dql, v.dd, v.ddl, p.B, p.N, p.Lq, p.Ld, 0, (int64_t)p.B * p.N, v.ds, ws, h->d_err, st,
+  return mt_forward(h->mt, v.dq, v.dql, v.dd, v.ddl, p.B, p.N, p.Lq, p.Ld, 0, (int64_t)p.B * p.N, v.ds, ws, p.d_err, st,
                     false, ph);
 }
 
@@ -666,8 +667,9 @@ int32_t pipe_finish(cair_handle* h, int sl, cudaStream_t st) {
   const PipeView v = pipe_view(p);
   CAIR_CUDA(cudaEventRecord(p.ev_int, st));   // the machine is free again: the next encoder need not wait for the copies
   CAIR_CUDA(cudaMemcpyAsync(p.scores_host, v.ds, (size_t)p.B * p.N * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CAIR_CUDA(cudaMemcpyAsync(p.err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CAIR_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int), st));
+  int* flag = p.tail_pending ? p.d_err : h->d_err;   // pipelined batches carry their own flag; the plain form uses the handle's
+  CAIR_CUDA(cudaMemcpyAsync(p.err, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CAIR_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
   CAIR_CUDA(cudaEventRecord(p.ev_done, st));
   p.tail_pending = false;
   return CAIR_OK;
@@ -706,6 +708,8 @@ int32_t cair_ranker_submit_host(cair_handle* h, const int64_t* q, const int64_t*
     CAIR_CUDA(cudaEventCreateWithFlags(&p.ev_int, cudaEventDisableTiming));
     CAIR_CUDA(cudaHostAlloc((void**)&p.err, sizeof(int), cudaHostAllocDefault));
     *p.err = 0;
+    CAIR_CUDA(h->own.alloc(&p.d_err, 1));
+    CAIR_CUDA(cudaMemset(p.d_err, 0, sizeof(int)));
   }
   size_t wsb = 0;
   CAIR_TRY(cair_ranker_workspace_bytes(h, B, N, Lq, Ld, &wsb));
@@ -777,7 +781,7 @@ int32_t cair_ranker_submit_host(cair_handle* h, const int64_t* q, const int64_t*
     MtPhase ph;
     ph.phase = MT_ENCODE;
     ph.doc_min_spc = h->pipe_spc;
-    CAIR_TRY(mt_forward(h->mt, v.dq, v.dql, v.dd, v.ddl, B, N, Lq, Ld, 0, (int64_t)nbn, v.ds, ws, h->d_err, H, false, ph));
+    CAIR_TRY(mt_forward(h->mt, v.dq, v.dql, v.dd, v.ddl, B, N, Lq, Ld, 0, (int64_t)nbn, v.ds, ws, p.d_err, H, false, ph));
   }
   CAIR_TRY(pipe_mark(h, slot, 1, H));
   CAIR_CUDA(cudaEventRecord(p.ev_enc, H));
@@ -858,11 +862,10 @@ int32_t cair_cars_workspace_bytes(cair_handle* h, int32_t B, int32_t S, int32_t 
   return CAIR_OK;
 }
 
-int32_t cair_cars_forward(cair_handle* h, const int64_t* q, const int64_t* qlen, const int64_t* d,
-                          const int64_t* dlen, const float* labels, int32_t B, int32_t S, int32_t N, int32_t Lq,
-                          int32_t Ld, int32_t session_begin, int32_t session_count, float* scores, float* pooled_q,
-                          float* pooled_d, float* clicks, float* sess_q_attn, float* sess_d_attn, void* workspace,
-                          size_t workspace_bytes, void* stream) {
+int32_t cair_cars_forward_ex(cair_handle* h, const int64_t* q, const int64_t* qlen, const int64_t* d,
+                             const int64_t* dlen, const float* labels, int32_t B, int32_t S, int32_t N, int32_t Lq,
+                             int32_t Ld, int32_t session_begin, int32_t session_count, float* scores,
+                             const cair_cars_outputs* outs, void* workspace, size_t workspace_bytes, void* stream) {
   if (!h || h->model != CAIR_MODEL_CARS) return fail(CAIR_ERR_BAD_ARG, "cars_forward: not a CARS handle");
   if (B <= 0 || S <= 0 || N <= 0 || Lq <= 0 || Ld <= 0) return fail(CAIR_ERR_BAD_SHAPE, "B, S, N, Lq, Ld must be positive");
   if (!q || !qlen || !d || !dlen || !labels || !scores) return fail(CAIR_ERR_BAD_ARG, "cars_forward: null tensor");
@@ -870,7 +873,12 @@ int32_t cair_cars_forward(cair_handle* h, const int64_t* q, const int64_t* qlen,
     return fail(CAIR_ERR_BAD_ARG, "cars_forward: session slice outside B");
   if (((uintptr_t)workspace & 255) != 0) return fail(CAIR_ERR_WORKSPACE, "workspace must be 256-byte aligned");
   DeviceGuard g(h->device);
-  CarsIO io{q, qlen, d, dlen, labels, scores, pooled_q, pooled_d, clicks, sess_q_attn, sess_d_attn};
+  CarsIO io{q, qlen, d, dlen, labels, scores, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (outs) {
+    io.pooled_q = outs->pooled_q, io.pooled_d = outs->pooled_d, io.clicks = outs->clicks;
+    io.sess_q_attn = outs->sess_q_attn, io.sess_d_attn = outs->sess_d_attn;
+    io.enc_q = outs->enc_q, io.sess_h = outs->sess_h, io.sess_c = outs->sess_c;
+  }
   Arena probe(nullptr, 0);
   CAIR_TRY(cars_forward(h->cars, io, B, S, N, Lq, Ld, session_begin, session_count, probe, h->d_err, 0, true));
   if (probe.off > workspace_bytes || (probe.off > 0 && !workspace))
@@ -880,6 +888,51 @@ int32_t cair_cars_forward(cair_handle* h, const int64_t* q, const int64_t* qlen,
   g_prof = &h->prof;
   prof_mark("begin", (cudaStream_t)stream);
   int32_t rc = cars_forward(h->cars, io, B, S, N, Lq, Ld, session_begin, session_count, ws, h->d_err, (cudaStream_t)stream, false);
+  prof_mark("end", (cudaStream_t)stream);
+  g_prof = nullptr;
+  return rc;
+}
+
+int32_t cair_cars_forward(cair_handle* h, const int64_t* q, const int64_t* qlen, const int64_t* d,
+                          const int64_t* dlen, const float* labels, int32_t B, int32_t S, int32_t N, int32_t Lq,
+                          int32_t Ld, int32_t session_begin, int32_t session_count, float* scores, float* pooled_q,
+                          float* pooled_d, float* clicks, float* sess_q_attn, float* sess_d_attn, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  cair_cars_outputs o{pooled_q, pooled_d, clicks, sess_q_attn, sess_d_attn, nullptr, nullptr, nullptr};
+  return cair_cars_forward_ex(h, q, qlen, d, dlen, labels, B, S, N, Lq, Ld, session_begin, session_count, scores, &o, workspace,
+                              workspace_bytes, stream);
+}
+
+int32_t cair_cars_set_decoder(cair_handle* h, const cair_cars_decoder_weights* w) {
+  if (!h || h->model != CAIR_MODEL_CARS || !w) return fail(CAIR_ERR_BAD_ARG, "cars_set_decoder: not a CARS handle");
+  DeviceGuard g(h->device);
+  CAIR_TRY(cars_set_decoder(h->own, &h->cars, *w, 0));
+  CAIR_CUDA(cudaStreamSynchronize(0));
+  return CAIR_OK;
+}
+
+int32_t cair_cars_decode_workspace_bytes(cair_handle* h, int32_t B, int32_t S, int32_t Lq, size_t* bytes) {
+  if (!h || h->model != CAIR_MODEL_CARS || !bytes) return fail(CAIR_ERR_BAD_ARG, "cars_decode_workspace_bytes: bad argument");
+  if (!h->cars.dec.ready) return fail(CAIR_ERR_BAD_ARG, "cars_decode: no decoder weights (cair_cars_set_decoder)");
+  if (B <= 0 || S <= 0 || Lq <= 0) return fail(CAIR_ERR_BAD_SHAPE, "B, S, Lq must be positive");
+  *bytes = cars_decode_workspace_bytes(h->cars, B, S, Lq);
+  return CAIR_OK;
+}
+
+int32_t cair_cars_decode(cair_handle* h, const float* enc_q, const int64_t* qlen, const float* sess_h, const float* sess_c,
+                         const float* sess_q_attn, const float* sess_d_attn, int32_t B, int32_t S, int32_t Lq,
+                         int32_t max_len, const int64_t* tgt2src, int64_t bos_id, int64_t* predictions, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  if (!h || h->model != CAIR_MODEL_CARS) return fail(CAIR_ERR_BAD_ARG, "cars_decode: not a CARS handle");
+  if (!enc_q || !qlen || !sess_h || !sess_c || !sess_q_attn || !sess_d_attn || !tgt2src || !predictions)
+    return fail(CAIR_ERR_BAD_ARG, "cars_decode: null tensor");
+  if (B <= 0 || S <= 0 || Lq <= 0 || max_len < 0) return fail(CAIR_ERR_BAD_SHAPE, "B, S, Lq must be positive");
+  if (((uintptr_t)workspace & 255) != 0) return fail(CAIR_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  DeviceGuard g(h->device);
+  h->prof.reset();
+  g_prof = &h->prof;
+  int32_t rc = cars_decode(h->cars, enc_q, qlen, sess_h, sess_c, sess_q_attn, sess_d_attn, B, S, Lq, max_len, tgt2src, bos_id,
+                           predictions, workspace, workspace_bytes, h->d_err, (cudaStream_t)stream);
   prof_mark("end", (cudaStream_t)stream);
   g_prof = nullptr;
   return rc;

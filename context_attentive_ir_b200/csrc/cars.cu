@@ -61,6 +61,7 @@ int32_t cars_create_state(Owned& own, const cair_cars_weights& w, CarsState* st,
   // both bias-free projectors see the same input (cars.py:506-512): W_shared x + W_priv x = (W_shared + W_priv) x
   const int64_t np = (int64_t)st->Hd * Hs;
   CAIR_CUDA(own.alloc(&st->sess_proj, (size_t)np));
+  CAIR_TRY(dev_copy(own, w.shared_session_projector.w, (size_t)np, &st->shared_proj, s));
   CAIR_LAUNCH(add_kernel, (unsigned)((np + 255) / 256), 256, 0, s, w.shared_session_projector.w,
               w.private_session_projector1.w, st->sess_proj, np);
   int in = 4 * st->Hd;
@@ -402,6 +403,8 @@ int32_t cars_forward(const CarsState& st, const CarsIO& io, int B, int S, int N,
   int64_t* slen = ws.take<int64_t>((size_t)sc);
   float* pre_sq = ws.take<float>(lstm_workspace_floats(st.sess_q, sc, S));
   float* Qs = ws.take<float>((size_t)nrows * Hsq);
+  float* Qc = ws.take<float>((size_t)nrows * Hsq);   // cell states per step (decoder-side output; reserved unconditionally so that
+  float* Dc = ws.take<float>((size_t)nrows * Hsd);   // the workspace size does not depend on the requested outputs)
   float* pre_sd = ws.take<float>(lstm_workspace_floats(st.sess_d, sc, S));
   float* Ds = ws.take<float>((size_t)nrows * Hsd);
   const int Hsmax = Hsq > Hsd ? Hsq : Hsd;
@@ -426,8 +429,10 @@ int32_t cars_forward(const CarsState& st, const CarsIO& io, int B, int S, int N,
   // 3. session LSTMs over the pooled queries / click vectors (zero initial state, S steps each)
   prof_mark("session_encoders", s);
   CAIR_LAUNCH(fill_len_kernel, (sc + 255) / 256, 256, 0, s, slen, sc, (int64_t)S);
-  CAIR_TRY(lstm_run(st.sess_q, gemm_dense(pq, Hq), slen, sc, S, Qs, nullptr, nullptr, pre_sq, err, s));
-  CAIR_TRY(lstm_run(st.sess_d, gemm_dense(clk, Hd), slen, sc, S, Ds, nullptr, nullptr, pre_sd, err, s));
+  CAIR_TRY(lstm_run(st.sess_q, gemm_dense(pq, Hq), slen, sc, S, Qs, nullptr, nullptr, pre_sq, err, s, "lstm_recurrence",
+                    io.sess_c ? Qc : nullptr));
+  CAIR_TRY(lstm_run(st.sess_d, gemm_dense(clk, Hd), slen, sc, S, Ds, nullptr, nullptr, pre_sd, err, s, "lstm_recurrence",
+                    io.sess_c ? Dc : nullptr));
   // 4. session attention + rank head
   prof_mark("rank_head", s);
   {
@@ -438,6 +443,17 @@ int32_t cars_forward(const CarsState& st, const CarsIO& io, int B, int S, int N,
     CAIR_CUDA(cudaFuncSetAttribute(cars_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CarsState stc = st;
     CAIR_LAUNCH(cars_rank_kernel, (unsigned)nrows, 256, smem, s, stc, pq, pd, Qs, Ds, S, N, r0, io.scores);
+  }
+  // decoder-side outputs: query memory banks, session-encoder states after every query
+  if (io.enc_q)
+    CAIR_CUDA(cudaMemcpyAsync(io.enc_q + r0 * Lq * Hq, enc_q, (size_t)nrows * Lq * Hq * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (io.sess_h) {
+    CAIR_CUDA(cudaMemcpy2DAsync(io.sess_h + r0 * (Hsq + Hsd), (size_t)(Hsq + Hsd) * 4, Qs, (size_t)Hsq * 4, (size_t)Hsq * 4, nrows, cudaMemcpyDeviceToDevice, s));
+    CAIR_CUDA(cudaMemcpy2DAsync(io.sess_h + r0 * (Hsq + Hsd) + Hsq, (size_t)(Hsq + Hsd) * 4, Ds, (size_t)Hsd * 4, (size_t)Hsd * 4, nrows, cudaMemcpyDeviceToDevice, s));
+  }
+  if (io.sess_c) {
+    CAIR_CUDA(cudaMemcpy2DAsync(io.sess_c + r0 * (Hsq + Hsd), (size_t)(Hsq + Hsd) * 4, Qc, (size_t)Hsq * 4, (size_t)Hsq * 4, nrows, cudaMemcpyDeviceToDevice, s));
+    CAIR_CUDA(cudaMemcpy2DAsync(io.sess_c + r0 * (Hsq + Hsd) + Hsq, (size_t)(Hsq + Hsd) * 4, Dc, (size_t)Hsd * 4, (size_t)Hsd * 4, nrows, cudaMemcpyDeviceToDevice, s));
   }
   // optional stage outputs (decoder-side session summaries included)
   if (io.pooled_q) CAIR_CUDA(cudaMemcpyAsync(io.pooled_q + r0 * Hq, pq, (size_t)nrows * Hq * sizeof(float), cudaMemcpyDeviceToDevice, s));

@@ -255,8 +255,11 @@ int32_t lstm_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* rev
                   cudaStream_t s, int rnn_type = CAIR_RNN_LSTM);
 size_t lstm_workspace_floats(const LstmPack& p, int64_t n, int L);
 // pre-gates GEMM (optionally gathering rows from `table`) + recurrence; out [n,L,dirs*h], zeros at t>=len.
+// c_seq (optional, LSTM): the cell state of every step, same layout as `out` (needed by the CARS decoder, which starts
+// from the session encoders' (h, c) after each query - neuroir/multitask/cars.py:385-411)
 int32_t lstm_run(const LstmPack& p, const GemmA& x, const int64_t* len, int n, int L, float* out, float* h_n,
-                 float* c_n, float* ws_pre, int* err, cudaStream_t s, const char* rec_name = "lstm_recurrence");
+                 float* c_n, float* ws_pre, int* err, cudaStream_t s, const char* rec_name = "lstm_recurrence",
+                 float* c_seq = nullptr);
 
 // tcgen05 LSTM (lstm_tc.cu): fused input + recurrent projection per step, weights resident in smem.
 struct LstmTcPack {

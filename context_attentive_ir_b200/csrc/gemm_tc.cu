@@ -22,8 +22,10 @@ constexpr int GT_BK = 64;         // K chunk
 constexpr int GT_MAXSTAGES = 4;   // ring depth: as many (A chunk + W chunk) stages as fit in shared memory, 2..4
 constexpr int GT_LWARPS = 8;      // loader / epilogue warps: two threads per row (32 K elements each)
 constexpr int GT_THREADS = (GT_LWARPS + 2) * 32;   // + W producer warp + MMA issuer warp
-constexpr uint32_t GT_APLANE = GT_BM * 16;
-constexpr uint32_t GT_AIMG = (GT_BK / 8) * GT_APLANE;  // one (hi|lo) A chunk image: 16 KB
+// A operand planes are padded by one 16-byte unit: with 16 lanes of a half warp writing the 8 planes of ONE row (coalesced
+// loader below), an unpadded plane stride (2048 B = a multiple of 128 B) would put all of them on the same banks
+constexpr uint32_t GT_APLANE = GT_BM * 16 + 16;
+constexpr uint32_t GT_AIMG = (GT_BK / 8) * GT_APLANE;  // one (hi|lo) A chunk image: 16.1 KB
 
 int g_gemm_impl = 1;  // 1: tcgen05 where the shape allows, 0: always the fp32 CUDA-core kernel
 
@@ -138,59 +140,101 @@ __global__ void __launch_bounds__(GT_THREADS, 1)
     }
     mma_commit_w(&acc_full, issue);
   } else {
-    // ---- A loaders (thread <-> row), then epilogue ----
-    // thread <-> (row, half of the K chunk): 8 independent 128-bit loads in flight per thread
-    const int row = tid & (GT_BM - 1), hp = tid >> 7;
-    const int64_t r = m0 + row;
-    const bool rvalid = r < M;
-    constexpr int NV = GT_BK / 8;   // float4 slices per thread
-    // gathered rows: (sequence, first position) of this thread's row, hoisted out of the chunk loop
-    const int64_t gseq = a.table ? r / a.T : 0;
-    const int gt0 = a.table ? (int)(r - gseq * a.T) - a.pad : 0;
-    bool bad_id = false;
-    for (int kc = 0; kc < nkc; ++kc) {
-      const int s = kc % nst;
-      mbar_wait_relaxed(&empty[s], ((kc / nst) & 1) ^ 1);
-      float4 v[NV];
-      if (a.table) {
-        // Two passes, both branch-free: first ALL token ids of the slice (independent loads), then ALL row slices.
-        // Going through gemm_a_load4 chains id -> row once per slice (the id check's atomic keeps the compiler from
-        // batching the loads): measured 17 k cycles per chunk, i.e. the loader, not the tensor pipe, set the pace.
-        const float* src[NV];
+    // ---- A loaders, then epilogue ----
+    // Coalesced: lanes 0-15 of a warp read the 16 float4 slices (256 contiguous bytes) of ONE row of the 64-wide K chunk,
+    // lanes 16-31 those of the next row, so a load instruction touches 4 cache lines instead of 32 (one 16-byte slice
+    // from each of 32 different rows: the L1 wavefront rate, 2048 per chunk, used to set the pace).  Warp w owns rows
+    // 16 w .. 16 w + 15 of the tile, iteration i -> row 16 w + 2 i + lane / 16; 8 independent loads in flight per thread.
+    const int j = lane & 15, rsub = lane >> 4;
+    constexpr int NV = 8;
+    int64_t gseq[NV];
+    int gt0[NV];
+    bool rv[NV];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          const int kk = kc * GT_BK + (hp * NV + i) * 4;
-          const int seg = kk / a.E;
-          const int pos = gt0 + seg;
-          const bool ok = rvalid && kk < K && pos >= 0 && pos < a.L;
-          int64_t id = a.ids[ok ? gseq * a.L + pos : 0];
-          const bool inr = id >= 0 && id < a.V;
-          bad_id |= ok && !inr;
-          id = inr ? id : 0;
-          src[i] = ok ? a.table + id * a.E + (kk - seg * a.E) : nullptr;
-        }
+    for (int i = 0; i < NV; ++i) {
+      const int64_t r = m0 + warp * 16 + 2 * i + rsub;
+      rv[i] = r < M;
+      gseq[i] = a.table ? (rv[i] ? r / a.T : 0) : r;
+      gt0[i] = a.table ? (int)((rv[i] ? r : 0) - gseq[i] * a.T) - a.pad : 0;
+    }
+    bool bad_id = false;
+    // Software pipeline over the K chunks: the token ids of chunk kc+2 are requested and the row slices of chunk kc+1
+    // loaded BEFORE chunk kc is converted and written, so the two dependent global-memory latencies of a gathered chunk
+    // (id -> row) overlap the conversion / barrier wait of the previous chunks.
+    int64_t idraw[NV];      // raw token ids of the chunk after next (consumed one iteration after they were requested)
+    const float* src[NV];   // row slices of the next chunk
+    float4 vn[NV];          // row slices of the next chunk to convert
+    // (segment, offset inside the embedding row) of this thread's slice, advanced by 64 columns per chunk (no divisions)
+    const int E_ = a.table ? a.E : 1;
+    int seg_c = a.table ? (4 * j) / E_ : 0, rem_c = a.table ? (4 * j) % E_ : 0;   // chunk whose ids are requested next
+    int seg_p = seg_c, rem_p = rem_c;                                              // chunk whose pointers are formed next
+    auto advance = [&](int& seg, int& rem) {
+      rem += GT_BK;
+      while (rem >= E_) rem -= E_, ++seg;
+    };
+    auto request_ids = [&](int kc) {   // independent loads, nothing consumes them in this iteration
+      const int kk = kc * GT_BK + 4 * j;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int pos = gt0[i] + seg_c;
+        const bool ok = rv[i] && kk < K && pos >= 0 && pos < a.L;
+        idraw[i] = a.ids[ok ? gseq[i] * a.L + pos : 0];
+      }
+      advance(seg_c, rem_c);
+    };
+    auto form_ptrs = [&](int kc) {     // ids of chunk kc (requested an iteration ago) -> source pointers
+      const int kk = kc * GT_BK + 4 * j;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int pos = gt0[i] + seg_p;
+        const bool ok = rv[i] && kk < K && pos >= 0 && pos < a.L;
+        int64_t id = idraw[i];
+        const bool inr = id >= 0 && id < a.V;
+        bad_id |= ok && !inr;
+        id = inr ? id : 0;
+        src[i] = ok ? a.table + id * a.E + rem_p : nullptr;
+      }
+      advance(seg_p, rem_p);
+    };
+    auto load_rows = [&](int kc) {
+      const int kk = kc * GT_BK + 4 * j;
+      if (a.table) {
 #pragma unroll
         for (int i = 0; i < NV; ++i)
-          v[i] = src[i] ? *reinterpret_cast<const float4*>(src[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          vn[i] = src[i] ? *reinterpret_cast<const float4*>(src[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
       } else {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          const int kk = kc * GT_BK + (hp * NV + i) * 4;
-          v[i] = (rvalid && kk < K) ? gemm_a_load4(a, r, kk) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int i = 0; i < NV; ++i)
+          vn[i] = (rv[i] && kk < K) ? gemm_a_load4(a, gseq[i], kk) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      uint8_t* ah = a_ring + (size_t)s * 2 * GT_AIMG;
+    };
+    if (a.table) {
+      request_ids(0);
+      form_ptrs(0);
+    }
+    load_rows(0);
+    if (a.table && nkc > 1) request_ids(1);
+    // operand image position of this thread's 8-byte half unit: plane j/2, row, bytes (j & 1) * 8
+    const uint32_t aoff = (uint32_t)(j >> 1) * GT_APLANE + (uint32_t)(warp * 16 + rsub) * 16 + (uint32_t)(j & 1) * 8;
+    for (int kc = 0; kc < nkc; ++kc) {
+      const int s = kc % nst;
+      float4 v[NV];
 #pragma unroll
-      for (int p2 = 0; p2 < NV / 2; ++p2) {
-        const int pl = hp * (NV / 2) + p2;
-        const float x[8] = {v[2 * p2].x, v[2 * p2].y, v[2 * p2].z, v[2 * p2].w,
-                            v[2 * p2 + 1].x, v[2 * p2 + 1].y, v[2 * p2 + 1].z, v[2 * p2 + 1].w};
-        uint32_t hi[4], lo[4];
+      for (int i = 0; i < NV; ++i) v[i] = vn[i];
+      if (kc + 1 < nkc) {
+        if (a.table) form_ptrs(kc + 1);
+        load_rows(kc + 1);
+      }
+      if (a.table && kc + 2 < nkc) request_ids(kc + 2);
+      mbar_wait_relaxed(&empty[s], ((kc / nst) & 1) ^ 1);
+      uint8_t* ah = a_ring + (size_t)s * 2 * GT_AIMG + aoff;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) split_bf16x2(x[2 * e], x[2 * e + 1], hi[e], lo[e]);
-        const size_t off = (size_t)pl * GT_APLANE + (size_t)row * 16;
-        *reinterpret_cast<uint4*>(ah + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(ah + GT_AIMG + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      for (int i = 0; i < NV; ++i) {
+        uint32_t h0, l0, h1, l1;
+        split_bf16x2(v[i].x, v[i].y, h0, l0);
+        split_bf16x2(v[i].z, v[i].w, h1, l1);
+        *reinterpret_cast<uint2*>(ah + (size_t)i * 32) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(ah + GT_AIMG + (size_t)i * 32) = make_uint2(l0, l1);
       }
       fence_proxy_async();
       __syncwarp();

@@ -79,7 +79,7 @@ size_t lstm_workspace_floats(const LstmPack& p, int64_t n, int L) {
 __global__ void lstm_cell_step_kernel(const float* __restrict__ tmp, const float* __restrict__ pre,
                                       const int64_t* __restrict__ len, int n, int L, int h, int dirs, int dir, int step,
                                       float* __restrict__ hprev, float* __restrict__ cst, float* __restrict__ out,
-                                      float* __restrict__ h_n, float* __restrict__ c_n, int* err) {
+                                      float* __restrict__ h_n, float* __restrict__ c_n, int* err, float* __restrict__ c_seq) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)n * h) return;
   const int s = (int)(i / h), u = (int)(i - (int64_t)s * h);
@@ -101,6 +101,7 @@ __global__ void lstm_cell_step_kernel(const float* __restrict__ tmp, const float
     cst[i] = c;
     hprev[i] = hv;
     out[((size_t)s * L + t) * Hout + dir * h + u] = hv;
+    if (c_seq) c_seq[((size_t)s * L + t) * Hout + dir * h + u] = c;
   }
   if (step == L - 1) {
     if (h_n) h_n[((size_t)dir * n + s) * h + u] = hprev[i];
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(REC_THREADS) rnn_rec_kernel(const float* __res
                                                               const float* __restrict__ b_hn_all,
                                                               const int64_t* __restrict__ len, int n, int L, int h, int dirs,
                                                               float* __restrict__ out, float* __restrict__ h_n,
-                                                              float* __restrict__ c_n, int* err) {
+                                                              float* __restrict__ c_n, int* err, float* __restrict__ c_seq) {
   extern __shared__ __align__(16) float smem[];
   constexpr int NG = GRU ? 3 : 4;
   const int G = NG * h, hp = (h + 3) & ~3;
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(REC_THREADS) rnn_rec_kernel(const float* __res
           float c = fg * cst[i] + ig * gg;
           hv = og * tanhf(c);
           cst[i] = c;
+          if (c_seq) c_seq[((size_t)(s0 + s) * L + (dir ? l - 1 - step : step)) * Hout + dir * h + u] = c;
         }
         hprev[s * hp + u] = hv;
         int t = dir ? l - 1 - step : step;
@@ -425,18 +427,19 @@ static inline bool lstm_rec2_usable(const LstmPack& p) {
 
 template <bool WSMEM, bool GRU, int TS>
 static int32_t launch_rec(const LstmPack& p, const float* pre, const int64_t* len, int n, int L, float* out, float* h_n,
-                          float* c_n, int* err, size_t smem, cudaStream_t s) {
+                          float* c_n, int* err, size_t smem, cudaStream_t s, float* c_seq) {
   if (smem > 40 * 1024)  // static smem counts against the 48 KB default limit too
     CAIR_CUDA(cudaFuncSetAttribute(rnn_rec_kernel<WSMEM, GRU, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((n + TS - 1) / TS, p.dirs);
   CAIR_LAUNCH((rnn_rec_kernel<WSMEM, GRU, TS>), grid, REC_THREADS, smem, s, pre, p.w_hh_t, p.b_hn, len, n, L, p.h, p.dirs, out,
-              h_n, c_n, err);
+              h_n, c_n, err, c_seq);
   return CAIR_OK;
 }
 
 int32_t lstm_run(const LstmPack& p, const GemmA& x, const int64_t* len, int n, int L, float* out, float* h_n,
-                 float* c_n, float* ws_pre, int* err, cudaStream_t s, const char* rec_name) {
+                 float* c_n, float* ws_pre, int* err, cudaStream_t s, const char* rec_name, float* c_seq) {
   if (n <= 0) return CAIR_OK;
+  if (c_seq && p.gates != 4) return fail(CAIR_ERR_UNSUPPORTED, "rnn: a cell-state sequence exists for LSTM only");
   const int G = p.gates * p.h, PG = p.dirs * G;
   CAIR_TRY(gemm_auto(x, p.w_ih, p.w_ih_tc, p.bias, ws_pre, PG, (int64_t)n * L, PG, p.in, ACT_NONE, s));
   if (rec_name) prof_mark(rec_name, s);
@@ -455,7 +458,7 @@ int32_t lstm_run(const LstmPack& p, const GemmA& x, const int64_t* len, int n, i
         float* tmp_d = tmp + (size_t)d * n * G;
         CAIR_TRY(gemm_f32(gemm_dense(hp_d, h), p.w_hh + (size_t)d * G * h, nullptr, tmp_d, G, n, G, h, ACT_NONE, s));
         CAIR_LAUNCH(lstm_cell_step_kernel, blocks, 256, 0, s, tmp_d, ws_pre, len, n, L, h, p.dirs, d, step, hp_d,
-                    cst + (size_t)d * n * h, out, h_n, c_n, err);
+                    cst + (size_t)d * n * h, out, h_n, c_n, err, c_seq);
       }
     return CAIR_OK;
   }
@@ -466,12 +469,12 @@ int32_t lstm_run(const LstmPack& p, const GemmA& x, const int64_t* len, int n, i
   const bool wsmem = wbytes + state8 <= 200 * 1024;
   const bool gru = p.gates == 3;
   if (wsmem)
-    return gru ? launch_rec<true, true, 8>(p, ws_pre, len, n, L, out, h_n, c_n, err, state8 + wbytes, s)
-               : launch_rec<true, false, 8>(p, ws_pre, len, n, L, out, h_n, c_n, err, state8 + wbytes, s);
-  if (lstm_rec2_usable(p)) return launch_rec2(p, ws_pre, len, n, L, out, h_n, c_n, err, s);
+    return gru ? launch_rec<true, true, 8>(p, ws_pre, len, n, L, out, h_n, c_n, err, state8 + wbytes, s, c_seq)
+               : launch_rec<true, false, 8>(p, ws_pre, len, n, L, out, h_n, c_n, err, state8 + wbytes, s, c_seq);
+  if (lstm_rec2_usable(p) && !c_seq) return launch_rec2(p, ws_pre, len, n, L, out, h_n, c_n, err, s);
   (void)state16;  // TS = 16 measured slower (fewer CTAs in flight); the streamed path keeps 8 sequences per CTA
-  return gru ? launch_rec<false, true, 8>(p, ws_pre, len, n, L, out, h_n, c_n, err, state8, s)
-             : launch_rec<false, false, 8>(p, ws_pre, len, n, L, out, h_n, c_n, err, state8, s);
+  return gru ? launch_rec<false, true, 8>(p, ws_pre, len, n, L, out, h_n, c_n, err, state8, s, c_seq)
+             : launch_rec<false, false, 8>(p, ws_pre, len, n, L, out, h_n, c_n, err, state8, s, c_seq);
 }
 
 }  // namespace cair

@@ -166,6 +166,17 @@ struct AttnPack {
   float *w0 = nullptr, *b0 = nullptr, *w3 = nullptr, *b3 = nullptr;
   GemmTcW w0_tc;
 };
+// suggestion decoder (cars.py:605-657 weights, :706-791 greedy decode)
+struct CarsDecoder {
+  bool ready = false;
+  int Hdec = 0, Vt = 0;
+  float *th_w = nullptr, *th_b = nullptr, *tc_w = nullptr, *tc_b = nullptr;   // transform_hid / transform_cell [Hdec, Hs]
+  float *w_ih = nullptr, *w_hh = nullptr, *bias = nullptr;                     // decoder LSTM [4Hdec,E], [4Hdec,Hdec], b_ih+b_hh
+  float *attn_in = nullptr, *attn_out = nullptr;                               // GlobalAttention 'general' [Hdec,Hdec], [Hdec,2Hdec]
+  float *dec_attn = nullptr;                                                   // [Hdec,Hq]
+  float *pred1 = nullptr, *pred2 = nullptr;                                    // [Hd,Hdec], [Vt,Hd]
+  float *sess_proj2 = nullptr;                                                 // shared_session_projector + private_session_projector2 [Hd,Hs]
+};
 struct CarsState {
   int V = 0, E = 0, Hq = 0, Hd = 0, Hsq = 0, Hsd = 0;
   int rd[3] = {0, 0, 0}, pool = 2;
@@ -177,13 +188,24 @@ struct CarsState {
   float *qp_w = nullptr, *qp_b = nullptr;  // q_projection
   float* sess_proj = nullptr;              // shared_session_projector + private_session_projector1 [Hd, Hsq+Hsd]
   float *rk_w[3] = {nullptr, nullptr, nullptr}, *rk_b[3] = {nullptr, nullptr, nullptr};
+  float* shared_proj = nullptr;            // shared_session_projector alone (the decoder adds private_session_projector2 to it)
+  CarsDecoder dec;
 };
 struct CarsIO {
   const int64_t *q, *qlen, *d, *dlen;
   const float* labels;
   float *scores, *pooled_q, *pooled_d, *clicks, *sess_q_attn, *sess_d_attn;
+  // decoder-side outputs (optional): query memory banks [B*S,Lq,Hq]; (h, c) of the two session encoders after every
+  // query, concatenated [B,S,Hsq+Hsd] (query part first, cars.py:391-411)
+  float *enc_q = nullptr, *sess_h = nullptr, *sess_c = nullptr;
 };
 int32_t cars_create_state(Owned& own, const cair_cars_weights& w, CarsState* st, cudaStream_t s);
+int32_t cars_set_decoder(Owned& own, CarsState* st, const cair_cars_decoder_weights& w, cudaStream_t s);
+size_t cars_decode_workspace_bytes(const CarsState& st, int B, int S, int Lq);
+// greedy decode of the next-query suggestion for the rows (b, s < S-1); predictions [B, S-1, max_len] int64
+int32_t cars_decode(const CarsState& st, const float* enc_q, const int64_t* qlen, const float* sess_h, const float* sess_c,
+                    const float* sess_q_attn, const float* sess_d_attn, int B, int S, int Lq, int max_len, const int64_t* tgt2src,
+                    int64_t bos, int64_t* predictions, void* ws, size_t ws_bytes, int* err, cudaStream_t s);
 int32_t cars_forward(const CarsState& st, const CarsIO& io, int B, int S, int N, int Lq, int Ld, int sb, int sc,
                      Arena& ws, int* err, cudaStream_t s, bool dry);
 

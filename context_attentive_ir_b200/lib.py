@@ -56,6 +56,11 @@ PROTOTYPES = {
     'cair_cars_workspace_bytes': (i32, [vp, i32, i32, i32, i32, i32, C.POINTER(C.c_size_t)]),
     'cair_cars_forward': (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32,
                                 vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]),
+    'cair_cars_forward_ex': (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, C.POINTER(_abi.CarsOutputs),
+                                   vp, C.c_size_t, vp]),
+    'cair_cars_set_decoder': (i32, [vp, C.POINTER(_abi.CarsDecoderWeights)]),
+    'cair_cars_decode_workspace_bytes': (i32, [vp, i32, i32, i32, C.POINTER(C.c_size_t)]),
+    'cair_cars_decode': (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, i64, vp, vp, C.c_size_t, vp]),
 }
 
 

@@ -1,11 +1,13 @@
-"""Host-side mirror of the CARS ranking path (neuroir/multitask/cars.py, layers.py).
+"""Host-side mirror of CARS (neuroir/multitask/cars.py, layers.py): ranking path and greedy suggestion decoder.
 
-Keeps the reference's predict-time call sequence (neuroir/models/multitask.py:264-269):
+Keeps the reference's predict-time call sequence (neuroir/models/multitask.py:264-292):
     pooled, encoded, hidden = net.encode(source_words, source_lens)
     click_scores, states, session_attns = net.rank_document(pooled, document_words, document_lens, document_label)
-and the reference's parameter names (extra `.encoder.` / `embedder.` levels from layers.py), so a
-reference state_dict loads by key (strict=False: decoder-side keys are carried by the caller).
-The suggestion decoder (cars.py:605-657, :706-791) is out of scope (scope table row f.3).
+    out = net.decode(states=..., max_len=..., src_dict=..., tgt_dict=..., batch_size=..., session_len=..., use_cuda=...,
+                     encoded_source=..., source_len=..., session_attns=...)          # {'predictions': [B, S-1, max_len]}
+and the reference's parameter names (extra `.encoder.` / `embedder.` levels from layers.py; `decoder.decoder.rnn.*`,
+`decoder.decoder.attn.linear_{in,out}`), so a reference state_dict loads by key.  The arithmetic is in libcair.so
+(cair_cars_forward_ex, cair_cars_decode); there is no PyTorch fallback.
 """
 import ctypes as C
 from collections import OrderedDict
@@ -15,6 +17,8 @@ import torch.nn as nn
 
 from . import _abi, lib
 from .rankers import PAD, Embeddings, RNNEncoder, _CairModule
+
+BOS = 2   # neuroir/inputters/constants.py:3
 
 
 class Embedder(nn.Module):
@@ -53,6 +57,40 @@ class Maxout(nn.Module):
         self._output_dims, self._pool_sizes = output_dims, pool_sizes
 
 
+class _GeneralAttention(nn.Module):
+    """Parameters of GlobalAttention(attn_type='general') (modules/global_attention.py:59-96)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.linear_in = nn.Linear(dim, dim, bias=False)
+        self.linear_out = nn.Linear(dim * 2, dim, bias=False)
+
+
+class _RNNDecoder(nn.Module):
+    """Parameters of RNNDecoder (decoders/decoder.py:68-104): one LSTM layer + attention."""
+
+    def __init__(self, input_size, hidden_size):
+        super().__init__()
+        self.rnn = nn.LSTM(input_size=input_size, hidden_size=hidden_size, num_layers=1, batch_first=True)
+        self.attn = _GeneralAttention(hidden_size)
+
+
+class Decoder(nn.Module):
+    """neuroir/multitask/layers.py:57-93 (adds the `decoder.` level to the keys)."""
+
+    def __init__(self, input_size, nhid):
+        super().__init__()
+        self.decoder = _RNNDecoder(input_size, nhid)
+
+
+class _DecoderStates:
+    """What rank_document hands to decode() as `states`: the session encoders' (h, c) after every query; the
+    transform_hid / transform_cell projections of cars.py:440-453 are applied inside cair_cars_decode."""
+
+    def __init__(self, sess_h, sess_c):
+        self.sess_h, self.sess_c = sess_h, sess_c
+
+
 class CARS(_CairModule):
     """Ranking half of neuroir/multitask/cars.py (stock configuration: LSTM, bidirectional, one layer,
     attention pooling, both session encoders on - neuroir/hyparam.py:197-225)."""
@@ -85,7 +123,20 @@ class CARS(_CairModule):
         self.q_projection = _proj(args.nhid_query, args.nhid_document, args.dropout, True)
         self.private_session_projector1 = _proj(srs, args.nhid_document, args.dropout, False)
         self.ranknet = Maxout(args.nhid_document * 4, 3, [256, 128, 1], [2, 2, 2])
+        # decoder-side modules (cars.py:605-657): parameter containers, the decode loop runs in cair_cars_decode
+        self.has_decoder = not getattr(args, 'turn_recommender_off', False)
+        if self.has_decoder:
+            if getattr(args, 'attn_type', 'general') != 'general':
+                raise NotImplementedError('libcair implements the stock CARS decoder attention (attn_type general)')
+            self.private_session_projector2 = _proj(srs, args.nhid_document, args.dropout, False)
+            self.transform_hid = _proj(srs, args.nhid_decoder, args.dropout, True)
+            self.transform_cell = _proj(srs, args.nhid_decoder, args.dropout, True)
+            self.decoder = Decoder(args.emsize, args.nhid_decoder)
+            self.dec_attn = nn.Linear(args.nhid_query, args.nhid_decoder, bias=False)
+            self.token_prob_predictor1 = nn.Linear(args.nhid_decoder, args.nhid_document, bias=False)
+            self.token_prob_predictor2 = nn.Linear(args.nhid_document, args.tgt_vocab_size, bias=False)
         self._last = None
+        self._fwd = None
 
     def _cfg(self):
         a = self.args
@@ -96,9 +147,18 @@ class CARS(_CairModule):
     def _create(self, w, device, out):
         return lib.load().cair_cars_create(w, device, out)
 
-    def score(self, queries, query_len, docs, doc_len, doc_labels, session_slice=None, want_stages=False):
+    def _on_handle_created(self, handle):
+        if self.has_decoder:
+            keep = []
+            a = self.args
+            from .rankers import _ptr_getter
+            w = _abi.pack_cars_decoder(dict(nhid_decoder=a.nhid_decoder, tgt_vocab_size=a.tgt_vocab_size), _ptr_getter(self, keep))
+            lib.check(lib.load().cair_cars_set_decoder(handle, C.byref(w)))
+
+    def score(self, queries, query_len, docs, doc_len, doc_labels, session_slice=None, want_stages=False, want_decoder_inputs=False):
         """One fused call: q [B,S,Lq], qlen [B,S], d [B,S,N,Ld], dlen [B,S,N], labels [B,S,N] ->
-        dict(scores [B,S,N], + pooled_queries, pooled_docs, clicks, sess_q_attn, sess_d_attn if want_stages)."""
+        dict(scores [B,S,N], + pooled_queries, pooled_docs, clicks, sess_q_attn, sess_d_attn if want_stages,
+        + enc_q [B*S,Lq,Hq], sess_h / sess_c [B,S,Hsq+Hsd] if want_decoder_inputs)."""
         q = self._ids(queries, 'queries')
         d = self._ids(docs, 'docs')
         dev = q.device
@@ -121,41 +181,98 @@ class CARS(_CairModule):
                        sess_q_attn=torch.zeros(B, S, a.nhid_session_query, device=dev),
                        sess_d_attn=torch.zeros(B, S, a.nhid_session_document, device=dev))
 
+        if want_decoder_inputs:
+            hs = a.nhid_session_query + a.nhid_session_document
+            out.update(enc_q=torch.zeros(B * S, Lq, a.nhid_query, device=dev), sess_h=torch.zeros(B, S, hs, device=dev),
+                       sess_c=torch.zeros(B, S, hs, device=dev))
+
         def p(k):
-            return out[k].data_ptr() if k in out else None
+            return C.cast(out[k].data_ptr(), _abi.f32p) if k in out else None
         sb, sc = (0, B) if session_slice is None else session_slice
-        lib.check(L.cair_cars_forward(h, q.data_ptr(), ql.data_ptr(), d.data_ptr(), dl.data_ptr(), lab.data_ptr(),
-                                      B, S, N, Lq, Ld, sb, sc, out['scores'].data_ptr(), p('pooled_queries'),
-                                      p('pooled_docs'), p('clicks'), p('sess_q_attn'), p('sess_d_attn'),
-                                      ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+        outs = _abi.CarsOutputs(p('pooled_queries'), p('pooled_docs'), p('clicks'), p('sess_q_attn'), p('sess_d_attn'),
+                                p('enc_q'), p('sess_h'), p('sess_c'))
+        lib.check(L.cair_cars_forward_ex(h, q.data_ptr(), ql.data_ptr(), d.data_ptr(), dl.data_ptr(), lab.data_ptr(),
+                                         B, S, N, Lq, Ld, sb, sc, out['scores'].data_ptr(), C.byref(outs),
+                                         ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
         return out
 
     # -- the reference's two-call predict sequence (models/multitask.py:264-269) ------------------
     def encode(self, queries, query_length):
         """Defers the work: the fused kernel sequence runs in rank_document, which needs the documents.
-        Returns (token, None, None); `token` stands in for pooled_rep and is only meaningful to
-        rank_document (the decoder-side encoded_rep / hidden outputs are out of scope)."""
+        Returns (token, token, None): the tokens stand in for pooled_rep / encoded_source and are resolved by
+        rank_document() / decode() (the query memory banks are an output of the same fused forward)."""
         self._last = (queries, query_length)
-        return ('cair-deferred', id(self)), None, None
+        tok = ('cair-deferred', id(self))
+        return tok, tok, None
 
     def rank_document(self, pooled_rep, document_rep, document_len, document_label):
         if self._last is None:
             raise RuntimeError('rank_document() must follow encode() (models/multitask.py:264-269)')
         queries, qlen = self._last
         self._last = None
-        out = self.score(queries, qlen, document_rep, document_len, document_label, want_stages=True)
-        return out['scores'], None, (out['sess_q_attn'], out['sess_d_attn'])
+        out = self.score(queries, qlen, document_rep, document_len, document_label, want_stages=True,
+                         want_decoder_inputs=self.has_decoder)
+        self._fwd = out
+        states = _DecoderStates(out['sess_h'], out['sess_c']) if self.has_decoder else None
+        return out['scores'], states, (out['sess_q_attn'], out['sess_d_attn'])
+
+    def _tgt2src(self, tgt_dict, src_dict, device):
+        """Target-vocabulary id -> source-vocabulary id of the same word: the per-step tgt_dict[idx] -> src_dict[word]
+        round trip of cars.py:780-783 as one lookup table (cached per dictionary pair)."""
+        key = (id(tgt_dict), id(src_dict), len(tgt_dict), str(device))
+        cache = self.__dict__.get('_tgt2src_cache')
+        if cache is None or cache[0] != key:
+            m = torch.tensor([int(src_dict[tgt_dict[i]]) for i in range(len(tgt_dict))], dtype=torch.int64)
+            if m.numel() < self.args.tgt_vocab_size:   # ids the dictionary does not hold cannot be mapped (the reference raises)
+                m = torch.cat([m, torch.full((self.args.tgt_vocab_size - m.numel(),), 1, dtype=torch.int64)])   # UNK
+            cache = (key, m.to(device))
+            self.__dict__['_tgt2src_cache'] = cache
+        return cache[1]
+
+    def decode(self, states, max_len, src_dict, tgt_dict, batch_size, session_len, use_cuda=True, encoded_source=None,
+               source_len=None, session_attns=None, **_):
+        """Greedy suggestion decode (cars.py:706-791): `session_len` is the number of decoded queries per session (S - 1);
+        returns {'predictions': LongTensor [batch_size, session_len, max_len]} of target-vocabulary ids."""
+        if not self.has_decoder:
+            raise RuntimeError('this CARS was built with turn_recommender_off: there is no decoder')
+        fwd = self._fwd
+        if fwd is None or not isinstance(states, _DecoderStates):
+            raise RuntimeError('decode() must follow rank_document() (models/multitask.py:264-292)')
+        enc_q = fwd['enc_q'] if not torch.is_tensor(encoded_source) else encoded_source.contiguous()
+        dev = enc_q.device
+        B, S = states.sess_h.shape[0], states.sess_h.shape[1]
+        assert batch_size == B and session_len == S - 1
+        Lq = enc_q.shape[1]
+        qlen = self._ids(source_len, 'source_len').to(dev).reshape(B, S)
+        sqa, sda = session_attns
+        L = lib.load()
+        h = self._handle_for(dev)
+        nbytes = C.c_size_t()
+        lib.check(L.cair_cars_decode_workspace_bytes(h, B, S, Lq, C.byref(nbytes)))
+        ws = self.__dict__.get('_cair_dec_ws')
+        if ws is None or ws.numel() < nbytes.value or ws.device != dev:
+            ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=dev)
+            self.__dict__['_cair_dec_ws'] = ws
+        preds = torch.zeros(B, S - 1, max_len, dtype=torch.int64, device=dev)
+        t2s = self._tgt2src(tgt_dict, src_dict, dev)
+        lib.check(L.cair_cars_decode(h, enc_q.data_ptr(), qlen.data_ptr(), states.sess_h.data_ptr(), states.sess_c.data_ptr(),
+                                     sqa.contiguous().data_ptr(), sda.contiguous().data_ptr(), B, S, Lq, max_len, t2s.data_ptr(),
+                                     BOS, preds.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+        return {'predictions': preds}
 
 
-# decoder-side parameters of the reference CARS (suggestion path, out of scope here)
+
+# decoder-side parameters of the reference CARS: real parameters of this module unless it was built with
+# turn_recommender_off, in which case a checkpoint that still holds them is carried through untouched
 DECODER_PREFIXES = ('decoder.', 'token_prob_predictor', 'dec_attn', 'transform_', 'private_session_projector2')
 
 
 def _carry_load_state_dict(self, state_dict, strict=True, **kw):
-    """nn.Module.load_state_dict for a reference checkpoint: the decoder-side tensors (suggestion path) are not parameters
-    of this module; they are kept untouched and handed back by state_dict(), so a checkpoint loaded and saved through the
-    reference's Multitask wrapper (models/multitask.py:49-58, 330-352) keeps every key."""
-    carried = {k: v for k, v in state_dict.items() if k.startswith(DECODER_PREFIXES)}
+    """nn.Module.load_state_dict for a reference checkpoint: decoder-side tensors this module has no parameter for are
+    kept untouched and handed back by state_dict(), so a checkpoint loaded and saved through the reference's Multitask
+    wrapper (models/multitask.py:49-58, 330-352) keeps every key."""
+    own = set(nn.Module.state_dict(self).keys())
+    carried = {k: v for k, v in state_dict.items() if k.startswith(DECODER_PREFIXES) and k not in own}
     mine = {k: v for k, v in state_dict.items() if k not in carried}
     out = nn.Module.load_state_dict(self, mine, strict=strict, **kw)
     self.__dict__['_carried_decoder_state'] = carried

@@ -360,6 +360,47 @@ CAIR_API int32_t cair_cars_forward(cair_handle* h, const int64_t* q, const int64
                           float* sess_q_attn, float* sess_d_attn, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+
+/* Optional outputs of the CARS forward beyond the scores (any pointer may be NULL): the stage outputs of
+ * cair_cars_forward plus what the suggestion decoder starts from - enc_q [B*S,Lq,Hq] the query memory banks
+ * (`encoded_source` of CARS.encode, cars.py:214-225), sess_h / sess_c [B,S,Hsq+Hsd] the (h, c) of the session query
+ * and session document encoders after every query, query part first (cars.py:391-411). */
+typedef struct {
+  float *pooled_q, *pooled_d, *clicks, *sess_q_attn, *sess_d_attn;
+  float *enc_q, *sess_h, *sess_c;
+} cair_cars_outputs;
+CAIR_API int32_t cair_cars_forward_ex(cair_handle* h, const int64_t* q, const int64_t* qlen, const int64_t* d,
+                             const int64_t* dlen, const float* labels, int32_t B, int32_t S, int32_t N,
+                             int32_t Lq, int32_t Ld, int32_t session_begin, int32_t session_count,
+                             float* scores, const cair_cars_outputs* outs, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* ---- CARS query-suggestion decoder ------------------------------------
+ * Weights of the decoder-side modules (neuroir/multitask/cars.py:605-657): transform_{hid,cell}.linear
+ * [Hdec,Hsq+Hsd] + bias; decoder.decoder.rnn (nn.LSTM: weight_ih_l0 [4Hdec,E], weight_hh_l0 [4Hdec,Hdec], biases);
+ * decoder.decoder.attn.linear_in [Hdec,Hdec] / linear_out [Hdec,2Hdec] (GlobalAttention 'general', no biases);
+ * dec_attn [Hdec,Hq]; token_prob_predictor1 [Hd,Hdec]; token_prob_predictor2 [Vt,Hd];
+ * private_session_projector2.linear [Hd,Hsq+Hsd] (all without bias).  Copied into the handle. */
+typedef struct {
+  int32_t nhid_decoder, tgt_vocab;
+  cair_linear transform_hid, transform_cell;
+  cair_lstm_dir rnn;
+  cair_linear attn_in, attn_out, dec_attn, predictor1, predictor2, private_session_projector2;
+} cair_cars_decoder_weights;
+CAIR_API int32_t cair_cars_set_decoder(cair_handle* h, const cair_cars_decoder_weights* w);
+CAIR_API int32_t cair_cars_decode_workspace_bytes(cair_handle* h, int32_t B, int32_t S, int32_t Lq, size_t* bytes);
+/* CARS.decode (cars.py:706-791; called by Multitask.predict, models/multitask.py:281-292): greedy decode of max_len
+ * tokens of the next query for every (session b, query s < S-1) row, starting from BOS.  Inputs are the outputs of
+ * cair_cars_forward_ex (device pointers) and qlen [B,S]; tgt2src [Vt] int64 maps a target-vocabulary id to the
+ * source-vocabulary id of the same word (the tgt_dict[idx] -> src_dict[word] round trip of cars.py:780-783).
+ * predictions [B,S-1,max_len] int64 (target-vocabulary ids).  The reference's row orderings are reproduced as they
+ * are (initial states query-index-major, memory banks / session summaries / predictions batch-major).
+ * Enqueued on `stream`; nothing is synchronised. */
+CAIR_API int32_t cair_cars_decode(cair_handle* h, const float* enc_q, const int64_t* qlen, const float* sess_h,
+                         const float* sess_c, const float* sess_q_attn, const float* sess_d_attn, int32_t B,
+                         int32_t S, int32_t Lq, int32_t max_len, const int64_t* tgt2src, int64_t bos_id,
+                         int64_t* predictions, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

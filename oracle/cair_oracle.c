@@ -482,7 +482,7 @@ static void attn_pool(const float* enc, int L, int H, int len, const cair_attn_m
 /* embed + BiLSTM + attention pooling over n sequences (cars.py:193-225 / :227-260) */
 static int cars_encode(const cair_cars_weights* w, const int64_t* ids, const int64_t* len, int n,
                        int L, int H, const cair_lstm_dir* fwd, const cair_lstm_dir* rev,
-                       const cair_attn_mlp* attn, float* pooled) {
+                       const cair_attn_mlp* attn, float* pooled, float* bank_out) {
   int E = w->emsize;
   float* x = (float*)malloc(sizeof(float) * (size_t)n * L * E);
   float* enc = (float*)malloc(sizeof(float) * (size_t)n * L * H);
@@ -493,6 +493,7 @@ static int cars_encode(const cair_cars_weights* w, const int64_t* ids, const int
     for (int s = 0; s < n; ++s)
       attn_pool(enc + (size_t)s * L * H, L, H, (int)len[s], attn, pooled + (size_t)s * H);
   }
+  if (rc == CAIR_OK && bank_out) memcpy(bank_out, enc, sizeof(float) * (size_t)n * L * H);
   free(x);
   free(enc);
   return rc;
@@ -527,11 +528,28 @@ static void maxout_layer(const float* x, int in, const cair_linear* l, int out, 
   }
 }
 
+ORA_API int cair_oracle_cars_ex(const cair_cars_weights* w, const int64_t* q, const int64_t* qlen,
+                                const int64_t* d, const int64_t* dlen, const float* labels, int B,
+                                int S, int N, int Lq, int Ld, float* scores, float* pooled_q_out,
+                                float* pooled_d_out, float* clicks_out, float* sess_q_attn_out,
+                                float* sess_d_attn_out, float* enc_q_out, float* sess_h_out, float* sess_c_out);
+
 ORA_API int cair_oracle_cars(const cair_cars_weights* w, const int64_t* q, const int64_t* qlen,
                              const int64_t* d, const int64_t* dlen, const float* labels, int B,
                              int S, int N, int Lq, int Ld, float* scores, float* pooled_q_out,
                              float* pooled_d_out, float* clicks_out, float* sess_q_attn_out,
                              float* sess_d_attn_out) {
+  return cair_oracle_cars_ex(w, q, qlen, d, dlen, labels, B, S, N, Lq, Ld, scores, pooled_q_out, pooled_d_out, clicks_out,
+                             sess_q_attn_out, sess_d_attn_out, NULL, NULL, NULL);
+}
+
+/* Same with the decoder-side outputs: enc_q [B*S,Lq,Hq] query memory banks (cars.py:214-225), sess_h / sess_c
+ * [B,S,Hsq+Hsd] the (h, c) of both session encoders after every query, query part first (cars.py:391-411). */
+ORA_API int cair_oracle_cars_ex(const cair_cars_weights* w, const int64_t* q, const int64_t* qlen,
+                                const int64_t* d, const int64_t* dlen, const float* labels, int B,
+                                int S, int N, int Lq, int Ld, float* scores, float* pooled_q_out,
+                                float* pooled_d_out, float* clicks_out, float* sess_q_attn_out,
+                                float* sess_d_attn_out, float* enc_q_out, float* sess_h_out, float* sess_c_out) {
   int Hq = w->nhid_query, Hd = w->nhid_document, Hsq = w->nhid_session_query,
       Hsd = w->nhid_session_document;
   int BS = B * S;
@@ -540,9 +558,9 @@ ORA_API int cair_oracle_cars(const cair_cars_weights* w, const int64_t* q, const
   float* pq = (float*)malloc(sizeof(float) * (size_t)BS * Hq);
   float* pd = (float*)malloc(sizeof(float) * (size_t)BS * N * Hd);
   float* clk = (float*)malloc(sizeof(float) * (size_t)BS * Hd);
-  int rc = cars_encode(w, q, qlen, BS, Lq, Hq, &w->query_fwd, &w->query_rev, &w->q_attn, pq);
+  int rc = cars_encode(w, q, qlen, BS, Lq, Hq, &w->query_fwd, &w->query_rev, &w->q_attn, pq, enc_q_out);
   if (rc == CAIR_OK)
-    rc = cars_encode(w, d, dlen, BS * N, Ld, Hd, &w->doc_fwd, &w->doc_rev, &w->d_attn, pd);
+    rc = cars_encode(w, d, dlen, BS * N, Ld, Hd, &w->doc_fwd, &w->doc_rev, &w->d_attn, pd, NULL);
   if (rc != CAIR_OK) {
     free(pq);
     free(pd);
@@ -660,6 +678,14 @@ ORA_API int cair_oracle_cars(const cair_cars_weights* w, const int64_t* q, const
       memcpy(Q + (size_t)(s + 1) * Hsq, hq, sizeof(float) * Hsq);
       lstm_step(clk + ((size_t)b * S + s) * Hd, Hd, Hsd, &w->session_doc, hdn, cds, gd);
       memcpy(D + (size_t)(s + 1) * Hsd, hdn, sizeof(float) * Hsd);
+      if (sess_h_out) {
+        memcpy(sess_h_out + ((size_t)b * S + s) * Hs, hq, sizeof(float) * Hsq);
+        memcpy(sess_h_out + ((size_t)b * S + s) * Hs + Hsq, hdn, sizeof(float) * Hsd);
+      }
+      if (sess_c_out) {
+        memcpy(sess_c_out + ((size_t)b * S + s) * Hs, cqs, sizeof(float) * Hsq);
+        memcpy(sess_c_out + ((size_t)b * S + s) * Hs + Hsq, cds, sizeof(float) * Hsd);
+      }
       /* inner attention over states 1..s+1 (:385-389, :407-411) - decoder-side outputs */
       if (sess_q_attn_out) {
         for (int k = 0; k < ns; ++k) {
@@ -691,6 +717,77 @@ ORA_API int cair_oracle_cars(const cair_cars_weights* w, const int64_t* q, const
   free(pq);
   free(pd);
   free(clk);
+  return CAIR_OK;
+}
+
+/* CARS.decode (multitask/cars.py:706-791): greedy decode of max_len tokens for every (b, s < S-1) row.
+ * decoders/rnn_decoder.py:19-90: one nn.LSTM step from the carried state (decoders/decoder.py:118-155 updates the
+ * state object in place on every call), GlobalAttention 'general' (modules/global_attention.py:121-211: align = (W_in h) m,
+ * masked beyond the memory length, softmax, context, tanh(W_out [context; h])), then token_prob_predictor1, the session
+ * summary (shared_session_projector + private_session_projector2), token_prob_predictor2, softmax, arg-max (cars.py:761-775),
+ * and the target-id -> source-id map for the next input (:780-783).  Row orderings as in the reference: initial states
+ * row i = s*B + b (torch.cat(hidden_states[:-1], dim=1), :440-453); memory banks, lengths, session summaries and
+ * predictions row i = b*(S-1) + s (:724-731, :747-757, :786). */
+ORA_API int cair_oracle_cars_decode(const cair_cars_weights* w, const cair_cars_decoder_weights* dw, const float* enc_q,
+                                    const int64_t* qlen, const float* sess_h, const float* sess_c, const float* sqa,
+                                    const float* sda, int B, int S, int Lq, int max_len, const int64_t* tgt2src,
+                                    int64_t bos, int64_t* predictions) {
+  const int Hq = w->nhid_query, Hd = w->nhid_document, Hsq = w->nhid_session_query, Hsd = w->nhid_session_document;
+  const int Hs = Hsq + Hsd, H = dw->nhid_decoder, Vt = dw->tgt_vocab, E = w->emsize;
+  const int R = B * (S - 1);
+  if (S < 2) return CAIR_OK;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int i = 0; i < R; ++i) {
+    const int s1 = i / B, b1 = i % B;            /* state rows */
+    const int b2 = i / (S - 1), s2 = i % (S - 1); /* memory / summary rows */
+    float* buf = (float*)malloc(sizeof(float) * ((size_t)2 * H + (size_t)Lq * H + Hs + Hd + 4 * H + H + Lq + 2 * H + H + Hd + Vt));
+    float *hs = buf, *cs = hs + H, *mb = cs + H, *sum = mb + (size_t)Lq * H, *sess = sum + Hs, *gates = sess + Hd,
+          *hq = gates + 4 * H, *al = hq + H, *cat = al + Lq, *ah = cat + 2 * H, *o1 = ah + H, *logit = o1 + Hd;
+    const float* h0 = sess_h + ((size_t)b1 * S + s1) * Hs;
+    const float* c0 = sess_c + ((size_t)b1 * S + s1) * Hs;
+    for (int o = 0; o < H; ++o) {
+      hs[o] = dotf(h0, dw->transform_hid.w + (size_t)o * Hs, Hs) + dw->transform_hid.b[o];
+      cs[o] = dotf(c0, dw->transform_cell.w + (size_t)o * Hs, Hs) + dw->transform_cell.b[o];
+    }
+    const float* bank = enc_q + ((size_t)b2 * S + s2) * Lq * Hq;
+    for (int t = 0; t < Lq; ++t)
+      for (int o = 0; o < H; ++o) mb[(size_t)t * H + o] = dotf(bank + (size_t)t * Hq, dw->dec_attn.w + (size_t)o * Hq, Hq);
+    int ml = (int)qlen[b2 * S + s2];
+    for (int k = 0; k < Hs; ++k) sum[k] = k < Hsq ? sqa[((size_t)b2 * S + s2) * Hsq + k] : sda[((size_t)b2 * S + s2) * Hsd + (k - Hsq)];
+    for (int o = 0; o < Hd; ++o)
+      sess[o] = dotf(sum, w->shared_session_projector.w + (size_t)o * Hs, Hs) +
+                dotf(sum, dw->private_session_projector2.w + (size_t)o * Hs, Hs);
+    int64_t tok = bos;
+    for (int t = 0; t < max_len; ++t) {
+      lstm_step(w->table + (size_t)tok * E, E, H, &dw->rnn, hs, cs, gates);
+      for (int o = 0; o < H; ++o) hq[o] = dotf(hs, dw->attn_in.w + (size_t)o * H, H);
+      float mx = -INFINITY, den = 0.0f;
+      for (int p = 0; p < ml; ++p) {
+        al[p] = dotf(hq, mb + (size_t)p * H, H);
+        if (al[p] > mx) mx = al[p];
+      }
+      for (int p = 0; p < ml; ++p) {
+        al[p] = expf(al[p] - mx);
+        den += al[p];
+      }
+      for (int o = 0; o < H; ++o) {
+        double a = 0.0;
+        for (int p = 0; p < ml; ++p) a += (double)(al[p] / den) * (double)mb[(size_t)p * H + o];
+        cat[o] = (float)a;
+        cat[H + o] = hs[o];
+      }
+      for (int o = 0; o < H; ++o) ah[o] = tanhf(dotf(cat, dw->attn_out.w + (size_t)o * 2 * H, 2 * H));
+      for (int o = 0; o < Hd; ++o) o1[o] = dotf(ah, dw->predictor1.w + (size_t)o * H, H) + sess[o];
+      int best = 0;
+      for (int v = 0; v < Vt; ++v) {
+        logit[v] = dotf(o1, dw->predictor2.w + (size_t)v * Hd, Hd);
+        if (logit[v] > logit[best]) best = v;
+      }
+      predictions[(size_t)i * max_len + t] = best;
+      tok = tgt2src[best];
+    }
+    free(buf);
+  }
   return CAIR_OK;
 }
 

@@ -155,7 +155,20 @@ def gen_arc(name, seed, B, N, Lq, Ld, E, V, two, **arch):
 
 
 # ------------------------------------------------------------------ Match-Tensor
-def gen_mt(name, seed, B, N, Lq, Ld, E, V, F, Hq, Hd, C, nf, mfs, rnn_type='LSTM', **kw):
+def _ref_metrics(scores, labels):
+    """MAP / MRR / P@1,3,5 of model scores exactly as the reference's evaluation loops compute them (main/ranker.py:257-264,
+    main/multitask.py:286-293): softmax over the candidates, np.argsort(-scores), neuroir.eval.ltorank."""
+    import torch.nn.functional as f
+    from neuroir.eval.ltorank import MAP, MRR, precision_at_k
+    probs = f.softmax(scores.reshape(-1, scores.shape[-1]), dim=-1).numpy()
+    lab = np.asarray(labels).reshape(-1, scores.shape[-1]).astype(np.int64)
+    pred = np.argsort(-probs)
+    return dict(metric_map=np.float64(MAP(pred, lab)), metric_mrr=np.float64(MRR(pred, lab)),
+                metric_p1=np.float64(precision_at_k(pred, lab, 1)), metric_p3=np.float64(precision_at_k(pred, lab, 3)),
+                metric_p5=np.float64(precision_at_k(pred, lab, 5)))
+
+
+def gen_mt(name, seed, B, N, Lq, Ld, E, V, F, Hq, Hd, C, nf, mfs, rnn_type='LSTM', metrics=False, **kw):
     from neuroir.rankers.mtensor import MatchTensor
     torch.manual_seed(1013)
     cfg = dict(model='match_tensor', emsize=E, src_vocab_size=V, dropout_emb=0.2, rnn_type=rnn_type,
@@ -171,7 +184,10 @@ def gen_mt(name, seed, B, N, Lq, Ld, E, V, F, Hq, Hd, C, nf, mfs, rnn_type='LSTM
         xq = net.linear_projection(net.word_embeddings(t['q'].unsqueeze(2)))
         _, hq = net.query_encoder(xq, t['qlen'])
         _, hd = net.document_encoder(xd, t['dlen'].reshape(-1))
-    _save(name, cfg, batch, net, dict(scores=s, proj_docs=xd, enc_queries=hq, enc_docs=hd))
+    outs = dict(scores=s, proj_docs=xd, enc_queries=hq, enc_docs=hd)
+    if metrics:
+        outs = dict(scores=s, **_ref_metrics(s, batch['label']))
+    _save(name, cfg, batch, net, outs)
 
 
 # ------------------------------------------------------------------ DRMM
@@ -204,7 +220,7 @@ def gen_duet(name, seed, B, N, Lq, Ld, E, V, nf, pool=5, **kw):
 
 
 # ------------------------------------------------------------------ CARS (ranking path)
-def gen_cars(name, seed, B, S, N, Lq, Ld, E, V, Hq, Hd, Hs, max_clicks=1, **kw):
+def gen_cars(name, seed, B, S, N, Lq, Ld, E, V, Hq, Hd, Hs, max_clicks=1, metrics=False, **kw):
     from neuroir.multitask.cars import CARS
     torch.manual_seed(1013)
     cfg = dict(model='cars', emsize=E, src_vocab_size=V, tgt_vocab_size=50, dropout_emb=0.2, dropout=0.2,
@@ -217,20 +233,30 @@ def gen_cars(name, seed, B, S, N, Lq, Ld, E, V, Hq, Hd, Hs, max_clicks=1, **kw):
     net = CARS(_ns(**{k: v for k, v in cfg.items() if k != 'model'})).eval()
     batch = synth.session_batch(seed, B, S, N, Lq, Ld, V, max_clicks=max_clicks, **kw)
     t = _t(batch)
+    # dictionaries of the decode loop (cars.py:774-783: tgt_dict[idx] -> word -> src_dict[word]); the target word i maps
+    # to an arbitrary fixed source id
+    rng = np.random.RandomState(seed)
+    tgt2src = rng.randint(4, V, size=cfg['tgt_vocab_size']).astype(np.int64)
+    tgt2src[:4] = np.arange(4)
+    tgt_dict = ['w%d' % i for i in range(cfg['tgt_vocab_size'])]
+    src_dict = {'w%d' % i: int(tgt2src[i]) for i in range(cfg['tgt_vocab_size'])}
+    max_len = 6
     with torch.no_grad():
         pooled, enc_src, _ = net.encode(t['q'], t['qlen'])
         pooled_docs = net.encode_document(t['d'], t['dlen'])
         clicks = net.encode_clicks(pooled_docs, t['label'])
         scores, states, sess_attn = net.rank_document(pooled, t['d'], t['dlen'], t['label'])
-    # decoder-side weights are not on the scoring path: drop them to keep fixtures small
-    sd = {k: v for k, v in net.state_dict().items()
-          if not k.startswith(('decoder.', 'token_prob_predictor', 'dec_attn', 'transform_'))}
-
-    class _SD:
-        def state_dict(self):
-            return sd
-    _save(name, cfg, batch, _SD(), dict(scores=scores, pooled_queries=pooled, pooled_docs=pooled_docs,
-                                        clicks=clicks, sess_q_attn=sess_attn[0], sess_d_attn=sess_attn[1]))
+        dec = net.decode(states=states, max_len=max_len, src_dict=src_dict, tgt_dict=tgt_dict, batch_size=B,
+                         session_len=S - 1, use_cuda=False, encoded_source=enc_src, source_len=t['qlen'],
+                         session_attns=sess_attn)
+    batch = dict(batch, tgt2src=tgt2src)
+    if metrics:
+        _save(name, cfg, batch, net, dict(scores=scores, predictions=dec['predictions'], **_ref_metrics(scores, batch['label'])))
+        return
+    _save(name, cfg, batch, net, dict(scores=scores, pooled_queries=pooled, pooled_docs=pooled_docs,
+                                      clicks=clicks, sess_q_attn=sess_attn[0], sess_d_attn=sess_attn[1],
+                                      encoded_source=enc_src, dec_h0=states[0], dec_c0=states[1],
+                                      predictions=dec['predictions']))
 
 
 # ------------------------------------------------------------------ ranking metrics (eval/ltorank.py)
@@ -323,6 +349,9 @@ def main():
            mfs=20, variable=False)
     gen_mt('mt_gru', 25, B=2, N=3, Lq=9, Ld=31, E=32, V=150, F=12, Hq=20, Hd=28, C=10, nf=6, mfs=8, rnn_type='GRU',
            bos_eos=True, overlap=0.15)
+    # >= 64 queries with the reference's own MAP / MRR / P@k of the reference scores (metric parity of model scores)
+    gen_mt('mt_map64', 27, B=64, N=10, Lq=8, Ld=24, E=32, V=300, F=8, Hq=16, Hd=24, C=10, nf=6, mfs=8, bos_eos=True,
+           overlap=0.1, metrics=True)
     # DRMM: strict (disjoint ids) and overlapping (bin-edge cells excluded by the test using out/cos)
     gen_drmm('drmm_strict', 1237, B=3, N=4, Lq=20, Ld=200, E=300, V=400, disjoint=True)
     gen_drmm('drmm_overlap', 32, B=2, N=3, Lq=12, Ld=60, E=64, V=300, bos_eos=True, overlap=0.1)
@@ -355,6 +384,10 @@ def main():
     gen_cars('cars_clicks', 52, B=3, S=4, N=5, Lq=8, Ld=30, E=32, V=200, Hq=32, Hd=32, Hs=48, max_clicks=3)
     gen_cars('cars_mid', 1238, B=2, S=7, N=10, Lq=20, Ld=200, E=300, V=400, Hq=64, Hd=64, Hs=96,
              max_clicks=2)
+    # stock encoder sizes (256 = 128 per direction: the 4-CTA cluster recurrence) at a batch where the click-mask width m = 3 > 1 matters at scale, with a few rows of one
+    # click next to rows of three
+    gen_cars('cars_map70', 1245, B=10, S=7, N=10, Lq=6, Ld=16, E=24, V=200, Hq=16, Hd=16, Hs=24, max_clicks=2, metrics=True)
+    gen_cars('cars_h256', 1244, B=4, S=7, N=10, Lq=20, Ld=60, E=64, V=500, Hq=256, Hd=256, Hs=128, max_clicks=3)
 
 
 if __name__ == '__main__':

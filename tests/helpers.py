@@ -17,9 +17,6 @@ def namespace(cfg):
 def build_module(cfg, sd=None, device=None):
     net = CLASSES[cfg['model']](namespace(cfg)).eval()
     if sd is not None:
-        if cfg['model'] == 'cars':
-            from context_attentive_ir_b200.multitask import ranking_state_dict
-            sd = ranking_state_dict(sd)
         missing, unexpected = net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()},
                                                    strict=False)
         assert not missing, missing

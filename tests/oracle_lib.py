@@ -97,6 +97,22 @@ def run_ranker(cfg, sd, q, qlen, d, dlen, want=()):
     return out
 
 
+def run_cars_decode(cfg, sd, fwd, qlen, max_len, tgt2src, bos=2):
+    """Oracle greedy decode from the outputs of run_cars (enc_q, sess_h, sess_c, sess_q_attn, sess_d_attn)."""
+    L = lib()
+    w = _abi.pack_cars(cfg, host_getter(sd))
+    dw = _abi.pack_cars_decoder(cfg, host_getter(sd))
+    B, S = fwd['sess_h'].shape[:2]
+    Lq = fwd['enc_q'].shape[1]
+    ql_, qlp = _i64(qlen)
+    t2s, t2sp = _i64(tgt2src)
+    pred = np.zeros((B, S - 1, max_len), np.int64)
+    _check(L.cair_oracle_cars_decode(C.byref(w), C.byref(dw), _f32(fwd['enc_q']), qlp, _f32(fwd['sess_h']), _f32(fwd['sess_c']),
+                                     _f32(fwd['sess_q_attn']), _f32(fwd['sess_d_attn']), B, S, Lq, max_len, t2sp, C.c_int64(bos),
+                                     pred.ctypes.data_as(_abi.i64p)), 'cars_decode')
+    return pred
+
+
 def run_cars(cfg, sd, q, qlen, d, dlen, label):
     L = lib()
     w = _abi.pack_cars(cfg, host_getter(sd))
@@ -112,9 +128,13 @@ def run_cars(cfg, sd, q, qlen, d, dlen, label):
                pooled_docs=np.zeros((B, S, N, Hd), np.float32), clicks=np.zeros((B, S, Hd), np.float32),
                sess_q_attn=np.zeros((B, S, cfg['nhid_session_query']), np.float32),
                sess_d_attn=np.zeros((B, S, cfg['nhid_session_document']), np.float32))
-    _check(L.cair_oracle_cars(C.byref(w), qp, qlp, dp, dlp, _f32(lab), B, S, N, Lq, Ld, _f32(out['scores']),
-                              _f32(out['pooled_queries']), _f32(out['pooled_docs']), _f32(out['clicks']),
-                              _f32(out['sess_q_attn']), _f32(out['sess_d_attn'])), 'cars')
+    hs = cfg['nhid_session_query'] + cfg['nhid_session_document']
+    out.update(enc_q=np.zeros((B * S, Lq, Hq), np.float32), sess_h=np.zeros((B, S, hs), np.float32),
+               sess_c=np.zeros((B, S, hs), np.float32))
+    _check(L.cair_oracle_cars_ex(C.byref(w), qp, qlp, dp, dlp, _f32(lab), B, S, N, Lq, Ld, _f32(out['scores']),
+                                 _f32(out['pooled_queries']), _f32(out['pooled_docs']), _f32(out['clicks']),
+                                 _f32(out['sess_q_attn']), _f32(out['sess_d_attn']), _f32(out['enc_q']), _f32(out['sess_h']),
+                                 _f32(out['sess_c'])), 'cars')
     return out
 
 

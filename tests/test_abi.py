@@ -46,10 +46,8 @@ def test_state_dict_keys_and_shapes_match_reference(name):
     cfg, _, sd, _ = ol.load_golden(name)
     net = helpers.build_module(cfg)
     mine = net.state_dict()
-    if cfg['model'] == 'cars':  # decoder-side keys (suggestion path) are carried by the caller, not this module
-        from context_attentive_ir_b200.multitask import ranking_state_dict
-        assert len(ranking_state_dict(sd)) < len(sd)
-        sd = ranking_state_dict(sd)
+    if cfg['model'] == 'cars':  # the suggestion-decoder keys are real parameters too (cars.py:605-657)
+        assert any(k.startswith('decoder.decoder.rnn.') for k in sd) and 'token_prob_predictor2.weight' in sd
     assert sorted(mine) == sorted(sd)
     for k in sd:
         assert tuple(mine[k].shape) == tuple(sd[k].shape), k

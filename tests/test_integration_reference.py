@@ -75,8 +75,8 @@ def test_reference_wrapper_builds_b200_networks_and_round_trips_mdl(name, tmp_pa
 
 def test_reference_multitask_wrapper_builds_b200_cars_and_keeps_decoder_keys(tmp_path):
     """CARS under the reference's Multitask wrapper: the FULL reference state_dict (ranking + suggestion-decoder keys)
-    loads through the wrapper's strict load_state_dict, the ranking tensors land in the B200 module, and the decoder-side
-    tensors are carried through unchanged into the next save()."""
+    loads through the wrapper's strict load_state_dict into real parameters of the B200 module and comes back unchanged
+    from the next save(); predict() reaches the B200 module's encode / rank_document / decode (which refuse CPU tensors)."""
     _import_reference()
     import importlib
     import neuroir.models.multitask as ref_mt
@@ -101,7 +101,8 @@ def test_reference_multitask_wrapper_builds_b200_cars_and_keeps_decoder_keys(tmp
     got = mine.network.state_dict()
     assert sorted(got) == sorted(full)
     decoder_keys = [k for k in full if k.startswith(multitask.DECODER_PREFIXES)]
-    assert decoder_keys
+    assert decoder_keys and all(k in dict(mine.network.named_parameters()) for k in decoder_keys)
     for k in full:
         assert torch.equal(got[k], full[k]), k
+    assert callable(mine.network.decode) and callable(mine.network.encode) and callable(mine.network.rank_document)
     importlib.reload(ref_mt)

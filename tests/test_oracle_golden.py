@@ -78,13 +78,54 @@ def test_duet_rejects_unpadded_shapes():
         ol.run_ranker(cfg, sd, ins['q'][:, :-1], ins['qlen'], ins['d'], ins['dlen'])
 
 
-@pytest.mark.parametrize('name', ['cars_tiny', 'cars_clicks', 'cars_mid'])
+@pytest.mark.parametrize('name', ['cars_tiny', 'cars_clicks', 'cars_mid', 'cars_h256'])
 def test_cars(name):
     cfg, ins, sd, outs = ol.load_golden(name)
     o = ol.run_cars(cfg, sd, ins['q'], ins['qlen'], ins['d'], ins['dlen'], ins['label'])
     for k in ('pooled_queries', 'pooled_docs', 'clicks', 'sess_q_attn', 'sess_d_attn'):
         assert np.abs(o[k] - outs[k]).max() < 2e-5, k
     assert _max_rel(o['scores'], outs['scores']) < 1e-4
+    # decoder side: memory banks, and the greedy decode (cars.py:706-791) token for token
+    assert np.abs(o['enc_q'] - outs['encoded_source']).max() < 2e-5
+    pred = ol.run_cars_decode(cfg, sd, o, ins['qlen'], outs['predictions'].shape[-1], ins['tgt2src'])
+    assert np.array_equal(pred, outs['predictions'])
+
+
+def test_cars_click_mask_width_matters_in_the_h256_fixture():
+    """cars_h256 mixes rows of one and of three clicks, so the batch-global mask width m = 3 leaks unclicked documents into
+    the one-click rows: scoring a one-click session alone (m = 1) must give different later-query scores."""
+    cfg, ins, sd, outs = ol.load_golden('cars_h256')
+    clicks = ins['label'].sum(-1)
+    assert clicks.max() == 3 and clicks.min() == 1
+    b = int(np.argmin(clicks.max(axis=1)))
+    if clicks[b].max() < 3:
+        alone = ol.run_cars(cfg, sd, ins['q'][b:b + 1], ins['qlen'][b:b + 1], ins['d'][b:b + 1], ins['dlen'][b:b + 1], ins['label'][b:b + 1])
+        assert np.abs(alone['scores'][0, 1:] - outs['scores'][b, 1:]).max() > 1e-6
+
+
+@pytest.mark.parametrize('rnn', [0, 1])
+def test_oracle_rnn_entry_matches_torch(rnn):
+    """cair_oracle_rnn (LSTM and GRU) against torch.nn.LSTM / GRU on packed sequences - the operator the reference calls
+    (encoders/rnn_encoder.py:45-53, 72-74, 100-113); torch is the reference's arithmetic dependency."""
+    import torch
+    rng = np.random.default_rng(3)
+    n, L, inp, h, G = 5, 7, 6, 9, (4, 3)[rnn]
+    x = rng.standard_normal((n, L, inp)).astype(np.float32)
+    lens = np.array([7, 3, 5, 1, 6], np.int64)
+    mk = lambda: dict(w_ih=(rng.standard_normal((G * h, inp)) * .3).astype(np.float32), w_hh=(rng.standard_normal((G * h, h)) * .3).astype(np.float32),
+                      b_ih=(rng.standard_normal(G * h) * .1).astype(np.float32), b_hh=(rng.standard_normal(G * h) * .1).astype(np.float32))
+    f, r = mk(), mk()
+    out, hn, cn = ol.run_lstm(x, lens, f, r, h, rnn)
+    m = (torch.nn.LSTM, torch.nn.GRU)[rnn](inp, h, batch_first=True, bidirectional=True)
+    with torch.no_grad():
+        for sfx, w in (('', f), ('_reverse', r)):
+            for k in ('w_ih', 'w_hh', 'b_ih', 'b_hh'):
+                getattr(m, k.replace('w_', 'weight_').replace('b_', 'bias_') + '_l0' + sfx).copy_(torch.from_numpy(w[k]))
+        pk = torch.nn.utils.rnn.pack_padded_sequence(torch.from_numpy(x), lens, batch_first=True, enforce_sorted=False)
+        o, st = m(pk)
+        o, _ = torch.nn.utils.rnn.pad_packed_sequence(o, batch_first=True, total_length=L)
+    assert np.abs(o.numpy() - out).max() < 1e-5
+    assert np.abs((st[0] if rnn == 0 else st).numpy() - hn).max() < 1e-5
 
 
 def test_bad_token_id_is_an_error():

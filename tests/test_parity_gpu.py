@@ -178,21 +178,57 @@ def test_duet_rejects_unpadded_batches():
         net(q[:, :-1], ql, d, dl)
 
 
-@pytest.mark.parametrize('name', ['cars_tiny', 'cars_clicks', 'cars_mid'])
+@pytest.mark.parametrize('name', ['cars_tiny', 'cars_clicks', 'cars_mid', 'cars_h256'])
 def test_cars_golden(name, gemm_engine):
     cfg, ins, sd, outs = ol.load_golden(name)
     net = helpers.build_module(cfg, sd, DEV)
     args = helpers.to_dev(ins, DEV, ('q', 'qlen', 'd', 'dlen', 'label'))
     with torch.no_grad():
-        out = net.score(*args, want_stages=True)
+        out = net.score(*args, want_stages=True, want_decoder_inputs=True)
         # the reference's two-call predict sequence gives the same scores
         pooled, _, _ = net.encode(args[0], args[1])
         s2, _, attns = net.rank_document(pooled, args[2], args[3], args[4])
     torch.cuda.synchronize()
     for k in ('pooled_queries', 'pooled_docs', 'clicks', 'sess_q_attn', 'sess_d_attn'):
         assert np.abs(out[k].cpu().numpy() - outs[k]).max() < 5e-4, k
+    assert np.abs(out['enc_q'].cpu().numpy() - outs['encoded_source']).max() < 5e-4
     assert _max_rel(out['scores'].cpu().numpy(), outs['scores']) < TOL
     assert torch.equal(s2, out['scores'])
+
+
+class _TgtDict(list):
+    """tgt_dict[idx] -> word (neuroir Vocabulary indexing by int)."""
+
+
+@pytest.mark.parametrize('name', ['cars_tiny', 'cars_clicks', 'cars_mid', 'cars_h256'])
+def test_cars_predict_sequence_matches_reference_decode(name):
+    """The body of the reference's Multitask.predict (neuroir/models/multitask.py:264-292) on the B200 module: encode ->
+    rank_document -> softmax -> decode(states=..., encoded_source=..., session_attns=...).  click scores within 1e-3 of
+    the reference's, suggested tokens identical to its greedy decode (fixture out/predictions, generated by the unmodified
+    CARS.decode)."""
+    cfg, ins, sd, outs = ol.load_golden(name)
+    net = helpers.build_module(cfg, sd, DEV)
+    src, qlen, docs, dlen, lab = helpers.to_dev(ins, DEV, ('q', 'qlen', 'd', 'dlen', 'label'))
+    nt = cfg['tgt_vocab_size']
+    tgt_dict = _TgtDict('w%d' % i for i in range(nt))
+    src_dict = {'w%d' % i: int(ins['tgt2src'][i]) for i in range(nt)}
+    B, S = src.shape[0], src.shape[1]
+    max_len = outs['predictions'].shape[-1]
+    with torch.no_grad():
+        pooled_rep, encoded_source, _ = net.encode(src, qlen)
+        click_scores, states, session_attns = net.rank_document(pooled_rep, docs, dlen, lab)
+        click_scores = torch.softmax(click_scores, dim=-1)
+        dec = net.decode(states=states, max_len=max_len, src_dict=src_dict, tgt_dict=tgt_dict, batch_size=B,
+                         session_len=S - 1, use_cuda=True, encoded_source=encoded_source, source_len=qlen,
+                         session_attns=session_attns)
+    ref_probs = torch.softmax(torch.from_numpy(outs['scores']), dim=-1).numpy()
+    assert _max_rel(click_scores.cpu().numpy(), ref_probs) < TOL
+    pred = dec['predictions'].cpu().numpy()
+    assert pred.shape == outs['predictions'].shape
+    assert np.array_equal(pred, outs['predictions']), (pred != outs['predictions']).mean()
+    # and against the oracle's own decode from the device outputs
+    fwd = {k: net._fwd[k].cpu().numpy() for k in ('enc_q', 'sess_h', 'sess_c', 'sess_q_attn', 'sess_d_attn')}
+    assert np.array_equal(pred, ol.run_cars_decode(cfg, sd, fwd, ins['qlen'], max_len, ins['tgt2src']))
 
 
 # ---- fresh seeded inputs against the oracle, sizes the oracle finishes in seconds ---------------

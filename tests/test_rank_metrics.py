@@ -120,3 +120,41 @@ def test_batchify_sessions_cuda_vs_oracle():
     oq, oql, od, odl = rmo.batchify_flat(qt, qo, dtok, do, B * S, N)
     assert np.array_equal(got[0].cpu().numpy(), oq.reshape(B, S, -1)) and np.array_equal(got[1].cpu().numpy(), oql.reshape(B, S))
     assert np.array_equal(got[2].cpu().numpy(), od.reshape(B, S, N, -1)) and np.array_equal(got[3].cpu().numpy(), odl.reshape(B, S, N))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['mt_map64', 'cars_map70'])
+def test_metrics_of_b200_scores_equal_metrics_of_reference_scores(name):
+    """BASELINE.json's metric is "...; MAP vs ref": the B200 model scores of a >= 64-query fixture through cair_rank_metrics
+    (softmax + ranking + MAP / MRR / P@1,3,5 on the device) against the reference's own evaluation of ITS scores
+    (fixture out/metric_*, computed by neuroir.eval.ltorank on np.argsort(-softmax(scores)) as main/ranker.py:257-264 does)."""
+    import helpers
+    from context_attentive_ir_b200.metrics import rank_metrics
+    cfg, ins, sd, outs = ol.load_golden(name)
+    net = helpers.build_module(cfg, sd, 'cuda')
+    with torch.no_grad():
+        if cfg['model'] == 'cars':
+            s = net.score(*helpers.to_dev(ins, 'cuda', ('q', 'qlen', 'd', 'dlen', 'label')))['scores']
+        else:
+            s = net(*helpers.to_dev(ins, 'cuda'))
+    n = s.shape[-1]
+    assert s.numel() // n >= 64
+    lab = torch.from_numpy(np.asarray(ins['label']).reshape(-1, n).astype(np.int64)).cuda()
+    m = rank_metrics(s.reshape(-1, n).contiguous(), lab)
+    ref = dict(zip(('map', 'mrr', 'prec@1', 'prec@3', 'prec@5'),
+                   (outs['metric_map'], outs['metric_mrr'], outs['metric_p1'], outs['metric_p3'], outs['metric_p5'])))
+    for k in ref:
+        assert abs(m[k] - float(ref[k])) < 1e-12, (k, m[k], float(ref[k]))
+
+
+@pytest.mark.parametrize('name', ['mt_map64', 'cars_map70'])
+def test_metrics_of_oracle_scores_equal_reference_metrics(name):
+    cfg, ins, sd, outs = ol.load_golden(name)
+    if cfg['model'] == 'cars':
+        s = ol.run_cars(cfg, sd, ins['q'], ins['qlen'], ins['d'], ins['dlen'], ins['label'])['scores']
+    else:
+        s = ol.run_ranker(cfg, sd, ins['q'], ins['qlen'], ins['d'], ins['dlen'])['scores']
+    n = s.shape[-1]
+    mean, _, _ = rmo.rank_metrics(s.reshape(-1, n), np.asarray(ins['label']).reshape(-1, n).astype(np.int64))
+    ref = np.array([outs['metric_map'], outs['metric_mrr'], outs['metric_p1'], outs['metric_p3'], outs['metric_p5']], dtype=np.float64)
+    assert np.abs(mean - ref).max() < 1e-12
