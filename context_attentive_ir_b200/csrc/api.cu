@@ -251,6 +251,10 @@ int32_t cair_set_rnn_impl(int32_t impl) {
 }
 
 // debugging / tuning aids (not in the public header)
+extern "C" __attribute__((visibility("default"))) int32_t cair_drmm_debug_timing(long long* dev_counters) {
+  cair::g_drmm_dbg = dev_counters;
+  return CAIR_OK;
+}
 extern "C" __attribute__((visibility("default"))) int32_t cair_rnn_debug_timing(long long* dev_counters) {
   cair::g_rnn_dbg = dev_counters;
   return CAIR_OK;
@@ -299,6 +303,12 @@ int32_t cair_mt_set_debug(cair_handle* h, float* enc_q, float* enc_d) {
 int32_t cair_set_gemm_impl(int32_t impl) {
   if (impl != 0 && impl != 1) return fail(CAIR_ERR_BAD_ARG, "set_gemm_impl: 0 (fp32 CUDA cores) or 1 (tcgen05)");
   g_gemm_impl = impl;
+  return CAIR_OK;
+}
+
+int32_t cair_set_drmm_impl(int32_t impl) {
+  if (impl != 0 && impl != 1) return fail(CAIR_ERR_BAD_ARG, "set_drmm_impl: 0 (fp32 CUDA cores) or 1 (tcgen05 cosines)");
+  g_drmm_impl = impl;
   return CAIR_OK;
 }
 
@@ -453,8 +463,7 @@ static int32_t ranker_run(cair_handle* h, const int64_t* q, const int64_t* qlen,
       if (dry) return CAIR_OK;
       return esm_forward(h->esm.table, h->esm.V, h->esm.E, q, d, N, Lq, Ld, pb, pc, scores, h->d_err, s);
     case CAIR_MODEL_DRMM:
-      if (dry) return CAIR_OK;
-      return drmm_forward(h->drmm.w, q, d, N, Lq, Ld, pb, pc, scores, h->drmm.dbg_hist, h->d_err, s);
+      return drmm_forward(h->drmm.w, q, d, N, Lq, Ld, pb, pc, scores, h->drmm.dbg_hist, ws, h->d_err, s, dry);
     case CAIR_MODEL_MT:
       return mt_forward(h->mt, q, qlen, d, dlen, B, N, Lq, Ld, pb, pc, scores, ws, h->d_err, s, dry);
     case CAIR_MODEL_DSSM:

@@ -7,7 +7,7 @@
 // discontinuous, so the cosine must be fp32-exact to land in the reference's bin), bin counts
 // are warp-aggregated into shared memory and the gating softmax + 5->1->1 FFN + sum + output
 // layer run in the epilogue.  One 4-byte store per pair.
-#include "common.cuh"
+#include "models.cuh"
 
 namespace cair {
 
@@ -373,11 +373,16 @@ __global__ void __launch_bounds__(DR_THREADS, 2)
 }
 
 int32_t drmm_forward(const cair_drmm_weights& w, const int64_t* q, const int64_t* d, int N, int Lq, int Ld,
-                     int64_t pair_begin, int64_t pair_count, float* scores, int32_t* hist_out, int* err,
-                     cudaStream_t s) {
-  if (pair_count <= 0) return CAIR_OK;
-  if (Lq > DR_MAXLQ) return fail(CAIR_ERR_UNSUPPORTED, "drmm: max_query_len %d > %d", Lq, DR_MAXLQ);
+                     int64_t pair_begin, int64_t pair_count, float* scores, int32_t* hist_out, Arena& ws, int* err,
+                     cudaStream_t s, bool dry) {
   const int E = w.emsize;
+  const int64_t nq = pair_count > 0 ? (pair_begin + pair_count - 1) / N - pair_begin / N + 1 : 0;
+  uint8_t* qrec = ws.take<uint8_t>(drmm_tc_workspace_bytes(E, nq));   // reserved whatever the engine: the size must not depend on it
+  if (dry || pair_count <= 0) return CAIR_OK;
+  if (!ws.ok()) return fail(CAIR_ERR_WORKSPACE, "drmm: workspace too small");
+  if (Lq > DR_MAXLQ) return fail(CAIR_ERR_UNSUPPORTED, "drmm: max_query_len %d > %d", Lq, DR_MAXLQ);
+  if (drmm_tc_usable(E, Lq, Ld, w.table, w.vocab))   // tensor-core cosines, one HBM pass, exact recompute at the bin edges
+    return drmm_tc_forward(w, q, d, N, Lq, Ld, pair_begin, pair_count, scores, hist_out, qrec, err, s);
   int ES = (E + 3) & ~3;
   if (((ES / 4) & 1) == 0) ES += 4;  // odd number of 16-byte groups per row: conflict-free LDS.128
   if ((E & 3) == 0 && Lq <= 4 * D2_QG && Ld <= D2_TOK && ((uintptr_t)w.table & 15) == 0) {

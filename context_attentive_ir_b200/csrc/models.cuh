@@ -24,8 +24,16 @@ struct DrmmState {
   int32_t* dbg_hist = nullptr;
 };
 int32_t drmm_forward(const cair_drmm_weights& w, const int64_t* q, const int64_t* d, int N, int Lq, int Ld,
-                     int64_t pair_begin, int64_t pair_count, float* scores, int32_t* hist_out, int* err,
-                     cudaStream_t s);
+                     int64_t pair_begin, int64_t pair_count, float* scores, int32_t* hist_out, Arena& ws, int* err,
+                     cudaStream_t s, bool dry);
+
+extern long long* g_drmm_dbg;
+extern int g_drmm_impl;   // 1 (default): tcgen05 cosines + exact recompute at the bin edges, 0: fp32 CUDA-core kernels
+bool drmm_tc_usable(int E, int Lq, int Ld, const float* table, int64_t vocab);
+size_t drmm_tc_workspace_bytes(int E, int64_t nq);   // per-query operand records
+int32_t drmm_tc_forward(const cair_drmm_weights& w, const int64_t* q, const int64_t* d, int N, int Lq, int Ld,
+                        int64_t pair_begin, int64_t pair_count, float* scores, int32_t* hist_out, uint8_t* qrec, int* err,
+                        cudaStream_t s);
 
 // ---- Match-Tensor ----
 struct MtPack {

@@ -197,6 +197,9 @@ typedef struct {
   cair_linear output; /* output [1,1] */
 } cair_drmm_weights;
 
+/* Process-wide DRMM engine (A/B runs, on-device cross-check): 1 = tcgen05 bf16x3 cosines with an exact fp32 recompute of
+ * every cell near a bin edge (default; histograms identical to the fp32 kernels'), 0 = fp32 CUDA-core kernels. */
+CAIR_API int32_t cair_set_drmm_impl(int32_t impl);
 CAIR_API int32_t cair_drmm_create(const cair_drmm_weights* w, int32_t device, cair_handle** out);
 /* Optional parity output: hist [B*N,Lq,5] int32 (numpy.histogram counts, drmm.py:71-75). */
 CAIR_API int32_t cair_drmm_set_debug(cair_handle* h, int32_t* hist);

@@ -105,7 +105,15 @@ def test_match_tensor_tc_vs_fp32_kernels_cfg2():
     assert _max_rel(a, b) < 2e-4
 
 
-def test_drmm_golden_strict():
+@pytest.fixture(params=['tcgen05-cos', 'fp32-cos'])
+def drmm_engine(request):
+    """DRMM with the tcgen05 cosines (+ exact recompute at the bin edges) and with the fp32 kernels."""
+    lib.check(lib.load().cair_set_drmm_impl(1 if request.param == 'tcgen05-cos' else 0))
+    yield request.param
+    lib.check(lib.load().cair_set_drmm_impl(1))
+
+
+def test_drmm_golden_strict(drmm_engine):
     cfg, ins, sd, outs = ol.load_golden('drmm_strict')
     net = helpers.build_module(cfg, sd, DEV)
     B, Lq = ins['q'].shape
@@ -121,7 +129,42 @@ def test_drmm_golden_strict():
     assert _max_rel(s.cpu().numpy(), outs['scores']) < 1e-4
 
 
-def test_drmm_golden_overlap_rows_away_from_bin_edges():
+def _drmm_hist(net, args, rows, Lq):
+    hist = torch.full((rows, Lq, 5), -1, dtype=torch.int32, device=DEV)
+    with torch.no_grad():
+        net(*args)
+        lib.check(lib.load().cair_drmm_set_debug(net._cair_handle, hist.data_ptr()))
+        s = net(*args)
+        lib.check(lib.load().cair_drmm_set_debug(net._cair_handle, None))
+    torch.cuda.synchronize()
+    return hist.cpu().numpy(), s.cpu().numpy()
+
+
+@pytest.mark.parametrize('case', ['overlap_pads', 'cfg3_full_lengths', 'odd_sizes'])
+def test_drmm_tensor_core_histograms_identical_to_fp32_kernels(case):
+    """The tcgen05 path recomputes every cosine near a bin edge with the fp32 kernels' arithmetic, so its histograms must be
+    IDENTICAL to theirs - also where the reference itself is rounding-chaotic (exact matches, cos ~ 1) and on PAD rows."""
+    E, V, B, N, Lq, Ld, kw = dict(overlap_pads=(300, 3000, 24, 10, 20, 200, dict(bos_eos=True, overlap=0.15)),
+                                  cfg3_full_lengths=(300, 131072, 64, 10, 20, 200, dict(variable=False)),
+                                  odd_sizes=(64, 500, 5, 3, 7, 131, dict(bos_eos=True, overlap=0.3)))[case]
+    cfg = dict(model='drmm', emsize=E, src_vocab_size=V, dropout_emb=0.2, nbins=5)
+    torch.manual_seed(11)
+    net = helpers.build_module(cfg).to(DEV)
+    with torch.no_grad():
+        net.word_embeddings.word_lut.weight[7].zero_()          # an OOV-style all-zero row that is not PAD
+    batch = synth.ranker_batch(21, B, N, Lq, Ld, V, **kw)
+    args = helpers.to_dev(batch, DEV)
+    L = lib.load()
+    lib.check(L.cair_set_drmm_impl(1))
+    h_tc, s_tc = _drmm_hist(net, args, B * N, Lq)
+    lib.check(L.cair_set_drmm_impl(0))
+    h_fp, s_fp = _drmm_hist(net, args, B * N, Lq)
+    lib.check(L.cair_set_drmm_impl(1))
+    assert (h_tc == h_fp).all(), int((h_tc != h_fp).sum())
+    assert np.array_equal(s_tc, s_fp)
+
+
+def test_drmm_golden_overlap_rows_away_from_bin_edges(drmm_engine):
     cfg, ins, sd, outs = ol.load_golden('drmm_overlap')
     net = helpers.build_module(cfg, sd, DEV)
     B, Lq = ins['q'].shape
@@ -390,7 +433,7 @@ def _ranker_properties(cfg, seed, B, N, Lq, Ld, spot=(0, 1), tol_eq=1e-5, **kw):
     return s[idx].cpu().numpy(), ref
 
 
-def test_drmm_full_cfg3_properties():
+def test_drmm_full_cfg3_properties(drmm_engine):
     """BASELINE configs[2]: B=256, Lq=20, Ld=200, N=10, E=300.  Disjoint query / document ids keep the cosines away from
     the exact-match bin edge, so the histograms - and hence the scores - are exactly permutation- and
     batch-invariant."""
