@@ -25,7 +25,7 @@ def _fill(rng, n, L, V, lens, lo=4, hi=None, bos_eos=False):
 
 
 def ranker_batch(seed, B, N, Lq, Ld, V, variable=True, bos_eos=False,
-                 disjoint=False, overlap=0.0):
+                 disjoint=False, overlap=0.0, realistic=False):
     """Returns dict(q[B,Lq], qlen[B], d[B,N,Ld], dlen[B,N], label[B,N]) of int64.
 
     variable=False: all lengths at max (headline throughput set).
@@ -35,7 +35,15 @@ def ranker_batch(seed, B, N, Lq, Ld, V, variable=True, bos_eos=False,
     overlap>0: that fraction of doc tokens is replaced by tokens of its query.
     """
     rng = np.random.default_rng(seed)
-    if variable:
+    if realistic:
+        # the dataset's length statistics (reference README.md:80-83: avg query 3.84 / max 40 tokens, avg document 63.41 /
+        # max 290, truncated to 200 by scripts/ranker.sh:18), plus the BOS / EOS the loader adds (inputters/ranker/utils.py:36,61)
+        qlen = np.clip(rng.poisson(3.84, size=B) + 2, 3, Lq).astype(np.int64)
+        dlen = np.clip(np.round(rng.lognormal(np.log(50.0), 0.65, size=B * N)) + 2, 3, Ld).astype(np.int64)
+        qlen[0] = Lq
+        dlen[0] = Ld
+        bos_eos = True
+    elif variable:
         qlen = rng.integers(2, Lq + 1, size=B, dtype=np.int64)
         dlen = rng.integers(2, Ld + 1, size=B * N, dtype=np.int64)
         qlen[0] = Lq

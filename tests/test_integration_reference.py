@@ -106,3 +106,29 @@ def test_reference_multitask_wrapper_builds_b200_cars_and_keeps_decoder_keys(tmp
         assert torch.equal(got[k], full[k]), k
     assert callable(mine.network.decode) and callable(mine.network.encode) and callable(mine.network.rank_document)
     importlib.reload(ref_mt)
+
+
+def test_two_layer_encoder_is_rejected_through_the_reference_config_path():
+    """`--nlayers 2` travels through the unmodified neuroir.config (add_model_args -> get_model_args) into Ranker.__init__;
+    the B200 Match-Tensor implements single-layer encoders (the reference's hyparam dicts fix nlayers = 1,
+    neuroir/hyparam.py:88-100) and must refuse loudly instead of scoring with one layer.  hyparam's arch dict overrides the
+    CLI flag, so the two-layer request is injected where get_model_args leaves it: on the Namespace."""
+    ref_ranker = _import_reference()
+    import importlib
+    stock = importlib.reload(ref_ranker)
+    import neuroir.config as config
+    parser = argparse.ArgumentParser()
+    parser.register('type', 'bool', lambda x: x.lower() in ('yes', 'true', 't', '1', 'y'))   # main/ranker.py:34
+    parser.add_argument('--model_type', type=str, default='dssm')                             # main/ranker.py:40
+    config.add_model_args(parser)
+    args = parser.parse_args(['--model_type', 'match_tensor', '--nlayers', '2'])
+    margs = config.get_model_args(args)
+    assert margs.nlayers == 1          # hyparam.py wins over the flag ...
+    import context_attentive_ir_b200.integration as integ
+    integ.install()
+    vocab = _Dict((i, i) for i in range(50))
+    stock.Ranker(margs, vocab)         # ... so the stock path builds
+    margs.nlayers = 2                  # a caller that really asks for two layers is refused, not silently truncated
+    with pytest.raises(NotImplementedError, match='single-layer'):
+        stock.Ranker(margs, vocab)
+    importlib.reload(ref_ranker)
