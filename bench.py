@@ -230,8 +230,22 @@ class Runner:
     """Shared timing harness: device-resident inputs, L2 flush before every step (outside the events), CUDA events per
     step on the launching stream, max over ranks."""
 
-    def __init__(self, dev, world, rank):
+    def make_gather(self, per):
+        """(gather(local, total) -> all scores, description): our NVLink peer-memory kernel (cair_allgather_scores) when the
+        symmetric-memory rendezvous works, else NCCL."""
+        from context_attentive_ir_b200.parallel import P2PScoreGather, gather_scores
+        if self.world == 1:
+            return gather_scores, 'none (1 GPU)'
+        if not self.no_p2p:
+            try:
+                return P2PScoreGather(per, self.dev), 'cair_allgather_scores: peer stores over NVLink + flags (torch symmetric memory mappings)'
+            except Exception as ex:   # noqa: BLE001 - any rendezvous problem: fall back to the library collective
+                self.p2p_error = repr(ex)[:200]
+        return gather_scores, 'NCCL all_gather_into_tensor'
+
+    def __init__(self, dev, world, rank, no_p2p=False):
         import torch
+        self.no_p2p, self.p2p_error = no_p2p, None
         self.torch, self.dev, self.world, self.rank = torch, dev, world, rank
         self.flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)   # 1.5 x the 126 MB L2
         self.stream = torch.cuda.current_stream(dev)
@@ -300,9 +314,12 @@ def other_configs(run, args, peaks):
     import torch
     import helpers
     from context_attentive_ir_b200 import synth
-    from context_attentive_ir_b200.parallel import gather_scores
+    from context_attentive_ir_b200.parallel import gather_scores as nccl_gather
     import torch.distributed as dist
     dev, world, rank = run.dev, run.world, run.rank
+
+    def make_gather(per):
+        return run.make_gather(per)[0]
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
     tf_peak = peaks.get('bf16_tflops_sustained', 1400.0)
     out = []
@@ -313,6 +330,7 @@ def other_configs(run, args, peaks):
         batch = synth.ranker_batch(1234 + rank, b, n, lq, ld, cfg['src_vocab_size'], **(batch_kw or dict(variable=False)))
         t = helpers.to_dev(batch, dev)
         total = b * n * world
+        gather_scores = make_gather(b * n)
 
         def step():
             with torch.no_grad():
@@ -371,6 +389,7 @@ def other_configs(run, args, peaks):
     batch = synth.session_batch(1238, Bc * world, S, Nc, Lq, Ld, CARS_CFG['src_vocab_size'], variable=False, max_clicks=2)
     t = helpers.to_dev(batch, dev, ('q', 'qlen', 'd', 'dlen', 'label'))
     total = Bc * world * S * Nc
+    gather_scores = make_gather(Bc * S * Nc)
 
     def cars_step():
         with torch.no_grad():
@@ -394,8 +413,6 @@ def run_product(args):
     import torch.distributed as dist
     import helpers
     from context_attentive_ir_b200 import lib
-    from context_attentive_ir_b200.parallel import gather_scores
-
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -404,7 +421,7 @@ def run_product(args):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    run = Runner(dev, world, rank)
+    run = Runner(dev, world, rank, args.nccl_collective)
 
     torch.manual_seed(1013)  # identical replicated weights on every rank
     net = helpers.build_module(CFG).to(dev)
@@ -415,6 +432,7 @@ def run_product(args):
     pinned = [[torch.from_numpy(np.ascontiguousarray(b[k])).pin_memory() for k in ('q', 'qlen', 'd', 'dlen')] for b in host]
     pairs_local, pairs_total = B * N, B * N * world
     stream = run.stream
+    gather_scores, collective = run.make_gather(pairs_local)
 
     def one(i):
         with torch.no_grad():
@@ -473,7 +491,7 @@ def run_product(args):
                     g = gather_scores(s.reshape(-1), pairs_total)
                     houts[s3].view(-1).copy_(g, non_blocking=True)
                 cstream.synchronize()
-        api = ('device entry point on 3 staging slots: pinned ids -> H2D -> kernels -> NCCL all-gather of the scores -> D2H of all '
+        api = ('device entry point on 3 staging slots: pinned ids -> H2D -> kernels -> all-gather of the scores (see run.collective) -> D2H of all '
                'B*world*N scores, stream-ordered, one synchronisation per step of 25 batches')
     e2e_loop(2 * nb)
     torch.cuda.synchronize()
@@ -557,7 +575,8 @@ def run_product(args):
             'dtype': 'f32 (tcgen05 bf16x3 split-precision MMA, fp32 accumulate/state)', 'data': 'synthetic',
             'config': CONFIG,
             'run': {'per_gpu_pairs_per_batch': pairs_local, 'global_pairs_per_step': pairs_total * nb, 'ms_per_batch': ms_per_step / nb,
-                    'parallelism': 'doc-parallel x%d, one all-gather of scores per batch' % world,
+                    'parallelism': 'doc-parallel x%d, one all-gather of scores per batch' % world, 'collective': collective,
+                    'collective_fallback_reason': run.p2p_error,
                     'timed_region_s': ms_per_step * args.steps / 1e3,
                     'table': 'eval-mode folded [V,40] table, pre-split into bf16 hi/lo operand rows (192 B per token, built once at handle creation)'},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'api': api,
@@ -587,6 +606,7 @@ def main():
     ap.add_argument('--cpu-sample-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-other-configs', action='store_true')
+    ap.add_argument('--nccl-collective', action='store_true', help='use NCCL for the score all-gather instead of cair_allgather_scores')
     ap.add_argument('--cpu-baseline-worker', action='store_true', help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_baseline_worker:

@@ -306,6 +306,11 @@ int32_t cair_set_gemm_impl(int32_t impl) {
   return CAIR_OK;
 }
 
+int32_t cair_allgather_scores(const float* send, int64_t count, const uint64_t* peer_recv, const uint64_t* peer_flags,
+                              int32_t rank, int32_t world, uint32_t seq, void* stream) {
+  return allgather_scores_p2p(send, count, peer_recv, peer_flags, rank, world, seq, (cudaStream_t)stream);
+}
+
 int32_t cair_set_drmm_impl(int32_t impl) {
   if (impl != 0 && impl != 1) return fail(CAIR_ERR_BAD_ARG, "set_drmm_impl: 0 (fp32 CUDA cores) or 1 (tcgen05 cosines)");
   g_drmm_impl = impl;

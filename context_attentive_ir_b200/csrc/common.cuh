@@ -282,6 +282,10 @@ int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, cons
 // table [V, in] fp32 -> image [V][hi|lo][48 x bf16] (constant 1 in K slot `in` = the bias column, zero padding)
 int32_t lstm_tc_pack_table(Owned& own, const float* table, int V, int in, uint8_t** img, cudaStream_t s);
 
+// all-gather of scores over NVLink peer memory (p2p.cu)
+int32_t allgather_scores_p2p(const float* send, int64_t count, const uint64_t* peer_recv, const uint64_t* peer_flags, int rank,
+                             int world, uint32_t seq, cudaStream_t s);
+
 // tcgen05 recurrence, gate rows split over a thread-block cluster (rnn_tc.cu): LSTM and GRU, h <= 128 per direction.
 struct RnnTcPack {
   int in = 0, h = 0, dirs = 0, cs = 0, gru = 0, fused = 0, planes = 0;

@@ -34,6 +34,48 @@ def gather_scores(local, total, group=None):
     return recv[:total]
 
 
+class P2PScoreGather:
+    """The same all-gather as our own kernel over NVLink peer memory (cair_allgather_scores): every rank stores its slice
+    straight into every peer's receive buffer (torch symmetric memory supplies the peer mappings) and waits on flags -
+    one launch, no NCCL call.  `per` = slice length of every rank (the last ranks' short slices are padded by the caller's
+    layout: slot r of the result starts at r * per).  The returned tensor is a view of one of two alternating receive
+    buffers: it stays valid until the call after next."""
+
+    def __init__(self, per, device, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank, self.per, self.dev = dist.get_world_size(group), dist.get_rank(group), int(per), device
+        n = self.world * self.per
+        self.recv = symm_mem.empty(2 * n, dtype=torch.float32, device=device)
+        self.flags = symm_mem.empty(64, dtype=torch.int32, device=device)
+        self.recv.zero_()
+        self.flags.zero_()
+        hr = symm_mem.rendezvous(self.recv, self.group)
+        hf = symm_mem.rendezvous(self.flags, self.group)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                       # every rank's flags are zero before anyone publishes into them
+        self._keep = (hr, hf)
+        self._flag_ptrs = (C.c_uint64 * self.world)(*[int(p) for p in hf.buffer_ptrs])
+        self._recv_ptrs = [(C.c_uint64 * self.world)(*[int(p) + par * n * 4 for p in hr.buffer_ptrs]) for par in (0, 1)]
+        self.seq = 0
+        self._lib, self._check = lib.load(), lib.check
+
+    def __call__(self, local, total):
+        assert local.is_cuda and local.dtype == torch.float32 and local.is_contiguous() and local.numel() <= self.per
+        send = local
+        if local.numel() < self.per:              # short trailing slice: pad to the common slot length
+            send = local.new_zeros(self.per)
+            send[:local.numel()] = local
+        self.seq += 1
+        par = self.seq & 1
+        self._check(self._lib.cair_allgather_scores(send.data_ptr(), self.per, self._recv_ptrs[par], self._flag_ptrs, self.rank,
+                                                    self.world, self.seq, torch.cuda.current_stream(self.dev).cuda_stream))
+        n = self.world * self.per
+        return self.recv[par * n:par * n + n][:total]
+
+
 class ShardedRanker:
     """Wraps a ranker network: each rank scores its pair slice, one all-gather assembles [B, N].
     `score_slice(q, qlen, d, dlen, begin, count) -> [B, N] tensor with the slice filled` defaults to the

@@ -300,6 +300,18 @@ CAIR_API int32_t cair_ranker_submit_host(cair_handle* h, const int64_t* q, const
 CAIR_API int32_t cair_ranker_wait_host(cair_handle* h, int32_t slot);
 CAIR_API int32_t cair_ranker_set_pipeline_split(cair_handle* h, float frac);
 
+/* ---- the one collective of the doc-parallel path (SURVEY.md sections 8b, 8e) ------------------------
+ * All-gather of fp32 scores over NVLink peer memory, replacing the gather of nn.DataParallel
+ * (neuroir/models/ranker.py:341-346; the softmax / loss / MAP of :87,:258 need all N candidates of a query).
+ * send [count] is this rank's slice; peer_recv[r] / peer_flags[r] (HOST arrays of `world` device pointers) are rank r's
+ * receive buffer [world*count floats] and flag array [world uint32, zero before the first call] as mapped into THIS
+ * process (torch symmetric memory or CUDA IPC); seq must increase by one per call on all ranks.  On return of the
+ * enqueued kernel slot r of this rank's own receive buffer holds rank r's scores for every r.  Consecutive calls must
+ * alternate between two receive buffers (the peers write the next call's slices while this rank may still read the
+ * previous result).  One launch on `stream`, nothing is synchronised; a peer that never arrives traps the launch. */
+CAIR_API int32_t cair_allgather_scores(const float* send, int64_t count, const uint64_t* peer_recv,
+                              const uint64_t* peer_flags, int32_t rank, int32_t world, uint32_t seq, void* stream);
+
 /* ---- ranking metrics of the evaluation loops, on the device ----------
  * Replaces, per batch, `scores.cpu()` + `np.argsort(-scores)` + MAP / MRR / precision_at_k(1,3,5)
  * (main/ranker.py:257-264, main/multitask.py:286-293; neuroir/eval/ltorank.py:4-26, 29-47, 104-123)
