@@ -55,6 +55,8 @@ struct MtEpiConst {
   float w1t[24][MT_TC_MAXM]; // 1x1 conv, transposed: [f][m] (m contiguous: one 128-bit constant load = 4 output channels)
   float b1[MT_TC_MAXM];
 };
+int32_t mt_pack(Owned& own, const cair_mt_weights& w, MtPack* p, cudaStream_t s);
+size_t mt_t_floats(const MtPack& p, int64_t nq, int Lq);
 bool mt_tc_supported(const MtPack& p, int Lq, int Ld);
 void mt_tc_workspace(const MtPack& p, int64_t nq, int64_t pc, int Lq, int Ld, size_t* timg_bytes, size_t* aimg_bytes);
 int32_t mt_epi_const(const MtPack& p, MtEpiConst* out, cudaStream_t s);  // synchronises s

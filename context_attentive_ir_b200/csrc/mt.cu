@@ -110,12 +110,16 @@ __global__ void __launch_bounds__(256) mt_build_t_kernel(const float* __restrict
 }
 
 // smem (floats): Dt[C][LdP] | Tsl[7*C*FPP] | wem[21*FPP] | bias[FPP] | w1[M*FPP] | b1[M] | red[M*8] | ids
+// ARG (training, train.cu): also returns the pooled features [pairs, M] and, per (pair, m), the cell i*Ld + j of the maximum
+// - the first one in row-major order, which is where torch's two max reductions (mtensor.py:128-129) route the gradient.
+template <bool ARG>
 __global__ void __launch_bounds__(MT_THREADS) mt_interact_kernel(const float* __restrict__ cd,
                                                                  const float* __restrict__ T, MtPack p,
                                                                  const int64_t* __restrict__ q,
                                                                  const int64_t* __restrict__ d, int N, int Lq, int Ld,
                                                                  int64_t pair_begin, int64_t q_begin,
-                                                                 float* __restrict__ scores) {
+                                                                 float* __restrict__ scores, float* __restrict__ pooled,
+                                                                 int* __restrict__ argidx) {
   extern __shared__ __align__(16) float sm[];
   const int C = p.C, FPP = p.FPP, FP4 = FPP / 4, M = p.M;
   const int LdP = Ld + 6;
@@ -152,8 +156,13 @@ __global__ void __launch_bounds__(MT_THREADS) mt_interact_kernel(const float* __
     Dt[(size_t)c * LdP + j + 3] = cdp[i];
   }
   float mx[MT_MAXM];
+  int ax[ARG ? MT_MAXM : 1];
 #pragma unroll
   for (int m = 0; m < MT_MAXM; ++m) mx[m] = -INFINITY;
+  if (ARG) {
+#pragma unroll
+    for (int m = 0; m < MT_MAXM; ++m) ax[ARG ? m : 0] = 0x7fffffff;
+  }
 
   const float* Tq = T + (size_t)ql * Lq * 7 * C * FPP;
   for (int i = 0; i < Lq; ++i) {
@@ -218,10 +227,52 @@ __global__ void __launch_bounds__(MT_THREADS) mt_interact_kernel(const float* __
               z = fmaf(w4.w, acc[4 * f4 + 3], z);
             }
           }
-          mx[m] = fmaxf(mx[m], z);
+          if (ARG) {
+            if (z > mx[m]) mx[m] = z, ax[ARG ? m : 0] = i * Ld + j;   // strict: keeps this thread's first maximum
+          } else {
+            mx[m] = fmaxf(mx[m], z);
+          }
         }
       }
     }
+  }
+  if (ARG) {
+    // block arg-max: larger value wins, equal values -> smaller cell index
+    int* redi = reinterpret_cast<int*>(Tsl);   // the T slice is no longer needed
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < MT_MAXM; ++m) {
+      if (m < M) {
+        float v = mx[m];
+        int ix = ax[ARG ? m : 0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
+          if (ov > v || (ov == v && oi < ix)) v = ov, ix = oi;
+        }
+        if ((tid & 31) == 0) red[m * (MT_THREADS / 32) + (tid >> 5)] = v, redi[m * (MT_THREADS / 32) + (tid >> 5)] = ix;
+      }
+    }
+    __syncthreads();
+    if (tid < 32) {
+      float sv = 0.f;
+      if (tid < M) {
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int w = 0; w < MT_THREADS / 32; ++w) {
+          const float v = red[tid * (MT_THREADS / 32) + w];
+          const int ix = redi[tid * (MT_THREADS / 32) + w];
+          if (v > best || (v == best && ix < bi)) best = v, bi = ix;
+        }
+        pooled[pl * M + tid] = best;
+        argidx[pl * M + tid] = bi;
+        sv = best * p.wo[tid];
+      }
+      sv = warp_sum(sv);
+      if (tid == 0) scores[p_glob] = sv + p.wo[M];
+    }
+    return;
   }
   // block max over j, then score = wo . max + bo
 #pragma unroll
@@ -253,10 +304,35 @@ int32_t mt_interact(const MtPack& p, const float* cq, const float* cd, float* T,
   size_t smem = ((((size_t)p.C * (Ld + 6) + 3) & ~(size_t)3) + 7 * p.C * p.FPP + 21 * p.FPP + p.FPP + p.M * p.FPP + MT_MAXM +
                  MT_MAXM * (MT_THREADS / 32)) * sizeof(float) + (size_t)(Ld + 6 + Lq) * sizeof(int);
   if (smem > 220 * 1024) return fail(CAIR_ERR_UNSUPPORTED, "match_tensor: Ld=%d x C=%d does not fit in shared memory", Ld, p.C);
-  CAIR_CUDA(cudaFuncSetAttribute(mt_interact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CAIR_CUDA(cudaFuncSetAttribute(mt_interact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_mark("interact", s);
-  CAIR_LAUNCH(mt_interact_kernel, (unsigned)pair_count, MT_THREADS, smem, s, cd, T, p, q, d, N, Lq, Ld, pair_begin,
-              q_begin, scores);
+  CAIR_LAUNCH(mt_interact_kernel<false>, (unsigned)pair_count, MT_THREADS, smem, s, cd, T, p, q, d, N, Lq, Ld, pair_begin,
+              q_begin, scores, (float*)nullptr, (int*)nullptr);
+  return CAIR_OK;
+}
+
+// training forward (train.cu): all pairs, with the pooled features and arg-max cells
+int32_t mt_interact_train(const MtPack& p, const float* cq, const float* cd, float* T, const int64_t* q, const int64_t* d, int N,
+                          int Lq, int Ld, int64_t pairs, int64_t nq, float* scores, float* pooled, int* argidx, cudaStream_t s) {
+  if (pairs <= 0) return CAIR_OK;
+  CAIR_LAUNCH(mt_build_t_kernel, dim3(Lq, (unsigned)nq), 256, 0, s, cq, p, Lq, T);
+  size_t smem = ((((size_t)p.C * (Ld + 6) + 3) & ~(size_t)3) + 7 * p.C * p.FPP + 21 * p.FPP + p.FPP + p.M * p.FPP + MT_MAXM +
+                 MT_MAXM * (MT_THREADS / 32)) * sizeof(float) + (size_t)(Ld + 6 + Lq) * sizeof(int);
+  if (smem > 220 * 1024) return fail(CAIR_ERR_UNSUPPORTED, "match_tensor: Ld=%d x C=%d does not fit in shared memory", Ld, p.C);
+  CAIR_CUDA(cudaFuncSetAttribute(mt_interact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CAIR_LAUNCH(mt_interact_kernel<true>, (unsigned)pairs, MT_THREADS, smem, s, cd, T, p, q, d, N, Lq, Ld, (int64_t)0, (int64_t)0,
+              scores, pooled, argidx);
+  return CAIR_OK;
+}
+
+// weights changed in place (training): rebuild the packed copies in the buffers mt_pack allocated
+int32_t mt_repack(const cair_mt_weights& w, MtPack* p, cudaStream_t s) {
+  const size_t n7t = (size_t)21 * p->FP * ((p->C + 15) & ~15);
+  CAIR_CUDA(cudaMemsetAsync(p->w7t, 0, n7t * sizeof(float), s));
+  int total = 21 * (p->C + 1) * p->FPP;
+  if (total < p->M * p->FPP) total = p->M * p->FPP;
+  CAIR_LAUNCH(mt_pack_kernel, (total + 255) / 256, 256, 0, s, w.conv1.w, w.conv2.w, w.conv3.w, w.conv1.b, w.conv2.b,
+              w.conv3.b, w.alpha, w.conv.w, w.conv.b, w.output.w, w.output.b, *p);
   return CAIR_OK;
 }
 

@@ -1,0 +1,906 @@
+// Training step of Match-Tensor: train-mode forward with saved activations + hand-written
+// backward, so that the reference's Ranker.update (neuroir/models/ranker.py:192-230: forward, criterion, loss.backward(),
+// clip_grad_norm, optimizer.step()) runs on libcair kernels.  The loss, the clipping and the optimizer stay in the
+// unchanged wrapper (they are torch calls on [B,N] scores / on the parameter list); what is here is everything between the
+// token ids and the scores, forward and backward:
+//   ids -> embedding rows * dropout mask (mtensor.py:77-84) -> linear_projection (:88-90) -> (Bi)LSTM encoders (:93-94,
+//   rnn_encoder.py:62-141, packed-sequence semantics) -> channel projections (:99,:108) -> match tensor + exact-match
+//   channel (:113-120) -> conv1/2/3 + ReLU + 1x1 conv + two max-pools + Linear (:123-131).
+// fp32 throughout (CUDA cores): the backward is a "next" row, correctness first.  Algebra:
+//  * the two max-pools route the gradient of a pair to at most match_filter_size cells (i*, j*) of the [Lq, Ld] plane
+//    (first maximum in row-major order, as ATen's max reduction breaks ties), so the backward of the whole interaction
+//    stack is SPARSE: per (pair, m) the conv outputs of that one cell are recomputed from cq / cd / ids and the
+//    gradient is scattered to the 3 x 7 x (C+1) taps around it.  The forward only has to remember the arg-max cells.
+//  * BPTT: a reverse-time recurrence kernel turns d(bank) into the pre-activation gate gradients in place of the saved
+//    gate activations; dW_hh, dW_ih, db, dx are then plain GEMMs over all (sequence, step) rows.
+//  * dropout masks are a counter-based hash of (seed, element index), recomputed in the backward (never stored).
+#include "models.cuh"
+
+namespace cair {
+
+// ------------------------------------------------------------------------------------------------
+// dropout: keep-scale of element idx (0 or 1/(1-p)); splitmix64 of (seed, idx)
+__device__ __forceinline__ float drop_scale(uint64_t seed, uint64_t idx, float p, float inv_keep) {
+  if (p <= 0.f) return 1.f;
+  uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+  z ^= z >> 30;
+  z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27;
+  z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = (float)(z >> 40) * (1.0f / 16777216.0f);
+  return u >= p ? inv_keep : 0.f;
+}
+
+__global__ void dropout_mask_kernel(uint64_t seed, float p, int64_t n, float* __restrict__ out) {
+  const float inv = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = drop_scale(seed, (uint64_t)i, p, inv);
+}
+
+// x[r, :] = table[ids[r], :] * mask(row0 + r, :)
+__global__ void embed_drop_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids, int V, int E, int64_t rows,
+                                  int64_t row0, float p, uint64_t seed, float* __restrict__ out, int* err) {
+  const float inv = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  const int64_t total = rows * E;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / E;
+    const int e = (int)(i - r * E);
+    const int64_t id = checked_id(ids[r], V, err);
+    out[i] = table[id * E + e] * drop_scale(seed, (uint64_t)((row0 + r) * E + e), p, inv);
+  }
+}
+
+__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
+// out[c * ldo + r] = in[r * cols + c]  (small weight matrices)
+__global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out, int64_t ldo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * cols) {
+    const int r = i / cols, c = i - r * cols;
+    out[(int64_t)c * ldo + r] = in[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C[M,N] += sum_r A[r, :M]^T B[r', :N]; r' = r + bshift inside the same block of L rows (zero outside): the weight
+// gradients.  64x64 tile per CTA over a chunk of rows, atomicAdd into C.
+constexpr int TN_T = 64, TN_K = 16;
+__global__ void __launch_bounds__(256) gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                                                      int64_t ldb, int bshift, int L, float* __restrict__ C, int64_t ldc,
+                                                      int64_t R, int M, int N, int64_t rows_per_cta) {
+  __shared__ __align__(16) float As[TN_K][TN_T + 4];
+  __shared__ __align__(16) float Bs[TN_K][TN_T + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * TN_T, n0 = blockIdx.y * TN_T;
+  const int64_t r_begin = (int64_t)blockIdx.z * rows_per_cta;
+  const int64_t r_end = r_begin + rows_per_cta < R ? r_begin + rows_per_cta : R;
+  const int lr = tid >> 4, lc = (tid & 15) * 4;
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += TN_K) {
+    const int64_t r = r0 + lr;
+    float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < r_end) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (m0 + lc + u < M) av[u] = A[r * lda + m0 + lc + u];
+      bool ok = true;
+      int64_t rb = r;
+      if (bshift != 0) {
+        const int t = (int)(r % L) + bshift;
+        ok = t >= 0 && t < L;
+        rb = r + bshift;
+      }
+      if (ok) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (n0 + lc + u < N) bv[u] = B[rb * ldb + n0 + lc + u];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      As[lr][lc + u] = av[u];
+      Bs[lr][lc + u] = bv[u];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TN_K; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float ar[4] = {a4.x, a4.y, a4.z, a4.w}, br[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N && acc[i][j] != 0.f) atomicAdd(&C[(int64_t)m * ldc + n], acc[i][j]);
+    }
+  }
+}
+
+static int32_t gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int bshift, int L, float* C, int64_t ldc,
+                       int64_t R, int M, int N, cudaStream_t s) {
+  if (R <= 0 || M <= 0 || N <= 0) return CAIR_OK;
+  const int mt = (M + TN_T - 1) / TN_T, nt = (N + TN_T - 1) / TN_T;
+  int64_t z = (4 * kSMs + mt * nt - 1) / (mt * nt);
+  int64_t rpc = (R + z - 1) / z;
+  rpc = (rpc + TN_K - 1) / TN_K * TN_K;
+  if (rpc < 256) rpc = 256;
+  z = (R + rpc - 1) / rpc;
+  CAIR_LAUNCH(gemm_tn_kernel, dim3(mt, nt, (unsigned)z), 256, 0, s, A, lda, B, ldb, bshift, L, C, ldc, R, M, N, rpc);
+  return CAIR_OK;
+}
+
+// out[c] += sum_r A[r, c]  (bias gradients); out2 (optional) receives the same sums (b_ih and b_hh share a gradient)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, int64_t lda, int64_t R, int N,
+                                                     int64_t rows_per_cta, float* __restrict__ out, float* __restrict__ out2) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const int64_t r_begin = (int64_t)blockIdx.y * rows_per_cta;
+  const int64_t r_end = r_begin + rows_per_cta < R ? r_begin + rows_per_cta : R;
+  float acc = 0.f;
+  if (c < N)
+    for (int64_t r = r_begin + ry; r < r_end; r += 8) acc += A[r * lda + c];
+  red[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && c < N) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += red[k][cx];
+    if (v != 0.f) {
+      atomicAdd(&out[c], v);
+      if (out2) atomicAdd(&out2[c], v);
+    }
+  }
+}
+static int32_t colsum(const float* A, int64_t lda, int64_t R, int N, float* out, float* out2, cudaStream_t s) {
+  if (R <= 0 || N <= 0 || !out) return CAIR_OK;
+  const int ct = (N + 31) / 32;
+  int64_t y = (2 * kSMs + ct - 1) / ct;
+  int64_t rpc = (R + y - 1) / y;
+  if (rpc < 64) rpc = 64;
+  y = (R + rpc - 1) / rpc;
+  CAIR_LAUNCH(colsum_kernel, dim3(ct, (unsigned)y), 256, 0, s, A, lda, R, N, rpc, out, out2);
+  return CAIR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LSTM forward for training: as rnn_rec_kernel (lstm.cu), and the gate ACTIVATIONS (i, f, g, o) replace the pre-gates in
+// `gates` [n*L, dirs*4h]; c_seq / out [n*L, dirs*h].  TS sequences of one direction per CTA.
+constexpr int TR_TS = 8;
+template <bool WSMEM>
+__global__ void __launch_bounds__(256) lstm_train_fwd_kernel(float* __restrict__ gates, const float* __restrict__ w_hh_t,
+                                                             const int64_t* __restrict__ len, int n, int L, int h, int dirs,
+                                                             float* __restrict__ out, float* __restrict__ c_seq, int* err) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int TS = TR_TS;
+  const int G = 4 * h, hp = (h + 3) & ~3, PG = dirs * G, Hout = dirs * h;
+  const int dir = blockIdx.y, s0 = blockIdx.x * TS, tid = threadIdx.x;
+  float* wsm = smem;
+  float* hprev = smem + (WSMEM ? (size_t)h * G : 0);
+  float* cst = hprev + TS * hp;
+  float* gs = cst + TS * h;
+  __shared__ int slen[TS];
+  __shared__ int smaxlen;
+  const float* wt = w_hh_t + (size_t)dir * h * G;
+  if (WSMEM)
+    for (int i = tid; i < h * G; i += 256) wsm[i] = wt[i];
+  const float* W = WSMEM ? wsm : wt;
+  for (int i = tid; i < TS * hp; i += 256) hprev[i] = 0.f;
+  for (int i = tid; i < TS * h; i += 256) cst[i] = 0.f;
+  if (tid < TS) {
+    int s = s0 + tid, l = 0;
+    if (s < n) {
+      int64_t ll = len[s];
+      if (ll < 1 || ll > L) {
+        atomicOr(err, ERRF_BAD_LENGTH);
+        ll = ll < 1 ? 1 : L;
+      }
+      l = (int)ll;
+    }
+    slen[tid] = l;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int m = 0;
+    for (int s = 0; s < TS; ++s) m = max(m, slen[s]);
+    smaxlen = m;
+  }
+  for (int s = 0; s < TS; ++s) {   // pad rows of the memory bank and of c_seq: zeros
+    if (s0 + s >= n) break;
+    const int npad = (L - slen[s]) * h;
+    const size_t base = ((size_t)(s0 + s) * L + slen[s]) * Hout + dir * h;
+    for (int i = tid; i < npad; i += 256) {
+      const size_t o = base + (size_t)(i / h) * Hout + (i % h);
+      out[o] = 0.f;
+      c_seq[o] = 0.f;
+    }
+  }
+  __syncthreads();
+  const int maxlen = smaxlen;
+  for (int step = 0; step < maxlen; ++step) {
+    for (int r = tid; r < G; r += 256) {
+      float acc[TS];
+#pragma unroll
+      for (int s = 0; s < TS; ++s) {
+        const int l = slen[s];
+        acc[s] = step < l ? gates[((size_t)(s0 + s) * L + (dir ? l - 1 - step : step)) * PG + dir * G + r] : 0.f;
+      }
+      for (int k = 0; k < h; ++k) {
+        const float w0 = W[(size_t)k * G + r];
+#pragma unroll
+        for (int s = 0; s < TS; ++s) acc[s] = fmaf(w0, hprev[s * hp + k], acc[s]);
+      }
+#pragma unroll
+      for (int s = 0; s < TS; ++s) gs[s * G + r] = acc[s];
+    }
+    __syncthreads();
+    for (int i = tid; i < TS * h; i += 256) {
+      const int s = i / h, u = i - s * h, l = slen[s];
+      if (step < l) {
+        const float* g = gs + s * G;
+        const float ig = 1.f / (1.f + expf(-g[u])), fg = 1.f / (1.f + expf(-g[h + u]));
+        const float gg = tanhf(g[2 * h + u]), og = 1.f / (1.f + expf(-g[3 * h + u]));
+        const float c = fg * cst[i] + ig * gg;
+        const float hv = og * tanhf(c);
+        cst[i] = c;
+        hprev[s * hp + u] = hv;
+        const size_t row = (size_t)(s0 + s) * L + (dir ? l - 1 - step : step);
+        float* gp = gates + row * PG + dir * G;
+        gp[u] = ig, gp[h + u] = fg, gp[2 * h + u] = gg, gp[3 * h + u] = og;
+        out[row * Hout + dir * h + u] = hv;
+        c_seq[row * Hout + dir * h + u] = c;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// BPTT: `gates` holds the activations on entry and the pre-activation gradients dL/da (zero at t >= len) on exit.
+// denc [n*L, dirs*h]: gradient of the memory bank.  w_hh [dirs][4h][h] (torch layout).
+template <bool WSMEM>
+__global__ void __launch_bounds__(256) lstm_train_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_seq,
+                                                             const float* __restrict__ denc, const float* __restrict__ w_hh,
+                                                             const int64_t* __restrict__ len, int n, int L, int h, int dirs) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int TS = TR_TS;
+  const int G = 4 * h, PG = dirs * G, Hout = dirs * h;
+  const int dir = blockIdx.y, s0 = blockIdx.x * TS, tid = threadIdx.x;
+  float* wsm = smem;                                         // [G][h]
+  float* da = smem + (WSMEM ? (size_t)G * h : 0);            // [G][TS]
+  float* dh = da + (size_t)G * TS;                           // [TS][h]
+  float* dc = dh + TS * h;                                   // [TS][h]
+  float* part = dc + TS * h;                                 // [4][TS][h] partial sums of the W_hh^T product
+  __shared__ int slen[TS];
+  __shared__ int smaxlen;
+  const float* wg = w_hh + (size_t)dir * G * h;
+  if (WSMEM)
+    for (int i = tid; i < G * h; i += 256) wsm[i] = wg[i];
+  const float* W = WSMEM ? wsm : wg;
+  for (int i = tid; i < TS * h; i += 256) dh[i] = 0.f, dc[i] = 0.f;
+  if (tid < TS) {
+    int s = s0 + tid, l = 0;
+    if (s < n) {
+      int64_t ll = len[s];
+      ll = ll < 1 ? 1 : (ll > L ? L : ll);
+      l = (int)ll;
+    }
+    slen[tid] = l;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int m = 0;
+    for (int s = 0; s < TS; ++s) m = max(m, slen[s]);
+    smaxlen = m;
+  }
+  for (int s = 0; s < TS; ++s) {   // pad rows: zero gate gradients (the weight-gradient GEMMs sum over all rows)
+    if (s0 + s >= n) break;
+    const int npad = (L - slen[s]) * G;
+    float* base = gates + ((size_t)(s0 + s) * L + slen[s]) * PG + dir * G;
+    for (int i = tid; i < npad; i += 256) base[(size_t)(i / G) * PG + (i % G)] = 0.f;
+  }
+  __syncthreads();
+  const int maxlen = smaxlen;
+  for (int step = maxlen - 1; step >= 0; --step) {
+    for (int i = tid; i < TS * h; i += 256) {
+      const int s = i / h, u = i - s * h, l = slen[s];
+      float ai = 0.f, af = 0.f, ag = 0.f, ao = 0.f;
+      if (step < l) {
+        const int t = dir ? l - 1 - step : step;
+        const size_t row = (size_t)(s0 + s) * L + t;
+        float* gp = gates + row * PG + dir * G;
+        const float gi = gp[u], gf = gp[h + u], gg = gp[2 * h + u], go = gp[3 * h + u];
+        const float c = c_seq[row * Hout + dir * h + u];
+        const float cprev = step > 0 ? c_seq[(dir ? row + 1 : row - 1) * Hout + dir * h + u] : 0.f;
+        const float dht = denc[row * Hout + dir * h + u] + dh[i];
+        const float tc = tanhf(c);
+        const float dct = dc[i] + dht * go * (1.f - tc * tc);
+        ai = dct * gg * gi * (1.f - gi);
+        af = dct * cprev * gf * (1.f - gf);
+        ag = dct * gi * (1.f - gg * gg);
+        ao = dht * tc * go * (1.f - go);
+        dc[i] = dct * gf;
+        gp[u] = ai, gp[h + u] = af, gp[2 * h + u] = ag, gp[3 * h + u] = ao;
+      }
+      da[(size_t)u * TS + s] = ai;
+      da[(size_t)(h + u) * TS + s] = af;
+      da[(size_t)(2 * h + u) * TS + s] = ag;
+      da[(size_t)(3 * h + u) * TS + s] = ao;
+    }
+    __syncthreads();
+    // dh[s][k] = sum_r da[r][s] W[r][k]: thread (k, group grp of gate rows) for all TS sequences
+    for (int idx = tid; idx < 4 * h; idx += 256) {
+      const int grp = idx / h, k = idx - grp * h;
+      float acc[TS];
+#pragma unroll
+      for (int s = 0; s < TS; ++s) acc[s] = 0.f;
+      const int r_lo = grp * h, r_hi = r_lo + h;   // one gate type per thread group
+      for (int r = r_lo; r < r_hi; ++r) {
+        const float w0 = W[(size_t)r * h + k];
+        const float4 d0 = *reinterpret_cast<const float4*>(&da[(size_t)r * TS]);
+        const float4 d1 = *reinterpret_cast<const float4*>(&da[(size_t)r * TS + 4]);
+        acc[0] = fmaf(w0, d0.x, acc[0]), acc[1] = fmaf(w0, d0.y, acc[1]), acc[2] = fmaf(w0, d0.z, acc[2]);
+        acc[3] = fmaf(w0, d0.w, acc[3]), acc[4] = fmaf(w0, d1.x, acc[4]), acc[5] = fmaf(w0, d1.y, acc[5]);
+        acc[6] = fmaf(w0, d1.z, acc[6]), acc[7] = fmaf(w0, d1.w, acc[7]);
+      }
+#pragma unroll
+      for (int s = 0; s < TS; ++s) part[((size_t)grp * TS + s) * h + k] = acc[s];
+    }
+    __syncthreads();
+    for (int i = tid; i < TS * h; i += 256)
+      dh[i] = part[i] + part[(size_t)TS * h + i] + part[(size_t)2 * TS * h + i] + part[(size_t)3 * TS * h + i];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// merged stencil for the sparse interaction backward: W7[(a*7+bt)*C1 + c][FPP] (f fastest, raw weights, no alpha)
+__global__ void mt_train_pack_kernel(const float* __restrict__ c1, const float* __restrict__ c2, const float* __restrict__ c3,
+                                     int C1, int nf, int FP, int FPP, float* __restrict__ w7) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 21 * C1 * FPP) return;
+  const int f = idx % FPP, c = (idx / FPP) % C1, bt = (idx / (FPP * C1)) % 7, a = idx / (FPP * C1 * 7);
+  float v = 0.f;
+  if (f < FP) {
+    const int k = f / nf, ff = f - k * nf, kw = 3 + 2 * k, bb = bt - (2 - k);
+    const float* w = k == 0 ? c1 : (k == 1 ? c2 : c3);
+    if (bb >= 0 && bb < kw) v = w[(((size_t)ff * C1 + c) * 3 + a) * kw + bb];
+  }
+  w7[idx] = v;
+}
+
+struct MtGradPtrs {
+  float *conv1_w, *conv2_w, *conv3_w, *conv1_b, *conv2_b, *conv3_b, *conv_w, *conv_b, *out_w, *out_b, *alpha;
+};
+constexpr int TRB_MAXT = 6;    // taps per thread: ceil(21 * 65 / 256)
+constexpr int TRB_MAXF = 24;
+
+// smem: dW7 [21*C1*FPP] | y [FPP] | red [8][FPP] | dw1 [M*FP] | db1 [M] | dwo [M] | dbias [FP] | misc [4] | qids [Lq] | dids [Ld]
+__global__ void __launch_bounds__(256) mt_train_interact_bwd_kernel(
+    const float* __restrict__ cq, const float* __restrict__ cd, const int64_t* __restrict__ q, const int64_t* __restrict__ d,
+    const float* __restrict__ dscores, const float* __restrict__ pooled, const int* __restrict__ argidx,
+    const float* __restrict__ w7, const float* __restrict__ cbias1, const float* __restrict__ cbias2,
+    const float* __restrict__ cbias3, const float* __restrict__ w1, const float* __restrict__ wo,
+    const float* __restrict__ alpha_p, int N, int Lq, int Ld, int C, int nf, int M, int64_t pairs, float* __restrict__ dcq,
+    float* __restrict__ dcd, MtGradPtrs g) {
+  extern __shared__ __align__(16) float sm[];
+  const int C1 = C + 1, FP = 3 * nf, FPP = (FP + 3) & ~3, NT = 21 * C1;
+  float* dW7 = sm;
+  float* ysm = dW7 + (size_t)NT * FPP;
+  float* red = ysm + FPP;
+  float* dw1 = red + 8 * FPP;
+  float* db1 = dw1 + M * FP;
+  float* dwo = db1 + M;
+  float* dbias = dwo + M;
+  float* misc = dbias + FP;     // [0] d alpha, [1] d output bias
+  int* qids = reinterpret_cast<int*>(misc + 4);
+  int* dids = qids + Lq;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float alpha = alpha_p[0];
+  for (int i = tid; i < NT * FPP + FPP + 8 * FPP + M * FP + 2 * M + FP + 4; i += 256) sm[i] = 0.f;
+  __syncthreads();
+  float dalpha_loc = 0.f;
+  for (int64_t p = blockIdx.x; p < pairs; p += gridDim.x) {
+    const int64_t b = p / N;
+    __syncthreads();
+    for (int i = tid; i < Lq; i += 256) qids[i] = (int)q[b * Lq + i];
+    for (int i = tid; i < Ld; i += 256) dids[i] = (int)d[p * Ld + i];
+    const float ds = dscores[p];
+    if (tid < M) dwo[tid] += ds * pooled[p * M + tid];
+    if (tid == 0) misc[1] += ds;
+    __syncthreads();
+    for (int m = 0; m < M; ++m) {
+      const int cell = argidx[p * M + m];
+      const int is = cell / Ld, js = cell - is * Ld;
+      const float dz = ds * wo[m];
+      float mtv[TRB_MAXT], cqv[TRB_MAXT], cdv[TRB_MAXT];
+      float acc[TRB_MAXF];
+#pragma unroll
+      for (int f = 0; f < TRB_MAXF; ++f) acc[f] = 0.f;
+#pragma unroll
+      for (int k = 0; k < TRB_MAXT; ++k) {
+        const int tap = tid + k * 256;
+        mtv[k] = 0.f, cqv[k] = 0.f, cdv[k] = 0.f;
+        if (tap < NT) {
+          const int c = tap % C1, ab = tap / C1, a = ab / 7, bt = ab - a * 7;
+          const int ii = is + a - 1, jj = js + bt - 3;
+          if (ii >= 0 && ii < Lq && jj >= 0 && jj < Ld) {
+            if (c < C) {
+              cqv[k] = cq[((size_t)b * Lq + ii) * C + c];
+              cdv[k] = cd[((size_t)p * Ld + jj) * C + c];
+              mtv[k] = cqv[k] * cdv[k];
+            } else {
+              cqv[k] = qids[ii] == dids[jj] ? 1.f : 0.f;   // the match indicator
+              mtv[k] = alpha * cqv[k];
+            }
+            const float* wr = w7 + (size_t)tap * FPP;
+#pragma unroll
+            for (int f = 0; f < TRB_MAXF; ++f)
+              if (f < FPP) acc[f] = fmaf(wr[f], mtv[k], acc[f]);
+          }
+        }
+      }
+#pragma unroll
+      for (int f = 0; f < TRB_MAXF; ++f) {
+        if (f < FPP) {
+          const float v = warp_sum(acc[f]);
+          if (lane == 0) red[warp * FPP + f] = v;
+        }
+      }
+      __syncthreads();
+      if (tid < FP) {
+        const int k = tid / nf, ff = tid - k * nf;
+        float y = (k == 0 ? cbias1 : (k == 1 ? cbias2 : cbias3))[ff];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) y += red[w * FPP + tid];
+        const float g1 = y > 0.f ? w1[m * FP + tid] * dz : 0.f;
+        ysm[tid] = g1;
+        dw1[m * FP + tid] += dz * fmaxf(y, 0.f);
+        dbias[tid] += g1;
+      } else if (tid >= FP && tid < FPP) {
+        ysm[tid] = 0.f;
+      }
+      if (tid == 255) db1[m] += dz;
+      __syncthreads();
+      float g1[TRB_MAXF];
+#pragma unroll
+      for (int f = 0; f < TRB_MAXF; ++f) g1[f] = f < FPP ? ysm[f] : 0.f;
+#pragma unroll
+      for (int k = 0; k < TRB_MAXT; ++k) {
+        const int tap = tid + k * 256;
+        if (tap < NT && (mtv[k] != 0.f || cqv[k] != 0.f || cdv[k] != 0.f)) {
+          const int c = tap % C1, ab = tap / C1, a = ab / 7, bt = ab - a * 7;
+          const int ii = is + a - 1, jj = js + bt - 3;
+          const float* wr = w7 + (size_t)tap * FPP;
+          float* dwr = dW7 + (size_t)tap * FPP;
+          float dmt = 0.f;
+#pragma unroll
+          for (int f = 0; f < TRB_MAXF; ++f) {
+            if (f < FPP) {
+              dwr[f] = fmaf(g1[f], mtv[k], dwr[f]);
+              dmt = fmaf(wr[f], g1[f], dmt);
+            }
+          }
+          if (c < C) {
+            if (dmt != 0.f) {
+              atomicAdd(&dcq[((size_t)b * Lq + ii) * C + c], dmt * cdv[k]);
+              atomicAdd(&dcd[((size_t)p * Ld + jj) * C + c], dmt * cqv[k]);
+            }
+          } else {
+            dalpha_loc += dmt * cqv[k];
+          }
+        }
+      }
+    }
+  }
+  // flush the CTA's accumulators
+  dalpha_loc = warp_sum(dalpha_loc);
+  if (lane == 0 && dalpha_loc != 0.f) atomicAdd(&misc[0], dalpha_loc);
+  __syncthreads();
+  for (int i = tid; i < NT * FPP; i += 256) {
+    const float v = dW7[i];
+    if (v == 0.f) continue;
+    const int f = i % FPP, tap = i / FPP;
+    if (f >= FP) continue;
+    const int c = tap % C1, ab = tap / C1, a = ab / 7, bt = ab - a * 7;
+    const int k = f / nf, ff = f - k * nf, kw = 3 + 2 * k, bb = bt - (2 - k);
+    if (bb < 0 || bb >= kw) continue;
+    float* gw = k == 0 ? g.conv1_w : (k == 1 ? g.conv2_w : g.conv3_w);
+    atomicAdd(&gw[(((size_t)ff * C1 + c) * 3 + a) * kw + bb], v);
+  }
+  for (int i = tid; i < M * FP; i += 256)
+    if (dw1[i] != 0.f) atomicAdd(&g.conv_w[i], dw1[i]);
+  for (int i = tid; i < M; i += 256) {
+    atomicAdd(&g.conv_b[i], db1[i]);
+    atomicAdd(&g.out_w[i], dwo[i]);
+  }
+  for (int i = tid; i < FP; i += 256) {
+    const int k = i / nf, ff = i - k * nf;
+    atomicAdd(&(k == 0 ? g.conv1_b : (k == 1 ? g.conv2_b : g.conv3_b))[ff], dbias[i]);
+  }
+  if (tid == 0) {
+    atomicAdd(g.alpha, misc[0]);
+    atomicAdd(g.out_b, misc[1]);
+  }
+}
+
+// d table[id[r], e] += mask(r, e) * sum_f df[r, f] Wp[f, e]   (PAD rows receive no gradient: nn.Embedding padding_idx)
+__global__ void __launch_bounds__(256) embed_grad_kernel(const float* __restrict__ df, const float* __restrict__ wp,
+                                                         const int64_t* __restrict__ ids, int V, int E, int F, int64_t rows,
+                                                         int64_t row0, float p, uint64_t seed, float* __restrict__ dtable) {
+  extern __shared__ __align__(16) float sm[];
+  float* dfr = sm;   // [8][F]
+  const float inv = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  const int tid = threadIdx.x;
+  for (int64_t r0 = (int64_t)blockIdx.x * 8; r0 < rows; r0 += (int64_t)gridDim.x * 8) {
+    __syncthreads();
+    for (int i = tid; i < 8 * F; i += 256) {
+      const int64_t r = r0 + i / F;
+      dfr[i] = r < rows ? df[r * F + (i % F)] : 0.f;
+    }
+    __syncthreads();
+    for (int e = tid; e < E; e += 256) {
+      float acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+      for (int f = 0; f < F; ++f) {
+        const float w = wp[(size_t)f * E + e];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(w, dfr[k * F + f], acc[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int64_t r = r0 + k;
+        if (r >= rows) break;
+        const int64_t id = ids[r];
+        if (id <= 0 || id >= V) continue;   // PAD (0) and invalid ids
+        const float v = acc[k] * drop_scale(seed, (uint64_t)((row0 + r) * E + e), p, inv);
+        if (v != 0.f) atomicAdd(&dtable[id * E + e], v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct MtTrainer {
+  int device = 0;
+  cair_mt_weights w{};    // LIVE parameter pointers (read at every step)
+  Owned own;
+  MtPack pack{};          // forward interaction weights (re-packed every step)
+  float* w7 = nullptr;    // merged stencil for the backward
+  float *whht_q = nullptr, *whht_d = nullptr;   // [dirs][h][4h]
+  float *bias_q = nullptr, *bias_d = nullptr;   // [dirs][4h] b_ih + b_hh
+  float *wiht_q = nullptr, *wiht_d = nullptr;   // [F][dirs*4h]
+  float *wqt = nullptr, *wdt = nullptr;         // [Hq][C], [Hd][C]
+  int dirs = 1, hq = 0, hd = 0;
+};
+
+struct MtTrainWs {
+  int* err;
+  float *xq, *xd, *fq, *fd, *gq, *gd, *cseq_q, *cseq_d, *enc_q, *enc_d, *cq, *cd, *T, *pooled;
+  int* argidx;
+  float *dcq, *dcd, *denc_q, *denc_d, *dfq, *dfd;
+};
+
+static void mt_train_layout(const MtTrainer& t, Arena& a, int B, int N, int Lq, int Ld, MtTrainWs* o) {
+  const size_t Rq = (size_t)B * Lq, Rd = (size_t)B * N * Ld, P = (size_t)B * N;
+  const cair_mt_weights& w = t.w;
+  o->err = a.take<int>(64);
+  o->xq = a.take<float>(Rq * w.emsize), o->xd = a.take<float>(Rd * w.emsize);
+  o->fq = a.take<float>(Rq * w.featsize), o->fd = a.take<float>(Rd * w.featsize);
+  o->gq = a.take<float>(Rq * t.dirs * 4 * t.hq), o->gd = a.take<float>(Rd * t.dirs * 4 * t.hd);
+  o->cseq_q = a.take<float>(Rq * w.nhid_query), o->cseq_d = a.take<float>(Rd * w.nhid_doc);
+  o->enc_q = a.take<float>(Rq * w.nhid_query), o->enc_d = a.take<float>(Rd * w.nhid_doc);
+  o->cq = a.take<float>(Rq * w.nchannels), o->cd = a.take<float>(Rd * w.nchannels);
+  o->T = a.take<float>(mt_t_floats(t.pack, B, Lq));
+  o->pooled = a.take<float>(P * w.match_filter_size);
+  o->argidx = a.take<int>(P * w.match_filter_size);
+  o->dcq = a.take<float>(Rq * w.nchannels), o->dcd = a.take<float>(Rd * w.nchannels);
+  o->denc_q = a.take<float>(Rq * w.nhid_query), o->denc_d = a.take<float>(Rd * w.nhid_doc);
+  o->dfq = a.take<float>(Rq * w.featsize), o->dfd = a.take<float>(Rd * w.featsize);
+}
+
+static int32_t lstm_train_fwd(float* gates, const float* whht, const int64_t* len, int n, int L, int h, int dirs, float* out,
+                              float* c_seq, int* err, cudaStream_t s) {
+  const int G = 4 * h, hp = (h + 3) & ~3;
+  const size_t wbytes = (size_t)h * G * sizeof(float);
+  const size_t rest = ((size_t)TR_TS * hp + TR_TS * h + TR_TS * G) * sizeof(float);
+  const bool wsmem = wbytes + rest <= 200 * 1024;
+  const size_t smem = (wsmem ? wbytes : 0) + rest;
+  dim3 grid((n + TR_TS - 1) / TR_TS, dirs);
+  if (wsmem) {
+    CAIR_CUDA(cudaFuncSetAttribute(lstm_train_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CAIR_LAUNCH(lstm_train_fwd_kernel<true>, grid, 256, smem, s, gates, whht, len, n, L, h, dirs, out, c_seq, err);
+  } else {
+    CAIR_CUDA(cudaFuncSetAttribute(lstm_train_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CAIR_LAUNCH(lstm_train_fwd_kernel<false>, grid, 256, smem, s, gates, whht, len, n, L, h, dirs, out, c_seq, err);
+  }
+  return CAIR_OK;
+}
+
+static int32_t lstm_train_bwd(float* gates, const float* c_seq, const float* denc, const float* w_hh_fwd, const float* w_hh_rev,
+                              float* whh_scratch, const int64_t* len, int n, int L, int h, int dirs, cudaStream_t s) {
+  // the kernel wants [dirs][4h][h] contiguous: the two directions are separate parameters, so stage them side by side
+  const int G = 4 * h;
+  CAIR_CUDA(cudaMemcpyAsync(whh_scratch, w_hh_fwd, (size_t)G * h * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (dirs == 2)
+    CAIR_CUDA(cudaMemcpyAsync(whh_scratch + (size_t)G * h, w_hh_rev, (size_t)G * h * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  const size_t wbytes = (size_t)G * h * sizeof(float);
+  const size_t rest = ((size_t)G * TR_TS + 2 * TR_TS * h + 4 * TR_TS * h) * sizeof(float);
+  const bool wsmem = wbytes + rest <= 200 * 1024;
+  const size_t smem = (wsmem ? wbytes : 0) + rest;
+  dim3 grid((n + TR_TS - 1) / TR_TS, dirs);
+  if (wsmem) {
+    CAIR_CUDA(cudaFuncSetAttribute(lstm_train_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CAIR_LAUNCH(lstm_train_bwd_kernel<true>, grid, 256, smem, s, gates, c_seq, denc, whh_scratch, len, n, L, h, dirs);
+  } else {
+    CAIR_CUDA(cudaFuncSetAttribute(lstm_train_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CAIR_LAUNCH(lstm_train_bwd_kernel<false>, grid, 256, smem, s, gates, c_seq, denc, whh_scratch, len, n, L, h, dirs);
+  }
+  return CAIR_OK;
+}
+
+static int32_t refresh_lstm(const cair_lstm_dir& fwd, const cair_lstm_dir& rev, int dirs, int in, int h, float* whht, float* bias,
+                            float* wiht, cudaStream_t s) {
+  const int G = 4 * h;
+  for (int dd = 0; dd < dirs; ++dd) {
+    const cair_lstm_dir& w = dd ? rev : fwd;
+    CAIR_LAUNCH(transpose_kernel, (G * h + 255) / 256, 256, 0, s, w.w_hh, G, h, whht + (size_t)dd * h * G, (int64_t)G);
+    CAIR_LAUNCH(add_vec_kernel, (G + 255) / 256, 256, 0, s, w.b_ih, w.b_hh, G, bias + (size_t)dd * G);
+    // wiht[f][dd*G + g] = w_ih[g][f]
+    CAIR_LAUNCH(transpose_kernel, (G * in + 255) / 256, 256, 0, s, w.w_ih, G, in, wiht + (size_t)dd * G, (int64_t)dirs * G);
+  }
+  return CAIR_OK;
+}
+
+int32_t mt_repack(const cair_mt_weights& w, MtPack* p, cudaStream_t s);   // mt.cu
+int32_t mt_interact_train(const MtPack& p, const float* cq, const float* cd, float* T, const int64_t* q, const int64_t* d, int N,
+                          int Lq, int Ld, int64_t pairs, int64_t nq, float* scores, float* pooled, int* argidx,
+                          cudaStream_t s);   // mt.cu
+
+}  // namespace cair
+
+using namespace cair;
+
+struct cair_mt_trainer {
+  MtTrainer t;
+  float* whh_scratch = nullptr;
+};
+
+namespace {
+struct DevGuard {
+  int prev = -1;
+  explicit DevGuard(int dev) {
+    cudaGetDevice(&prev);
+    cudaSetDevice(dev);
+  }
+  ~DevGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+}  // namespace
+
+extern "C" {
+
+int32_t cair_dropout_mask(uint64_t seed, float p, int64_t n, float* out, void* stream) {
+  if (!out || n < 0 || p < 0.f || p > 1.f) return fail(CAIR_ERR_BAD_ARG, "dropout_mask: bad argument");
+  if (n == 0) return CAIR_OK;
+  CAIR_LAUNCH(dropout_mask_kernel, 592, 256, 0, (cudaStream_t)stream, seed, p, n, out);
+  return CAIR_OK;
+}
+
+int32_t cair_mt_train_create(const cair_mt_weights* w, int32_t device, cair_mt_trainer** out) {
+  if (!w || !out) return fail(CAIR_ERR_BAD_ARG, "mt_train_create: null argument");
+  if (w->rnn_type != CAIR_RNN_LSTM) return fail(CAIR_ERR_UNSUPPORTED, "mt_train: only LSTM encoders have a backward pass");
+  DevGuard g(device);
+  cair_mt_trainer* h = new cair_mt_trainer();
+  MtTrainer& t = h->t;
+  t.device = device, t.w = *w, t.dirs = w->bidirectional ? 2 : 1;
+  t.hq = w->nhid_query / t.dirs, t.hd = w->nhid_doc / t.dirs;
+  cudaStream_t s = 0;
+  auto body = [&]() -> int32_t {
+    CAIR_TRY(mt_pack(t.own, *w, &t.pack, s));
+    const int C1 = w->nchannels + 1, FPP = t.pack.FPP;
+    if (21 * C1 > TRB_MAXT * 256) return fail(CAIR_ERR_UNSUPPORTED, "mt_train: nchannels %d too large", w->nchannels);
+    CAIR_CUDA(t.own.alloc(&t.w7, (size_t)21 * C1 * FPP));
+    CAIR_CUDA(t.own.alloc(&t.whht_q, (size_t)t.dirs * t.hq * 4 * t.hq));
+    CAIR_CUDA(t.own.alloc(&t.whht_d, (size_t)t.dirs * t.hd * 4 * t.hd));
+    CAIR_CUDA(t.own.alloc(&t.bias_q, (size_t)t.dirs * 4 * t.hq));
+    CAIR_CUDA(t.own.alloc(&t.bias_d, (size_t)t.dirs * 4 * t.hd));
+    CAIR_CUDA(t.own.alloc(&t.wiht_q, (size_t)w->featsize * t.dirs * 4 * t.hq));
+    CAIR_CUDA(t.own.alloc(&t.wiht_d, (size_t)w->featsize * t.dirs * 4 * t.hd));
+    CAIR_CUDA(t.own.alloc(&t.wqt, (size_t)w->nhid_query * w->nchannels));
+    CAIR_CUDA(t.own.alloc(&t.wdt, (size_t)w->nhid_doc * w->nchannels));
+    const int hm = t.hq > t.hd ? t.hq : t.hd;
+    CAIR_CUDA(t.own.alloc(&h->whh_scratch, (size_t)t.dirs * 4 * hm * hm));
+    CAIR_CUDA(cudaStreamSynchronize(s));
+    return CAIR_OK;
+  };
+  const int32_t rc = body();
+  if (rc != CAIR_OK) {
+    t.own.release();
+    delete h;
+    *out = nullptr;
+    return rc;
+  }
+  *out = h;
+  return CAIR_OK;
+}
+
+int32_t cair_mt_train_destroy(cair_mt_trainer* h) {
+  if (!h) return CAIR_OK;
+  DevGuard g(h->t.device);
+  cudaDeviceSynchronize();
+  h->t.own.release();
+  delete h;
+  return CAIR_OK;
+}
+
+int32_t cair_mt_train_workspace_bytes(cair_mt_trainer* h, int32_t B, int32_t N, int32_t Lq, int32_t Ld, size_t* bytes) {
+  if (!h || !bytes || B <= 0 || N <= 0 || Lq <= 0 || Ld <= 0) return fail(CAIR_ERR_BAD_ARG, "mt_train_workspace_bytes: bad argument");
+  Arena a(nullptr, 0);
+  MtTrainWs o;
+  mt_train_layout(h->t, a, B, N, Lq, Ld, &o);
+  *bytes = align_up(a.off) + 256;
+  return CAIR_OK;
+}
+
+int32_t cair_mt_train_forward(cair_mt_trainer* h, const int64_t* q, const int64_t* qlen, const int64_t* d, const int64_t* dlen,
+                              int32_t B, int32_t N, int32_t Lq, int32_t Ld, float p_drop, uint64_t seed, float* scores, void* ws,
+                              size_t ws_bytes, void* stream) {
+  if (!h || !q || !qlen || !d || !dlen || !scores || !ws) return fail(CAIR_ERR_BAD_ARG, "mt_train_forward: null argument");
+  if (p_drop < 0.f || p_drop >= 1.f) return fail(CAIR_ERR_BAD_ARG, "mt_train_forward: dropout must be in [0, 1)");
+  if ((uintptr_t)ws % 256) return fail(CAIR_ERR_WORKSPACE, "mt_train_forward: workspace must be 256-byte aligned");
+  MtTrainer& t = h->t;
+  DevGuard g(t.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const cair_mt_weights& w = t.w;
+  Arena a(ws, ws_bytes);
+  MtTrainWs o;
+  mt_train_layout(t, a, B, N, Lq, Ld, &o);
+  if (!a.ok()) return fail(CAIR_ERR_WORKSPACE, "mt_train_forward: workspace too small (%zu < %zu)", ws_bytes, a.off);
+  const int64_t Rq = (int64_t)B * Lq, Rd = (int64_t)B * N * Ld, P = (int64_t)B * N;
+  const int E = w.emsize, F = w.featsize, C = w.nchannels, Hq = w.nhid_query, Hd = w.nhid_doc;
+  CAIR_CUDA(cudaMemsetAsync(o.err, 0, 256, s));
+  // weights change every step: refresh the repacked copies from the live parameters
+  CAIR_TRY(mt_repack(w, &t.pack, s));
+  CAIR_LAUNCH(mt_train_pack_kernel, (21 * (C + 1) * t.pack.FPP + 255) / 256, 256, 0, s, w.conv1.w, w.conv2.w, w.conv3.w, C + 1,
+              w.nfilters, t.pack.FP, t.pack.FPP, t.w7);
+  CAIR_TRY(refresh_lstm(w.query_fwd, w.query_rev, t.dirs, F, t.hq, t.whht_q, t.bias_q, t.wiht_q, s));
+  CAIR_TRY(refresh_lstm(w.doc_fwd, w.doc_rev, t.dirs, F, t.hd, t.whht_d, t.bias_d, t.wiht_d, s));
+  CAIR_LAUNCH(transpose_kernel, (C * Hq + 255) / 256, 256, 0, s, w.query_projection.w, C, Hq, t.wqt, (int64_t)C);
+  CAIR_LAUNCH(transpose_kernel, (C * Hd + 255) / 256, 256, 0, s, w.document_projection.w, C, Hd, t.wdt, (int64_t)C);
+  // embedding + dropout (mtensor.py:77-84), linear_projection (:88-90)
+  CAIR_LAUNCH(embed_drop_kernel, 1184, 256, 0, s, w.table, q, w.vocab, E, Rq, (int64_t)0, p_drop, seed, o.xq, o.err);
+  CAIR_LAUNCH(embed_drop_kernel, 1184, 256, 0, s, w.table, d, w.vocab, E, Rd, Rq, p_drop, seed, o.xd, o.err);
+  CAIR_TRY(gemm_f32(gemm_dense(o.xq, E), w.linear_projection.w, w.linear_projection.b, o.fq, F, Rq, F, E, ACT_NONE, s));
+  CAIR_TRY(gemm_f32(gemm_dense(o.xd, E), w.linear_projection.w, w.linear_projection.b, o.fd, F, Rd, F, E, ACT_NONE, s));
+  // encoders (:93-94)
+  for (int dd = 0; dd < t.dirs; ++dd) {
+    const int Gq = 4 * t.hq, Gd = 4 * t.hd;
+    CAIR_TRY(gemm_f32(gemm_dense(o.fq, F), (dd ? w.query_rev : w.query_fwd).w_ih, t.bias_q + (size_t)dd * Gq, o.gq + (size_t)dd * Gq,
+                      (int64_t)t.dirs * Gq, Rq, Gq, F, ACT_NONE, s));
+    CAIR_TRY(gemm_f32(gemm_dense(o.fd, F), (dd ? w.doc_rev : w.doc_fwd).w_ih, t.bias_d + (size_t)dd * Gd, o.gd + (size_t)dd * Gd,
+                      (int64_t)t.dirs * Gd, Rd, Gd, F, ACT_NONE, s));
+  }
+  CAIR_TRY(lstm_train_fwd(o.gq, t.whht_q, qlen, B, Lq, t.hq, t.dirs, o.enc_q, o.cseq_q, o.err, s));
+  CAIR_TRY(lstm_train_fwd(o.gd, t.whht_d, dlen, (int)P, Ld, t.hd, t.dirs, o.enc_d, o.cseq_d, o.err, s));
+  // channel projections (:99, :108)
+  CAIR_TRY(gemm_f32(gemm_dense(o.enc_q, Hq), w.query_projection.w, w.query_projection.b, o.cq, C, Rq, C, Hq, ACT_NONE, s));
+  CAIR_TRY(gemm_f32(gemm_dense(o.enc_d, Hd), w.document_projection.w, w.document_projection.b, o.cd, C, Rd, C, Hd, ACT_NONE, s));
+  // interaction (:113-131) with the arg-max cells of the two max-pools
+  return mt_interact_train(t.pack, o.cq, o.cd, o.T, q, d, N, Lq, Ld, P, B, scores, o.pooled, o.argidx, s);
+}
+
+static float* gp(const float* p) { return const_cast<float*>(p); }
+
+int32_t cair_mt_train_backward(cair_mt_trainer* h, const int64_t* q, const int64_t* qlen, const int64_t* d, const int64_t* dlen,
+                               int32_t B, int32_t N, int32_t Lq, int32_t Ld, float p_drop, uint64_t seed, const float* dscores,
+                               const cair_mt_weights* grads, void* ws, size_t ws_bytes, void* stream) {
+  if (!h || !q || !qlen || !d || !dlen || !dscores || !grads || !ws) return fail(CAIR_ERR_BAD_ARG, "mt_train_backward: null argument");
+  MtTrainer& t = h->t;
+  DevGuard g(t.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const cair_mt_weights& w = t.w;
+  const cair_mt_weights& G = *grads;
+  if (!G.linear_projection.w || !G.linear_projection.b || !G.query_projection.w || !G.query_projection.b ||
+      !G.document_projection.w || !G.document_projection.b || !G.alpha || !G.conv1.w || !G.conv2.w || !G.conv3.w || !G.conv1.b ||
+      !G.conv2.b || !G.conv3.b || !G.conv.w || !G.conv.b || !G.output.w || !G.output.b || !G.query_fwd.w_ih || !G.doc_fwd.w_ih)
+    return fail(CAIR_ERR_BAD_ARG, "mt_train_backward: null gradient pointer (only `table` may be NULL: fixed embeddings)");
+  Arena a(ws, ws_bytes);
+  MtTrainWs o;
+  mt_train_layout(t, a, B, N, Lq, Ld, &o);
+  if (!a.ok()) return fail(CAIR_ERR_WORKSPACE, "mt_train_backward: workspace too small");
+  const int64_t Rq = (int64_t)B * Lq, Rd = (int64_t)B * N * Ld, P = (int64_t)B * N;
+  const int E = w.emsize, F = w.featsize, C = w.nchannels, Hq = w.nhid_query, Hd = w.nhid_doc, M = w.match_filter_size;
+  // ---- interaction stack (sparse) ----
+  CAIR_CUDA(cudaMemsetAsync(o.dcq, 0, (size_t)Rq * C * sizeof(float), s));
+  CAIR_CUDA(cudaMemsetAsync(o.dcd, 0, (size_t)Rd * C * sizeof(float), s));
+  {
+    const int C1 = C + 1, FP = t.pack.FP, FPP = t.pack.FPP;
+    const size_t smem = ((size_t)21 * C1 * FPP + FPP + 8 * FPP + (size_t)M * FP + 2 * M + FP + 4) * sizeof(float) +
+                        (size_t)(Lq + Ld) * sizeof(int);
+    if (smem > 220 * 1024) return fail(CAIR_ERR_UNSUPPORTED, "mt_train_backward: stencil does not fit in shared memory");
+    CAIR_CUDA(cudaFuncSetAttribute(mt_train_interact_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MtGradPtrs gpz{gp(G.conv1.w), gp(G.conv2.w), gp(G.conv3.w), gp(G.conv1.b), gp(G.conv2.b), gp(G.conv3.b),
+                   gp(G.conv.w),  gp(G.conv.b),  gp(G.output.w), gp(G.output.b), gp(G.alpha)};
+    const unsigned grid = (unsigned)(P < 2 * kSMs ? P : 2 * kSMs);
+    CAIR_LAUNCH(mt_train_interact_bwd_kernel, grid, 256, smem, s, o.cq, o.cd, q, d, dscores, o.pooled, o.argidx, t.w7, w.conv1.b,
+                w.conv2.b, w.conv3.b, w.conv.w, w.output.w, w.alpha, N, Lq, Ld, C, w.nfilters, M, P, o.dcq, o.dcd, gpz);
+  }
+  // ---- channel projections ----
+  CAIR_TRY(gemm_tn(o.dcq, C, o.enc_q, Hq, 0, Lq, gp(G.query_projection.w), Hq, Rq, C, Hq, s));
+  CAIR_TRY(colsum(o.dcq, C, Rq, C, gp(G.query_projection.b), nullptr, s));
+  CAIR_TRY(gemm_f32(gemm_dense(o.dcq, C), t.wqt, nullptr, o.denc_q, Hq, Rq, Hq, C, ACT_NONE, s));
+  CAIR_TRY(gemm_tn(o.dcd, C, o.enc_d, Hd, 0, Ld, gp(G.document_projection.w), Hd, Rd, C, Hd, s));
+  CAIR_TRY(colsum(o.dcd, C, Rd, C, gp(G.document_projection.b), nullptr, s));
+  CAIR_TRY(gemm_f32(gemm_dense(o.dcd, C), t.wdt, nullptr, o.denc_d, Hd, Rd, Hd, C, ACT_NONE, s));
+  // ---- encoders: BPTT, then the weight gradients as GEMMs over all (sequence, step) rows ----
+  struct Enc {
+    float *gates, *cseq, *denc, *enc, *f, *df, *wiht;
+    const int64_t* len;
+    int n, L, h;
+    int64_t R;
+    const cair_lstm_dir *wf, *wr, *gf, *gr;
+  } encs[2] = {{o.gq, o.cseq_q, o.denc_q, o.enc_q, o.fq, o.dfq, t.wiht_q, qlen, B, Lq, t.hq, Rq, &w.query_fwd, &w.query_rev, &G.query_fwd, &G.query_rev},
+               {o.gd, o.cseq_d, o.denc_d, o.enc_d, o.fd, o.dfd, t.wiht_d, dlen, (int)P, Ld, t.hd, Rd, &w.doc_fwd, &w.doc_rev, &G.doc_fwd, &G.doc_rev}};
+  for (const Enc& e : encs) {
+    const int Gh = 4 * e.h, PG = t.dirs * Gh, Hout = t.dirs * e.h;
+    CAIR_TRY(lstm_train_bwd(e.gates, e.cseq, e.denc, e.wf->w_hh, e.wr->w_hh, h->whh_scratch, e.len, e.n, e.L, e.h, t.dirs, s));
+    for (int dd = 0; dd < t.dirs; ++dd) {
+      const cair_lstm_dir* gw = dd ? e.gr : e.gf;
+      if (!gw->w_ih || !gw->w_hh || !gw->b_ih || !gw->b_hh) return fail(CAIR_ERR_BAD_ARG, "mt_train_backward: null LSTM gradient pointer");
+      const float* dg = e.gates + (size_t)dd * Gh;
+      // h_{t-1} of the forward direction is the bank row before, of the reverse direction the row after
+      CAIR_TRY(gemm_tn(dg, PG, e.enc + (size_t)dd * e.h, Hout, dd ? 1 : -1, e.L, gp(gw->w_hh), e.h, e.R, Gh, e.h, s));
+      CAIR_TRY(gemm_tn(dg, PG, e.f, F, 0, e.L, gp(gw->w_ih), F, e.R, Gh, F, s));
+      CAIR_TRY(colsum(dg, PG, e.R, Gh, gp(gw->b_ih), gp(gw->b_hh), s));
+    }
+    CAIR_TRY(gemm_f32(gemm_dense(e.gates, PG), e.wiht, nullptr, e.df, F, e.R, F, PG, ACT_NONE, s));
+  }
+  // ---- linear_projection and the embedding table ----
+  CAIR_TRY(gemm_tn(o.dfq, F, o.xq, E, 0, Lq, gp(G.linear_projection.w), E, Rq, F, E, s));
+  CAIR_TRY(gemm_tn(o.dfd, F, o.xd, E, 0, Ld, gp(G.linear_projection.w), E, Rd, F, E, s));
+  CAIR_TRY(colsum(o.dfq, F, Rq, F, gp(G.linear_projection.b), nullptr, s));
+  CAIR_TRY(colsum(o.dfd, F, Rd, F, gp(G.linear_projection.b), nullptr, s));
+  if (G.table) {
+    const size_t smem = (size_t)8 * F * sizeof(float);
+    CAIR_LAUNCH(embed_grad_kernel, 1184, 256, smem, s, o.dfq, w.linear_projection.w, q, w.vocab, E, F, Rq, (int64_t)0, p_drop, seed,
+                gp(G.table));
+    CAIR_LAUNCH(embed_grad_kernel, 1184, 256, smem, s, o.dfd, w.linear_projection.w, d, w.vocab, E, F, Rd, Rq, p_drop, seed,
+                gp(G.table));
+  }
+  return CAIR_OK;
+}
+
+/* device error word of the last forward (bad token ids / lengths): synchronises the stream */
+int32_t cair_mt_train_poll_error(cair_mt_trainer* h, void* ws, void* stream) {
+  if (!h || !ws) return fail(CAIR_ERR_BAD_ARG, "mt_train_poll_error: null argument");
+  DevGuard g(h->t.device);
+  int flags = 0;
+  CAIR_CUDA(cudaMemcpyAsync(&flags, ws, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CAIR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (flags & ERRF_BAD_TOKEN) return fail(CAIR_ERR_BAD_ARG, "token id outside [0, vocab)");
+  if (flags & ERRF_BAD_LENGTH) return fail(CAIR_ERR_BAD_ARG, "sequence length outside [1, L]");
+  return CAIR_OK;
+}
+
+}  // extern "C"

@@ -62,6 +62,14 @@ PROTOTYPES = {
                                    vp, C.c_size_t, vp]),
     'cair_cars_set_decoder': (i32, [vp, C.POINTER(_abi.CarsDecoderWeights)]),
     'cair_cars_decode_workspace_bytes': (i32, [vp, i32, i32, i32, C.POINTER(C.c_size_t)]),
+    'cair_mt_train_create': (i32, [C.POINTER(_abi.MtWeights), i32, C.POINTER(vp)]),
+    'cair_mt_train_destroy': (i32, [vp]),
+    'cair_mt_train_workspace_bytes': (i32, [vp, i32, i32, i32, i32, C.POINTER(C.c_size_t)]),
+    'cair_mt_train_forward': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, C.c_float, C.c_uint64, vp, vp, C.c_size_t, vp]),
+    'cair_mt_train_backward': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, C.c_float, C.c_uint64, vp,
+                                     C.POINTER(_abi.MtWeights), vp, C.c_size_t, vp]),
+    'cair_mt_train_poll_error': (i32, [vp, vp, vp]),
+    'cair_dropout_mask': (i32, [C.c_uint64, C.c_float, i64, vp, vp]),
     'cair_cars_decode': (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, i64, vp, vp, C.c_size_t, vp]),
 }
 

@@ -5,8 +5,10 @@ src_vocab_size), same call contract `network(queries, que_len, documents, doc_le
 FloatTensor[B, N]` (neuroir/models/ranker.py:213,257), same parameter names / shapes /
 initialisers as the reference modules, so reference state_dicts load by key.
 The arithmetic is not here: forward() hands device pointers to libcair.so.  Inputs must be CUDA
-tensors; there is no CPU or eager-PyTorch fallback.  Scoring only (eval / no_grad): the backward
-pass is the first "next" row of the scope table.
+tensors; there is no CPU or eager-PyTorch fallback.  In eval mode a module scores through its libcair
+handle; in train mode MatchTensor runs libcair's training step (train-mode forward + hand-written
+backward behind a torch.autograd.Function), so the reference's Ranker.update (loss, backward, clipping,
+optimizer) runs unchanged on top.  The other rankers raise in train mode.
 """
 import ctypes as C
 from collections import OrderedDict
@@ -97,7 +99,7 @@ def _named_tensors(module, prefix=''):
             yield from _named_tensors(child, prefix + name + '.')
 
 
-_HANDLE_KEYS = ('_cair_handle', '_cair_key', '_cair_ws')
+_HANDLE_KEYS = ('_cair_handle', '_cair_key', '_cair_ws', '_cair_trainer', '_cair_trainer_key')
 
 
 def _ptr_getter(module, keep):
@@ -202,10 +204,11 @@ class _Ranker(_CairModule):
     def forward(self, batch_queries, query_len, batch_docs, doc_len, pair_slice=None):
         """scores[B, N] (fp32, no softmax).  pair_slice=(begin, count) scores only that contiguous
         slice of the flattened pairs (doc-parallel sharding); the rest of the output is left zero."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError('training through libcair is not implemented yet (scoring path only); '
-                                      'call under torch.no_grad() / .eval()')
         assert batch_queries.shape[0] == batch_docs.shape[0]  # rankers/*.py, e.g. mtensor.py:71
+        if self.training:
+            if pair_slice is not None:
+                raise NotImplementedError('pair_slice is a scoring-path (eval) feature')
+            return self._train_forward(batch_queries, query_len, batch_docs, doc_len)
         q = self._ids(batch_queries, 'batch_queries')
         d = self._ids(batch_docs, 'batch_docs')
         ql = self._ids(query_len, 'query_len').to(q.device)
@@ -224,6 +227,10 @@ class _Ranker(_CairModule):
         lib.check(L.cair_ranker_forward(h, q.data_ptr(), ql.data_ptr(), d.data_ptr(), dl.data_ptr(), B, N, Lq, Ld,
                                         begin, count, scores.data_ptr(), ws.data_ptr(), ws.numel(), stream))
         return scores
+
+    def _train_forward(self, batch_queries, query_len, batch_docs, doc_len):
+        raise NotImplementedError('%s: the libcair training step exists for MatchTensor only; score under .eval()'
+                                  % type(self).__name__)
 
     @staticmethod
     def _host_args(q, qlen, d, dlen, out, need_pinned):
@@ -465,6 +472,46 @@ class MatchTensor(_Ranker):
     def _create(self, w, device, out):
         return lib.load().cair_mt_create(w, device, out)
 
+    # ---- training: cair_mt_train_forward / cair_mt_train_backward ----
+    def _trainer_for(self, device):
+        """The native trainer reads the LIVE parameter storage at every step; it is rebuilt only when a parameter moved."""
+        params = dict(self.named_parameters())
+        for name, p in params.items():
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError('MatchTensor training needs contiguous fp32 CUDA parameters (%s)' % name)
+        key = (tuple(p.data_ptr() for p in params.values()), device.index)
+        t = self.__dict__.get('_cair_trainer')
+        if t is not None and self.__dict__.get('_cair_trainer_key') == key:
+            return t
+        self._release_trainer()
+        w = _abi.PACKERS[self.MODEL](self._cfg(), lambda k: C.cast(params[k].data_ptr(), _abi.f32p))
+        out = C.c_void_p()
+        lib.check(lib.load().cair_mt_train_create(C.byref(w), device.index, C.byref(out)))
+        self.__dict__['_cair_trainer'], self.__dict__['_cair_trainer_key'] = out, key
+        return out
+
+    def _release_trainer(self):
+        t = self.__dict__.get('_cair_trainer')
+        if t is not None:
+            lib.load().cair_mt_train_destroy(t)
+            self.__dict__['_cair_trainer'] = None
+
+    def _release(self):
+        super()._release()
+        self._release_trainer()
+
+    def _train_forward(self, batch_queries, query_len, batch_docs, doc_len):
+        q = self._ids(batch_queries, 'batch_queries')
+        d = self._ids(batch_docs, 'batch_docs')
+        ql = self._ids(query_len, 'query_len').to(q.device)
+        dl = self._ids(doc_len, 'doc_len').to(q.device).reshape(d.shape[0], d.shape[1])
+        p_drop = float(self.emb_drop.p)
+        seed = self.__dict__.get('_cair_drop_seed')   # tests pin the mask; otherwise drawn from torch's host generator
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        names = [n for n, _ in self.named_parameters()]
+        return _MtTrainFn.apply(self, names, q, ql, d, dl, p_drop, seed, *[p for _, p in self.named_parameters()])
+
     def set_interaction_impl(self, impl):
         """'tc' (default): tcgen05 bf16x3 tensor-core kernels; 'fp32': CUDA-core fp32 kernels;
         'tc_split': tensor-core interaction with the unfused fp32 document projection."""
@@ -478,6 +525,55 @@ class MatchTensor(_Ranker):
         impl = self.__dict__.get('_cair_impl')
         if impl is not None:
             lib.check(lib.load().cair_mt_set_impl(handle, impl))
+
+
+class _MtTrainFn(torch.autograd.Function):
+    """scores = MatchTensor(q, d) in train mode through libcair, with libcair's backward: gradients for every parameter
+    that requires one (the embedding table is skipped when its requires_grad is False, i.e. --fix_embeddings)."""
+
+    @staticmethod
+    def forward(ctx, module, names, q, ql, d, dl, p_drop, seed, *params):
+        dev = q.device
+        L = lib.load()
+        t = module._trainer_for(dev)
+        B, Lq = q.shape
+        _, N, Ld = d.shape
+        nbytes = C.c_size_t()
+        lib.check(L.cair_mt_train_workspace_bytes(t, B, N, Lq, Ld, C.byref(nbytes)))
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        scores = torch.empty(B, N, dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        lib.check(L.cair_mt_train_forward(t, q.data_ptr(), ql.data_ptr(), d.data_ptr(), dl.data_ptr(), B, N, Lq, Ld, p_drop,
+                                          seed, scores.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        ctx.module, ctx.names, ctx.args = module, names, (q, ql, d, dl, p_drop, seed, ws, t)
+        ctx.shapes = [(p.shape, p.requires_grad) for p in params]
+        return scores
+
+    @staticmethod
+    def backward(ctx, dscores):
+        module, names = ctx.module, ctx.names
+        q, ql, d, dl, p_drop, seed, ws, t = ctx.args
+        dev = q.device
+        B, Lq = q.shape
+        _, N, Ld = d.shape
+        dscores = dscores.contiguous().float()
+        grads, keep = {}, []
+        for name, (shape, req) in zip(names, ctx.shapes):
+            if name == _abi.TABLE_KEY and not req:
+                grads[name] = None            # fixed embeddings: the scatter-add is skipped
+            else:
+                grads[name] = torch.zeros(shape, dtype=torch.float32, device=dev)
+
+        def get(k):
+            g = grads[k]
+            return C.cast(g.data_ptr(), _abi.f32p) if g is not None else C.cast(None, _abi.f32p)
+        gw = _abi.PACKERS[module.MODEL](module._cfg(), get)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        lib.check(lib.load().cair_mt_train_backward(t, q.data_ptr(), ql.data_ptr(), d.data_ptr(), dl.data_ptr(), B, N, Lq, Ld,
+                                                    p_drop, seed, dscores.data_ptr(), C.byref(gw), ws.data_ptr(), ws.numel(),
+                                                    stream))
+        out = [grads[n] if req else None for n, (_, req) in zip(names, ctx.shapes)]
+        return (None,) * 8 + tuple(out)
 
 
 class GatingNetwork(nn.Module):

@@ -416,6 +416,36 @@ CAIR_API int32_t cair_cars_decode(cair_handle* h, const float* enc_q, const int6
                          int32_t S, int32_t Lq, int32_t max_len, const int64_t* tgt2src, int64_t bos_id,
                          int64_t* predictions, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- training step of Match-Tensor ---------------------------------------
+ * Replaces, inside Ranker.update (neuroir/models/ranker.py:192-230), the train-mode `self.network(...)` call (:213) and
+ * the part of `loss.backward()` (:219) below the scores: criterion (:214, :53-65, :80-89), clip_grad_norm (:222) and
+ * optimizer.step() (:226) stay torch calls of the unchanged wrapper on the [B,N] scores / the parameter list.
+ * A trainer holds the LIVE device pointers of the parameters (cair_mt_weights; read again at every step, so in-place
+ * optimizer updates are seen; LSTM encoders only) and small repacked copies it refreshes itself.
+ * forward: train-mode MatchTensor.forward (rankers/mtensor.py:62-131) with emb_drop (:84, :89; mask = counter-based
+ *   hash of (seed, element), scale 1/(1-p); p = 0 gives the eval arithmetic) -> scores [B,N]; the workspace keeps the
+ *   saved activations (gate activations, cell states, memory banks, channel projections, arg-max cells of the max-pools).
+ * backward: dscores [B,N] -> gradients ACCUMULATED (+=) into the buffers of `grads`, a cair_mt_weights whose pointers
+ *   address zero-initialised (or running) gradient buffers of the parameters' shapes; grads->table may be NULL
+ *   (--fix_embeddings, models/ranker.py:160-162).  Must follow the forward of the same batch with the same workspace,
+ *   p_drop and seed.  Row 0 (PAD) of the table receives no gradient (nn.Embedding padding_idx).
+ * Both enqueue on `stream` and synchronise nothing.  cair_mt_train_poll_error synchronises and reports token ids /
+ * lengths out of range seen by the last forward.  cair_dropout_mask writes the keep-scale (0 or 1/(1-p)) of elements
+ * [0, n) of that hash: element index = row * emsize + e with the B*Lq query rows first, then the B*N*Ld document rows. */
+typedef struct cair_mt_trainer cair_mt_trainer;
+CAIR_API int32_t cair_mt_train_create(const cair_mt_weights* params, int32_t device, cair_mt_trainer** out);
+CAIR_API int32_t cair_mt_train_destroy(cair_mt_trainer* t);
+CAIR_API int32_t cair_mt_train_workspace_bytes(cair_mt_trainer* t, int32_t B, int32_t N, int32_t Lq, int32_t Ld, size_t* bytes);
+CAIR_API int32_t cair_mt_train_forward(cair_mt_trainer* t, const int64_t* q, const int64_t* qlen, const int64_t* d,
+                              const int64_t* dlen, int32_t B, int32_t N, int32_t Lq, int32_t Ld, float p_drop, uint64_t seed,
+                              float* scores, void* workspace, size_t workspace_bytes, void* stream);
+CAIR_API int32_t cair_mt_train_backward(cair_mt_trainer* t, const int64_t* q, const int64_t* qlen, const int64_t* d,
+                               const int64_t* dlen, int32_t B, int32_t N, int32_t Lq, int32_t Ld, float p_drop, uint64_t seed,
+                               const float* dscores, const cair_mt_weights* grads, void* workspace, size_t workspace_bytes,
+                               void* stream);
+CAIR_API int32_t cair_mt_train_poll_error(cair_mt_trainer* t, void* workspace, void* stream);
+CAIR_API int32_t cair_dropout_mask(uint64_t seed, float p, int64_t n, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

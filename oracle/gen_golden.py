@@ -27,6 +27,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, '/root/reference')
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 
 from context_attentive_ir_b200 import synth  # noqa: E402
 
@@ -190,6 +191,62 @@ def gen_mt(name, seed, B, N, Lq, Ld, E, V, F, Hq, Hd, C, nf, mfs, rnn_type='LSTM
     _save(name, cfg, batch, net, outs)
 
 
+def gen_mt_train(name, seed, B, N, Lq, Ld, E, V, F, Hq, Hd, C, nf, mfs, p_drop=0.0, drop_seed=0, steps=3, lr=0.05,
+                 clip=5.0, **kw):
+    """Training fixtures: one train-mode forward + loss.backward() of the unmodified reference
+    MatchTensor under BCEWithLogitsLoss (models/ranker.py:62-63, 213-219), then `steps` updates in the order of
+    Ranker.update (:192-230: forward, criterion, zero_grad, backward, clip_grad_norm, SGD step) on the same batch.
+    emb_drop (mtensor.py:33, :84, :89) is replaced by a module that applies the keep-scale mask of oracle/dropout_oracle.py
+    (the hash the CUDA kernels draw from): queries first, then documents - nn.Dropout's own Philox stream cannot be
+    reproduced outside torch."""
+    from neuroir.rankers.mtensor import MatchTensor
+    from dropout_oracle import drop_scale
+    torch.manual_seed(1013)
+    cfg = dict(model='match_tensor', emsize=E, src_vocab_size=V, dropout_emb=p_drop, rnn_type='LSTM',
+               bidirection=True, nlayers=1, dropout_rnn=0.2, featsize=F, nhid_query=Hq,
+               nhid_doc=Hd, nchannels=C, nfilters=nf, match_filter_size=mfs)
+    net = MatchTensor(_ns(**{k: v for k, v in cfg.items() if k != 'model'})).train()
+    batch = synth.ranker_batch(seed, B, N, Lq, Ld, V, **kw)
+    t = _t(batch)
+    mask = torch.from_numpy(drop_scale(drop_seed, (B * Lq + B * N * Ld) * E, p_drop))
+
+    class MaskDrop(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.calls = 0
+
+        def forward(self, x):
+            lo = 0 if self.calls % 2 == 0 else B * Lq * E
+            self.calls += 1
+            return x * mask[lo:lo + x.numel()].view(x.shape)
+    net.emb_drop = MaskDrop()
+    init = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    labels = t['label'].float()
+    crit = torch.nn.BCEWithLogitsLoss()
+    scores = net(t['q'], t['qlen'], t['d'], t['dlen'])
+    loss = crit(scores, labels)
+    loss.backward()
+    outs = dict(scores=scores.detach(), loss=loss.detach())
+    for k, p in net.named_parameters():
+        outs['grad/' + k] = p.grad.detach().clone()
+    opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr, momentum=0.0, weight_decay=0.0)
+    losses = []
+    for _ in range(steps):
+        sc = net(t['q'], t['qlen'], t['d'], t['dlen'])
+        ls = crit(sc, labels)
+        opt.zero_grad()
+        ls.backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), clip)
+        opt.step()
+        losses.append(float(ls))
+    outs['losses'] = np.asarray(losses, dtype=np.float64)
+    for k, v in net.state_dict().items():
+        outs['final/' + k] = v.detach().clone()
+    cfg = dict(cfg, drop_seed=drop_seed, lr=lr, clip=clip, steps=steps)
+    net.load_state_dict(init)
+    _save(name, cfg, batch, net, outs)
+
+
 # ------------------------------------------------------------------ DRMM
 def gen_drmm(name, seed, B, N, Lq, Ld, E, V, **kw):
     DRMMShim = _drmm_shim_class()
@@ -333,7 +390,7 @@ def main():
     only = sys.argv[1:]  # optional: fixture-name prefixes to (re)generate
     if only:
         g = globals()
-        for fn in ('gen_esm', 'gen_mt', 'gen_drmm', 'gen_duet', 'gen_cars', 'gen_dssm', 'gen_arc', 'gen_rank_metrics', 'gen_batchify'):
+        for fn in ('gen_esm', 'gen_mt', 'gen_mt_train', 'gen_drmm', 'gen_duet', 'gen_cars', 'gen_dssm', 'gen_arc', 'gen_rank_metrics', 'gen_batchify'):
             g[fn] = (lambda f: (lambda name, *a, **k: f(name, *a, **k) if any(name.startswith(o) for o in only) else None))(g[fn])
     # BASELINE configs[0]: the reference's own CPU-runnable case (vocab cut 10k -> 1k to keep the file small)
     gen_esm('esm_cfg1', 1235, B=8, N=5, Lq=10, Ld=50, E=64, V=1000)
@@ -352,6 +409,12 @@ def main():
     # >= 64 queries with the reference's own MAP / MRR / P@k of the reference scores (metric parity of model scores)
     gen_mt('mt_map64', 27, B=64, N=10, Lq=8, Ld=24, E=32, V=300, F=8, Hq=16, Hd=24, C=10, nf=6, mfs=8, bos_eos=True,
            overlap=0.1, metrics=True)
+    # training step (first "next" row): gradients of every parameter + a 3-step SGD loss curve
+    gen_mt_train('mt_train_tiny', 28, B=3, N=4, Lq=7, Ld=23, E=32, V=100, F=8, Hq=12, Hd=20, C=10, nf=4, mfs=6, overlap=0.2)
+    gen_mt_train('mt_train_drop', 29, B=4, N=3, Lq=9, Ld=31, E=32, V=150, F=12, Hq=20, Hd=28, C=10, nf=6, mfs=8, p_drop=0.3,
+                 drop_seed=20261017, bos_eos=True, overlap=0.15)
+    gen_mt_train('mt_train_arch', 30, B=2, N=3, Lq=20, Ld=200, E=300, V=400, F=40, Hq=128, Hd=128, C=50, nf=6, mfs=20,
+                 p_drop=0.2, drop_seed=77, bos_eos=True, overlap=0.1)
     # DRMM: strict (disjoint ids) and overlapping (bin-edge cells excluded by the test using out/cos)
     gen_drmm('drmm_strict', 1237, B=3, N=4, Lq=20, Ld=200, E=300, V=400, disjoint=True)
     gen_drmm('drmm_overlap', 32, B=2, N=3, Lq=12, Ld=60, E=64, V=300, bos_eos=True, overlap=0.1)
