@@ -42,6 +42,13 @@ class MtWeights(C.Structure):
         ('conv1', Linear), ('conv2', Linear), ('conv3', Linear), ('conv', Linear), ('output', Linear)]
 
 
+class MnsrfWeights(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ('vocab', 'emsize', 'nhid_query', 'nhid_document', 'nhid_session', 'rnn_type',
+                                          'bidirectional')] + [
+        ('table', f32p), ('query_fwd', LstmDir), ('query_rev', LstmDir), ('doc_fwd', LstmDir), ('doc_rev', LstmDir),
+        ('session', LstmDir), ('projection', Linear)]
+
+
 class DrmmWeights(C.Structure):
     _fields_ = [('vocab', C.c_int32), ('emsize', C.c_int32), ('nbins', C.c_int32), ('table', f32p),
                 ('gating', Linear), ('ffnn0', Linear), ('ffnn1', Linear), ('output', Linear)]
@@ -145,6 +152,35 @@ def pack_mt(cfg, get):
     w.alpha = get('exact_match_channel.alpha')
     for k in ('conv1', 'conv2', 'conv3', 'conv', 'output'):
         setattr(w, k, _lin(get, k))
+    return w
+
+
+def pack_mmt(cfg, get):
+    """M_MATCH_TENSOR (multitask/mmtensor.py:10-48): the Match-Tensor struct from the multitask key names
+    (`embedder.` / `.encoder.` levels of multitask/layers.py, `nhid_document`)."""
+    def mapped(key):
+        if key == TABLE_KEY:
+            return get('embedder.' + key)
+        for enc in ('query_encoder.', 'document_encoder.'):
+            if key.startswith(enc + 'rnns.'):
+                return get(enc + 'encoder.' + key[len(enc):])
+        return get(key)
+    return pack_mt(dict(cfg, nhid_doc=cfg['nhid_document']), mapped)
+
+
+def pack_mnsrf(cfg, get):
+    """MNSRF (multitask/mnsrf.py:10-57)."""
+    bi = bool(cfg['bidirection'])
+    w = MnsrfWeights(cfg['src_vocab_size'], cfg['emsize'], cfg['nhid_query'], cfg['nhid_document'], cfg['nhid_session'],
+                     RNN_TYPES[cfg['rnn_type']], int(bi))
+    w.table = get('embedder.' + TABLE_KEY)
+    w.query_fwd = _lstm(get, 'query_encoder.encoder.rnns.0')
+    w.doc_fwd = _lstm(get, 'document_encoder.encoder.rnns.0')
+    if bi:
+        w.query_rev = _lstm(get, 'query_encoder.encoder.rnns.0', '_reverse')
+        w.doc_rev = _lstm(get, 'document_encoder.encoder.rnns.0', '_reverse')
+    w.session = _lstm(get, 'session_query_encoder.encoder.rnns.0')
+    w.projection = _lin(get, 'projection.linear')
     return w
 
 
@@ -256,5 +292,5 @@ def pack_cars_decoder(cfg, get):
     return w
 
 
-PACKERS = {'arci': pack_arci, 'arcii': pack_arcii, 'dssm': pack_dssm, 'cdssm': pack_cdssm, 'esm': pack_esm, 'match_tensor': pack_mt, 'drmm': pack_drmm, 'duet': pack_duet,
+PACKERS = {'arci': pack_arci, 'arcii': pack_arcii, 'dssm': pack_dssm, 'cdssm': pack_cdssm, 'esm': pack_esm, 'match_tensor': pack_mt, 'm_match_tensor': pack_mmt, 'mnsrf': pack_mnsrf, 'drmm': pack_drmm, 'duet': pack_duet,
            'cars': pack_cars}

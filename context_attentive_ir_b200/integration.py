@@ -14,8 +14,9 @@ def install():
         done.append('neuroir.models.ranker.' + name)
     try:
         import neuroir.models.multitask as ref_multitask
-        setattr(ref_multitask, 'CARS', multitask.CARS)
-        done.append('neuroir.models.multitask.CARS')
+        for name in ('CARS', 'MNSRF', 'M_MATCH_TENSOR'):
+            setattr(ref_multitask, name, getattr(multitask, name))
+            done.append('neuroir.models.multitask.' + name)
     except ImportError:  # the multitask wrapper pulls in optional deps (prettytable, tqdm)
         pass
     return done

@@ -70,6 +70,11 @@ PROTOTYPES = {
                                      C.POINTER(_abi.MtWeights), vp, C.c_size_t, vp]),
     'cair_mt_train_poll_error': (i32, [vp, vp, vp]),
     'cair_dropout_mask': (i32, [C.c_uint64, C.c_float, i64, vp, vp]),
+    'cair_mnsrf_create': (i32, [C.POINTER(_abi.MnsrfWeights), i32, C.POINTER(vp)]),
+    'cair_mnsrf_destroy': (i32, [vp]),
+    'cair_mnsrf_workspace_bytes': (i32, [vp, i32, i32, i32, i32, i32, C.POINTER(C.c_size_t)]),
+    'cair_mnsrf_forward': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, C.c_size_t, vp]),
+    'cair_mnsrf_poll_error': (i32, [vp, vp]),
     'cair_cars_decode': (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, i64, vp, vp, C.c_size_t, vp]),
 }
 

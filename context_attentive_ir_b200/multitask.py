@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import _abi, lib
-from .rankers import PAD, Embeddings, RNNEncoder, _CairModule
+from .rankers import PAD, Embeddings, ExactMatchChannel, RNNEncoder, _CairModule, _Ranker
 
 BOS = 2   # neuroir/inputters/constants.py:3
 
@@ -69,18 +69,19 @@ class _GeneralAttention(nn.Module):
 class _RNNDecoder(nn.Module):
     """Parameters of RNNDecoder (decoders/decoder.py:68-104): one LSTM layer + attention."""
 
-    def __init__(self, input_size, hidden_size):
+    def __init__(self, input_size, hidden_size, attn=True, rnn_type='LSTM'):
         super().__init__()
-        self.rnn = nn.LSTM(input_size=input_size, hidden_size=hidden_size, num_layers=1, batch_first=True)
-        self.attn = _GeneralAttention(hidden_size)
+        self.rnn = getattr(nn, rnn_type)(input_size=input_size, hidden_size=hidden_size, num_layers=1, batch_first=True)
+        if attn:   # attn_type 'none' (MNSRF, M_MATCH_TENSOR): the reference decoder has no attention parameters
+            self.attn = _GeneralAttention(hidden_size)
 
 
 class Decoder(nn.Module):
     """neuroir/multitask/layers.py:57-93 (adds the `decoder.` level to the keys)."""
 
-    def __init__(self, input_size, nhid):
+    def __init__(self, input_size, nhid, attn=True, rnn_type='LSTM'):
         super().__init__()
-        self.decoder = _RNNDecoder(input_size, nhid)
+        self.decoder = _RNNDecoder(input_size, nhid, attn, rnn_type)
 
 
 class _DecoderStates:
@@ -296,4 +297,169 @@ def ranking_state_dict(reference_state_dict):
     return {k: v for k, v in reference_state_dict.items() if not k.startswith(DECODER_PREFIXES)}
 
 
-MULTITASK = {'CARS': CARS}
+_NO_DECODE = ('%s: only the ranking path (encode + rank_document, SURVEY.md section 8f row 4) runs on libcair; the suggestion '
+              'decoder of this model is not built (CARS has one: cair_cars_decode).  Use the click scores, or run decode() of the '
+              'reference module on the carried decoder parameters')
+
+
+class MNSRF(_CairModule):
+    """Ranking half of neuroir/multitask/mnsrf.py:10-162 (encode + rank_document); decoder-side parameters (decoder.*,
+    generator.*) are carried as parameters so that reference checkpoints load by key."""
+    MODEL = 'mnsrf'
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        if args.nlayers != 1:
+            raise NotImplementedError('libcair implements single-layer encoders')
+        if args.rnn_type != 'LSTM':   # the reference's own session loop raises for GRU (`if init_states:`, rnn_encoder.py:77)
+            raise NotImplementedError('MNSRF: rnn_type LSTM only (the reference cannot run its session loop with GRU either)')
+        self.embedder = Embedder(args.emsize, args.src_vocab_size, args.dropout_emb)
+        self.query_encoder = Encoder(args.rnn_type, args.emsize, args.bidirection, 1, args.nhid_query, args.dropout_rnn)
+        self.document_encoder = Encoder(args.rnn_type, args.emsize, args.bidirection, 1, args.nhid_document, args.dropout_rnn)
+        self.nhid_session = args.nhid_session
+        self.session_query_encoder = Encoder(args.rnn_type, args.nhid_query, False, 1, args.nhid_session, args.dropout_rnn)
+        self.decoder = Decoder(args.emsize, args.nhid_session, attn=False, rnn_type=args.rnn_type)
+        self.projection = nn.Sequential(OrderedDict([('linear', nn.Linear(args.nhid_query + args.nhid_session, args.nhid_document)),
+                                                     ('tanh', nn.Tanh())]))
+        self.dropout = nn.Dropout(args.dropout)
+        self.generator = nn.Linear(args.nhid_session, args.tgt_vocab_size)
+        self._last = None
+
+    def _cfg(self):
+        a = self.args
+        return dict(src_vocab_size=a.src_vocab_size, emsize=a.emsize, nhid_query=a.nhid_query, nhid_document=a.nhid_document,
+                    nhid_session=a.nhid_session, rnn_type=a.rnn_type, bidirection=a.bidirection)
+
+    def _create(self, w, device, out):
+        return lib.load().cair_mnsrf_create(w, device, out)
+
+    def _release(self):
+        h = self.__dict__.get('_cair_handle')
+        if h is not None:
+            lib.load().cair_mnsrf_destroy(h)
+            self.__dict__['_cair_handle'] = None
+
+    def score(self, queries, query_len, docs, doc_len, session_slice=None, want_banks=False):
+        """q [B,S,Lq], qlen [B,S], d [B,S,N,Ld], dlen [B,S,N] -> dict(scores [B,S,N] + memory_bank [B,S,Hq], session_bank,
+        session_cell [B,S,Hs] if want_banks); session_slice=(begin, count) scores only those sessions."""
+        q = self._ids(queries, 'queries')
+        d = self._ids(docs, 'docs')
+        dev = q.device
+        ql = self._ids(query_len, 'query_len').to(dev)
+        dl = self._ids(doc_len, 'doc_len').to(dev)
+        B, S, Lq = q.shape
+        N, Ld = d.shape[2], d.shape[3]
+        a = self.args
+        L = lib.load()
+        h = self._handle_for(dev)
+        nbytes = C.c_size_t()
+        lib.check(L.cair_mnsrf_workspace_bytes(h, B, S, N, Lq, Ld, C.byref(nbytes)))
+        ws = self._workspace(nbytes.value, dev)
+        out = dict(scores=torch.zeros(B, S, N, device=dev))
+        if want_banks:
+            out.update(memory_bank=torch.zeros(B, S, a.nhid_query, device=dev), session_bank=torch.zeros(B, S, a.nhid_session, device=dev),
+                       session_cell=torch.zeros(B, S, a.nhid_session, device=dev))
+
+        def p(k):
+            return out[k].data_ptr() if k in out else None
+        sb, sc = (0, B) if session_slice is None else session_slice
+        lib.check(L.cair_mnsrf_forward(h, q.data_ptr(), ql.data_ptr(), d.data_ptr(), dl.data_ptr(), B, S, N, Lq, Ld, sb, sc,
+                                       out['scores'].data_ptr(), p('memory_bank'), p('session_bank'), p('session_cell'),
+                                       ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+        return out
+
+    def poll_error(self):
+        h = self.__dict__.get('_cair_handle')
+        if h is not None:
+            lib.check(lib.load().cair_mnsrf_poll_error(h, torch.cuda.current_stream().cuda_stream))
+
+    # -- the reference's predict-time call sequence (models/multitask.py:270-276) --
+    def encode(self, source_rep, source_len):
+        """Deferred like CARS.encode: the fused forward runs in rank_document, which has the documents."""
+        self._last = (source_rep, source_len)
+        tok = ('cair-deferred', id(self))
+        return tok, tok, None
+
+    def rank_document(self, source_rep, memory_bank, session_bank, document_rep, document_len):
+        if self._last is None:
+            raise RuntimeError('rank_document() must follow encode() (models/multitask.py:270-276)')
+        queries, qlen = self._last
+        self._last = None
+        out = self.score(queries, qlen, document_rep, document_len, want_banks=True)
+        self._fwd = out
+        return out['scores']
+
+    def decode(self, *args, **kw):
+        raise NotImplementedError(_NO_DECODE % 'MNSRF')
+
+
+class M_MATCH_TENSOR(_Ranker):
+    """Ranking half of neuroir/multitask/mmtensor.py:10-189.  rank_document never looks at the session: it is Match-Tensor on
+    every (query, candidate) of every session, so it runs on a Match-Tensor handle with B*S queries; the session encoder,
+    decoder and generator are carried as parameters for checkpoint compatibility."""
+    MODEL = 'm_match_tensor'
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        if args.nlayers != 1:
+            raise NotImplementedError('libcair implements single-layer encoders')
+        self.embedder = Embedder(args.emsize, args.src_vocab_size, args.dropout_emb)
+        self.linear_projection = nn.Linear(args.emsize, args.featsize)
+        self.query_encoder = Encoder(args.rnn_type, args.featsize, args.bidirection, 1, args.nhid_query, args.dropout_rnn)
+        self.document_encoder = Encoder(args.rnn_type, args.featsize, args.bidirection, 1, args.nhid_document, args.dropout_rnn)
+        self.query_projection = nn.Linear(args.nhid_query, args.nchannels)
+        self.document_projection = nn.Linear(args.nhid_document, args.nchannels)
+        self.exact_match_channel = ExactMatchChannel()
+        self.conv1 = nn.Conv2d(args.nchannels + 1, args.nfilters, (3, 3), padding=1)
+        self.conv2 = nn.Conv2d(args.nchannels + 1, args.nfilters, (3, 5), padding=(1, 2))
+        self.conv3 = nn.Conv2d(args.nchannels + 1, args.nfilters, (3, 7), padding=(1, 3))
+        self.conv = nn.Conv2d(args.nfilters * 3, args.match_filter_size, (1, 1))
+        self.output = nn.Linear(args.match_filter_size, 1)
+        self.nhid_session = args.nhid_session
+        self.session_query_encoder = Encoder(args.rnn_type, args.nchannels, False, 1, args.nhid_session, args.dropout_rnn)
+        self.decoder = Decoder(args.emsize, args.nhid_session, attn=False, rnn_type=args.rnn_type)
+        self.dropout = nn.Dropout(args.dropout)
+        self.generator = nn.Linear(args.nhid_session, args.tgt_vocab_size)
+        self._last = None
+
+    def _cfg(self):
+        a = self.args
+        return dict(src_vocab_size=a.src_vocab_size, emsize=a.emsize, featsize=a.featsize, nhid_query=a.nhid_query,
+                    nhid_document=a.nhid_document, nchannels=a.nchannels, nfilters=a.nfilters,
+                    match_filter_size=a.match_filter_size, rnn_type=a.rnn_type, bidirection=a.bidirection)
+
+    def _create(self, w, device, out):
+        return lib.load().cair_mt_create(w, device, out)
+
+    def _on_handle_created(self, handle):
+        impl = self.__dict__.get('_cair_impl')   # 0: fp32 kernels, 1: tcgen05 (default), as MatchTensor.set_interaction_impl
+        if impl is not None:
+            lib.check(lib.load().cair_mt_set_impl(handle, impl))
+
+    def score(self, queries, query_len, docs, doc_len):
+        """q [B,S,Lq], qlen [B,S], d [B,S,N,Ld], dlen [B,S,N] -> scores [B,S,N]."""
+        B, S, Lq = queries.shape
+        N, Ld = docs.shape[2], docs.shape[3]
+        s = self.forward(queries.reshape(B * S, Lq), query_len.reshape(B * S), docs.reshape(B * S, N, Ld),
+                         doc_len.reshape(B * S, N))
+        return s.view(B, S, N)
+
+    def encode(self, source_rep, source_len):
+        self._last = (source_rep, source_len)
+        tok = ('cair-deferred', id(self))
+        return tok, tok, None
+
+    def rank_document(self, source_rep, projected_queries, session_bank, document_rep, document_len):
+        if self._last is None:
+            raise RuntimeError('rank_document() must follow encode() (models/multitask.py:270-276)')
+        queries, qlen = self._last
+        self._last = None
+        return self.score(queries, qlen, document_rep, document_len)
+
+    def decode(self, *args, **kw):
+        raise NotImplementedError(_NO_DECODE % 'M_MATCH_TENSOR')
+
+
+MULTITASK = {'CARS': CARS, 'MNSRF': MNSRF, 'M_MATCH_TENSOR': M_MATCH_TENSOR}

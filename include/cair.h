@@ -446,6 +446,32 @@ CAIR_API int32_t cair_mt_train_backward(cair_mt_trainer* t, const int64_t* q, co
 CAIR_API int32_t cair_mt_train_poll_error(cair_mt_trainer* t, void* workspace, void* stream);
 CAIR_API int32_t cair_dropout_mask(uint64_t seed, float p, int64_t n, float* out, void* stream);
 
+/* ---- MNSRF ranking path ---------------------------------------------------
+ * Replaces MNSRF.encode + MNSRF.rank_document (neuroir/multitask/mnsrf.py:61-162) as Multitask.predict calls them
+ * (neuroir/models/multitask.py:270-276).  Weights are copied into the handle: table = embedder.word_embeddings...weight
+ * [V,E]; {query,document}_encoder.encoder.rnns.0.* ((Bi)LSTM or (Bi)GRU); session = session_query_encoder.encoder.rnns.0.*
+ * (unidirectional, input nhid_query, hidden nhid_session); projection = projection.linear [Hd, Hq+Hs] + bias.
+ * forward: q [B,S,Lq], qlen [B,S], d [B,S,N,Ld], dlen [B,S,N] int64 -> scores [B,S,N] (no softmax) for the sessions
+ * [session_begin, session_begin+session_count); optional outputs (NULL to skip): memory_bank [B,S,Hq] (max-pooled query
+ * encodings), session_bank [B,S,Hs], session_cell [B,S,Hs] (LSTM only) - what MNSRF.encode returns / the decoder starts from.
+ * M_MATCH_TENSOR.rank_document (multitask/mmtensor.py:127-189) needs no entry point of its own: its scores do not depend
+ * on the session, it is cair_ranker_forward on a Match-Tensor handle with B*S queries (see multitask.py M_MATCH_TENSOR). */
+typedef struct {
+  int32_t vocab, emsize, nhid_query, nhid_document, nhid_session, rnn_type, bidirectional;
+  const float* table;
+  cair_lstm_dir query_fwd, query_rev, doc_fwd, doc_rev, session;
+  cair_linear projection;
+} cair_mnsrf_weights;
+typedef struct cair_mnsrf cair_mnsrf;
+CAIR_API int32_t cair_mnsrf_create(const cair_mnsrf_weights* w, int32_t device, cair_mnsrf** out);
+CAIR_API int32_t cair_mnsrf_destroy(cair_mnsrf* h);
+CAIR_API int32_t cair_mnsrf_workspace_bytes(cair_mnsrf* h, int32_t B, int32_t S, int32_t N, int32_t Lq, int32_t Ld, size_t* bytes);
+CAIR_API int32_t cair_mnsrf_forward(cair_mnsrf* h, const int64_t* q, const int64_t* qlen, const int64_t* d, const int64_t* dlen,
+                           int32_t B, int32_t S, int32_t N, int32_t Lq, int32_t Ld, int32_t session_begin, int32_t session_count,
+                           float* scores, float* memory_bank, float* session_bank, float* session_cell, void* workspace,
+                           size_t workspace_bytes, void* stream);
+CAIR_API int32_t cair_mnsrf_poll_error(cair_mnsrf* h, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -316,6 +316,39 @@ def gen_cars(name, seed, B, S, N, Lq, Ld, E, V, Hq, Hd, Hs, max_clicks=1, metric
                                       predictions=dec['predictions']))
 
 
+# ------------------------------------------------------------------ MNSRF / M-Match-Tensor ranking paths
+def gen_session_ranker(name, which, seed, B, S, N, Lq, Ld, E, V, Hq, Hd, Hs, rnn_type='LSTM', **arch):
+    """encode + rank_document of the unmodified multitask models, as Multitask.predict calls them
+    (models/multitask.py:270-276)."""
+    if which == 'mnsrf':
+        from neuroir.multitask.mnsrf import MNSRF as Net
+    else:
+        from neuroir.multitask.mmtensor import M_MATCH_TENSOR as Net
+    torch.manual_seed(1013)
+    cfg = dict(model=which, emsize=E, src_vocab_size=V, tgt_vocab_size=50, dropout_emb=0.2, dropout=0.2, rnn_type=rnn_type,
+               bidirection=True, nlayers=1, nhid_query=Hq, nhid_document=Hd, nhid_session=Hs, dropout_rnn=0.2,
+               regularize_coeff=0.1, **arch)
+    net = Net(_ns(**{k: v for k, v in cfg.items() if k != 'model'})).eval()
+    batch = synth.session_batch(seed, B, S, N, Lq, Ld, V, max_clicks=1)
+    if which == 'm_match_tensor':   # some exact matches for the extra channel
+        rng = np.random.default_rng(seed + 1)
+        d, q = batch['d'], batch['q']
+        for b in range(B):
+            for s_ in range(S):
+                for n in range(N):
+                    L = int(batch['dlen'][b, s_, n])
+                    for j in rng.choice(L, size=max(1, L // 8), replace=False):
+                        d[b, s_, n, j] = q[b, s_, rng.integers(0, int(batch['qlen'][b, s_]))]
+    t = _t(batch)
+    with torch.no_grad():
+        memory_bank, session_bank, states = net.encode(t['q'], t['qlen'])
+        scores = net.rank_document(t['q'], memory_bank, session_bank, t['d'], t['dlen'])
+    outs = dict(scores=scores, session_bank=session_bank)
+    if which == 'mnsrf':
+        outs['memory_bank'] = memory_bank
+    _save(name, cfg, batch, net, outs)
+
+
 # ------------------------------------------------------------------ ranking metrics (eval/ltorank.py)
 def gen_rank_metrics(name, seed, B, N, max_rel=1, ties=False):
     """scores -> f.softmax (models/ranker.py:258) -> np.argsort(-scores) -> MAP / MRR / precision_at_k exactly as
@@ -390,7 +423,7 @@ def main():
     only = sys.argv[1:]  # optional: fixture-name prefixes to (re)generate
     if only:
         g = globals()
-        for fn in ('gen_esm', 'gen_mt', 'gen_mt_train', 'gen_drmm', 'gen_duet', 'gen_cars', 'gen_dssm', 'gen_arc', 'gen_rank_metrics', 'gen_batchify'):
+        for fn in ('gen_esm', 'gen_mt', 'gen_mt_train', 'gen_session_ranker', 'gen_drmm', 'gen_duet', 'gen_cars', 'gen_dssm', 'gen_arc', 'gen_rank_metrics', 'gen_batchify'):
             g[fn] = (lambda f: (lambda name, *a, **k: f(name, *a, **k) if any(name.startswith(o) for o in only) else None))(g[fn])
     # BASELINE configs[0]: the reference's own CPU-runnable case (vocab cut 10k -> 1k to keep the file small)
     gen_esm('esm_cfg1', 1235, B=8, N=5, Lq=10, Ld=50, E=64, V=1000)
@@ -442,6 +475,16 @@ def main():
     gen_rank_metrics('rank_metrics_n10', 81, B=64, N=10, max_rel=1)
     gen_rank_metrics('rank_metrics_ties', 82, B=32, N=12, max_rel=3, ties=True)
     gen_rank_metrics('rank_metrics_n100', 83, B=16, N=100, max_rel=5)
+    # MNSRF / M-Match-Tensor ranking paths
+    gen_session_ranker('mnsrf_tiny', 'mnsrf', 53, B=3, S=4, N=5, Lq=8, Ld=30, E=32, V=200, Hq=32, Hd=32, Hs=48)
+    # (rnn_type GRU is not a fixture: the reference's own session loop raises there - `if init_states:` on a tensor,
+    # encoders/rnn_encoder.py:77)
+    gen_session_ranker('mnsrf_small', 'mnsrf', 54, B=2, S=3, N=4, Lq=6, Ld=17, E=24, V=150, Hq=16, Hd=20, Hs=24)
+    gen_session_ranker('mnsrf_h256', 'mnsrf', 55, B=2, S=5, N=6, Lq=12, Ld=60, E=64, V=300, Hq=256, Hd=256, Hs=96)
+    gen_session_ranker('mmt_tiny', 'm_match_tensor', 56, B=2, S=3, N=4, Lq=7, Ld=23, E=32, V=100, Hq=12, Hd=20, Hs=24,
+                       featsize=8, nchannels=10, nfilters=4, match_filter_size=6)
+    gen_session_ranker('mmt_arch', 'm_match_tensor', 57, B=2, S=3, N=3, Lq=12, Ld=60, E=64, V=300, Hq=128, Hd=128, Hs=64,
+                       featsize=40, nchannels=50, nfilters=6, match_filter_size=20)
     # CARS ranking path
     gen_cars('cars_tiny', 51, B=2, S=3, N=4, Lq=6, Ld=17, E=24, V=150, Hq=16, Hd=16, Hs=24, max_clicks=1)
     gen_cars('cars_clicks', 52, B=3, S=4, N=5, Lq=8, Ld=30, E=32, V=200, Hq=32, Hd=32, Hs=48, max_clicks=3)

@@ -7,7 +7,7 @@ import torch
 import context_attentive_ir_b200 as cair
 
 CLASSES = {'arci': cair.ARCI, 'arcii': cair.ARCII, 'dssm': cair.DSSM, 'cdssm': cair.CDSSM, 'esm': cair.ESM, 'match_tensor': cair.MatchTensor, 'drmm': cair.DRMM, 'duet': cair.DUET,
-           'cars': cair.CARS}
+           'cars': cair.CARS, 'mnsrf': cair.MNSRF, 'm_match_tensor': cair.M_MATCH_TENSOR}
 
 
 def namespace(cfg):
