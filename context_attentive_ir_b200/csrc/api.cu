@@ -301,8 +301,14 @@ int32_t cair_mt_set_debug(cair_handle* h, float* enc_q, float* enc_d) {
 }
 
 int32_t cair_set_gemm_impl(int32_t impl) {
-  if (impl != 0 && impl != 1) return fail(CAIR_ERR_BAD_ARG, "set_gemm_impl: 0 (fp32 CUDA cores) or 1 (tcgen05)");
+  if (impl < 0 || impl > 2) return fail(CAIR_ERR_BAD_ARG, "set_gemm_impl: 0 (fp32 CUDA cores), 1 (tcgen05, persistent) or 2 (tcgen05, one tile per CTA)");
   g_gemm_impl = impl;
+  return CAIR_OK;
+}
+
+/* timing experiments only (not in the header): see g_gemm_dbg */
+CAIR_API int32_t cair_debug_gemm(int32_t bits) {
+  g_gemm_dbg = bits;
   return CAIR_OK;
 }
 

@@ -228,6 +228,7 @@ struct GemmTcW {
   int N = 0, K = 0, NT = 0, nct = 0, nkc = 0;
   uint8_t* img = nullptr;
 };
+extern int g_gemm_dbg;
 extern int g_gemm_impl;  // 1 (default): tcgen05 GEMM where usable, 0: fp32 CUDA-core GEMM everywhere
 int32_t gemm_tc_pack(Owned& own, const float* w, int N, int K, GemmTcW* out, cudaStream_t s);
 bool gemm_tc_usable(const GemmA& a, int K);

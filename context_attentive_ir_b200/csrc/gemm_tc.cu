@@ -28,6 +28,7 @@ constexpr uint32_t GT_APLANE = GT_BM * 16 + 16;
 constexpr uint32_t GT_AIMG = (GT_BK / 8) * GT_APLANE;  // one (hi|lo) A chunk image: 16.1 KB
 
 int g_gemm_impl = 1;  // 1: tcgen05 where the shape allows, 0: always the fp32 CUDA-core kernel
+int g_gemm_dbg = 0;   // timing experiments of the persistent kernel (results are wrong): 1 no stores, 2 no W traffic, 4 short epilogue
 
 // W image: [column tile][K chunk][hi|lo][plane kc][row n < NT][8 x bf16]
 __global__ void gemm_tc_pack_kernel(const float* __restrict__ w, int N, int K, int NT, int nkc, uint8_t* __restrict__ img) {
@@ -277,6 +278,287 @@ __global__ void __launch_bounds__(GT_THREADS, 1)
   if (warp == 0) tmem_dealloc(tbase, tcols);
 }
 
+
+// ---- persistent, fully pipelined version (default) -------------------------------------------------------------
+// The kernel above runs one tile per CTA and one CTA per SM: while a tile is in its epilogue (128 x NT fp32 through shared
+// memory to HBM) nothing is being loaded, and every tile pays the id -> row latency chain of its first chunk again.  Here a
+// CTA walks over tiles (column tile fastest, so the row tile's A rows are re-read from L2 by neighbouring SMs at the same
+// time): the loader warps run ONE software pipeline over the flattened (tile, K chunk) sequence, the accumulator is double
+// buffered in TMEM, and four dedicated warps drain accumulator k while the MMAs of tile k+1 run.
+constexpr int G2_EWARPS = 4;
+constexpr int G2_THREADS = (GT_LWARPS + G2_EWARPS + 2) * 32;   // 8 loaders, 4 epilogue, W producer, MMA issuer
+constexpr int G2_ESTAGE = 32 * 33;                               // floats per epilogue warp
+
+__global__ void __launch_bounds__(G2_THREADS, 1)
+    gemm_tc2_kernel(GemmA a, const uint8_t* __restrict__ wimg, const float* __restrict__ bias, float* __restrict__ c,
+                    int64_t ldc, int64_t M, int N, int K, int NT, int nkc, int nct, int act, uint32_t tcols1, int nst,
+                    int ntiles, int dbg) {
+  extern __shared__ __align__(128) uint8_t smraw[];
+  __shared__ uint64_t a_full[GT_MAXSTAGES], w_full[GT_MAXSTAGES], empty[GT_MAXSTAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t w_plane = (uint32_t)NT * 16, w_half = (GT_BK / 8) * w_plane;
+  uint8_t* a_ring = smraw;
+  uint8_t* w_ring = a_ring + (size_t)nst * 2 * GT_AIMG;
+  float* estage = reinterpret_cast<float*>(w_ring + (size_t)nst * 2 * w_half);
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, 2 * tcols1);
+  if (tid == GT_LWARPS * 32) {
+    for (int s = 0; s < nst; ++s) {
+      mbar_init(&a_full[s], GT_LWARPS);
+      mbar_init(&w_full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], G2_EWARPS);
+    }
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+
+  if (warp == GT_LWARPS + G2_EWARPS) {
+    // ---- W producer ----
+    if (lane == 0) {
+      int g = 0;
+      for (int kt = 0; kt < my_tiles; ++kt) {
+        const int t = (int)blockIdx.x + kt * (int)gridDim.x, ct = t % nct;
+        const uint8_t* src = wimg + (size_t)ct * nkc * 2 * w_half;
+        for (int kc = 0; kc < nkc; ++kc, ++g) {
+          const int s = g % nst;
+          mbar_wait_relaxed(&empty[s], ((g / nst) & 1) ^ 1);
+          const uint32_t bytes = 2 * w_half;
+          if ((dbg & 2) && g >= nst) {   // timing experiment: no W traffic (stale operands)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&w_full[s])) : "memory");
+            continue;
+          }
+          mbar_arrive_expect_tx(&w_full[s], bytes);
+          uint8_t* dst = w_ring + (size_t)s * bytes;
+          for (uint32_t o = 0; o < bytes; o += 32768) bulk_g2s(dst + o, src + (size_t)kc * bytes + o, min(32768u, bytes - o), &w_full[s]);
+        }
+      }
+    }
+  } else if (warp == GT_LWARPS + G2_EWARPS + 1) {
+    // ---- MMA issuer ----
+    const uint32_t issue = elect_one();
+    const uint32_t idesc = idesc_bf16_f32(128, NT);
+    const uint64_t ad0 = smem_desc(smem_u32(a_ring), GT_APLANE, 128);
+    const uint64_t wd0 = smem_desc(smem_u32(w_ring), w_plane, 128);
+    int g = 0;
+    for (int kt = 0; kt < my_tiles; ++kt) {
+      const int buf = kt & 1;
+      mbar_wait(&acc_empty[buf], ((kt >> 1) & 1) ^ 1);   // the epilogue of tile kt-2 has drained this accumulator
+      tc_fence_after();
+      const uint32_t tacc = tbase + (uint32_t)buf * tcols1;
+      for (int kc = 0; kc < nkc; ++kc, ++g) {
+        const int s = g % nst;
+        const uint32_t ph = (g / nst) & 1;
+        mbar_wait(&a_full[s], ph);
+        mbar_wait(&w_full[s], ph);
+        tc_fence_after();
+        const uint64_t ah = ad0 + (uint64_t)((uint32_t)s * 2 * GT_AIMG >> 4), al = ah + (uint64_t)(GT_AIMG >> 4);
+        const uint64_t wh = wd0 + (uint64_t)((uint32_t)s * 2 * w_half >> 4), wl = wh + (uint64_t)(w_half >> 4);
+#pragma unroll
+        for (int ks = 0; ks < GT_BK / 16; ++ks) {
+          const uint64_t ao = (uint64_t)(ks * ((2 * GT_APLANE) >> 4)), wo = (uint64_t)(ks * ((2 * w_plane) >> 4));
+          mma_bf16_ss_w(tacc, ah + ao, wh + wo, idesc, (uint32_t)((kc | ks) != 0), issue);
+          mma_bf16_ss_w(tacc, al + ao, wh + wo, idesc, 1, issue);
+          mma_bf16_ss_w(tacc, ah + ao, wl + wo, idesc, 1, issue);
+        }
+        mma_commit_w(&empty[s], issue);
+      }
+      mma_commit_w(&acc_full[buf], issue);
+    }
+  } else if (warp >= GT_LWARPS) {
+    // ---- epilogue warps: TMEM -> shared-memory transpose -> coalesced 128-byte row segments ----
+    const int qt = warp & 3;   // TMEM lane quarter (warps 8..11 -> 0..3)
+    float* stage = estage + (size_t)(warp - GT_LWARPS) * G2_ESTAGE;
+    const bool vec_ok = (ldc & 3) == 0 && ((uintptr_t)c & 15) == 0 && (NT & 3) == 0 && (!bias || ((uintptr_t)bias & 15) == 0);
+    for (int kt = 0; kt < my_tiles; ++kt) {
+      const int buf = kt & 1;
+      const int t = (int)blockIdx.x + kt * (int)gridDim.x, mt = t / nct, ct = t - mt * nct;
+      const int64_t rbase = (int64_t)mt * GT_BM + qt * 32;
+      const int n0 = ct * NT;
+      mbar_wait_relaxed(&acc_full[buf], (kt >> 1) & 1);
+      tc_fence_after();
+      for (int c0 = 0; c0 < NT; c0 += 32) {
+        float v[32];
+        tmem_ld32(tbase + ((uint32_t)(qt * 32) << 16) + (uint32_t)buf * tcols1 + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) stage[lane * 33 + jj] = v[jj];
+        __syncwarp();
+        if (vec_ok && n0 + c0 + 32 <= N && c0 + 32 <= NT) {
+          // four rows x 128 bytes per store instruction: lanes 8 g .. 8 g + 7 write row 4 k + g as float4 (a quarter of the
+          // store instructions of the one-row-per-instruction form; the stride-33 staging stays conflict-free)
+          const int g4 = lane >> 3, cq = (lane & 7) * 4;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias) b4 = *reinterpret_cast<const float4*>(bias + n0 + c0 + cq);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int rr = 4 * k + g4;
+            const float* sp = stage + rr * 33 + cq;
+            float4 x = make_float4(sp[0] + b4.x, sp[1] + b4.y, sp[2] + b4.z, sp[3] + b4.w);
+            if (act == ACT_TANH) x = make_float4(tanhf(x.x), tanhf(x.y), tanhf(x.z), tanhf(x.w));
+            if (act == ACT_RELU) x = make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f));
+            if (rbase + rr < M && !(dbg & 1)) *reinterpret_cast<float4*>(c + (rbase + rr) * ldc + n0 + c0 + cq) = x;
+          }
+        } else {
+          const int col = n0 + c0 + lane;
+          const bool cvalid = c0 + lane < NT && col < N;
+          const float bcol = (bias && cvalid) ? bias[col] : 0.f;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            float x = stage[rr * 33 + lane] + bcol;
+            if (act == ACT_TANH) x = tanhf(x);
+            if (act == ACT_RELU) x = fmaxf(x, 0.f);
+            if (cvalid && rbase + rr < M && !(dbg & 1)) c[(rbase + rr) * ldc + col] = x;   // dbg 1: timing experiment without the stores
+          }
+        }
+        __syncwarp();
+        if (dbg & 4) break;   // timing experiment: drain one chunk only
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) gt_arrive(&acc_empty[buf]);
+    }
+  } else {
+    // ---- A loaders: one software pipeline over the flattened (tile, chunk) sequence ----
+    // ids of chunk g+2 requested, rows of chunk g+1 loaded, chunk g converted and written (see the kernel above for the
+    // lane <-> (row, 16-byte slice) mapping).  Each of the three stages has its own (tile, chunk) cursor, so the
+    // pipeline does not drain at tile boundaries.
+    const int j = lane & 15, rsub = lane >> 4;
+    constexpr int NV = 8;
+    const int total = my_tiles * nkc;
+    const bool gathered = a.table != nullptr;
+    const int E_ = gathered ? a.E : 1;
+    const int seg0 = gathered ? (4 * j) / E_ : 0, rem0 = gathered ? (4 * j) % E_ : 0;
+    // row set of the tile the FIRST pipeline stage is in (ids stage when gathered, load stage when dense)
+    int rs_seq[NV], rs_t0[NV];
+    unsigned rs_valid = 0;
+    auto set_rows = [&](int kt) {
+      const int t = (int)blockIdx.x + kt * (int)gridDim.x;
+      const int64_t m0 = (int64_t)(t / nct) * GT_BM;
+      rs_valid = 0;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int64_t r = m0 + warp * 16 + 2 * i + rsub;
+        const bool v = r < M;
+        rs_valid |= (v ? 1u : 0u) << i;
+        if (gathered) {
+          const int64_t sq = v ? r / a.T : 0;
+          rs_seq[i] = (int)sq;
+          rs_t0[i] = (int)((v ? r : 0) - sq * a.T) - a.pad;
+        } else {
+          rs_seq[i] = (int)r;   // dense providers index rows directly (M < 2^31)
+          rs_t0[i] = 0;
+        }
+      }
+    };
+    bool bad_id = false;
+    int64_t idraw[NV];
+    unsigned ok_ids = 0, ok_ptr = 0;   // per-slice validity of the chunk in the ids stage / handed on to the pointer stage
+    int src[NV];   // element offset of the slice in the table (-1: zero slice); V * E < 2^31 is checked by the launcher
+    float4 vn[NV];
+    int c_kt = 0, c_kc = 0, c_seg = seg0, c_rem = rem0;   // ids stage cursor (gathered)
+    int p_kc = 0, p_rem = rem0, p_kt = 0;                 // pointer / load stage cursor
+    int rows_kt = -1;
+    auto request_ids = [&]() {
+      if (rows_kt != c_kt) set_rows(c_kt), rows_kt = c_kt;
+      const int kk = c_kc * GT_BK + 4 * j;
+      ok_ids = 0;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int pos = rs_t0[i] + c_seg;
+        const bool ok = ((rs_valid >> i) & 1) && kk < K && pos >= 0 && pos < a.L;
+        ok_ids |= (ok ? 1u : 0u) << i;
+        idraw[i] = a.ids[ok ? (int64_t)rs_seq[i] * a.L + pos : 0];
+      }
+      if (++c_kc == nkc) {
+        c_kc = 0, ++c_kt, c_seg = seg0, c_rem = rem0;
+      } else {
+        c_rem += GT_BK;
+        while (c_rem >= E_) c_rem -= E_, ++c_seg;
+      }
+    };
+    auto form_ptrs = [&]() {   // ids requested one call of request_ids ago -> source pointers
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const bool ok = (ok_ptr >> i) & 1;
+        int64_t id = idraw[i];
+        const bool inr = id >= 0 && id < a.V;
+        bad_id |= ok && !inr;
+        id = inr ? id : 0;
+        src[i] = ok ? (int)id * a.E + p_rem : -1;
+      }
+    };
+    auto load_rows = [&]() {
+      if (gathered) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          vn[i] = src[i] >= 0 ? *reinterpret_cast<const float4*>(a.table + src[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        if (rows_kt != p_kt) set_rows(p_kt), rows_kt = p_kt;
+        const int kk = p_kc * GT_BK + 4 * j;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          vn[i] = (((rs_valid >> i) & 1) && kk < K) ? gemm_a_load4(a, (int64_t)rs_seq[i], kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (++p_kc == nkc) {
+        p_kc = 0, ++p_kt, p_rem = rem0;
+      } else if (gathered) {
+        p_rem += GT_BK;
+        while (p_rem >= E_) p_rem -= E_;
+      }
+    };
+    if (total > 0) {
+      if (gathered) {
+        request_ids();
+        ok_ptr = ok_ids;
+        form_ptrs();
+      }
+      load_rows();
+      if (gathered && total > 1) request_ids();
+    }
+    const uint32_t aoff = (uint32_t)(j >> 1) * GT_APLANE + (uint32_t)(warp * 16 + rsub) * 16 + (uint32_t)(j & 1) * 8;
+    for (int g = 0; g < total; ++g) {
+      const int s = g % nst;
+      float4 v[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = vn[i];
+      if (g + 1 < total) {
+        if (gathered) {
+          ok_ptr = ok_ids;
+          form_ptrs();
+        }
+        load_rows();
+      }
+      if (gathered && g + 2 < total) request_ids();
+      mbar_wait_relaxed(&empty[s], ((g / nst) & 1) ^ 1);
+      uint8_t* ah = a_ring + (size_t)s * 2 * GT_AIMG + aoff;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        uint32_t h0, l0, h1, l1;
+        split_bf16x2(v[i].x, v[i].y, h0, l0);
+        split_bf16x2(v[i].z, v[i].w, h1, l1);
+        *reinterpret_cast<uint2*>(ah + (size_t)i * 32) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(ah + GT_AIMG + (size_t)i * 32) = make_uint2(l0, l1);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) gt_arrive(&a_full[s]);
+    }
+    if (bad_id && a.err) atomicOr(a.err, ERRF_BAD_TOKEN);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 2 * tcols1);
+}
+
 bool gemm_tc_usable(const GemmA& a, int K) {
   if (!g_gemm_impl) return false;
   if (K % 4) return false;
@@ -289,6 +571,27 @@ int32_t gemm_tc(const GemmA& a, const GemmTcW& w, const float* bias, float* c, i
                 cudaStream_t s) {
   if (M <= 0) return CAIR_OK;
   if ((a.table || a.dwin) && w.K != a.win * a.E) return fail(CAIR_ERR_BAD_ARG, "gemm_tc: K != win*E");
+  if (g_gemm_impl != 2 && M < ((int64_t)1 << 31) && (!a.table || (int64_t)a.V * a.E < ((int64_t)1 << 31))) {
+    // persistent pipelined kernel
+    const size_t stage_bytes = (size_t)2 * GT_AIMG + (size_t)2 * (GT_BK / 8) * w.NT * 16;
+    const size_t ebytes = (size_t)G2_EWARPS * G2_ESTAGE * sizeof(float);
+    int nst = (int)((220 * 1024 - ebytes) / stage_bytes);
+    nst = nst > GT_MAXSTAGES ? GT_MAXSTAGES : nst;
+    if (nst >= 2) {
+      uint32_t tcols1 = 32;
+      while ((int)tcols1 < ((w.NT + 31) & ~31)) tcols1 <<= 1;
+      const int64_t mtiles = (M + GT_BM - 1) / GT_BM;
+      const int64_t ntiles = mtiles * w.nct;
+      if (ntiles < ((int64_t)1 << 31)) {
+        const size_t smem = (size_t)nst * stage_bytes + ebytes;
+        CAIR_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)(ntiles < kSMs ? ntiles : kSMs);
+        CAIR_LAUNCH(gemm_tc2_kernel, grid, G2_THREADS, smem, s, a, w.img, bias, c, ldc, M, w.N, w.K, w.NT, w.nkc, w.nct, (int)act,
+                    tcols1, nst, (int)ntiles, g_gemm_dbg);
+        return CAIR_OK;
+      }
+    }
+  }
   const size_t stage_bytes = (size_t)2 * GT_AIMG + (size_t)2 * (GT_BK / 8) * w.NT * 16;
   int nst = (int)((220 * 1024) / stage_bytes);
   nst = nst > GT_MAXSTAGES ? GT_MAXSTAGES : nst;

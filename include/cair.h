@@ -177,7 +177,9 @@ CAIR_API int32_t cair_mt_create(const cair_mt_weights* w, int32_t device, cair_h
 CAIR_API int32_t cair_mt_set_debug(cair_handle* h, float* enc_q, float* enc_d);
 
 /* Process-wide GEMM engine for the generic projections / convolutions (DUET, CARS, DSSM, channel projections):
- * 1 = tcgen05 bf16x3 tensor-core GEMM where the operand layout allows (default), 0 = fp32 CUDA-core GEMM. */
+ * 1 = tcgen05 bf16x3 tensor-core GEMM where the operand layout allows (default: persistent CTAs, one loader pipeline across
+ * tiles, double-buffered TMEM accumulator drained by dedicated warps), 2 = the same arithmetic with one tile per CTA (the
+ * round-1 kernel, kept for A/B runs), 0 = fp32 CUDA-core GEMM. */
 CAIR_API int32_t cair_set_gemm_impl(int32_t impl);
 
 /* Interaction kernel selection: 1 = tcgen05 bf16x3 split-precision tensor-core kernel (default when the
