@@ -377,7 +377,7 @@ def other_configs(run, args, peaks):
     ranker_case('esm E=300 (cfg3 shape)', dict(model='esm', emsize=300, src_vocab_size=131072), 256, 10, 20, 200, 10,
                 hbm_roof('esm_kernel', bpp_fp32(300, 20, 200, 10)))
     ranker_case('drmm cfg3', dict(model='drmm', emsize=300, src_vocab_size=131072, dropout_emb=0.2, nbins=5), 256, 10, 20, 200, 10,
-                hbm_roof('drmm2_kernel', bpp_fp32(300, 20, 200, 10)))
+                hbm_roof('drmm_tc_kernel', bpp_fp32(300, 20, 200, 10)))
     for n in (10, 50, 100, 500):
         ranker_case('duet cfg5 N=%d' % n, DUET_CFG, 32, n, 20, 200, 10 if n <= 100 else 4, tensor_roof('gemm_tc_kernel', 145.8))
 
@@ -405,6 +405,61 @@ def other_configs(run, args, peaks):
              steps=10, stages_ms={k: round(v, 4) for k, v in st.items() if k != 'begin'})
     e['roofline'] = tensor_roof('rnn_tc_kernel', 205.0)(Bc * S * Nc, ms, st)
     out.append(e)
+    del net
+    torch.cuda.empty_cache()
+
+    # MNSRF ranking path at the cfg4 shape, sharded by session like CARS
+    torch.manual_seed(1013)
+    mcfg = dict(model='mnsrf', emsize=300, src_vocab_size=CARS_CFG['src_vocab_size'], tgt_vocab_size=50, dropout_emb=0.2, dropout=0.2,
+                rnn_type='LSTM', bidirection=True, nlayers=1, nhid_query=256, nhid_document=256, nhid_session=512, dropout_rnn=0.2,
+                regularize_coeff=0.1)
+    net = helpers.build_module(mcfg).to(dev)
+
+    def mnsrf_step():
+        with torch.no_grad():
+            s = net.score(*t[:4], session_slice=(rank * Bc, Bc))['scores']
+            if world > 1:
+                s = gather_scores(s[rank * Bc:(rank + 1) * Bc].reshape(-1), total)
+        return s
+    ms, _ = run.time_steps(mnsrf_step, 10, 3)
+    out.append(dict(name='mnsrf, cfg4 shape (ranking path)', config=dict(model='mnsrf', B=Bc, S=S, N=Nc, Lq=Lq, Ld=Ld, E=300, H=256),
+                    pairs_per_s=total / (ms / 1e3), ms_per_step=ms, n_gpus=world, scaling='weak', steps=10,
+                    parallelism='session-parallel x%d: %d sessions per GPU, one all-gather of scores per step' % (world, Bc),
+                    roofline=tensor_roof('rnn_tc_kernel', 197.0)(Bc * S * Nc, ms, {})))
+    del net
+    torch.cuda.empty_cache()
+
+    # Match-Tensor TRAINING step at the cfg2 shape: the statement order of the reference's Ranker.update
+    # (forward, BCEWithLogitsLoss, zero_grad, backward, clip_grad_norm, SGD step); data-parallel replicas, gradients
+    # all-reduced by NCCL at N > 1 (what nn.DataParallel's backward does in the reference)
+    torch.manual_seed(1013)
+    tnet = helpers.build_module(CFG).to(dev).train()
+    tb = synth.ranker_batch(4321 + rank, B, N, LQ, LD, CFG['src_vocab_size'], variable=False)
+    tq = helpers.to_dev(tb, dev)
+    labels = torch.from_numpy(tb['label']).float().to(dev)
+    params = [p for p in tnet.parameters() if p.requires_grad]
+    opt = torch.optim.SGD(params, 0.05)
+    crit = torch.nn.BCEWithLogitsLoss()
+
+    def train_step():
+        loss = crit(tnet(*tq), labels)
+        opt.zero_grad()
+        loss.backward()
+        if world > 1:
+            for p in params:
+                dist.all_reduce(p.grad)
+                p.grad.div_(world)
+        torch.nn.utils.clip_grad_norm_(params, 5.0)
+        opt.step()
+        return loss
+    ms, _ = run.time_steps(train_step, 6, 3)
+    out.append(dict(name='match_tensor cfg2 TRAINING step (forward + backward + clip + SGD)', config=dict(model='match_tensor', B=B, N=N, Lq=LQ, Ld=LD, dropout_emb=CFG['dropout_emb']),
+                    pairs_per_s=B * N * world / (ms / 1e3), ms_per_step=ms, n_gpus=world, scaling='weak', steps=6,
+                    parallelism='data-parallel x%d: %d pairs per GPU, gradient all-reduce per step' % (world, B * N),
+                    roofline=tensor_roof('mt_interact_kernel<1> / lstm_train_*', 3 * flops_per_pair()['ref'])(B * N, ms, {}),
+                    note='fp32 CUDA-core training kernels (csrc/train.cu): first slice of the backward row, not yet on the tensor cores'))
+    del tnet, opt
+    torch.cuda.empty_cache()
     return out
 
 

@@ -75,10 +75,11 @@ int32_t cars_create_state(Owned& own, const cair_cars_weights& w, CarsState* st,
 
 // ---- attention pooling (cars.py:671-691): one CTA per sequence ----
 // hid [n*L, H] = tanh(l0(enc)) precomputed by the GEMM; score_t = w3 . hid_t + b3, masked softmax, mix.
+// scores (optional): w3 . hid_t + b3 already computed by the GEMM's row-dot epilogue (hid is then not materialised)
 __global__ void __launch_bounds__(256) attn_pool_kernel(const float* __restrict__ enc, const float* __restrict__ hid,
                                                         const int64_t* __restrict__ len, int L, int H,
                                                         const float* __restrict__ w3, const float* __restrict__ b3,
-                                                        float* __restrict__ pooled) {
+                                                        float* __restrict__ pooled, const float* __restrict__ scores) {
   extern __shared__ float sc[];  // [L]
   __shared__ float red[8];
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -86,7 +87,9 @@ __global__ void __launch_bounds__(256) attn_pool_kernel(const float* __restrict_
   l = l < 1 ? 1 : (l > L ? L : l);
   for (int t = warp; t < L; t += 8) {
     float v = -INFINITY;
-    if (t < l) {
+    if (t < l && scores) {
+      v = scores[(size_t)s * L + t];
+    } else if (t < l) {
       const float* hrow = hid + ((size_t)s * L + t) * H;
       float a = 0.f;
       for (int k = lane; k < H; k += 32) a = fmaf(w3[k], hrow[k], a);
@@ -375,9 +378,15 @@ static int32_t encode_pool(const CarsState& st, const LstmPack& lp, const RnnTcP
     CAIR_TRY(lstm_run(lp, gemm_gather(st.table, st.V, st.E, ids, 1, 1, 1, err), len, (int)n, L, enc, nullptr, nullptr,
                       pre, err, s, rec_name));
   prof_mark("attention_pool", s);
+  if (gemm_tc_rowdot_usable(gemm_dense(enc, H), ap.w0_tc, n * L)) {
+    // tanh(l0(enc)) . w3 + b3 inside the GEMM epilogue: the [n*L, H] hidden tensor is never written (hid holds the scores)
+    CAIR_TRY(gemm_tc_rowdot(gemm_dense(enc, H), ap.w0_tc, ap.b0, ACT_TANH, ap.w3, ap.b3, hid, n * L, s));
+    CAIR_LAUNCH(attn_pool_kernel, (unsigned)n, 256, (size_t)L * sizeof(float), s, enc, nullptr, len, L, H, ap.w3, ap.b3, pooled, hid);
+    return CAIR_OK;
+  }
   CAIR_TRY(gemm_auto(gemm_dense(enc, H), ap.w0, ap.w0_tc, ap.b0, hid, H, n * L, H, H, ACT_TANH, s));
   CAIR_LAUNCH(attn_pool_kernel, (unsigned)n, 256, (size_t)L * sizeof(float), s, enc, hid, len, L, H, ap.w3, ap.b3,
-              pooled);
+              pooled, (const float*)nullptr);
   return CAIR_OK;
 }
 

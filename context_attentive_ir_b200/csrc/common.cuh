@@ -234,6 +234,10 @@ int32_t gemm_tc_pack(Owned& own, const float* w, int N, int K, GemmTcW* out, cud
 bool gemm_tc_usable(const GemmA& a, int K);
 int32_t gemm_tc(const GemmA& a, const GemmTcW& w, const float* bias, float* c, int64_t ldc, int64_t M, Act act,
                 cudaStream_t s);
+// out[r] = dot_w . act(A[r] W^T + bias) + dot_b with the [M, N] product kept in TMEM (attention-MLP scores)
+bool gemm_tc_rowdot_usable(const GemmA& a, const GemmTcW& w, int64_t M);
+int32_t gemm_tc_rowdot(const GemmA& a, const GemmTcW& w, const float* bias, Act act, const float* dot_w, const float* dot_b,
+                       float* out, int64_t M, cudaStream_t s);
 // tensor-core GEMM when a packed image exists and the A provider is 128-bit loadable, else the fp32 kernel
 inline int32_t gemm_auto(const GemmA& a, const float* w, const GemmTcW& tw, const float* bias, float* c, int64_t ldc,
                          int64_t M, int N, int K, Act act, cudaStream_t s) {

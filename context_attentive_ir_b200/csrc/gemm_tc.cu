@@ -292,7 +292,8 @@ constexpr int G2_ESTAGE = 32 * 33;                               // floats per e
 __global__ void __launch_bounds__(G2_THREADS, 1)
     gemm_tc2_kernel(GemmA a, const uint8_t* __restrict__ wimg, const float* __restrict__ bias, float* __restrict__ c,
                     int64_t ldc, int64_t M, int N, int K, int NT, int nkc, int nct, int act, uint32_t tcols1, int nst,
-                    int ntiles, int dbg) {
+                    int ntiles, int dbg, const float* __restrict__ dot_w, const float* __restrict__ dot_b,
+                    float* __restrict__ dot_out) {
   extern __shared__ __align__(128) uint8_t smraw[];
   __shared__ uint64_t a_full[GT_MAXSTAGES], w_full[GT_MAXSTAGES], empty[GT_MAXSTAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
@@ -385,6 +386,30 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
       const int n0 = ct * NT;
       mbar_wait_relaxed(&acc_full[buf], (kt >> 1) & 1);
       tc_fence_after();
+      if (dot_out) {
+        // row-dot epilogue (one column tile): out[r] = dot_w . act(row r + bias) + dot_b; the [M, N] product is never stored
+        float dot = 0.f;
+        for (int c0 = 0; c0 < NT; c0 += 32) {
+          float v[32];
+          tmem_ld32(tbase + ((uint32_t)(qt * 32) << 16) + (uint32_t)buf * tcols1 + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int col = c0 + jj;
+            if (col < N) {   // uniform
+              float x = v[jj] + (bias ? __ldg(bias + col) : 0.f);
+              if (act == ACT_TANH) x = tanhf(x);
+              if (act == ACT_RELU) x = fmaxf(x, 0.f);
+              dot = fmaf(__ldg(dot_w + col), x, dot);
+            }
+          }
+        }
+        if (rbase + lane < M) dot_out[rbase + lane] = dot + (dot_b ? __ldg(dot_b) : 0.f);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) gt_arrive(&acc_empty[buf]);
+        continue;
+      }
       for (int c0 = 0; c0 < NT; c0 += 32) {
         float v[32];
         tmem_ld32(tbase + ((uint32_t)(qt * 32) << 16) + (uint32_t)buf * tcols1 + c0, v);
@@ -567,30 +592,49 @@ bool gemm_tc_usable(const GemmA& a, int K) {
   return (a.lda % 4 == 0) && ((uintptr_t)a.dense % 16 == 0);
 }
 
+static bool gemm_tc2_shape_ok(const GemmA& a, int64_t M) {
+  return g_gemm_impl == 1 && M < ((int64_t)1 << 31) && (!a.table || (int64_t)a.V * a.E < ((int64_t)1 << 31));
+}
+// out[r] = dot_w . act(A[r] W^T + bias) + dot_b without storing the [M, N] product (N <= 256: one column tile)
+bool gemm_tc_rowdot_usable(const GemmA& a, const GemmTcW& w, int64_t M) {
+  return w.img && w.nct == 1 && M >= 128 && gemm_tc_usable(a, w.K) && gemm_tc2_shape_ok(a, M);
+}
+static int32_t gemm_tc2_launch(const GemmA& a, const GemmTcW& w, const float* bias, float* c, int64_t ldc, int64_t M, Act act,
+                               const float* dot_w, const float* dot_b, float* dot_out, cudaStream_t s, bool* done) {
+  *done = false;
+  const size_t stage_bytes = (size_t)2 * GT_AIMG + (size_t)2 * (GT_BK / 8) * w.NT * 16;
+  const size_t ebytes = (size_t)G2_EWARPS * G2_ESTAGE * sizeof(float);
+  int nst = (int)((220 * 1024 - ebytes) / stage_bytes);
+  nst = nst > GT_MAXSTAGES ? GT_MAXSTAGES : nst;
+  if (nst < 2) return CAIR_OK;
+  uint32_t tcols1 = 32;
+  while ((int)tcols1 < ((w.NT + 31) & ~31)) tcols1 <<= 1;
+  const int64_t ntiles = ((M + GT_BM - 1) / GT_BM) * w.nct;
+  if (ntiles >= ((int64_t)1 << 31)) return CAIR_OK;
+  const size_t smem = (size_t)nst * stage_bytes + ebytes;
+  CAIR_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)(ntiles < kSMs ? ntiles : kSMs);
+  CAIR_LAUNCH(gemm_tc2_kernel, grid, G2_THREADS, smem, s, a, w.img, bias, c, ldc, M, w.N, w.K, w.NT, w.nkc, w.nct, (int)act, tcols1, nst,
+              (int)ntiles, g_gemm_dbg, dot_w, dot_b, dot_out);
+  *done = true;
+  return CAIR_OK;
+}
+int32_t gemm_tc_rowdot(const GemmA& a, const GemmTcW& w, const float* bias, Act act, const float* dot_w, const float* dot_b,
+                       float* out, int64_t M, cudaStream_t s) {
+  if ((a.table || a.dwin) && w.K != a.win * a.E) return fail(CAIR_ERR_BAD_ARG, "gemm_tc: K != win*E");
+  bool done = false;
+  CAIR_TRY(gemm_tc2_launch(a, w, bias, nullptr, 0, M, act, dot_w, dot_b, out, s, &done));
+  return done ? CAIR_OK : fail(CAIR_ERR_UNSUPPORTED, "gemm_tc_rowdot: shape not supported (check gemm_tc_rowdot_usable)");
+}
+
 int32_t gemm_tc(const GemmA& a, const GemmTcW& w, const float* bias, float* c, int64_t ldc, int64_t M, Act act,
                 cudaStream_t s) {
   if (M <= 0) return CAIR_OK;
   if ((a.table || a.dwin) && w.K != a.win * a.E) return fail(CAIR_ERR_BAD_ARG, "gemm_tc: K != win*E");
-  if (g_gemm_impl != 2 && M < ((int64_t)1 << 31) && (!a.table || (int64_t)a.V * a.E < ((int64_t)1 << 31))) {
-    // persistent pipelined kernel
-    const size_t stage_bytes = (size_t)2 * GT_AIMG + (size_t)2 * (GT_BK / 8) * w.NT * 16;
-    const size_t ebytes = (size_t)G2_EWARPS * G2_ESTAGE * sizeof(float);
-    int nst = (int)((220 * 1024 - ebytes) / stage_bytes);
-    nst = nst > GT_MAXSTAGES ? GT_MAXSTAGES : nst;
-    if (nst >= 2) {
-      uint32_t tcols1 = 32;
-      while ((int)tcols1 < ((w.NT + 31) & ~31)) tcols1 <<= 1;
-      const int64_t mtiles = (M + GT_BM - 1) / GT_BM;
-      const int64_t ntiles = mtiles * w.nct;
-      if (ntiles < ((int64_t)1 << 31)) {
-        const size_t smem = (size_t)nst * stage_bytes + ebytes;
-        CAIR_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const unsigned grid = (unsigned)(ntiles < kSMs ? ntiles : kSMs);
-        CAIR_LAUNCH(gemm_tc2_kernel, grid, G2_THREADS, smem, s, a, w.img, bias, c, ldc, M, w.N, w.K, w.NT, w.nkc, w.nct, (int)act,
-                    tcols1, nst, (int)ntiles, g_gemm_dbg);
-        return CAIR_OK;
-      }
-    }
+  if (gemm_tc2_shape_ok(a, M)) {
+    bool done = false;
+    CAIR_TRY(gemm_tc2_launch(a, w, bias, c, ldc, M, act, nullptr, nullptr, nullptr, s, &done));
+    if (done) return CAIR_OK;
   }
   const size_t stage_bytes = (size_t)2 * GT_AIMG + (size_t)2 * (GT_BK / 8) * w.NT * 16;
   int nst = (int)((220 * 1024) / stage_bytes);
