@@ -676,6 +676,124 @@ int32_t mt_interact_train(const MtPack& p, const float* cq, const float* cd, flo
                           int Lq, int Ld, int64_t pairs, int64_t nq, float* scores, float* pooled, int* argidx,
                           cudaStream_t s);   // mt.cu
 
+
+// ------------------------------------------------------------------------------------------------
+// DRMM training step (neuroir/rankers/drmm.py:29-84 in train mode).  The histogram is computed with numpy in the reference
+// (no gradient flows through the cosines), so the differentiable part is tiny: gating softmax over the (dropped) query
+// embeddings, ffnn (5 -> 1 -> 1), output layer.  Forward: the dropped embedding rows of this batch are materialised as a
+// per-batch "virtual table" (query rows first, then document rows; row r of it = token r of the batch) and the ordinary
+// DRMM kernels run on it with ids 0, 1, 2, ... - so train-mode dropout reaches the cosines exactly as in the reference,
+// and with p = 0 the arithmetic is the eval path's.  The histograms are kept for the backward.
+__global__ void iota_kernel(int64_t* p, int64_t n, int64_t base) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = base + i;
+}
+
+// one CTA per query: its N documents share the term gate
+__global__ void __launch_bounds__(128) drmm_train_bwd_kernel(const float* __restrict__ vtable, const int64_t* __restrict__ q,
+                                                             const int32_t* __restrict__ hist, const float* __restrict__ dscores,
+                                                             const float* __restrict__ wg, const float* __restrict__ bg,
+                                                             const float* __restrict__ w0, const float* __restrict__ b0,
+                                                             const float* __restrict__ w1, const float* __restrict__ b1,
+                                                             const float* __restrict__ wo, int V, int E, int N, int Lq, float p,
+                                                             uint64_t seed, float* g_wg, float* g_bg, float* g_w0, float* g_b0,
+                                                             float* g_w1, float* g_b1, float* g_wo, float* g_bo, float* g_table) {
+  __shared__ float gate[32], dg[32], da[32], acc[16];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float inv = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  if (tid < 16) acc[tid] = 0.f;
+  // gate = softmax_i(wg . xq_i + bg) over all Lq positions (drmm.py:95-98)
+  for (int i = warp; i < Lq; i += 4) {
+    const float* x = vtable + ((size_t)b * Lq + i) * E;
+    float a = 0.f;
+    for (int e = lane; e < E; e += 32) a = fmaf(wg[e], x[e], a);
+    a = warp_sum(a);
+    if (lane == 0) gate[i] = a + bg[0];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float v = lane < Lq ? gate[lane] : -INFINITY;
+    const float mx = warp_max(v);
+    const float ex = lane < Lq ? expf(v - mx) : 0.f;
+    const float den = warp_sum(ex);
+    if (lane < Lq) gate[lane] = ex / den, dg[lane] = 0.f;
+  }
+  __syncthreads();
+  // per document: score = wo * sum_i f_i g_i + bo, f_i = w1 (w0 . hist_i + b0) + b1
+  if (warp == 0) {
+    float a_wo = 0.f, a_bo = 0.f, a_w1 = 0.f, a_b1 = 0.f, a_b0 = 0.f, a_w0[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, dgl = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const int64_t pr = (int64_t)b * N + n;
+      const float ds = dscores[pr];
+      float z = 0.f, f = 0.f, h5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      if (lane < Lq) {
+        z = b0[0];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          h5[k] = (float)hist[(pr * Lq + lane) * 5 + k];
+          z = fmaf(w0[k], h5[k], z);
+        }
+        f = w1[0] * z + b1[0];
+      }
+      const float S = warp_sum(lane < Lq ? f * gate[lane] : 0.f);
+      a_wo += ds * S, a_bo += ds;
+      const float dS = ds * wo[0];
+      if (lane < Lq) {
+        const float df = dS * gate[lane];
+        dgl += dS * f;
+        a_w1 += df * z, a_b1 += df;
+        const float dz = df * w1[0];
+        a_b0 += dz;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) a_w0[k] += dz * h5[k];
+      }
+    }
+    a_w1 = warp_sum(a_w1), a_b1 = warp_sum(a_b1), a_b0 = warp_sum(a_b0);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) a_w0[k] = warp_sum(a_w0[k]);
+    // softmax backward
+    const float gd = warp_sum(lane < Lq ? gate[lane] * dgl : 0.f);
+    if (lane < Lq) da[lane] = gate[lane] * (dgl - gd);
+    const float sda = warp_sum(lane < Lq ? gate[lane] * (dgl - gd) : 0.f);
+    if (lane == 0) {
+      atomicAdd(g_wo, a_wo), atomicAdd(g_bo, a_bo), atomicAdd(g_w1, a_w1), atomicAdd(g_b1, a_b1), atomicAdd(g_b0, a_b0);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) atomicAdd(&g_w0[k], a_w0[k]);
+      atomicAdd(g_bg, sda);
+    }
+  }
+  __syncthreads();
+  // d wg = sum_i da_i xq_i ;  d xq_i = da_i wg  -> mask -> table rows (PAD skipped)
+  for (int e = tid; e < E; e += 128) {
+    float a = 0.f;
+    for (int i = 0; i < Lq; ++i) a = fmaf(da[i], vtable[((size_t)b * Lq + i) * E + e], a);
+    if (a != 0.f) atomicAdd(&g_wg[e], a);
+    if (g_table) {
+      const float w = wg[e];
+      for (int i = 0; i < Lq; ++i) {
+        const int64_t id = q[(size_t)b * Lq + i];
+        if (id <= 0 || id >= V) continue;
+        const float v = da[i] * w * drop_scale(seed, (uint64_t)(((size_t)b * Lq + i) * E + e), p, inv);
+        if (v != 0.f) atomicAdd(&g_table[id * E + e], v);
+      }
+    }
+  }
+}
+
+struct DrmmTrainWs {
+  int* err;
+  float* vtable;
+  int64_t *vq, *vd;
+  int32_t* hist;
+};
+static void drmm_train_layout(Arena& a, int E, int B, int N, int Lq, int Ld, DrmmTrainWs* o) {
+  const size_t Rq = (size_t)B * Lq, Rd = (size_t)B * N * Ld;
+  o->err = a.take<int>(64);
+  o->vtable = a.take<float>((Rq + Rd) * E);
+  o->vq = a.take<int64_t>(Rq), o->vd = a.take<int64_t>(Rd);
+  o->hist = a.take<int32_t>((size_t)B * N * Lq * 5);
+}
+
 }  // namespace cair
 
 using namespace cair;
@@ -888,6 +1006,68 @@ int32_t cair_mt_train_backward(cair_mt_trainer* h, const int64_t* q, const int64
     CAIR_LAUNCH(embed_grad_kernel, 1184, 256, smem, s, o.dfd, w.linear_projection.w, d, w.vocab, E, F, Rd, Rq, p_drop, seed,
                 gp(G.table));
   }
+  return CAIR_OK;
+}
+
+int32_t cair_drmm_train_workspace_bytes(int32_t emsize, int32_t B, int32_t N, int32_t Lq, int32_t Ld, size_t* bytes) {
+  if (!bytes || emsize <= 0 || B <= 0 || N <= 0 || Lq <= 0 || Ld <= 0) return fail(CAIR_ERR_BAD_ARG, "drmm_train_workspace_bytes: bad argument");
+  Arena a(nullptr, 0);
+  DrmmTrainWs o;
+  drmm_train_layout(a, emsize, B, N, Lq, Ld, &o);
+  Arena fwd(nullptr, 0);
+  cair_drmm_weights w{};
+  w.emsize = emsize;
+  CAIR_TRY(drmm_forward(w, nullptr, nullptr, N, Lq, Ld, 0, (int64_t)B * N, nullptr, nullptr, fwd, nullptr, 0, true));
+  *bytes = align_up(a.off) + align_up(fwd.off) + 512;
+  return CAIR_OK;
+}
+
+int32_t cair_drmm_train_forward(const cair_drmm_weights* w, const int64_t* q, const int64_t* d, int32_t B, int32_t N, int32_t Lq,
+                                int32_t Ld, float p_drop, uint64_t seed, float* scores, void* ws, size_t ws_bytes, void* stream) {
+  if (!w || !q || !d || !scores || !ws || !w->table) return fail(CAIR_ERR_BAD_ARG, "drmm_train_forward: null argument");
+  if (p_drop < 0.f || p_drop >= 1.f) return fail(CAIR_ERR_BAD_ARG, "drmm_train_forward: dropout must be in [0, 1)");
+  if ((uintptr_t)ws % 256) return fail(CAIR_ERR_WORKSPACE, "drmm_train_forward: workspace must be 256-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena a(ws, ws_bytes);
+  DrmmTrainWs o;
+  drmm_train_layout(a, w->emsize, B, N, Lq, Ld, &o);
+  a.off = align_up(a.off);
+  const int64_t Rq = (int64_t)B * Lq, Rd = (int64_t)B * N * Ld;
+  if (Rq + Rd >= ((int64_t)1 << 31)) return fail(CAIR_ERR_UNSUPPORTED, "drmm_train_forward: batch too large");
+  {
+    Arena probe = a;
+    cair_drmm_weights wp = *w;
+    CAIR_TRY(drmm_forward(wp, nullptr, nullptr, N, Lq, Ld, 0, (int64_t)B * N, nullptr, nullptr, probe, nullptr, 0, true));
+    if (!probe.ok()) return fail(CAIR_ERR_WORKSPACE, "drmm_train_forward: workspace too small");
+  }
+  CAIR_CUDA(cudaMemsetAsync(o.err, 0, 256, s));
+  CAIR_LAUNCH(embed_drop_kernel, 1184, 256, 0, s, w->table, q, w->vocab, w->emsize, Rq, (int64_t)0, p_drop, seed, o.vtable, o.err);
+  CAIR_LAUNCH(embed_drop_kernel, 1184, 256, 0, s, w->table, d, w->vocab, w->emsize, Rd, Rq, p_drop, seed,
+              o.vtable + (size_t)Rq * w->emsize, o.err);
+  CAIR_LAUNCH(iota_kernel, (unsigned)((Rq + 255) / 256), 256, 0, s, o.vq, Rq, (int64_t)0);
+  CAIR_LAUNCH(iota_kernel, (unsigned)((Rd + 255) / 256), 256, 0, s, o.vd, Rd, Rq);
+  cair_drmm_weights wv = *w;
+  wv.table = o.vtable;
+  wv.vocab = (int32_t)(Rq + Rd);
+  return drmm_forward(wv, o.vq, o.vd, N, Lq, Ld, 0, (int64_t)B * N, scores, o.hist, a, o.err, s, false);
+}
+
+int32_t cair_drmm_train_backward(const cair_drmm_weights* w, const cair_drmm_weights* grads, const int64_t* q, int32_t B, int32_t N,
+                                 int32_t Lq, int32_t Ld, float p_drop, uint64_t seed, const float* dscores, void* ws, size_t ws_bytes,
+                                 void* stream) {
+  if (!w || !grads || !q || !dscores || !ws) return fail(CAIR_ERR_BAD_ARG, "drmm_train_backward: null argument");
+  const cair_drmm_weights& G = *grads;
+  if (!G.gating.w || !G.gating.b || !G.ffnn0.w || !G.ffnn0.b || !G.ffnn1.w || !G.ffnn1.b || !G.output.w || !G.output.b)
+    return fail(CAIR_ERR_BAD_ARG, "drmm_train_backward: null gradient pointer (only `table` may be NULL)");
+  if (Lq > 32) return fail(CAIR_ERR_UNSUPPORTED, "drmm_train_backward: max_query_len > 32");
+  Arena a(ws, ws_bytes);
+  DrmmTrainWs o;
+  drmm_train_layout(a, w->emsize, B, N, Lq, Ld, &o);
+  if (!a.ok()) return fail(CAIR_ERR_WORKSPACE, "drmm_train_backward: workspace too small");
+  CAIR_LAUNCH(drmm_train_bwd_kernel, (unsigned)B, 128, 0, (cudaStream_t)stream, o.vtable, q, o.hist, dscores, w->gating.w, w->gating.b,
+              w->ffnn0.w, w->ffnn0.b, w->ffnn1.w, w->ffnn1.b, w->output.w, w->vocab, w->emsize, N, Lq, p_drop, seed,
+              gp(G.gating.w), gp(G.gating.b), gp(G.ffnn0.w), gp(G.ffnn0.b), gp(G.ffnn1.w), gp(G.ffnn1.b), gp(G.output.w),
+              gp(G.output.b), gp(G.table));
   return CAIR_OK;
 }
 

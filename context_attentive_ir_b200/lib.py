@@ -70,6 +70,11 @@ PROTOTYPES = {
                                      C.POINTER(_abi.MtWeights), vp, C.c_size_t, vp]),
     'cair_mt_train_poll_error': (i32, [vp, vp, vp]),
     'cair_dropout_mask': (i32, [C.c_uint64, C.c_float, i64, vp, vp]),
+    'cair_drmm_train_workspace_bytes': (i32, [i32, i32, i32, i32, i32, C.POINTER(C.c_size_t)]),
+    'cair_drmm_train_forward': (i32, [C.POINTER(_abi.DrmmWeights), vp, vp, i32, i32, i32, i32, C.c_float, C.c_uint64, vp, vp,
+                                      C.c_size_t, vp]),
+    'cair_drmm_train_backward': (i32, [C.POINTER(_abi.DrmmWeights), C.POINTER(_abi.DrmmWeights), vp, i32, i32, i32, i32, C.c_float,
+                                       C.c_uint64, vp, vp, C.c_size_t, vp]),
     'cair_mnsrf_create': (i32, [C.POINTER(_abi.MnsrfWeights), i32, C.POINTER(vp)]),
     'cair_mnsrf_destroy': (i32, [vp]),
     'cair_mnsrf_workspace_bytes': (i32, [vp, i32, i32, i32, i32, i32, C.POINTER(C.c_size_t)]),

@@ -229,7 +229,7 @@ class _Ranker(_CairModule):
         return scores
 
     def _train_forward(self, batch_queries, query_len, batch_docs, doc_len):
-        raise NotImplementedError('%s: the libcair training step exists for MatchTensor only; score under .eval()'
+        raise NotImplementedError('%s: the libcair training step exists for MatchTensor and DRMM only; score under .eval()'
                                   % type(self).__name__)
 
     @staticmethod
@@ -576,6 +576,48 @@ class _MtTrainFn(torch.autograd.Function):
         return (None,) * 8 + tuple(out)
 
 
+class _DrmmTrainFn(torch.autograd.Function):
+    """Train-mode DRMM scores through libcair (cair_drmm_train_forward) with libcair's backward for the gate / ffnn / output
+    parameters and, through the gate, the embedding rows of the query tokens."""
+
+    @staticmethod
+    def forward(ctx, module, names, q, d, p_drop, seed, *params):
+        dev = q.device
+        L = lib.load()
+        B, Lq = q.shape
+        _, N, Ld = d.shape
+        live = dict(zip(names, params))
+        w = _abi.PACKERS['drmm'](module._cfg(), lambda k: C.cast(live[k].data_ptr(), _abi.f32p))
+        nbytes = C.c_size_t()
+        lib.check(L.cair_drmm_train_workspace_bytes(module.args.emsize, B, N, Lq, Ld, C.byref(nbytes)))
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        scores = torch.empty(B, N, dtype=torch.float32, device=dev)
+        lib.check(L.cair_drmm_train_forward(C.byref(w), q.data_ptr(), d.data_ptr(), B, N, Lq, Ld, p_drop, seed, scores.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+        ctx.module, ctx.names, ctx.args = module, names, (q, d, p_drop, seed, ws, params)
+        ctx.shapes = [(p.shape, p.requires_grad) for p in params]
+        return scores
+
+    @staticmethod
+    def backward(ctx, dscores):
+        module, names = ctx.module, ctx.names
+        q, d, p_drop, seed, ws, params = ctx.args
+        dev = q.device
+        B, Lq = q.shape
+        _, N, Ld = d.shape
+        live = dict(zip(names, params))
+        grads = {}
+        for name, (shape, req) in zip(names, ctx.shapes):
+            grads[name] = None if (name == _abi.TABLE_KEY and not req) else torch.zeros(shape, dtype=torch.float32, device=dev)
+        w = _abi.PACKERS['drmm'](module._cfg(), lambda k: C.cast(live[k].data_ptr(), _abi.f32p))
+        gw = _abi.PACKERS['drmm'](module._cfg(), lambda k: C.cast(grads[k].data_ptr() if grads[k] is not None else None, _abi.f32p))
+        dscores = dscores.contiguous().float()
+        lib.check(lib.load().cair_drmm_train_backward(C.byref(w), C.byref(gw), q.data_ptr(), B, N, Lq, Ld, p_drop, seed,
+                                                      dscores.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                      torch.cuda.current_stream(dev).cuda_stream))
+        return (None,) * 6 + tuple(grads[n] if req else None for n, (_, req) in zip(names, ctx.shapes))
+
+
 class GatingNetwork(nn.Module):
     """neuroir/rankers/drmm.py:87-93."""
 
@@ -604,6 +646,19 @@ class DRMM(_Ranker):
 
     def _create(self, w, device, out):
         return lib.load().cair_drmm_create(w, device, out)
+
+    def _train_forward(self, batch_queries, query_len, batch_docs, doc_len):
+        """Train mode (Ranker.update): cair_drmm_train_forward / cair_drmm_train_backward on the live parameters."""
+        q = self._ids(batch_queries, 'batch_queries')
+        d = self._ids(batch_docs, 'batch_docs')
+        for name, p in self.named_parameters():
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError('DRMM training needs contiguous fp32 CUDA parameters (%s)' % name)
+        seed = self.__dict__.get('_cair_drop_seed')
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        names = [n for n, _ in self.named_parameters()]
+        return _DrmmTrainFn.apply(self, names, q, d, float(self.emb_drop.p), seed, *[p for _, p in self.named_parameters()])
 
 
 class LocalModel(nn.Module):

@@ -448,6 +448,21 @@ CAIR_API int32_t cair_mt_train_backward(cair_mt_trainer* t, const int64_t* q, co
 CAIR_API int32_t cair_mt_train_poll_error(cair_mt_trainer* t, void* workspace, void* stream);
 CAIR_API int32_t cair_dropout_mask(uint64_t seed, float p, int64_t n, float* out, void* stream);
 
+/* Training step of DRMM (neuroir/rankers/drmm.py:29-84 in train mode under Ranker.update, models/ranker.py:192-230).  The
+ * reference computes the histograms with numpy, so no gradient flows through the cosines: the differentiable part is the
+ * term gate (softmax over the dropped query embeddings), ffnn and output.  Stateless: `w` holds the live parameter pointers.
+ * forward: train-mode scores [B,N]; emb_drop (same hash and element order as above: B*Lq query rows, then B*N*Ld document
+ * rows) is applied to the rows the cosines see, exactly as drmm.py:47,57 do; the workspace keeps the dropped rows and the
+ * histograms.  backward: dscores -> gradients accumulated into `grads` (a cair_drmm_weights of gradient buffers; table may
+ * be NULL = fixed embeddings; only query tokens reach the table, through the gate; PAD row untouched). */
+CAIR_API int32_t cair_drmm_train_workspace_bytes(int32_t emsize, int32_t B, int32_t N, int32_t Lq, int32_t Ld, size_t* bytes);
+CAIR_API int32_t cair_drmm_train_forward(const cair_drmm_weights* w, const int64_t* q, const int64_t* d, int32_t B, int32_t N,
+                                int32_t Lq, int32_t Ld, float p_drop, uint64_t seed, float* scores, void* workspace,
+                                size_t workspace_bytes, void* stream);
+CAIR_API int32_t cair_drmm_train_backward(const cair_drmm_weights* w, const cair_drmm_weights* grads, const int64_t* q, int32_t B,
+                                 int32_t N, int32_t Lq, int32_t Ld, float p_drop, uint64_t seed, const float* dscores,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- MNSRF ranking path ---------------------------------------------------
  * Replaces MNSRF.encode + MNSRF.rank_document (neuroir/multitask/mnsrf.py:61-162) as Multitask.predict calls them
  * (neuroir/models/multitask.py:270-276).  Weights are copied into the handle: table = embedder.word_embeddings...weight
