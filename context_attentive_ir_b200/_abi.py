@@ -49,6 +49,11 @@ class MnsrfWeights(C.Structure):
         ('session', LstmDir), ('projection', Linear)]
 
 
+class SessDecWeights(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ('vocab', 'emsize', 'nhid_in', 'nhid_session', 'tgt_vocab')] + [
+        ('table', f32p), ('session', LstmDir), ('dec_rnn', LstmDir), ('generator', Linear)]
+
+
 class DrmmWeights(C.Structure):
     _fields_ = [('vocab', C.c_int32), ('emsize', C.c_int32), ('nbins', C.c_int32), ('table', f32p),
                 ('gating', Linear), ('ffnn0', Linear), ('ffnn1', Linear), ('output', Linear)]
@@ -181,6 +186,18 @@ def pack_mnsrf(cfg, get):
         w.doc_rev = _lstm(get, 'document_encoder.encoder.rnns.0', '_reverse')
     w.session = _lstm(get, 'session_query_encoder.encoder.rnns.0')
     w.projection = _lin(get, 'projection.linear')
+    return w
+
+
+def pack_sessdec(cfg, get, with_session):
+    """Decoder-side weights of MNSRF / M_MATCH_TENSOR (multitask/mnsrf.py:33-57)."""
+    w = SessDecWeights(cfg['src_vocab_size'], cfg['emsize'], cfg['nhid_in'], cfg['nhid_session'], cfg['tgt_vocab_size'])
+    w.table = get('embedder.' + TABLE_KEY)
+    if with_session:
+        w.session = _lstm(get, 'session_query_encoder.encoder.rnns.0')
+    w.dec_rnn = LstmDir(get('decoder.decoder.rnn.weight_ih_l0'), get('decoder.decoder.rnn.weight_hh_l0'),
+                        get('decoder.decoder.rnn.bias_ih_l0'), get('decoder.decoder.rnn.bias_hh_l0'))
+    w.generator = _lin(get, 'generator')
     return w
 
 

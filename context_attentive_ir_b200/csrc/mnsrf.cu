@@ -89,9 +89,91 @@ static void mnsrf_carve(const MnsrfState& st, Arena& ws, int S, int N, int Lq, i
   o->slen = ws.take<int64_t>((size_t)sc);
 }
 
+
+// ---- attention-free suggestion decoder of MNSRF / M_MATCH_TENSOR (mnsrf.py:258-300, mmtensor.py:258-300) ----------
+// decode(): RNNDecoder without attention (decoders/rnn_decoder.py:44-70; the state object is updated in place by every
+// call, decoders/decoder.py:118-155) + generator + arg-max, greedy, from BOS.  Row conventions are the reference's: the
+// initial states are concatenated query-index-major (torch.cat(hidden_states[:-1], dim=1): row i = s*B + b) while the
+// predictions are viewed batch-major ([B, S-1, max_len]: row i = b*(S-1) + s) - reproduced, not fixed.
+__global__ void sd_gather_state_kernel(const float* __restrict__ sess_h, const float* __restrict__ sess_c, int B, int S, int H,
+                                       float* __restrict__ h, float* __restrict__ c) {
+  const int i = blockIdx.x;   // decode row
+  const int s1 = i / B, b1 = i - s1 * B;
+  for (int k = threadIdx.x; k < H; k += blockDim.x) {
+    h[(size_t)i * H + k] = sess_h[((size_t)b1 * S + s1) * H + k];
+    c[(size_t)i * H + k] = sess_c[((size_t)b1 * S + s1) * H + k];
+  }
+}
+__global__ void sd_cell_kernel(const float* __restrict__ gx, const float* __restrict__ gh, int R, int H, float* __restrict__ h,
+                               float* __restrict__ c) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)R * H) return;
+  const int r = (int)(idx / H), u = (int)(idx - (int64_t)r * H);
+  const float* a = gx + (size_t)r * 4 * H;
+  const float* b = gh + (size_t)r * 4 * H;
+  const float ig = sigmoid_f(a[u] + b[u]), fg = sigmoid_f(a[H + u] + b[H + u]);
+  const float gg = tanhf(a[2 * H + u] + b[2 * H + u]), og = sigmoid_f(a[3 * H + u] + b[3 * H + u]);
+  const float cn = fg * c[idx] + ig * gg;
+  c[idx] = cn;
+  h[idx] = og * tanhf(cn);
+}
+// first maximum over the target vocabulary (torch.max), prediction store, next input through the target -> source id map
+__global__ void __launch_bounds__(256) sd_argmax_kernel(const float* __restrict__ logits, int Vt, const int64_t* __restrict__ tgt2src,
+                                                        int64_t* __restrict__ pred, int max_len, int t, int64_t* __restrict__ next) {
+  __shared__ float bv[256];
+  __shared__ int bi[256];
+  const int i = blockIdx.x, tid = threadIdx.x;
+  float best = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int v = tid; v < Vt; v += 256) {
+    const float x = logits[(size_t)i * Vt + v];
+    if (x > best) best = x, arg = v;
+  }
+  bv[tid] = best, bi[tid] = arg;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o && (bv[tid + o] > bv[tid] || (bv[tid + o] == bv[tid] && bi[tid + o] < bi[tid]))) bv[tid] = bv[tid + o], bi[tid] = bi[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const int a = bi[0] == 0x7fffffff ? 0 : bi[0];
+    pred[(size_t)i * max_len + t] = a;
+    next[i] = tgt2src[a];
+  }
+}
+__global__ void sd_fill_kernel(int64_t* p, int n, int64_t v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+struct SessDecState {
+  int device = 0, V = 0, E = 0, Hin = 0, Hs = 0, Vt = 0;
+  bool has_session = false;
+  Owned own;
+  const float* table = nullptr;   // live pointer (the embedder's table)
+  LstmPack sess{};
+  float *w_ih = nullptr, *w_hh = nullptr, *bias = nullptr, *gen_w = nullptr, *gen_b = nullptr;
+  int* d_err = nullptr;
+};
+struct SessDecWs {
+  float *pre_s, *h, *c, *gx, *gh, *logits;
+  int64_t *slen, *tok;
+};
+static void sessdec_carve(const SessDecState& st, Arena& ws, int B, int S, SessDecWs* o) {
+  const size_t R = (size_t)B * (S > 1 ? S - 1 : 1), H = st.Hs;
+  o->pre_s = ws.take<float>(st.has_session ? lstm_workspace_floats(st.sess, B, S) : 0);
+  o->h = ws.take<float>(R * H), o->c = ws.take<float>(R * H), o->gx = ws.take<float>(R * 4 * H), o->gh = ws.take<float>(R * 4 * H);
+  o->logits = ws.take<float>(R * st.Vt);
+  o->slen = ws.take<int64_t>((size_t)B), o->tok = ws.take<int64_t>(R);
+}
+
 }  // namespace cair
 
 using namespace cair;
+
+struct cair_sessdec {
+  SessDecState st;
+};
 
 struct cair_mnsrf {
   MnsrfState st;
@@ -200,6 +282,117 @@ int32_t cair_mnsrf_forward(cair_mnsrf* h, const int64_t* q, const int64_t* qlen,
   if (session_bank) CAIR_CUDA(cudaMemcpyAsync(session_bank + r0 * st.Hs, o.Qs, (size_t)nrows * st.Hs * sizeof(float), cudaMemcpyDeviceToDevice, s));
   if (session_cell && st.rnn == CAIR_RNN_LSTM)
     CAIR_CUDA(cudaMemcpyAsync(session_cell + r0 * st.Hs, o.Qc, (size_t)nrows * st.Hs * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return CAIR_OK;
+}
+
+int32_t cair_sessdec_create(const cair_sessdec_weights* w, int32_t device, cair_sessdec** out) {
+  if (!w || !out || !w->table || !w->dec_rnn.w_ih || !w->dec_rnn.w_hh || !w->dec_rnn.b_ih || !w->dec_rnn.b_hh || !w->generator.w ||
+      !w->generator.b)
+    return fail(CAIR_ERR_BAD_ARG, "sessdec_create: null argument");
+  DevGuard2 g(device);
+  cair_sessdec* h = new cair_sessdec();
+  SessDecState& st = h->st;
+  st.device = device, st.V = w->vocab, st.E = w->emsize, st.Hin = w->nhid_in, st.Hs = w->nhid_session, st.Vt = w->tgt_vocab;
+  st.table = w->table;
+  cudaStream_t s = 0;
+  auto body = [&]() -> int32_t {
+    const int H = st.Hs;
+    if (w->session.w_ih) {
+      CAIR_TRY(lstm_pack(st.own, &w->session, nullptr, st.Hin, H, &st.sess, s, CAIR_RNN_LSTM));
+      st.has_session = true;
+    }
+    CAIR_TRY(dev_copy(st.own, w->dec_rnn.w_ih, (size_t)4 * H * st.E, &st.w_ih, s));
+    CAIR_TRY(dev_copy(st.own, w->dec_rnn.w_hh, (size_t)4 * H * H, &st.w_hh, s));
+    CAIR_CUDA(st.own.alloc(&st.bias, (size_t)4 * H));
+    std::vector<float> bi(4 * H), bh(4 * H);
+    CAIR_CUDA(cudaMemcpy(bi.data(), w->dec_rnn.b_ih, (size_t)4 * H * sizeof(float), cudaMemcpyDeviceToHost));
+    CAIR_CUDA(cudaMemcpy(bh.data(), w->dec_rnn.b_hh, (size_t)4 * H * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4 * H; ++i) bi[i] += bh[i];
+    CAIR_CUDA(cudaMemcpy(st.bias, bi.data(), (size_t)4 * H * sizeof(float), cudaMemcpyHostToDevice));
+    CAIR_TRY(dev_copy(st.own, w->generator.w, (size_t)st.Vt * H, &st.gen_w, s));
+    CAIR_TRY(dev_copy(st.own, w->generator.b, (size_t)st.Vt, &st.gen_b, s));
+    CAIR_CUDA(st.own.alloc(&st.d_err, 1));
+    CAIR_CUDA(cudaMemsetAsync(st.d_err, 0, sizeof(int), s));
+    CAIR_CUDA(cudaStreamSynchronize(s));
+    return CAIR_OK;
+  };
+  const int32_t rc = body();
+  if (rc != CAIR_OK) {
+    st.own.release();
+    delete h;
+    *out = nullptr;
+    return rc;
+  }
+  *out = h;
+  return CAIR_OK;
+}
+
+int32_t cair_sessdec_destroy(cair_sessdec* h) {
+  if (!h) return CAIR_OK;
+  DevGuard2 g(h->st.device);
+  cudaDeviceSynchronize();
+  h->st.own.release();
+  delete h;
+  return CAIR_OK;
+}
+
+int32_t cair_sessdec_workspace_bytes(cair_sessdec* h, int32_t B, int32_t S, size_t* bytes) {
+  if (!h || !bytes || B <= 0 || S <= 0) return fail(CAIR_ERR_BAD_ARG, "sessdec_workspace_bytes: bad argument");
+  Arena a(nullptr, 0);
+  SessDecWs o;
+  sessdec_carve(h->st, a, B, S, &o);
+  *bytes = align_up(a.off) + 256;
+  return CAIR_OK;
+}
+
+int32_t cair_sessdec_states(cair_sessdec* h, const float* pooled, int32_t B, int32_t S, float* sess_h, float* sess_c, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  if (!h || !pooled || !sess_h || !sess_c || !workspace) return fail(CAIR_ERR_BAD_ARG, "sessdec_states: null argument");
+  const SessDecState& st = h->st;
+  if (!st.has_session) return fail(CAIR_ERR_BAD_ARG, "sessdec_states: created without session-encoder weights");
+  DevGuard2 g(st.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena ws(workspace, workspace_bytes);
+  SessDecWs o;
+  sessdec_carve(st, ws, B, S, &o);
+  if (!ws.ok()) return fail(CAIR_ERR_WORKSPACE, "sessdec_states: workspace too small");
+  CAIR_LAUNCH(mnsrf_fill_len_kernel, (B + 255) / 256, 256, 0, s, o.slen, B, (int64_t)S);
+  return lstm_run(st.sess, gemm_dense(pooled, st.Hin), o.slen, B, S, sess_h, nullptr, nullptr, o.pre_s, st.d_err, s, nullptr, sess_c);
+}
+
+int32_t cair_sessdec_decode(cair_sessdec* h, const float* sess_h, const float* sess_c, int32_t B, int32_t S, int32_t max_len,
+                            const int64_t* tgt2src, int64_t bos_id, int64_t* predictions, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  if (!h || !sess_h || !sess_c || !tgt2src || !predictions || !workspace) return fail(CAIR_ERR_BAD_ARG, "sessdec_decode: null argument");
+  if (S < 2 || max_len < 1) return CAIR_OK;
+  const SessDecState& st = h->st;
+  DevGuard2 g(st.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena ws(workspace, workspace_bytes);
+  SessDecWs o;
+  sessdec_carve(st, ws, B, S, &o);
+  if (!ws.ok()) return fail(CAIR_ERR_WORKSPACE, "sessdec_decode: workspace too small");
+  const int R = B * (S - 1), H = st.Hs;
+  CAIR_LAUNCH(sd_gather_state_kernel, (unsigned)R, 128, 0, s, sess_h, sess_c, B, S, H, o.h, o.c);
+  CAIR_LAUNCH(sd_fill_kernel, (R + 255) / 256, 256, 0, s, o.tok, R, bos_id);
+  for (int t = 0; t < max_len; ++t) {
+    CAIR_TRY(gemm_f32(gemm_gather(st.table, st.V, st.E, o.tok, 1, 1, 1, st.d_err), st.w_ih, st.bias, o.gx, 4 * H, R, 4 * H, st.E, ACT_NONE, s));
+    CAIR_TRY(gemm_f32(gemm_dense(o.h, H), st.w_hh, nullptr, o.gh, 4 * H, R, 4 * H, H, ACT_NONE, s));
+    CAIR_LAUNCH(sd_cell_kernel, (unsigned)(((int64_t)R * H + 255) / 256), 256, 0, s, o.gx, o.gh, R, H, o.h, o.c);
+    CAIR_TRY(gemm_f32(gemm_dense(o.h, H), st.gen_w, st.gen_b, o.logits, st.Vt, R, st.Vt, H, ACT_NONE, s));
+    CAIR_LAUNCH(sd_argmax_kernel, (unsigned)R, 256, 0, s, o.logits, st.Vt, tgt2src, predictions, max_len, t, o.tok);
+  }
+  return CAIR_OK;
+}
+
+/* out[n, :] = max_t (x[n, t, :] W^T + b): the max-pooled projected queries M_MATCH_TENSOR.encode feeds its session encoder
+ * (mmtensor.py:86-92); scratch: n*L*C floats */
+int32_t cair_linear_maxpool(const float* x, const float* w, const float* b, int32_t n, int32_t L, int32_t H, int32_t Cc, float* out,
+                            float* scratch, void* stream) {
+  if (!x || !w || !out || !scratch || n <= 0 || L <= 0) return fail(CAIR_ERR_BAD_ARG, "linear_maxpool: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  CAIR_TRY(gemm_f32(gemm_dense(x, H), w, b, scratch, Cc, (int64_t)n * L, Cc, H, ACT_NONE, s));
+  CAIR_LAUNCH(maxpool_time_kernel, (unsigned)n, 128, 0, s, scratch, L, Cc, out);
   return CAIR_OK;
 }
 

@@ -80,6 +80,12 @@ PROTOTYPES = {
     'cair_mnsrf_workspace_bytes': (i32, [vp, i32, i32, i32, i32, i32, C.POINTER(C.c_size_t)]),
     'cair_mnsrf_forward': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, C.c_size_t, vp]),
     'cair_mnsrf_poll_error': (i32, [vp, vp]),
+    'cair_sessdec_create': (i32, [C.POINTER(_abi.SessDecWeights), i32, C.POINTER(vp)]),
+    'cair_sessdec_destroy': (i32, [vp]),
+    'cair_sessdec_workspace_bytes': (i32, [vp, i32, i32, C.POINTER(C.c_size_t)]),
+    'cair_sessdec_states': (i32, [vp, vp, i32, i32, vp, vp, vp, C.c_size_t, vp]),
+    'cair_sessdec_decode': (i32, [vp, vp, vp, i32, i32, i32, vp, i64, vp, vp, C.c_size_t, vp]),
+    'cair_linear_maxpool': (i32, [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]),
     'cair_cars_decode': (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, i64, vp, vp, C.c_size_t, vp]),
 }
 

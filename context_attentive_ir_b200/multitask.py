@@ -217,19 +217,6 @@ class CARS(_CairModule):
         states = _DecoderStates(out['sess_h'], out['sess_c']) if self.has_decoder else None
         return out['scores'], states, (out['sess_q_attn'], out['sess_d_attn'])
 
-    def _tgt2src(self, tgt_dict, src_dict, device):
-        """Target-vocabulary id -> source-vocabulary id of the same word: the per-step tgt_dict[idx] -> src_dict[word]
-        round trip of cars.py:780-783 as one lookup table (cached per dictionary pair)."""
-        key = (id(tgt_dict), id(src_dict), len(tgt_dict), str(device))
-        cache = self.__dict__.get('_tgt2src_cache')
-        if cache is None or cache[0] != key:
-            m = torch.tensor([int(src_dict[tgt_dict[i]]) for i in range(len(tgt_dict))], dtype=torch.int64)
-            if m.numel() < self.args.tgt_vocab_size:   # ids the dictionary does not hold cannot be mapped (the reference raises)
-                m = torch.cat([m, torch.full((self.args.tgt_vocab_size - m.numel(),), 1, dtype=torch.int64)])   # UNK
-            cache = (key, m.to(device))
-            self.__dict__['_tgt2src_cache'] = cache
-        return cache[1]
-
     def decode(self, states, max_len, src_dict, tgt_dict, batch_size, session_len, use_cuda=True, encoded_source=None,
                source_len=None, session_attns=None, **_):
         """Greedy suggestion decode (cars.py:706-791): `session_len` is the number of decoded queries per session (S - 1);
@@ -255,7 +242,7 @@ class CARS(_CairModule):
             ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=dev)
             self.__dict__['_cair_dec_ws'] = ws
         preds = torch.zeros(B, S - 1, max_len, dtype=torch.int64, device=dev)
-        t2s = self._tgt2src(tgt_dict, src_dict, dev)
+        t2s = _tgt2src_table(self, tgt_dict, src_dict, dev, self.args.tgt_vocab_size)
         lib.check(L.cair_cars_decode(h, enc_q.data_ptr(), qlen.data_ptr(), states.sess_h.data_ptr(), states.sess_c.data_ptr(),
                                      sqa.contiguous().data_ptr(), sda.contiguous().data_ptr(), B, S, Lq, max_len, t2s.data_ptr(),
                                      BOS, preds.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
@@ -297,14 +284,64 @@ def ranking_state_dict(reference_state_dict):
     return {k: v for k, v in reference_state_dict.items() if not k.startswith(DECODER_PREFIXES)}
 
 
-_NO_DECODE = ('%s: only the ranking path (encode + rank_document, SURVEY.md section 8f row 4) runs on libcair; the suggestion '
-              'decoder of this model is not built (CARS has one: cair_cars_decode).  Use the click scores, or run decode() of the '
-              'reference module on the carried decoder parameters')
+def _tgt2src_table(module, tgt_dict, src_dict, device, tgt_vocab_size):
+    """Target-vocabulary id -> source-vocabulary id of the same word (the per-step tgt_dict[idx] -> src_dict[word] round trip
+    of the reference decode loops) as one cached lookup table."""
+    key = (id(tgt_dict), id(src_dict), len(tgt_dict), str(device))
+    cache = module.__dict__.get('_tgt2src_cache')
+    if cache is None or cache[0] != key:
+        m = torch.tensor([int(src_dict[tgt_dict[i]]) for i in range(len(tgt_dict))], dtype=torch.int64)
+        if m.numel() < tgt_vocab_size:
+            m = torch.cat([m, torch.full((tgt_vocab_size - m.numel(),), 1, dtype=torch.int64)])   # UNK
+        cache = (key, m.to(device))
+        module.__dict__['_tgt2src_cache'] = cache
+    return cache[1]
 
 
-class MNSRF(_CairModule):
+class _SessionDecoderMixin:
+    """decode() of MNSRF / M_MATCH_TENSOR (mnsrf.py:258-300, mmtensor.py:258-300) on cair_sessdec_*: an attention-free LSTM
+    decoder + generator, greedy from BOS.  The native decoder object follows the parameters like the scoring handle."""
+
+    def _sessdec_for(self, device, nhid_in, with_session):
+        from .rankers import _ptr_getter
+        key = (self._state_key(), device.index)
+        h = self.__dict__.get('_cair_sessdec')
+        if h is not None and self.__dict__.get('_cair_sessdec_key') == key:
+            return h
+        self._release_sessdec()
+        a = self.args
+        keep = []
+        w = _abi.pack_sessdec(dict(src_vocab_size=a.src_vocab_size, emsize=a.emsize, nhid_in=nhid_in, nhid_session=a.nhid_session,
+                                   tgt_vocab_size=a.tgt_vocab_size), _ptr_getter(self, keep), with_session)
+        out = C.c_void_p()
+        torch.cuda.synchronize(device)
+        lib.check(lib.load().cair_sessdec_create(C.byref(w), device.index, C.byref(out)))
+        self.__dict__['_cair_sessdec'], self.__dict__['_cair_sessdec_key'] = out, key
+        return out
+
+    def _release_sessdec(self):
+        h = self.__dict__.get('_cair_sessdec')
+        if h is not None:
+            lib.load().cair_sessdec_destroy(h)
+            self.__dict__['_cair_sessdec'] = None
+
+    def _greedy(self, h, sess_h, sess_c, max_len, src_dict, tgt_dict):
+        dev = sess_h.device
+        B, S = sess_h.shape[0], sess_h.shape[1]
+        L = lib.load()
+        nbytes = C.c_size_t()
+        lib.check(L.cair_sessdec_workspace_bytes(h, B, S, C.byref(nbytes)))
+        ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=dev)
+        preds = torch.zeros(B, max(S - 1, 0), max_len, dtype=torch.int64, device=dev)
+        t2s = _tgt2src_table(self, tgt_dict, src_dict, dev, self.args.tgt_vocab_size)
+        lib.check(L.cair_sessdec_decode(h, sess_h.data_ptr(), sess_c.data_ptr(), B, S, max_len, t2s.data_ptr(), BOS, preds.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+        return {'predictions': preds}
+
+
+class MNSRF(_SessionDecoderMixin, _CairModule):
     """Ranking half of neuroir/multitask/mnsrf.py:10-162 (encode + rank_document); decoder-side parameters (decoder.*,
-    generator.*) are carried as parameters so that reference checkpoints load by key."""
+    generator.*) feed the greedy suggestion decoder (decode(), cair_sessdec_decode)."""
     MODEL = 'mnsrf'
 
     def __init__(self, args):
@@ -339,6 +376,7 @@ class MNSRF(_CairModule):
         if h is not None:
             lib.load().cair_mnsrf_destroy(h)
             self.__dict__['_cair_handle'] = None
+        self._release_sessdec()
 
     def score(self, queries, query_len, docs, doc_len, session_slice=None, want_banks=False):
         """q [B,S,Lq], qlen [B,S], d [B,S,N,Ld], dlen [B,S,N] -> dict(scores [B,S,N] + memory_bank [B,S,Hq], session_bank,
@@ -387,17 +425,25 @@ class MNSRF(_CairModule):
         queries, qlen = self._last
         self._last = None
         out = self.score(queries, qlen, document_rep, document_len, want_banks=True)
-        self._fwd = out
+        self.__dict__['_fwd'] = out
         return out['scores']
 
-    def decode(self, *args, **kw):
-        raise NotImplementedError(_NO_DECODE % 'MNSRF')
+    def decode(self, states, max_len, src_dict, tgt_dict, batch_size, session_len, use_cuda=True, **_):
+        """Greedy suggestion decode (mnsrf.py:258-300) from the session states of the last rank_document();
+        returns {'predictions': LongTensor [batch_size, session_len, max_len]} (session_len = S - 1)."""
+        fwd = self.__dict__.get('_fwd')
+        if fwd is None:
+            raise RuntimeError('decode() must follow rank_document() (models/multitask.py:270-292)')
+        sess_h, sess_c = fwd['session_bank'], fwd['session_cell']
+        assert batch_size == sess_h.shape[0] and session_len == sess_h.shape[1] - 1
+        h = self._sessdec_for(sess_h.device, self.args.nhid_query, with_session=False)
+        return self._greedy(h, sess_h, sess_c, max_len, src_dict, tgt_dict)
 
 
-class M_MATCH_TENSOR(_Ranker):
+class M_MATCH_TENSOR(_SessionDecoderMixin, _Ranker):
     """Ranking half of neuroir/multitask/mmtensor.py:10-189.  rank_document never looks at the session: it is Match-Tensor on
     every (query, candidate) of every session, so it runs on a Match-Tensor handle with B*S queries; the session encoder,
-    decoder and generator are carried as parameters for checkpoint compatibility."""
+    decoder and generator serve decode() (cair_linear_maxpool, cair_sessdec_states, cair_sessdec_decode)."""
     MODEL = 'm_match_tensor'
 
     def __init__(self, args):
@@ -456,10 +502,51 @@ class M_MATCH_TENSOR(_Ranker):
             raise RuntimeError('rank_document() must follow encode() (models/multitask.py:270-276)')
         queries, qlen = self._last
         self._last = None
-        return self.score(queries, qlen, document_rep, document_len)
+        # keep the query memory banks of this forward: decode() derives the session states from them
+        B, S, Lq = queries.shape
+        dev = document_rep.device
+        enc_q = torch.zeros(B * S, Lq, self.args.nhid_query, device=dev)
+        h = self._handle_for(dev)
+        lib.check(lib.load().cair_mt_set_debug(h, enc_q.data_ptr(), None))
+        try:
+            scores = self.score(queries, qlen, document_rep, document_len)
+        finally:
+            lib.check(lib.load().cair_mt_set_debug(h, None, None))
+        self.__dict__['_fwd'] = dict(enc_q=enc_q, B=B, S=S)
+        return scores
 
-    def decode(self, *args, **kw):
-        raise NotImplementedError(_NO_DECODE % 'M_MATCH_TENSOR')
+    def _release(self):
+        super()._release()
+        self._release_sessdec()
+
+    def decode(self, states, max_len, src_dict, tgt_dict, batch_size, session_len, use_cuda=True, **_):
+        """Greedy suggestion decode (mmtensor.py:258-300): the session encoder runs over the max-pooled projected queries of the
+        last rank_document() (mmtensor.py:86-116), its (h, c) after every query start the decoder."""
+        fwd = self.__dict__.get('_fwd')
+        if fwd is None:
+            raise RuntimeError('decode() must follow rank_document() (models/multitask.py:270-292)')
+        enc_q, B, S = fwd['enc_q'], fwd['B'], fwd['S']
+        assert batch_size == B and session_len == S - 1
+        dev = enc_q.device
+        a = self.args
+        L = lib.load()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        Lq = enc_q.shape[1]
+        pooled = torch.empty(B * S, a.nchannels, device=dev)
+        scratch = torch.empty(B * S * Lq * a.nchannels, device=dev)
+        wq, bq = self.query_projection.weight.detach().contiguous(), self.query_projection.bias.detach().contiguous()
+        lib.check(L.cair_linear_maxpool(enc_q.data_ptr(), wq.data_ptr(), bq.data_ptr(), B * S, Lq, a.nhid_query, a.nchannels,
+                                        pooled.data_ptr(), scratch.data_ptr(), stream))
+        h = self._sessdec_for(dev, a.nchannels, with_session=True)
+        nbytes = C.c_size_t()
+        lib.check(L.cair_sessdec_workspace_bytes(h, B, S, C.byref(nbytes)))
+        ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=dev)
+        sess_h = torch.empty(B, S, a.nhid_session, device=dev)
+        sess_c = torch.empty(B, S, a.nhid_session, device=dev)
+        lib.check(L.cair_sessdec_states(h, pooled.data_ptr(), B, S, sess_h.data_ptr(), sess_c.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        stream))
+        self.__dict__['_fwd'].update(session_bank=sess_h, session_cell=sess_c)
+        return self._greedy(h, sess_h, sess_c, max_len, src_dict, tgt_dict)
 
 
 MULTITASK = {'CARS': CARS, 'MNSRF': MNSRF, 'M_MATCH_TENSOR': M_MATCH_TENSOR}

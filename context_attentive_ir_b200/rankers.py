@@ -99,7 +99,7 @@ def _named_tensors(module, prefix=''):
             yield from _named_tensors(child, prefix + name + '.')
 
 
-_HANDLE_KEYS = ('_cair_handle', '_cair_key', '_cair_ws', '_cair_trainer', '_cair_trainer_key')
+_HANDLE_KEYS = ('_cair_handle', '_cair_key', '_cair_ws', '_cair_trainer', '_cair_trainer_key', '_cair_sessdec', '_cair_sessdec_key', '_fwd')
 
 
 def _ptr_getter(module, keep):

@@ -489,6 +489,32 @@ CAIR_API int32_t cair_mnsrf_forward(cair_mnsrf* h, const int64_t* q, const int64
                            size_t workspace_bytes, void* stream);
 CAIR_API int32_t cair_mnsrf_poll_error(cair_mnsrf* h, void* stream);
 
+/* Suggestion decoder of MNSRF / M_MATCH_TENSOR (multitask/mnsrf.py:258-300, mmtensor.py:258-300; called by
+ * Multitask.predict, models/multitask.py:281-292): RNNDecoder without attention + generator, greedy from BOS.
+ * table = the embedder's table [V,E] (LIVE pointer, not copied); session = session_query_encoder.encoder.rnns.0.* or all
+ * NULL when the states come from cair_mnsrf_forward; dec_rnn = decoder.decoder.rnn.* ([4Hs,E], [4Hs,Hs]); generator [Vt,Hs]+b.
+ * cair_sessdec_states: session LSTM over pooled [B,S,nhid_in] -> sess_h, sess_c [B,S,Hs] (M_MATCH_TENSOR.encode, :94-116).
+ * cair_sessdec_decode: sess_h / sess_c [B,S,Hs] -> predictions [B,S-1,max_len] int64 (target ids); tgt2src [Vt] int64 as in
+ * cair_cars_decode.  The reference's row orderings are reproduced (initial states query-index-major, predictions
+ * batch-major).  cair_linear_maxpool: out[n,:] = max_t(x[n,t,:] W^T + b) (mmtensor.py:86-92), scratch n*L*C floats. */
+typedef struct {
+  int32_t vocab, emsize, nhid_in, nhid_session, tgt_vocab;
+  const float* table;
+  cair_lstm_dir session, dec_rnn;
+  cair_linear generator;
+} cair_sessdec_weights;
+typedef struct cair_sessdec cair_sessdec;
+CAIR_API int32_t cair_sessdec_create(const cair_sessdec_weights* w, int32_t device, cair_sessdec** out);
+CAIR_API int32_t cair_sessdec_destroy(cair_sessdec* h);
+CAIR_API int32_t cair_sessdec_workspace_bytes(cair_sessdec* h, int32_t B, int32_t S, size_t* bytes);
+CAIR_API int32_t cair_sessdec_states(cair_sessdec* h, const float* pooled, int32_t B, int32_t S, float* sess_h, float* sess_c,
+                            void* workspace, size_t workspace_bytes, void* stream);
+CAIR_API int32_t cair_sessdec_decode(cair_sessdec* h, const float* sess_h, const float* sess_c, int32_t B, int32_t S,
+                            int32_t max_len, const int64_t* tgt2src, int64_t bos_id, int64_t* predictions, void* workspace,
+                            size_t workspace_bytes, void* stream);
+CAIR_API int32_t cair_linear_maxpool(const float* x, const float* w, const float* b, int32_t n, int32_t L, int32_t H, int32_t C,
+                            float* out, float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -388,13 +388,21 @@ def gen_session_ranker(name, which, seed, B, S, N, Lq, Ld, E, V, Hq, Hd, Hs, rnn
                     for j in rng.choice(L, size=max(1, L // 8), replace=False):
                         d[b, s_, n, j] = q[b, s_, rng.integers(0, int(batch['qlen'][b, s_]))]
     t = _t(batch)
+    # dictionaries of the decode loop (mnsrf.py:291-294: tgt_dict[idx] -> word -> src_dict[word]), as in gen_cars
+    rng = np.random.RandomState(seed)
+    tgt2src = rng.randint(4, V, size=cfg['tgt_vocab_size']).astype(np.int64)
+    tgt2src[:4] = np.arange(4)
+    tgt_dict = ['w%d' % i for i in range(cfg['tgt_vocab_size'])]
+    src_dict = {'w%d' % i: int(tgt2src[i]) for i in range(cfg['tgt_vocab_size'])}
     with torch.no_grad():
         memory_bank, session_bank, states = net.encode(t['q'], t['qlen'])
         scores = net.rank_document(t['q'], memory_bank, session_bank, t['d'], t['dlen'])
-    outs = dict(scores=scores, session_bank=session_bank)
+        dec = net.decode(states=states, max_len=6, src_dict=src_dict, tgt_dict=tgt_dict, batch_size=B, session_len=S - 1,
+                         use_cuda=False)
+    outs = dict(scores=scores, session_bank=session_bank, predictions=dec['predictions'])
     if which == 'mnsrf':
         outs['memory_bank'] = memory_bank
-    _save(name, cfg, batch, net, outs)
+    _save(name, cfg, dict(batch, tgt2src=tgt2src), net, outs)
 
 
 # ------------------------------------------------------------------ ranking metrics (eval/ltorank.py)

@@ -17,6 +17,29 @@ DEV = 'cuda:0'
 TOL = 1e-3
 
 
+class _TgtDict:
+    """tgt_dict[i] -> word (the reference's Vocabulary indexing)."""
+
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return 'w%d' % i
+
+
+class _SrcDict:
+    """src_dict[word] -> id, from the fixture's target -> source map."""
+
+    def __init__(self, tgt2src):
+        self.m = {'w%d' % i: int(v) for i, v in enumerate(tgt2src)}
+
+    def __getitem__(self, w):
+        return self.m[w]
+
+
 def _rel(a, ref):
     return float(ol.rel_err(np.asarray(a), np.asarray(ref)).max())
 
@@ -55,8 +78,10 @@ def test_mnsrf_golden(name):
         mb, sb, states = net.encode(q, ql)
         s2 = net.rank_document(q, mb, sb, d, dl)
     assert torch.equal(s2, out['scores'])
-    with pytest.raises(NotImplementedError):
-        net.decode(states=states)
+    with torch.no_grad():
+        dec = net.decode(states=states, max_len=6, src_dict=_SrcDict(ins['tgt2src']), tgt_dict=_TgtDict(len(ins['tgt2src'])),
+                         batch_size=B, session_len=q.shape[1] - 1, use_cuda=True)
+    assert np.array_equal(dec['predictions'].cpu().numpy(), outs['predictions'])     # greedy tokens identical to the reference
 
 
 @pytest.mark.gpu
@@ -86,6 +111,11 @@ def test_m_match_tensor_golden(name, impl):
     net.poll_error()
     assert s.shape == outs['scores'].shape
     assert _rel(s.cpu().numpy(), outs['scores']) < TOL
+    with torch.no_grad():
+        dec = net.decode(states=states, max_len=6, src_dict=_SrcDict(ins['tgt2src']), tgt_dict=_TgtDict(len(ins['tgt2src'])),
+                         batch_size=q.shape[0], session_len=q.shape[1] - 1, use_cuda=True)
+    assert np.abs(net._fwd['session_bank'].cpu().numpy() - outs['session_bank']).max() < 5e-4
+    assert np.array_equal(dec['predictions'].cpu().numpy(), outs['predictions'])
     # the same numbers as the stand-alone Match-Tensor oracle on the flattened (session, query) rows
     B, S, Lq = ins['q'].shape
     N, Ld = ins['d'].shape[2], ins['d'].shape[3]
