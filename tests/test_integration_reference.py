@@ -108,6 +108,35 @@ def test_reference_multitask_wrapper_builds_b200_cars_and_keeps_decoder_keys(tmp
     importlib.reload(ref_mt)
 
 
+@pytest.mark.parametrize('name, ref_cls', [('mnsrf_tiny', 'MNSRF'), ('mmt_tiny', 'M_MATCH_TENSOR')])
+def test_reference_multitask_wrapper_builds_b200_mnsrf_and_mmt(name, ref_cls):
+    """MNSRF / M_MATCH_TENSOR under the reference's Multitask wrapper (models/multitask.py:41-58): after install() the wrapper
+    constructs the B200 mirrors, and the stock network's full state_dict loads strictly and comes back unchanged."""
+    _import_reference()
+    import importlib
+    import neuroir.models.multitask as ref_mt
+    ref_mt = importlib.reload(ref_mt)
+    cfg, ins, sd, outs = ol.load_golden(name)
+    args = _args(cfg)
+    src = _Dict((i, i) for i in range(cfg['src_vocab_size']))
+    tgt = _Dict((i, i) for i in range(cfg['tgt_vocab_size']))
+    stock = ref_mt.Multitask(argparse.Namespace(**vars(args)), src, tgt, {k: torch.from_numpy(v) for k, v in sd.items()})
+    assert type(stock.network).__name__ == ref_cls and type(stock.network).__module__.startswith('neuroir.')
+    full = stock.network.state_dict()
+    import context_attentive_ir_b200.integration as integ
+    from context_attentive_ir_b200 import multitask
+    assert 'neuroir.models.multitask.' + ref_cls in integ.install()
+    mine = ref_mt.Multitask(argparse.Namespace(**vars(args)), src, tgt, dict(full))
+    assert isinstance(mine.network, getattr(multitask, ref_cls))
+    got = mine.network.state_dict()
+    assert sorted(got) == sorted(full)
+    for k in full:
+        assert torch.equal(got[k], full[k]), k
+    for fn in ('encode', 'rank_document', 'decode'):     # the three calls of Multitask.predict (models/multitask.py:270-292)
+        assert callable(getattr(mine.network, fn))
+    importlib.reload(ref_mt)
+
+
 def test_two_layer_encoder_is_rejected_through_the_reference_config_path():
     """`--nlayers 2` travels through the unmodified neuroir.config (add_model_args -> get_model_args) into Ranker.__init__;
     the B200 Match-Tensor implements single-layer encoders (the reference's hyparam dicts fix nlayers = 1,
