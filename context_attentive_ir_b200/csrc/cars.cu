@@ -68,6 +68,7 @@ int32_t cars_create_state(Owned& own, const cair_cars_weights& w, CarsState* st,
   for (int i = 0; i < 3; ++i) {
     CAIR_TRY(dev_copy(own, w.ranknet[i].w, (size_t)st->rd[i] * 2 * in, &st->rk_w[i], s));
     CAIR_TRY(dev_copy(own, w.ranknet[i].b, (size_t)st->rd[i] * 2, &st->rk_b[i], s));
+    if (i < 2 && in % 4 == 0) CAIR_TRY(gemm_tc_pack(own, st->rk_w[i], st->rd[i] * 2, in, &st->rk_tc[i], s));
     in = st->rd[i];
   }
   return CAIR_OK;
@@ -223,7 +224,8 @@ __device__ void softmax_small(float* att, int ns) {
 __global__ void __launch_bounds__(256) cars_rank_kernel(CarsState st, const float* __restrict__ pq,
                                                         const float* __restrict__ pd, const float* __restrict__ Qs,
                                                         const float* __restrict__ Ds, int S, int N,
-                                                        int64_t row_begin, float* __restrict__ scores) {
+                                                        int64_t row_begin, float* __restrict__ scores,
+                                                        float* __restrict__ feat_out) {
   extern __shared__ float smr[];
   const int Hq = st.Hq, Hd = st.Hd, Hsq = st.Hsq, Hsd = st.Hsd, Hs = Hsq + Hsd;
   const int Hmax = max(max(Hsq, Hsd), Hd);  // u doubles as the session-projection scratch
@@ -294,6 +296,11 @@ __global__ void __launch_bounds__(256) cars_rank_kernel(CarsState st, const floa
     f[o] = qv, f[Hd + o] = dv, f[2 * Hd + o] = fabsf(qv - dv), f[3 * Hd + o] = qv * dv;
   }
   __syncthreads();
+  if (feat_out) {   // the Maxout layers run as GEMMs over all B*S*N candidate rows (cars_forward)
+    float* fo = feat_out + (size_t)rl * N * 4 * Hd;
+    for (int i = tid; i < N * 4 * Hd; i += 256) fo[i] = feat[i];
+    return;
+  }
   // Maxout layers: out[o] = max(row 2o, row 2o+1); each warp owns output o for all N docs
   const float* xin = feat;
   float* yout = y0;
@@ -340,6 +347,29 @@ __global__ void __launch_bounds__(256) cars_rank_kernel(CarsState st, const floa
     in = out;
     yout = y1;
   }
+}
+
+// Maxout pooling between the rank-net GEMMs (modules/maxout.py:70-84): x[r, o] = max(y[r, 2o], y[r, 2o+1])
+__global__ void maxout_pool_kernel(const float* __restrict__ y, int64_t rows, int out, float* __restrict__ x) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * out) return;
+  const float2 v = *reinterpret_cast<const float2*>(y + 2 * i);
+  x[i] = fmaxf(v.x, v.y);
+}
+// last Maxout layer (1 output, pool 2): score[r] = max(w0 . x + b0, w1 . x + b1); one warp per row
+__global__ void maxout_final_kernel(const float* __restrict__ x, int64_t rows, int in, const float* __restrict__ w,
+                                    const float* __restrict__ b, float* __restrict__ scores) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float a0 = 0.f, a1 = 0.f;
+  for (int k = lane; k < in; k += 32) {
+    const float xv = x[r * in + k];
+    a0 = fmaf(w[k], xv, a0);
+    a1 = fmaf(w[in + k], xv, a1);
+  }
+  a0 = warp_sum(a0), a1 = warp_sum(a1);
+  if (lane == 0) scores[r] = fmaxf(a0 + b[0], a1 + b[1]);
 }
 
 // inner attention over the session states 1..s+1 (cars.py:385-389, :407-411): one CTA per (b,s)
@@ -419,6 +449,11 @@ int32_t cars_forward(const CarsState& st, const CarsIO& io, int B, int S, int N,
   const int Hsmax = Hsq > Hsd ? Hsq : Hsd;
   float* hid_s = ws.take<float>((size_t)nrows * Hsmax);
   float* sc_s = ws.take<float>((size_t)nrows);
+  // rank head as GEMMs over the candidate rows
+  float* rk_feat = ws.take<float>((size_t)ndocs * 4 * Hd);
+  float* rk_y = ws.take<float>((size_t)ndocs * 2 * (st.rd[0] > st.rd[1] ? st.rd[0] : st.rd[1]));
+  float* rk_x0 = ws.take<float>((size_t)ndocs * st.rd[0]);
+  float* rk_x1 = ws.take<float>((size_t)ndocs * st.rd[1]);
   if (dry || sc <= 0) return CAIR_OK;
   if (!ws.ok()) return fail(CAIR_ERR_WORKSPACE, "cars: workspace too small");
 
@@ -451,7 +486,19 @@ int32_t cars_forward(const CarsState& st, const CarsIO& io, int B, int S, int N,
     if (smem > 220 * 1024) return fail(CAIR_ERR_UNSUPPORTED, "cars: N=%d x Hd=%d does not fit the rank kernel", N, Hd);
     CAIR_CUDA(cudaFuncSetAttribute(cars_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CarsState stc = st;
-    CAIR_LAUNCH(cars_rank_kernel, (unsigned)nrows, 256, smem, s, stc, pq, pd, Qs, Ds, S, N, r0, io.scores);
+    const bool as_gemm = st.rk_tc[0].img && st.rk_tc[1].img && ndocs >= 128;
+    CAIR_LAUNCH(cars_rank_kernel, (unsigned)nrows, 256, smem, s, stc, pq, pd, Qs, Ds, S, N, r0, io.scores,
+                as_gemm ? rk_feat : (float*)nullptr);
+    if (as_gemm) {
+      // Maxout(4Hd -> rd0 -> rd1 -> 1, pool 2): two tensor-core GEMMs over all B*S*N rows instead of every (b,s) CTA
+      // streaming the 2 MB of layer-0 weights from L2
+      const int o0 = st.rd[0], o1 = st.rd[1];
+      CAIR_TRY(gemm_auto(gemm_dense(rk_feat, 4 * Hd), st.rk_w[0], st.rk_tc[0], st.rk_b[0], rk_y, 2 * o0, ndocs, 2 * o0, 4 * Hd, ACT_NONE, s));
+      CAIR_LAUNCH(maxout_pool_kernel, (unsigned)((ndocs * o0 + 255) / 256), 256, 0, s, rk_y, ndocs, o0, rk_x0);
+      CAIR_TRY(gemm_auto(gemm_dense(rk_x0, o0), st.rk_w[1], st.rk_tc[1], st.rk_b[1], rk_y, 2 * o1, ndocs, 2 * o1, o0, ACT_NONE, s));
+      CAIR_LAUNCH(maxout_pool_kernel, (unsigned)((ndocs * o1 + 255) / 256), 256, 0, s, rk_y, ndocs, o1, rk_x1);
+      CAIR_LAUNCH(maxout_final_kernel, (unsigned)((ndocs + 7) / 8), 256, 0, s, rk_x1, ndocs, o1, st.rk_w[2], st.rk_b[2], io.scores + r0 * N);
+    }
   }
   // decoder-side outputs: query memory banks, session-encoder states after every query
   if (io.enc_q)

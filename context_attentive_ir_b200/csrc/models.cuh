@@ -198,6 +198,7 @@ struct CarsState {
   float *qp_w = nullptr, *qp_b = nullptr;  // q_projection
   float* sess_proj = nullptr;              // shared_session_projector + private_session_projector1 [Hd, Hsq+Hsd]
   float *rk_w[3] = {nullptr, nullptr, nullptr}, *rk_b[3] = {nullptr, nullptr, nullptr};
+  GemmTcW rk_tc[2];                        // tensor-core images of the first two Maxout layers (rows = B*S*N candidates)
   float* shared_proj = nullptr;            // shared_session_projector alone (the decoder adds private_session_projector2 to it)
   CarsDecoder dec;
 };
