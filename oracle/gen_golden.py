@@ -325,7 +325,7 @@ def gen_duet(name, seed, B, N, Lq, Ld, E, V, nf, pool=5, **kw):
 
 
 # ------------------------------------------------------------------ CARS (ranking path)
-def gen_cars(name, seed, B, S, N, Lq, Ld, E, V, Hq, Hd, Hs, max_clicks=1, metrics=False, **kw):
+def gen_cars(name, seed, B, S, N, Lq, Ld, E, V, Hq, Hd, Hs, max_clicks=1, metrics=False, zero_click=None, **kw):
     from neuroir.multitask.cars import CARS
     torch.manual_seed(1013)
     cfg = dict(model='cars', emsize=E, src_vocab_size=V, tgt_vocab_size=50, dropout_emb=0.2, dropout=0.2,
@@ -337,6 +337,8 @@ def gen_cars(name, seed, B, S, N, Lq, Ld, E, V, Hq, Hd, Hs, max_clicks=1, metric
                turn_recommender_off=False)
     net = CARS(_ns(**{k: v for k, v in cfg.items() if k != 'model'})).eval()
     batch = synth.session_batch(seed, B, S, N, Lq, Ld, V, max_clicks=max_clicks, **kw)
+    if zero_click is not None:   # a query nobody clicked on: its click vector is built from masked attention only (cars.py:285-304)
+        batch['label'][zero_click[0], zero_click[1], :] = 0.0
     t = _t(batch)
     # dictionaries of the decode loop (cars.py:774-783: tgt_dict[idx] -> word -> src_dict[word]); the target word i maps
     # to an arbitrary fixed source id
@@ -545,6 +547,7 @@ def main():
                        featsize=40, nchannels=50, nfilters=6, match_filter_size=20)
     # CARS ranking path
     gen_cars('cars_tiny', 51, B=2, S=3, N=4, Lq=6, Ld=17, E=24, V=150, Hq=16, Hd=16, Hs=24, max_clicks=1)
+    gen_cars('cars_zeroclick', 61, B=3, S=4, N=5, Lq=6, Ld=17, E=24, V=150, Hq=16, Hd=16, Hs=24, max_clicks=3, zero_click=(1, 1))
     gen_cars('cars_clicks', 52, B=3, S=4, N=5, Lq=8, Ld=30, E=32, V=200, Hq=32, Hd=32, Hs=48, max_clicks=3)
     gen_cars('cars_mid', 1238, B=2, S=7, N=10, Lq=20, Ld=200, E=300, V=400, Hq=64, Hd=64, Hs=96,
              max_clicks=2)

@@ -78,7 +78,7 @@ def test_duet_rejects_unpadded_shapes():
         ol.run_ranker(cfg, sd, ins['q'][:, :-1], ins['qlen'], ins['d'], ins['dlen'])
 
 
-@pytest.mark.parametrize('name', ['cars_tiny', 'cars_clicks', 'cars_mid', 'cars_h256'])
+@pytest.mark.parametrize('name', ['cars_tiny', 'cars_clicks', 'cars_zeroclick', 'cars_mid', 'cars_h256'])
 def test_cars(name):
     cfg, ins, sd, outs = ol.load_golden(name)
     o = ol.run_cars(cfg, sd, ins['q'], ins['qlen'], ins['d'], ins['dlen'], ins['label'])

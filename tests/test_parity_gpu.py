@@ -221,7 +221,7 @@ def test_duet_rejects_unpadded_batches():
         net(q[:, :-1], ql, d, dl)
 
 
-@pytest.mark.parametrize('name', ['cars_tiny', 'cars_clicks', 'cars_mid', 'cars_h256'])
+@pytest.mark.parametrize('name', ['cars_tiny', 'cars_clicks', 'cars_zeroclick', 'cars_mid', 'cars_h256'])
 def test_cars_golden(name, gemm_engine):
     cfg, ins, sd, outs = ol.load_golden(name)
     net = helpers.build_module(cfg, sd, DEV)
@@ -243,7 +243,7 @@ class _TgtDict(list):
     """tgt_dict[idx] -> word (neuroir Vocabulary indexing by int)."""
 
 
-@pytest.mark.parametrize('name', ['cars_tiny', 'cars_clicks', 'cars_mid', 'cars_h256'])
+@pytest.mark.parametrize('name', ['cars_tiny', 'cars_clicks', 'cars_zeroclick', 'cars_mid', 'cars_h256'])
 def test_cars_predict_sequence_matches_reference_decode(name):
     """The body of the reference's Multitask.predict (neuroir/models/multitask.py:264-292) on the B200 module: encode ->
     rank_document -> softmax -> decode(states=..., encoded_source=..., session_attns=...).  click scores within 1e-3 of
