@@ -244,7 +244,21 @@ __global__ void __launch_bounds__(256) lstm_train_fwd_kernel(float* __restrict__
         const int l = slen[s];
         acc[s] = step < l ? gates[((size_t)(s0 + s) * L + (dir ? l - 1 - step : step)) * PG + dir * G + r] : 0.f;
       }
-      for (int k = 0; k < h; ++k) {
+      int k = 0;
+#pragma unroll 2
+      for (; k + 4 <= h; k += 4) {   // four weights + one 128-bit state load per sequence per 4 k: 12 loads per 32 FMAs
+        const float w0 = W[(size_t)(k + 0) * G + r], w1 = W[(size_t)(k + 1) * G + r];
+        const float w2 = W[(size_t)(k + 2) * G + r], w3 = W[(size_t)(k + 3) * G + r];
+#pragma unroll
+        for (int s = 0; s < TS; ++s) {
+          const float4 hv = *reinterpret_cast<const float4*>(&hprev[s * hp + k]);
+          acc[s] = fmaf(w0, hv.x, acc[s]);
+          acc[s] = fmaf(w1, hv.y, acc[s]);
+          acc[s] = fmaf(w2, hv.z, acc[s]);
+          acc[s] = fmaf(w3, hv.w, acc[s]);
+        }
+      }
+      for (; k < h; ++k) {
         const float w0 = W[(size_t)k * G + r];
 #pragma unroll
         for (int s = 0; s < TS; ++s) acc[s] = fmaf(w0, hprev[s * hp + k], acc[s]);
