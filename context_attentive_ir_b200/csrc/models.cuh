@@ -54,6 +54,9 @@ struct MtEpiConst {
   float bias[24];           // merged conv bias
   float w1t[24][MT_TC_MAXM]; // 1x1 conv, transposed: [f][m] (m contiguous: one 128-bit constant load = 4 output channels)
   float b1[MT_TC_MAXM];
+  // PAD x PAD exact matches (PAD == PAD counts, mtensor.py:156): prefix sums over the document taps, already summed over the
+  // query taps of a PAD run: padtab[qz][k][f] = sum_{a in qz} sum_{bt < k} wem[a*7+bt][f] (qz = bit mask of the PAD query taps)
+  float padtab[8][8][24];
 };
 int32_t mt_pack(Owned& own, const cair_mt_weights& w, MtPack* p, cudaStream_t s);
 size_t mt_t_floats(const MtPack& p, int64_t nq, int Lq);

@@ -24,6 +24,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cstdlib>
+
 #include "models.cuh"
 #include "umma.cuh"
 
@@ -72,9 +74,10 @@ __host__ __device__ inline uint32_t tc_stage_bytes(const TcK& k) {
 }
 __host__ __device__ inline uint32_t tc_timg_per_tile(const TcK& k) { return 7u * tc_slab_main(k) + tc_slab_tail(k); }
 static inline size_t tc_a_bytes(const TcK& k) { return (size_t)2 * k.KA * TC_MAXRA * 16; }
+constexpr int TC_PADTAB = 8 * 8 * 24;   // floats of MtEpiConst::padtab, copied to shared memory by the kernel
 static inline size_t tc_misc_bytes(const MtPack& p, int Lq) {
   (void)p;
-  return (size_t)(MT_TC_MAXM * TC_EPI_WARPS + 24 * MT_TC_MAXM) * sizeof(float) + (size_t)(TC_MAXRA + 8 + Lq) * sizeof(int);
+  return (size_t)(MT_TC_MAXM * TC_EPI_WARPS + 24 * MT_TC_MAXM + TC_PADTAB) * sizeof(float) + (size_t)(TC_MAXRA + 8 + Lq) * sizeof(int);
 }
 static inline int tc_stages(const MtPack& p, int Lq) {
   const TcK k = tc_k(p.C);
@@ -466,29 +469,51 @@ __device__ __forceinline__ void tmem_ld_fp(uint32_t taddr, float* v) {
 // y[f] = relu(conv accumulator + bias + exact-match taps) of (query position i, this thread's document row)
 // exact-match channel: alpha * W7[f, C, a, bt] wherever q[i+a-1] == d[j+bt-3] (PAD==PAD counts); dj = dids + jrow
 template <int FP>
-__device__ __forceinline__ void mt_epi_prep(float* y, int i, int Lq, const int* dj, const int* qids, const MtEpiConst& ec) {
+__device__ __forceinline__ void mt_epi_prep(float* y, int i, int Lq, const int* dj, const int* qids, const MtEpiConst& ec,
+                                            const float* padtab) {
 #pragma unroll
   for (int f = 0; f < FP; ++f) y[f] += ec.bias[f];
-  // Matches are rare (a few cells per pair): test all 21 (a, bt) taps branch-free first (one predicate-accumulating
-  // compare each) and enter the tap loop only on a hit.  Out-of-range query positions are -2, out-of-range document
-  // positions -1: they never match.
+  // Out-of-range query positions are -2, out-of-range document positions -1: they never match.
   int qv[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     const int ii = i + a - 1;
     qv[a] = (ii >= 0 && ii < Lq) ? qids[ii] : -2;
   }
-  bool hit = false;
+  // PAD == PAD counts as a match (mtensor.py:156), and on real data most of the [Lq, Ld] plane is PAD x PAD (documents
+  // average 63 of 200 positions, queries 4 of 20).  Those matches are separable - tap (a, bt) matches iff query tap a
+  // AND document tap bt are PAD - and the PAD taps of a row are a contiguous run [lo, hi), so their contribution is a
+  // difference of two pre-summed table rows: 2 x FP shared-memory loads for ANY pad pattern, the rows at the border of the
+  // padding included (with a tap loop those rows made every (i, warp) unit of a padded pair take 21 x FP predicated adds).
+  // Real-token matches (a few cells per pair) keep the tap loop.
+  int zm = 0, qz = 0;
+  bool real = false;
 #pragma unroll
-  for (int a = 0; a < 3; ++a)
+  for (int bt = 0; bt < 7; ++bt) zm |= (dj[bt] == 0 ? 1 : 0) << bt;
 #pragma unroll
-    for (int bt = 0; bt < 7; ++bt) hit |= dj[bt] == qv[a];
-  if (hit) {
+  for (int a = 0; a < 3; ++a) {
+    qz |= (qv[a] == 0 ? 1 : 0) << a;
+#pragma unroll
+    for (int bt = 0; bt < 7; ++bt) real |= qv[a] > 0 && dj[bt] == qv[a];
+  }
+  bool padgen = false;
+  if (zm != 0 && qz != 0) {
+    const int lo = __ffs(zm) - 1, hi = 32 - __clz(zm);
+    if ((zm >> lo) == (1 << (hi - lo)) - 1 && qz != 5) {
+      const float* th = padtab + (qz * 8 + hi) * 24;
+      const float* tl = padtab + (qz * 8 + lo) * 24;
+#pragma unroll
+      for (int f = 0; f < FP; ++f) y[f] += th[f] - tl[f];
+    } else {
+      padgen = true;   // PAD tokens inside a sequence (not produced by batchify): the general tap loop handles them
+    }
+  }
+  if (real || padgen) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
 #pragma unroll
       for (int bt = 0; bt < 7; ++bt) {
-        if (dj[bt] == qv[a]) {
+        if (dj[bt] == qv[a] && (qv[a] > 0 || padgen)) {
 #pragma unroll
           for (int f = 0; f < FP; ++f) y[f] += ec.wem[a * 7 + bt][f];
         }
@@ -516,7 +541,7 @@ __device__ __forceinline__ void mt_epi_unit(uint32_t tacc, int i0, int Lq, bool 
 #pragma unroll
   for (int bt = 0; bt < 7; ++bt) dj[bt] = djp[bt];
 #pragma unroll
-  for (int n = 0; n < NI; ++n) mt_epi_prep<FP>(y[n], i0 + n, Lq, dj, qids, ec);
+  for (int n = 0; n < NI; ++n) mt_epi_prep<FP>(y[n], i0 + n, Lq, dj, qids, ec, w1t + 24 * MT_TC_MAXM);
   float2 zz[NI][10];
 #pragma unroll
   for (int n = 0; n < NI; ++n)
@@ -557,7 +582,7 @@ __device__ __forceinline__ void mt_epi_unit_wide(uint32_t tacc, int i, int Lq, b
   int dj[7];
 #pragma unroll
   for (int bt = 0; bt < 7; ++bt) dj[bt] = djp[bt];
-  mt_epi_prep<FP>(y, i, Lq, dj, qids, ec);
+  mt_epi_prep<FP>(y, i, Lq, dj, qids, ec, w1t + 24 * MT_TC_MAXM);
   float z[MT_TC_MAXM];
 #pragma unroll
   for (int m = 0; m < MT_TC_MAXM; ++m) z[m] = ec.b1[m];
@@ -603,7 +628,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   // FFMA takes them as immediate c[][] operands, no shared-memory loads in the hot loop
   float* red = reinterpret_cast<float*>(b_ring + (size_t)nstages * stage);  // [8 warps][32]
   float* w1t = red + MT_TC_MAXM * TC_EPI_WARPS;               // [24][32] 1x1 conv weights, transposed (m contiguous)
-  int* dids = reinterpret_cast<int*>(w1t + 24 * MT_TC_MAXM);
+  float* padtab = w1t + 24 * MT_TC_MAXM;                      // [8][8][24] PAD x PAD exact-match sums (mt_epi_prep)
+  int* dids = reinterpret_cast<int*>(padtab + TC_PADTAB);
   int* qids = dids + TC_MAXRA + 8;
 
   if (warp == 0) tmem_alloc(&tmem_slot, TC_TCOLS);
@@ -621,6 +647,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     fence_mbar_init();
   }
   for (int i = tid; i < 24 * MT_TC_MAXM; i += TC_THREADS) w1t[i] = ec.w1t[i / MT_TC_MAXM][i % MT_TC_MAXM];
+  for (int i = tid; i < TC_PADTAB; i += TC_THREADS) padtab[i] = ec.padtab[i / 192][(i / 24) % 8][i % 24];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -844,7 +871,18 @@ int32_t mt_epi_const(const MtPack& p, MtEpiConst* out, cudaStream_t s) {
   CAIR_CUDA(cudaMemcpyAsync(b1.data(), p.b1, b1.size() * 4, cudaMemcpyDeviceToHost, s));
   CAIR_CUDA(cudaStreamSynchronize(s));
   for (int t = 0; t < 21; ++t)
-    for (int f = 0; f < p.FPP; ++f) out->wem[t][f] = wem[(size_t)t * p.FPP + f];
+    for (int f = 0; f < p.FPP; ++f) {
+      out->wem[t][f] = wem[(size_t)t * p.FPP + f];
+    }
+  for (int qz = 1; qz < 8; ++qz)
+    for (int k = 1; k < 8; ++k)
+      for (int f = 0; f < p.FPP; ++f) {
+        float acc = 0.f;
+        for (int a = 0; a < 3; ++a)
+          if ((qz >> a) & 1)
+            for (int bt = 0; bt < k; ++bt) acc += wem[(size_t)(a * 7 + bt) * p.FPP + f];
+        out->padtab[qz][k][f] = acc;
+      }
   for (int f = 0; f < p.FPP; ++f) out->bias[f] = bias[f];
   for (int m = 0; m < p.M; ++m) {
     out->b1[m] = b1[m];

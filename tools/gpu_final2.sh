@@ -8,17 +8,17 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/b
 # launch list of two headline steps (cold-cache, serialised: compare SHARES with the live stage split)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_final_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-other-configs > gpurun_out/ncu_launches.log 2>&1
 # every kernel of the headline step
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"lstm_tc_kernel|mt_tc_interact_kernel|mt_tc_proj_image_kernel|mt_tc_build_t_kernel|gemm_f32_kernel" -s 12 -c 6 -o gpurun_out/prof_r02f_cfg2 -f python tools/one_batch.py > gpurun_out/ncu_cfg2.log 2>&1
-ncu -i gpurun_out/prof_r02f_cfg2.ncu-rep --page raw --csv > gpurun_out/r02_final_cfg2_step_ncu_raw.csv 2>/dev/null
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"lstm_tc_kernel|mt_tc_interact_kernel|mt_tc_proj_image_kernel|mt_tc_build_t_kernel|gemm_f32_kernel" -s 12 -c 6 -o /tmp/prof_r02f_cfg2 -f python tools/one_batch.py > gpurun_out/ncu_cfg2.log 2>&1
+ncu -i /tmp/prof_r02f_cfg2.ncu-rep --page raw --csv > gpurun_out/r02_final_cfg2_step_ncu_raw.csv 2>/dev/null
 # CARS: persistent GEMM (pre-gates), cluster recurrence
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc2_kernel|rnn_tc_kernel" -s 14 -c 10 -o gpurun_out/prof_r02f_cars -f python tools/bench_models.py --models cars --steps 1 --warmup 1 > gpurun_out/ncu_cars.log 2>&1
-ncu -i gpurun_out/prof_r02f_cars.ncu-rep --page raw --csv > gpurun_out/r02_final_cars_gemm_rnn_ncu_raw.csv 2>/dev/null
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc2_kernel|rnn_tc_kernel" -s 14 -c 10 -o /tmp/prof_r02f_cars -f python tools/bench_models.py --models cars --steps 1 --warmup 1 > gpurun_out/ncu_cars.log 2>&1
+ncu -i /tmp/prof_r02f_cars.ncu-rep --page raw --csv > gpurun_out/r02_final_cars_gemm_rnn_ncu_raw.csv 2>/dev/null
 # DRMM tcgen05 kernel
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"drmm_tc_kernel" -s 2 -c 1 -o gpurun_out/prof_r02f_drmm -f python tools/bench_models.py --models drmm --steps 1 --warmup 1 > gpurun_out/ncu_drmm.log 2>&1
-ncu -i gpurun_out/prof_r02f_drmm.ncu-rep --page raw --csv > gpurun_out/r02_final_drmm_tc_ncu_raw.csv 2>/dev/null
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"drmm_tc_kernel" -s 1 -c 1 -o /tmp/prof_r02f_drmm -f python tools/bench_models.py --models drmm --steps 1 --warmup 1 > gpurun_out/ncu_drmm.log 2>&1
+ncu -i /tmp/prof_r02f_drmm.ncu-rep --page raw --csv > gpurun_out/r02_final_drmm_tc_ncu_raw.csv 2>/dev/null
 # training step kernels
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"mt_interact_kernel|lstm_train_bwd_kernel|lstm_train_fwd_kernel|gemm_tn_kernel|mt_train_interact_bwd_kernel|embed_grad_kernel" -s 40 -c 12 -o gpurun_out/prof_r02f_train -f python tools/train_timing.py 128 > gpurun_out/ncu_train.log 2>&1
-ncu -i gpurun_out/prof_r02f_train.ncu-rep --page raw --csv > gpurun_out/r02_final_train_ncu_raw.csv 2>/dev/null
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"mt_interact_kernel|lstm_train_bwd_kernel|lstm_train_fwd_kernel|gemm_tn_kernel|mt_train_interact_bwd_kernel|embed_grad_kernel" -s 40 -c 12 -o /tmp/prof_r02f_train -f python tools/train_timing.py 128 > gpurun_out/ncu_train.log 2>&1
+ncu -i /tmp/prof_r02f_train.ncu-rep --page raw --csv > gpurun_out/r02_final_train_ncu_raw.csv 2>/dev/null
 timeout 300 python tools/train_timing.py 128 > gpurun_out/train_timing.log 2>&1
 timeout 300 python tools/lstm_timing.py > gpurun_out/lstm_timing.log 2>&1
 timeout 300 python tools/drmm_timing.py > gpurun_out/drmm_timing.log 2>&1
