@@ -486,36 +486,44 @@ __device__ __forceinline__ void mt_epi_prep(float* y, int i, int Lq, const int* 
   // difference of two pre-summed table rows: 2 x FP shared-memory loads for ANY pad pattern, the rows at the border of the
   // padding included (with a tap loop those rows made every (i, warp) unit of a padded pair take 21 x FP predicated adds).
   // Real-token matches (a few cells per pair) keep the tap loop.
-  int zm = 0, qz = 0;
-  bool real = false;
+  // Common case first (full-length batches, real x real cells): 21 predicate-accumulating compares and one branch.
+  bool hit = false;
 #pragma unroll
-  for (int bt = 0; bt < 7; ++bt) zm |= (dj[bt] == 0 ? 1 : 0) << bt;
+  for (int a = 0; a < 3; ++a)
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    qz |= (qv[a] == 0 ? 1 : 0) << a;
+    for (int bt = 0; bt < 7; ++bt) hit |= dj[bt] == qv[a];
+  if (hit) {
+    int zm = 0, qz = 0;
+    bool real = false;
 #pragma unroll
-    for (int bt = 0; bt < 7; ++bt) real |= qv[a] > 0 && dj[bt] == qv[a];
-  }
-  bool padgen = false;
-  if (zm != 0 && qz != 0) {
-    const int lo = __ffs(zm) - 1, hi = 32 - __clz(zm);
-    if ((zm >> lo) == (1 << (hi - lo)) - 1 && qz != 5) {
-      const float* th = padtab + (qz * 8 + hi) * 24;
-      const float* tl = padtab + (qz * 8 + lo) * 24;
-#pragma unroll
-      for (int f = 0; f < FP; ++f) y[f] += th[f] - tl[f];
-    } else {
-      padgen = true;   // PAD tokens inside a sequence (not produced by batchify): the general tap loop handles them
-    }
-  }
-  if (real || padgen) {
+    for (int bt = 0; bt < 7; ++bt) zm |= (dj[bt] == 0 ? 1 : 0) << bt;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
+      qz |= (qv[a] == 0 ? 1 : 0) << a;
 #pragma unroll
-      for (int bt = 0; bt < 7; ++bt) {
-        if (dj[bt] == qv[a] && (qv[a] > 0 || padgen)) {
+      for (int bt = 0; bt < 7; ++bt) real |= qv[a] > 0 && dj[bt] == qv[a];
+    }
+    bool padgen = false;
+    if (zm != 0 && qz != 0) {
+      const int lo = __ffs(zm) - 1, hi = 32 - __clz(zm);
+      if ((zm >> lo) == (1 << (hi - lo)) - 1 && qz != 5) {
+        const float* th = padtab + (qz * 8 + hi) * 24;
+        const float* tl = padtab + (qz * 8 + lo) * 24;
 #pragma unroll
-          for (int f = 0; f < FP; ++f) y[f] += ec.wem[a * 7 + bt][f];
+        for (int f = 0; f < FP; ++f) y[f] += th[f] - tl[f];
+      } else {
+        padgen = true;   // PAD tokens inside a sequence (not produced by batchify): the general tap loop handles them
+      }
+    }
+    if (real || padgen) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int bt = 0; bt < 7; ++bt) {
+          if (dj[bt] == qv[a] && (qv[a] > 0 || padgen)) {
+#pragma unroll
+            for (int f = 0; f < FP; ++f) y[f] += ec.wem[a * 7 + bt][f];
+          }
         }
       }
     }
