@@ -64,6 +64,9 @@ int32_t duet_create_state(Owned& own, const cair_duet_weights& w, DuetState* st,
   CAIR_TRY(dev_copy(own, w.dist_fc3.b, (size_t)nf, &st->fc3_b, s));
   CAIR_TRY(dev_copy(own, w.dist_fc4.w, (size_t)nf, &st->fc4_w, s));
   CAIR_TRY(dev_copy(own, w.dist_fc4.b, 1, &st->fc4_b, s));
+  CAIR_CUDA(cudaStreamCreateWithFlags(&st->side, cudaStreamNonBlocking));
+  CAIR_CUDA(cudaEventCreateWithFlags(&st->ev_fork, cudaEventDisableTiming));
+  CAIR_CUDA(cudaEventCreateWithFlags(&st->ev_join, cudaEventDisableTiming));
   return CAIR_OK;
 }
 
@@ -199,16 +202,26 @@ int32_t duet_forward(const DuetState& st, const int64_t* q, const int64_t* d, in
   if (smem > 200 * 1024) return fail(CAIR_ERR_UNSUPPORTED, "duet: Lq*Ld too large for the local model kernel");
   if (smem > 48 * 1024)
     CAIR_CUDA(cudaFuncSetAttribute(duet_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  prof_mark("local_model", s);
-  CAIR_LAUNCH(duet_local_kernel, (unsigned)pc, 256, smem, s, q, d, N, Lq, Ld, nf, pb, st.lconv_t, st.lconv_b,
+  // The local model (ids only) and the query side of the distributed model are small, latency-sized kernels that do not
+  // depend on the document convolutions: forked onto the handle's side stream (events keep the caller's stream semantics
+  // and stay graph-capturable), joined before the head.
+  cudaStream_t sq = st.side ? st.side : s;
+  if (st.side) {
+    CAIR_CUDA(cudaEventRecord(st.ev_fork, s));
+    CAIR_CUDA(cudaStreamWaitEvent(st.side, st.ev_fork, 0));
+  } else {
+    prof_mark("local_model", s);
+  }
+  CAIR_LAUNCH(duet_local_kernel, (unsigned)pc, 256, smem, sq, q, d, N, Lq, Ld, nf, pb, st.lconv_t, st.lconv_b,
               st.lfc1_w, st.lfc1_b, m1l);
-  CAIR_TRY(gemm_f32(gemm_dense(m1l, nf), st.lfc2_w, st.lfc2_b, m2l, nf, pc, nf, nf, ACT_TANH, s));
+  CAIR_TRY(gemm_f32(gemm_dense(m1l, nf), st.lfc2_w, st.lfc2_b, m2l, nf, pc, nf, nf, ACT_TANH, sq));
   // distributed model, query side
-  prof_mark("query_conv", s);
+  if (!st.side) prof_mark("query_conv", s);
   CAIR_TRY(gemm_auto(gemm_gather(st.table, st.V, E, q + qb * Lq, 3, Lq, Tq, err), st.cq_w, st.cq_tc, st.cq_b, cqv, nf,
-                     nq * Tq, nf, 3 * E, ACT_TANH, s));
-  CAIR_LAUNCH(colmax_kernel, (unsigned)nq, 256, 0, s, cqv, Tq, nf, mq);
-  CAIR_TRY(gemm_f32(gemm_dense(mq, nf), st.fc1_w, st.fc1_b, rq, nf, nq, nf, nf, ACT_TANH, s));
+                     nq * Tq, nf, 3 * E, ACT_TANH, sq));
+  CAIR_LAUNCH(colmax_kernel, (unsigned)nq, 256, 0, sq, cqv, Tq, nf, mq);
+  CAIR_TRY(gemm_f32(gemm_dense(mq, nf), st.fc1_w, st.fc1_b, rq, nf, nq, nf, nf, ACT_TANH, sq));
+  if (st.side) CAIR_CUDA(cudaEventRecord(st.ev_join, st.side));
   // distributed model, document side
   prof_mark("conv_d1", s);
   CAIR_TRY(gemm_auto(gemm_gather(st.table, st.V, E, d + pb * Ld, 3, Ld, Td, err), st.cd1_w, st.cd1_tc, st.cd1_b, cdv, nf,
@@ -222,6 +235,10 @@ int32_t duet_forward(const DuetState& st, const int64_t* q, const int64_t* d, in
   } else {
     CAIR_TRY(gemm_auto(gemm_pooled(cdv, nf, st.pool, Td, Tp), st.cd2_w, st.cd2_tc, st.cd2_b, rd, nf, pc * Tp, nf, nf,
                        ACT_TANH, s));
+  }
+  if (st.side) {
+    prof_mark("join_query_side", s);
+    CAIR_CUDA(cudaStreamWaitEvent(s, st.ev_join, 0));
   }
   prof_mark("head", s);
   CAIR_LAUNCH(duet_hadamard_kernel, dim3((unsigned)pc, (nf + 127) / 128), 128, 0, s, rd, rq, st.fc2_w, st.fc2_b, N, Tp,

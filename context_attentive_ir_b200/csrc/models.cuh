@@ -168,6 +168,9 @@ struct DuetState {
   GemmTcW cq_tc, cd1_tc, cd2_tc;  // tensor-core images of the three convolutions
   float *fc1_w = nullptr, *fc1_b = nullptr, *fc2_w = nullptr, *fc2_b = nullptr, *fc3_w = nullptr, *fc3_b = nullptr,
         *fc4_w = nullptr, *fc4_b = nullptr;
+  // the local model and the query side depend on the queries only: they run on a side stream, concurrently with the document convolutions
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 int32_t duet_create_state(Owned& own, const cair_duet_weights& w, DuetState* st, cudaStream_t s);
 int32_t duet_forward(const DuetState& st, const int64_t* q, const int64_t* d, int B, int N, int Lq, int Ld,
