@@ -518,7 +518,14 @@ def run_product(args):
     # ---- end-to-end: host ids -> H2D -> score (-> all-gather) -> D2H scores, every step over its 25 pinned host batches ----
     houts = [torch.empty(B * world, N, dtype=torch.float32).pin_memory() for _ in range(3)]
     cstream = torch.cuda.Stream(dev)
-    if world == 1:
+    pipe_gather = None
+    if world > 1 and not args.nccl_collective:
+        try:   # the all-gather inside the serving pipeline (cair_ranker_set_gather) needs its own peer buffers
+            from context_attentive_ir_b200.parallel import P2PScoreGather
+            pipe_gather = P2PScoreGather(pairs_local, dev).attach(net)
+        except Exception as ex:   # noqa: BLE001
+            run.p2p_error = run.p2p_error or repr(ex)[:200]
+    if world == 1 or pipe_gather is not None:
         # serving loop over three staging slots of the C ABI (cair_ranker_submit_host / cair_ranker_wait_host): the copies of
         # batch k+1 and its document encoder overlap the interaction kernel of batch k
         def e2e_loop(k):
@@ -530,7 +537,9 @@ def run_product(args):
                 for i in range(max(0, k - 3), k):
                     net.wait_host(i % 3)
         api = ('cair_ranker_submit_host / cair_ranker_wait_host over 3 staging slots: H2D of batch k+1 and its document encoder '
-               'overlap the interaction kernel of batch k; 25 distinct pinned batches per step')
+               'overlap the interaction kernel of batch k; 25 distinct pinned batches per step'
+               + ('; the scores of every batch are all-gathered over NVLink peer memory inside the pipeline '
+                  '(cair_ranker_set_gather) and every rank copies all B*world*N scores to its host' if world > 1 else ''))
     else:
         # N > 1: the score all-gather sits between the kernels and the D2H copy, so the loop runs on the device entry point:
         # pinned ids -> device staging (3 slots) -> this rank's scores -> NCCL all-gather -> all B*world*N scores to the host

@@ -80,6 +80,14 @@ struct cair_handle {
   int pipe_spc = 32;                     // document-encoder sequences per CTA in the pipeline (80 CTAs at cfg2: 68 SMs stay free)
   cudaStream_t hi_stream = nullptr, lo_stream = nullptr;
   cudaStream_t copy_stream = nullptr;
+  // optional: all-gather of the scores over NVLink peer memory between the kernels and the D2H copy of the host entry points
+  struct Gather {
+    bool on = false;
+    int rank = 0, world = 1;
+    int64_t count = 0;
+    uint32_t seq = 0;
+    std::vector<uint64_t> recv[2], flags;
+  } gather;
 };
 
 namespace {
@@ -689,7 +697,20 @@ int32_t pipe_finish(cair_handle* h, int sl, cudaStream_t st) {
   cair_handle::PipeSlot& p = h->pipe[sl];
   const PipeView v = pipe_view(p);
   CAIR_CUDA(cudaEventRecord(p.ev_int, st));   // the machine is free again: the next encoder need not wait for the copies
-  CAIR_CUDA(cudaMemcpyAsync(p.scores_host, v.ds, (size_t)p.B * p.N * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (h->gather.on) {
+    // doc-parallel serving: every rank's slice into every rank's receive buffer (one kernel over NVLink peer memory), then
+    // ALL world * B * N scores to this rank's host buffer.  Two receive buffers alternate; a peer overwrites buffer k & 1
+    // only after this rank's gather k-1 ran, which is stream-ordered behind the D2H copy of result k-2.
+    cair_handle::Gather& g = h->gather;
+    if ((int64_t)p.B * p.N != g.count) return fail(CAIR_ERR_BAD_SHAPE, "ranker host path: batch has %lld pairs, the gather was set up for %lld", (long long)p.B * p.N, (long long)g.count);
+    const uint32_t seq = ++g.seq;
+    const int par = (int)(seq & 1);
+    CAIR_TRY(allgather_scores_p2p(v.ds, g.count, g.recv[par].data(), g.flags.data(), g.rank, g.world, seq, st));
+    CAIR_CUDA(cudaMemcpyAsync(p.scores_host, reinterpret_cast<const float*>(g.recv[par][g.rank]), (size_t)g.world * g.count * sizeof(float),
+                              cudaMemcpyDeviceToHost, st));
+  } else {
+    CAIR_CUDA(cudaMemcpyAsync(p.scores_host, v.ds, (size_t)p.B * p.N * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
   int* flag = p.tail_pending ? p.d_err : h->d_err;   // pipelined batches carry their own flag; the plain form uses the handle's
   CAIR_CUDA(cudaMemcpyAsync(p.err, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   CAIR_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
@@ -863,6 +884,25 @@ extern "C" __attribute__((visibility("default"))) int32_t cair_ranker_pipeline_t
       cudaGetLastError();
     }
   }
+  return CAIR_OK;
+}
+
+int32_t cair_ranker_set_gather(cair_handle* h, const uint64_t* peer_recv0, const uint64_t* peer_recv1, const uint64_t* peer_flags,
+                               int32_t rank, int32_t world, int64_t count) {
+  if (!h) return fail(CAIR_ERR_BAD_ARG, "null handle");
+  cair_handle::Gather& g = h->gather;
+  if (world <= 1 || !peer_recv0) {   // switch off
+    g.on = false;
+    return CAIR_OK;
+  }
+  if (!peer_recv1 || !peer_flags || rank < 0 || rank >= world || world > 16 || count <= 0)
+    return fail(CAIR_ERR_BAD_ARG, "ranker_set_gather: bad argument");
+  for (int k = 0; k < 3; ++k)
+    if (h->pipe[k].busy) return fail(CAIR_ERR_BAD_ARG, "ranker_set_gather: batches in flight");
+  g.recv[0].assign(peer_recv0, peer_recv0 + world);
+  g.recv[1].assign(peer_recv1, peer_recv1 + world);
+  g.flags.assign(peer_flags, peer_flags + world);
+  g.rank = rank, g.world = world, g.count = count, g.seq = 0, g.on = true;
   return CAIR_OK;
 }
 

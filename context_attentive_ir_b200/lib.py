@@ -37,6 +37,7 @@ PROTOTYPES = {
     'cair_mt_set_debug': (i32, [vp, vp, vp]),
     'cair_mt_set_impl': (i32, [vp, i32]),
     'cair_allgather_scores': (i32, [vp, i64, vp, vp, i32, i32, C.c_uint32, vp]),
+    'cair_ranker_set_gather': (i32, [vp, vp, vp, vp, i32, i32, i64]),
     'cair_set_gemm_impl': (i32, [i32]),
     'cair_set_drmm_impl': (i32, [i32]),
     'cair_drmm_create': (i32, [C.POINTER(_abi.DrmmWeights), i32, C.POINTER(vp)]),

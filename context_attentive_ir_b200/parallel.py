@@ -62,7 +62,21 @@ class P2PScoreGather:
         self.seq = 0
         self._lib, self._check = lib.load(), lib.check
 
+    def attach(self, net):
+        """Hands this instance's buffers to the ranker's host entry points (cair_ranker_set_gather): submit_host / wait_host
+        then return ALL world * per scores per batch, gathered inside the serving pipeline.  The instance must not be
+        called directly afterwards (the sequence numbers are the handle's from now on)."""
+        dev = self.dev if isinstance(self.dev, torch.device) else torch.device(self.dev)
+        h = net._handle_for(dev)
+        self._check(self._lib.cair_ranker_set_gather(h, self._recv_ptrs[0], self._recv_ptrs[1], self._flag_ptrs, self.rank,
+                                                     self.world, self.per))
+        self._attached = net
+        net.__dict__['_cair_gather_world'] = self.world
+        net.__dict__['_cair_gather'] = self          # the peer mappings must outlive every batch the handle gathers
+        return self
+
     def __call__(self, local, total):
+        assert not getattr(self, '_attached', None), 'attached to a ranker: use its submit_host / wait_host'
         assert local.is_cuda and local.dtype == torch.float32 and local.is_contiguous() and local.numel() <= self.per
         send = local
         if local.numel() < self.per:              # short trailing slice: pad to the common slot length

@@ -99,7 +99,7 @@ def _named_tensors(module, prefix=''):
             yield from _named_tensors(child, prefix + name + '.')
 
 
-_HANDLE_KEYS = ('_cair_handle', '_cair_key', '_cair_ws', '_cair_trainer', '_cair_trainer_key', '_cair_sessdec', '_cair_sessdec_key', '_fwd')
+_HANDLE_KEYS = ('_cair_handle', '_cair_key', '_cair_ws', '_cair_trainer', '_cair_trainer_key', '_cair_sessdec', '_cair_sessdec_key', '_fwd', '_cair_gather_world', '_cair_gather')
 
 
 def _ptr_getter(module, keep):
@@ -177,6 +177,8 @@ class _CairModule(nn.Module):
         if h is not None:
             lib.load().cair_destroy(h)
             self.__dict__['_cair_handle'] = None
+        self.__dict__.pop('_cair_gather_world', None)   # a score gather is attached to a handle: re-attach after a rebuild
+        self.__dict__.pop('_cair_gather', None)
 
     def __del__(self):
         try:
@@ -233,7 +235,7 @@ class _Ranker(_CairModule):
                                   % type(self).__name__)
 
     @staticmethod
-    def _host_args(q, qlen, d, dlen, out, need_pinned):
+    def _host_args(q, qlen, d, dlen, out, need_pinned, mult=1):
         """The host entry points take raw pointers: insist on CPU int64 contiguous ids / lengths of the documented shapes
         and a CPU float32 [B, N] result buffer (pinned where the copy is asynchronous)."""
         for name, t in (('q', q), ('qlen', qlen), ('d', d), ('dlen', dlen)):
@@ -248,8 +250,9 @@ class _Ranker(_CairModule):
             raise ValueError('qlen must hold B and dlen B*N lengths')
         if out is not None:
             if (not torch.is_tensor(out) or out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous()
-                    or out.numel() != B * N):
-                raise ValueError('out must be a contiguous CPU float32 tensor with B*N elements')
+                    or out.numel() != B * N * mult):
+                raise ValueError('out must be a contiguous CPU float32 tensor with B*N elements (world*B*N when a score '
+                                 'gather is attached to the handle)')
             if need_pinned and not out.is_pinned():
                 raise ValueError('out must be in pinned host memory (asynchronous copy)')
 
@@ -277,7 +280,7 @@ class _Ranker(_CairModule):
         dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         if out is None:
             raise ValueError('submit_host needs a pinned float32 result buffer')
-        self._host_args(q, qlen, d, dlen, out, need_pinned=True)
+        self._host_args(q, qlen, d, dlen, out, need_pinned=True, mult=self.__dict__.get('_cair_gather_world', 1))
         B, Lq = q.shape
         _, N, Ld = d.shape
         h = self._handle_for(dev)

@@ -313,6 +313,14 @@ CAIR_API int32_t cair_ranker_set_pipeline_split(cair_handle* h, float frac);
  * previous result).  One launch on `stream`, nothing is synchronised; a peer that never arrives traps the launch. */
 CAIR_API int32_t cair_allgather_scores(const float* send, int64_t count, const uint64_t* peer_recv,
                               const uint64_t* peer_flags, int32_t rank, int32_t world, uint32_t seq, void* stream);
+/* The same gather INSIDE the host entry points (cair_ranker_submit_host / wait_host / the plain submit form): after this
+ * call every batch's scores are all-gathered between the kernels and the D2H copy, and the host buffer passed to
+ * cair_ranker_submit_host receives ALL world * B * N scores (rank-major), so the doc-parallel serving loop keeps its
+ * cross-batch software pipeline at N > 1.  peer_recv0 / peer_recv1: the two alternating receive buffers (each rank's
+ * [world * count] floats, as mapped into this process), peer_flags as above (zeroed, used by this handle only);
+ * count = B * N of every batch.  All ranks must submit the same number of batches.  world <= 1 or NULL switches it off. */
+CAIR_API int32_t cair_ranker_set_gather(cair_handle* h, const uint64_t* peer_recv0, const uint64_t* peer_recv1,
+                               const uint64_t* peer_flags, int32_t rank, int32_t world, int64_t count);
 
 /* ---- ranking metrics of the evaluation loops, on the device ----------
  * Replaces, per batch, `scores.cpu()` + `np.argsort(-scores)` + MAP / MRR / precision_at_k(1,3,5)

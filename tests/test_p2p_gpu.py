@@ -18,4 +18,4 @@ def test_p2p_allgather_matches_nccl():
            '--master-port', '29533', os.path.join(ROOT, 'tools', 'p2p_test.py')]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert 'identical=True' in r.stdout
+    assert 'identical=True' in r.stdout and 'pipelined gather inside submit_host / wait_host: identical=True' in r.stdout
