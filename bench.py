@@ -372,6 +372,10 @@ def other_configs(run, args, peaks):
     # semantics retire short documents early; reported beside the full-length headline, not instead of it
     ranker_case('match_tensor cfg2, realistic lengths (avg doc 63 + BOS/EOS)', CFG, B, N, LQ, LD, 20,
                 tensor_roof('lstm_tc_kernel', flops_per_pair()['ref']), realistic=True)
+    # the reference's STOCK Match-Tensor hidden sizes (neuroir/hyparam.py:88-100: nhid_query 30, nhid_doc 140 = 15 / 70 per
+    # direction): the 70-wide document encoder is beyond the single-CTA tcgen05 kernel and runs on the cluster-split one
+    ranker_case('match_tensor, stock hidden sizes 30/140 (SURVEY 8d)', dict(CFG, nhid_query=30, nhid_doc=140), B, N, LQ, LD, 20,
+                tensor_roof('rnn_tc_kernel', 145.3))   # conv 113.1 + projections 7.6 + BiLSTM 24.6 MFLOP per pair (reference-equivalent)
     ranker_case('esm cfg1', dict(model='esm', emsize=64, src_vocab_size=10000), 8, 5, 10, 50, 20,
                 hbm_roof('esm_kernel', bpp_fp32(64, 10, 50, 5)))
     ranker_case('esm E=300 (cfg3 shape)', dict(model='esm', emsize=300, src_vocab_size=131072), 256, 10, 20, 200, 10,

@@ -135,3 +135,25 @@ class ShardedCars:
         recv = local.new_empty(per * S * N * world)
         dist.all_gather_into_tensor(recv, send, group=self.group)
         return recv[:B * S * N].reshape(B, S, N)
+
+
+class ShardedSessionRanker(ShardedCars):
+    """Session-sharded MNSRF / M_MATCH_TENSOR scoring (no labels on their ranking path): rank r scores sessions
+    [begin, begin+count), one all-gather of scores.  `network.score(q, qlen, d, dlen, session_slice=...)` for MNSRF; the
+    default for networks without a session slice (M_MATCH_TENSOR scores every (session, query) row independently) slices
+    the batch itself."""
+
+    def __init__(self, network, score_slice=None, group=None):
+        def default(q, ql, d, dl, lab, b, c):
+            import inspect
+            if 'session_slice' in inspect.signature(network.score).parameters:
+                return network.score(q, ql, d, dl, session_slice=(b, c))['scores']
+            full = q.new_zeros(d.shape[:3], dtype=torch.float32)
+            if c > 0:
+                full[b:b + c] = network.score(q[b:b + c], ql[b:b + c], d[b:b + c], dl[b:b + c])
+            return full
+        super().__init__(network, score_slice=(lambda q, ql, d, dl, lab, b, c: score_slice(q, ql, d, dl, b, c)) if score_slice else default,
+                         group=group)
+
+    def __call__(self, q, qlen, d, dlen):
+        return super().__call__(q, qlen, d, dlen, None)
