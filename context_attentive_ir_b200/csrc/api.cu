@@ -158,6 +158,9 @@ int32_t cair_destroy(cair_handle* h) {
   if (h->mt.side) cudaStreamDestroy(h->mt.side);
   if (h->mt.ev_fork) cudaEventDestroy(h->mt.ev_fork);
   if (h->mt.ev_join) cudaEventDestroy(h->mt.ev_join);
+  if (h->cars.side) cudaStreamDestroy(h->cars.side);
+  if (h->cars.ev_fork) cudaEventDestroy(h->cars.ev_fork);
+  if (h->cars.ev_join) cudaEventDestroy(h->cars.ev_join);
   if (h->duet.side) cudaStreamDestroy(h->duet.side);
   if (h->duet.ev_fork) cudaEventDestroy(h->duet.ev_fork);
   if (h->duet.ev_join) cudaEventDestroy(h->duet.ev_join);

@@ -71,6 +71,9 @@ int32_t cars_create_state(Owned& own, const cair_cars_weights& w, CarsState* st,
     if (i < 2 && in % 4 == 0) CAIR_TRY(gemm_tc_pack(own, st->rk_w[i], st->rd[i] * 2, in, &st->rk_tc[i], s));
     in = st->rd[i];
   }
+  CAIR_CUDA(cudaStreamCreateWithFlags(&st->side, cudaStreamNonBlocking));
+  CAIR_CUDA(cudaEventCreateWithFlags(&st->ev_fork, cudaEventDisableTiming));
+  CAIR_CUDA(cudaEventCreateWithFlags(&st->ev_join, cudaEventDisableTiming));
   return CAIR_OK;
 }
 
@@ -399,7 +402,7 @@ __global__ void fill_len_kernel(int64_t* len, int n, int64_t v) {
 
 static int32_t encode_pool(const CarsState& st, const LstmPack& lp, const RnnTcPack& rt, const AttnPack& ap, const int64_t* ids,
                            const int64_t* len, int64_t n, int L, float* pre, float* enc, float* hid, float* pooled,
-                           int* err, cudaStream_t s, const char* rec_name) {
+                           int* err, cudaStream_t s, const char* rec_name, bool marks = true) {
   const int H = ap.H;
   if (g_rnn_impl >= RNN_IMPL_AUTO && rt.wimg)   // tcgen05 recurrence (pre-gates from the gathered tcgen05 GEMM)
     CAIR_TRY(rnn_tc_run(rt, gemm_gather(st.table, st.V, st.E, ids, 1, 1, 1, err), len, (int)n, L, enc, nullptr, nullptr, pre,
@@ -407,7 +410,7 @@ static int32_t encode_pool(const CarsState& st, const LstmPack& lp, const RnnTcP
   else
     CAIR_TRY(lstm_run(lp, gemm_gather(st.table, st.V, st.E, ids, 1, 1, 1, err), len, (int)n, L, enc, nullptr, nullptr,
                       pre, err, s, rec_name));
-  prof_mark("attention_pool", s);
+  if (marks) prof_mark("attention_pool", s);
   if (gemm_tc_rowdot_usable(gemm_dense(enc, H), ap.w0_tc, n * L)) {
     // tanh(l0(enc)) . w3 + b3 inside the GEMM epilogue: the [n*L, H] hidden tensor is never written (hid holds the scores)
     CAIR_TRY(gemm_tc_rowdot(gemm_dense(enc, H), ap.w0_tc, ap.b0, ACT_TANH, ap.w3, ap.b3, hid, n * L, s));
@@ -457,9 +460,22 @@ int32_t cars_forward(const CarsState& st, const CarsIO& io, int B, int S, int N,
   if (dry || sc <= 0) return CAIR_OK;
   if (!ws.ok()) return fail(CAIR_ERR_WORKSPACE, "cars: workspace too small");
 
-  // 1. encode + attention pooling
-  prof_mark("query_pregates", s);
-  CAIR_TRY(encode_pool(st, st.enc_q, st.rt_q, st.q_attn, io.q + r0 * Lq, io.qlen + r0, nrows, Lq, pre_q, enc_q, hid_q, pq, err, s, "query_recurrence"));
+  // 1. encode + attention pooling.  The query chain (encoder, pooling, query-session LSTM) only needs the queries: it is
+  // forked onto the handle's side stream and runs under the document chain; joined before the rank head.
+  CAIR_LAUNCH(fill_len_kernel, (sc + 255) / 256, 256, 0, s, slen, sc, (int64_t)S);
+  cudaStream_t sq = st.side ? st.side : s;
+  if (st.side) {
+    CAIR_CUDA(cudaEventRecord(st.ev_fork, s));
+    CAIR_CUDA(cudaStreamWaitEvent(st.side, st.ev_fork, 0));
+  } else {
+    prof_mark("query_pregates", s);
+  }
+  CAIR_TRY(encode_pool(st, st.enc_q, st.rt_q, st.q_attn, io.q + r0 * Lq, io.qlen + r0, nrows, Lq, pre_q, enc_q, hid_q, pq, err, sq,
+                       st.side ? nullptr : "query_recurrence", !st.side));
+  // 3a. session LSTM over the pooled queries (zero initial state, S steps)
+  CAIR_TRY(lstm_run(st.sess_q, gemm_dense(pq, Hq), slen, sc, S, Qs, nullptr, nullptr, pre_sq, err, sq, st.side ? nullptr : "lstm_recurrence",
+                    io.sess_c ? Qc : nullptr));
+  if (st.side) CAIR_CUDA(cudaEventRecord(st.ev_join, st.side));
   prof_mark("doc_pregates", s);
   CAIR_TRY(encode_pool(st, st.enc_d, st.rt_d, st.d_attn, io.d + r0 * N * Ld, io.dlen + r0 * N, ndocs, Ld, pre_d, enc_d, hid_d, pd, err, s, "doc_recurrence"));
   // 2. click vectors
@@ -470,13 +486,14 @@ int32_t cars_forward(const CarsState& st, const CarsIO& io, int B, int S, int N,
                      ACT_TANH, s));
   CAIR_LAUNCH(rowdot_kernel, (unsigned)((ndocs + 7) / 8), 256, 0, s, hid_c, ndocs, Hd, st.click_attn.w3, st.click_attn.b3, att_c);
   CAIR_LAUNCH(clicks_kernel, (unsigned)nrows, 128, (size_t)N * 8, s, pd, att_c, io.labels, N, Hd, mwidth, r0, clk);
-  // 3. session LSTMs over the pooled queries / click vectors (zero initial state, S steps each)
+  // 3b. session LSTM over the click vectors
   prof_mark("session_encoders", s);
-  CAIR_LAUNCH(fill_len_kernel, (sc + 255) / 256, 256, 0, s, slen, sc, (int64_t)S);
-  CAIR_TRY(lstm_run(st.sess_q, gemm_dense(pq, Hq), slen, sc, S, Qs, nullptr, nullptr, pre_sq, err, s, "lstm_recurrence",
-                    io.sess_c ? Qc : nullptr));
   CAIR_TRY(lstm_run(st.sess_d, gemm_dense(clk, Hd), slen, sc, S, Ds, nullptr, nullptr, pre_sd, err, s, "lstm_recurrence",
                     io.sess_c ? Dc : nullptr));
+  if (st.side) {
+    prof_mark("join_query_side", s);
+    CAIR_CUDA(cudaStreamWaitEvent(s, st.ev_join, 0));
+  }
   // 4. session attention + rank head
   prof_mark("rank_head", s);
   {

@@ -207,6 +207,10 @@ struct CarsState {
   GemmTcW rk_tc[2];                        // tensor-core images of the first two Maxout layers (rows = B*S*N candidates)
   float* shared_proj = nullptr;            // shared_session_projector alone (the decoder adds private_session_projector2 to it)
   CarsDecoder dec;
+  // the query chain (encode, pool, query-session LSTM) depends on the queries only: forked onto a side stream, it runs under
+  // the document chain
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 struct CarsIO {
   const int64_t *q, *qlen, *d, *dlen;
