@@ -72,7 +72,7 @@ int32_t mt_tc_proj_image(const MtPack& p, const float* enc_d, int Hd, const uint
 int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const uint8_t* timg, const uint8_t* aimg,
                        const int64_t* q, const int64_t* d, int N, int Lq, int Ld, int64_t pair_begin,
                        int64_t pair_count, int64_t q_begin, int64_t nq, float* scores, cudaStream_t s,
-                       int max_ctas = 0);
+                       int max_ctas = 0, float* pooled = nullptr, int* argidx = nullptr);
 
 extern long long* g_mt_dbg;  // optional role-timing counters of the tcgen05 interaction kernel (debug)
 enum { MT_IMPL_FP32 = 0, MT_IMPL_TC = 1, MT_IMPL_TC_SPLIT = 2 };  // 2: tcgen05 interaction, fp32 doc projection + image kernel

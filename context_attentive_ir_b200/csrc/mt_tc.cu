@@ -536,9 +536,12 @@ __device__ __forceinline__ void mt_epi_prep(float* y, int i, int Lq, const int* 
 // 1x1 conv: f outer, output-channel pairs inner -> independent accumulators; packed fp32x2 FMAs (FFMA2) with y[f] as the
 // broadcast scalar operand; the weights come from shared memory as broadcast LDS.128 (w1t[f][m], m contiguous), shared
 // by the NI positions.  Outputs m >= M see zero weights and are ignored at the end.
-template <int NF, int NI>
+// ARG (training forward): also track, per output channel, the cell i * Ld + jrow of this thread's running maximum (strict
+// comparison: cells are visited in ascending linear order per thread, so the first maximum is kept, as torch.max does).
+template <int NF, int NI, bool ARG = false>
 __device__ __forceinline__ void mt_epi_unit(uint32_t tacc, int i0, int Lq, bool row_ok, const int* djp, const int* qids,
-                                            const MtEpiConst& ec, const float* w1t, float* mx) {
+                                            const MtEpiConst& ec, const float* w1t, float* mx, int* ai = nullptr, int jrow = 0,
+                                            int Ld = 0) {
   constexpr int FP = 3 * NF;
   float y[NI][FP];
 #pragma unroll
@@ -571,17 +574,24 @@ __device__ __forceinline__ void mt_epi_unit(uint32_t tacc, int i0, int Lq, bool 
     if (i0 + n < Lq) {
 #pragma unroll
       for (int m2 = 0; m2 < 10; ++m2) {
-        mx[2 * m2] = fmaxf(mx[2 * m2], zz[n][m2].x);
-        mx[2 * m2 + 1] = fmaxf(mx[2 * m2 + 1], zz[n][m2].y);
+        if constexpr (ARG) {
+          const int cell = (i0 + n) * Ld + jrow;
+          if (zz[n][m2].x > mx[2 * m2]) mx[2 * m2] = zz[n][m2].x, ai[2 * m2] = cell;
+          if (zz[n][m2].y > mx[2 * m2 + 1]) mx[2 * m2 + 1] = zz[n][m2].y, ai[2 * m2 + 1] = cell;
+        } else {
+          mx[2 * m2] = fmaxf(mx[2 * m2], zz[n][m2].x);
+          mx[2 * m2 + 1] = fmaxf(mx[2 * m2 + 1], zz[n][m2].y);
+        }
       }
     }
   }
 }
 
 // General-M (20 < M <= MT_TC_MAXM) unit, one query position, scalar FMAs.
-template <int NF>
+template <int NF, bool ARG = false>
 __device__ __forceinline__ void mt_epi_unit_wide(uint32_t tacc, int i, int Lq, bool row_ok, const int* djp, const int* qids,
-                                                 const MtEpiConst& ec, const float* w1t, float* mx) {
+                                                 const MtEpiConst& ec, const float* w1t, float* mx, int* ai = nullptr, int jrow = 0,
+                                                 int Ld = 0) {
   constexpr int FP = 3 * NF;
   float y[FP];
   tmem_ld_fp<FP>(tacc, y);
@@ -607,16 +617,22 @@ __device__ __forceinline__ void mt_epi_unit_wide(uint32_t tacc, int i, int Lq, b
     }
   }
 #pragma unroll
-  for (int m = 0; m < MT_TC_MAXM; ++m) mx[m] = fmaxf(mx[m], z[m]);
+  for (int m = 0; m < MT_TC_MAXM; ++m) {
+    if constexpr (ARG) {
+      if (z[m] > mx[m]) mx[m] = z[m], ai[m] = i * Ld + jrow;
+    } else {
+      mx[m] = fmaxf(mx[m], z[m]);
+    }
+  }
 }
 
-template <int NF>
+template <int NF, bool ARG = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     mt_tc_interact_kernel(const uint8_t* __restrict__ aimg, const uint8_t* __restrict__ timg, MtPack p,
                           const __grid_constant__ MtEpiConst ec, const int64_t* __restrict__ q,
                           const int64_t* __restrict__ d, int N, int Lq, int Ld, int ntiles, int nstages,
                           int64_t pair_begin, int64_t pair_count, int64_t q_begin, float* __restrict__ scores,
-                          long long* __restrict__ dbg) {
+                          long long* __restrict__ dbg, float* __restrict__ pooled, int* __restrict__ argidx) {
   constexpr int FP = 3 * NF, FPP = (FP + 3) & ~3, IPT = TC_NROWS / FP;
   extern __shared__ __align__(128) uint8_t smraw[];
   __shared__ uint64_t full_b[8], empty_b[8], acc_full[2], acc_empty[2], a_full, a_empty;
@@ -792,8 +808,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       if (warp == 0) TC_ACC(5);
 
       float mx[MT_TC_MAXM];
+      int ai[ARG ? MT_TC_MAXM : 1];
 #pragma unroll
       for (int m = 0; m < MT_TC_MAXM; ++m) mx[m] = -INFINITY;
+      if constexpr (ARG) {
+#pragma unroll
+        for (int m = 0; m < MT_TC_MAXM; ++m) ai[m] = 0x7fffffff;
+      }
 
       for (int nt = 0; nt < ntiles; ++nt, ++tile) {
         const int as = tile & 1;
@@ -811,12 +832,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const uint32_t tacc = tbase + ((uint32_t)lane_base << 16) + (uint32_t)(as * 2 + mt) * TC_NROWS + il0 * FP;
             const int i0 = nt * IPT + il0;
             if (M <= 20 && TC_NI == 2 && il0 + 1 < IPT)
-              mt_epi_unit<NF, TC_NI>(tacc, i0, Lq, jrow < Ld, dids + jrow, qids, ec, w1t, mx);
+              mt_epi_unit<NF, TC_NI, ARG>(tacc, i0, Lq, jrow < Ld, dids + jrow, qids, ec, w1t, mx, ai, jrow, Ld);
             else if (M <= 20)
-              mt_epi_unit<NF, 1>(tacc, i0, Lq, jrow < Ld, dids + jrow, qids, ec, w1t, mx);
+              mt_epi_unit<NF, 1, ARG>(tacc, i0, Lq, jrow < Ld, dids + jrow, qids, ec, w1t, mx, ai, jrow, Ld);
             else {
               for (int n = 0; n < TC_NI && il0 + n < IPT; ++n)
-                mt_epi_unit_wide<NF>(tacc + n * FP, i0 + n, Lq, jrow < Ld, dids + jrow, qids, ec, w1t, mx);
+                mt_epi_unit_wide<NF, ARG>(tacc + n * FP, i0 + n, Lq, jrow < Ld, dids + jrow, qids, ec, w1t, mx, ai, jrow, Ld);
             }
           }
         }
@@ -826,18 +847,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (lane == 0) mbar_arrive(&acc_empty[as]);
       }
       // ---- max over all rows of the pair, Linear(M -> 1), one store ----
+      int* redi = dids;   // (ARG) the ids of this pair are no longer needed; 8 warps x 32 slots fit in TC_MAXRA + 8 ints
+      if constexpr (ARG) named_bar_sync(1, TC_EPI_THREADS);   // every warp is done with dids
 #pragma unroll
       for (int m = 0; m < MT_TC_MAXM; ++m) {
-        float v = warp_max(mx[m]);
-        if (lane == 0) red[warp * MT_TC_MAXM + m] = v;
+        if constexpr (ARG) {
+          float v = mx[m];
+          int ix = ai[m];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
+            if (ov > v || (ov == v && oi < ix)) v = ov, ix = oi;
+          }
+          if (lane == 0) red[warp * MT_TC_MAXM + m] = v, redi[warp * MT_TC_MAXM + m] = ix;
+        } else {
+          float v = warp_max(mx[m]);
+          if (lane == 0) red[warp * MT_TC_MAXM + m] = v;
+        }
       }
       named_bar_sync(1, TC_EPI_THREADS);
       if (warp == 0) {
         float v = 0.f;
         if (lane < M) {
           float best = red[lane];
+          int bi = ARG ? redi[lane] : 0;
 #pragma unroll
-          for (int w = 1; w < TC_EPI_WARPS; ++w) best = fmaxf(best, red[w * MT_TC_MAXM + lane]);
+          for (int w = 1; w < TC_EPI_WARPS; ++w) {
+            const float o = red[w * MT_TC_MAXM + lane];
+            if constexpr (ARG) {
+              const int oi = redi[w * MT_TC_MAXM + lane];
+              if (o > best || (o == best && oi < bi)) best = o, bi = oi;
+            } else {
+              best = fmaxf(best, o);
+            }
+          }
+          if constexpr (ARG) pooled[pl * M + lane] = best, argidx[pl * M + lane] = bi;
           v = best * p.wo[lane];
         }
         v = warp_sum(v);
@@ -948,7 +993,7 @@ int32_t mt_tc_proj_image(const MtPack& p, const float* enc_d, int Hd, const uint
 
 int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const uint8_t* timg, const uint8_t* aimg, const int64_t* q,
                        const int64_t* d, int N, int Lq, int Ld, int64_t pair_begin, int64_t pair_count, int64_t q_begin,
-                       int64_t nq, float* scores, cudaStream_t s, int max_ctas) {
+                       int64_t nq, float* scores, cudaStream_t s, int max_ctas, float* pooled, int* argidx) {
   (void)nq;
   if (pair_count <= 0) return CAIR_OK;
   const TcK k = tc_k(p.C);
@@ -958,14 +1003,27 @@ int32_t mt_tc_interact(const MtPack& p, const MtEpiConst& ec, const uint8_t* tim
   prof_mark("interact", s);
   unsigned grid = (unsigned)(pair_count < kSMs ? pair_count : kSMs);
   if (max_ctas > 0 && grid > (unsigned)max_ctas) grid = (unsigned)max_ctas;
+  if (pooled && argidx) {
+    // training forward (train.cu): pooled features and arg-max cells of every (pair, output channel); local pair indexing
+    if (p.nf == 6) {
+      CAIR_CUDA(cudaFuncSetAttribute(mt_tc_interact_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CAIR_LAUNCH((mt_tc_interact_kernel<6, true>), grid, TC_THREADS, smem, s, aimg, timg, p, ec, q, d, N, Lq, Ld, ntiles, nstages,
+                  pair_begin, pair_count, q_begin, scores, (long long*)nullptr, pooled, argidx);
+    } else {
+      CAIR_CUDA(cudaFuncSetAttribute(mt_tc_interact_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CAIR_LAUNCH((mt_tc_interact_kernel<4, true>), grid, TC_THREADS, smem, s, aimg, timg, p, ec, q, d, N, Lq, Ld, ntiles, nstages,
+                  pair_begin, pair_count, q_begin, scores, (long long*)nullptr, pooled, argidx);
+    }
+    return CAIR_OK;
+  }
   if (p.nf == 6) {
     CAIR_CUDA(cudaFuncSetAttribute(mt_tc_interact_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CAIR_LAUNCH(mt_tc_interact_kernel<6>, grid, TC_THREADS, smem, s, aimg, timg, p, ec, q, d, N, Lq, Ld, ntiles,
-                nstages, pair_begin, pair_count, q_begin, scores, g_mt_dbg);
+                nstages, pair_begin, pair_count, q_begin, scores, g_mt_dbg, (float*)nullptr, (int*)nullptr);
   } else {
     CAIR_CUDA(cudaFuncSetAttribute(mt_tc_interact_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CAIR_LAUNCH(mt_tc_interact_kernel<4>, grid, TC_THREADS, smem, s, aimg, timg, p, ec, q, d, N, Lq, Ld, ntiles,
-                nstages, pair_begin, pair_count, q_begin, scores, g_mt_dbg);
+                nstages, pair_begin, pair_count, q_begin, scores, g_mt_dbg, (float*)nullptr, (int*)nullptr);
   }
   return CAIR_OK;
 }
