@@ -605,10 +605,12 @@ struct MtTrainer {
   float *wiht_q = nullptr, *wiht_d = nullptr;   // [F][dirs*4h]
   float *wqt = nullptr, *wdt = nullptr;         // [Hq][C], [Hd][C]
   int dirs = 1, hq = 0, hd = 0;
+  int tc_forward = 1;     // forward interaction on the tcgen05 kernel (with arg-max) where the shape allows; 0: fp32 kernel
 };
 
 struct MtTrainWs {
   int* err;
+  uint8_t *timg, *aimg;   // operand images of the tensor-core interaction kernel (forward)
   float *xq, *xd, *fq, *fd, *gq, *gd, *cseq_q, *cseq_d, *enc_q, *enc_d, *cq, *cd, *T, *pooled;
   int* argidx;
   float *dcq, *dcd, *denc_q, *denc_d, *dfq, *dfd;
@@ -625,6 +627,12 @@ static void mt_train_layout(const MtTrainer& t, Arena& a, int B, int N, int Lq, 
   o->enc_q = a.take<float>(Rq * w.nhid_query), o->enc_d = a.take<float>(Rd * w.nhid_doc);
   o->cq = a.take<float>(Rq * w.nchannels), o->cd = a.take<float>(Rd * w.nchannels);
   o->T = a.take<float>(mt_t_floats(t.pack, B, Lq));
+  o->timg = o->aimg = nullptr;
+  if (mt_tc_supported(t.pack, Lq, Ld)) {
+    size_t tb = 0, ab = 0;
+    mt_tc_workspace(t.pack, B, (int64_t)P, Lq, Ld, &tb, &ab);
+    o->timg = a.take<uint8_t>(tb), o->aimg = a.take<uint8_t>(ab);
+  }
   o->pooled = a.take<float>(P * w.match_filter_size);
   o->argidx = a.take<int>(P * w.match_filter_size);
   o->dcq = a.take<float>(Rq * w.nchannels), o->dcd = a.take<float>(Rd * w.nchannels);
@@ -877,6 +885,12 @@ int32_t cair_mt_train_create(const cair_mt_weights* w, int32_t device, cair_mt_t
   return CAIR_OK;
 }
 
+int32_t cair_mt_train_set_impl(cair_mt_trainer* h, int32_t tc_forward) {
+  if (!h) return fail(CAIR_ERR_BAD_ARG, "mt_train_set_impl: null trainer");
+  h->t.tc_forward = tc_forward ? 1 : 0;
+  return CAIR_OK;
+}
+
 int32_t cair_mt_train_destroy(cair_mt_trainer* h) {
   if (!h) return CAIR_OK;
   DevGuard g(h->t.device);
@@ -938,7 +952,15 @@ int32_t cair_mt_train_forward(cair_mt_trainer* h, const int64_t* q, const int64_
   // channel projections (:99, :108)
   CAIR_TRY(gemm_f32(gemm_dense(o.enc_q, Hq), w.query_projection.w, w.query_projection.b, o.cq, C, Rq, C, Hq, ACT_NONE, s));
   CAIR_TRY(gemm_f32(gemm_dense(o.enc_d, Hd), w.document_projection.w, w.document_projection.b, o.cd, C, Rd, C, Hd, ACT_NONE, s));
-  // interaction (:113-131) with the arg-max cells of the two max-pools
+  // interaction (:113-131) with the arg-max cells of the two max-pools: the tensor-core kernel of the scoring path (its
+  // arg-max instantiation) where the shape allows, else the fp32 kernel.  The backward recomputes the winning cells in fp32.
+  if (t.tc_forward && o.timg) {
+    MtEpiConst ec;
+    CAIR_TRY(mt_epi_const(t.pack, &ec, s));   // epilogue constants of the CURRENT weights (synchronises s)
+    CAIR_TRY(mt_tc_build_t(t.pack, o.cq, o.timg, Lq, B, s));
+    CAIR_TRY(mt_tc_doc_image(t.pack, o.cd, o.aimg, Ld, P, s));
+    return mt_tc_interact(t.pack, ec, o.timg, o.aimg, q, d, N, Lq, Ld, 0, P, 0, B, scores, s, 0, o.pooled, o.argidx);
+  }
   return mt_interact_train(t.pack, o.cq, o.cd, o.T, q, d, N, Lq, Ld, P, B, scores, o.pooled, o.argidx, s);
 }
 

@@ -65,6 +65,7 @@ PROTOTYPES = {
     'cair_cars_decode_workspace_bytes': (i32, [vp, i32, i32, i32, C.POINTER(C.c_size_t)]),
     'cair_mt_train_create': (i32, [C.POINTER(_abi.MtWeights), i32, C.POINTER(vp)]),
     'cair_mt_train_destroy': (i32, [vp]),
+    'cair_mt_train_set_impl': (i32, [vp, i32]),
     'cair_mt_train_workspace_bytes': (i32, [vp, i32, i32, i32, i32, C.POINTER(C.c_size_t)]),
     'cair_mt_train_forward': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, C.c_float, C.c_uint64, vp, vp, C.c_size_t, vp]),
     'cair_mt_train_backward': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, C.c_float, C.c_uint64, vp,

@@ -491,7 +491,17 @@ class MatchTensor(_Ranker):
         out = C.c_void_p()
         lib.check(lib.load().cair_mt_train_create(C.byref(w), device.index, C.byref(out)))
         self.__dict__['_cair_trainer'], self.__dict__['_cair_trainer_key'] = out, key
+        if self.__dict__.get('_cair_train_tc') is not None:
+            lib.check(lib.load().cair_mt_train_set_impl(out, int(self.__dict__['_cair_train_tc'])))
         return out
+
+    def set_training_impl(self, tc_forward=True):
+        """Training forward interaction on the tcgen05 kernel (default) or the fp32 kernel."""
+        self.__dict__['_cair_train_tc'] = bool(tc_forward)
+        t = self.__dict__.get('_cair_trainer')
+        if t is not None:
+            lib.check(lib.load().cair_mt_train_set_impl(t, int(bool(tc_forward))))
+        return self
 
     def _release_trainer(self):
         t = self.__dict__.get('_cair_trainer')
