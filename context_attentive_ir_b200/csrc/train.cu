@@ -414,11 +414,12 @@ __global__ void __launch_bounds__(256) mt_train_interact_bwd_kernel(
     const float* __restrict__ w7, const float* __restrict__ cbias1, const float* __restrict__ cbias2,
     const float* __restrict__ cbias3, const float* __restrict__ w1, const float* __restrict__ wo,
     const float* __restrict__ alpha_p, int N, int Lq, int Ld, int C, int nf, int M, int64_t pairs, float* __restrict__ dcq,
-    float* __restrict__ dcd, MtGradPtrs g) {
+    float* __restrict__ dcd, MtGradPtrs g, int w7_smem) {
   extern __shared__ __align__(16) float sm[];
   const int C1 = C + 1, FP = 3 * nf, FPP = (FP + 3) & ~3, NT = 21 * C1;
   float* dW7 = sm;
-  float* ysm = dW7 + (size_t)NT * FPP;
+  float* w7s = dW7 + (size_t)NT * FPP;                                  // the stencil itself, when it fits beside its gradient
+  float* ysm = w7s + (w7_smem ? (size_t)NT * FPP : 0);
   float* red = ysm + FPP;
   float* dw1 = red + 8 * FPP;
   float* db1 = dw1 + M * FP;
@@ -429,7 +430,12 @@ __global__ void __launch_bounds__(256) mt_train_interact_bwd_kernel(
   int* dids = qids + Lq;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float alpha = alpha_p[0];
-  for (int i = tid; i < NT * FPP + FPP + 8 * FPP + M * FP + 2 * M + FP + 4; i += 256) sm[i] = 0.f;
+  for (int i = tid; i < NT * FPP; i += 256) dW7[i] = 0.f;
+  for (int i = tid; i < FPP + 8 * FPP + M * FP + 2 * M + FP + 4; i += 256) ysm[i] = 0.f;
+  if (w7_smem) {
+    for (int i = tid; i < NT * FPP; i += 256) w7s[i] = w7[i];
+    w7 = w7s;   // every (pair, m) unit reads all 21 (C+1) FPP weights twice: from shared memory instead of L1 / L2
+  }
   __syncthreads();
   float dalpha_loc = 0.f;
   for (int64_t p = blockIdx.x; p < pairs; p += gridDim.x) {
@@ -990,15 +996,17 @@ int32_t cair_mt_train_backward(cair_mt_trainer* h, const int64_t* q, const int64
   CAIR_CUDA(cudaMemsetAsync(o.dcd, 0, (size_t)Rd * C * sizeof(float), s));
   {
     const int C1 = C + 1, FP = t.pack.FP, FPP = t.pack.FPP;
-    const size_t smem = ((size_t)21 * C1 * FPP + FPP + 8 * FPP + (size_t)M * FP + 2 * M + FP + 4) * sizeof(float) +
-                        (size_t)(Lq + Ld) * sizeof(int);
+    const size_t rest = ((size_t)FPP + 8 * FPP + (size_t)M * FP + 2 * M + FP + 4) * sizeof(float) + (size_t)(Lq + Ld) * sizeof(int);
+    const size_t w7b = (size_t)21 * C1 * FPP * sizeof(float);
+    const int w7_smem = 2 * w7b + rest <= 220 * 1024;
+    const size_t smem = (w7_smem ? 2 : 1) * w7b + rest;
     if (smem > 220 * 1024) return fail(CAIR_ERR_UNSUPPORTED, "mt_train_backward: stencil does not fit in shared memory");
     CAIR_CUDA(cudaFuncSetAttribute(mt_train_interact_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MtGradPtrs gpz{gp(G.conv1.w), gp(G.conv2.w), gp(G.conv3.w), gp(G.conv1.b), gp(G.conv2.b), gp(G.conv3.b),
                    gp(G.conv.w),  gp(G.conv.b),  gp(G.output.w), gp(G.output.b), gp(G.alpha)};
-    const unsigned grid = (unsigned)(P < 2 * kSMs ? P : 2 * kSMs);
+    const unsigned grid = (unsigned)(P < (w7_smem ? 1 : 2) * kSMs ? P : (w7_smem ? 1 : 2) * kSMs);
     CAIR_LAUNCH(mt_train_interact_bwd_kernel, grid, 256, smem, s, o.cq, o.cd, q, d, dscores, o.pooled, o.argidx, t.w7, w.conv1.b,
-                w.conv2.b, w.conv3.b, w.conv.w, w.output.w, w.alpha, N, Lq, Ld, C, w.nfilters, M, P, o.dcq, o.dcd, gpz);
+                w.conv2.b, w.conv3.b, w.conv.w, w.output.w, w.alpha, N, Lq, Ld, C, w.nfilters, M, P, o.dcq, o.dcd, gpz, w7_smem);
   }
   // ---- channel projections ----
   CAIR_TRY(gemm_tn(o.dcq, C, o.enc_q, Hq, 0, Lq, gp(G.query_projection.w), Hq, Rq, C, Hq, s));
