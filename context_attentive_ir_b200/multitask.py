@@ -197,6 +197,9 @@ class CARS(_CairModule):
                                          ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
         return out
 
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError(_NO_TRAINING % 'CARS')
+
     # -- the reference's two-call predict sequence (models/multitask.py:264-269) ------------------
     def encode(self, queries, query_length):
         """Defers the work: the fused kernel sequence runs in rank_document, which needs the documents.
@@ -296,6 +299,11 @@ def _tgt2src_table(module, tgt_dict, src_dict, device, tgt_vocab_size):
         cache = (key, m.to(device))
         module.__dict__['_tgt2src_cache'] = cache
     return cache[1]
+
+
+_NO_TRAINING = ('%s.forward() is the training entry point of the reference (ranking + suggestion losses, '
+                'models/multitask.py:161-223): the libcair training step exists for the stand-alone MatchTensor and DRMM rankers '
+                'only.  Scoring and suggestion decoding run through encode() / rank_document() / decode().')
 
 
 class _SessionDecoderMixin:
@@ -411,6 +419,9 @@ class MNSRF(_SessionDecoderMixin, _CairModule):
         h = self.__dict__.get('_cair_handle')
         if h is not None:
             lib.check(lib.load().cair_mnsrf_poll_error(h, torch.cuda.current_stream().cuda_stream))
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError(_NO_TRAINING % 'MNSRF')
 
     # -- the reference's predict-time call sequence (models/multitask.py:270-276) --
     def encode(self, source_rep, source_len):
