@@ -349,18 +349,18 @@ def other_configs(run, args, peaks):
         del net
         torch.cuda.empty_cache()
 
-    def hbm_roof(kernel, bytes_per_pair):
+    def hbm_roof(kernel, bytes_per_pair, captured=False):
         def f(pairs, ms, st):
             ach = bytes_per_pair * pairs / (ms / 1e3) / 1e9
-            tr, src = traffic_for(kernel)
+            tr, src = traffic_for(kernel) if captured else (None, None)   # only where the committed capture is of THIS workload
             return dict(kernel=kernel, bound='hbm', achieved=ach, peak=hbm_peak, unit='GB/s', frac=ach / hbm_peak,
                         traffic=tr, bytes_per_pair=bytes_per_pair, note='whole step (one fused kernel chain) against the measured copy bandwidth')
         return f
 
-    def tensor_roof(kernel, mflop_ref_per_pair):
+    def tensor_roof(kernel, mflop_ref_per_pair, captured=False):
         def f(pairs, ms, st):
             ach = mflop_ref_per_pair * 1e6 * pairs / (ms / 1e3) / 1e12
-            tr, src = traffic_for(kernel)
+            tr, src = traffic_for(kernel) if captured else (None, None)   # only where the committed capture is of THIS workload
             cand = [k for k in st if k not in ('begin', 'end')]
             top = max(cand, key=lambda k: st[k]) if cand else None
             return dict(kernel=kernel, bound='tensor', achieved=ach, peak=tf_peak, unit='TFLOP/s', frac=ach / tf_peak, traffic=tr,
@@ -381,7 +381,7 @@ def other_configs(run, args, peaks):
     ranker_case('esm E=300 (cfg3 shape)', dict(model='esm', emsize=300, src_vocab_size=131072), 256, 10, 20, 200, 10,
                 hbm_roof('esm_kernel', bpp_fp32(300, 20, 200, 10)))
     ranker_case('drmm cfg3', dict(model='drmm', emsize=300, src_vocab_size=131072, dropout_emb=0.2, nbins=5), 256, 10, 20, 200, 10,
-                hbm_roof('drmm_tc_kernel', bpp_fp32(300, 20, 200, 10)))
+                hbm_roof('drmm_tc_kernel', bpp_fp32(300, 20, 200, 10), captured=True))
     for n in (10, 50, 100, 500):
         ranker_case('duet cfg5 N=%d' % n, DUET_CFG, 32, n, 20, 200, 10 if n <= 100 else 4, tensor_roof('gemm_tc_kernel', 145.8))
 
@@ -407,7 +407,7 @@ def other_configs(run, args, peaks):
              pairs_per_s=total / (ms / 1e3), ms_per_step=ms, n_gpus=world, scaling='weak',
              parallelism='session-parallel x%d: %d sessions per GPU, one all-gather of scores per step' % (world, Bc),
              steps=10, stages_ms={k: round(v, 4) for k, v in st.items() if k != 'begin'})
-    e['roofline'] = tensor_roof('rnn_tc_kernel', 205.0)(Bc * S * Nc, ms, st)
+    e['roofline'] = tensor_roof('rnn_tc_kernel', 205.0, captured=True)(Bc * S * Nc, ms, st)
     out.append(e)
     del net
     torch.cuda.empty_cache()
