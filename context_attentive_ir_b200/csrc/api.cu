@@ -308,6 +308,14 @@ int32_t cair_mt_create(const cair_mt_weights* w, int32_t device, cair_handle** o
   return rc;
 }
 
+int32_t cair_mt_add_encoder_layer(cair_handle* h, int32_t side, const cair_lstm_dir* fwd, const cair_lstm_dir* rev) {
+  if (!h || h->model != CAIR_MODEL_MT) return fail(CAIR_ERR_BAD_ARG, "mt_add_encoder_layer: not a match-tensor handle");
+  DeviceGuard g(h->device);
+  CAIR_TRY(mt_add_encoder_layer(h->own, &h->mt, side, fwd, rev, 0));
+  if (cudaStreamSynchronize(0) != cudaSuccess) return fail(CAIR_ERR_CUDA, "mt_add_encoder_layer: %s", cudaGetErrorString(cudaGetLastError()));
+  return CAIR_OK;
+}
+
 int32_t cair_mt_set_debug(cair_handle* h, float* enc_q, float* enc_d) {
   if (!h || h->model != CAIR_MODEL_MT) return fail(CAIR_ERR_BAD_ARG, "mt_set_debug: not a match-tensor handle");
   h->mt.dbg_enc_q = enc_q, h->mt.dbg_enc_d = enc_d;

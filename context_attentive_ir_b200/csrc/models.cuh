@@ -91,7 +91,15 @@ struct MtState {
   cudaStream_t side = nullptr;            // query-side work runs here, forked/joined with events
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   float *dbg_enc_q = nullptr, *dbg_enc_d = nullptr;
+  // stacked encoder layers 1.. (rnn_encoder.py:45-53,92-113; use_last: only the top layer's bank is consumed): dense input of
+  // width H, h = H / dirs per direction.  Side 0 = query encoder, 1 = document encoder.
+  static constexpr int MAX_EXTRA = 3;
+  int nextra[2] = {0, 0};
+  LstmPack xl[2][MAX_EXTRA]{};
+  RnnTcPack xrt[2][MAX_EXTRA]{};
+  int rnn_type = 0, dirs = 1;
 };
+int32_t mt_add_encoder_layer(Owned& own, MtState* st, int side, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, cudaStream_t s);
 int32_t mt_create_state(Owned& own, const cair_mt_weights& w, MtState* st, cudaStream_t s);
 // Phases of one forward, for the cross-batch software pipeline of cair_ranker_submit_host: MT_ALL = everything on `s`;
 // MT_ENCODE = query side (forked stream) + document encoder + channel projection / operand image; MT_INTERACT = the

@@ -341,6 +341,7 @@ int32_t mt_repack(const cair_mt_weights& w, MtPack* p, cudaStream_t s) {
 int32_t mt_create_state(Owned& own, const cair_mt_weights& w, MtState* st, cudaStream_t s) {
   const int dirs = w.bidirectional ? 2 : 1;
   st->V = w.vocab, st->E = w.emsize, st->F = w.featsize, st->Hq = w.nhid_query, st->Hd = w.nhid_doc, st->C = w.nchannels;
+  st->rnn_type = w.rnn_type, st->dirs = dirs;
   if (!w.linear_projection.w || !w.linear_projection.b || !w.query_projection.w || !w.query_projection.b ||
       !w.document_projection.w || !w.document_projection.b || !w.alpha || !w.conv1.w || !w.conv2.w || !w.conv3.w ||
       !w.conv1.b || !w.conv2.b || !w.conv3.b || !w.conv.w || !w.conv.b || !w.output.w || !w.output.b)
@@ -376,6 +377,44 @@ int32_t mt_create_state(Owned& own, const cair_mt_weights& w, MtState* st, cudaS
   return CAIR_OK;
 }
 
+int32_t mt_add_encoder_layer(Owned& own, MtState* st, int side, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, cudaStream_t s) {
+  if (side < 0 || side > 1 || !fwd) return fail(CAIR_ERR_BAD_ARG, "mt_add_encoder_layer: side must be 0 (query) or 1 (document)");
+  if ((st->dirs == 2) != (rev != nullptr)) return fail(CAIR_ERR_BAD_ARG, "mt_add_encoder_layer: directions differ from layer 0");
+  if (st->nextra[side] >= MtState::MAX_EXTRA) return fail(CAIR_ERR_UNSUPPORTED, "mt_add_encoder_layer: at most 4 stacked layers");
+  const int H = side ? st->Hd : st->Hq, h = H / st->dirs, i = st->nextra[side];
+  CAIR_TRY(lstm_pack(own, fwd, rev, H, h, &st->xl[side][i], s, st->rnn_type));
+  if (rnn_tc_supported(H, h)) CAIR_TRY(rnn_tc_pack(own, fwd, rev, H, h, st->rnn_type, &st->xrt[side][i], s));
+  st->nextra[side] = i + 1;
+  return CAIR_OK;
+}
+
+// Layers 1.. of a stacked encoder over the dense bank of the layer below (the dropout between layers is the identity in
+// eval mode; pad rows of a bank are zero and are never read by the packed-sequence recurrence).  Returns the top bank.
+static int32_t mt_extra_layers(const MtState& st, int side, float*& bank, float*& other, float* pre, const int64_t* len, int n,
+                               int L, int* err, cudaStream_t s, const char* tag) {
+  const int H = side ? st.Hd : st.Hq;
+  for (int i = 0; i < st.nextra[side]; ++i) {
+    const RnnTcPack& rt = st.xrt[side][i];
+    if (rt.wimg && st.impl != MT_IMPL_FP32 && g_rnn_impl != RNN_IMPL_FP32)
+      CAIR_TRY(rnn_tc_run(rt, gemm_dense(bank, H), len, n, L, other, nullptr, nullptr, pre, err, s, tag));
+    else
+      CAIR_TRY(lstm_run(st.xl[side][i], gemm_dense(bank, H), len, n, L, other, nullptr, nullptr, pre, err, s, tag));
+    float* t = bank;
+    bank = other, other = t;
+  }
+  return CAIR_OK;
+}
+static size_t mt_extra_ws_floats(const MtState& st, int side, int64_t n, int L) {
+  size_t m = 0;
+  for (int i = 0; i < st.nextra[side]; ++i) {
+    const RnnTcPack& rt = st.xrt[side][i];
+    const size_t f = (rt.wimg && st.impl != MT_IMPL_FP32 && g_rnn_impl != RNN_IMPL_FP32) ? rnn_tc_workspace_floats(rt, n, L)
+                                                                                         : lstm_workspace_floats(st.xl[side][i], n, L);
+    m = f > m ? f : m;
+  }
+  return m;
+}
+
 // engine of one encoder under the process-wide g_rnn_impl switch (see common.cuh)
 static bool mt_uses_cluster_kernel(const RnnTcPack& rt, const LstmTcPack& r1) {
   if (!rt.wimg) return false;
@@ -401,6 +440,10 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
   float* enc_d = ws.take<float>((size_t)pc * Ld * st.Hd);
   float* cq = ws.take<float>((size_t)nq * Lq * st.C);
   float* cd = ws.take<float>((size_t)pc * Ld * st.C);
+  float* enc_q2 = st.nextra[0] ? ws.take<float>((size_t)nq * Lq * st.Hq) : nullptr;
+  float* enc_d2 = st.nextra[1] ? ws.take<float>((size_t)pc * Ld * st.Hd) : nullptr;
+  float* pre_xq = st.nextra[0] ? ws.take<float>(mt_extra_ws_floats(st, 0, nq, Lq)) : nullptr;
+  float* pre_xd = st.nextra[1] ? ws.take<float>(mt_extra_ws_floats(st, 1, pc, Ld)) : nullptr;
   const bool use_tc = st.impl != MT_IMPL_FP32 && mt_tc_supported(st.pack, Lq, Ld);
   float* T = nullptr;
   uint8_t* timg = nullptr;
@@ -446,6 +489,7 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
   else
     CAIR_TRY(lstm_run(st.enc_q, gemm_gather(st.folded, st.V, st.F, qs, 1, 1, 1, err), qlen + qb, (int)nq, Lq, enc_q,
                       nullptr, nullptr, pre_q, err, sq, st.side ? nullptr : "query_recurrence"));
+  CAIR_TRY(mt_extra_layers(st, 0, enc_q, enc_q2, pre_xq, qlen + qb, (int)nq, Lq, err, sq, st.side ? nullptr : "query_recurrence_upper"));
   if (st.dbg_enc_q)
     CAIR_CUDA(cudaMemcpyAsync(st.dbg_enc_q + (size_t)qb * Lq * st.Hq, enc_q, (size_t)nq * Lq * st.Hq * sizeof(float),
                               cudaMemcpyDeviceToDevice, sq));
@@ -462,6 +506,7 @@ int32_t mt_forward(const MtState& st, const int64_t* q, const int64_t* qlen, con
   else
     CAIR_TRY(lstm_run(st.enc_d, gemm_gather(st.folded, st.V, st.F, ds, 1, 1, 1, err), dlen + pb, (int)pc, Ld, enc_d,
                       nullptr, nullptr, pre_d, err, s, "doc_recurrence"));
+  CAIR_TRY(mt_extra_layers(st, 1, enc_d, enc_d2, pre_xd, dlen + pb, (int)pc, Ld, err, s, "doc_recurrence_upper"));
   if (st.dbg_enc_d)
     CAIR_CUDA(cudaMemcpyAsync(st.dbg_enc_d + (size_t)pb * Ld * st.Hd, enc_d, (size_t)pc * Ld * st.Hd * sizeof(float),
                               cudaMemcpyDeviceToDevice, s));

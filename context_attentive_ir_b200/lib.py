@@ -35,6 +35,7 @@ PROTOTYPES = {
     'cair_esm_create': (i32, [C.POINTER(_abi.EsmWeights), i32, C.POINTER(vp)]),
     'cair_mt_create': (i32, [C.POINTER(_abi.MtWeights), i32, C.POINTER(vp)]),
     'cair_mt_set_debug': (i32, [vp, vp, vp]),
+    'cair_mt_add_encoder_layer': (i32, [vp, i32, vp, vp]),
     'cair_mt_set_impl': (i32, [vp, i32]),
     'cair_allgather_scores': (i32, [vp, i64, vp, vp, i32, i32, C.c_uint32, vp]),
     'cair_ranker_set_gather': (i32, [vp, vp, vp, vp, i32, i32, i64]),

@@ -463,8 +463,8 @@ class MatchTensor(_Ranker):
         self.conv3 = nn.Conv2d(args.nchannels + 1, args.nfilters, (3, 7), padding=(1, 3))
         self.conv = nn.Conv2d(args.nfilters * 3, args.match_filter_size, (1, 1))
         self.output = nn.Linear(args.match_filter_size, 1)
-        if args.nlayers != 1:
-            raise NotImplementedError('libcair implements single-layer encoders (neuroir/hyparam.py:88-100 uses 1)')
+        if not 1 <= args.nlayers <= 4:
+            raise NotImplementedError('libcair stacks at most 4 encoder layers (neuroir/hyparam.py:88-100 uses 1)')
 
     def _cfg(self):
         a = self.args
@@ -514,6 +514,8 @@ class MatchTensor(_Ranker):
         self._release_trainer()
 
     def _train_forward(self, batch_queries, query_len, batch_docs, doc_len):
+        if self.args.nlayers != 1:
+            raise NotImplementedError('MatchTensor: the libcair training step covers single-layer encoders; score under .eval()')
         q = self._ids(batch_queries, 'batch_queries')
         d = self._ids(batch_docs, 'batch_docs')
         ql = self._ids(query_len, 'query_len').to(q.device)
@@ -538,6 +540,14 @@ class MatchTensor(_Ranker):
         impl = self.__dict__.get('_cair_impl')
         if impl is not None:
             lib.check(lib.load().cair_mt_set_impl(handle, impl))
+        # stacked encoders (rnn_encoder.py:45-53): layers 1.. are appended to the handle, which packs (copies) them
+        keep = []
+        get = _ptr_getter(self, keep)
+        for side, enc in enumerate(('query_encoder', 'document_encoder')):
+            for k in range(1, self.args.nlayers):
+                fwd = _abi._lstm(get, '%s.rnns.%d' % (enc, k))
+                rev = C.byref(_abi._lstm(get, '%s.rnns.%d' % (enc, k), '_reverse')) if self.args.bidirection else None
+                lib.check(lib.load().cair_mt_add_encoder_layer(handle, side, C.byref(fwd), rev))
 
 
 class _MtTrainFn(torch.autograd.Function):

@@ -172,6 +172,11 @@ typedef struct {
 } cair_mt_weights;
 
 CAIR_API int32_t cair_mt_create(const cair_mt_weights* w, int32_t device, cair_handle** out);
+/* Stacked encoders (neuroir/encoders/rnn_encoder.py:45-53 builds `nlayers` single-layer RNNs, :92-113 feeds each the bank of
+ * the one below; Match-Tensor keeps use_last = True, so only the top bank is consumed): appends layer `rnns.<k>` (k = 1, 2, 3 in
+ * call order) to the query (side 0) or document (side 1) encoder.  Its input width is the side's hidden size; `rev` is NULL for a
+ * unidirectional encoder.  Call after cair_mt_create and before the first forward; the weights are packed (copied) here. */
+CAIR_API int32_t cair_mt_add_encoder_layer(cair_handle* h, int32_t side, const cair_lstm_dir* fwd, const cair_lstm_dir* rev);
 /* Stage outputs for parity tests (any may be NULL): encoder memory banks
  * enc_q [B,Lq,Hq], enc_d [B*N,Ld,Hd] as RNNEncoder returns them (mtensor.py:93-94). */
 CAIR_API int32_t cair_mt_set_debug(cair_handle* h, float* enc_q, float* enc_d);

@@ -180,9 +180,33 @@ ORA_API int cair_oracle_esm(const cair_esm_weights* w, const int64_t* q, const i
 }
 
 /* ---- Match-Tensor (rankers/mtensor.py:62-131; exact match :144-158) ----------------------- */
+/* Stacked encoders (encoders/rnn_encoder.py:45-53, :92-113): layer k >= 1 reads the memory bank of layer k-1 (the dropout between
+ * them is the identity in eval mode; use_last = True keeps the top bank only).  xq / xd: [nextra][fwd, rev] weights of the
+ * query / document encoder's layers 1..nextra (rev ignored when unidirectional). */
+static int oracle_rnn_stack(int rnn_type, float** bank, const int64_t* len, int n, int L, int H, int dirs,
+                            const cair_lstm_dir* extra, int nextra) {
+  for (int k = 0; k < nextra; ++k) {
+    float* next = (float*)malloc(sizeof(float) * (size_t)n * L * H);
+    int rc = oracle_rnn(rnn_type, *bank, len, n, L, H, H / dirs, &extra[2 * k], dirs == 2 ? &extra[2 * k + 1] : NULL, next, NULL, NULL);
+    free(*bank);
+    *bank = next;
+    if (rc != CAIR_OK) return rc;
+  }
+  return CAIR_OK;
+}
+
+ORA_API int cair_oracle_mt_stacked(const cair_mt_weights* w, const cair_lstm_dir* xq, const cair_lstm_dir* xd, int nextra,
+                                   const int64_t* q, const int64_t* qlen, const int64_t* d, const int64_t* dlen, int B, int N,
+                                   int Lq, int Ld, float* scores, float* enc_q_out, float* enc_d_out);
 ORA_API int cair_oracle_mt(const cair_mt_weights* w, const int64_t* q, const int64_t* qlen,
                            const int64_t* d, const int64_t* dlen, int B, int N, int Lq, int Ld,
                            float* scores, float* enc_q_out, float* enc_d_out) {
+  return cair_oracle_mt_stacked(w, NULL, NULL, 0, q, qlen, d, dlen, B, N, Lq, Ld, scores, enc_q_out, enc_d_out);
+}
+
+ORA_API int cair_oracle_mt_stacked(const cair_mt_weights* w, const cair_lstm_dir* xq, const cair_lstm_dir* xd, int nextra,
+                                   const int64_t* q, const int64_t* qlen, const int64_t* d, const int64_t* dlen, int B, int N,
+                                   int Lq, int Ld, float* scores, float* enc_q_out, float* enc_d_out) {
   if (w->rnn_type != CAIR_RNN_LSTM && w->rnn_type != CAIR_RNN_GRU) return CAIR_ERR_UNSUPPORTED;
   int E = w->emsize, F = w->featsize, C = w->nchannels, nf = w->nfilters,
       M = w->match_filter_size;
@@ -212,6 +236,8 @@ ORA_API int cair_oracle_mt(const cair_mt_weights* w, const int64_t* q, const int
                     dirs == 2 ? &w->doc_rev : NULL, hd_, NULL, NULL);
   free(pq);
   free(pd);
+  if (rc == CAIR_OK) rc = oracle_rnn_stack(w->rnn_type, &hq_, qlen, B, Lq, Hq, dirs, xq, nextra);
+  if (rc == CAIR_OK) rc = oracle_rnn_stack(w->rnn_type, &hd_, dlen, (int)BN, Ld, Hd, dirs, xd, nextra);
   if (rc != CAIR_OK) {
     free(hq_);
     free(hd_);

@@ -169,11 +169,11 @@ def _ref_metrics(scores, labels):
                 metric_p5=np.float64(precision_at_k(pred, lab, 5)))
 
 
-def gen_mt(name, seed, B, N, Lq, Ld, E, V, F, Hq, Hd, C, nf, mfs, rnn_type='LSTM', metrics=False, **kw):
+def gen_mt(name, seed, B, N, Lq, Ld, E, V, F, Hq, Hd, C, nf, mfs, rnn_type='LSTM', metrics=False, nlayers=1, **kw):
     from neuroir.rankers.mtensor import MatchTensor
     torch.manual_seed(1013)
     cfg = dict(model='match_tensor', emsize=E, src_vocab_size=V, dropout_emb=0.2, rnn_type=rnn_type,
-               bidirection=True, nlayers=1, dropout_rnn=0.2, featsize=F, nhid_query=Hq,
+               bidirection=True, nlayers=nlayers, dropout_rnn=0.2, featsize=F, nhid_query=Hq,
                nhid_doc=Hd, nchannels=C, nfilters=nf, match_filter_size=mfs)
     net = MatchTensor(_ns(**{k: v for k, v in cfg.items() if k != 'model'})).eval()
     batch = synth.ranker_batch(seed, B, N, Lq, Ld, V, **kw)
@@ -497,6 +497,11 @@ def main():
            mfs=20, variable=False)
     gen_mt('mt_gru', 25, B=2, N=3, Lq=9, Ld=31, E=32, V=150, F=12, Hq=20, Hd=28, C=10, nf=6, mfs=8, rnn_type='GRU',
            bos_eos=True, overlap=0.15)
+    # stacked encoders (--nlayers, encoders/rnn_encoder.py:45-53, :92-113): 2 LSTM layers at the cfg2 hidden sizes, 3 GRU layers
+    gen_mt('mt_2layer', 35, B=2, N=3, Lq=12, Ld=50, E=48, V=300, F=40, Hq=128, Hd=128, C=50, nf=6, mfs=20, nlayers=2,
+           bos_eos=True, overlap=0.1)
+    gen_mt('mt_3layer_gru', 36, B=2, N=3, Lq=9, Ld=31, E=32, V=150, F=12, Hq=20, Hd=28, C=10, nf=6, mfs=8, rnn_type='GRU',
+           nlayers=3, bos_eos=True, overlap=0.15)
     # >= 64 queries with the reference's own MAP / MRR / P@k of the reference scores (metric parity of model scores)
     gen_mt('mt_map64', 27, B=64, N=10, Lq=8, Ld=24, E=32, V=300, F=8, Hq=16, Hd=24, C=10, nf=6, mfs=8, bos_eos=True,
            overlap=0.1, metrics=True)

@@ -77,7 +77,18 @@ def run_ranker(cfg, sd, q, qlen, d, dlen, want=()):
     elif model == 'match_tensor':
         eq = np.zeros((B, Lq, cfg['nhid_query']), np.float32) if 'enc_queries' in want else None
         ed = np.zeros((B * N, Ld, cfg['nhid_doc']), np.float32) if 'enc_docs' in want else None
-        _check(L.cair_oracle_mt(C.byref(w), qp, qlp, dp, dlp, B, N, Lq, Ld, _f32(scores), _f32(eq), _f32(ed)), 'mt')
+        nx = int(cfg.get('nlayers', 1)) - 1
+        get, bi = host_getter(sd), bool(cfg['bidirection'])
+        extra = []
+        for enc in ('query_encoder', 'document_encoder'):      # layers 1.. of the stacked encoders: [k][fwd, rev]
+            arr = (_abi.LstmDir * max(2 * nx, 1))()
+            for k in range(nx):
+                arr[2 * k] = _abi._lstm(get, '%s.rnns.%d' % (enc, k + 1))
+                if bi:
+                    arr[2 * k + 1] = _abi._lstm(get, '%s.rnns.%d' % (enc, k + 1), '_reverse')
+            extra.append(arr)
+        _check(L.cair_oracle_mt_stacked(C.byref(w), extra[0], extra[1], nx, qp, qlp, dp, dlp, B, N, Lq, Ld, _f32(scores),
+                                        _f32(eq), _f32(ed)), 'mt')
         out.update(enc_queries=eq, enc_docs=ed)
     elif model == 'drmm':
         hist = np.zeros((B * N, Lq, 5), np.int32) if 'hist' in want else None

@@ -65,7 +65,7 @@ def test_weight_struct_layout_matches_oracle_view():
 
 def test_unsupported_configs_raise():
     cfg, _, _, _ = ol.load_golden('mt_tiny')
-    bad = dict(cfg, nlayers=2)
+    bad = dict(cfg, nlayers=5)     # stacked encoders: 1..4 layers
     with pytest.raises(NotImplementedError):
         helpers.build_module(bad)
     cfgd, _, _, _ = ol.load_golden('duet_tiny')

@@ -137,11 +137,12 @@ def test_reference_multitask_wrapper_builds_b200_mnsrf_and_mmt(name, ref_cls):
     importlib.reload(ref_mt)
 
 
-def test_two_layer_encoder_is_rejected_through_the_reference_config_path():
-    """`--nlayers 2` travels through the unmodified neuroir.config (add_model_args -> get_model_args) into Ranker.__init__;
-    the B200 Match-Tensor implements single-layer encoders (the reference's hyparam dicts fix nlayers = 1,
-    neuroir/hyparam.py:88-100) and must refuse loudly instead of scoring with one layer.  hyparam's arch dict overrides the
-    CLI flag, so the two-layer request is injected where get_model_args leaves it: on the Namespace."""
+def test_stacked_encoders_through_the_reference_config_path():
+    """`--nlayers` travels through the unmodified neuroir.config (add_model_args -> get_model_args) into Ranker.__init__.
+    hyparam's arch dict overrides the CLI flag (neuroir/hyparam.py:88-100 fixes nlayers = 1), so a stacked
+    request is injected where get_model_args leaves it: on the Namespace.  The B200 Match-Tensor builds 1..4 layers with the
+    reference's state_dict keys (`rnns.<k>.*`; scores: tests/test_parity_gpu.py mt_2layer / mt_3layer_gru) and refuses
+    more loudly instead of truncating."""
     ref_ranker = _import_reference()
     import importlib
     stock = importlib.reload(ref_ranker)
@@ -153,11 +154,20 @@ def test_two_layer_encoder_is_rejected_through_the_reference_config_path():
     args = parser.parse_args(['--model_type', 'match_tensor', '--nlayers', '2'])
     margs = config.get_model_args(args)
     assert margs.nlayers == 1          # hyparam.py wins over the flag ...
+    ref_keys = set(stock.Ranker(margs, _Dict((i, i) for i in range(50))).network.state_dict())
     import context_attentive_ir_b200.integration as integ
     integ.install()
     vocab = _Dict((i, i) for i in range(50))
     stock.Ranker(margs, vocab)         # ... so the stock path builds
-    margs.nlayers = 2                  # a caller that really asks for two layers is refused, not silently truncated
-    with pytest.raises(NotImplementedError, match='single-layer'):
+    margs.nlayers = 2
+    importlib.reload(ref_ranker)
+    two_ref = set(stock.Ranker(margs, vocab).network.state_dict())
+    integ.install()
+    two = stock.Ranker(margs, vocab).network
+    assert type(two).__module__.startswith('context_attentive_ir_b200')
+    assert set(two.state_dict()) == two_ref and two_ref > ref_keys
+    assert 'document_encoder.rnns.1.weight_ih_l0_reverse' in two_ref
+    margs.nlayers = 5
+    with pytest.raises(NotImplementedError, match='at most 4'):
         stock.Ranker(margs, vocab)
     importlib.reload(ref_ranker)

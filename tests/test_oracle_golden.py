@@ -19,7 +19,7 @@ def test_esm(name):
     assert _max_rel(o['scores'], outs['scores']) < 1e-5
 
 
-@pytest.mark.parametrize('name', ['mt_tiny', 'mt_fullpad', 'mt_stock', 'mt_cfg2arch', 'mt_gru'])
+@pytest.mark.parametrize('name', ['mt_tiny', 'mt_fullpad', 'mt_stock', 'mt_cfg2arch', 'mt_gru', 'mt_2layer', 'mt_3layer_gru'])
 def test_match_tensor(name):
     cfg, ins, sd, outs = ol.load_golden(name)
     o = ol.run_ranker(cfg, sd, ins['q'], ins['qlen'], ins['d'], ins['dlen'], want=('enc_queries', 'enc_docs'))

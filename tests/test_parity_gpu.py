@@ -68,7 +68,7 @@ def test_tcgen05_conventions_selftest():
 
 
 @pytest.mark.parametrize('impl', ['tc', 'tc_split', 'fp32'])
-@pytest.mark.parametrize('name', ['mt_tiny', 'mt_fullpad', 'mt_stock', 'mt_cfg2arch', 'mt_gru'])
+@pytest.mark.parametrize('name', ['mt_tiny', 'mt_fullpad', 'mt_stock', 'mt_cfg2arch', 'mt_gru', 'mt_2layer', 'mt_3layer_gru'])
 def test_match_tensor_golden(name, impl):
     cfg, ins, sd, outs = ol.load_golden(name)
     net = helpers.build_module(cfg, sd, DEV).set_interaction_impl(impl)
