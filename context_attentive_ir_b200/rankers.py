@@ -231,7 +231,7 @@ class _Ranker(_CairModule):
         return scores
 
     def _train_forward(self, batch_queries, query_len, batch_docs, doc_len):
-        raise NotImplementedError('%s: the libcair training step exists for MatchTensor and DRMM only; score under .eval()'
+        raise NotImplementedError('%s: the libcair training step exists for MatchTensor, DRMM and ESM only; score under .eval()'
                                   % type(self).__name__)
 
     @staticmethod
@@ -314,6 +314,48 @@ class ESM(_Ranker):
 
     def _create(self, w, device, out):
         return lib.load().cair_esm_create(w, device, out)
+
+    def _train_forward(self, batch_queries, query_len, batch_docs, doc_len):
+        """Train mode (Ranker.update): cair_esm_train_forward / cair_esm_train_backward on the live embedding table."""
+        q = self._ids(batch_queries, 'batch_queries')
+        d = self._ids(batch_docs, 'batch_docs')
+        table = self.word_embeddings.word_lut.weight
+        if not table.is_cuda or table.dtype != torch.float32 or not table.is_contiguous():
+            raise RuntimeError('ESM training needs a contiguous fp32 CUDA embedding table')
+        return _EsmTrainFn.apply(q, d, table)
+
+
+class _EsmTrainFn(torch.autograd.Function):
+    """Train-mode ESM scores through libcair with libcair's backward into the embedding table (skipped under --fix_embeddings)."""
+
+    @staticmethod
+    def forward(ctx, q, d, table):
+        dev = q.device
+        L = lib.load()
+        B, Lq = q.shape
+        _, N, Ld = d.shape
+        V, E = table.shape
+        nbytes = C.c_size_t()
+        lib.check(L.cair_esm_train_workspace_bytes(E, B, N, C.byref(nbytes)))
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        scores = torch.empty(B, N, dtype=torch.float32, device=dev)
+        lib.check(L.cair_esm_train_forward(table.data_ptr(), V, E, q.data_ptr(), d.data_ptr(), B, N, Lq, Ld, scores.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+        ctx.args = (q, d, ws, scores, table.shape, table.requires_grad)
+        return scores.clone()
+
+    @staticmethod
+    def backward(ctx, dscores):
+        q, d, ws, scores, shape, req = ctx.args
+        dev = q.device
+        B, Lq = q.shape
+        _, N, Ld = d.shape
+        dtable = torch.zeros(shape, dtype=torch.float32, device=dev) if req else None
+        dscores = dscores.contiguous().float()
+        lib.check(lib.load().cair_esm_train_backward(shape[0], shape[1], q.data_ptr(), d.data_ptr(), B, N, Lq, Ld, scores.data_ptr(),
+                                                     dscores.data_ptr(), dtable.data_ptr() if req else None, ws.data_ptr(),
+                                                     ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+        return None, None, dtable
 
 
 class DSSM(_Ranker):

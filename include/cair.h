@@ -479,6 +479,20 @@ CAIR_API int32_t cair_drmm_train_backward(const cair_drmm_weights* w, const cair
                                  int32_t N, int32_t Lq, int32_t Ld, float p_drop, uint64_t seed, const float* dscores,
                                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* Training step of ESM (neuroir/rankers/esm.py:19-45 under Ranker.update, models/ranker.py:192-230).  The embedding table is
+ * the model's only parameter.  forward: train-mode scores [B,N] (ESM has no dropout: the same arithmetic as the scoring path,
+ * normalise first, then dot) and, in the workspace, the mean vectors and norms.  backward: dscores [B,N] -> dtable [V,E]
+ * ACCUMULATED (atomic adds; zero it first): the cosine's derivative per pair, summed over the N documents of a query, divided
+ * by the padded length and scattered to the rows of the non-PAD tokens (row 0 untouched, nn.Embedding padding_idx).
+ * dtable NULL = fixed embeddings (nothing to do).  `scores` in backward are the forward's. */
+CAIR_API int32_t cair_esm_train_workspace_bytes(int32_t emsize, int32_t B, int32_t N, size_t* bytes);
+CAIR_API int32_t cair_esm_train_forward(const float* table, int32_t vocab, int32_t emsize, const int64_t* q, const int64_t* d, int32_t B,
+                               int32_t N, int32_t Lq, int32_t Ld, float* scores, void* workspace, size_t workspace_bytes,
+                               void* stream);
+CAIR_API int32_t cair_esm_train_backward(int32_t vocab, int32_t emsize, const int64_t* q, const int64_t* d, int32_t B, int32_t N,
+                                int32_t Lq, int32_t Ld, const float* scores, const float* dscores, float* dtable, void* workspace,
+                                size_t workspace_bytes, void* stream);
+
 /* ---- MNSRF ranking path ---------------------------------------------------
  * Replaces MNSRF.encode + MNSRF.rank_document (neuroir/multitask/mnsrf.py:61-162) as Multitask.predict calls them
  * (neuroir/models/multitask.py:270-276).  Weights are copied into the handle: table = embedder.word_embeddings...weight
