@@ -822,6 +822,119 @@ static void drmm_train_layout(Arena& a, int E, int B, int N, int Lq, int Ld, Drm
   o->hist = a.take<int32_t>((size_t)B * N * Lq * 5);
 }
 
+// ------------------------------------------------------------------------------------------------
+// DSSM (dssm.py:33-63) in train mode: x[r, e] = max_t table[id_t, e] * mask(t, e) with the arg-max position kept for the
+// backward; the two Linear + Tanh layers per side are small dense GEMMs; cosine as in ESM.
+struct DssmTrainWs {
+  float *x, *h1, *y, *nrm, *dy, *dh1, *dx;   // rows: B queries then B*N documents
+  int* arg;                                    // [R, E] arg-max token position
+  float *w0t_q, *w2t_q, *w0t_d, *w2t_d;        // transposed weights for the input gradients
+  int* err;
+};
+static void dssm_train_layout(Arena& a, int E, int H, int O, int B, int N, DssmTrainWs* o) {
+  const size_t R = (size_t)B + (size_t)B * N;
+  o->x = a.take<float>(R * E), o->h1 = a.take<float>(R * H), o->y = a.take<float>(R * O), o->nrm = a.take<float>(R);
+  o->dy = a.take<float>(R * O), o->dh1 = a.take<float>(R * H), o->dx = a.take<float>(R * E);
+  o->arg = a.take<int>(R * E);
+  o->w0t_q = a.take<float>((size_t)E * H), o->w2t_q = a.take<float>((size_t)H * O);
+  o->w0t_d = a.take<float>((size_t)E * H), o->w2t_d = a.take<float>((size_t)H * O);
+  o->err = a.take<int>(4);
+}
+
+// one CTA per row; mask element index = (token row of the batch: queries first) * E + e, as embed_drop_kernel
+__global__ void __launch_bounds__(256) dssm_train_pool_kernel(const float* __restrict__ table, const int64_t* __restrict__ q,
+                                                              const int64_t* __restrict__ d, int V, int E, int B, int Lq, int Ld,
+                                                              float p, uint64_t seed, float* __restrict__ x, int* __restrict__ arg,
+                                                              int* err) {
+  const int64_t r = blockIdx.x;
+  const bool isq = r < B;
+  const int L = isq ? Lq : Ld;
+  const int64_t* ids = isq ? q + r * Lq : d + (r - B) * Ld;
+  const int64_t tok0 = isq ? r * Lq : (int64_t)B * Lq + (r - B) * Ld;
+  const float inv = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  for (int e = threadIdx.x; e < E; e += 256) {
+    float best = -INFINITY;
+    int bt = 0;
+    for (int t = 0; t < L; ++t) {
+      const int64_t id = checked_id(ids[t], V, err);
+      const float v = table[id * E + e] * drop_scale(seed, (uint64_t)((tok0 + t) * E + e), p, inv);
+      if (v > best) best = v, bt = t;
+    }
+    x[r * E + e] = best;
+    arg[r * E + e] = bt;
+  }
+}
+
+__global__ void row_norm_kernel(const float* __restrict__ y, int O, int64_t R, float* __restrict__ nrm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= R) return;
+  float ss = 0.f;
+  for (int e = lane; e < O; e += 32) ss += y[r * O + e] * y[r * O + e];
+  ss = warp_sum(ss);
+  if (lane == 0) nrm[r] = fmaxf(sqrtf(ss), 1e-8f);
+}
+
+__global__ void cos_score_kernel(const float* __restrict__ y, const float* __restrict__ nrm, int O, int B, int N,
+                                 float* __restrict__ scores) {
+  const int lane = threadIdx.x & 31;
+  const int64_t p = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (p >= (int64_t)B * N) return;
+  const int64_t b = p / N;
+  const float* a = y + b * O;
+  const float* c = y + ((int64_t)B + p) * O;
+  const float na = nrm[b], nc = nrm[B + p];
+  float dot = 0.f;
+  for (int e = lane; e < O; e += 32) dot += (a[e] / na) * (c[e] / nc);
+  dot = warp_sum(dot);
+  if (lane == 0) scores[p] = dot;
+}
+
+// d(pre-activation of the last Tanh) for every row: the cosine's derivative (see esm_train_bwd_kernel) times 1 - y^2
+__global__ void __launch_bounds__(128) dssm_train_cos_bwd_kernel(const float* __restrict__ y, const float* __restrict__ nrm,
+                                                                 const float* __restrict__ scores, const float* __restrict__ dscores,
+                                                                 int O, int B, int N, float* __restrict__ dy) {
+  const int b = blockIdx.x;
+  const float* a = y + (size_t)b * O;
+  const float na = nrm[b];
+  for (int e = threadIdx.x; e < O; e += 128) {
+    const float ah = a[e] / na;
+    float da = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const int64_t p = (int64_t)b * N + n;
+      const float nc = nrm[B + p], s = scores[p], g = dscores[p];
+      const float cv = y[((size_t)B + p) * O + e], ch = cv / nc;
+      da += g * (na <= 1e-8f ? ch : (ch - s * ah)) / na;
+      dy[((size_t)B + p) * O + e] = g * (nc <= 1e-8f ? ah : (ah - s * ch)) / nc * (1.f - cv * cv);
+    }
+    dy[(size_t)b * O + e] = da * (1.f - a[e] * a[e]);
+  }
+}
+
+__global__ void tanh_bwd_kernel(float* __restrict__ dh, const float* __restrict__ h, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dh[i] *= 1.f - h[i] * h[i];
+}
+
+// d table[id of the arg-max token, e] += dx[r, e] * mask   (PAD: no gradient)
+__global__ void __launch_bounds__(256) dssm_train_scatter_kernel(const float* __restrict__ dx, const int* __restrict__ arg,
+                                                                 const int64_t* __restrict__ q, const int64_t* __restrict__ d, int V,
+                                                                 int E, int B, int Lq, int Ld, float p, uint64_t seed,
+                                                                 float* __restrict__ dtable) {
+  const int64_t r = blockIdx.x;
+  const bool isq = r < B;
+  const int64_t* ids = isq ? q + r * Lq : d + (r - B) * Ld;
+  const int64_t tok0 = isq ? r * Lq : (int64_t)B * Lq + (r - B) * Ld;
+  const float inv = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  for (int e = threadIdx.x; e < E; e += 256) {
+    const int t = arg[r * E + e];
+    const int64_t id = ids[t];
+    if (id <= 0 || id >= V) continue;
+    const float m = drop_scale(seed, (uint64_t)((tok0 + t) * E + e), p, inv);
+    if (m != 0.f) atomicAdd(dtable + id * E + e, dx[r * E + e] * m);
+  }
+}
+
 }  // namespace cair
 
 using namespace cair;
@@ -1126,5 +1239,94 @@ int32_t cair_mt_train_poll_error(cair_mt_trainer* h, void* ws, void* stream) {
   if (flags & ERRF_BAD_LENGTH) return fail(CAIR_ERR_BAD_ARG, "sequence length outside [1, L]");
   return CAIR_OK;
 }
+
+int32_t cair_dssm_train_workspace_bytes(int32_t emsize, int32_t nhid, int32_t nout, int32_t B, int32_t N, size_t* bytes) {
+  if (!bytes || emsize <= 0 || nhid <= 0 || nout <= 0 || B <= 0 || N <= 0) return fail(CAIR_ERR_BAD_ARG, "dssm_train_workspace_bytes: bad argument");
+  Arena a(nullptr, 0);
+  DssmTrainWs o;
+  dssm_train_layout(a, emsize, nhid, nout, B, N, &o);
+  *bytes = align_up(a.off) + 256;
+  return CAIR_OK;
+}
+
+int32_t cair_dssm_train_forward(const cair_dssm_weights* w, const int64_t* q, const int64_t* d, int32_t B, int32_t N, int32_t Lq,
+                                int32_t Ld, float p_drop, uint64_t seed, float* scores, void* ws, size_t ws_bytes, void* stream) {
+  if (!w || !q || !d || !scores || !ws || !w->table || !w->query_mlp0.w || !w->query_mlp0.b || !w->query_mlp2.w || !w->query_mlp2.b ||
+      !w->doc_mlp0.w || !w->doc_mlp0.b || !w->doc_mlp2.w || !w->doc_mlp2.b)
+    return fail(CAIR_ERR_BAD_ARG, "dssm_train_forward: null argument");
+  if (B <= 0 || N <= 0 || Lq <= 0 || Ld <= 0) return fail(CAIR_ERR_BAD_ARG, "dssm_train_forward: bad shape");
+  if (p_drop < 0.f || p_drop >= 1.f) return fail(CAIR_ERR_BAD_ARG, "dssm_train_forward: dropout must be in [0, 1)");
+  if ((uintptr_t)ws % 256) return fail(CAIR_ERR_WORKSPACE, "dssm_train_forward: workspace must be 256-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int E = w->emsize, H = w->nhid, O = w->nout;
+  Arena a(ws, ws_bytes);
+  DssmTrainWs o;
+  dssm_train_layout(a, E, H, O, B, N, &o);
+  if (!a.ok()) return fail(CAIR_ERR_WORKSPACE, "dssm_train_forward: workspace too small");
+  const int64_t P = (int64_t)B * N, R = B + P;
+  CAIR_CUDA(cudaMemsetAsync(o.err, 0, 4 * sizeof(int), s));
+  CAIR_LAUNCH(dssm_train_pool_kernel, (unsigned)R, 256, 0, s, w->table, q, d, w->vocab, E, B, Lq, Ld, p_drop, seed, o.x, o.arg, o.err);
+  // query_mlp on rows [0, B), doc_mlp on rows [B, R)  (dssm.py:58-59)
+  CAIR_TRY(gemm_f32(gemm_dense(o.x, E), w->query_mlp0.w, w->query_mlp0.b, o.h1, H, B, H, E, ACT_TANH, s));
+  CAIR_TRY(gemm_f32(gemm_dense(o.h1, H), w->query_mlp2.w, w->query_mlp2.b, o.y, O, B, O, H, ACT_TANH, s));
+  CAIR_TRY(gemm_f32(gemm_dense(o.x + (size_t)B * E, E), w->doc_mlp0.w, w->doc_mlp0.b, o.h1 + (size_t)B * H, H, P, H, E, ACT_TANH, s));
+  CAIR_TRY(gemm_f32(gemm_dense(o.h1 + (size_t)B * H, H), w->doc_mlp2.w, w->doc_mlp2.b, o.y + (size_t)B * O, O, P, O, H, ACT_TANH, s));
+  CAIR_LAUNCH(row_norm_kernel, (unsigned)((R + 7) / 8), 256, 0, s, o.y, O, R, o.nrm);
+  CAIR_LAUNCH(cos_score_kernel, (unsigned)((P + 7) / 8), 256, 0, s, o.y, o.nrm, O, B, N, scores);
+  return CAIR_OK;
+}
+
+int32_t cair_dssm_train_backward(const cair_dssm_weights* w, const cair_dssm_weights* grads, const int64_t* q, const int64_t* d,
+                                 int32_t B, int32_t N, int32_t Lq, int32_t Ld, float p_drop, uint64_t seed, const float* scores,
+                                 const float* dscores, void* ws, size_t ws_bytes, void* stream) {
+  if (!w || !grads || !q || !d || !scores || !dscores || !ws) return fail(CAIR_ERR_BAD_ARG, "dssm_train_backward: null argument");
+  const cair_dssm_weights& G = *grads;
+  if (!G.query_mlp0.w || !G.query_mlp0.b || !G.query_mlp2.w || !G.query_mlp2.b || !G.doc_mlp0.w || !G.doc_mlp0.b || !G.doc_mlp2.w ||
+      !G.doc_mlp2.b)
+    return fail(CAIR_ERR_BAD_ARG, "dssm_train_backward: null gradient pointer (only `table` may be NULL: fixed embeddings)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int E = w->emsize, H = w->nhid, O = w->nout;
+  Arena a(ws, ws_bytes);
+  DssmTrainWs o;
+  dssm_train_layout(a, E, H, O, B, N, &o);
+  if (!a.ok()) return fail(CAIR_ERR_WORKSPACE, "dssm_train_backward: workspace too small");
+  int flags = 0;
+  CAIR_CUDA(cudaMemcpyAsync(&flags, o.err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CAIR_CUDA(cudaStreamSynchronize(s));
+  if (flags) return fail(CAIR_ERR_BAD_ARG, "dssm_train: token id outside [0, vocab)");
+  const int64_t P = (int64_t)B * N, R = B + P;
+  CAIR_LAUNCH(dssm_train_cos_bwd_kernel, (unsigned)B, 128, 0, s, o.y, o.nrm, scores, dscores, O, B, N, o.dy);
+  const cair_linear* l0[2] = {&w->query_mlp0, &w->doc_mlp0};
+  const cair_linear* l2[2] = {&w->query_mlp2, &w->doc_mlp2};
+  const cair_linear* g0[2] = {&G.query_mlp0, &G.doc_mlp0};
+  const cair_linear* g2[2] = {&G.query_mlp2, &G.doc_mlp2};
+  float* w0t[2] = {o.w0t_q, o.w0t_d};
+  float* w2t[2] = {o.w2t_q, o.w2t_d};
+  for (int side = 0; side < 2; ++side) {
+    const int64_t r0 = side ? B : 0, rows = side ? P : B;
+    const float* x = o.x + (size_t)r0 * E;
+    const float* h1 = o.h1 + (size_t)r0 * H;
+    float* dy = o.dy + (size_t)r0 * O;
+    float* dh1 = o.dh1 + (size_t)r0 * H;
+    float* dx = o.dx + (size_t)r0 * E;
+    // second Linear: db2, dW2 = dy^T h1, dh1 = dy W2
+    CAIR_TRY(colsum(dy, O, rows, O, gp(g2[side]->b), nullptr, s));
+    CAIR_TRY(gemm_tn(dy, O, h1, H, 0, 1, gp(g2[side]->w), H, rows, O, H, s));
+    CAIR_LAUNCH(transpose_kernel, (O * H + 255) / 256, 256, 0, s, l2[side]->w, O, H, w2t[side], (int64_t)O);
+    CAIR_TRY(gemm_f32(gemm_dense(dy, O), w2t[side], nullptr, dh1, H, rows, H, O, ACT_NONE, s));
+    CAIR_LAUNCH(tanh_bwd_kernel, 296, 256, 0, s, dh1, h1, rows * H);
+    // first Linear: db0, dW0 = dh1^T x, dx = dh1 W0
+    CAIR_TRY(colsum(dh1, H, rows, H, gp(g0[side]->b), nullptr, s));
+    CAIR_TRY(gemm_tn(dh1, H, x, E, 0, 1, gp(g0[side]->w), E, rows, H, E, s));
+    if (G.table) {
+      CAIR_LAUNCH(transpose_kernel, (H * E + 255) / 256, 256, 0, s, l0[side]->w, H, E, w0t[side], (int64_t)H);
+      CAIR_TRY(gemm_f32(gemm_dense(dh1, H), w0t[side], nullptr, dx, E, rows, E, H, ACT_NONE, s));
+    }
+  }
+  if (G.table)
+    CAIR_LAUNCH(dssm_train_scatter_kernel, (unsigned)R, 256, 0, s, o.dx, o.arg, q, d, w->vocab, E, B, Lq, Ld, p_drop, seed, gp(G.table));
+  return CAIR_OK;
+}
+
 
 }  // extern "C"

@@ -493,6 +493,20 @@ CAIR_API int32_t cair_esm_train_backward(int32_t vocab, int32_t emsize, const in
                                 int32_t Lq, int32_t Ld, const float* scores, const float* dscores, float* dtable, void* workspace,
                                 size_t workspace_bytes, void* stream);
 
+/* Training step of DSSM (neuroir/rankers/dssm.py:33-63 under Ranker.update, models/ranker.py:192-230).  Stateless: `w` holds
+ * the live parameter pointers.  forward: embedding rows x emb_drop mask (the hash and element order of cair_dropout_mask: B*Lq
+ * query token rows, then B*N*Ld document token rows) -> max over the padded length (arg-max position kept) -> Linear, Tanh,
+ * Linear, Tanh per side -> cosine; train-mode scores [B,N].  backward: dscores -> gradients ACCUMULATED into `grads` (a
+ * cair_dssm_weights of zeroed gradient buffers; table may be NULL = fixed embeddings; the PAD row receives nothing).
+ * `scores` in backward are the forward's. */
+CAIR_API int32_t cair_dssm_train_workspace_bytes(int32_t emsize, int32_t nhid, int32_t nout, int32_t B, int32_t N, size_t* bytes);
+CAIR_API int32_t cair_dssm_train_forward(const cair_dssm_weights* w, const int64_t* q, const int64_t* d, int32_t B, int32_t N,
+                                int32_t Lq, int32_t Ld, float p_drop, uint64_t seed, float* scores, void* workspace,
+                                size_t workspace_bytes, void* stream);
+CAIR_API int32_t cair_dssm_train_backward(const cair_dssm_weights* w, const cair_dssm_weights* grads, const int64_t* q, const int64_t* d,
+                                 int32_t B, int32_t N, int32_t Lq, int32_t Ld, float p_drop, uint64_t seed, const float* scores,
+                                 const float* dscores, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- MNSRF ranking path ---------------------------------------------------
  * Replaces MNSRF.encode + MNSRF.rank_document (neuroir/multitask/mnsrf.py:61-162) as Multitask.predict calls them
  * (neuroir/models/multitask.py:270-276).  Weights are copied into the handle: table = embedder.word_embeddings...weight

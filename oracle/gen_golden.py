@@ -343,6 +343,54 @@ def gen_esm_train(name, seed, B, N, Lq, Ld, E, V, steps=3, lr=10.0, clip=5.0, **
     _save(name, cfg, batch, net, outs)
 
 
+def gen_dssm_train(name, seed, B, N, Lq, Ld, E, V, nhid, nout, p_drop=0.0, drop_seed=0, steps=3, lr=1.0, clip=5.0, **kw):
+    """DSSM under the statement order of Ranker.update (models/ranker.py:192-230): gradients of one train-mode forward / backward
+    of the unmodified reference and a 3-step SGD curve; emb_drop replaced by the oracle mask (query token rows, then documents)."""
+    from neuroir.rankers.dssm import DSSM
+    from dropout_oracle import drop_scale
+    torch.manual_seed(1013)
+    cfg = dict(model='dssm', emsize=E, src_vocab_size=V, dropout_emb=p_drop, nhid=nhid, nout=nout)
+    net = DSSM(_ns(**{k: v for k, v in cfg.items() if k != 'model'})).train()
+    batch = synth.ranker_batch(seed, B, N, Lq, Ld, V, **kw)
+    t = _t(batch)
+    mask = torch.from_numpy(drop_scale(drop_seed, (B * Lq + B * N * Ld) * E, p_drop))
+
+    class MaskDrop(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.calls = 0
+
+        def forward(self, x):
+            lo = 0 if self.calls % 2 == 0 else B * Lq * E
+            self.calls += 1
+            return x * mask[lo:lo + x.numel()].view(x.shape)
+    net.emb_drop = MaskDrop()
+    init = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    labels = t['label'].float()
+    crit = torch.nn.BCEWithLogitsLoss()
+    scores = net(t['q'], t['qlen'], t['d'], t['dlen'])
+    loss = crit(scores, labels)
+    loss.backward()
+    outs = dict(scores=scores.detach(), loss=loss.detach())
+    for k, p in net.named_parameters():
+        outs['grad/' + k] = p.grad.detach().clone()
+    opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr, momentum=0.0, weight_decay=0.0)
+    losses = []
+    for _ in range(steps):
+        ls = crit(net(t['q'], t['qlen'], t['d'], t['dlen']), labels)
+        opt.zero_grad()
+        ls.backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), clip)
+        opt.step()
+        losses.append(float(ls.detach()))
+    outs['losses'] = np.asarray(losses, dtype=np.float64)
+    for k, v in net.state_dict().items():
+        outs['final/' + k] = v.detach().clone()
+    cfg = dict(cfg, drop_seed=drop_seed, lr=lr, clip=clip, steps=steps)
+    net.load_state_dict(init)
+    _save(name, cfg, batch, net, outs)
+
+
 # ------------------------------------------------------------------ DUET
 def gen_duet(name, seed, B, N, Lq, Ld, E, V, nf, pool=5, **kw):
     from neuroir.rankers.duet import DUET
@@ -516,7 +564,7 @@ def main():
     only = sys.argv[1:]  # optional: fixture-name prefixes to (re)generate
     if only:
         g = globals()
-        for fn in ('gen_esm', 'gen_mt', 'gen_mt_train', 'gen_drmm_train', 'gen_esm_train', 'gen_session_ranker', 'gen_drmm', 'gen_duet', 'gen_cars', 'gen_dssm', 'gen_arc', 'gen_rank_metrics', 'gen_batchify'):
+        for fn in ('gen_esm', 'gen_mt', 'gen_mt_train', 'gen_drmm_train', 'gen_esm_train', 'gen_dssm_train', 'gen_session_ranker', 'gen_drmm', 'gen_duet', 'gen_cars', 'gen_dssm', 'gen_arc', 'gen_rank_metrics', 'gen_batchify'):
             g[fn] = (lambda f: (lambda name, *a, **k: f(name, *a, **k) if any(name.startswith(o) for o in only) else None))(g[fn])
     # BASELINE configs[0]: the reference's own CPU-runnable case (vocab cut 10k -> 1k to keep the file small)
     gen_esm('esm_cfg1', 1235, B=8, N=5, Lq=10, Ld=50, E=64, V=1000)
@@ -548,6 +596,9 @@ def main():
                  p_drop=0.2, drop_seed=77, bos_eos=True, overlap=0.1)
     gen_esm_train('esm_train_tiny', 37, B=3, N=4, Lq=7, Ld=23, E=32, V=100, overlap=0.2)
     gen_esm_train('esm_train_e300', 38, B=4, N=5, Lq=20, Ld=200, E=300, V=300, bos_eos=True, overlap=0.1)
+    gen_dssm_train('dssm_train_tiny', 39, B=3, N=4, Lq=6, Ld=19, E=24, V=120, nhid=16, nout=8)
+    gen_dssm_train('dssm_train_drop', 40, B=4, N=3, Lq=12, Ld=60, E=64, V=300, nhid=48, nout=32, p_drop=0.2, drop_seed=977,
+                   bos_eos=True, overlap=0.1)
     gen_drmm_train('drmm_train_tiny', 33, B=3, N=4, Lq=8, Ld=30, E=32, V=200, disjoint=True)
     gen_drmm_train('drmm_train_drop', 34, B=4, N=3, Lq=12, Ld=60, E=64, V=300, p_drop=0.2, drop_seed=4242, disjoint=True)
     # DRMM: strict (disjoint ids) and overlapping (bin-edge cells excluded by the test using out/cos)
