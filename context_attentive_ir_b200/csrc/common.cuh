@@ -231,6 +231,7 @@ struct GemmTcW {
 extern int g_gemm_dbg;
 extern int g_gemm_impl;  // 1 (default): tcgen05 GEMM where usable, 0: fp32 CUDA-core GEMM everywhere
 int32_t gemm_tc_pack(Owned& own, const float* w, int N, int K, GemmTcW* out, cudaStream_t s);
+int32_t gemm_tc_repack(const float* w, const GemmTcW& tw, cudaStream_t s);
 bool gemm_tc_usable(const GemmA& a, int K);
 int32_t gemm_tc(const GemmA& a, const GemmTcW& w, const float* bias, float* c, int64_t ldc, int64_t M, Act act,
                 cudaStream_t s);
@@ -283,7 +284,9 @@ int32_t lstm_tc_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* 
 // then copy 16-byte units instead of converting fp32 rows on every step.
 int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, const int64_t* len, int n, int L,
                     float* out, float* h_n, float* c_n, int* err, cudaStream_t s, const char* rec_name,
-                    const uint8_t* ximg = nullptr, int min_spc = 8);   // min_spc: fewest sequences per CTA to consider
+                    const uint8_t* ximg = nullptr, int min_spc = 8,   // min_spc: fewest sequences per CTA to consider
+                    float* gates_out = nullptr, float* cseq_out = nullptr);   // training: gate activations [n*L, dirs*4h], c [n*L, dirs*h]
+int32_t lstm_tc_repack(const LstmTcPack& p, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, cudaStream_t s);
 // table [V, in] fp32 -> image [V][hi|lo][48 x bf16] (constant 1 in K slot `in` = the bias column, zero padding)
 int32_t lstm_tc_pack_table(Owned& own, const float* table, int V, int in, uint8_t** img, cudaStream_t s);
 

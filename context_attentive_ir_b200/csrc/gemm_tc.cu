@@ -70,6 +70,13 @@ int32_t gemm_tc_pack(Owned& own, const float* w, int N, int K, GemmTcW* out, cud
   return CAIR_OK;
 }
 
+// Re-packs changed weights into an image of the same shape (training: the parameters move every step).
+int32_t gemm_tc_repack(const float* w, const GemmTcW& tw, cudaStream_t s) {
+  if (!tw.img) return CAIR_OK;
+  CAIR_LAUNCH(gemm_tc_pack_kernel, dim3(tw.nkc, tw.nct), 256, 0, s, w, tw.N, tw.K, tw.NT, tw.nkc, tw.img);
+  return CAIR_OK;
+}
+
 __device__ __forceinline__ void gt_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -89,6 +89,15 @@ int32_t lstm_tc_pack(Owned& own, const cair_lstm_dir* fwd, const cair_lstm_dir* 
   return CAIR_OK;
 }
 
+// Re-packs changed weights into an existing image (training: the parameters move every step).
+int32_t lstm_tc_repack(const LstmTcPack& p, const cair_lstm_dir* fwd, const cair_lstm_dir* rev, cudaStream_t s) {
+  for (int d = 0; d < p.dirs; ++d) {
+    const cair_lstm_dir* w = d ? rev : fwd;
+    CAIR_LAUNCH(lstm_tc_pack_kernel, 64, 256, 0, s, w->w_ih, w->w_hh, w->b_ih, w->b_hh, p.in, p.h, p.wimg + (size_t)d * 4 * LT_AIMG);
+  }
+  return CAIR_OK;
+}
+
 // x-operand rows of a gathered table: row v = [hi: LT_XP bf16][lo: LT_XP bf16] (192 B), K slot `in` = 1 (bias column).
 __global__ void lstm_tc_pack_table_kernel(const float* __restrict__ table, int V, int in, uint8_t* __restrict__ img) {
   const int64_t total = (int64_t)V * LT_XP;
@@ -150,6 +159,26 @@ __device__ __forceinline__ void lt_cell(float ti, float tf, float tg, float to, 
   h_new = (1.0f - ec) * lt_rcp((1.0f + eo) * (1.0f + ec));
 }
 
+// The same cell update that also returns the four gate activations (training: the BPTT kernel wants sigma(i), sigma(f),
+// tanh(g), sigma(o) and c per step).  No extra MUFU work: every activation is a product of terms already at hand and one of the
+// two reciprocals (1/(1+ei) = (1+eg)(1+ef) r1, ...).
+__device__ __forceinline__ void lt_cell_save(float ti, float tf, float tg, float to, float c, float& c_new, float& h_new,
+                                             float& gi, float& gf, float& gg, float& go) {
+  const float ei = lt_ex2(ti), ef = lt_ex2(tf), eg = lt_ex2(tg), eo = lt_ex2(to);
+  const float pi = 1.0f + ei, pf = 1.0f + ef, pg = 1.0f + eg;
+  const float pig = pi * pg, mg = 1.0f - eg;
+  const float r1 = lt_rcp(pig * pf);
+  c_new = fmaf(c, pig, mg * pf) * r1;
+  gi = pg * pf * r1;
+  gf = pig * r1;
+  gg = mg * pi * pf * r1;
+  const float ec = lt_ex2(-2.0f * 1.4426950408889634f * c_new);
+  const float pc = 1.0f + ec;
+  const float r2 = lt_rcp((1.0f + eo) * pc);
+  h_new = (1.0f - ec) * r2;
+  go = pc * r2;
+}
+
 // Optional role timing (dbg != nullptr; CTA (0,0), lane 0 of the role's first warp), see tools/lstm_timing.py
 #define LT_T0() long long t0_ = dbg ? clock64() : 0
 #define LT_ACC(slot) do { if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) dbg[slot] += clock64() - t0_; } while (0)
@@ -161,11 +190,15 @@ constexpr uint32_t LT_TCOLS = 4 * LT_NSEQ;                 // TMEM columns: 2 pa
 
 // smem: W image (4 x LT_AIMG) | h operand [2 parities][hi|lo] | x operand ring [LT_XS][hi|lo]
 // TMEM: [2 step parities][2 row tiles][32 sequences] fp32 columns
+// SAVE (training forward): additionally writes the gate activations [n*L, dirs*4h] (i, f, g, o blocks per direction) and the
+// cell states [n*L, dirs*h] of every valid step - the inputs of the BPTT kernel (train.cu).
+template <bool SAVE>
 __global__ void __launch_bounds__(LT_THREADS, 1)
     lstm_tc_kernel(GemmA x, const uint8_t* __restrict__ wimg_all, const float* __restrict__ bias_all,
                    const int64_t* __restrict__ len, int n, int L, int in, int h, int dirs, uint32_t ks_mask, int spc,
                    float* __restrict__ out, float* __restrict__ h_n, float* __restrict__ c_n, int* err,
-                   long long* __restrict__ dbg, const uint8_t* __restrict__ ximg) {
+                   long long* __restrict__ dbg, const uint8_t* __restrict__ ximg, float* __restrict__ gates_out,
+                   float* __restrict__ cseq_out) {
   extern __shared__ __align__(128) uint8_t smraw[];
   __shared__ uint64_t bar_w, bar_h[2], bar_acc[2], x_full[LT_XS], x_empty[LT_XS];
   __shared__ uint32_t tmem_slot;
@@ -425,6 +458,11 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
       cst[c] = 0.f, hst[c] = 0.f;
       optr[c] = out + ((size_t)(s0 + sl[c]) * L + (dir ? max(lk[c] - 1, 0) : 0)) * Hout + dir * h + u;
     }
+    int rowi[4] = {0, 0, 0, 0};   // SAVE: (sequence, time) row of this step for each cell
+    if (SAVE) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) rowi[c] = (s0 + sl[c]) * L + (dir ? max(lk[c] - 1, 0) : 0);
+    }
     const ptrdiff_t ostep = dir ? -(ptrdiff_t)Hout : (ptrdiff_t)Hout;
     const uint32_t tq = tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * LT_NSEQ + shalf * 16);
     const uint32_t hoff = (uint32_t)(u >> 3) * LT_BPLANE + (uint32_t)(u & 7) * 2;
@@ -451,8 +489,19 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
           if (c >= 2 && !do23) continue;
           const int r = (c >> 1) * 4 + (c & 1);
           float cn, hn_v;
-          lt_cell(ga[r], ga[r + 2], gb[r], gb[r + 2], cst[c], cn, hn_v);
           const bool act = step < lk[c];
+          if (SAVE) {
+            float gi, gf, gg, go;
+            lt_cell_save(ga[r], ga[r + 2], gb[r], gb[r + 2], cst[c], cn, hn_v, gi, gf, gg, go);
+            if (act && uvalid) {
+              float* g = gates_out + (size_t)rowi[c] * (4 * Hout) + dir * 4 * h + u;
+              g[0] = gi, g[h] = gf, g[2 * h] = gg, g[3 * h] = go;
+              cseq_out[(size_t)rowi[c] * Hout + dir * h + u] = cn;
+            }
+            rowi[c] += dir ? -1 : 1;
+          } else {
+            lt_cell(ga[r], ga[r + 2], gb[r], gb[r + 2], cst[c], cn, hn_v);
+          }
           cst[c] = act ? cn : cst[c];
           hst[c] = act ? hn_v : hst[c];
           hv[c] = hn_v;
@@ -516,7 +565,7 @@ int lstm_tc_ctas(int n, int dirs, int min_spc) {
 
 int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, const int64_t* len, int n, int L,
                     float* out, float* h_n, float* c_n, int* err, cudaStream_t s, const char* rec_name, const uint8_t* ximg,
-                    int min_spc) {
+                    int min_spc, float* gates_out, float* cseq_out) {
   if (n <= 0) return CAIR_OK;
   if (rec_name) prof_mark(rec_name, s);
   uint32_t ks_mask = 0;
@@ -527,13 +576,22 @@ int32_t lstm_tc_run(const LstmTcPack& p, const float* bias, const GemmA& x, cons
     if (x_part || h_part) ks_mask |= 1u << ks;
   }
   const size_t smem = (size_t)4 * LT_AIMG + 4 * LT_HIMG + 2 * LT_XS * LT_XIMG;
-  CAIR_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool save = gates_out != nullptr && cseq_out != nullptr;
+  if (save && (int64_t)n * L >= ((int64_t)1 << 31)) return fail(CAIR_ERR_UNSUPPORTED, "lstm_tc: too many rows for the training outputs");
+  if (save)
+    CAIR_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else
+    CAIR_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // Sequences per CTA: the per-step cost is latency + the cell updates of one SM (MUFU / issue bound), not the MMAs
   // (an N = 32 MMA costs the same as a narrower one), so use the fewest sequences per CTA that still fit one wave.
   const int spc = lstm_tc_seqs_per_cta(n, p.dirs, min_spc);
   dim3 grid((n + spc - 1) / spc, p.dirs);
-  CAIR_LAUNCH(lstm_tc_kernel, grid, LT_THREADS, smem, s, x, p.wimg, bias, len, n, L, p.in, p.h, p.dirs, ks_mask, spc, out,
-              h_n, c_n, err, g_lstm_dbg, x.table ? ximg : nullptr);
+  if (save)
+    CAIR_LAUNCH(lstm_tc_kernel<true>, grid, LT_THREADS, smem, s, x, p.wimg, bias, len, n, L, p.in, p.h, p.dirs, ks_mask, spc, out,
+                h_n, c_n, err, g_lstm_dbg, x.table ? ximg : nullptr, gates_out, cseq_out);
+  else
+    CAIR_LAUNCH(lstm_tc_kernel<false>, grid, LT_THREADS, smem, s, x, p.wimg, bias, len, n, L, p.in, p.h, p.dirs, ks_mask, spc, out,
+                h_n, c_n, err, g_lstm_dbg, x.table ? ximg : nullptr, (float*)nullptr, (float*)nullptr);
   return CAIR_OK;
 }
 

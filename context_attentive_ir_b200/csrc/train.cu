@@ -612,6 +612,13 @@ struct MtTrainer {
   float *wqt = nullptr, *wdt = nullptr;         // [Hq][C], [Hd][C]
   int dirs = 1, hq = 0, hd = 0;
   int tc_forward = 1;     // forward interaction on the tcgen05 kernel (with arg-max) where the shape allows; 0: fp32 kernel
+  // bf16x3 operand images of the dense layers for the tcgen05 GEMM (re-packed from the live parameters every step; used when
+  // tc_forward is on and the operand layout allows, else the fp32 GEMM): linear_projection, w_ih per encoder and direction,
+  // the channel projections, and w_ih^T (gate gradients -> d featsize rows in the backward)
+  GemmTcW tw_proj{}, tw_ih_q[2]{}, tw_ih_d[2]{}, tw_cq{}, tw_cd{}, tw_wiht_q{}, tw_wiht_d{};
+  // weight images of the tcgen05 recurrence (lstm_tc.cu, gate-saving instantiation) where the encoder fits it (in < 48,
+  // h <= 64 per direction): the forward recurrence then runs fused with its input projection, no pre-gate GEMM
+  LstmTcPack tcp_q{}, tcp_d{};
 };
 
 struct MtTrainWs {
@@ -988,6 +995,19 @@ int32_t cair_mt_train_create(const cair_mt_weights* w, int32_t device, cair_mt_t
     CAIR_CUDA(t.own.alloc(&t.wiht_d, (size_t)w->featsize * t.dirs * 4 * t.hd));
     CAIR_CUDA(t.own.alloc(&t.wqt, (size_t)w->nhid_query * w->nchannels));
     CAIR_CUDA(t.own.alloc(&t.wdt, (size_t)w->nhid_doc * w->nchannels));
+    CAIR_TRY(gemm_tc_pack(t.own, w->linear_projection.w, w->featsize, w->emsize, &t.tw_proj, s));
+    for (int dd = 0; dd < t.dirs; ++dd) {
+      CAIR_TRY(gemm_tc_pack(t.own, (dd ? w->query_rev : w->query_fwd).w_ih, 4 * t.hq, w->featsize, &t.tw_ih_q[dd], s));
+      CAIR_TRY(gemm_tc_pack(t.own, (dd ? w->doc_rev : w->doc_fwd).w_ih, 4 * t.hd, w->featsize, &t.tw_ih_d[dd], s));
+    }
+    CAIR_TRY(gemm_tc_pack(t.own, w->query_projection.w, w->nchannels, w->nhid_query, &t.tw_cq, s));
+    CAIR_TRY(gemm_tc_pack(t.own, w->document_projection.w, w->nchannels, w->nhid_doc, &t.tw_cd, s));
+    CAIR_TRY(gemm_tc_pack(t.own, t.wiht_q, w->featsize, t.dirs * 4 * t.hq, &t.tw_wiht_q, s));   // contents refreshed per step
+    CAIR_TRY(gemm_tc_pack(t.own, t.wiht_d, w->featsize, t.dirs * 4 * t.hd, &t.tw_wiht_d, s));
+    if (lstm_tc_supported(w->featsize, t.hq))
+      CAIR_TRY(lstm_tc_pack(t.own, &w->query_fwd, t.dirs == 2 ? &w->query_rev : nullptr, w->featsize, t.hq, &t.tcp_q, s));
+    if (lstm_tc_supported(w->featsize, t.hd))
+      CAIR_TRY(lstm_tc_pack(t.own, &w->doc_fwd, t.dirs == 2 ? &w->doc_rev : nullptr, w->featsize, t.hd, &t.tcp_d, s));
     const int hm = t.hq > t.hd ? t.hq : t.hd;
     CAIR_CUDA(t.own.alloc(&h->whh_scratch, (size_t)t.dirs * 4 * hm * hm));
     CAIR_CUDA(cudaStreamSynchronize(s));
@@ -1053,24 +1073,52 @@ int32_t cair_mt_train_forward(cair_mt_trainer* h, const int64_t* q, const int64_
   CAIR_TRY(refresh_lstm(w.doc_fwd, w.doc_rev, t.dirs, F, t.hd, t.whht_d, t.bias_d, t.wiht_d, s));
   CAIR_LAUNCH(transpose_kernel, (C * Hq + 255) / 256, 256, 0, s, w.query_projection.w, C, Hq, t.wqt, (int64_t)C);
   CAIR_LAUNCH(transpose_kernel, (C * Hd + 255) / 256, 256, 0, s, w.document_projection.w, C, Hd, t.wdt, (int64_t)C);
+  const GemmTcW none{};
+  const bool tcg = t.tc_forward != 0;
+  if (tcg) {
+    CAIR_TRY(gemm_tc_repack(w.linear_projection.w, t.tw_proj, s));
+    for (int dd = 0; dd < t.dirs; ++dd) {
+      CAIR_TRY(gemm_tc_repack((dd ? w.query_rev : w.query_fwd).w_ih, t.tw_ih_q[dd], s));
+      CAIR_TRY(gemm_tc_repack((dd ? w.doc_rev : w.doc_fwd).w_ih, t.tw_ih_d[dd], s));
+    }
+    CAIR_TRY(gemm_tc_repack(w.query_projection.w, t.tw_cq, s));
+    CAIR_TRY(gemm_tc_repack(w.document_projection.w, t.tw_cd, s));
+    CAIR_TRY(gemm_tc_repack(t.wiht_q, t.tw_wiht_q, s));
+    CAIR_TRY(gemm_tc_repack(t.wiht_d, t.tw_wiht_d, s));
+  }
   // embedding + dropout (mtensor.py:77-84), linear_projection (:88-90)
   CAIR_LAUNCH(embed_drop_kernel, 1184, 256, 0, s, w.table, q, w.vocab, E, Rq, (int64_t)0, p_drop, seed, o.xq, o.err);
   CAIR_LAUNCH(embed_drop_kernel, 1184, 256, 0, s, w.table, d, w.vocab, E, Rd, Rq, p_drop, seed, o.xd, o.err);
-  CAIR_TRY(gemm_f32(gemm_dense(o.xq, E), w.linear_projection.w, w.linear_projection.b, o.fq, F, Rq, F, E, ACT_NONE, s));
-  CAIR_TRY(gemm_f32(gemm_dense(o.xd, E), w.linear_projection.w, w.linear_projection.b, o.fd, F, Rd, F, E, ACT_NONE, s));
-  // encoders (:93-94)
+  CAIR_TRY(gemm_auto(gemm_dense(o.xq, E), w.linear_projection.w, tcg ? t.tw_proj : none, w.linear_projection.b, o.fq, F, Rq, F, E, ACT_NONE, s));
+  CAIR_TRY(gemm_auto(gemm_dense(o.xd, E), w.linear_projection.w, tcg ? t.tw_proj : none, w.linear_projection.b, o.fd, F, Rd, F, E, ACT_NONE, s));
+  // encoders (:93-94): the tcgen05 recurrence with its fused input projection where the encoder fits it (it leaves the gate
+  // activations and cell states the BPTT kernel reads), else pre-gate GEMMs + the fp32 recurrence
+  const bool rq = tcg && t.tcp_q.wimg != nullptr && g_rnn_impl != RNN_IMPL_FP32;
+  const bool rd = tcg && t.tcp_d.wimg != nullptr && g_rnn_impl != RNN_IMPL_FP32;
+  if (rq) CAIR_TRY(lstm_tc_repack(t.tcp_q, &w.query_fwd, &w.query_rev, s));
+  if (rd) CAIR_TRY(lstm_tc_repack(t.tcp_d, &w.doc_fwd, &w.doc_rev, s));
   for (int dd = 0; dd < t.dirs; ++dd) {
     const int Gq = 4 * t.hq, Gd = 4 * t.hd;
-    CAIR_TRY(gemm_f32(gemm_dense(o.fq, F), (dd ? w.query_rev : w.query_fwd).w_ih, t.bias_q + (size_t)dd * Gq, o.gq + (size_t)dd * Gq,
-                      (int64_t)t.dirs * Gq, Rq, Gq, F, ACT_NONE, s));
-    CAIR_TRY(gemm_f32(gemm_dense(o.fd, F), (dd ? w.doc_rev : w.doc_fwd).w_ih, t.bias_d + (size_t)dd * Gd, o.gd + (size_t)dd * Gd,
-                      (int64_t)t.dirs * Gd, Rd, Gd, F, ACT_NONE, s));
+    if (!rq)
+      CAIR_TRY(gemm_auto(gemm_dense(o.fq, F), (dd ? w.query_rev : w.query_fwd).w_ih, tcg ? t.tw_ih_q[dd] : none, t.bias_q + (size_t)dd * Gq,
+                         o.gq + (size_t)dd * Gq, (int64_t)t.dirs * Gq, Rq, Gq, F, ACT_NONE, s));
+    if (!rd)
+      CAIR_TRY(gemm_auto(gemm_dense(o.fd, F), (dd ? w.doc_rev : w.doc_fwd).w_ih, tcg ? t.tw_ih_d[dd] : none, t.bias_d + (size_t)dd * Gd,
+                         o.gd + (size_t)dd * Gd, (int64_t)t.dirs * Gd, Rd, Gd, F, ACT_NONE, s));
   }
-  CAIR_TRY(lstm_train_fwd(o.gq, t.whht_q, qlen, B, Lq, t.hq, t.dirs, o.enc_q, o.cseq_q, o.err, s));
-  CAIR_TRY(lstm_train_fwd(o.gd, t.whht_d, dlen, (int)P, Ld, t.hd, t.dirs, o.enc_d, o.cseq_d, o.err, s));
+  if (rq)
+    CAIR_TRY(lstm_tc_run(t.tcp_q, nullptr, gemm_dense(o.fq, F), qlen, B, Lq, o.enc_q, nullptr, nullptr, o.err, s, nullptr, nullptr, 8,
+                         o.gq, o.cseq_q));
+  else
+    CAIR_TRY(lstm_train_fwd(o.gq, t.whht_q, qlen, B, Lq, t.hq, t.dirs, o.enc_q, o.cseq_q, o.err, s));
+  if (rd)
+    CAIR_TRY(lstm_tc_run(t.tcp_d, nullptr, gemm_dense(o.fd, F), dlen, (int)P, Ld, o.enc_d, nullptr, nullptr, o.err, s, nullptr, nullptr, 8,
+                         o.gd, o.cseq_d));
+  else
+    CAIR_TRY(lstm_train_fwd(o.gd, t.whht_d, dlen, (int)P, Ld, t.hd, t.dirs, o.enc_d, o.cseq_d, o.err, s));
   // channel projections (:99, :108)
-  CAIR_TRY(gemm_f32(gemm_dense(o.enc_q, Hq), w.query_projection.w, w.query_projection.b, o.cq, C, Rq, C, Hq, ACT_NONE, s));
-  CAIR_TRY(gemm_f32(gemm_dense(o.enc_d, Hd), w.document_projection.w, w.document_projection.b, o.cd, C, Rd, C, Hd, ACT_NONE, s));
+  CAIR_TRY(gemm_auto(gemm_dense(o.enc_q, Hq), w.query_projection.w, tcg ? t.tw_cq : none, w.query_projection.b, o.cq, C, Rq, C, Hq, ACT_NONE, s));
+  CAIR_TRY(gemm_auto(gemm_dense(o.enc_d, Hd), w.document_projection.w, tcg ? t.tw_cd : none, w.document_projection.b, o.cd, C, Rd, C, Hd, ACT_NONE, s));
   // interaction (:113-131) with the arg-max cells of the two max-pools: the tensor-core kernel of the scoring path (its
   // arg-max instantiation) where the shape allows, else the fp32 kernel.  The backward recomputes the winning cells in fp32.
   if (t.tc_forward && o.timg) {
@@ -1131,12 +1179,13 @@ int32_t cair_mt_train_backward(cair_mt_trainer* h, const int64_t* q, const int64
   // ---- encoders: BPTT, then the weight gradients as GEMMs over all (sequence, step) rows ----
   struct Enc {
     float *gates, *cseq, *denc, *enc, *f, *df, *wiht;
+    const GemmTcW* tw_wiht;
     const int64_t* len;
     int n, L, h;
     int64_t R;
     const cair_lstm_dir *wf, *wr, *gf, *gr;
-  } encs[2] = {{o.gq, o.cseq_q, o.denc_q, o.enc_q, o.fq, o.dfq, t.wiht_q, qlen, B, Lq, t.hq, Rq, &w.query_fwd, &w.query_rev, &G.query_fwd, &G.query_rev},
-               {o.gd, o.cseq_d, o.denc_d, o.enc_d, o.fd, o.dfd, t.wiht_d, dlen, (int)P, Ld, t.hd, Rd, &w.doc_fwd, &w.doc_rev, &G.doc_fwd, &G.doc_rev}};
+  } encs[2] = {{o.gq, o.cseq_q, o.denc_q, o.enc_q, o.fq, o.dfq, t.wiht_q, &t.tw_wiht_q, qlen, B, Lq, t.hq, Rq, &w.query_fwd, &w.query_rev, &G.query_fwd, &G.query_rev},
+               {o.gd, o.cseq_d, o.denc_d, o.enc_d, o.fd, o.dfd, t.wiht_d, &t.tw_wiht_d, dlen, (int)P, Ld, t.hd, Rd, &w.doc_fwd, &w.doc_rev, &G.doc_fwd, &G.doc_rev}};
   for (const Enc& e : encs) {
     const int Gh = 4 * e.h, PG = t.dirs * Gh, Hout = t.dirs * e.h;
     CAIR_TRY(lstm_train_bwd(e.gates, e.cseq, e.denc, e.wf->w_hh, e.wr->w_hh, h->whh_scratch, e.len, e.n, e.L, e.h, t.dirs, s));
@@ -1149,7 +1198,10 @@ int32_t cair_mt_train_backward(cair_mt_trainer* h, const int64_t* q, const int64
       CAIR_TRY(gemm_tn(dg, PG, e.f, F, 0, e.L, gp(gw->w_ih), F, e.R, Gh, F, s));
       CAIR_TRY(colsum(dg, PG, e.R, Gh, gp(gw->b_ih), gp(gw->b_hh), s));
     }
-    CAIR_TRY(gemm_f32(gemm_dense(e.gates, PG), e.wiht, nullptr, e.df, F, e.R, F, PG, ACT_NONE, s));
+    {
+      const GemmTcW none{};
+      CAIR_TRY(gemm_auto(gemm_dense(e.gates, PG), e.wiht, t.tc_forward ? *e.tw_wiht : none, nullptr, e.df, F, e.R, F, PG, ACT_NONE, s));
+    }
   }
   // ---- linear_projection and the embedding table ----
   CAIR_TRY(gemm_tn(o.dfq, F, o.xq, E, 0, Lq, gp(G.linear_projection.w), E, Rq, F, E, s));

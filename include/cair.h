@@ -450,8 +450,10 @@ CAIR_API int32_t cair_cars_decode(cair_handle* h, const float* enc_q, const int6
 typedef struct cair_mt_trainer cair_mt_trainer;
 CAIR_API int32_t cair_mt_train_create(const cair_mt_weights* params, int32_t device, cair_mt_trainer** out);
 CAIR_API int32_t cair_mt_train_destroy(cair_mt_trainer* t);
-/* forward interaction engine: 1 (default) = the tcgen05 interaction kernel of the scoring path in its arg-max instantiation
- * where the shape allows, 0 = the fp32 CUDA-core kernel (A/B runs; the backward is the same either way) */
+/* engines: 1 (default) = the tcgen05 interaction kernel of the scoring path in its arg-max instantiation and the tcgen05
+ * bf16x3 GEMM for the dense layers (linear_projection, pre-gates, channel projections, gate gradients -> feature rows) where
+ * the shapes allow, 0 = fp32 CUDA-core kernels throughout (A/B runs; the recurrences, the sparse interaction backward and the
+ * weight-gradient GEMMs are the same either way) */
 CAIR_API int32_t cair_mt_train_set_impl(cair_mt_trainer* t, int32_t tc_forward);
 CAIR_API int32_t cair_mt_train_workspace_bytes(cair_mt_trainer* t, int32_t B, int32_t N, int32_t Lq, int32_t Ld, size_t* bytes);
 CAIR_API int32_t cair_mt_train_forward(cair_mt_trainer* t, const int64_t* q, const int64_t* qlen, const int64_t* d,
