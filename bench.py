@@ -460,8 +460,8 @@ def other_configs(run, args, peaks):
     out.append(dict(name='match_tensor cfg2 TRAINING step (forward + backward + clip + SGD)', config=dict(model='match_tensor', B=B, N=N, Lq=LQ, Ld=LD, dropout_emb=CFG['dropout_emb']),
                     pairs_per_s=B * N * world / (ms / 1e3), ms_per_step=ms, n_gpus=world, scaling='weak', steps=6,
                     parallelism='data-parallel x%d: %d pairs per GPU, gradient all-reduce per step' % (world, B * N),
-                    roofline=tensor_roof('lstm_train_bwd_kernel / lstm_train_fwd_kernel / gemm_tn_kernel', 3 * flops_per_pair()['ref'])(B * N, ms, {}),
-                    note='first slice of the backward row (csrc/train.cu): forward interaction on the tcgen05 kernel (arg-max instantiation), recurrences / weight-gradient GEMMs / sparse interaction backward on fp32 CUDA cores'))
+                    roofline=tensor_roof('lstm_train_bwd_kernel / mt_train_interact_bwd_kernel / gemm_tn_kernel', 3 * flops_per_pair()['ref'])(B * N, ms, {}),
+                    note='training row (csrc/train.cu): forward on the tcgen05 kernels (interaction with arg-max, gate-saving lstm_tc, gemm_tc dense layers); BPTT / weight-gradient GEMMs / sparse interaction backward on fp32 CUDA cores'))
     del tnet, opt
     torch.cuda.empty_cache()
     return out
