@@ -290,12 +290,11 @@ __global__ void __launch_bounds__(256) lstm_train_fwd_kernel(float* __restrict__
 
 // BPTT: `gates` holds the activations on entry and the pre-activation gradients dL/da (zero at t >= len) on exit.
 // denc [n*L, dirs*h]: gradient of the memory bank.  w_hh [dirs][4h][h] (torch layout).
-template <bool WSMEM>
+template <bool WSMEM, int TS>
 __global__ void __launch_bounds__(256) lstm_train_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_seq,
                                                              const float* __restrict__ denc, const float* __restrict__ w_hh,
                                                              const int64_t* __restrict__ len, int n, int L, int h, int dirs) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int TS = TR_TS;
   const int G = 4 * h, PG = dirs * G, Hout = dirs * h;
   const int dir = blockIdx.y, s0 = blockIdx.x * TS, tid = threadIdx.x;
   float* wsm = smem;                                         // [G][h]
@@ -369,11 +368,12 @@ __global__ void __launch_bounds__(256) lstm_train_bwd_kernel(float* __restrict__
       const int r_lo = grp * h, r_hi = r_lo + h;   // one gate type per thread group
       for (int r = r_lo; r < r_hi; ++r) {
         const float w0 = W[(size_t)r * h + k];
-        const float4 d0 = *reinterpret_cast<const float4*>(&da[(size_t)r * TS]);
-        const float4 d1 = *reinterpret_cast<const float4*>(&da[(size_t)r * TS + 4]);
-        acc[0] = fmaf(w0, d0.x, acc[0]), acc[1] = fmaf(w0, d0.y, acc[1]), acc[2] = fmaf(w0, d0.z, acc[2]);
-        acc[3] = fmaf(w0, d0.w, acc[3]), acc[4] = fmaf(w0, d1.x, acc[4]), acc[5] = fmaf(w0, d1.y, acc[5]);
-        acc[6] = fmaf(w0, d1.z, acc[6]), acc[7] = fmaf(w0, d1.w, acc[7]);
+#pragma unroll
+        for (int s4 = 0; s4 < TS / 4; ++s4) {
+          const float4 d0 = *reinterpret_cast<const float4*>(&da[(size_t)r * TS + 4 * s4]);
+          acc[4 * s4] = fmaf(w0, d0.x, acc[4 * s4]), acc[4 * s4 + 1] = fmaf(w0, d0.y, acc[4 * s4 + 1]);
+          acc[4 * s4 + 2] = fmaf(w0, d0.z, acc[4 * s4 + 2]), acc[4 * s4 + 3] = fmaf(w0, d0.w, acc[4 * s4 + 3]);
+        }
       }
 #pragma unroll
       for (int s = 0; s < TS; ++s) part[((size_t)grp * TS + s) * h + k] = acc[s];
@@ -679,17 +679,29 @@ static int32_t lstm_train_bwd(float* gates, const float* c_seq, const float* den
   if (dirs == 2)
     CAIR_CUDA(cudaMemcpyAsync(whh_scratch + (size_t)G * h, w_hh_rev, (size_t)G * h * sizeof(float), cudaMemcpyDeviceToDevice, s));
   const size_t wbytes = (size_t)G * h * sizeof(float);
-  const size_t rest = ((size_t)G * TR_TS + 2 * TR_TS * h + 4 * TR_TS * h) * sizeof(float);
+  // Sequences per CTA: the fewest of 8 / 12 / 16 whose grid fits ONE wave of two resident CTAs per SM (1280 documents x 2
+  // directions at 8 per CTA are 320 CTAs = a full wave plus a 24-CTA tail that costs a second full pass)
+  int ts = 8;
+  while (ts < 16 && (int64_t)((n + ts - 1) / ts) * dirs > 2 * kSMs) ts += 4;
+  const size_t rest = ((size_t)G * ts + 2 * ts * h + 4 * ts * h) * sizeof(float);
   const bool wsmem = wbytes + rest <= 200 * 1024;
   const size_t smem = (wsmem ? wbytes : 0) + rest;
-  dim3 grid((n + TR_TS - 1) / TR_TS, dirs);
+  dim3 grid((n + ts - 1) / ts, dirs);
+#define CAIR_BWD_LAUNCH(WS, TSV)                                                                                           \
+  do {                                                                                                                     \
+    CAIR_CUDA(cudaFuncSetAttribute(lstm_train_bwd_kernel<WS, TSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    CAIR_LAUNCH((lstm_train_bwd_kernel<WS, TSV>), grid, 256, smem, s, gates, c_seq, denc, whh_scratch, len, n, L, h, dirs);  \
+  } while (0)
   if (wsmem) {
-    CAIR_CUDA(cudaFuncSetAttribute(lstm_train_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CAIR_LAUNCH(lstm_train_bwd_kernel<true>, grid, 256, smem, s, gates, c_seq, denc, whh_scratch, len, n, L, h, dirs);
+    if (ts == 8) CAIR_BWD_LAUNCH(true, 8);
+    else if (ts == 12) CAIR_BWD_LAUNCH(true, 12);
+    else CAIR_BWD_LAUNCH(true, 16);
   } else {
-    CAIR_CUDA(cudaFuncSetAttribute(lstm_train_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CAIR_LAUNCH(lstm_train_bwd_kernel<false>, grid, 256, smem, s, gates, c_seq, denc, whh_scratch, len, n, L, h, dirs);
+    if (ts == 8) CAIR_BWD_LAUNCH(false, 8);
+    else if (ts == 12) CAIR_BWD_LAUNCH(false, 12);
+    else CAIR_BWD_LAUNCH(false, 16);
   }
+#undef CAIR_BWD_LAUNCH
   return CAIR_OK;
 }
 
