@@ -123,6 +123,12 @@ __global__ void cdssm_merge_kernel(const float* __restrict__ w, int Lh, int E, f
   w5[i] = v;
 }
 
+void cdssm_merge_launch(const float* w, int H, int E, float* w5, cudaStream_t s) {
+  const int64_t n5 = (int64_t)H * 5 * E;
+  cdssm_merge_kernel<<<(unsigned)((n5 + 255) / 256), 256, 0, s>>>(w, H, E, w5);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
 int32_t cdssm_create_state(Owned& own, const cair_cdssm_weights& w, CdssmState* st, cudaStream_t s) {
   st->V = w.vocab, st->E = w.emsize, st->H = w.nhid, st->O = w.nout;
   CAIR_TRY(dev_copy(own, w.table, (size_t)w.vocab * w.emsize, &st->table, s));

@@ -954,6 +954,95 @@ __global__ void __launch_bounds__(256) dssm_train_scatter_kernel(const float* __
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// CDSSM (cdssm.py:42-77) in train mode.  The interleave + Conv1d(k = 3) pair is one linear map over 5-token windows (the merged
+// weight W5 of the scoring path, cdssm_merge_kernel), so with one ROW PER TOKEN (window r = the 5E contiguous floats starting at
+// token row r of the dropped embedding matrix; rows t >= L - 4 of a sequence are not windows of it: never pooled, zero
+// gradient) every layer is a dense GEMM forward and backward:
+//   h1 = tanh(X5 W5^T + b) [R, H],  s2 = tanh(h1 Ws^T + bs) [R, O],  y = max over the valid t (arg-max kept),  cosine;
+//   dz2 = scatter of dy (1 - y^2) to the arg-max rows,  dWs = dz2^T h1,  dh1 = (dz2 Ws) (1 - h1^2),  dW5 = dh1^T X5,
+//   dx[r] = sum_j dh1[r - j] W5[:, j]  = one GEMM over the 5H floats ending at row r of dh1 (4 zero rows in front),
+//   table gradient = dx * mask scattered to the non-PAD token ids, conv gradient = W5 gradient un-merged.
+void cdssm_merge_launch(const float* w, int H, int E, float* w5, cudaStream_t s);   // dssm.cu
+
+struct CdssmTrainWs {
+  float *x, *h1, *s2, *y, *nrm, *dy, *dz2, *dh1, *dx;   // token rows: B*Lq query rows, then B*N*Ld document rows (+ padding rows)
+  int* arg;                                               // [B + B*N, O] arg-max token row
+  float *w5[2], *dw5[2], *wst[2], *w5r[2];                // merged conv weight [H,5E], its gradient, Ws^T [H,O], reordered [E,5H]
+  int* err;
+};
+static void cdssm_train_layout(Arena& a, int E, int H, int O, int B, int N, int Lq, int Ld, CdssmTrainWs* o) {
+  const size_t Rt = (size_t)B * Lq + (size_t)B * N * Ld, Rs = (size_t)B + (size_t)B * N;
+  o->x = a.take<float>((Rt + 4) * E);
+  o->h1 = a.take<float>(Rt * H), o->s2 = a.take<float>(Rt * O);
+  o->y = a.take<float>(Rs * O), o->nrm = a.take<float>(Rs), o->dy = a.take<float>(Rs * O);
+  o->dz2 = a.take<float>(Rt * O), o->dh1 = a.take<float>((Rt + 4) * H), o->dx = a.take<float>(Rt * E);
+  o->arg = a.take<int>(Rs * O);
+  for (int i = 0; i < 2; ++i) {
+    o->w5[i] = a.take<float>((size_t)H * 5 * E), o->dw5[i] = a.take<float>((size_t)H * 5 * E);
+    o->wst[i] = a.take<float>((size_t)H * O), o->w5r[i] = a.take<float>((size_t)E * 5 * H);
+  }
+  o->err = a.take<int>(4);
+}
+
+// y[s, o] = max over the valid windows t < L - 4 of s2[(row0 + s*L + t), o]; arg = that token row (first maximum)
+__global__ void cdssm_train_max_kernel(const float* __restrict__ s2, int O, int L, int64_t row0, int64_t nseq, float* __restrict__ y,
+                                       int* __restrict__ arg) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nseq * O) return;
+  const int64_t s = i / O;
+  const int o = (int)(i - s * O);
+  float best = -INFINITY;
+  int bt = 0;
+  for (int t = 0; t < L - 4; ++t) {
+    const float v = s2[(row0 + s * L + t) * O + o];
+    if (v > best) best = v, bt = t;
+  }
+  y[i] = best;
+  arg[i] = (int)(row0 + s * L + bt);
+}
+
+__global__ void cdssm_train_route_kernel(const float* __restrict__ dy, const int* __restrict__ arg, int O, int64_t n,
+                                         float* __restrict__ dz2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dz2[(int64_t)arg[i] * O + (i % O)] = dy[i];
+}
+
+// w5r[e][jj*H + h] = w5[h][(4 - jj)*E + e]: the weight of "dx[r] = [dh1[r-4] .. dh1[r]] . w5r^T"
+__global__ void cdssm_train_reorder_kernel(const float* __restrict__ w5, int H, int E, float* __restrict__ w5r) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)E * 5 * H) return;
+  const int h = (int)(i % H), jj = (int)((i / H) % 5), e = (int)(i / ((int64_t)5 * H));
+  w5r[i] = w5[(size_t)h * 5 * E + (size_t)(4 - jj) * E + e];
+}
+
+// d conv.weight[f][wi*E + e][k] += d W5[f][(wi + k)*E + e]   (the transpose of cdssm_merge_kernel)
+__global__ void cdssm_train_unmerge_kernel(const float* __restrict__ dw5, int H, int E, float* __restrict__ dw) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)H * 3 * E * 3) return;
+  const int k = (int)(i % 3);
+  const int64_t c = i / 3;
+  const int e = (int)(c % E), wi = (int)((c / E) % 3), f = (int)(c / ((int64_t)3 * E));
+  dw[i] += dw5[(size_t)f * 5 * E + (size_t)(wi + k) * E + e];
+}
+
+// d table[ids[r], e] += dx[r, e] * mask(row0 + r, e)   (PAD: no gradient)
+__global__ void embed_scatter_kernel(const float* __restrict__ dx, const int64_t* __restrict__ ids, int V, int E, int64_t rows,
+                                     int64_t row0, float p, uint64_t seed, float* __restrict__ dtable) {
+  const float inv = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  const int64_t total = rows * E;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / E;
+    const int e = (int)(i - r * E);
+    const int64_t id = ids[r];
+    if (id <= 0 || id >= V) continue;
+    const float m = drop_scale(seed, (uint64_t)((row0 + r) * E + e), p, inv);
+    const float g = dx[(row0 + r) * E + e] * m;
+    if (g != 0.f) atomicAdd(dtable + id * E + e, g);
+  }
+}
+
 }  // namespace cair
 
 using namespace cair;
@@ -1389,6 +1478,114 @@ int32_t cair_dssm_train_backward(const cair_dssm_weights* w, const cair_dssm_wei
   }
   if (G.table)
     CAIR_LAUNCH(dssm_train_scatter_kernel, (unsigned)R, 256, 0, s, o.dx, o.arg, q, d, w->vocab, E, B, Lq, Ld, p_drop, seed, gp(G.table));
+  return CAIR_OK;
+}
+
+
+int32_t cair_cdssm_train_workspace_bytes(int32_t emsize, int32_t nhid, int32_t nout, int32_t B, int32_t N, int32_t Lq, int32_t Ld,
+                                         size_t* bytes) {
+  if (!bytes || emsize <= 0 || nhid <= 0 || nout <= 0 || B <= 0 || N <= 0 || Lq < 5 || Ld < 5)
+    return fail(CAIR_ERR_BAD_ARG, "cdssm_train_workspace_bytes: bad argument (sequences need at least 5 tokens)");
+  Arena a(nullptr, 0);
+  CdssmTrainWs o;
+  cdssm_train_layout(a, emsize, nhid, nout, B, N, Lq, Ld, &o);
+  *bytes = align_up(a.off) + 256;
+  return CAIR_OK;
+}
+
+int32_t cair_cdssm_train_forward(const cair_cdssm_weights* w, const int64_t* q, const int64_t* d, int32_t B, int32_t N, int32_t Lq,
+                                 int32_t Ld, float p_drop, uint64_t seed, float* scores, void* ws, size_t ws_bytes, void* stream) {
+  if (!w || !q || !d || !scores || !ws || !w->table || !w->query_conv.w || !w->query_conv.b || !w->query_sem.w || !w->query_sem.b ||
+      !w->doc_conv.w || !w->doc_conv.b || !w->doc_sem.w || !w->doc_sem.b)
+    return fail(CAIR_ERR_BAD_ARG, "cdssm_train_forward: null argument");
+  if (B <= 0 || N <= 0 || Lq < 5 || Ld < 5) return fail(CAIR_ERR_BAD_SHAPE, "cdssm_train_forward: sequences shorter than 5 tokens");
+  if (p_drop < 0.f || p_drop >= 1.f) return fail(CAIR_ERR_BAD_ARG, "cdssm_train_forward: dropout must be in [0, 1)");
+  if ((uintptr_t)ws % 256) return fail(CAIR_ERR_WORKSPACE, "cdssm_train_forward: workspace must be 256-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int E = w->emsize, H = w->nhid, O = w->nout;
+  Arena a(ws, ws_bytes);
+  CdssmTrainWs o;
+  cdssm_train_layout(a, E, H, O, B, N, Lq, Ld, &o);
+  if (!a.ok()) return fail(CAIR_ERR_WORKSPACE, "cdssm_train_forward: workspace too small");
+  const int64_t Rq = (int64_t)B * Lq, Rd = (int64_t)B * N * Ld, Rt = Rq + Rd, P = (int64_t)B * N;
+  if (Rt + 4 >= ((int64_t)1 << 31)) return fail(CAIR_ERR_UNSUPPORTED, "cdssm_train_forward: too many token rows");
+  CAIR_CUDA(cudaMemsetAsync(o.err, 0, 4 * sizeof(int), s));
+  CAIR_CUDA(cudaMemsetAsync(o.x + (size_t)Rt * E, 0, (size_t)4 * E * sizeof(float), s));   // the last windows read 4 rows past the end
+  CAIR_LAUNCH(embed_drop_kernel, 1184, 256, 0, s, w->table, q, w->vocab, E, Rq, (int64_t)0, p_drop, seed, o.x, o.err);
+  CAIR_LAUNCH(embed_drop_kernel, 1184, 256, 0, s, w->table, d, w->vocab, E, Rd, Rq, p_drop, seed, o.x + (size_t)Rq * E, o.err);
+  const cair_linear* conv[2] = {&w->query_conv, &w->doc_conv};
+  const cair_linear* sem[2] = {&w->query_sem, &w->doc_sem};
+  for (int side = 0; side < 2; ++side) {
+    const int64_t r0 = side ? Rq : 0, rows = side ? Rd : Rq, nseq = side ? P : B;
+    const int L = side ? Ld : Lq;
+    cdssm_merge_launch(conv[side]->w, H, E, o.w5[side], s);
+    CAIR_TRY(gemm_f32(gemm_dense(o.x + (size_t)r0 * E, E), o.w5[side], conv[side]->b, o.h1 + (size_t)r0 * H, H, rows, H, 5 * E, ACT_TANH, s));
+    CAIR_TRY(gemm_f32(gemm_dense(o.h1 + (size_t)r0 * H, H), sem[side]->w, sem[side]->b, o.s2 + (size_t)r0 * O, O, rows, O, H, ACT_TANH, s));
+    CAIR_LAUNCH(cdssm_train_max_kernel, (unsigned)((nseq * O + 255) / 256), 256, 0, s, o.s2, O, L, r0, nseq, o.y + (size_t)(side ? B : 0) * O,
+                o.arg + (size_t)(side ? B : 0) * O);
+  }
+  const int64_t Rs = B + P;
+  CAIR_LAUNCH(row_norm_kernel, (unsigned)((Rs + 7) / 8), 256, 0, s, o.y, O, Rs, o.nrm);
+  CAIR_LAUNCH(cos_score_kernel, (unsigned)((P + 7) / 8), 256, 0, s, o.y, o.nrm, O, B, N, scores);
+  return CAIR_OK;
+}
+
+int32_t cair_cdssm_train_backward(const cair_cdssm_weights* w, const cair_cdssm_weights* grads, const int64_t* q, const int64_t* d,
+                                  int32_t B, int32_t N, int32_t Lq, int32_t Ld, float p_drop, uint64_t seed, const float* scores,
+                                  const float* dscores, void* ws, size_t ws_bytes, void* stream) {
+  if (!w || !grads || !q || !d || !scores || !dscores || !ws) return fail(CAIR_ERR_BAD_ARG, "cdssm_train_backward: null argument");
+  const cair_cdssm_weights& G = *grads;
+  if (!G.query_conv.w || !G.query_conv.b || !G.query_sem.w || !G.query_sem.b || !G.doc_conv.w || !G.doc_conv.b || !G.doc_sem.w ||
+      !G.doc_sem.b)
+    return fail(CAIR_ERR_BAD_ARG, "cdssm_train_backward: null gradient pointer (only `table` may be NULL: fixed embeddings)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int E = w->emsize, H = w->nhid, O = w->nout;
+  Arena a(ws, ws_bytes);
+  CdssmTrainWs o;
+  cdssm_train_layout(a, E, H, O, B, N, Lq, Ld, &o);
+  if (!a.ok()) return fail(CAIR_ERR_WORKSPACE, "cdssm_train_backward: workspace too small");
+  int flags = 0;
+  CAIR_CUDA(cudaMemcpyAsync(&flags, o.err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CAIR_CUDA(cudaStreamSynchronize(s));
+  if (flags) return fail(CAIR_ERR_BAD_ARG, "cdssm_train: token id outside [0, vocab)");
+  const int64_t Rq = (int64_t)B * Lq, Rd = (int64_t)B * N * Ld, Rt = Rq + Rd, P = (int64_t)B * N, Rs = B + P;
+  CAIR_LAUNCH(dssm_train_cos_bwd_kernel, (unsigned)B, 128, 0, s, o.y, o.nrm, scores, dscores, O, B, N, o.dy);
+  CAIR_CUDA(cudaMemsetAsync(o.dz2, 0, (size_t)Rt * O * sizeof(float), s));
+  CAIR_LAUNCH(cdssm_train_route_kernel, (unsigned)((Rs * O + 255) / 256), 256, 0, s, o.dy, o.arg, O, Rs * O, o.dz2);
+  CAIR_CUDA(cudaMemsetAsync(o.dh1, 0, (size_t)4 * H * sizeof(float), s));   // the 4 rows in front of the first token
+  float* dh1 = o.dh1 + (size_t)4 * H;
+  const cair_linear* sem[2] = {&w->query_sem, &w->doc_sem};
+  const cair_linear* gconv[2] = {&G.query_conv, &G.doc_conv};
+  const cair_linear* gsem[2] = {&G.query_sem, &G.doc_sem};
+  for (int side = 0; side < 2; ++side) {
+    const int64_t r0 = side ? Rq : 0, rows = side ? Rd : Rq;
+    const float* x = o.x + (size_t)r0 * E;
+    const float* h1 = o.h1 + (size_t)r0 * H;
+    const float* dz2 = o.dz2 + (size_t)r0 * O;
+    float* dh = dh1 + (size_t)r0 * H;
+    // sem layer
+    CAIR_TRY(colsum(dz2, O, rows, O, gp(gsem[side]->b), nullptr, s));
+    CAIR_TRY(gemm_tn(dz2, O, h1, H, 0, 1, gp(gsem[side]->w), H, rows, O, H, s));
+    CAIR_LAUNCH(transpose_kernel, (O * H + 255) / 256, 256, 0, s, sem[side]->w, O, H, o.wst[side], (int64_t)O);
+    CAIR_TRY(gemm_f32(gemm_dense(dz2, O), o.wst[side], nullptr, dh, H, rows, H, O, ACT_NONE, s));
+    CAIR_LAUNCH(tanh_bwd_kernel, 296, 256, 0, s, dh, h1, rows * H);
+    // conv layer (merged 5-token form): bias, W5 gradient, un-merged into conv.weight
+    CAIR_TRY(colsum(dh, H, rows, H, gp(gconv[side]->b), nullptr, s));
+    CAIR_CUDA(cudaMemsetAsync(o.dw5[side], 0, (size_t)H * 5 * E * sizeof(float), s));
+    CAIR_TRY(gemm_tn(dh, H, x, E, 0, 1, o.dw5[side], (int64_t)5 * E, rows, H, 5 * E, s));
+    CAIR_LAUNCH(cdssm_train_unmerge_kernel, (unsigned)(((int64_t)H * 9 * E + 255) / 256), 256, 0, s, o.dw5[side], H, E, gp(gconv[side]->w));
+    if (G.table) {
+      // a window never crosses a sequence end, and the rows of the other side carry the other weights: the 4 rows in front of
+      // this side's first token must read as zero - they do for the queries (zeroed above); for the documents they are the last
+      // 4 query rows, which are never valid windows (t >= Lq - 4), so their dh1 is exactly zero
+      CAIR_LAUNCH(cdssm_train_reorder_kernel, (unsigned)(((int64_t)E * 5 * H + 255) / 256), 256, 0, s, o.w5[side], H, E, o.w5r[side]);
+      CAIR_TRY(gemm_f32(gemm_dense(dh - (size_t)4 * H, H), o.w5r[side], nullptr, o.dx + (size_t)r0 * E, E, rows, E, 5 * H, ACT_NONE, s));
+    }
+  }
+  if (G.table) {
+    CAIR_LAUNCH(embed_scatter_kernel, 1184, 256, 0, s, o.dx, q, w->vocab, E, Rq, (int64_t)0, p_drop, seed, gp(G.table));
+    CAIR_LAUNCH(embed_scatter_kernel, 1184, 256, 0, s, o.dx, d, w->vocab, E, Rd, Rq, p_drop, seed, gp(G.table));
+  }
   return CAIR_OK;
 }
 

@@ -86,6 +86,11 @@ PROTOTYPES = {
                                       C.c_size_t, vp]),
     'cair_dssm_train_backward': (i32, [C.POINTER(_abi.DssmWeights), C.POINTER(_abi.DssmWeights), vp, vp, i32, i32, i32, i32,
                                        C.c_float, C.c_uint64, vp, vp, vp, C.c_size_t, vp]),
+    'cair_cdssm_train_workspace_bytes': (i32, [i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_size_t)]),
+    'cair_cdssm_train_forward': (i32, [C.POINTER(_abi.CdssmWeights), vp, vp, i32, i32, i32, i32, C.c_float, C.c_uint64, vp, vp,
+                                       C.c_size_t, vp]),
+    'cair_cdssm_train_backward': (i32, [C.POINTER(_abi.CdssmWeights), C.POINTER(_abi.CdssmWeights), vp, vp, i32, i32, i32, i32,
+                                        C.c_float, C.c_uint64, vp, vp, vp, C.c_size_t, vp]),
     'cair_mnsrf_create': (i32, [C.POINTER(_abi.MnsrfWeights), i32, C.POINTER(vp)]),
     'cair_mnsrf_destroy': (i32, [vp]),
     'cair_mnsrf_workspace_bytes': (i32, [vp, i32, i32, i32, i32, i32, C.POINTER(C.c_size_t)]),

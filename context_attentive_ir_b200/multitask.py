@@ -302,7 +302,7 @@ def _tgt2src_table(module, tgt_dict, src_dict, device, tgt_vocab_size):
 
 
 _NO_TRAINING = ('%s.forward() is the training entry point of the reference (ranking + suggestion losses, '
-                'models/multitask.py:161-223): the libcair training step exists for the stand-alone MatchTensor, DRMM, ESM and DSSM rankers '
+                'models/multitask.py:161-223): the libcair training step exists for the stand-alone MatchTensor, DRMM, ESM, DSSM and CDSSM rankers '
                 'only.  Scoring and suggestion decoding run through encode() / rank_document() / decode().')
 
 

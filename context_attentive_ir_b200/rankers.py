@@ -231,7 +231,7 @@ class _Ranker(_CairModule):
         return scores
 
     def _train_forward(self, batch_queries, query_len, batch_docs, doc_len):
-        raise NotImplementedError('%s: the libcair training step exists for MatchTensor, DRMM, ESM and DSSM only; score under .eval()'
+        raise NotImplementedError('%s: the libcair training step exists for MatchTensor, DRMM, ESM, DSSM and CDSSM only; score under .eval()'
                                   % type(self).__name__)
 
     @staticmethod
@@ -383,7 +383,7 @@ class DSSM(_Ranker):
         d = self._ids(batch_docs, 'batch_docs')
         for name, p in self.named_parameters():
             if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
-                raise RuntimeError('DSSM training needs contiguous fp32 CUDA parameters (%s)' % name)
+                raise RuntimeError('%s training needs contiguous fp32 CUDA parameters (%s)' % (type(self).__name__, name))
         seed = self.__dict__.get('_cair_drop_seed')   # tests pin the mask; otherwise drawn from torch's host generator
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
@@ -403,12 +403,16 @@ class _DssmTrainFn(torch.autograd.Function):
         _, N, Ld = d.shape
         a = module.args
         live = dict(zip(names, params))
-        w = _abi.PACKERS['dssm'](module._cfg(), lambda k: C.cast(live[k].data_ptr(), _abi.f32p))
+        kind = module.MODEL   # 'dssm' or 'cdssm': same call shapes, cair_<kind>_train_*
+        w = _abi.PACKERS[kind](module._cfg(), lambda k: C.cast(live[k].data_ptr(), _abi.f32p))
         nbytes = C.c_size_t()
-        lib.check(L.cair_dssm_train_workspace_bytes(a.emsize, a.nhid, a.nout, B, N, C.byref(nbytes)))
+        if kind == 'dssm':
+            lib.check(L.cair_dssm_train_workspace_bytes(a.emsize, a.nhid, a.nout, B, N, C.byref(nbytes)))
+        else:
+            lib.check(L.cair_cdssm_train_workspace_bytes(a.emsize, a.nhid, a.nout, B, N, Lq, Ld, C.byref(nbytes)))
         ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
         scores = torch.empty(B, N, dtype=torch.float32, device=dev)
-        lib.check(L.cair_dssm_train_forward(C.byref(w), q.data_ptr(), d.data_ptr(), B, N, Lq, Ld, p_drop, seed, scores.data_ptr(),
+        lib.check(getattr(L, 'cair_%s_train_forward' % kind)(C.byref(w), q.data_ptr(), d.data_ptr(), B, N, Lq, Ld, p_drop, seed, scores.data_ptr(),
                                             ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
         ctx.module, ctx.names, ctx.args = module, names, (q, d, p_drop, seed, ws, scores, params)
         ctx.shapes = [(p.shape, p.requires_grad) for p in params]
@@ -425,10 +429,11 @@ class _DssmTrainFn(torch.autograd.Function):
         grads = {}
         for name, (shape, req) in zip(names, ctx.shapes):
             grads[name] = None if (name == _abi.TABLE_KEY and not req) else torch.zeros(shape, dtype=torch.float32, device=dev)
-        w = _abi.PACKERS['dssm'](module._cfg(), lambda k: C.cast(live[k].data_ptr(), _abi.f32p))
-        gw = _abi.PACKERS['dssm'](module._cfg(), lambda k: C.cast(grads[k].data_ptr() if grads[k] is not None else None, _abi.f32p))
+        kind = module.MODEL
+        w = _abi.PACKERS[kind](module._cfg(), lambda k: C.cast(live[k].data_ptr(), _abi.f32p))
+        gw = _abi.PACKERS[kind](module._cfg(), lambda k: C.cast(grads[k].data_ptr() if grads[k] is not None else None, _abi.f32p))
         dscores = dscores.contiguous().float()
-        lib.check(lib.load().cair_dssm_train_backward(C.byref(w), C.byref(gw), q.data_ptr(), d.data_ptr(), B, N, Lq, Ld, p_drop, seed,
+        lib.check(getattr(lib.load(), 'cair_%s_train_backward' % kind)(C.byref(w), C.byref(gw), q.data_ptr(), d.data_ptr(), B, N, Lq, Ld, p_drop, seed,
                                                       scores.data_ptr(), dscores.data_ptr(), ws.data_ptr(), ws.numel(),
                                                       torch.cuda.current_stream(dev).cuda_stream))
         return (None,) * 6 + tuple(grads[n] if req else None for n, (_, req) in zip(names, ctx.shapes))
@@ -455,6 +460,8 @@ class CDSSM(_Ranker):
 
     def _create(self, w, device, out):
         return lib.load().cair_cdssm_create(w, device, out)
+
+    _train_forward = DSSM._train_forward   # same call shape: cair_cdssm_train_forward / cair_cdssm_train_backward
 
 
 class ARCI(_Ranker):

@@ -509,6 +509,19 @@ CAIR_API int32_t cair_dssm_train_backward(const cair_dssm_weights* w, const cair
                                  int32_t B, int32_t N, int32_t Lq, int32_t Ld, float p_drop, uint64_t seed, const float* scores,
                                  const float* dscores, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Training step of CDSSM (neuroir/rankers/cdssm.py:42-77 under Ranker.update).  As cair_dssm_train_*: stateless, live parameter
+ * pointers in `w`, gradients ACCUMULATED into zeroed buffers laid out as a cair_cdssm_weights (conv weights in the reference's
+ * Conv1d layout [nhid, 3E, 3]; table may be NULL), the emb_drop mask of cair_dropout_mask.  The interleave + Conv1d pair runs
+ * as one linear map over 5-token windows, every layer a dense GEMM forward and backward; Lq, Ld >= 5. */
+CAIR_API int32_t cair_cdssm_train_workspace_bytes(int32_t emsize, int32_t nhid, int32_t nout, int32_t B, int32_t N, int32_t Lq,
+                                         int32_t Ld, size_t* bytes);
+CAIR_API int32_t cair_cdssm_train_forward(const cair_cdssm_weights* w, const int64_t* q, const int64_t* d, int32_t B, int32_t N,
+                                 int32_t Lq, int32_t Ld, float p_drop, uint64_t seed, float* scores, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+CAIR_API int32_t cair_cdssm_train_backward(const cair_cdssm_weights* w, const cair_cdssm_weights* grads, const int64_t* q,
+                                  const int64_t* d, int32_t B, int32_t N, int32_t Lq, int32_t Ld, float p_drop, uint64_t seed,
+                                  const float* scores, const float* dscores, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- MNSRF ranking path ---------------------------------------------------
  * Replaces MNSRF.encode + MNSRF.rank_document (neuroir/multitask/mnsrf.py:61-162) as Multitask.predict calls them
  * (neuroir/models/multitask.py:270-276).  Weights are copied into the handle: table = embedder.word_embeddings...weight

@@ -343,14 +343,15 @@ def gen_esm_train(name, seed, B, N, Lq, Ld, E, V, steps=3, lr=10.0, clip=5.0, **
     _save(name, cfg, batch, net, outs)
 
 
-def gen_dssm_train(name, seed, B, N, Lq, Ld, E, V, nhid, nout, p_drop=0.0, drop_seed=0, steps=3, lr=1.0, clip=5.0, **kw):
+def gen_dssm_train(name, seed, B, N, Lq, Ld, E, V, nhid, nout, p_drop=0.0, drop_seed=0, steps=3, lr=1.0, clip=5.0, conv=False, **kw):
     """DSSM under the statement order of Ranker.update (models/ranker.py:192-230): gradients of one train-mode forward / backward
     of the unmodified reference and a 3-step SGD curve; emb_drop replaced by the oracle mask (query token rows, then documents)."""
     from neuroir.rankers.dssm import DSSM
+    from neuroir.rankers.cdssm import CDSSM
     from dropout_oracle import drop_scale
     torch.manual_seed(1013)
-    cfg = dict(model='dssm', emsize=E, src_vocab_size=V, dropout_emb=p_drop, nhid=nhid, nout=nout)
-    net = DSSM(_ns(**{k: v for k, v in cfg.items() if k != 'model'})).train()
+    cfg = dict(model='cdssm' if conv else 'dssm', emsize=E, src_vocab_size=V, dropout_emb=p_drop, nhid=nhid, nout=nout)
+    net = (CDSSM if conv else DSSM)(_ns(**{k: v for k, v in cfg.items() if k != 'model'})).train()
     batch = synth.ranker_batch(seed, B, N, Lq, Ld, V, **kw)
     t = _t(batch)
     mask = torch.from_numpy(drop_scale(drop_seed, (B * Lq + B * N * Ld) * E, p_drop))
@@ -599,6 +600,9 @@ def main():
     gen_dssm_train('dssm_train_tiny', 39, B=3, N=4, Lq=6, Ld=19, E=24, V=120, nhid=16, nout=8)
     gen_dssm_train('dssm_train_drop', 40, B=4, N=3, Lq=12, Ld=60, E=64, V=300, nhid=48, nout=32, p_drop=0.2, drop_seed=977,
                    bos_eos=True, overlap=0.1)
+    gen_dssm_train('cdssm_train_tiny', 42, B=3, N=4, Lq=7, Ld=21, E=24, V=120, nhid=16, nout=8, conv=True)
+    gen_dssm_train('cdssm_train_drop', 43, B=4, N=3, Lq=12, Ld=60, E=64, V=300, nhid=48, nout=32, p_drop=0.2, drop_seed=1977,
+                   bos_eos=True, overlap=0.1, conv=True)
     gen_drmm_train('drmm_train_tiny', 33, B=3, N=4, Lq=8, Ld=30, E=32, V=200, disjoint=True)
     gen_drmm_train('drmm_train_drop', 34, B=4, N=3, Lq=12, Ld=60, E=64, V=300, p_drop=0.2, drop_seed=4242, disjoint=True)
     # DRMM: strict (disjoint ids) and overlapping (bin-edge cells excluded by the test using out/cos)
