@@ -233,16 +233,19 @@ extern int g_gemm_impl;  // 1 (default): tcgen05 GEMM where usable, 0: fp32 CUDA
 int32_t gemm_tc_pack(Owned& own, const float* w, int N, int K, GemmTcW* out, cudaStream_t s);
 int32_t gemm_tc_repack(const float* w, const GemmTcW& tw, cudaStream_t s);
 bool gemm_tc_usable(const GemmA& a, int K);
+// aimg_scratch (optional, gemm_tc_aimg_bytes(M, K) bytes, 128-byte aligned): when the weights span several column tiles the A
+// rows are gathered / converted ONCE into this operand image and the GEMM streams it with bulk copies
+size_t gemm_tc_aimg_bytes(int64_t M, int K);
 int32_t gemm_tc(const GemmA& a, const GemmTcW& w, const float* bias, float* c, int64_t ldc, int64_t M, Act act,
-                cudaStream_t s);
+                cudaStream_t s, uint8_t* aimg_scratch = nullptr);
 // out[r] = dot_w . act(A[r] W^T + bias) + dot_b with the [M, N] product kept in TMEM (attention-MLP scores)
 bool gemm_tc_rowdot_usable(const GemmA& a, const GemmTcW& w, int64_t M);
 int32_t gemm_tc_rowdot(const GemmA& a, const GemmTcW& w, const float* bias, Act act, const float* dot_w, const float* dot_b,
                        float* out, int64_t M, cudaStream_t s);
 // tensor-core GEMM when a packed image exists and the A provider is 128-bit loadable, else the fp32 kernel
 inline int32_t gemm_auto(const GemmA& a, const float* w, const GemmTcW& tw, const float* bias, float* c, int64_t ldc,
-                         int64_t M, int N, int K, Act act, cudaStream_t s) {
-  if (tw.img && M >= 128 && gemm_tc_usable(a, K)) return gemm_tc(a, tw, bias, c, ldc, M, act, s);
+                         int64_t M, int N, int K, Act act, cudaStream_t s, uint8_t* aimg_scratch = nullptr) {
+  if (tw.img && M >= 128 && gemm_tc_usable(a, K)) return gemm_tc(a, tw, bias, c, ldc, M, act, s, aimg_scratch);
   return gemm_f32(a, w, bias, c, ldc, M, N, K, act, s);
 }
 

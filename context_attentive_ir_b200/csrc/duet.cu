@@ -195,6 +195,13 @@ int32_t duet_forward(const DuetState& st, const int64_t* q, const int64_t* d, in
   float* pooled = ws.take<float>((nf & 3) ? 0 : (size_t)pc * Tp * nf);
   float* m1d = ws.take<float>((size_t)pc * nf);
   float* m2d = ws.take<float>((size_t)pc * nf);
+  // A operand image of the pooled-row GEMM, whose weights span two column tiles (nf = 300): its rows are converted once instead
+  // of once per column tile.  (conv_d1 keeps the in-kernel gather: the image of its 3-token windows would be three times the rows.)
+  uint8_t* aimg = nullptr;
+  if (st.cd2_tc.img && st.cd2_tc.nct >= 2) {
+    aimg = ws.take<uint8_t>(gemm_tc_aimg_bytes(pc * Tp, nf) + 128);
+    aimg = reinterpret_cast<uint8_t*>(((uintptr_t)aimg + 127) & ~(uintptr_t)127);
+  }
   if (dry || pc <= 0) return CAIR_OK;
   if (!ws.ok()) return fail(CAIR_ERR_WORKSPACE, "duet: workspace too small");
   // local model
@@ -231,7 +238,7 @@ int32_t duet_forward(const DuetState& st, const int64_t* q, const int64_t* d, in
     const int64_t total = (int64_t)pc * Tp * (nf / 4);
     CAIR_LAUNCH(timepool4_kernel, (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16), 256, 0, s,
                 reinterpret_cast<const float4*>(cdv), Td, Tp, st.pool, nf / 4, total, reinterpret_cast<float4*>(pooled));
-    CAIR_TRY(gemm_auto(gemm_dense(pooled, nf), st.cd2_w, st.cd2_tc, st.cd2_b, rd, nf, pc * Tp, nf, nf, ACT_TANH, s));
+    CAIR_TRY(gemm_auto(gemm_dense(pooled, nf), st.cd2_w, st.cd2_tc, st.cd2_b, rd, nf, pc * Tp, nf, nf, ACT_TANH, s, aimg));
   } else {
     CAIR_TRY(gemm_auto(gemm_pooled(cdv, nf, st.pool, Td, Tp), st.cd2_w, st.cd2_tc, st.cd2_b, rd, nf, pc * Tp, nf, nf,
                        ACT_TANH, s));

@@ -293,6 +293,37 @@ __global__ void __launch_bounds__(GT_THREADS, 1)
 // time): the loader warps run ONE software pipeline over the flattened (tile, K chunk) sequence, the accumulator is double
 // buffered in TMEM, and four dedicated warps drain accumulator k while the MMAs of tile k+1 run.
 constexpr int G2_EWARPS = 4;
+// A operand image for weights with several column tiles (N > 256, or N = 300 cut in two): the persistent kernel would gather and
+// convert the same A rows once per column tile; instead one pass writes every (row tile, K chunk) stage in the exact shared-memory
+// layout (hi | lo images with the padded planes), and the GEMM's loader warps become plain cp.async.bulk producers.
+size_t gemm_tc_aimg_bytes(int64_t M, int K) {
+  return (size_t)((M + GT_BM - 1) / GT_BM) * (size_t)((K + GT_BK - 1) / GT_BK) * 2 * GT_AIMG;
+}
+__global__ void __launch_bounds__(256) gemm_tc_aimg_kernel(GemmA a, int64_t M, int K, int nkc, uint8_t* __restrict__ img) {
+  const int kc = blockIdx.x, tid = threadIdx.x;
+  const int64_t mt = blockIdx.y;
+  const int row = tid >> 1, half = tid & 1;
+  const int64_t r = mt * GT_BM + row;
+  uint8_t* blk = img + ((size_t)mt * nkc + kc) * 2 * GT_AIMG;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {   // 16-byte unit u of this thread = K elements [8 (4 half + u), +8) of the chunk = plane 4 half + u
+    const int pl = 4 * half + u;
+    const int kk = kc * GT_BK + 8 * pl;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (r < M && kk < K) v0 = gemm_a_load4(a, r, kk);
+    if (r < M && kk + 4 < K) v1 = gemm_a_load4(a, r, kk + 4);
+    uint32_t h0, l0, h1, l1, h2, l2, h3, l3;
+    split_bf16x2(v0.x, v0.y, h0, l0);
+    split_bf16x2(v0.z, v0.w, h1, l1);
+    split_bf16x2(v1.x, v1.y, h2, l2);
+    split_bf16x2(v1.z, v1.w, h3, l3);
+    const size_t off = (size_t)pl * GT_APLANE + (size_t)row * 16;
+    *reinterpret_cast<uint4*>(blk + off) = make_uint4(h0, h1, h2, h3);
+    *reinterpret_cast<uint4*>(blk + GT_AIMG + off) = make_uint4(l0, l1, l2, l3);
+  }
+  // the 16 padding bytes at the end of every plane are never read by the MMA (rows 0..127 only)
+}
+
 constexpr int G2_THREADS = (GT_LWARPS + G2_EWARPS + 2) * 32;   // 8 loaders, 4 epilogue, W producer, MMA issuer
 constexpr int G2_ESTAGE = 32 * 33;                               // floats per epilogue warp
 
@@ -300,7 +331,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
     gemm_tc2_kernel(GemmA a, const uint8_t* __restrict__ wimg, const float* __restrict__ bias, float* __restrict__ c,
                     int64_t ldc, int64_t M, int N, int K, int NT, int nkc, int nct, int act, uint32_t tcols1, int nst,
                     int ntiles, int dbg, const float* __restrict__ dot_w, const float* __restrict__ dot_b,
-                    float* __restrict__ dot_out) {
+                    float* __restrict__ dot_out, const uint8_t* __restrict__ aimg) {
   extern __shared__ __align__(128) uint8_t smraw[];
   __shared__ uint64_t a_full[GT_MAXSTAGES], w_full[GT_MAXSTAGES], empty[GT_MAXSTAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
@@ -458,6 +489,23 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
       __syncwarp();
       if (lane == 0) gt_arrive(&acc_empty[buf]);
     }
+  } else if (aimg) {
+    // ---- A producers: the stages were written by gemm_tc_aimg_kernel; each loader warp bulk-copies its eighth of a stage ----
+    if (lane == 0) {
+      constexpr uint32_t PART = 2 * GT_AIMG / GT_LWARPS;
+      static_assert(PART % 16 == 0 && PART * GT_LWARPS == 2 * GT_AIMG, "stage must split into 16-byte multiples");
+      int g = 0;
+      for (int kt = 0; kt < my_tiles; ++kt) {
+        const int t = (int)blockIdx.x + kt * (int)gridDim.x;
+        const uint8_t* src = aimg + (size_t)(t / nct) * nkc * 2 * GT_AIMG + (size_t)warp * PART;
+        for (int kc = 0; kc < nkc; ++kc, ++g) {
+          const int s = g % nst;
+          mbar_wait_relaxed(&empty[s], ((g / nst) & 1) ^ 1);
+          mbar_arrive_expect_tx(&a_full[s], PART);
+          bulk_g2s(a_ring + (size_t)s * 2 * GT_AIMG + (size_t)warp * PART, src + (size_t)kc * 2 * GT_AIMG, PART, &a_full[s]);
+        }
+      }
+    }
   } else {
     // ---- A loaders: one software pipeline over the flattened (tile, chunk) sequence ----
     // ids of chunk g+2 requested, rows of chunk g+1 loaded, chunk g converted and written (see the kernel above for the
@@ -607,7 +655,8 @@ bool gemm_tc_rowdot_usable(const GemmA& a, const GemmTcW& w, int64_t M) {
   return w.img && w.nct == 1 && M >= 128 && gemm_tc_usable(a, w.K) && gemm_tc2_shape_ok(a, M);
 }
 static int32_t gemm_tc2_launch(const GemmA& a, const GemmTcW& w, const float* bias, float* c, int64_t ldc, int64_t M, Act act,
-                               const float* dot_w, const float* dot_b, float* dot_out, cudaStream_t s, bool* done) {
+                               const float* dot_w, const float* dot_b, float* dot_out, cudaStream_t s, bool* done,
+                               uint8_t* aimg_scratch = nullptr) {
   *done = false;
   const size_t stage_bytes = (size_t)2 * GT_AIMG + (size_t)2 * (GT_BK / 8) * w.NT * 16;
   const size_t ebytes = (size_t)G2_EWARPS * G2_ESTAGE * sizeof(float);
@@ -621,8 +670,15 @@ static int32_t gemm_tc2_launch(const GemmA& a, const GemmTcW& w, const float* bi
   const size_t smem = (size_t)nst * stage_bytes + ebytes;
   CAIR_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)(ntiles < kSMs ? ntiles : kSMs);
+  const uint8_t* aimg = nullptr;
+  // several column tiles share the A rows: convert them once - unless the provider is a window of several tokens, whose image
+  // would be `win` times the size of the rows it is made of (DUET conv_d1 at N = 500: 11.5 ms with the image, 9.1 ms without)
+  if (aimg_scratch && w.nct >= 2 && !((a.table || a.dwin) && a.win > 1) && !(g_gemm_dbg & 8)) {
+    CAIR_LAUNCH(gemm_tc_aimg_kernel, dim3((unsigned)w.nkc, (unsigned)((M + GT_BM - 1) / GT_BM)), 256, 0, s, a, M, w.K, w.nkc, aimg_scratch);
+    aimg = aimg_scratch;
+  }
   CAIR_LAUNCH(gemm_tc2_kernel, grid, G2_THREADS, smem, s, a, w.img, bias, c, ldc, M, w.N, w.K, w.NT, w.nkc, w.nct, (int)act, tcols1, nst,
-              (int)ntiles, g_gemm_dbg, dot_w, dot_b, dot_out);
+              (int)ntiles, g_gemm_dbg, dot_w, dot_b, dot_out, aimg);
   *done = true;
   return CAIR_OK;
 }
@@ -635,12 +691,12 @@ int32_t gemm_tc_rowdot(const GemmA& a, const GemmTcW& w, const float* bias, Act 
 }
 
 int32_t gemm_tc(const GemmA& a, const GemmTcW& w, const float* bias, float* c, int64_t ldc, int64_t M, Act act,
-                cudaStream_t s) {
+                cudaStream_t s, uint8_t* aimg_scratch) {
   if (M <= 0) return CAIR_OK;
   if ((a.table || a.dwin) && w.K != a.win * a.E) return fail(CAIR_ERR_BAD_ARG, "gemm_tc: K != win*E");
   if (gemm_tc2_shape_ok(a, M)) {
     bool done = false;
-    CAIR_TRY(gemm_tc2_launch(a, w, bias, c, ldc, M, act, nullptr, nullptr, nullptr, s, &done));
+    CAIR_TRY(gemm_tc2_launch(a, w, bias, c, ldc, M, act, nullptr, nullptr, nullptr, s, &done, aimg_scratch));
     if (done) return CAIR_OK;
   }
   const size_t stage_bytes = (size_t)2 * GT_AIMG + (size_t)2 * (GT_BK / 8) * w.NT * 16;

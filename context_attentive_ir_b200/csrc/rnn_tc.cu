@@ -773,8 +773,14 @@ RnnTcPlan rnn_tc_plan(const RnnTcPack& p, int n, int min_spc) {
   return pl;
 }
 
+// pre-gates [n*L, dirs*4h] and, when the pre-gate weights span several column tiles, the A operand image of the pre-gate GEMM
+// (the embedding rows gathered / converted once instead of once per column tile)
+static bool rt_pre_uses_aimg(const RnnTcPack& p) { return !p.fused && p.wp_tc.img && p.wp_tc.nct >= 2; }
 size_t rnn_tc_workspace_floats(const RnnTcPack& p, int64_t n, int L) {
-  return p.fused ? 0 : (size_t)n * L * p.dirs * 4 * p.h;
+  if (p.fused) return 0;
+  size_t f = (size_t)n * L * p.dirs * 4 * p.h;
+  if (rt_pre_uses_aimg(p)) f += gemm_tc_aimg_bytes(n * L, p.in) / sizeof(float) + 64;
+  return f;
 }
 
 template <bool GRU, bool FUSED, int NB>
@@ -812,7 +818,9 @@ int32_t rnn_tc_run(const RnnTcPack& p, const GemmA& x, const int64_t* len, int n
   if (!p.fused) {
     if (!ws_pre) return fail(CAIR_ERR_WORKSPACE, "rnn_tc: pre-gate workspace missing");
     const int PW = p.dirs * 4 * p.h;
-    CAIR_TRY(gemm_auto(x, p.wp, p.wp_tc, p.bp, ws_pre, PW, (int64_t)n * L, PW, p.in, ACT_NONE, s));
+    uint8_t* aimg = nullptr;
+    if (rt_pre_uses_aimg(p)) aimg = reinterpret_cast<uint8_t*>(((uintptr_t)(ws_pre + (size_t)n * L * PW) + 127) & ~(uintptr_t)127);
+    CAIR_TRY(gemm_auto(x, p.wp, p.wp_tc, p.bp, ws_pre, PW, (int64_t)n * L, PW, p.in, ACT_NONE, s, aimg));
   }
   if (rec_name) prof_mark(rec_name, s);
   RnnTcArgs a;
