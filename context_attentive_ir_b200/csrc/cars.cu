@@ -401,8 +401,8 @@ __global__ void fill_len_kernel(int64_t* len, int n, int64_t v) {
 }
 
 static int32_t encode_pool(const CarsState& st, const LstmPack& lp, const RnnTcPack& rt, const AttnPack& ap, const int64_t* ids,
-                           const int64_t* len, int64_t n, int L, float* pre, float* enc, float* hid, float* pooled,
-                           int* err, cudaStream_t s, const char* rec_name, bool marks = true) {
+                           const int64_t* len, int64_t n, int L, float* pre, size_t pre_floats, float* enc, float* hid,
+                           float* pooled, int* err, cudaStream_t s, const char* rec_name, bool marks = true) {
   const int H = ap.H;
   if (g_rnn_impl >= RNN_IMPL_AUTO && rt.wimg)   // tcgen05 recurrence (pre-gates from the gathered tcgen05 GEMM)
     CAIR_TRY(rnn_tc_run(rt, gemm_gather(st.table, st.V, st.E, ids, 1, 1, 1, err), len, (int)n, L, enc, nullptr, nullptr, pre,
@@ -413,7 +413,11 @@ static int32_t encode_pool(const CarsState& st, const LstmPack& lp, const RnnTcP
   if (marks) prof_mark("attention_pool", s);
   if (gemm_tc_rowdot_usable(gemm_dense(enc, H), ap.w0_tc, n * L)) {
     // tanh(l0(enc)) . w3 + b3 inside the GEMM epilogue: the [n*L, H] hidden tensor is never written (hid holds the scores)
-    CAIR_TRY(gemm_tc_rowdot(gemm_dense(enc, H), ap.w0_tc, ap.b0, ACT_TANH, ap.w3, ap.b3, hid, n * L, s));
+    // the pre-gate workspace is free once the recurrence has run: it holds the A operand image of this GEMM (the memory bank
+    // split into bf16 hi / lo once by gemm_tc_aimg_kernel, then streamed by bulk copies instead of the register loader)
+    uint8_t* aimg = reinterpret_cast<uint8_t*>(((uintptr_t)pre + 127) & ~(uintptr_t)127);
+    if (!pre || pre_floats * sizeof(float) < gemm_tc_aimg_bytes(n * L, H) + 128) aimg = nullptr;
+    CAIR_TRY(gemm_tc_rowdot(gemm_dense(enc, H), ap.w0_tc, ap.b0, ACT_TANH, ap.w3, ap.b3, hid, n * L, s, aimg));
     CAIR_LAUNCH(attn_pool_kernel, (unsigned)n, 256, (size_t)L * sizeof(float), s, enc, nullptr, len, L, H, ap.w3, ap.b3, pooled, hid);
     return CAIR_OK;
   }
@@ -430,11 +434,18 @@ int32_t cars_forward(const CarsState& st, const CarsIO& io, int B, int S, int N,
   const int64_t nrows = (int64_t)sc * S, ndocs = nrows * N;
   const int64_t r0 = (int64_t)sb * S;
   // workspace
-  float* pre_q = ws.take<float>(lstm_workspace_floats(st.enc_q, nrows, Lq));
+  // pre-gate workspaces: the larger of what the two recurrence engines ask for (the tcgen05 path adds the A operand image of its
+  // pre-gate GEMM, rnn_tc_workspace_floats)
+  auto pre_floats = [](const LstmPack& lp, const RnnTcPack& rt, int64_t n, int L) {
+    const size_t a = lstm_workspace_floats(lp, n, L), b = rt.wimg ? rnn_tc_workspace_floats(rt, n, L) : 0;
+    return a > b ? a : b;
+  };
+  const size_t pre_q_floats = pre_floats(st.enc_q, st.rt_q, nrows, Lq), pre_d_floats = pre_floats(st.enc_d, st.rt_d, ndocs, Ld);
+  float* pre_q = ws.take<float>(pre_q_floats);
   float* enc_q = ws.take<float>((size_t)nrows * Lq * Hq);
   float* hid_q = ws.take<float>((size_t)nrows * Lq * Hq);
   float* pq = ws.take<float>((size_t)nrows * Hq);
-  float* pre_d = ws.take<float>(lstm_workspace_floats(st.enc_d, ndocs, Ld));
+  float* pre_d = ws.take<float>(pre_d_floats);
   float* enc_d = ws.take<float>((size_t)ndocs * Ld * Hd);
   float* hid_d = ws.take<float>((size_t)ndocs * Ld * Hd);
   float* pd = ws.take<float>((size_t)ndocs * Hd);
@@ -470,14 +481,14 @@ int32_t cars_forward(const CarsState& st, const CarsIO& io, int B, int S, int N,
   } else {
     prof_mark("query_pregates", s);
   }
-  CAIR_TRY(encode_pool(st, st.enc_q, st.rt_q, st.q_attn, io.q + r0 * Lq, io.qlen + r0, nrows, Lq, pre_q, enc_q, hid_q, pq, err, sq,
+  CAIR_TRY(encode_pool(st, st.enc_q, st.rt_q, st.q_attn, io.q + r0 * Lq, io.qlen + r0, nrows, Lq, pre_q, pre_q_floats, enc_q, hid_q, pq, err, sq,
                        st.side ? nullptr : "query_recurrence", !st.side));
   // 3a. session LSTM over the pooled queries (zero initial state, S steps)
   CAIR_TRY(lstm_run(st.sess_q, gemm_dense(pq, Hq), slen, sc, S, Qs, nullptr, nullptr, pre_sq, err, sq, st.side ? nullptr : "lstm_recurrence",
                     io.sess_c ? Qc : nullptr));
   if (st.side) CAIR_CUDA(cudaEventRecord(st.ev_join, st.side));
   prof_mark("doc_pregates", s);
-  CAIR_TRY(encode_pool(st, st.enc_d, st.rt_d, st.d_attn, io.d + r0 * N * Ld, io.dlen + r0 * N, ndocs, Ld, pre_d, enc_d, hid_d, pd, err, s, "doc_recurrence"));
+  CAIR_TRY(encode_pool(st, st.enc_d, st.rt_d, st.d_attn, io.d + r0 * N * Ld, io.dlen + r0 * N, ndocs, Ld, pre_d, pre_d_floats, enc_d, hid_d, pd, err, s, "doc_recurrence"));
   // 2. click vectors
   prof_mark("clicks", s);
   CAIR_CUDA(cudaMemsetAsync(mwidth, 0, sizeof(int), s));

@@ -241,7 +241,7 @@ int32_t gemm_tc(const GemmA& a, const GemmTcW& w, const float* bias, float* c, i
 // out[r] = dot_w . act(A[r] W^T + bias) + dot_b with the [M, N] product kept in TMEM (attention-MLP scores)
 bool gemm_tc_rowdot_usable(const GemmA& a, const GemmTcW& w, int64_t M);
 int32_t gemm_tc_rowdot(const GemmA& a, const GemmTcW& w, const float* bias, Act act, const float* dot_w, const float* dot_b,
-                       float* out, int64_t M, cudaStream_t s);
+                       float* out, int64_t M, cudaStream_t s, uint8_t* aimg_scratch = nullptr);
 // tensor-core GEMM when a packed image exists and the A provider is 128-bit loadable, else the fp32 kernel
 inline int32_t gemm_auto(const GemmA& a, const float* w, const GemmTcW& tw, const float* bias, float* c, int64_t ldc,
                          int64_t M, int N, int K, Act act, cudaStream_t s, uint8_t* aimg_scratch = nullptr) {

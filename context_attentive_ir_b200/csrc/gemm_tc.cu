@@ -673,7 +673,7 @@ static int32_t gemm_tc2_launch(const GemmA& a, const GemmTcW& w, const float* bi
   const uint8_t* aimg = nullptr;
   // several column tiles share the A rows: convert them once - unless the provider is a window of several tokens, whose image
   // would be `win` times the size of the rows it is made of (DUET conv_d1 at N = 500: 11.5 ms with the image, 9.1 ms without)
-  if (aimg_scratch && w.nct >= 2 && !((a.table || a.dwin) && a.win > 1) && !(g_gemm_dbg & 8)) {
+  if (aimg_scratch && (w.nct >= 2 || dot_out) && !((a.table || a.dwin) && a.win > 1) && !(g_gemm_dbg & 8)) {
     CAIR_LAUNCH(gemm_tc_aimg_kernel, dim3((unsigned)w.nkc, (unsigned)((M + GT_BM - 1) / GT_BM)), 256, 0, s, a, M, w.K, w.nkc, aimg_scratch);
     aimg = aimg_scratch;
   }
@@ -683,10 +683,10 @@ static int32_t gemm_tc2_launch(const GemmA& a, const GemmTcW& w, const float* bi
   return CAIR_OK;
 }
 int32_t gemm_tc_rowdot(const GemmA& a, const GemmTcW& w, const float* bias, Act act, const float* dot_w, const float* dot_b,
-                       float* out, int64_t M, cudaStream_t s) {
+                       float* out, int64_t M, cudaStream_t s, uint8_t* aimg_scratch) {
   if ((a.table || a.dwin) && w.K != a.win * a.E) return fail(CAIR_ERR_BAD_ARG, "gemm_tc: K != win*E");
   bool done = false;
-  CAIR_TRY(gemm_tc2_launch(a, w, bias, nullptr, 0, M, act, dot_w, dot_b, out, s, &done));
+  CAIR_TRY(gemm_tc2_launch(a, w, bias, nullptr, 0, M, act, dot_w, dot_b, out, s, &done, aimg_scratch));
   return done ? CAIR_OK : fail(CAIR_ERR_UNSUPPORTED, "gemm_tc_rowdot: shape not supported (check gemm_tc_rowdot_usable)");
 }
 
